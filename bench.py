@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the per-RoI captioning hot path (contract in the task prompt, section 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload roi_features]
+
+One "step" = one pass of the hot path over one batch of synthetic input.  Workloads:
+
+  roi_features  BASELINE.json configs[1]: 8 images x 1000 RoIs (FPN P2-P5 of a 1024x1024 image,
+                256 ch, fp32) -> PyramidROIAlign -> [8000, 7, 7, 256].  With N GPUs every rank
+                owns its own 8 images (weak scaling, images sharded, no collective).
+
+`value` is measured with inputs resident in HBM; `e2e` goes through the host-buffer C-ABI entry
+point with pinned host buffers (H2D of the pyramid and D2H of the features inside the timed
+region).  `--impl reference` times the CPU restatement of the reference (oracle/c, all host
+threads) on a bounded sample of the same workload -- the reference itself is TensorFlow-1.x
+Python and cannot run here.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+POOL = (7, 7)
+IMAGE_SHAPE = (1024, 1024, 3)
+CHANNELS = 256
+IMAGES_PER_GPU = 8
+ROIS_PER_IMAGE = 1000
+SEED_CFG2 = 1002           # 1000 + config index
+
+
+# --------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def tap_unique_pixels(boxes, levels, fm_shapes, pool):
+    """T_unique of SURVEY.md section 8(d): distinct (image, level, y, x) pixels touched by any
+    in-range bilinear tap.  `levels` come from the GPU kernel; this is byte accounting for the
+    roofline, not part of the product path."""
+    B, N = boxes.shape[:2]
+    fb = boxes.reshape(-1, 4).astype(np.float32)
+    lv = levels.reshape(-1)
+    img = np.repeat(np.arange(B), N)
+    ph, pw = pool
+    total = 0
+    f32 = np.float32
+    for i in range(4):
+        sel = np.nonzero(lv == i + 2)[0]
+        if sel.size == 0:
+            continue
+        H, W = fm_shapes[i]
+        bx = fb[sel]
+        Hm1, Wm1 = f32(H - 1), f32(W - 1)
+        hs = ((bx[:, 2] - bx[:, 0]) * Hm1) / f32(ph - 1)
+        ws = ((bx[:, 3] - bx[:, 1]) * Wm1) / f32(pw - 1)
+        in_y = ((bx[:, 0] * Hm1)[:, None] + np.arange(ph, dtype=f32)[None] * hs[:, None]).astype(f32)
+        in_x = ((bx[:, 1] * Wm1)[:, None] + np.arange(pw, dtype=f32)[None] * ws[:, None]).astype(f32)
+        y_ok = (in_y >= 0) & (in_y <= Hm1)
+        x_ok = (in_x >= 0) & (in_x <= Wm1)
+        ys = np.stack([np.floor(in_y), np.ceil(in_y)], -1).astype(np.int64)
+        xs = np.stack([np.floor(in_x), np.ceil(in_x)], -1).astype(np.int64)
+        shape = (len(sel), ph, 2, pw, 2)
+        ok = np.broadcast_to(y_ok[:, :, None, None, None] & x_ok[:, None, None, :, None], shape)
+        yy = np.broadcast_to(ys[:, :, :, None, None], shape)
+        xx = np.broadcast_to(xs[:, None, None, :, :], shape)
+        ii = np.broadcast_to(img[sel][:, None, None, None, None], shape)
+        total += np.unique((ii[ok] * H + yy[ok]) * W + xx[ok]).size
+    return int(total)
+
+
+def dist_env():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import image_captioning_b200 as pkg
+    from image_captioning_b200 import synth
+
+    rank, local_rank, world = dist_env()
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = pkg._lib.load()
+    sms, cc = pkg._lib.device_info()
+
+    # ---- synthetic workload (cfg2): every rank owns IMAGES_PER_GPU images ----
+    B, N = IMAGES_PER_GPU, ROIS_PER_IMAGE
+    rng = np.random.default_rng(SEED_CFG2 + 7919 * rank)
+    boxes_np = synth.synth_boxes(rng, B, N, float(IMAGE_SHAPE[0]))
+    gen = torch.Generator(device=dev).manual_seed(SEED_CFG2 + rank)
+    fms = [torch.randn((B, IMAGE_SHAPE[0] >> l, IMAGE_SHAPE[1] >> l, CHANNELS), device=dev,
+                       generator=gen) for l in range(2, 6)]
+    boxes = torch.from_numpy(boxes_np).to(dev)
+    out = torch.empty((B * N, POOL[0], POOL[1], CHANNELS), device=dev)
+    levels = torch.empty((B, N), dtype=torch.int32, device=dev)
+
+    def step():
+        pkg.pyramid_roi_align(boxes, fms, POOL, IMAGE_SHAPE, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    _, levels = pkg.pyramid_roi_align(boxes, fms, POOL, IMAGE_SHAPE, out=out, return_levels=True)
+    torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- device-resident timing: CUDA events on the launching (torch current) stream ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.summary()
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    rois_per_step = B * N * world
+    value = rois_per_step / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (roi_align_kernel), algorithmic bytes ----
+    t_unique = tap_unique_pixels(boxes_np, levels.cpu().numpy(), [tuple(f.shape[1:3]) for f in fms], POOL)
+    alg_bytes = 4 * CHANNELS * (POOL[0] * POOL[1] * B * N + t_unique)
+    k_ms = float(np.mean(kernel_ms))
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peaks()
+    roofline = {"bound": "hbm", "kernel": "roi_align_kernel", "achieved": round(achieved, 1),
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+                "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                "t_unique_pixels": t_unique, "kernel_ms": round(k_ms, 5)}
+    prof = os.path.join(ROOT, "profiles", "roi_align_traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: host buffers through the C-ABI host entry point ----
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h_boxes = torch.from_numpy(boxes_np).pin_memory()
+    h_fms = [f.cpu().pin_memory() for f in fms]
+    h_out = torch.empty((B * N, POOL[0], POOL[1], CHANNELS)).pin_memory()
+    ptrs = (ctypes.c_void_p * 4)(*[f.data_ptr() for f in h_fms])
+    hs = (ctypes.c_int * 4)(*[f.shape[1] for f in h_fms])
+    ws = (ctypes.c_int * 4)(*[f.shape[2] for f in h_fms])
+
+    def e2e_step():
+        pkg._lib.check(lib.dc_pyramid_roi_align_host_f32(
+            ctypes.c_void_p(h_boxes.data_ptr()), ptrs, hs, ws, B, N, CHANNELS, POOL[0], POOL[1],
+            IMAGE_SHAPE[0], IMAGE_SHAPE[1], ctypes.c_void_p(h_out.data_ptr()), None))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    ok = bool(torch.equal(h_out, out.cpu()))
+    h2d = int(sum(f.numel() * 4 for f in h_fms) + h_boxes.numel() * 4)
+    d2h = int(h_out.numel() * 4)
+    e2e = {"value": round(rois_per_step / e2e_s, 1), "unit": "RoI/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps, "matches_device_result": ok,
+           "api": "dc_pyramid_roi_align_host_f32 (pinned host buffers)"}
+
+    line = {
+        "metric": "roi_features_per_sec", "value": round(value, 1), "unit": "RoI/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2 roi_features: %d images x %d RoIs per GPU, P2-P5 of 1024x1024, "
+                               "256 ch fp32 -> 7x7x256" % (B, N),
+                   "rois_per_step": rois_per_step, "sharding": "images per rank, no collective",
+                   "l2": "inputs larger than L2 (pyramid %d MB, output %d MB per GPU)"
+                         % (sum(f.numel() for f in fms) * 4 // 2 ** 20, out.numel() * 4 // 2 ** 20),
+                   "sm_count": sms, "cc": cc},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps, "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(boxes_np, [f.cpu().numpy() for f in h_fms], budget_s=12.0)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline / reference arm (the ONLY places bench.py touches oracle/)
+# --------------------------------------------------------------------------------------------
+
+def cpu_baseline(boxes_np, fms_np, budget_s):
+    """Times the reference's CPU algorithm (literal form: 4 per-level crop_and_resize calls +
+    re-sort gather, boxes sharded over all host threads) restated in C (oracle/c), on as many
+    whole images of the same workload as fit in ~budget_s seconds."""
+    from tests import _c_oracle
+    n_img = boxes_np.shape[0]
+    N = boxes_np.shape[1]
+    out = np.empty((N, POOL[0], POOL[1], CHANNELS), np.float32)
+    scratch = np.empty_like(out)
+    _c_oracle.pyramid_roi_align(boxes_np[:1], [f[:1] for f in fms_np], POOL, IMAGE_SHAPE, literal=True,
+                                out=out, scratch=scratch)          # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        i = done % n_img
+        _c_oracle.pyramid_roi_align(boxes_np[i:i + 1], [f[i:i + 1] for f in fms_np], POOL, IMAGE_SHAPE,
+                                    literal=True, out=out, scratch=scratch)
+        done += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or done >= 64:
+            break
+    return {"value": round(done * N / el, 1), "unit": "RoI/s", "cores": _c_oracle.num_threads(),
+            "kind": "port", "sample": "%d images x %d RoIs of the same cfg2 workload, literal "
+            "reference form (4x crop_and_resize + re-sort), C/OpenMP restatement" % (done, N),
+            "seconds": round(el, 2)}
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from image_captioning_b200 import synth
+    rng = np.random.default_rng(SEED_CFG2)
+    B, N = 2, ROIS_PER_IMAGE           # bounded sample: 2 images of the cfg2 workload per step
+    boxes_np = synth.synth_boxes(rng, B, N, float(IMAGE_SHAPE[0]))
+    fms = [rng.standard_normal((B, IMAGE_SHAPE[0] >> l, IMAGE_SHAPE[1] >> l, CHANNELS), dtype=np.float32)
+           for l in range(2, 6)]
+    from tests import _c_oracle
+    out = np.empty((B * N, POOL[0], POOL[1], CHANNELS), np.float32)
+    scratch = np.empty_like(out)
+
+    def step():
+        _c_oracle.pyramid_roi_align(boxes_np, fms, POOL, IMAGE_SHAPE, literal=True, out=out, scratch=scratch)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    value = args.steps * B * N / el
+    sample = ("%d images x %d RoIs per step (bounded sample of cfg2), literal reference form, "
+              "C/OpenMP restatement of the TF CPU path" % (B, N))
+    line = {"impl": "reference", "metric": "roi_features_per_sec", "value": round(value, 1),
+            "unit": "RoI/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(el / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2 roi_features (bounded sample: %d images x %d RoIs per step)" % (B, N)},
+            "cpu_baseline": {"value": round(value, 1), "unit": "RoI/s", "cores": _c_oracle.num_threads(),
+                             "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 1), "unit": "RoI/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "note": "the reference is TF-1.x/Keras Python and cannot be installed here; this arm "
+                    "times the C restatement of its CPU algorithm (oracle/c) on all host threads"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="roi_features")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,9 @@
+"""B200-native per-RoI captioning path: PyramidROIAlign -> RoI head -> inject-LSTM decoder.
+
+Host side is Python/PyTorch (device memory, streams, torch.distributed); all arithmetic runs in
+hand-written sm_100a CUDA kernels behind the C ABI of ``include/dcap.h`` (``libdcap.so``).
+The directory is named ``image-captioning_b200``; import it as ``image_captioning_b200``.
+"""
+from . import _lib                                            # noqa: F401
+from .roi_align import PyramidROIAlign, pyramid_roi_align, fpn_levels    # noqa: F401
+from . import synth  # noqa: F401

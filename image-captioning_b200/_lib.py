@@ -1,0 +1,79 @@
+"""ctypes binding of libdcap.so (the C ABI declared in include/dcap.h).
+
+There is NO CPU fallback: if the shared library is missing or a CUDA device is not usable the
+calls raise -- the oracle under ``oracle/`` is test infrastructure and is never imported here.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdcap.so")
+
+_lib = None
+_lock = threading.Lock()
+
+
+class DcapError(RuntimeError):
+    """Error reported by libdcap.so (negative return code + dc_last_error message)."""
+
+    def __init__(self, code, msg):
+        super().__init__("libdcap error %d: %s" % (code, msg))
+        self.code = code
+
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_i32_p = ctypes.POINTER(ctypes.c_int32)
+c_void = ctypes.c_void_p
+
+# name -> (restype, argtypes); kept in one table so tests can check it against include/dcap.h
+SIGNATURES = {
+    "dc_last_error": (ctypes.c_char_p, []),
+    "dc_device_info": (ctypes.c_int, [c_int_p, c_int_p]),
+    "dc_fpn_levels_f32": (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                         c_void, c_void]),
+    "dc_pyramid_roi_align_f32": (ctypes.c_int, [c_void, c_void * 4, ctypes.c_int * 4,
+                                                ctypes.c_int * 4] + [ctypes.c_int] * 7 +
+                                 [c_void, c_void, c_void]),
+    "dc_pyramid_roi_align_bf16out": (ctypes.c_int, [c_void, c_void * 4, ctypes.c_int * 4,
+                                                    ctypes.c_int * 4] + [ctypes.c_int] * 7 +
+                                     [c_void, c_void, c_void]),
+    "dc_pyramid_roi_align_host_f32": (ctypes.c_int, [c_void, c_void * 4, ctypes.c_int * 4,
+                                                     ctypes.c_int * 4] + [ctypes.c_int] * 7 +
+                                      [c_void, c_void]),
+}
+
+
+def load():
+    """Load libdcap.so once; raises if it has not been built (run __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libdcap.so not found at %s -- build it with `python -c 'import __graft_entry__ as "
+                "g; g.build()'` (there is no CPU fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().dc_last_error()
+        raise DcapError(rc, msg.decode("utf-8", "replace") if msg else "")
+
+
+def device_info():
+    lib = load()
+    sms, cc = ctypes.c_int(0), ctypes.c_int(0)
+    check(lib.dc_device_info(ctypes.byref(sms), ctypes.byref(cc)))
+    return sms.value, cc.value

@@ -1,0 +1,151 @@
+"""GPU parity: the sm_100a PyramidROIAlign kernel (through the C ABI) against the CPU oracle.
+Bar: FPN levels bit-exact; features within 1e-5 relative (north_star) -- in fact bit-exact,
+because both sides round every fp32 op individually."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import roi_align as ra
+from image_captioning_b200 import synth
+from tests import _c_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # north_star tolerance for ROIAlign features
+
+
+def _dev(arrs):
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs]
+
+
+def _run(boxes, fms, pool, ishape, dtype=torch.float32):
+    import image_captioning_b200 as pkg
+    tb, *tf = _dev([boxes] + list(fms))
+    out, lv = pkg.pyramid_roi_align(tb, tf, pool, ishape, out_dtype=dtype, return_levels=True)
+    torch.cuda.synchronize()
+    return out, lv.cpu().numpy()
+
+
+def test_golden_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "roi_align_small.npz"))
+    fms = [g["p2"], g["p3"], g["p4"], g["p5"]]
+    out, lv = _run(g["boxes"], fms, (7, 7), tuple(g["image_shape"]))
+    assert np.array_equal(lv, g["levels"])
+    got = out.cpu().numpy()
+    np.testing.assert_allclose(got, g["pooled"][0], rtol=RTOL, atol=1e-6)
+    assert np.array_equal(got.view(np.uint32), g["pooled"][0].view(np.uint32))
+
+
+def test_layer_surface_matches_reference_contract(golden_dir):
+    import image_captioning_b200 as pkg
+    g = np.load(os.path.join(golden_dir, "roi_align_small.npz"))
+    fms = [g["p2"], g["p3"], g["p4"], g["p5"]]
+    layer = pkg.PyramidROIAlign([7, 7], tuple(g["image_shape"]), name="roi_align_classifier")
+    # numpy in -> numpy out through the host-buffer entry point, literal [1, B*N, 7, 7, C]
+    out = layer([g["boxes"]] + fms)
+    assert isinstance(out, np.ndarray) and out.shape == (1, 96, 7, 7, 8)
+    assert np.array_equal(out.view(np.uint32), g["pooled"].view(np.uint32))
+    assert layer.compute_output_shape([g["boxes"].shape] + [f.shape for f in fms]) == (2, 48, 7, 7, 8)
+    # torch CUDA in -> torch CUDA out
+    tout = layer(_dev([g["boxes"]] + fms))
+    assert tout.is_cuda and tuple(tout.shape) == (1, 96, 7, 7, 8)
+    assert np.array_equal(tout.cpu().numpy().view(np.uint32), g["pooled"].view(np.uint32))
+    with pytest.raises(ValueError):
+        layer([g["boxes"][:, :, :3]] + fms)
+    with pytest.raises(ValueError):
+        layer([g["boxes"][:1]] + fms)
+
+
+@pytest.mark.parametrize("seed,B,N,C,pool", [(1001, 1, 100, 256, (7, 7)), (5, 2, 333, 256, (7, 7)),
+                                             (6, 1, 64, 256, (14, 14)), (7, 3, 50, 32, (3, 5)),
+                                             (8, 1, 10, 4, (1, 1))])
+def test_synthetic_vs_c_oracle(seed, B, N, C, pool):
+    """cfg1-shaped case (seed 1001: 1 image, 100 RoIs, 256 ch) and ragged variants."""
+    rng = np.random.default_rng(seed)
+    size = 1024 if C == 256 else 256
+    boxes = synth.synth_boxes(rng, B, N, 1024.0, pad_frac=0.05, straddle_frac=0.05)
+    fms = [rng.standard_normal((B, (size >> l), (size >> l), C), dtype=np.float32) for l in range(2, 6)]
+    want, lv_want = _c_oracle.pyramid_roi_align(boxes, fms, pool, (1024, 1024, 3))
+    out, lv = _run(boxes, fms, pool, (1024, 1024, 3))
+    assert np.array_equal(lv, lv_want)
+    got = out.cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-6)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_edge_boxes():
+    rng = np.random.default_rng(12)
+    fms = [rng.standard_normal((1, 64 >> i, 64 >> i, 16), dtype=np.float32) for i in range(4)]
+    b = np.array([[0, 0, 0, 0], [0.2, 0.6, 0.5, 0.4], [-0.3, -0.3, 0.4, 0.4], [0.5, 0.5, 1.5, 1.5],
+                  [0, 0, 1, 1], [1, 1, 1, 1], [0.25, 0.25, 0.75, 0.75], [0.6, 0.6, 0.4, 0.4],
+                  [np.nan, 0, 0.5, 0.5], [0, 0, np.inf, 0.5]], np.float32)[None]
+    want, lv_want = ra.pyramid_roi_align(b, fms, (7, 7), (1024, 1024, 3))
+    out, lv = _run(b, fms, (7, 7), (1024, 1024, 3))
+    assert np.array_equal(lv, lv_want)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want[0].view(np.uint32))
+    # zero box: every bin equals P2[0,0,0,:]
+    assert torch.equal(out[0].cpu(), torch.from_numpy(fms[0][0, 0, 0]).expand(7, 7, 16))
+
+
+def test_level_boundaries_bit_exact():
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(11)
+    n = 20000
+    ks = rng.integers(-3, 2, n)
+    side = 224.0 * 2.0 ** (ks + 0.5) / 1024.0 * (1 + rng.integers(-3, 4, n) * 2.0 ** -23)
+    asp = np.exp(rng.uniform(-0.5, 0.5, n))
+    b = np.zeros((n, 4), np.float32)
+    b[:, 2] = side * asp
+    b[:, 3] = side / asp
+    lv = pkg.fpn_levels(torch.from_numpy(b).cuda(), (1024, 1024, 3)).cpu().numpy()
+    assert np.array_equal(lv, ra.fpn_level(b, (1024, 1024, 3)))
+
+
+def test_bf16_output_is_rounded_fp32(golden_dir):
+    g = np.load(os.path.join(golden_dir, "roi_align_small.npz"))
+    fms = [g["p2"], g["p3"], g["p4"], g["p5"]]
+    out, _ = _run(g["boxes"], fms, (7, 7), tuple(g["image_shape"]), dtype=torch.bfloat16)
+    want = torch.from_numpy(g["pooled"][0]).to(torch.bfloat16)
+    assert torch.equal(out.cpu(), want)
+
+
+def test_empty_inputs():
+    import image_captioning_b200 as pkg
+    fms = [torch.zeros((2, 8 >> i, 8 >> i, 4), device="cuda") for i in range(4)]
+    out = pkg.pyramid_roi_align(torch.zeros((2, 0, 4), device="cuda"), fms, (7, 7), (1024, 1024, 3))
+    assert tuple(out.shape) == (0, 7, 7, 4)
+
+
+def test_full_size_properties():
+    """BASELINE cfg2 size (8 images x 1000 RoIs, 256 ch): size-independent properties --
+    (1) linearity in the feature maps, (2) a constant map gives the constant wherever the sample
+    is in range and 0 elsewhere, (3) per-image independence (a batch equals its images run alone),
+    (4) a random sample of rows matches the oracle bit for bit."""
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(1002)
+    B, N = 8, 1000
+    boxes = synth.synth_boxes(rng, B, N, 1024.0)
+    tb = torch.from_numpy(boxes).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1002)
+    fa = [torch.randn((B, 1024 >> l, 1024 >> l, 256), device="cuda", generator=g) for l in range(2, 6)]
+    oa, lv = pkg.pyramid_roi_align(tb, fa, (7, 7), (1024, 1024, 3), return_levels=True)
+    assert np.array_equal(lv.cpu().numpy(), ra.fpn_level(boxes, (1024, 1024, 3)))
+    # (4) sampled rows vs oracle (image 3)
+    sel = np.arange(0, N, 37)
+    want, _ = ra.pyramid_roi_align(boxes[3:4, sel], [f[3:4].cpu().numpy() for f in fa], (7, 7),
+                                   (1024, 1024, 3))
+    got = oa.view(B, N, 7, 7, 256)[3, torch.from_numpy(sel).cuda()].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want[0].view(np.uint32))
+    # (3) per-image independence
+    o5 = pkg.pyramid_roi_align(tb[5:6], [f[5:6] for f in fa], (7, 7), (1024, 1024, 3))
+    assert torch.equal(o5, oa.view(B, N, 7, 7, 256)[5])
+    # (2) constant maps
+    fc = [torch.full_like(f, 3.0) for f in fa]
+    oc = pkg.pyramid_roi_align(tb, fc, (7, 7), (1024, 1024, 3))
+    assert bool(((oc == 3.0) | (oc == 0.0)).all())
+    del fc
+    # (1) linearity: align(2*F) == 2*align(F) exactly (power-of-two scaling commutes with rounding)
+    o2 = pkg.pyramid_roi_align(tb, [f * 2 for f in fa], (7, 7), (1024, 1024, 3))
+    assert torch.equal(o2, oa * 2)
