@@ -9,9 +9,10 @@
 //     written once, in its final (image, box) slot, with 128-bit streaming stores -- the
 //     reference's concat + top_k re-sort + gather (an extra read+write of the whole output)
 //     does not exist here;
-//   * RoIs are walked in (image, box) order by a grid sized in multiples of the SM count, so
-//     the CTAs resident at any moment work on the same image: its touched pixels (~60 MB at
-//     the cfg2 box distribution) stay in the 126 MB L2 and every pixel crosses HBM ~once.
+//   * a small first pass (one CTA per image) turns every box into a sampling record and
+//     counting-sorts the image's RoIs by (level, Morton tile of the box centre); the streaming
+//     pass walks that order, so overlapping boxes are processed together and every touched
+//     pixel crosses HBM about once while its re-uses hit the 126 MB L2.
 //
 // Arithmetic is bit-identical to the CPU oracle: every fp32 op is individually rounded
 // (__fmul_rn/__fadd_rn/__fsub_rn are never contracted into FMA) and tf.log is the correctly
@@ -19,24 +20,11 @@
 #include "common.cuh"
 #include <math.h>
 #include <limits.h>
+#include <stdlib.h>
 
 namespace dcap {
 
 constexpr int kMaxPool = 32;
-
-struct RoiAlignParams {
-    const float *boxes;
-    const float *fm[4];
-    int fm_h[4];
-    int fm_w[4];
-    int n_boxes;          // per image
-    int c4;               // channels / 4
-    int ph, pw;
-    float denom;          // 224 / sqrt(img_h*img_w), fp32
-    void *out;
-    int32_t *levels;
-    long long total;      // n_images * n_boxes
-};
 
 // modified_dense_model.py:351-363.  NaN / +-inf / out-of-range follow x86 cvttss2si (INT_MIN),
 // which is what the reference's TF CPU cast produces; CUDA's own cvt would give 0 for NaN.
@@ -62,6 +50,159 @@ __global__ void fpn_levels_kernel(const float *__restrict__ boxes, long long n, 
     const float4 b = __ldg(reinterpret_cast<const float4 *>(boxes) + i);
     levels[i] = fpn_level_dev(b.x, b.y, b.z, b.w, denom);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Pass 1 (one CTA per image): locality order + per-RoI sampling records, stored IN SORTED ORDER.
+//
+// Record of sorted position s (16-byte entries, `1 + ph + pw` of them):
+//   [0]        {map base pointer of the RoI's image at its level (64 bit), RoI index, level}
+//   [1+y]      {top*W*c4, bottom*W*c4, bits(y_lerp), in_range}   for each of the ph sample rows
+//   [1+ph+x]   {left*c4,  right*c4,    bits(x_lerp), in_range}   for each of the pw sample columns
+// (offsets in float4 units) so that the streaming pass needs no per-RoI arithmetic, no shared
+// memory and no block barrier.
+//
+// Order: RoIs of an image are counting-sorted by (level, Morton code of the box centre on a
+// 16x16 grid).  Overlapping boxes are then processed close together in time, every feature-map
+// pixel is fetched from HBM about once and re-used out of L2 (the natural order re-read 1.75x
+// the compulsory bytes at the cfg2 size).  Results are still written to the RoI's own slot.
+// ---------------------------------------------------------------------------------------------
+struct RoiPrepParams {
+    const float *boxes;
+    const float *fm[4];
+    int fm_h[4];
+    int fm_w[4];
+    int n_boxes;          // per image
+    int c4;               // channels / 4
+    int ph, pw;
+    float denom;          // 224 / sqrt(img_h*img_w), fp32
+    int4 *records;        // [total][1 + ph + pw], sorted order
+    int4 *scratch;        // [total] {key, rank, level, -}
+    int32_t *levels;      // optional
+};
+
+constexpr int kBuckets = 1024;      // 4 levels x 256 Morton tiles
+constexpr int kPrepThreads = 1024;
+
+__device__ __forceinline__ unsigned morton4(unsigned v) {   // spread 4 bits: abcd -> 0a0b0c0d
+    v &= 0xF;
+    v = (v | (v << 2)) & 0x33;
+    v = (v | (v << 1)) & 0x55;
+    return v;
+}
+
+__global__ void __launch_bounds__(kPrepThreads) roi_prepare_kernel(const RoiPrepParams p) {
+    __shared__ int s_hist[kBuckets];
+    __shared__ int s_warp_sum[kPrepThreads / 32];
+    const int tid = threadIdx.x;
+    const long long img = blockIdx.x;
+    const int rec_len = 1 + p.ph + p.pw;
+    for (int i = tid; i < kBuckets; i += kPrepThreads) s_hist[i] = 0;
+    __syncthreads();
+
+    // phase 1: level (the only fp64 work), locality key, rank inside the bucket
+    for (int i = tid; i < p.n_boxes; i += kPrepThreads) {
+        const long long roi = img * p.n_boxes + i;
+        const float4 box = __ldg(reinterpret_cast<const float4 *>(p.boxes) + roi);
+        const float y1 = box.x, x1 = box.y, y2 = box.z, x2 = box.w;
+        const int lv = fpn_level_dev(y1, x1, y2, x2, p.denom);
+        if (p.levels) p.levels[roi] = lv;
+        float cy = 0.5f * (y1 + y2), cx = 0.5f * (x1 + x2);
+        cy = (cy >= 0.f && cy <= 1.f) ? cy : 0.f;       // also maps NaN to 0
+        cx = (cx >= 0.f && cx <= 1.f) ? cx : 0.f;
+        const unsigned ty = min(15u, (unsigned)(cy * 16.f)), tx = min(15u, (unsigned)(cx * 16.f));
+        const int key = (lv - 2) * 256 + (int)((morton4(ty) << 1) | morton4(tx));
+        const int rank = atomicAdd(&s_hist[key], 1);
+        p.scratch[roi] = make_int4(key, rank, lv, 0);
+    }
+    __syncthreads();
+    // exclusive scan of the 1024 bucket counts (one bucket per thread)
+    {
+        const int v = s_hist[tid];
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((tid & 31) >= d) inc += t;
+        }
+        if ((tid & 31) == 31) s_warp_sum[tid >> 5] = inc;
+        __syncthreads();
+        if (tid < 32) {
+            int w = s_warp_sum[tid];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, d);
+                if (tid >= d) w += t;
+            }
+            s_warp_sum[tid] = w;
+        }
+        __syncthreads();
+        const int warp_off = (tid >> 5) ? s_warp_sum[(tid >> 5) - 1] : 0;
+        s_hist[tid] = warp_off + inc - v;
+    }
+    __syncthreads();
+    // phase 2: sampling records at the sorted slots.  One thread per record ENTRY, so that a warp
+    // writes 32 consecutive 16-byte entries (coalesced) instead of 32 scattered records.
+    const int entries = p.n_boxes * rec_len;
+    for (int idx = tid; idx < entries; idx += kPrepThreads) {
+        const int i = idx / rec_len;
+        const int e = idx - i * rec_len;
+        const long long roi = img * p.n_boxes + i;
+        const int4 kr = p.scratch[roi];
+        const float4 box = __ldg(reinterpret_cast<const float4 *>(p.boxes) + roi);
+        const int lv = kr.z, li = lv - 2;
+        int H, W;
+        const float *base;
+        switch (li) {
+            case 0: H = p.fm_h[0]; W = p.fm_w[0]; base = p.fm[0]; break;
+            case 1: H = p.fm_h[1]; W = p.fm_w[1]; base = p.fm[1]; break;
+            case 2: H = p.fm_h[2]; W = p.fm_w[2]; base = p.fm[2]; break;
+            default: H = p.fm_h[3]; W = p.fm_w[3]; base = p.fm[3]; break;
+        }
+        int4 *rec = p.records + (img * p.n_boxes + s_hist[kr.x] + kr.y) * rec_len;
+        int4 v;
+        if (e == 0) {
+            base += img * (long long)H * W * p.c4 * 4;
+            const unsigned long long bp = (unsigned long long)base;
+            v = make_int4((int)(bp & 0xffffffffull), (int)(bp >> 32), (int)roi, lv);
+        } else {
+            // tf.image.crop_and_resize sample coordinate (one sample per bin, end points inclusive)
+            const bool is_y = e <= p.ph;
+            const int j = is_y ? e - 1 : e - 1 - p.ph;
+            const int n = is_y ? p.ph : p.pw;
+            const float a1 = is_y ? box.x : box.y, a2 = is_y ? box.z : box.w;
+            const float Dm1 = (float)((is_y ? H : W) - 1);
+            const int stride = is_y ? W * p.c4 : p.c4;
+            float in;
+            if (n > 1) {
+                const float sc = __fdiv_rn(__fmul_rn(__fsub_rn(a2, a1), Dm1), (float)(n - 1));
+                in = __fadd_rn(__fmul_rn(a1, Dm1), __fmul_rn((float)j, sc));
+            } else {
+                in = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(a1, a2)), Dm1);
+            }
+            const bool ok = (in >= 0.0f) && (in <= Dm1);
+            const float fl = floorf(in);
+            v = make_int4(ok ? (int)fl * stride : 0, ok ? (int)ceilf(in) * stride : 0,
+                          __float_as_int(__fsub_rn(in, fl)), ok ? 1 : 0);
+        }
+        rec[e] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass 2: streaming gather.  One CTA walks sorted RoIs (grid-stride); warp w owns sample rows
+// w, w+W, ...  For a row the warp loads the y entry once and then, per 32-quad channel part,
+// streams the pw bins in groups of kUnroll: 4 x LDG.128 taps per bin (each 512 B contiguous per
+// warp), two-level lerp, one streaming STG.128.  4*kUnroll independent 128-bit loads are in
+// flight per lane; there is no shared memory and no block barrier.
+// ---------------------------------------------------------------------------------------------
+struct RoiStreamParams {
+    const int4 *records;
+    int c4;
+    int parts;            // ceil(c4 / 32)
+    int ph, pw;
+    void *out;
+    int total;            // RoIs
+};
 
 __device__ __forceinline__ float lerp_rn(float a, float b, float t) {
     return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));
@@ -91,115 +232,60 @@ __device__ __forceinline__ void store_out(void *out, long long idx4, const float
     }
 }
 
-// One CTA per RoI (grid-stride).  Threads 0..ph-1 derive the 7 sample rows, threads 32..32+pw-1
-// the 7 sample columns (floor/ceil tap index, lerp weight, in-range flag) into shared memory;
-// then all threads stream (bin, channel-quad) items: 4 x LDG.128 taps -> 2-level lerp ->
-// 1 x STG.128, kUnroll items in flight per thread.
-template <int kThreads, int kUnroll, bool kBf16, int kC4Log2>
-__global__ void __launch_bounds__(kThreads)
-roi_align_kernel(const RoiAlignParams p) {
-    __shared__ int s_top[kMaxPool], s_bot[kMaxPool], s_left[kMaxPool], s_right[kMaxPool];
-    __shared__ float s_ly[kMaxPool], s_lx[kMaxPool];
-    __shared__ int s_yok[kMaxPool], s_xok[kMaxPool];
-    __shared__ int s_level;
+template <int kUnroll, int kMaxReg, bool kBf16>
+__global__ void __maxnreg__(kMaxReg)
+roi_align_stream_kernel(const RoiStreamParams p) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarp = blockDim.x >> 5;
+    const int rec_len = 1 + p.ph + p.pw;
+    const int bins = p.ph * p.pw;
 
-    const int tid = threadIdx.x;
-    const int c4 = (kC4Log2 >= 0) ? (1 << (kC4Log2 < 0 ? 0 : kC4Log2)) : p.c4;
-    const int items = p.ph * p.pw * c4;
-
-    for (long long roi = blockIdx.x; roi < p.total; roi += gridDim.x) {
-        const float4 box = __ldg(reinterpret_cast<const float4 *>(p.boxes) + roi);
-        const float y1 = box.x, x1 = box.y, y2 = box.z, x2 = box.w;
-        const bool is_y = tid < p.ph;
-        const bool is_x = tid >= 32 && tid < 32 + p.pw;
-        if (is_y || is_x) {
-            const int lv = fpn_level_dev(y1, x1, y2, x2, p.denom);
-            const int li = lv - 2;
-            if (is_y) {
-                const int H = p.fm_h[li];
-                const float Hm1 = (float)(H - 1);
-                float in_y;
-                if (p.ph > 1) {
-                    const float hs = __fdiv_rn(__fmul_rn(__fsub_rn(y2, y1), Hm1), (float)(p.ph - 1));
-                    in_y = __fadd_rn(__fmul_rn(y1, Hm1), __fmul_rn((float)tid, hs));
-                } else {
-                    in_y = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(y1, y2)), Hm1);
-                }
-                const bool ok = (in_y >= 0.0f) && (in_y <= Hm1);
-                const float fl = floorf(in_y);
-                s_yok[tid] = ok;
-                s_top[tid] = ok ? (int)fl : 0;
-                s_bot[tid] = ok ? (int)ceilf(in_y) : 0;
-                s_ly[tid] = __fsub_rn(in_y, fl);
-                if (tid == 0) {
-                    s_level = lv;
-                    if (p.levels) p.levels[roi] = lv;
-                }
-            } else {
-                const int j = tid - 32;
-                const int W = p.fm_w[li];
-                const float Wm1 = (float)(W - 1);
-                float in_x;
-                if (p.pw > 1) {
-                    const float ws = __fdiv_rn(__fmul_rn(__fsub_rn(x2, x1), Wm1), (float)(p.pw - 1));
-                    in_x = __fadd_rn(__fmul_rn(x1, Wm1), __fmul_rn((float)j, ws));
-                } else {
-                    in_x = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x1, x2)), Wm1);
-                }
-                const bool ok = (in_x >= 0.0f) && (in_x <= Wm1);
-                const float fl = floorf(in_x);
-                s_xok[j] = ok;
-                s_left[j] = ok ? (int)fl : 0;
-                s_right[j] = ok ? (int)ceilf(in_x) : 0;
-                s_lx[j] = __fsub_rn(in_x, fl);
-            }
-        }
-        __syncthreads();
-
-        const int li = s_level - 2;
-        const int W = p.fm_w[li];
-        const long long img = roi / p.n_boxes;
-        const float4 *__restrict__ fm = reinterpret_cast<const float4 *>(p.fm[li]) +
-                                        img * (long long)p.fm_h[li] * W * c4;
-        const long long out_base = roi * (long long)items;
-
-        for (int it = tid; it < items; it += kThreads * kUnroll) {
-            float4 tl[kUnroll], tr[kUnroll], bl[kUnroll], br[kUnroll];
-            float lx[kUnroll], ly[kUnroll];
-            bool ok[kUnroll];
+    for (int spos = blockIdx.x; spos < p.total; spos += gridDim.x) {
+        const int4 *rec = p.records + (long long)spos * rec_len;
+        const int4 hd = __ldg(rec);
+        const float4 *fm = reinterpret_cast<const float4 *>(
+            ((unsigned long long)(unsigned)hd.x) | ((unsigned long long)(unsigned)hd.y << 32));
+        const long long out_roi = (long long)hd.z * bins * p.c4;
+        for (int by = warp; by < p.ph; by += nwarp) {
+            const int4 ye = __ldg(rec + 1 + by);
+            const float ly = __int_as_float(ye.z);
+            const float4 *row_t = fm + ye.x;
+            const float4 *row_b = fm + ye.y;
+            const long long out_row = out_roi + (long long)by * p.pw * p.c4;
+            for (int part = 0; part < p.parts; ++part) {
+                const int c = part * 32 + lane;
+                const bool act = c < p.c4;
+                for (int bx0 = 0; bx0 < p.pw; bx0 += kUnroll) {
+                    float4 tl[kUnroll], tr[kUnroll], bl[kUnroll], br[kUnroll];
+                    float lx[kUnroll];
+                    bool ok[kUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int idx = it + u * kThreads;
-                ok[u] = false;
-                if (idx < items) {
-                    const int bin = (kC4Log2 >= 0) ? (idx >> (kC4Log2 < 0 ? 0 : kC4Log2)) : idx / c4;
-                    const int c = idx - bin * c4;
-                    const int by = bin / p.pw;
-                    const int bx = bin - by * p.pw;
-                    ok[u] = s_yok[by] && s_xok[bx];
-                    if (ok[u]) {
-                        const int rt = s_top[by] * W, rb = s_bot[by] * W;
-                        const int cl = s_left[bx], cr = s_right[bx];
-                        tl[u] = __ldg(fm + (long long)(rt + cl) * c4 + c);
-                        tr[u] = __ldg(fm + (long long)(rt + cr) * c4 + c);
-                        bl[u] = __ldg(fm + (long long)(rb + cl) * c4 + c);
-                        br[u] = __ldg(fm + (long long)(rb + cr) * c4 + c);
-                        lx[u] = s_lx[bx];
-                        ly[u] = s_ly[by];
+                    for (int k = 0; k < kUnroll; ++k) {
+                        ok[k] = false;
+                        if (bx0 + k < p.pw) {
+                            const int4 xe = __ldg(rec + 1 + p.ph + bx0 + k);
+                            ok[k] = act && ye.w && xe.w;
+                            lx[k] = __int_as_float(xe.z);
+                            if (ok[k]) {
+                                tl[k] = __ldg(row_t + xe.x + c);
+                                tr[k] = __ldg(row_t + xe.y + c);
+                                bl[k] = __ldg(row_b + xe.x + c);
+                                br[k] = __ldg(row_b + xe.y + c);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kUnroll; ++k) {
+                        if (act && bx0 + k < p.pw) {
+                            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (ok[k]) o = bilerp4(tl[k], tr[k], bl[k], br[k], lx[k], ly);
+                            store_out<kBf16>(p.out, out_row + (long long)(bx0 + k) * p.c4 + c, o);
+                        }
                     }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int idx = it + u * kThreads;
-                if (idx < items) {
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok[u]) o = bilerp4(tl[u], tr[u], bl[u], br[u], lx[u], ly[u]);
-                    store_out<kBf16>(p.out, out_base + idx, o);
-                }
-            }
         }
-        __syncthreads();      // shared row/column tables are rewritten for the next RoI
     }
 }
 
@@ -241,28 +327,60 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
     int rc = validate(boxes, fmaps, fm_h, fm_w, n_images, n_boxes, channels, pool_h, pool_w, img_h,
                       img_w, out);
     if (rc != DC_OK) return rc;
-    RoiAlignParams p;
-    p.total = (long long)n_images * n_boxes;
-    if (p.total == 0) return DC_OK;
-    p.boxes = boxes;
-    for (int l = 0; l < 4; ++l) { p.fm[l] = fmaps[l]; p.fm_h[l] = fm_h[l]; p.fm_w[l] = fm_w[l]; }
-    p.n_boxes = n_boxes;
-    p.c4 = channels / 4;
-    p.ph = pool_h; p.pw = pool_w;
-    p.denom = level_denominator(img_h, img_w);
-    p.out = out;
-    p.levels = levels;
-    constexpr int kThreads = 256;
-    constexpr int kUnroll = 4;
-    // 8 resident CTAs of 256 threads per SM at most; a grid of sm_count*8 is one full wave and the
-    // grid-stride loop keeps the walk in (image, box) order.
-    const long long max_grid = (long long)sm_count() * 8;
-    const int grid = (int)(p.total < max_grid ? p.total : max_grid);
-    if (p.c4 == 64)
-        roi_align_kernel<kThreads, kUnroll, kBf16, 6><<<grid, kThreads, 0, stream>>>(p);
-    else
-        roi_align_kernel<kThreads, kUnroll, kBf16, -1><<<grid, kThreads, 0, stream>>>(p);
-    DC_CHECK_LAUNCH();
+    const long long total = (long long)n_images * n_boxes;
+    if (total == 0) return DC_OK;
+    DC_REQUIRE(total < (1ll << 31), "n_images*n_boxes must fit in int32");
+    const int rec_len = 1 + pool_h + pool_w;
+
+    // stream-ordered workspace: sorted records + scratch (cached by the default pool)
+    const size_t rec_bytes = sizeof(int4) * (size_t)total * rec_len;
+    const size_t scr_bytes = sizeof(int4) * (size_t)total;
+    char *ws = nullptr;
+    DC_CHECK_CUDA(cudaMallocAsync((void **)&ws, rec_bytes + scr_bytes, stream));
+
+    RoiPrepParams pp;
+    pp.boxes = boxes;
+    for (int l = 0; l < 4; ++l) { pp.fm[l] = fmaps[l]; pp.fm_h[l] = fm_h[l]; pp.fm_w[l] = fm_w[l]; }
+    pp.n_boxes = n_boxes;
+    pp.c4 = channels / 4;
+    pp.ph = pool_h; pp.pw = pool_w;
+    pp.denom = level_denominator(img_h, img_w);
+    pp.records = reinterpret_cast<int4 *>(ws);
+    pp.scratch = reinterpret_cast<int4 *>(ws + rec_bytes);
+    pp.levels = levels;
+    roi_prepare_kernel<<<n_images, kPrepThreads, 0, stream>>>(pp);
+    cudaError_t e = cudaGetLastError();
+
+    if (e == cudaSuccess) {
+        RoiStreamParams sp;
+        sp.records = pp.records;
+        sp.c4 = channels / 4;
+        sp.parts = (sp.c4 + 31) / 32;
+        sp.ph = pool_h; sp.pw = pool_w;
+        sp.out = out;
+        sp.total = (int)total;
+        const int warps = pool_h < 7 ? pool_h : 7;          // one warp per sample row
+        // a whole number of waves: SM count x resident CTAs per SM
+        const long long max_grid = (long long)sm_count() * 8;
+        const int grid = (int)(total < max_grid ? total : max_grid);
+        static const int variant = getenv("DCAP_ROI_VARIANT") ? atoi(getenv("DCAP_ROI_VARIANT")) : 5;
+        static const int ctas = getenv("DCAP_ROI_CTAS") ? atoi(getenv("DCAP_ROI_CTAS")) : 4;
+        const long long mg = (long long)sm_count() * ctas;
+        const int g2 = (int)(total < mg ? total : mg);
+        switch (variant) {
+            case 1: roi_align_stream_kernel<4, 128, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
+            case 2: roi_align_stream_kernel<2, 64, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
+            case 3: roi_align_stream_kernel<2, 80, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
+            case 4: roi_align_stream_kernel<1, 40, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
+            case 5: roi_align_stream_kernel<2, 72, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
+            case 6: roi_align_stream_kernel<1, 48, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
+            default: roi_align_stream_kernel<4, 96, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
+        }
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(ws, stream);
+    if (e != cudaSuccess)
+        return set_error(DC_ERR_CUDA, "roi align launch failed: %s", cudaGetErrorString(e));
     return DC_OK;
 }
 
