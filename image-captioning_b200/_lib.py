@@ -42,6 +42,23 @@ SIGNATURES = {
     "dc_pyramid_roi_align_host_f32": (ctypes.c_int, [c_void, c_void * 4, ctypes.c_int * 4,
                                                      ctypes.c_int * 4] + [ctypes.c_int] * 7 +
                                       [c_void, c_void]),
+    "dc_decoder_create": (ctypes.c_int, [c_void, c_void]),
+    "dc_decoder_destroy": (ctypes.c_int, [c_void]),
+    "dc_decoder_weight_count": (ctypes.c_int, [c_void]),
+    "dc_decoder_weight_name": (ctypes.c_char_p, [c_void, ctypes.c_int]),
+    "dc_decoder_weight_numel": (ctypes.c_int64, [c_void, ctypes.c_int]),
+    "dc_decoder_set_weight": (ctypes.c_int, [c_void, ctypes.c_char_p, c_void, ctypes.c_int64]),
+    "dc_decoder_get_weight": (ctypes.c_int, [c_void, ctypes.c_char_p, c_void, ctypes.c_int64]),
+    "dc_decoder_finalize": (ctypes.c_int, [c_void, c_void]),
+    "dc_head_forward": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void]),
+    "dc_decoder_greedy": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void]),
+    "dc_decoder_beam": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void,
+                                       c_void, c_void]),
+    "dc_decoder_v2_predict": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_void, ctypes.c_int,
+                                             ctypes.c_int, c_void, c_void]),
+    "dc_decoder_v2_greedy": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void,
+                                            c_void]),
+    "dc_decoder_greedy_host": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void]),
 }
 
 

@@ -1,0 +1,84 @@
+// Decoder handle (see decoder.cu).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "decoder_kernels.cuh"
+#include "gemm.cuh"
+
+namespace dcap {
+
+constexpr int kDense = 1024;      // Dense(1024, relu) of the word model (text_generation_model.py:143)
+
+struct Weight {
+    std::string name;
+    std::vector<int64_t> shape;
+    int64_t numel = 0;
+    float *dev = nullptr;         // fp32, Keras layout
+};
+
+struct Workspace {
+    float *F = nullptr, *a1 = nullptr, *g1f = nullptr, *d1f = nullptr;
+    float *xh1 = nullptr, *xh1b = nullptr, *xh2 = nullptr, *xh2b = nullptr;
+    float *c1 = nullptr, *c1b = nullptr, *c2 = nullptr, *c2b = nullptr;
+    float *gates = nullptr, *d = nullptr, *h2 = nullptr, *logits = nullptr, *cand_p = nullptr;
+    int32_t *tok = nullptr, *newtok = nullptr, *parent = nullptr, *cand_idx = nullptr;
+    int32_t *hist_a = nullptr, *hist_b = nullptr;
+    double *score_a = nullptr, *score_b = nullptr;
+};
+
+struct Bf16State;                 // decoder_bf16.cu
+
+struct Decoder {
+    DcDecoderConfig cfg{};
+    int device = 0;
+    std::vector<Weight> weights;
+    std::vector<void *> owned, ws_owned;
+    bool finalized = false;
+    int cap = 0, rep_cap = 0;
+    Workspace ws;
+    float *bn_scale[2] = {nullptr, nullptr}, *bn_shift[2] = {nullptr, nullptr};
+    float *w1cat = nullptr, *w2cat = nullptr;
+    float *rep_g1f = nullptr, *rep_d1f = nullptr;
+    Bf16State *bf = nullptr;
+
+    ~Decoder();
+    void declare(const std::string &name, std::vector<int64_t> shape);
+    void declare_all();
+    Weight *find(const std::string &name);
+    const float *W(const char *name);
+    int dev_alloc(void **p, size_t bytes, std::vector<void *> &list);
+    int finalize(cudaStream_t s);
+    int reserve(int rows);
+    int ensure_rep(int R);
+    int check_ready(int B);
+
+    int linear_f32(const float *x, int ldx, int M, const float *Wk, int K, int N, const float *bias,
+                   const float *addend, int ld_addend, const float *scale, const float *shift, bool relu,
+                   float *out, int ldo, cudaStream_t s);
+    int head(const void *feats, int kind, int B, float *out, cudaStream_t s);
+    int v1_hoist(int B, cudaStream_t s);
+    int v1_reset_state(int R, cudaStream_t s);
+    int v1_step(int R, const float *g1f, const float *d1f, cudaStream_t s);
+    int greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s);
+    int beam(const void *feats, int kind, int B, int k, int32_t *tokens, double *scores, cudaStream_t s);
+    int v2_reset(int B, cudaStream_t s);
+    int v2_word_step(int B, cudaStream_t s);
+    int v2_output(int B, cudaStream_t s);
+    int v2_head_into_xin(const void *feats, int kind, int B, cudaStream_t s);
+    int v2_predict(const void *feats, int kind, const int32_t *words, int B, int L, float *probs, cudaStream_t s);
+    int v2_greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s);
+
+    // bf16 / tcgen05 path (decoder_bf16.cu)
+    int finalize_bf16(cudaStream_t s);
+    int reserve_bf16(size_t R);
+    int head_bf16(const void *feats, int kind, int B, float *out, cudaStream_t s);
+    int v1_hoist_bf16(int B, cudaStream_t s);
+    int reset_state_bf16(int R, cudaStream_t s);
+    int v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_t s);
+    int greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s);
+    int beam_gather_bf16(int R, int k, cudaStream_t s);
+};
+
+}  // namespace dcap

@@ -1,0 +1,373 @@
+"""Drop-in for the reference's text-generation Keras models.
+
+Mirrors /root/reference/dense_img_cap_separate_models/text_generation_model.py:
+``DenseCapConfig`` (:23-49), ``build_lstm_model(features_input, config, units, mode)`` (:235-283)
+and text_generation_model_v2.py ``build_model(features_shape, word_shape, config, units, inject)``
+(:140-166).  The returned objects expose the part of the Keras ``Model`` surface the reference's
+callers use -- ``predict``, ``get_weights`` / ``set_weights`` / ``load_weights`` / ``save_weights``,
+``compile`` / ``train_on_batch`` / ``fit_generator``, ``summary`` -- and run entirely in the sm_100a
+kernels behind the C ABI (include/dcap.h).  No TensorFlow, no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ARCH_V1, ARCH_V2_INJECT = 1, 2
+DTYPE_F32, DTYPE_BF16 = 0, 1
+FEATS_ROI_F32, FEATS_HEAD_F32, FEATS_ROI_BF16 = 0, 1, 2
+_HEAD = ["mrcnn_class_conv1/kernel", "mrcnn_class_conv1/bias",
+         "mrcnn_class_bn1/gamma", "mrcnn_class_bn1/beta", "mrcnn_class_bn1/moving_mean",
+         "mrcnn_class_bn1/moving_variance",
+         "mrcnn_class_conv2/kernel", "mrcnn_class_conv2/bias",
+         "mrcnn_class_bn2/gamma", "mrcnn_class_bn2/beta", "mrcnn_class_bn2/moving_mean",
+         "mrcnn_class_bn2/moving_variance"]
+# Keras get_weights() order: per layer trainable then non-trainable; the caption layer lists the
+# word model's trainable weights first and the frozen embedding last (text_generation_model.py:205-206).
+V1_WEIGHT_ORDER = _HEAD + [
+    "imgcap_lstm1/kernel", "imgcap_lstm1/recurrent_kernel", "imgcap_lstm1/bias",
+    "imgcap_lstm2/kernel", "imgcap_lstm2/recurrent_kernel", "imgcap_lstm2/bias",
+    "imgcap_lstm_d1/kernel", "imgcap_lstm_d1/bias", "imgcap_lstm_d2/kernel", "imgcap_lstm_d2/bias",
+    "imgcap_embedding_layer/embeddings"]
+V2_WEIGHT_ORDER = _HEAD + [
+    "imgcap_embedding_layer/embeddings",
+    "lstm_1/kernel", "lstm_1/recurrent_kernel", "lstm_1/bias",
+    "imgcap_lstm/kernel", "imgcap_lstm/recurrent_kernel", "imgcap_lstm/bias",
+    "imgcap_d1/kernel", "imgcap_d1/bias"]
+
+
+class DenseCapConfig(object):
+    """The fields of the reference's DenseCapConfig that the text models read
+    (text_generation_model.py:23-49)."""
+    NAME = "dense image captioning"
+    GPU_COUNT = 1
+    IMAGES_PER_GPU = 1
+    BATCH_SIZE = 10
+    PADDING_SIZE = 10
+    POOL_SIZE = 7
+
+    def __init__(self, vocab_size, embedding_weights, batch_size=None, padding_size=None):
+        self.VOCABULARY_SIZE = int(vocab_size)
+        self.EMBEDDING_WEIGHTS = np.asarray(embedding_weights, dtype=np.float32)
+        self.EMBEDDING_SIZE = int(self.EMBEDDING_WEIGHTS.shape[1])
+        if batch_size is not None:
+            self.BATCH_SIZE = int(batch_size)
+        if padding_size is not None:
+            self.PADDING_SIZE = int(padding_size)
+
+
+class _DcDecoderConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("arch", "dtype", "vocab", "embed", "feat", "units",
+                                            "word_units", "pool", "channels", "padding")]
+
+
+def _dtype_code(dtype):
+    if dtype in ("float32", "fp32", torch.float32, np.float32, DTYPE_F32):
+        return DTYPE_F32
+    if dtype in ("bfloat16", "bf16", torch.bfloat16, DTYPE_BF16):
+        return DTYPE_BF16
+    raise ValueError("dtype must be 'float32' or 'bfloat16'")
+
+
+class _ModelBase(object):
+    """Handle owner + the weight half of the Keras Model surface."""
+
+    def __init__(self, arch, config, units, features_input, dtype, word_units=0, device=None):
+        if len(features_input) != 3 or features_input[0] != features_input[1]:
+            raise ValueError("features_input must be [pool, pool, channels]")
+        if features_input[0] != config.POOL_SIZE:
+            raise ValueError("features_input pool %d != config.POOL_SIZE %d"
+                             % (features_input[0], config.POOL_SIZE))
+        self.config = config
+        self.units = int(units)
+        self.arch = arch
+        self.dtype = _dtype_code(dtype)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self._lib = _lib.load()
+        cfg = _DcDecoderConfig(arch, self.dtype, config.VOCABULARY_SIZE, config.EMBEDDING_SIZE, 1024,
+                               self.units, int(word_units), int(features_input[0]),
+                               int(features_input[2]), config.PADDING_SIZE)
+        self._cfg = cfg
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        self._dirty = True
+        self._names = [self._lib.dc_decoder_weight_name(self._h, i).decode()
+                       for i in range(self._lib.dc_decoder_weight_count(self._h))]
+        self._numel = {n: self._lib.dc_decoder_weight_numel(self._h, i) for i, n in enumerate(self._names)}
+        self._shapes = self._weight_shapes()
+        self._set = set()
+        # like the Keras models, the embedding layer is initialised from config.EMBEDDING_WEIGHTS
+        self._set_one("imgcap_embedding_layer/embeddings", config.EMBEDDING_WEIGHTS)
+        self.optimizer = None
+        self.loss = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                self._lib.dc_decoder_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    # ---- weights ----
+    def _weight_shapes(self):
+        c, u = self._cfg, self.units
+        F, E, V, p, C = c.feat, c.embed, c.vocab, c.pool, c.channels
+        s = {"mrcnn_class_conv1/kernel": (p, p, C, F), "mrcnn_class_conv1/bias": (F,),
+             "mrcnn_class_conv2/kernel": (1, 1, F, F), "mrcnn_class_conv2/bias": (F,),
+             "imgcap_embedding_layer/embeddings": (V, E)}
+        for bn in ("mrcnn_class_bn1", "mrcnn_class_bn2"):
+            for n in ("gamma", "beta", "moving_mean", "moving_variance"):
+                s["%s/%s" % (bn, n)] = (F,)
+        if self.arch == ARCH_V1:
+            s.update({"imgcap_lstm1/kernel": (E + F, 4 * u), "imgcap_lstm1/recurrent_kernel": (u, 4 * u),
+                      "imgcap_lstm1/bias": (4 * u,), "imgcap_lstm2/kernel": (u, 4 * u),
+                      "imgcap_lstm2/recurrent_kernel": (u, 4 * u), "imgcap_lstm2/bias": (4 * u,),
+                      "imgcap_lstm_d1/kernel": (u + F, 1024), "imgcap_lstm_d1/bias": (1024,),
+                      "imgcap_lstm_d2/kernel": (1024, V), "imgcap_lstm_d2/bias": (V,)})
+        else:
+            wu = c.word_units
+            s.update({"lstm_1/kernel": (E, 4 * wu), "lstm_1/recurrent_kernel": (wu, 4 * wu),
+                      "lstm_1/bias": (4 * wu,), "imgcap_lstm/kernel": (F + wu, 4 * u),
+                      "imgcap_lstm/recurrent_kernel": (u, 4 * u), "imgcap_lstm/bias": (4 * u,),
+                      "imgcap_d1/kernel": (u, V), "imgcap_d1/bias": (V,)})
+        assert sorted(s) == sorted(self._names)
+        return s
+
+    @property
+    def weight_names(self):
+        return list(V1_WEIGHT_ORDER if self.arch == ARCH_V1 else V2_WEIGHT_ORDER)
+
+    def _set_one(self, name, value):
+        if name not in self._shapes:
+            raise ValueError("unknown weight %r" % name)
+        a = np.ascontiguousarray(np.asarray(value, dtype=np.float32))
+        if tuple(a.shape) != tuple(self._shapes[name]):
+            raise ValueError("weight %r: expected shape %s, got %s" % (name, self._shapes[name], a.shape))
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_set_weight(self._h, name.encode(), ctypes.c_void_p(a.ctypes.data),
+                                                       ctypes.c_int64(a.size)))
+        self._set.add(name)
+        self._dirty = True
+
+    def set_weights(self, weights):
+        """Keras-ordered list (see ``weight_names``) or a ``{name: array}`` dict."""
+        if isinstance(weights, dict):
+            for n, v in weights.items():
+                self._set_one(n, v)
+            return
+        names = self.weight_names
+        if len(weights) != len(names):
+            raise ValueError("expected %d weight arrays, got %d" % (len(names), len(weights)))
+        for n, v in zip(names, weights):
+            self._set_one(n, v)
+
+    def _get_one(self, name):
+        out = np.empty(self._shapes[name], np.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_get_weight(self._h, name.encode(), ctypes.c_void_p(out.ctypes.data),
+                                                       ctypes.c_int64(out.size)))
+        return out
+
+    def get_weights(self):
+        return [self._get_one(n) for n in self.weight_names]
+
+    def get_weights_dict(self):
+        return {n: self._get_one(n) for n in self.weight_names}
+
+    def save_weights(self, path):
+        """Weights as an .npz keyed by Keras weight name (h5py is not available; the converter
+        from Keras HDF5 is an offline tool)."""
+        np.savez(path, **{n.replace("/", "__"): v for n, v in self.get_weights_dict().items()})
+
+    def load_weights(self, path, by_name=False, skip_mismatch=False):
+        """by_name=True loads only the tensors present in the file (as the reference does with
+        mask_rcnn_coco.h5 to fill the head, text_generation_model.py:468)."""
+        with np.load(path) as z:
+            found = {k.replace("__", "/"): z[k] for k in z.files}
+        for n, v in found.items():
+            if n not in self._shapes:
+                if by_name:
+                    continue
+                raise ValueError("file holds unknown weight %r" % n)
+            if tuple(v.shape) != tuple(self._shapes[n]):
+                if skip_mismatch:
+                    continue
+                raise ValueError("weight %r: expected shape %s, got %s" % (n, self._shapes[n], v.shape))
+            self._set_one(n, v)
+        if not by_name:
+            missing = [n for n in self._shapes if n not in found]
+            if missing:
+                raise ValueError("file lacks weights: %s" % ", ".join(missing))
+
+    def _ready(self):
+        if self._dirty:
+            missing = [n for n in self._names if n not in self._set]
+            if missing:
+                raise RuntimeError("weights not set: %s" % ", ".join(missing))
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.dc_decoder_finalize(self._h, self._stream()))
+            self._dirty = False
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def summary(self):
+        total = 0
+        print("%-40s %-24s %12s" % ("weight", "shape", "params"))
+        for n in self.weight_names:
+            k = int(np.prod(self._shapes[n]))
+            total += k
+            print("%-40s %-24s %12d" % (n, self._shapes[n], k))
+        print("Total params: %d" % total)
+
+    # ---- feature plumbing ----
+    def _feats_to_device(self, x):
+        """Accepts [N,p,p,C] RoI features or [N,1024] head features (numpy or torch; fp32, or bf16
+        RoI features on the device).  Returns (tensor, feats_kind, was_numpy)."""
+        c = self._cfg
+        was_numpy = not isinstance(x, torch.Tensor)
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)) if was_numpy else x
+        if t.dim() == 4 and tuple(t.shape[1:]) == (c.pool, c.pool, c.channels):
+            kind = FEATS_ROI_BF16 if t.dtype == torch.bfloat16 else FEATS_ROI_F32
+        elif t.dim() == 2 and t.shape[1] == c.feat:
+            kind = FEATS_HEAD_F32
+        else:
+            raise ValueError("features must be [N,%d,%d,%d] or [N,%d], got %s"
+                             % (c.pool, c.pool, c.channels, c.feat, tuple(t.shape)))
+        if kind != FEATS_ROI_BF16:
+            t = t.to(torch.float32)
+        return t.to(self.device).contiguous(), kind, was_numpy
+
+
+class RoiCaptionModel(_ModelBase):
+    """build_lstm_model(...) result: v1 "inject at every step" model."""
+
+    def __init__(self, features_input, config, units, mode, dtype="float32", device=None):
+        assert mode in ["training", "inference"]
+        self.mode = mode
+        super().__init__(ARCH_V1, config, units, list(features_input), dtype, device=device)
+
+    def generate(self, features, return_probs=False, chunk=None):
+        """Greedy captions: token ids [N,P] (int32) and optionally the [N,P,V] probabilities.
+        torch CUDA in -> torch CUDA out; numpy in -> numpy out."""
+        self._ready()
+        t, kind, was_numpy = self._feats_to_device(features)
+        N, P, V = t.shape[0], self.config.PADDING_SIZE, self.config.VOCABULARY_SIZE
+        tokens = torch.empty((N, P), dtype=torch.int32, device=self.device)
+        probs = torch.empty((N, P, V), dtype=torch.float32, device=self.device) if return_probs else None
+        chunk = N if not chunk else int(chunk)
+        with torch.cuda.device(self.device):
+            for i in range(0, N, max(chunk, 1)):
+                j = min(N, i + chunk)
+                _lib.check(self._lib.dc_decoder_greedy(
+                    self._h, ctypes.c_void_p(t[i:j].data_ptr()), kind, j - i,
+                    ctypes.c_void_p(tokens[i:j].data_ptr()),
+                    ctypes.c_void_p(probs[i:j].data_ptr()) if probs is not None else None, self._stream()))
+        if was_numpy:
+            tokens = tokens.cpu().numpy()
+            probs = probs.cpu().numpy() if probs is not None else None
+        return (tokens, probs) if return_probs else tokens
+
+    def predict(self, x, batch_size=None, verbose=0):
+        """Keras predict of the inference model: [N,P,V] word probabilities
+        (evaluate_models/eval_text_generation_model.py:141).  As in Keras the sample count must be
+        a multiple of config.BATCH_SIZE (the graph bakes the batch in, :211)."""
+        if self.mode != "inference":
+            raise RuntimeError("predict() on the training graph needs [features, gt_captions]; "
+                               "use predict_teacher_forced")
+        n = len(x)
+        if n % self.config.BATCH_SIZE != 0:
+            raise ValueError("number of samples %d is not a multiple of config.BATCH_SIZE %d"
+                             % (n, self.config.BATCH_SIZE))
+        _, probs = self.generate(x, return_probs=True)
+        return probs
+
+    def beam_search(self, features, beam_width=3, chunk=None):
+        """gen_captions semantics (image captioning/test.py:23-64) on the v1 decoder: returns
+        (tokens [N,k,P] ascending by score -- best beam last --, scores [N,k] float64)."""
+        self._ready()
+        t, kind, was_numpy = self._feats_to_device(features)
+        N, P, k = t.shape[0], self.config.PADDING_SIZE, int(beam_width)
+        tokens = torch.empty((N, k, P), dtype=torch.int32, device=self.device)
+        scores = torch.empty((N, k), dtype=torch.float64, device=self.device)
+        chunk = N if not chunk else int(chunk)
+        with torch.cuda.device(self.device):
+            for i in range(0, N, max(chunk, 1)):
+                j = min(N, i + chunk)
+                _lib.check(self._lib.dc_decoder_beam(
+                    self._h, ctypes.c_void_p(t[i:j].data_ptr()), kind, j - i, k,
+                    ctypes.c_void_p(tokens[i:j].data_ptr()), ctypes.c_void_p(scores[i:j].data_ptr()),
+                    self._stream()))
+        if was_numpy:
+            return tokens.cpu().numpy(), scores.cpu().numpy()
+        return tokens, scores
+
+    def head_features(self, features):
+        """`features_new` of build_lstm_model (:249-262): [N,1024]."""
+        self._ready()
+        t, kind, was_numpy = self._feats_to_device(features)
+        out = torch.empty((t.shape[0], self._cfg.feat), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_head_forward(self._h, ctypes.c_void_p(t.data_ptr()), kind, t.shape[0],
+                                                 ctypes.c_void_p(out.data_ptr()), self._stream()))
+        return out.cpu().numpy() if was_numpy else out
+
+
+class InjectModelV2(_ModelBase):
+    """build_model(features_shape, word_shape, config, units, inject=True) result."""
+
+    def __init__(self, features_shape, word_shape, config, units, device=None):
+        self.word_shape = tuple(word_shape)
+        super().__init__(ARCH_V2_INJECT, config, units, list(features_shape), "float32", word_units=1024,
+                         device=device)
+
+    def predict(self, x, batch_size=None, verbose=0):
+        """model.predict([features, words]) -> [N,V] next-word probabilities
+        (evaluate_models/test_score_dense_captions.py:221)."""
+        self._ready()
+        feats, words = x
+        t, kind, was_numpy = self._feats_to_device(feats)
+        w = torch.as_tensor(np.asarray(words) if not isinstance(words, torch.Tensor) else words)
+        if w.dim() != 2 or w.shape[0] != t.shape[0]:
+            raise ValueError("words must be [N, L] with the same N as the features")
+        w = w.to(torch.int32).to(self.device).contiguous()
+        probs = torch.empty((t.shape[0], self.config.VOCABULARY_SIZE), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_v2_predict(
+                self._h, ctypes.c_void_p(t.data_ptr()), kind, ctypes.c_void_p(w.data_ptr()), t.shape[0],
+                w.shape[1], ctypes.c_void_p(probs.data_ptr()), self._stream()))
+        return probs.cpu().numpy() if was_numpy else probs
+
+    def generate(self, features, return_probs=False):
+        """The reference's greedy loop (test_score_dense_captions.py:216-225): P-1 ids per RoI."""
+        self._ready()
+        t, kind, was_numpy = self._feats_to_device(features)
+        N, P, V = t.shape[0], self.config.PADDING_SIZE, self.config.VOCABULARY_SIZE
+        tokens = torch.empty((N, P - 1), dtype=torch.int32, device=self.device)
+        probs = torch.empty((N, P - 1, V), dtype=torch.float32, device=self.device) if return_probs else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_v2_greedy(
+                self._h, ctypes.c_void_p(t.data_ptr()), kind, N, ctypes.c_void_p(tokens.data_ptr()),
+                ctypes.c_void_p(probs.data_ptr()) if probs is not None else None, self._stream()))
+        if was_numpy:
+            tokens = tokens.cpu().numpy()
+            probs = probs.cpu().numpy() if probs is not None else None
+        return (tokens, probs) if return_probs else tokens
+
+
+def build_lstm_model(features_input, config, units, mode, dtype="float32", device=None):
+    """Same signature as the reference (text_generation_model.py:235) plus `dtype`/`device`."""
+    return RoiCaptionModel(features_input, config, units, mode, dtype=dtype, device=device)
+
+
+def build_model(features_shape, word_shape, config, units, inject=True, device=None):
+    """Same signature as the reference (text_generation_model_v2.py:140).  Only the inject
+    variant ("m1") is on the hot path; the merge variant is out of scope."""
+    if not inject:
+        raise NotImplementedError("merge model (inject=False) is outside the hot path")
+    return InjectModelV2(features_shape, word_shape, config, units, device=device)

@@ -95,6 +95,93 @@ int dc_pyramid_roi_align_host_f32(const float *boxes, const float *const fmaps[4
                                   int channels, int pool_h, int pool_w, int img_h, int img_w,
                                   float *out, int32_t *levels);
 
+/* ------------------------------------------------------------------------------------------
+ * RoI head + "inject" LSTM caption decoder
+ * ---------------------------------------------------------------------------------------- */
+
+#define DC_ARCH_V1         1   /* build_lstm_model: text_generation_model.py:235-283          */
+#define DC_ARCH_V2_INJECT  2   /* build_model(inject=True): text_generation_model_v2.py:140-166 */
+#define DC_DTYPE_F32       0   /* FFMA GEMMs: greedy ids equal the fp32 model's               */
+#define DC_DTYPE_BF16      1   /* tcgen05 GEMMs, bf16 operands, fp32 accumulate and state     */
+
+/* What `feats` points at in the decoder calls. */
+#define DC_FEATS_ROI_F32   0   /* [B, pool, pool, channels] fp32 (ROIAlign output)            */
+#define DC_FEATS_HEAD_F32  1   /* [B, feat] fp32: output of the RoI head (`features_new`,
+                                  text_generation_model.py:261)                               */
+#define DC_FEATS_ROI_BF16  2   /* [B, pool, pool, channels] bf16 (dc_pyramid_roi_align_bf16out) */
+
+typedef struct DcDecoder DcDecoder;
+
+/* Mirrors the reference's DenseCapConfig fields the text models read
+ * (text_generation_model.py:23-49: PADDING_SIZE, VOCABULARY_SIZE, EMBEDDING_SIZE, POOL_SIZE)
+ * plus the `units` argument of build_lstm_model / build_model. */
+typedef struct DcDecoderConfig {
+    int arch;        /* DC_ARCH_*                                                              */
+    int dtype;       /* DC_DTYPE_*                                                             */
+    int vocab;       /* VOCABULARY_SIZE                                                        */
+    int embed;       /* EMBEDDING_SIZE                                                         */
+    int feat;        /* RoI head width (1024)                                                  */
+    int units;       /* LSTM units (v1: both LSTMs; v2: the `imgcap_lstm` layer)               */
+    int word_units;  /* v2 only: width of the word LSTM (1024 in the reference)                */
+    int pool;        /* POOL_SIZE (7)                                                          */
+    int channels;    /* feature-map channels (256)                                             */
+    int padding;     /* PADDING_SIZE (caption length P)                                        */
+} DcDecoderConfig;
+
+/* Creates a decoder on the CURRENT device.  Replaces the Keras model objects returned by
+ * build_lstm_model(features_input, config, units, mode) (text_generation_model.py:235) and
+ * build_model(features_shape, word_shape, config, units, inject) (text_generation_model_v2.py:140). */
+int dc_decoder_create(const DcDecoderConfig *cfg, DcDecoder **out);
+int dc_decoder_destroy(DcDecoder *dec);
+
+/* Weights travel as fp32 HOST arrays in the Keras layout under the Keras weight name
+ * ("<layer>/<kernel|recurrent_kernel|bias|gamma|beta|moving_mean|moving_variance|embeddings>"),
+ * i.e. what model.get_weights()/set_weights()/load_weights(by_name=True) exchange
+ * (text_generation_model.py:468,484).  LSTM kernels are [in,4u] / [u,4u] / [4u] with gate blocks
+ * i|f|c|o; conv kernels are HWIO.  dc_decoder_weight_* enumerate the expected tensors. */
+int dc_decoder_weight_count(const DcDecoder *dec);
+const char *dc_decoder_weight_name(const DcDecoder *dec, int index);
+int64_t dc_decoder_weight_numel(const DcDecoder *dec, int index);
+int dc_decoder_set_weight(DcDecoder *dec, const char *name, const float *host, int64_t numel);
+int dc_decoder_get_weight(DcDecoder *dec, const char *name, float *host, int64_t numel);
+/* Builds the derived device buffers (folded BatchNorm, stacked / hoisted matrices, bf16 copies).
+ * Must be called after the weights change and before any forward call. */
+int dc_decoder_finalize(DcDecoder *dec, void *stream);
+
+/* RoI head: relu(bn2(relu(bn1(conv7x7_valid(X)))*W2+b2)), text_generation_model.py:249-262.
+ * feats per DC_FEATS_ROI_*; out [B, feat] fp32 (device). */
+int dc_head_forward(DcDecoder *dec, const void *feats, int feats_kind, int B, float *out,
+                    void *stream);
+
+/* v1 greedy captioning = model.predict(features) of build_lstm_model(mode='inference'):
+ * ROICaptionInferenceLayer, text_generation_model.py:192-232 -- start id 1, P steps, argmax
+ * (first index on ties) fed back, no early stop -- as ONE incremental masked scan.
+ *   tokens [B, P] int32 (device); probs optional [B, P, V] fp32 (device; the Keras output). */
+int dc_decoder_greedy(DcDecoder *dec, const void *feats, int feats_kind, int B, int32_t *tokens,
+                      float *probs, void *stream);
+
+/* Beam search with the semantics of gen_captions (image captioning/test.py:23-64) applied to the
+ * v1 decoder: width k, scores are SUMS OF PROBABILITIES (fp64 accumulation of fp32), children
+ * pooled in generation order, stable ascending sort, keep the last k, no end-token handling.
+ *   tokens [B, k, P] int32 (beams in ascending score order, best last); scores [B, k] fp64. */
+int dc_decoder_beam(DcDecoder *dec, const void *feats, int feats_kind, int B, int k,
+                    int32_t *tokens, double *scores, void *stream);
+
+/* v2 inject model.predict([features, words]) (text_generation_model_v2.py:140-166; caller
+ * evaluate_models/test_score_dense_captions.py:221): words [B, L] int32 pre-padded ids
+ * (0 = masked).  probs [B, V] fp32. */
+int dc_decoder_v2_predict(DcDecoder *dec, const void *feats, int feats_kind, const int32_t *words,
+                          int B, int L, float *probs, void *stream);
+
+/* v2 greedy loop (test_score_dense_captions.py:216-225): start from [0], P-1 predictions.
+ *   tokens [B, P-1] int32; probs optional [B, P-1, V]. */
+int dc_decoder_v2_greedy(DcDecoder *dec, const void *feats, int feats_kind, int B,
+                         int32_t *tokens, float *probs, void *stream);
+
+/* Host-buffer forms (what Keras predict callers see): HOST pointers in and out, copies inside. */
+int dc_decoder_greedy_host(DcDecoder *dec, const float *feats, int feats_kind, int B,
+                           int32_t *tokens, float *probs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -427,101 +427,3 @@ def beam_v1(f, w, P, k, dtype=F32, start=1):
         out_tok[r, k - nb:] = np.array(caps, np.int32)
         out_sc[r, k - nb:] = scores
     return out_tok, out_sc
-
-
-# ----------------------------------------------------------------------------------------
-# synthetic weights in Keras layouts
-# ----------------------------------------------------------------------------------------
-
-def _glorot(rng, shape, fan_in, fan_out):
-    lim = np.sqrt(6.0 / (fan_in + fan_out))
-    return rng.uniform(-lim, lim, shape).astype(F32)
-
-
-def _orthogonal(rng, rows, cols):
-    """Keras 'orthogonal' recurrent initializer: QR of a Gaussian [rows, cols]."""
-    a = rng.standard_normal((max(rows, cols), max(rows, cols)))
-    q, r = np.linalg.qr(a)
-    q = q * np.sign(np.diag(r))
-    return q[:rows, :cols].astype(F32)
-
-
-def _lstm_weights(rng, n_in, u):
-    kern = _glorot(rng, (n_in, 4 * u), n_in, 4 * u)
-    rec = np.concatenate([_orthogonal(rng, u, u) for _ in range(4)], 1)
-    bias = np.zeros(4 * u, F32)
-    bias[u:2 * u] = 1.0                                   # unit_forget_bias
-    return kern, rec, bias
-
-
-def _head_weights(rng, pool=7, C=256, F=1024):
-    w = {}
-    w["mrcnn_class_conv1/kernel"] = _glorot(rng, (pool, pool, C, F), pool * pool * C, pool * pool * F)
-    # Keras conv fan computation uses receptive field * channels; scale so activations stay O(1)
-    w["mrcnn_class_conv1/kernel"] *= F32(np.sqrt((pool * pool * C + pool * pool * F) / (2.0 * pool * pool * C)))
-    w["mrcnn_class_conv1/bias"] = (0.1 * rng.standard_normal(F)).astype(F32)
-    w["mrcnn_class_conv2/kernel"] = _glorot(rng, (1, 1, F, F), F, F) * F32(1.5)
-    w["mrcnn_class_conv2/bias"] = (0.1 * rng.standard_normal(F)).astype(F32)
-    for bn in ("mrcnn_class_bn1", "mrcnn_class_bn2"):
-        w[bn + "/gamma"] = rng.uniform(0.9, 1.1, F).astype(F32)
-        w[bn + "/beta"] = rng.uniform(-0.1, 0.1, F).astype(F32)
-        w[bn + "/moving_mean"] = rng.uniform(-0.1, 0.1, F).astype(F32)
-        w[bn + "/moving_variance"] = rng.uniform(0.9, 1.1, F).astype(F32)
-    return w
-
-
-def _embedding(rng, V, E):
-    e = rng.uniform(-0.5, 0.5, (V, E)).astype(F32)
-    e[0] = 0.0                                            # preprocess.py:11 (<unk>/pad row)
-    return e
-
-
-def _vocab_bias(V, trained_like):
-    if not trained_like:
-        return np.zeros(V, F32)
-    # Zipfian unigram prior, as a trained captioner's output bias has (log frequency).
-    return (-np.log(1.0 + np.arange(V))).astype(F32)
-
-
-def synth_weights_v1(rng, V=10000, E=300, F=1024, U=512, pool=7, C=256, trained_like=True):
-    """Keras-ordered weights of build_lstm_model.  ``trained_like`` sharpens the output
-    distribution (logit temperature + Zipf bias) the way a trained captioner's is; plain
-    Glorot gives a near-uniform softmax whose argmax is decided by 1e-3-sized gaps."""
-    w = _head_weights(rng, pool, C, F)
-    w["imgcap_embedding_layer/embeddings"] = _embedding(rng, V, E)
-    (w["imgcap_lstm1/kernel"], w["imgcap_lstm1/recurrent_kernel"],
-     w["imgcap_lstm1/bias"]) = _lstm_weights(rng, E + F, U)
-    (w["imgcap_lstm2/kernel"], w["imgcap_lstm2/recurrent_kernel"],
-     w["imgcap_lstm2/bias"]) = _lstm_weights(rng, U, U)
-    w["imgcap_lstm_d1/kernel"] = _glorot(rng, (U + F, 1024), U + F, 1024)
-    w["imgcap_lstm_d1/bias"] = np.zeros(1024, F32)
-    w["imgcap_lstm_d2/kernel"] = _glorot(rng, (1024, V), 1024, V)
-    if trained_like:
-        w["imgcap_lstm_d2/kernel"] *= F32(12.0)
-    w["imgcap_lstm_d2/bias"] = _vocab_bias(V, trained_like)
-    return w
-
-
-def synth_weights_v2(rng, V=10000, E=300, F=1024, units=256, pool=7, C=256, trained_like=True):
-    """Keras-ordered weights of build_model(inject=True) (text_generation_model_v2.py:140-166)."""
-    w = _head_weights(rng, pool, C, F)
-    w["imgcap_embedding_layer/embeddings"] = _embedding(rng, V, E)
-    w["lstm_1/kernel"], w["lstm_1/recurrent_kernel"], w["lstm_1/bias"] = _lstm_weights(rng, E, 1024)
-    (w["imgcap_lstm/kernel"], w["imgcap_lstm/recurrent_kernel"],
-     w["imgcap_lstm/bias"]) = _lstm_weights(rng, F + 1024, units)
-    w["imgcap_d1/kernel"] = _glorot(rng, (units, V), units, V)
-    if trained_like:
-        w["imgcap_d1/kernel"] *= F32(12.0)
-    w["imgcap_d1/bias"] = _vocab_bias(V, trained_like)
-    return w
-
-
-def synth_captions(rng, B, P, V):
-    """[1, w.., 2, 0-pad]; length uniform 3..P including <start>/<end>; ids in [3,V)."""
-    gt = np.zeros((B, P), F32)
-    for i in range(B):
-        L = int(rng.integers(3, P + 1))
-        gt[i, 0] = 1
-        gt[i, 1:L - 1] = rng.integers(3, V, L - 2)
-        gt[i, L - 1] = 2
-    return gt

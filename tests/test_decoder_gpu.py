@@ -1,0 +1,149 @@
+"""GPU parity of the RoI head + inject-LSTM decoder (fp32 mode) against the CPU oracle, through
+the Keras-surface shims (build_lstm_model / build_model) which call the C ABI.
+Bars (north_star): greedy token ids bit-exact in fp32 mode; probabilities within 1e-4 relative
+(fp32 re-association only)."""
+import numpy as np
+import pytest
+import torch
+
+from image_captioning_b200 import synth
+from oracle import decoder as dec
+
+pytestmark = pytest.mark.gpu
+
+PROB_RTOL, PROB_ATOL = 2e-4, 1e-7
+
+
+def _model_v1(w, P, V, E, U, C, pool=7, batch_size=1, dtype="float32"):
+    import image_captioning_b200 as pkg
+    cfg = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], batch_size, P)
+    cfg.POOL_SIZE = pool
+    m = pkg.build_lstm_model([pool, pool, C], cfg, U, "inference", dtype=dtype)
+    m.set_weights(w)
+    return m
+
+
+def test_head_matches_oracle():
+    rng = np.random.default_rng(21)
+    w = synth.synth_weights_v1(rng, V=64, E=16, U=64, C=32)
+    feat = rng.standard_normal((37, 7, 7, 32)).astype(np.float32)
+    m = _model_v1(w, 5, 64, 16, 64, 32)
+    got = m.head_features(feat)
+    want = dec.head(feat, w)
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5)
+
+
+def test_greedy_v1_cfg1_bit_exact_tokens():
+    """BASELINE cfg1 decoder shapes: 100 RoIs, hidden 512, vocab 10k, embedding 300, P = 15."""
+    rng = np.random.default_rng(1001)
+    V, E, U, C, P, B = 10000, 300, 512, 256, 15, 100
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    feat = rng.standard_normal((B, 7, 7, C)).astype(np.float32)
+    m = _model_v1(w, P, V, E, U, C, batch_size=10)
+    tok_want, p_want = dec.greedy_v1(dec.head(feat, w), w, P)
+    probs = m.predict(feat, batch_size=10)
+    assert probs.shape == (B, P, V)
+    tok = m.generate(feat)
+    assert np.array_equal(probs.argmax(-1), tok)
+    assert np.array_equal(tok, tok_want), "greedy ids differ from the fp32 oracle"
+    np.testing.assert_allclose(probs, p_want, rtol=PROB_RTOL, atol=PROB_ATOL)
+    with pytest.raises(ValueError):
+        m.predict(feat[:7], batch_size=10)               # not a multiple of BATCH_SIZE
+
+
+def test_greedy_small_with_zero_token_paths():
+    """Small vocabulary with a strongly favoured id 0 so that masked steps occur mid-caption."""
+    rng = np.random.default_rng(22)
+    V, E, U, C, P, B = 40, 16, 64, 8, 8, 33
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    w["imgcap_lstm_d2/bias"][0] += 2.0
+    feat = rng.standard_normal((B, 7, 7, C)).astype(np.float32)
+    m = _model_v1(w, P, V, E, U, C)
+    tok_want, p_want = dec.greedy_v1(dec.head(feat, w), w, P)
+    assert (tok_want == 0).any()
+    tok, probs = m.generate(feat, return_probs=True)
+    assert np.array_equal(tok, tok_want)
+    np.testing.assert_allclose(probs, p_want, rtol=PROB_RTOL, atol=PROB_ATOL)
+    # literal O(P^2) form agrees too
+    lit = dec.greedy_v1_literal(dec.head(feat, w), w, P)
+    assert np.array_equal(lit.argmax(-1), tok)
+
+
+def test_head_feature_input_and_torch_io():
+    rng = np.random.default_rng(23)
+    V, E, U, C, P, B = 64, 16, 64, 8, 6, 10
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    feat = rng.standard_normal((B, 7, 7, C)).astype(np.float32)
+    m = _model_v1(w, P, V, E, U, C)
+    a = m.generate(feat)
+    hf = m.head_features(torch.from_numpy(feat).cuda())
+    assert hf.is_cuda
+    b = m.generate(hf)                                   # [B,1024] post-head vectors (cfg4 input form)
+    assert b.is_cuda and np.array_equal(a, b.cpu().numpy())
+
+
+def test_weights_roundtrip_and_errors(tmp_path):
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(24)
+    V, E, U, C, P = 48, 12, 64, 8, 5
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    m = _model_v1(w, P, V, E, U, C)
+    got = m.get_weights()
+    assert len(got) == 23
+    for n, a in zip(m.weight_names, got):
+        assert np.array_equal(a, w[n])
+    path = str(tmp_path / "w.npz")
+    m.save_weights(path)
+    cfg = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], 1, P)
+    m2 = pkg.build_lstm_model([7, 7, C], cfg, U, "inference")
+    with pytest.raises(RuntimeError):
+        m2.generate(np.zeros((1, 7, 7, C), np.float32))          # weights not set
+    m2.load_weights(path)
+    feat = rng.standard_normal((4, 7, 7, C)).astype(np.float32)
+    assert np.array_equal(m.generate(feat), m2.generate(feat))
+    with pytest.raises(ValueError):
+        m2.set_weights({"imgcap_lstm1/bias": np.zeros(3, np.float32)})
+    with pytest.raises(ValueError):
+        m2.generate(np.zeros((2, 5, 5, C), np.float32))
+
+
+def test_beam_matches_oracle():
+    rng = np.random.default_rng(25)
+    V, E, U, C, P, B, k = 200, 24, 64, 8, 7, 12, 3
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    feat = rng.standard_normal((B, 7, 7, C)).astype(np.float32)
+    m = _model_v1(w, P, V, E, U, C)
+    t_want, s_want = dec.beam_v1(dec.head(feat, w), w, P, k)
+    t, s = m.beam_search(feat, beam_width=k)
+    assert t.shape == (B, k, P) and s.shape == (B, k)
+    assert np.array_equal(t, t_want)
+    np.testing.assert_allclose(s, s_want, rtol=1e-5)
+    # width 1 == greedy
+    t1, _ = m.beam_search(feat, beam_width=1)
+    assert np.array_equal(t1[:, 0, 1:], m.generate(feat)[:, :P - 1])
+
+
+def test_v2_inject_predict_and_greedy():
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(26)
+    V, E, units, C, P, B = 300, 20, 64, 8, 10, 9
+    w = synth.synth_weights_v2(rng, V=V, E=E, units=units, C=C)
+    cfg = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], 1, P)
+    m = pkg.build_model((7, 7, C), (P,), cfg, units, inject=True)
+    m.set_weights(w)
+    feat = rng.standard_normal((B, 7, 7, C)).astype(np.float32)
+    words = np.zeros((B, P), np.int32)
+    for i in range(B):
+        L = int(rng.integers(0, P + 1))
+        words[i, P - L:] = rng.integers(1, V, L)
+    words[3, P - 2] = 0                                            # masked id inside the prefix
+    got = m.predict([feat, words])
+    want = dec.v2_inject_predict(feat, words, w)
+    np.testing.assert_allclose(got, want, rtol=PROB_RTOL, atol=PROB_ATOL)
+    tok_want, p_want = dec.greedy_v2(feat, w, P)
+    tok, probs = m.generate(feat, return_probs=True)
+    assert tok.shape == (B, P - 1)
+    assert np.array_equal(tok, tok_want)
+    np.testing.assert_allclose(probs, p_want, rtol=PROB_RTOL, atol=PROB_ATOL)
+    with pytest.raises(NotImplementedError):
+        pkg.build_model((7, 7, C), (P,), cfg, units, inject=False)
