@@ -52,10 +52,12 @@ def test_greedy_v1_cfg1_bit_exact_tokens():
 
 
 def test_greedy_small_with_zero_token_paths():
-    """Small vocabulary with a strongly favoured id 0 so that masked steps occur mid-caption."""
+    """Small vocabulary with a favoured id 0: once 0 is generated the step is masked, the state is
+    carried and 0 repeats (an absorbing state of the reference's greedy loop)."""
     rng = np.random.default_rng(22)
     V, E, U, C, P, B = 40, 16, 64, 8, 8, 33
-    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C, trained_like=False)
+    w["imgcap_lstm_d2/kernel"] *= 4
     w["imgcap_lstm_d2/bias"][0] += 2.0
     feat = rng.standard_normal((B, 7, 7, C)).astype(np.float32)
     m = _model_v1(w, P, V, E, U, C)
