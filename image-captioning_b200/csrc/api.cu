@@ -1,5 +1,7 @@
 // Error reporting and device introspection for libdcap.so.
 #include "common.cuh"
+#include "gemm.cuh"
+#include "gemm_tc.cuh"
 #include <string.h>
 
 namespace dcap {
@@ -37,4 +39,48 @@ extern "C" int dc_device_info(int *sm_count, int *compute_capability) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     return DC_OK;
+}
+
+using namespace dcap;
+
+extern "C" int dc_gemm_f32(const float *A, int64_t lda, int trans_a, const float *B, int64_t ldb, int trans_b,
+                           int M, int N, int K, const float *bias, const float *addend, int64_t ld_addend,
+                           int relu, int accumulate, float *C, int64_t ldc, void *stream) {
+    SgemmArgs g;
+    g.A = A; g.lda = (int)lda; g.B = B; g.ldb = (int)ldb; g.C = C; g.ldc = (int)ldc;
+    g.M = M; g.N = N; g.K = K; g.bias = bias; g.addend = addend; g.ld_addend = (int)ld_addend;
+    g.relu = relu; g.accumulate = accumulate;
+    return sgemm(g, trans_a != 0, trans_b != 0, (cudaStream_t)stream);
+}
+
+extern "C" int dc_gemm_bf16(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M, int N, int K,
+                            const float *bias, const float *addend, int64_t ld_addend, int relu,
+                            float *out_f32, int64_t ld_f32, uint16_t *out_bf16, int64_t ld_bf16, void *stream) {
+    TcOperand a, b;
+    a.ptr = reinterpret_cast<const __nv_bfloat16 *>(A); a.ld = lda;
+    b.ptr = reinterpret_cast<const __nv_bfloat16 *>(Bt); b.ld = ldb;
+    TcEpilogue ep;
+    ep.bias = bias; ep.addend = addend; ep.ld_addend = ld_addend; ep.relu = relu;
+    ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
+    ep.out_bf16 = reinterpret_cast<__nv_bfloat16 *>(out_bf16); ep.ld_bf16 = ld_bf16;
+    return gemm_bf16_tc(a, b, ep, M, N, K, kEpiStore, (cudaStream_t)stream);
+}
+
+extern "C" int dc_gemm_bf16_argmax(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M, int N,
+                                   int K, const float *bias, int32_t *tokens, float *maxprob, void *stream) {
+    if (M <= 0) return DC_OK;
+    DC_REQUIRE(tokens && bias, "null pointer argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int tiles = gemm_tc_argmax_tiles(N);
+    float *partial = nullptr;
+    DC_CHECK_CUDA(cudaMallocAsync((void **)&partial, sizeof(float) * 4 * (size_t)M * tiles, s));
+    TcOperand a, b;
+    a.ptr = reinterpret_cast<const __nv_bfloat16 *>(A); a.ld = lda;
+    b.ptr = reinterpret_cast<const __nv_bfloat16 *>(Bt); b.ld = ldb;
+    TcEpilogue ep;
+    ep.bias = bias; ep.partial = partial;
+    int rc = gemm_bf16_tc(a, b, ep, M, N, K, kEpiArgmax, s);
+    if (rc == DC_OK) rc = argmax_merge(partial, M, tiles, tokens, 1, nullptr, maxprob, s);
+    cudaFreeAsync(partial, s);
+    return rc;
 }

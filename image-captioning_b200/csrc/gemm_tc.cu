@@ -1,0 +1,449 @@
+// bf16 GEMM on the 5th-generation tensor cores (sm_100a): tcgen05.mma issued by one thread,
+// operands staged in shared memory by TMA (128-byte swizzle), fp32 accumulators in TMEM
+// (double buffered, so the epilogue of tile i overlaps the MMAs of tile i+1), persistent over
+// tiles with one CTA per SM.
+//
+//   D[M,N] = epilogue( A[M,K] * B[N,K]^T )        A, B bf16, K contiguous ("K-major") in both
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (each owns the 32 TMEM lanes 32*(warp%4)..+31, i.e. 32 rows of the tile).
+//
+// Epilogues
+//   kEpiStore : v = acc (+bias[n]) (+addend[m,n]); v = v*scale[n]+shift[n]; relu; store fp32 and/or
+//               bf16 (the bf16 copy is the next GEMM's A operand)
+//   kEpiArgmax: v = acc + bias[n]; per row and per N-tile (max, first arg-max, sum exp(v-max))
+//               -> partial[m, n_tile]; the [M,V] logits are never written (greedy decoding)
+//   kEpiTopK  : like kEpiArgmax but keeps the k best (value, index) pairs per row and tile
+#include "gemm_tc.cuh"
+
+#include <cuda.h>
+#include <map>
+#include <mutex>
+
+namespace dcap {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulation
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives TMEM lane (base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// descriptors
+// ------------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major operand tile [rows][64 bf16] written by TMA with
+// CU_TENSOR_MAP_SWIZZLE_128B: 8-row groups of 1024 B (stride-dimension byte offset = 1024),
+// leading-dimension offset unused for swizzled K-major (set to 1), version 1 (sm_100),
+// layout type 2 = SWIZZLE_128B.  Fields are in 16-byte units.
+__device__ __forceinline__ uint64_t make_smem_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address      bits [0,14)
+    d |= (uint64_t)1 << 16;                               // leading byte off.  bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte off.   bits [32,46)
+    d |= (uint64_t)1 << 46;                               // descriptor version bits [46,48)
+    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B       bits [61,64)
+    return d;
+}
+
+// Instruction descriptor for kind::f16: D fp32, A/B bf16, both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4)                        // c_format  = F32
+           | (1u << 7)                      // a_format  = BF16
+           | (1u << 10)                     // b_format  = BF16
+           | ((uint32_t)(N >> 3) << 17)     // n_dim
+           | ((uint32_t)(M >> 4) << 24);    // m_dim
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                 // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 192;
+
+template <int kBlockN>
+struct TcSmem {
+    static constexpr int kStageA = kBlockM * kBlockK * 2;
+    static constexpr int kStageB = kBlockN * kBlockK * 2;
+    static constexpr int kStages = (kBlockN == 256) ? 4 : 6;
+    static constexpr int kBytes = kStages * (kStageA + kStageB) + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int kBlockN, int kEpi>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const TcEpilogue ep, int M, int N, int K) {
+    using S = TcSmem<kBlockN>;
+    constexpr int kStages = S::kStages;
+    constexpr uint32_t kTmemCols = 2 * kBlockN;                  // two accumulator buffers (power of 2)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + kStages * S::kStageA;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * (S::kStageA + S::kStageB));
+    uint64_t *empty_bar = full_bar + kStages;
+    uint64_t *tmem_full = empty_bar + kStages;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_n = (N + kBlockN - 1) / kBlockN;
+    const int tiles_m = (M + kBlockM - 1) / kBlockM;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (K + kBlockK - 1) / kBlockK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * kBlockM, n0 = (tile % tiles_n) * kBlockN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], S::kStageA + S::kStageB);
+                    tma_load_2d(&map_a, &full_bar[stage], smem_a + stage * S::kStageA, kb * kBlockK, m0);
+                    tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * S::kStageB, kb * kBlockK, n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, kBlockN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);             // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kBlockN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);                // TMA bytes landed
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc_k_sw128(smem_u32(smem_a + stage * S::kStageA));
+                    const uint64_t b_desc = make_smem_desc_k_sw128(smem_u32(smem_b + stage * S::kStageB));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in 16-B units
+                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);                    // frees the smem slot when MMAs finish
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);                          // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quarter = warp & 3;                                  // TMEM lane quarter owned by this warp
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tile_n = tile % tiles_n;
+            const int m0 = (tile / tiles_n) * kBlockM, n0 = tile_n * kBlockN;
+            const int m = m0 + quarter * 32 + lane;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN;
+            if constexpr (kEpi == kEpiStore) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + c0, v);
+                    if (m < M && n0 + c0 < N) {
+                        const int n_base = n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = n_base + j;
+                            if (n < N) {
+                                float x = v[j];
+                                if (ep.bias) x += __ldg(ep.bias + n);
+                                if (ep.addend) x += __ldg(ep.addend + (long long)m * ep.ld_addend + n);
+                                if (ep.scale) x = x * __ldg(ep.scale + n) + __ldg(ep.shift + n);
+                                if (ep.relu) x = fmaxf(x, 0.f);
+                                v[j] = x;
+                            }
+                        }
+                        if (n_base + 32 <= N) {
+                            if (ep.out_f32) {
+                                float4 *o = reinterpret_cast<float4 *>(ep.out_f32 + (long long)m * ep.ld_f32 + n_base);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            }
+                            if (ep.out_bf16) {
+                                uint4 *o = reinterpret_cast<uint4 *>(ep.out_bf16 + (long long)m * ep.ld_bf16 + n_base);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+                                    __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+                                    __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                                    o[j] = make_uint4(*reinterpret_cast<uint32_t *>(&p0), *reinterpret_cast<uint32_t *>(&p1),
+                                                      *reinterpret_cast<uint32_t *>(&p2), *reinterpret_cast<uint32_t *>(&p3));
+                                }
+                            }
+                        } else {
+                            for (int j = 0; j < 32 && n_base + j < N; ++j) {
+                                if (ep.out_f32) ep.out_f32[(long long)m * ep.ld_f32 + n_base + j] = v[j];
+                                if (ep.out_bf16) ep.out_bf16[(long long)m * ep.ld_bf16 + n_base + j] = __float2bfloat16_rn(v[j]);
+                            }
+                        }
+                    }
+                }
+            } else {
+                // per-row statistics over this tile's columns: max, first arg-max, sum exp(v - max)
+                float best = -INFINITY, sum = 0.f;
+                int best_i = 0x7fffffff;
+#pragma unroll 1
+                for (int c0 = 0; c0 < kBlockN; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + c0, v);
+                    const int n_base = n0 + c0;
+                    if (n_base < N) {
+                        float cmax = -INFINITY;
+                        int ci = 0x7fffffff;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = n_base + j;
+                            const float x = (n < N) ? v[j] + __ldg(ep.bias + n) : -INFINITY;
+                            v[j] = x;
+                            if (x > cmax) { cmax = x; ci = n; }        // strict > keeps the first index
+                        }
+                        if (cmax > best) {
+                            sum *= __expf(best - cmax);
+                            best = cmax; best_i = ci;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sum += __expf(v[j] - best);
+                    }
+                }
+                if (m < M) {
+                    float4 *dst = reinterpret_cast<float4 *>(ep.partial) + (long long)m * tiles_n + tile_n;
+                    *dst = make_float4(best, __int_as_float(best_i), sum, 0.f);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols]
+int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(DC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    DC_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, "TMA operand must be 16-byte aligned with ld %% 8 == 0");
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(DC_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return DC_OK;
+}
+
+template <int kBlockN, int kEpi>
+static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcEpilogue &ep, int M, int N, int K,
+                     cudaStream_t stream) {
+    using S = TcSmem<kBlockN>;
+    static bool attr_set = false;
+    auto kern = gemm_bf16_tc_kernel<kBlockN, kEpi>;
+    if (!attr_set) {
+        DC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
+        attr_set = true;
+    }
+    const int tiles = ceil_div(M, kBlockM) * ceil_div(N, kBlockN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<grid, kThreads, S::kBytes, stream>>>(ma, mb, ep, M, N, K);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
+int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, int M, int N, int K, int epi,
+                 cudaStream_t stream) {
+    if (M <= 0 || N <= 0) return DC_OK;
+    DC_REQUIRE(K > 0 && A.ptr && B.ptr, "gemm_bf16_tc: bad arguments");
+    const bool wide = N > 128;
+    CUtensorMap ma, mb;
+    if (int rc = make_tmap_bf16(&ma, A.ptr, M, K, A.ld, kBlockM)) return rc;
+    if (int rc = make_tmap_bf16(&mb, B.ptr, N, K, B.ld, wide ? 256 : 128)) return rc;
+    if (epi == kEpiStore) {
+        DC_REQUIRE(ep.out_f32 || ep.out_bf16, "gemm_bf16_tc: no output");
+        DC_REQUIRE(!ep.out_f32 || (((uintptr_t)ep.out_f32 & 15) == 0 && ep.ld_f32 % 4 == 0), "fp32 output alignment");
+        DC_REQUIRE(!ep.out_bf16 || (((uintptr_t)ep.out_bf16 & 15) == 0 && ep.ld_bf16 % 8 == 0), "bf16 output alignment");
+        return wide ? launch_tc<256, kEpiStore>(ma, mb, ep, M, N, K, stream)
+                    : launch_tc<128, kEpiStore>(ma, mb, ep, M, N, K, stream);
+    }
+    DC_REQUIRE(epi == kEpiArgmax && ep.partial && ep.bias, "gemm_bf16_tc: arg-max epilogue needs bias and partial buffer");
+    return wide ? launch_tc<256, kEpiArgmax>(ma, mb, ep, M, N, K, stream)
+                : launch_tc<128, kEpiArgmax>(ma, mb, ep, M, N, K, stream);
+}
+
+int gemm_tc_argmax_tiles(int N) { return ceil_div(N, N > 128 ? 256 : 128); }
+
+// merge the per-tile partials: token = first arg-max over tiles; optional max probability
+__global__ void argmax_merge_kernel(const float4 *__restrict__ partial, int rows, int tiles,
+                                    int32_t *__restrict__ tok_out, int tok_stride, int32_t *__restrict__ tok_cur,
+                                    float *__restrict__ maxprob) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float best = -INFINITY, sum = 0.f;
+    int bi = 0x7fffffff;
+    for (int t = 0; t < tiles; ++t) {
+        const float4 p = __ldg(partial + (long long)r * tiles + t);
+        const int idx = __float_as_int(p.y);
+        if (p.x > best) {                       // tiles are visited in column order: strict > keeps the first
+            sum = sum * __expf(best - p.x) + p.z;
+            best = p.x; bi = idx;
+        } else {
+            sum += p.z * __expf(p.x - best);
+        }
+    }
+    if (tok_out) tok_out[(long long)r * tok_stride] = bi;
+    if (tok_cur) tok_cur[r] = bi;
+    if (maxprob) maxprob[r] = 1.0f / sum;
+}
+
+int argmax_merge(const float *partial, int rows, int tiles, int32_t *tok_out, int tok_stride, int32_t *tok_cur,
+                 float *maxprob, cudaStream_t s) {
+    if (rows <= 0) return DC_OK;
+    argmax_merge_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(reinterpret_cast<const float4 *>(partial), rows, tiles,
+                                                           tok_out, tok_stride, tok_cur, maxprob);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
+}  // namespace dcap

@@ -1,0 +1,34 @@
+// bf16 tcgen05 GEMM (see gemm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace dcap {
+
+constexpr int kEpiStore = 0;
+constexpr int kEpiArgmax = 1;
+
+struct TcOperand {
+    const __nv_bfloat16 *ptr = nullptr;   // [rows, K] row-major, K contiguous
+    long long ld = 0;                     // elements; multiple of 8
+};
+
+struct TcEpilogue {
+    const float *bias = nullptr;          // [N]
+    const float *addend = nullptr;        // [M, ld_addend] fp32
+    long long ld_addend = 0;
+    const float *scale = nullptr;         // [N] (with shift): frozen BatchNorm
+    const float *shift = nullptr;
+    int relu = 0;
+    float *out_f32 = nullptr; long long ld_f32 = 0;
+    __nv_bfloat16 *out_bf16 = nullptr; long long ld_bf16 = 0;
+    float *partial = nullptr;             // kEpiArgmax: [M, tiles_n] float4 {max, argmax bits, sumexp, -}
+};
+
+// D = epilogue(A * B^T): A [M,K], B [N,K], both bf16 K-major.
+int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, int M, int N, int K, int epi,
+                 cudaStream_t stream);
+int gemm_tc_argmax_tiles(int N);
+int argmax_merge(const float *partial, int rows, int tiles, int32_t *tok_out, int tok_stride, int32_t *tok_cur,
+                 float *maxprob, cudaStream_t s);
+
+}  // namespace dcap

@@ -1,0 +1,57 @@
+"""Thin torch-tensor wrappers over the exported GEMM primitives (dc_gemm_*); used by tests and
+tuning scripts.  The decoder calls the same kernels from C++."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _s(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def gemm_f32(a, b, trans_a=False, trans_b=False, bias=None, addend=None, relu=False, out=None, accumulate=False):
+    lib = _lib.load()
+    M = a.shape[1] if trans_a else a.shape[0]
+    K = a.shape[0] if trans_a else a.shape[1]
+    N = b.shape[0] if trans_b else b.shape[1]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.dc_gemm_f32(_p(a), a.stride(0), int(trans_a), _p(b), b.stride(0), int(trans_b), M, N, K,
+                                   _p(bias), _p(addend), addend.stride(0) if addend is not None else 0,
+                                   int(relu), int(accumulate), _p(out), out.stride(0), _s(a.device)))
+    return out
+
+
+def gemm_bf16(a, bt, bias=None, addend=None, relu=False, out_dtype=torch.float32):
+    """a [M,K] bf16, bt [N,K] bf16 (K contiguous) -> [M,N]."""
+    lib = _lib.load()
+    M, K = a.shape
+    N = bt.shape[0]
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    f32 = out if out_dtype == torch.float32 else None
+    b16 = out if out_dtype == torch.bfloat16 else None
+    with torch.cuda.device(a.device):
+        _lib.check(lib.dc_gemm_bf16(_p(a), a.stride(0), _p(bt), bt.stride(0), M, N, K, _p(bias), _p(addend),
+                                    addend.stride(0) if addend is not None else 0, int(relu),
+                                    _p(f32), N if f32 is not None else 0, _p(b16), N if b16 is not None else 0,
+                                    _s(a.device)))
+    return out
+
+
+def gemm_bf16_argmax(a, bt, bias, want_prob=False):
+    lib = _lib.load()
+    M, K = a.shape
+    N = bt.shape[0]
+    tok = torch.empty((M,), dtype=torch.int32, device=a.device)
+    prob = torch.empty((M,), dtype=torch.float32, device=a.device) if want_prob else None
+    with torch.cuda.device(a.device):
+        _lib.check(lib.dc_gemm_bf16_argmax(_p(a), a.stride(0), _p(bt), bt.stride(0), M, N, K, _p(bias), _p(tok),
+                                           _p(prob), _s(a.device)))
+    return (tok, prob) if want_prob else tok

@@ -182,6 +182,32 @@ int dc_decoder_v2_greedy(DcDecoder *dec, const void *feats, int feats_kind, int 
 int dc_decoder_greedy_host(DcDecoder *dec, const float *feats, int feats_kind, int B,
                            int32_t *tokens, float *probs);
 
+/* ------------------------------------------------------------------------------------------
+ * Dense contraction primitives (exported so that tests can pin the GEMM kernels in isolation;
+ * the decoder calls the same code).  They replace the MatMul ops behind KL.Dense / KL.LSTM /
+ * KL.Conv2D(valid, full-window) on this path (text_generation_model.py:141-154, 251-262).
+ * ---------------------------------------------------------------------------------------- */
+
+/* fp32 FFMA GEMM: C[M,N] = relu?(op(A)*op(B) + bias[n] + addend[m,n]); op = identity or transpose
+ * (trans_a: A stored [K,M]; trans_b: B stored [N,K]); accumulate != 0 adds to the existing C. */
+int dc_gemm_f32(const float *A, int64_t lda, int trans_a, const float *B, int64_t ldb, int trans_b,
+                int M, int N, int K, const float *bias, const float *addend, int64_t ld_addend,
+                int relu, int accumulate, float *C, int64_t ldc, void *stream);
+
+/* bf16 tcgen05 GEMM: D[M,N] = relu?(A[M,K] * Bt[N,K]^T + bias[n] + addend[m,n]) with fp32
+ * accumulation in TMEM.  A and Bt are bf16 bit patterns, K contiguous, lda/ldb multiples of 8.
+ * Writes fp32 and/or bf16 outputs (either may be NULL, not both). */
+int dc_gemm_bf16(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M, int N, int K,
+                 const float *bias, const float *addend, int64_t ld_addend, int relu,
+                 float *out_f32, int64_t ld_f32, uint16_t *out_bf16, int64_t ld_bf16, void *stream);
+
+/* bf16 tcgen05 GEMM with the fused arg-max epilogue (Dense(V) + softmax + tf.argmax of the greedy
+ * loop, text_generation_model.py:144,222-225): tokens[m] = first arg-max over n of
+ * (A*Bt^T + bias)[m,n]; maxprob[m] (optional) = its softmax probability.  The [M,N] logits are
+ * never written. */
+int dc_gemm_bf16_argmax(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M, int N,
+                        int K, const float *bias, int32_t *tokens, float *maxprob, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

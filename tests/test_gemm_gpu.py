@@ -1,0 +1,86 @@
+"""GPU numerics of the GEMM primitives against plain PyTorch references of the same op:
+fp32 FFMA GEMM vs torch fp64 matmul; bf16 tcgen05 GEMM vs torch matmul on the SAME bf16 inputs
+with fp32 accumulation (tolerance: fp32 re-association only, 1e-3 relative of the row scale)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, dtype=torch.float32):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(shape, device="cuda", generator=g).to(dtype)
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(100, 2048, 812, False, False), (257, 130, 300, False, False),
+                                         (64, 96, 40, True, False), (130, 70, 129, False, True),
+                                         (33, 65, 17, True, True), (1, 10000, 1024, False, False)])
+def test_sgemm_all_layouts(M, N, K, ta, tb):
+    from image_captioning_b200 import gemm
+    a = _rand((K, M) if ta else (M, K), 1)
+    b = _rand((N, K) if tb else (K, N), 2)
+    bias = _rand((N,), 3)
+    add = _rand((M, N), 4)
+    out = gemm.gemm_f32(a, b, ta, tb, bias=bias, addend=add, relu=True)
+    A = (a.t() if ta else a).double()
+    B = (b.t() if tb else b).double()
+    want = torch.relu(A @ B + bias.double() + add.double()).float()
+    torch.testing.assert_close(out, want, rtol=1e-4, atol=1e-4 * K ** 0.5)
+    acc = gemm.gemm_f32(a, b, ta, tb, out=out.clone(), accumulate=True)
+    torch.testing.assert_close(acc, (want.double() + A @ B).float(), rtol=1e-4, atol=2e-4 * K ** 0.5)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 128, 128), (8000, 2048, 832), (100, 1024, 512),
+                                   (777, 10000, 1024), (4096, 1024, 12544), (129, 72, 320), (5, 2048, 1024)])
+def test_tcgen05_gemm_store(M, N, K):
+    from image_captioning_b200 import gemm
+    a = _rand((M, K), 11, torch.bfloat16)
+    bt = _rand((N, K), 12, torch.bfloat16)
+    bias = _rand((N,), 13)
+    out = gemm.gemm_bf16(a, bt, bias=bias)
+    want = a.float() @ bt.float().t() + bias
+    scale = float(K) ** 0.5
+    torch.testing.assert_close(out, want, rtol=1e-3, atol=1e-3 * scale)
+    # relu + addend + bf16 output
+    add = _rand((M, N), 14)
+    out2 = gemm.gemm_bf16(a, bt, bias=bias, addend=add, relu=True, out_dtype=torch.bfloat16)
+    want2 = torch.relu(want + add).to(torch.bfloat16)
+    torch.testing.assert_close(out2.float(), want2.float(), rtol=2e-2, atol=2e-2 * scale)
+
+
+def test_tcgen05_gemm_strided_operands():
+    """A and the outputs are column slices of wider buffers (how the decoder's [emb|h] operand
+    buffers are laid out)."""
+    from image_captioning_b200 import gemm
+    M, N, K = 300, 512, 512
+    wide = _rand((M, 1024), 21, torch.bfloat16)
+    a = wide[:, 512:]
+    bt = _rand((N, K), 22, torch.bfloat16)
+    out = gemm.gemm_bf16(a, bt)
+    torch.testing.assert_close(out, a.float() @ bt.float().t(), rtol=1e-3, atol=3e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 10000, 1024), (130, 300, 128), (64, 128, 64)])
+def test_tcgen05_gemm_argmax_epilogue(M, N, K):
+    from image_captioning_b200 import gemm
+    a = _rand((M, K), 31, torch.bfloat16)
+    bt = _rand((N, K), 32, torch.bfloat16)
+    bias = _rand((N,), 33)
+    tok, prob = gemm.gemm_bf16_argmax(a, bt, bias, want_prob=True)
+    logits = gemm.gemm_bf16(a, bt, bias=bias)                   # same kernel, store epilogue
+    want = logits.argmax(-1).to(torch.int32)
+    # identical accumulation order in both epilogues -> identical arg-max
+    assert torch.equal(tok, want)
+    torch.testing.assert_close(prob, torch.softmax(logits, -1).max(-1).values, rtol=2e-3, atol=1e-6)
+
+
+def test_argmax_first_index_on_ties():
+    from image_captioning_b200 import gemm
+    M, N, K = 64, 600, 64
+    a = torch.zeros((M, K), device="cuda", dtype=torch.bfloat16)
+    bt = _rand((N, K), 41, torch.bfloat16)
+    bias = torch.zeros((N,), device="cuda")
+    bias[[17, 300, 555]] = 1.0                                   # three equal maxima in different tiles
+    tok = gemm.gemm_bf16_argmax(a, bt, bias)
+    assert bool((tok == 17).all())
