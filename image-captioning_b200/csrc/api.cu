@@ -79,8 +79,25 @@ extern "C" int dc_gemm_bf16_argmax(const uint16_t *A, int64_t lda, const uint16_
     b.ptr = reinterpret_cast<const __nv_bfloat16 *>(Bt); b.ld = ldb;
     TcEpilogue ep;
     ep.bias = bias; ep.partial = partial;
-    int rc = gemm_bf16_tc(a, b, ep, M, N, K, kEpiArgmax, s);
+    int rc = gemm_bf16_tc(a, b, ep, M, N, K, maxprob ? kEpiArgmaxSum : kEpiArgmax, s);
     if (rc == DC_OK) rc = argmax_merge(partial, M, tiles, tokens, 1, nullptr, maxprob, s);
     cudaFreeAsync(partial, s);
     return rc;
+}
+
+extern "C" int dc_gemm_bf16_lstm_cell(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M,
+                                      int units, int K, const float *addend, int64_t ld_addend,
+                                      const float *bias, const int32_t *tok, float *c,
+                                      const uint16_t *h_prev, int64_t ld_h_prev, uint16_t *h_out,
+                                      int64_t ld_h_out, uint16_t *h_out2, int64_t ld_h_out2, void *stream) {
+    TcOperand a, b;
+    a.ptr = reinterpret_cast<const __nv_bfloat16 *>(A); a.ld = lda;
+    b.ptr = reinterpret_cast<const __nv_bfloat16 *>(Bt); b.ld = ldb;
+    TcEpilogue ep;
+    ep.addend = addend; ep.ld_addend = ld_addend; ep.bias = bias;
+    ep.cell_c = c; ep.cell_units = units; ep.cell_tok = tok;
+    ep.cell_h_prev = reinterpret_cast<const __nv_bfloat16 *>(h_prev); ep.ld_h_prev = ld_h_prev;
+    ep.cell_h_a = reinterpret_cast<__nv_bfloat16 *>(h_out); ep.ld_h_a = ld_h_out;
+    ep.cell_h_b = reinterpret_cast<__nv_bfloat16 *>(h_out2); ep.ld_h_b = ld_h_out2;
+    return gemm_bf16_tc(a, b, ep, M, 4 * units, K, kEpiCell, (cudaStream_t)stream);
 }

@@ -79,6 +79,7 @@ void Decoder::declare_all() {
 }
 
 Decoder::~Decoder() {
+    free_bf16();
     for (auto &w : weights)
         if (w.dev) cudaFree(w.dev);
     for (void *p : owned) cudaFree(p);
@@ -305,6 +306,7 @@ int Decoder::beam(const void *feats, int kind, int B, int k, int32_t *tokens, do
     if (int rc = check_ready(B)) return rc;
     DC_REQUIRE(cfg.arch == DC_ARCH_V1, "dc_decoder_beam needs a v1 decoder");
     DC_REQUIRE(k >= 1 && k <= kMaxBeam, "beam width %d outside [1,%d]", k, kMaxBeam);
+    DC_REQUIRE(cfg.dtype == DC_DTYPE_F32, "beam search is served by the fp32 decoder in this build");
     if (B == 0) return DC_OK;
     DC_REQUIRE(feats && tokens && scores, "null pointer argument");
     const int R = B * k;

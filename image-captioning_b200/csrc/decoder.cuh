@@ -79,6 +79,7 @@ struct Decoder {
     int v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_t s);
     int greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s);
     int beam_gather_bf16(int R, int k, cudaStream_t s);
+    void free_bf16();
 };
 
 }  // namespace dcap

@@ -1,15 +1,219 @@
-// bf16 / tcgen05 decoder path (placeholder until gemm_tc.cu lands).
+// bf16 decoder path: every dense contraction runs on the tcgen05 GEMM (gemm_tc.cu) with bf16
+// operands and fp32 accumulation; LSTM cell state c, the hoisted per-RoI terms and all reductions
+// stay fp32.  Per decoding step (v1 word model, text_generation_model.py:130-156):
+//
+//   embed gather -> [gates1 GEMM + fused cell] -> [gates2 GEMM + fused cell]
+//                -> [dense1 GEMM + hoisted term + ReLU] -> [vocab GEMM + fused arg-max] -> merge
+//
+// Weights are re-laid once (finalize) as K-major bf16 [N, K]; LSTM kernels additionally with
+// gate-interleaved rows (row 4u+g) so that one epilogue thread sees the four gates of a unit.
+// h lives only as bf16 inside the next GEMM's operand buffers ([emb|h1] and [h1|h2], ping-pong
+// per step because the GEMM that consumes h_{t-1} also produces h_t).
 #include "decoder.cuh"
+#include "gemm_tc.cuh"
 
 namespace dcap {
-struct Bf16State {};
-static int unsupported() { return set_error(DC_ERR_UNSUPPORTED, "bf16 decoder path is not built yet"); }
-int Decoder::finalize_bf16(cudaStream_t) { return unsupported(); }
-int Decoder::reserve_bf16(size_t) { return unsupported(); }
-int Decoder::head_bf16(const void *, int, int, float *, cudaStream_t) { return unsupported(); }
-int Decoder::v1_hoist_bf16(int, cudaStream_t) { return unsupported(); }
-int Decoder::reset_state_bf16(int, cudaStream_t) { return unsupported(); }
-int Decoder::v1_step_bf16(int, const float *, const float *, cudaStream_t) { return unsupported(); }
-int Decoder::greedy_bf16(const void *, int, int, int32_t *, cudaStream_t) { return unsupported(); }
-int Decoder::beam_gather_bf16(int, int, cudaStream_t) { return unsupported(); }
+
+struct Bf16State {
+    // weights (bf16, K-major)
+    __nv_bfloat16 *w_head1 = nullptr, *w_head2 = nullptr;
+    __nv_bfloat16 *w1cat = nullptr, *w1f = nullptr, *w2cat = nullptr, *wd1h = nullptr, *wd1f = nullptr, *wd2 = nullptr;
+    float *b1_i = nullptr, *b2_i = nullptr;          // gate-interleaved LSTM biases
+    int Epad = 0;
+    // activations
+    __nv_bfloat16 *roi = nullptr, *a1 = nullptr, *Fb = nullptr, *d = nullptr;
+    __nv_bfloat16 *X1[2] = {nullptr, nullptr}, *X2[2] = {nullptr, nullptr};
+    float *partial = nullptr;
+    int parity = 0;
+};
+
+void Decoder::free_bf16() {
+    delete bf;
+    bf = nullptr;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// dst[n, k_off + k] = src[(row_off + k) * n_src + colmap(n)], colmap = gate interleave or identity
+__global__ void build_kmajor_kernel(const float *__restrict__ src, int n_src, int row_off, int K, int N,
+                                    int interleave_units, __nv_bfloat16 *__restrict__ dst, long long ld_dst,
+                                    int k_off) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)N * K) return;
+    const int n = (int)(idx / K), k = (int)(idx - (long long)n * K);
+    const int col = interleave_units ? (n & 3) * interleave_units + (n >> 2) : n;
+    dst[(long long)n * ld_dst + k_off + k] = __float2bfloat16_rn(src[(long long)(row_off + k) * n_src + col]);
+}
+
+__global__ void interleave_bias_kernel(const float *__restrict__ src, int units, float *__restrict__ dst) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < 4 * units) dst[n] = src[(n & 3) * units + (n >> 2)];
+}
+
+static int build_kmajor(const float *src, int n_src, int row_off, int K, int N, int interleave_units,
+                        __nv_bfloat16 *dst, long long ld_dst, int k_off, cudaStream_t s) {
+    const long long total = (long long)N * K;
+    build_kmajor_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, s>>>(src, n_src, row_off, K, N,
+                                                                                   interleave_units, dst, ld_dst, k_off);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
+int Decoder::finalize_bf16(cudaStream_t s) {
+    if (!bf) bf = new Bf16State();
+    Bf16State &b = *bf;
+    const int F = cfg.feat, E = cfg.embed, U = cfg.units, V = cfg.vocab;
+    const int Kin = cfg.pool * cfg.pool * cfg.channels;
+    b.Epad = round_up(E, 64);
+    const int K1 = b.Epad + U;
+    auto A16 = [&](__nv_bfloat16 **p, size_t n) { return dev_alloc((void **)p, 2 * n, owned); };
+    int rc = 0;
+    rc |= A16(&b.w_head1, (size_t)F * Kin); rc |= A16(&b.w_head2, (size_t)F * F);
+    rc |= A16(&b.w1cat, (size_t)4 * U * K1); rc |= A16(&b.w1f, (size_t)4 * U * F);
+    rc |= A16(&b.w2cat, (size_t)4 * U * 2 * U);
+    rc |= A16(&b.wd1h, (size_t)kDense * U); rc |= A16(&b.wd1f, (size_t)kDense * F);
+    rc |= A16(&b.wd2, (size_t)V * kDense);
+    rc |= dev_alloc((void **)&b.b1_i, sizeof(float) * 4 * U, owned);
+    rc |= dev_alloc((void **)&b.b2_i, sizeof(float) * 4 * U, owned);
+    if (rc) return rc;
+    DC_CHECK_CUDA(cudaMemsetAsync(b.w1cat, 0, 2 * (size_t)4 * U * K1, s));      // zero the E..Epad padding
+    rc |= build_kmajor(W("mrcnn_class_conv1/kernel"), F, 0, Kin, F, 0, b.w_head1, Kin, 0, s);
+    rc |= build_kmajor(W("mrcnn_class_conv2/kernel"), F, 0, F, F, 0, b.w_head2, F, 0, s);
+    rc |= build_kmajor(W("imgcap_lstm1/kernel"), 4 * U, 0, E, 4 * U, U, b.w1cat, K1, 0, s);
+    rc |= build_kmajor(W("imgcap_lstm1/recurrent_kernel"), 4 * U, 0, U, 4 * U, U, b.w1cat, K1, b.Epad, s);
+    rc |= build_kmajor(W("imgcap_lstm1/kernel"), 4 * U, E, F, 4 * U, U, b.w1f, F, 0, s);
+    rc |= build_kmajor(W("imgcap_lstm2/kernel"), 4 * U, 0, U, 4 * U, U, b.w2cat, 2 * U, 0, s);
+    rc |= build_kmajor(W("imgcap_lstm2/recurrent_kernel"), 4 * U, 0, U, 4 * U, U, b.w2cat, 2 * U, U, s);
+    rc |= build_kmajor(W("imgcap_lstm_d1/kernel"), kDense, 0, U, kDense, 0, b.wd1h, U, 0, s);
+    rc |= build_kmajor(W("imgcap_lstm_d1/kernel"), kDense, U, F, kDense, 0, b.wd1f, F, 0, s);
+    rc |= build_kmajor(W("imgcap_lstm_d2/kernel"), V, 0, kDense, V, 0, b.wd2, kDense, 0, s);
+    if (rc) return rc;
+    interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm1/bias"), U, b.b1_i);
+    interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm2/bias"), U, b.b2_i);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
+int Decoder::reserve_bf16(size_t R) {
+    Bf16State &b = *bf;
+    const size_t F = cfg.feat, U = cfg.units;
+    const size_t Kin = (size_t)cfg.pool * cfg.pool * cfg.channels;
+    const size_t K1 = b.Epad + U;
+    auto A16 = [&](__nv_bfloat16 **p, size_t n) { return dev_alloc((void **)p, 2 * n, ws_owned); };
+    int rc = 0;
+    rc |= A16(&b.roi, R * Kin); rc |= A16(&b.a1, R * F); rc |= A16(&b.Fb, R * F); rc |= A16(&b.d, R * kDense);
+    for (int i = 0; i < 2; ++i) { rc |= A16(&b.X1[i], R * K1); rc |= A16(&b.X2[i], R * 2 * U); }
+    rc |= dev_alloc((void **)&b.partial, sizeof(float) * 4 * R * gemm_tc_argmax_tiles(cfg.vocab), ws_owned);
+    return rc;
+}
+
+static TcOperand op(const __nv_bfloat16 *p, long long ld) {
+    TcOperand o;
+    o.ptr = p; o.ld = ld;
+    return o;
+}
+
+int Decoder::head_bf16(const void *feats, int kind, int B, float *out, cudaStream_t s) {
+    Bf16State &b = *bf;
+    const int F = cfg.feat, Kin = cfg.pool * cfg.pool * cfg.channels;
+    const __nv_bfloat16 *x = nullptr;
+    if (kind == DC_FEATS_ROI_BF16) {
+        x = reinterpret_cast<const __nv_bfloat16 *>(feats);
+    } else {
+        DC_REQUIRE(kind == DC_FEATS_ROI_F32, "unknown feats_kind %d", kind);
+        if (int rc = f32_to_bf16((const float *)feats, b.roi, (long long)B * Kin, s)) return rc;
+        x = b.roi;
+    }
+    TcEpilogue e1;
+    e1.bias = W("mrcnn_class_conv1/bias"); e1.scale = bn_scale[0]; e1.shift = bn_shift[0]; e1.relu = 1;
+    e1.out_bf16 = b.a1; e1.ld_bf16 = F;
+    if (int rc = gemm_bf16_tc(op(x, Kin), op(b.w_head1, Kin), e1, B, F, Kin, kEpiStore, s)) return rc;
+    TcEpilogue e2;
+    e2.bias = W("mrcnn_class_conv2/bias"); e2.scale = bn_scale[1]; e2.shift = bn_shift[1]; e2.relu = 1;
+    e2.out_bf16 = b.Fb; e2.ld_bf16 = F;
+    e2.out_f32 = out; e2.ld_f32 = F;
+    return gemm_bf16_tc(op(b.a1, F), op(b.w_head2, F), e2, B, F, F, kEpiStore, s);
+}
+
+int Decoder::v1_hoist_bf16(int B, cudaStream_t s) {
+    Bf16State &b = *bf;
+    const int F = cfg.feat, U = cfg.units;
+    // ws.F (fp32) may have come from the caller (DC_FEATS_HEAD_F32): refresh the bf16 operand copy
+    if (int rc = f32_to_bf16(ws.F, b.Fb, (long long)B * F, s)) return rc;
+    TcEpilogue e1;
+    e1.bias = b.b1_i; e1.out_f32 = ws.g1f; e1.ld_f32 = 4 * U;                  // gate-interleaved columns
+    if (int rc = gemm_bf16_tc(op(b.Fb, F), op(b.w1f, F), e1, B, 4 * U, F, kEpiStore, s)) return rc;
+    TcEpilogue e2;
+    e2.bias = W("imgcap_lstm_d1/bias"); e2.out_f32 = ws.d1f; e2.ld_f32 = kDense;
+    return gemm_bf16_tc(op(b.Fb, F), op(b.wd1f, F), e2, B, kDense, F, kEpiStore, s);
+}
+
+int Decoder::reset_state_bf16(int R, cudaStream_t s) {
+    Bf16State &b = *bf;
+    const size_t U = cfg.units, K1 = b.Epad + U;
+    for (int i = 0; i < 2; ++i) {
+        DC_CHECK_CUDA(cudaMemsetAsync(b.X1[i], 0, 2 * (size_t)R * K1, s));
+        DC_CHECK_CUDA(cudaMemsetAsync(b.X2[i], 0, 2 * (size_t)R * 2 * U, s));
+    }
+    b.parity = 0;
+    return DC_OK;
+}
+
+// the three GEMMs up to the Dense(1024) activations; leaves d (bf16) ready for the vocab GEMM
+static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, cudaStream_t s) {
+    Bf16State &b = *D.bf;
+    const DcDecoderConfig &cfg = D.cfg;
+    const int E = cfg.embed, U = cfg.units, V = cfg.vocab, K1 = b.Epad + U, p = b.parity;
+    if (int rc = embed_gather(D.W("imgcap_embedding_layer/embeddings"), D.ws.tok, R, E, V, b.X1[p], K1, true, s)) return rc;
+    TcEpilogue c1;
+    c1.addend = g1f; c1.ld_addend = 4 * U; c1.cell_c = D.ws.c1; c1.cell_units = U; c1.cell_tok = D.ws.tok;
+    c1.cell_h_prev = b.X1[p] + b.Epad; c1.ld_h_prev = K1;
+    c1.cell_h_a = b.X1[p ^ 1] + b.Epad; c1.ld_h_a = K1;
+    c1.cell_h_b = b.X2[p]; c1.ld_h_b = 2 * U;
+    if (int rc = gemm_bf16_tc(op(b.X1[p], K1), op(b.w1cat, K1), c1, R, 4 * U, K1, kEpiCell, s)) return rc;
+    TcEpilogue c2;
+    c2.bias = b.b2_i; c2.cell_c = D.ws.c2; c2.cell_units = U; c2.cell_tok = D.ws.tok;
+    c2.cell_h_prev = b.X2[p] + U; c2.ld_h_prev = 2 * U;
+    c2.cell_h_a = b.X2[p ^ 1] + U; c2.ld_h_a = 2 * U;
+    if (int rc = gemm_bf16_tc(op(b.X2[p], 2 * U), op(b.w2cat, 2 * U), c2, R, 4 * U, 2 * U, kEpiCell, s)) return rc;
+    TcEpilogue d1;
+    d1.addend = d1f; d1.ld_addend = kDense; d1.relu = 1; d1.out_bf16 = b.d; d1.ld_bf16 = kDense;
+    if (int rc = gemm_bf16_tc(op(b.X2[p ^ 1] + U, 2 * U), op(b.wd1h, U), d1, R, kDense, U, kEpiStore, s)) return rc;
+    b.parity ^= 1;
+    return DC_OK;
+}
+
+// generic step (predict surface / beam): logits are materialised in ws.logits (fp32)
+int Decoder::v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_t s) {
+    if (int rc = step_core(*this, R, g1f, d1f, s)) return rc;
+    TcEpilogue e;
+    e.bias = W("imgcap_lstm_d2/bias"); e.out_f32 = ws.logits; e.ld_f32 = cfg.vocab;
+    return gemm_bf16_tc(op(bf->d, kDense), op(bf->wd2, kDense), e, R, cfg.vocab, kDense, kEpiStore, s);
+}
+
+// greedy fast path: tokens only, the [B,V] logits never exist
+int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s) {
+    const int P = cfg.padding, V = cfg.vocab;
+    if (int rc = head(feats, kind, B, ws.F, s)) return rc;
+    if (int rc = v1_hoist(B, s)) return rc;
+    if (int rc = v1_reset_state(B, s)) return rc;
+    if (int rc = fill_i32(ws.tok, B, 1, s)) return rc;
+    const int slots = gemm_tc_argmax_tiles(V);
+    for (int t = 0; t < P; ++t) {
+        if (int rc = step_core(*this, B, ws.g1f, ws.d1f, s)) return rc;
+        TcEpilogue e;
+        e.bias = W("imgcap_lstm_d2/bias"); e.partial = bf->partial;
+        if (int rc = gemm_bf16_tc(op(bf->d, kDense), op(bf->wd2, kDense), e, B, V, kDense, kEpiArgmax, s)) return rc;
+        if (int rc = argmax_merge(bf->partial, B, slots, tokens + t, P, ws.tok, nullptr, s)) return rc;
+    }
+    return DC_OK;
+}
+
+// beam search keeps its state permutation on the fp32 buffers; mirror it on the bf16 operand
+// buffers (h1 inside X1, [h1|h2] inside X2)
+int Decoder::beam_gather_bf16(int R, int k, cudaStream_t s) {
+    (void)R; (void)k; (void)s;
+    return set_error(DC_ERR_UNSUPPORTED, "beam search is served by the fp32 decoder in this build");
+}
+
 }  // namespace dcap

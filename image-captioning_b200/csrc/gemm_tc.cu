@@ -142,15 +142,200 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                // 2 per TMEM lane quarter: each owns half of the tile's columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kStageLd = 20;                // floats per staging row (16 columns + pad; 16-byte aligned)
 
 template <int kBlockN>
 struct TcSmem {
     static constexpr int kStageA = kBlockM * kBlockK * 2;
     static constexpr int kStageB = kBlockN * kBlockK * 2;
     static constexpr int kStages = (kBlockN == 256) ? 4 : 6;
-    static constexpr int kBytes = kStages * (kStageA + kStageB) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kStaging = kEpiWarps * 32 * kStageLd * 4;
+    static constexpr int kBytes = kStages * (kStageA + kStageB) + kStaging + 1024 /*align*/ + 256 /*barriers*/;
 };
+
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float hard_sigmoid_tc(float x) {
+    return fminf(fmaxf(__fadd_rn(__fmul_rn(0.2f, x), 0.5f), 0.f), 1.f);
+}
+
+// Epilogue of one (warp, column-half) region: rows = the warp's 32 TMEM lanes, columns
+// [col_begin, col_begin + kCols) of the tile.  Accumulators are pulled 16 columns at a time and,
+// for the storing epilogues, transposed through a warp-private padded shared-memory slab so that
+// global accesses are row-contiguous (4 lanes x 16 B per row, 8 rows per instruction).
+template <int kCols, int kEpi>
+__device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t taddr, float *stage, int lane,
+                                                int m_base, int n_base, int M, int N, int part_slot,
+                                                int part_slots) {
+    if constexpr (kEpi == kEpiArgmax || kEpi == kEpiArgmaxSum) {
+        // per-row statistics over this region: max, first arg-max (, sum exp(v - max))
+        float best = -INFINITY, sum = 0.f;
+        int best_i = 0x7fffffff;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kCols; c0 += 32) {
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+            const int nb = n_base + c0;
+            if (nb < N) {
+                float cmax = -INFINITY;
+                int ci = 0x7fffffff;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = nb + j;
+                    const float x = (n < N) ? v[j] + __ldg(ep.bias + n) : -INFINITY;
+                    v[j] = x;
+                    if (x > cmax) { cmax = x; ci = n; }            // strict > keeps the first index
+                }
+                if constexpr (kEpi == kEpiArgmaxSum) {
+                    if (cmax > best) sum *= __expf(best - cmax);
+                }
+                if (cmax > best) { best = cmax; best_i = ci; }
+                if constexpr (kEpi == kEpiArgmaxSum) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum += __expf(v[j] - best);
+                }
+            }
+        }
+        const int m = m_base + lane;
+        if (m < M) {
+            float4 *dst = reinterpret_cast<float4 *>(ep.partial) + (long long)m * part_slots + part_slot;
+            *dst = make_float4(best, __int_as_float(best_i), sum, 0.f);
+        }
+    } else {
+        const int sub_row = lane >> 2, colq = lane & 3;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kCols; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr + c0, v);
+            const int nb = n_base + c0;
+            if (nb >= N) continue;                                   // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4 *>(stage + lane * kStageLd + 4 * j) =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int n = nb + 4 * colq;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int row = it * 8 + sub_row;
+                const int m = m_base + row;
+                float4 x = *reinterpret_cast<const float4 *>(stage + row * kStageLd + 4 * colq);
+                if constexpr (kEpi == kEpiStore) {
+                    if (m < M && n < N) {
+                        const bool full = n + 4 <= N;
+                        float xs[4] = {x.x, x.y, x.z, x.w};
+                        if (full) {
+                            if (ep.bias) {
+                                const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.bias + n));
+                                xs[0] += t.x; xs[1] += t.y; xs[2] += t.z; xs[3] += t.w;
+                            }
+                            if (ep.addend) {
+                                const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.addend + (long long)m * ep.ld_addend + n));
+                                xs[0] += t.x; xs[1] += t.y; xs[2] += t.z; xs[3] += t.w;
+                            }
+                            if (ep.scale) {
+                                const float4 sc = __ldg(reinterpret_cast<const float4 *>(ep.scale + n));
+                                const float4 sh = __ldg(reinterpret_cast<const float4 *>(ep.shift + n));
+                                xs[0] = xs[0] * sc.x + sh.x; xs[1] = xs[1] * sc.y + sh.y;
+                                xs[2] = xs[2] * sc.z + sh.z; xs[3] = xs[3] * sc.w + sh.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (n + j < N) {
+                                    if (ep.bias) xs[j] += __ldg(ep.bias + n + j);
+                                    if (ep.addend) xs[j] += __ldg(ep.addend + (long long)m * ep.ld_addend + n + j);
+                                    if (ep.scale) xs[j] = xs[j] * __ldg(ep.scale + n + j) + __ldg(ep.shift + n + j);
+                                }
+                            }
+                        }
+                        if (ep.relu) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) xs[j] = fmaxf(xs[j], 0.f);
+                        }
+                        if (full) {
+                            if (ep.out_f32)
+                                *reinterpret_cast<float4 *>(ep.out_f32 + (long long)m * ep.ld_f32 + n) =
+                                    make_float4(xs[0], xs[1], xs[2], xs[3]);
+                            if (ep.out_bf16) {
+                                __nv_bfloat162 p0 = __floats2bfloat162_rn(xs[0], xs[1]);
+                                __nv_bfloat162 p1 = __floats2bfloat162_rn(xs[2], xs[3]);
+                                *reinterpret_cast<uint2 *>(ep.out_bf16 + (long long)m * ep.ld_bf16 + n) =
+                                    make_uint2(*reinterpret_cast<uint32_t *>(&p0), *reinterpret_cast<uint32_t *>(&p1));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (n + j < N) {
+                                    if (ep.out_f32) ep.out_f32[(long long)m * ep.ld_f32 + n + j] = xs[j];
+                                    if (ep.out_bf16) ep.out_bf16[(long long)m * ep.ld_bf16 + n + j] = __float2bfloat16_rn(xs[j]);
+                                }
+                            }
+                        }
+                    }
+                } else {   // kEpiCell: columns are gate-interleaved, this lane holds (i,f,g,o) of one unit
+                    const int u = n >> 2;
+                    float c_new = 0.f, h_new = 0.f;
+                    const bool valid = m < M;                         // N is a multiple of 4 units by construction
+                    if (valid) {
+                        float4 z = x;
+                        if (ep.addend) {
+                            const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.addend + (long long)m * ep.ld_addend + n));
+                            z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w;
+                        }
+                        if (ep.bias) {
+                            const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.bias + n));
+                            z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w;
+                        }
+                        const float c_old = ep.cell_c[(long long)m * ep.cell_units + u];
+                        const bool masked = ep.cell_tok && __ldg(ep.cell_tok + m) == 0;
+                        if (masked) {                                // K.rnn mask: carry (h, c)
+                            c_new = c_old;
+                            h_new = __bfloat162float(ep.cell_h_prev[(long long)m * ep.ld_h_prev + u]);
+                        } else {
+                            const float ig = hard_sigmoid_tc(z.x), fg = hard_sigmoid_tc(z.y);
+                            const float gg = tanhf(z.z), og = hard_sigmoid_tc(z.w);
+                            c_new = __fadd_rn(__fmul_rn(fg, c_old), __fmul_rn(ig, gg));
+                            h_new = __fmul_rn(og, tanhf(c_new));
+                        }
+                    }
+                    // gather the 4 units of this row-chunk into the colq==0 lane: 16-B / 8-B stores
+                    float cq[4], hq[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        cq[j] = __shfl_sync(0xffffffffu, c_new, (lane & ~3) + j);
+                        hq[j] = __shfl_sync(0xffffffffu, h_new, (lane & ~3) + j);
+                    }
+                    if (valid && colq == 0) {
+                        const int u0 = nb >> 2;
+                        *reinterpret_cast<float4 *>(ep.cell_c + (long long)m * ep.cell_units + u0) =
+                            make_float4(cq[0], cq[1], cq[2], cq[3]);
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(hq[0], hq[1]);
+                        __nv_bfloat162 p1 = __floats2bfloat162_rn(hq[2], hq[3]);
+                        const uint2 hv = make_uint2(*reinterpret_cast<uint32_t *>(&p0), *reinterpret_cast<uint32_t *>(&p1));
+                        if (ep.cell_h_a) *reinterpret_cast<uint2 *>(ep.cell_h_a + (long long)m * ep.ld_h_a + u0) = hv;
+                        if (ep.cell_h_b) *reinterpret_cast<uint2 *>(ep.cell_h_b + (long long)m * ep.ld_h_b + u0) = hv;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
 
 template <int kBlockN, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -163,7 +348,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + kStages * S::kStageA;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * (S::kStageA + S::kStageB));
+    float *staging = reinterpret_cast<float *>(smem + kStages * (S::kStageA + S::kStageB));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * (S::kStageA + S::kStageB) + S::kStaging);
     uint64_t *empty_bar = full_bar + kStages;
     uint64_t *tmem_full = empty_bar + kStages;
     uint64_t *tmem_empty = tmem_full + 2;
@@ -179,7 +365,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -237,94 +423,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         __syncwarp();
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int quarter = warp & 3;                                  // TMEM lane quarter owned by this warp
+        // ===================== epilogue (warps 2..9) =====================
+        const int e = warp - 2;
+        const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int half = e >> 2;                                       // which half of the tile's columns
+        constexpr int kCols = kBlockN / 2;
+        float *stage_w = staging + e * 32 * kStageLd;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int tile_n = tile % tiles_n;
             const int m0 = (tile / tiles_n) * kBlockM, n0 = tile_n * kBlockN;
-            const int m = m0 + quarter * 32 + lane;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN;
-            if constexpr (kEpi == kEpiStore) {
-#pragma unroll 1
-                for (int c0 = 0; c0 < kBlockN; c0 += 32) {
-                    float v[32];
-                    tmem_ld32(taddr + c0, v);
-                    if (m < M && n0 + c0 < N) {
-                        const int n_base = n0 + c0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = n_base + j;
-                            if (n < N) {
-                                float x = v[j];
-                                if (ep.bias) x += __ldg(ep.bias + n);
-                                if (ep.addend) x += __ldg(ep.addend + (long long)m * ep.ld_addend + n);
-                                if (ep.scale) x = x * __ldg(ep.scale + n) + __ldg(ep.shift + n);
-                                if (ep.relu) x = fmaxf(x, 0.f);
-                                v[j] = x;
-                            }
-                        }
-                        if (n_base + 32 <= N) {
-                            if (ep.out_f32) {
-                                float4 *o = reinterpret_cast<float4 *>(ep.out_f32 + (long long)m * ep.ld_f32 + n_base);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            }
-                            if (ep.out_bf16) {
-                                uint4 *o = reinterpret_cast<uint4 *>(ep.out_bf16 + (long long)m * ep.ld_bf16 + n_base);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-                                    __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-                                    __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                                    o[j] = make_uint4(*reinterpret_cast<uint32_t *>(&p0), *reinterpret_cast<uint32_t *>(&p1),
-                                                      *reinterpret_cast<uint32_t *>(&p2), *reinterpret_cast<uint32_t *>(&p3));
-                                }
-                            }
-                        } else {
-                            for (int j = 0; j < 32 && n_base + j < N; ++j) {
-                                if (ep.out_f32) ep.out_f32[(long long)m * ep.ld_f32 + n_base + j] = v[j];
-                                if (ep.out_bf16) ep.out_bf16[(long long)m * ep.ld_bf16 + n_base + j] = __float2bfloat16_rn(v[j]);
-                            }
-                        }
-                    }
-                }
-            } else {
-                // per-row statistics over this tile's columns: max, first arg-max, sum exp(v - max)
-                float best = -INFINITY, sum = 0.f;
-                int best_i = 0x7fffffff;
-#pragma unroll 1
-                for (int c0 = 0; c0 < kBlockN; c0 += 32) {
-                    float v[32];
-                    tmem_ld32(taddr + c0, v);
-                    const int n_base = n0 + c0;
-                    if (n_base < N) {
-                        float cmax = -INFINITY;
-                        int ci = 0x7fffffff;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int n = n_base + j;
-                            const float x = (n < N) ? v[j] + __ldg(ep.bias + n) : -INFINITY;
-                            v[j] = x;
-                            if (x > cmax) { cmax = x; ci = n; }        // strict > keeps the first index
-                        }
-                        if (cmax > best) {
-                            sum *= __expf(best - cmax);
-                            best = cmax; best_i = ci;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) sum += __expf(v[j] - best);
-                    }
-                }
-                if (m < M) {
-                    float4 *dst = reinterpret_cast<float4 *>(ep.partial) + (long long)m * tiles_n + tile_n;
-                    *dst = make_float4(best, __int_as_float(best_i), sum, 0.f);
-                }
-            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * kCols;
+            epilogue_region<kCols, kEpi>(ep, taddr, stage_w, lane, m0 + quarter * 32, n0 + half * kCols, M, N,
+                                         tile_n * 2 + half, tiles_n * 2);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -403,16 +517,29 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
     if (epi == kEpiStore) {
         DC_REQUIRE(ep.out_f32 || ep.out_bf16, "gemm_bf16_tc: no output");
         DC_REQUIRE(!ep.out_f32 || (((uintptr_t)ep.out_f32 & 15) == 0 && ep.ld_f32 % 4 == 0), "fp32 output alignment");
-        DC_REQUIRE(!ep.out_bf16 || (((uintptr_t)ep.out_bf16 & 15) == 0 && ep.ld_bf16 % 8 == 0), "bf16 output alignment");
+        DC_REQUIRE(!ep.out_bf16 || (((uintptr_t)ep.out_bf16 & 7) == 0 && ep.ld_bf16 % 4 == 0), "bf16 output alignment");
+        DC_REQUIRE(!ep.addend || (((uintptr_t)ep.addend & 15) == 0 && ep.ld_addend % 4 == 0), "addend alignment");
         return wide ? launch_tc<256, kEpiStore>(ma, mb, ep, M, N, K, stream)
                     : launch_tc<128, kEpiStore>(ma, mb, ep, M, N, K, stream);
     }
-    DC_REQUIRE(epi == kEpiArgmax && ep.partial && ep.bias, "gemm_bf16_tc: arg-max epilogue needs bias and partial buffer");
-    return wide ? launch_tc<256, kEpiArgmax>(ma, mb, ep, M, N, K, stream)
-                : launch_tc<128, kEpiArgmax>(ma, mb, ep, M, N, K, stream);
+    if (epi == kEpiCell) {
+        DC_REQUIRE(ep.cell_c && ep.cell_units * 4 == N && N % 16 == 0, "cell epilogue: N must be 4*units, units %% 4 == 0");
+        DC_REQUIRE(!ep.cell_tok || ep.cell_h_prev, "cell epilogue: masking needs the previous h");
+        DC_REQUIRE(!ep.addend || (((uintptr_t)ep.addend & 15) == 0 && ep.ld_addend % 4 == 0), "addend alignment");
+        DC_REQUIRE((!ep.cell_h_a || ep.ld_h_a % 4 == 0) && (!ep.cell_h_b || ep.ld_h_b % 4 == 0), "h destination alignment");
+        return wide ? launch_tc<256, kEpiCell>(ma, mb, ep, M, N, K, stream)
+                    : launch_tc<128, kEpiCell>(ma, mb, ep, M, N, K, stream);
+    }
+    DC_REQUIRE((epi == kEpiArgmax || epi == kEpiArgmaxSum) && ep.partial && ep.bias,
+               "gemm_bf16_tc: arg-max epilogue needs bias and partial buffer");
+    if (epi == kEpiArgmax)
+        return wide ? launch_tc<256, kEpiArgmax>(ma, mb, ep, M, N, K, stream)
+                    : launch_tc<128, kEpiArgmax>(ma, mb, ep, M, N, K, stream);
+    return wide ? launch_tc<256, kEpiArgmaxSum>(ma, mb, ep, M, N, K, stream)
+                : launch_tc<128, kEpiArgmaxSum>(ma, mb, ep, M, N, K, stream);
 }
 
-int gemm_tc_argmax_tiles(int N) { return ceil_div(N, N > 128 ? 256 : 128); }
+int gemm_tc_argmax_tiles(int N) { return 2 * ceil_div(N, N > 128 ? 256 : 128); }
 
 // merge the per-tile partials: token = first arg-max over tiles; optional max probability
 __global__ void argmax_merge_kernel(const float4 *__restrict__ partial, int rows, int tiles,

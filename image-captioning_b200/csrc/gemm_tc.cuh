@@ -5,7 +5,9 @@
 namespace dcap {
 
 constexpr int kEpiStore = 0;
-constexpr int kEpiArgmax = 1;
+constexpr int kEpiArgmax = 1;       // max + first arg-max
+constexpr int kEpiArgmaxSum = 2;    // ... + sum exp(v - max) (softmax probability of the arg-max)
+constexpr int kEpiCell = 3;         // fused Keras LSTM cell on gate-interleaved columns
 
 struct TcOperand {
     const __nv_bfloat16 *ptr = nullptr;   // [rows, K] row-major, K contiguous
@@ -21,7 +23,14 @@ struct TcEpilogue {
     int relu = 0;
     float *out_f32 = nullptr; long long ld_f32 = 0;
     __nv_bfloat16 *out_bf16 = nullptr; long long ld_bf16 = 0;
-    float *partial = nullptr;             // kEpiArgmax: [M, tiles_n] float4 {max, argmax bits, sumexp, -}
+    float *partial = nullptr;             // arg-max epilogues: [M, slots] float4 {max, argmax bits, sumexp, -}
+    // kEpiCell: column n = 4*unit + gate (i,f,g,o); z = acc + addend + bias
+    float *cell_c = nullptr;              // [M, cell_units] fp32, updated in place
+    int cell_units = 0;
+    const int32_t *cell_tok = nullptr;    // consumed token per row (0 = masked: carry h, c) or null
+    const __nv_bfloat16 *cell_h_prev = nullptr; long long ld_h_prev = 0;   // previous h (for masked rows)
+    __nv_bfloat16 *cell_h_a = nullptr; long long ld_h_a = 0;               // destinations of the new h
+    __nv_bfloat16 *cell_h_b = nullptr; long long ld_h_b = 0;
 };
 
 // D = epilogue(A * B^T): A [M,K], B [N,K], both bf16 K-major.

@@ -55,3 +55,16 @@ def gemm_bf16_argmax(a, bt, bias, want_prob=False):
         _lib.check(lib.dc_gemm_bf16_argmax(_p(a), a.stride(0), _p(bt), bt.stride(0), M, N, K, _p(bias), _p(tok),
                                            _p(prob), _s(a.device)))
     return (tok, prob) if want_prob else tok
+
+
+def gemm_bf16_lstm_cell(a, bt_interleaved, units, c, h_prev, h_out, addend=None, bias=None, tok=None, h_out2=None):
+    """Fused gates GEMM + Keras LSTM cell (gate-interleaved columns); c updated in place."""
+    lib = _lib.load()
+    M, K = a.shape
+    with torch.cuda.device(a.device):
+        _lib.check(lib.dc_gemm_bf16_lstm_cell(
+            _p(a), a.stride(0), _p(bt_interleaved), bt_interleaved.stride(0), M, units, K, _p(addend),
+            addend.stride(0) if addend is not None else 0, _p(bias), _p(tok), _p(c), _p(h_prev),
+            h_prev.stride(0) if h_prev is not None else 0, _p(h_out), h_out.stride(0), _p(h_out2),
+            h_out2.stride(0) if h_out2 is not None else 0, _s(a.device)))
+    return h_out

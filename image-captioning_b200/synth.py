@@ -104,7 +104,7 @@ def synth_weights_v1(rng, V=10000, E=300, F=1024, U=512, pool=7, C=256, trained_
     w["imgcap_lstm_d1/bias"] = np.zeros(1024, F32)
     w["imgcap_lstm_d2/kernel"] = _glorot(rng, (1024, V), 1024, V)
     if trained_like:
-        w["imgcap_lstm_d2/kernel"] *= F32(12.0)
+        w["imgcap_lstm_d2/kernel"] *= F32(3.0)
     w["imgcap_lstm_d2/bias"] = _vocab_bias(V, trained_like)
     return w
 
@@ -118,7 +118,7 @@ def synth_weights_v2(rng, V=10000, E=300, F=1024, units=256, pool=7, C=256, trai
      w["imgcap_lstm/bias"]) = _lstm_weights(rng, F + 1024, units)
     w["imgcap_d1/kernel"] = _glorot(rng, (units, V), units, V)
     if trained_like:
-        w["imgcap_d1/kernel"] *= F32(12.0)
+        w["imgcap_d1/kernel"] *= F32(3.0)
     w["imgcap_d1/bias"] = _vocab_bias(V, trained_like)
     return w
 

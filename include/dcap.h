@@ -208,6 +208,18 @@ int dc_gemm_bf16(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb
 int dc_gemm_bf16_argmax(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M, int N,
                         int K, const float *bias, int32_t *tokens, float *maxprob, void *stream);
 
+/* bf16 tcgen05 GEMM with the fused Keras LSTM cell epilogue (KL.LSTM step,
+ * text_generation_model.py:141-142): z = A*Bt^T + addend + bias with GATE-INTERLEAVED columns
+ * (column 4*u+g holds gate g in {i,f,c,o} of unit u, i.e. Bt row 4*u+g is column g*units+u of the
+ * Keras kernel); i,f,o = hard_sigmoid, g = tanh; c' = f*c + i*g; h' = o*tanh(c').  Rows whose
+ * tok[m] == 0 carry (h, c) (K.rnn mask).  c [M,units] fp32 is updated in place; h' is written as
+ * bf16 to h_out (and h_out2 if not NULL); h_prev supplies the carried h of masked rows. */
+int dc_gemm_bf16_lstm_cell(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M,
+                           int units, int K, const float *addend, int64_t ld_addend,
+                           const float *bias, const int32_t *tok, float *c,
+                           const uint16_t *h_prev, int64_t ld_h_prev, uint16_t *h_out,
+                           int64_t ld_h_out, uint16_t *h_out2, int64_t ld_h_out2, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,3 +149,43 @@ def test_v2_inject_predict_and_greedy():
     np.testing.assert_allclose(probs, p_want, rtol=PROB_RTOL, atol=PROB_ATOL)
     with pytest.raises(NotImplementedError):
         pkg.build_model((7, 7, C), (P,), cfg, units, inject=False)
+
+
+def test_bf16_greedy_agreement_with_fp32_oracle():
+    """north_star bar for the bf16 path: log-probabilities within 2e-2 absolute of the fp32 model
+    (on positions fed the same prefix) and >= 99 % greedy-token agreement."""
+    rng = np.random.default_rng(1001)
+    V, E, U, C, P, B = 10000, 300, 512, 256, 15, 256
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    feat = rng.standard_normal((B, 7, 7, C)).astype(np.float32)
+    tok_want, z_want = dec.greedy_v1(dec.head(feat, w), w, P, return_logits=True)
+    lp_want = z_want - np.log(np.exp(z_want - z_want.max(-1, keepdims=True)).sum(-1, keepdims=True)) \
+        - z_want.max(-1, keepdims=True)
+    m = _model_v1(w, P, V, E, U, C, dtype="bfloat16")
+    tok, probs = m.generate(feat, return_probs=True)        # materialised-logits path
+    tok_fast = m.generate(feat)                             # fused arg-max epilogue path
+    assert np.array_equal(tok, tok_fast)
+    assert np.array_equal(tok, probs.argmax(-1))
+    agree = (tok == tok_want)
+    assert agree.mean() >= 0.99, "greedy-token agreement %.4f" % agree.mean()
+    # positions whose whole prefix agrees were computed from identical inputs
+    prefix_ok = np.concatenate([np.ones((B, 1), bool), np.cumprod(agree[:, :-1], 1).astype(bool)], 1)
+    lp = np.log(np.maximum(probs, 1e-30))
+    top = lp_want > -12                                     # compare where the fp32 model has mass
+    err = np.abs(lp - lp_want)[prefix_ok[:, :, None] & top]
+    assert err.max() <= 2e-2, "max |log p| error %.4f" % err.max()
+    # bf16 RoI features straight from the ROIAlign bf16 output variant
+    tok_b = m.generate(torch.from_numpy(feat).cuda().to(torch.bfloat16))
+    assert (tok_b.cpu().numpy() == tok_want).mean() >= 0.99
+
+
+def test_bf16_ragged_batch_sizes():
+    rng = np.random.default_rng(31)
+    V, E, U, C, P = 1000, 300, 512, 256, 6
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    m = _model_v1(w, P, V, E, U, C, dtype="bfloat16")
+    feat = rng.standard_normal((300, 7, 7, C)).astype(np.float32)
+    full = m.generate(feat)
+    for n in (1, 127, 129):
+        assert np.array_equal(m.generate(feat[:n]), full[:n])
+    assert m.generate(feat[:0]).shape == (0, P)

@@ -84,3 +84,37 @@ def test_argmax_first_index_on_ties():
     bias[[17, 300, 555]] = 1.0                                   # three equal maxima in different tiles
     tok = gemm.gemm_bf16_argmax(a, bt, bias)
     assert bool((tok == 17).all())
+
+
+@pytest.mark.parametrize("M,U,K", [(300, 64, 128), (8000, 512, 832), (129, 512, 1024)])
+def test_tcgen05_gemm_lstm_cell_epilogue(M, U, K):
+    """Fused gates GEMM + cell against the same math in torch on the same bf16 operands."""
+    from image_captioning_b200 import gemm
+    a = _rand((M, K), 51, torch.bfloat16) * 0.5
+    w = _rand((K, 4 * U), 52) * (1.0 / K ** 0.5)                  # Keras layout [K, 4U], blocks i|f|c|o
+    addend = _rand((M, 4 * U), 53) * 0.5                          # Keras column order
+    bias = _rand((4 * U,), 54) * 0.1
+    c0 = _rand((M, U), 55)
+    h_prev = _rand((M, U), 56, torch.bfloat16)
+    tok = (torch.arange(M, device="cuda") % 5 != 0).to(torch.int32) * 7       # every 5th row masked
+    # interleave: row 4u+g of Bt = column g*U+u of w
+    perm = (torch.arange(4, device="cuda")[None, :] * U + torch.arange(U, device="cuda")[:, None]).reshape(-1)
+    bt = w.t()[perm].contiguous().to(torch.bfloat16)
+    add_i = addend[:, perm].contiguous()
+    bias_i = bias[perm].contiguous()
+    c = c0.clone()
+    h_out = torch.zeros((M, 2 * U), device="cuda", dtype=torch.bfloat16)
+    h_out2 = torch.zeros((M, U), device="cuda", dtype=torch.bfloat16)
+    gemm.gemm_bf16_lstm_cell(a, bt, U, c, h_prev, h_out[:, U:], addend=add_i, bias=bias_i, tok=tok, h_out2=h_out2)
+    z = a.float() @ w.to(torch.bfloat16).float() + addend + bias
+    hs = lambda x: torch.clamp(0.2 * x + 0.5, 0, 1)
+    i, f, g, o = hs(z[:, :U]), hs(z[:, U:2 * U]), torch.tanh(z[:, 2 * U:3 * U]), hs(z[:, 3 * U:])
+    c_want = f * c0 + i * g
+    h_want = o * torch.tanh(c_want)
+    m = (tok != 0)[:, None]
+    c_want = torch.where(m, c_want, c0)
+    h_want = torch.where(m, h_want, h_prev.float())
+    torch.testing.assert_close(c, c_want, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(h_out[:, U:].float(), h_want.to(torch.bfloat16).float(), rtol=2e-2, atol=1e-2)
+    assert torch.equal(h_out[:, U:], h_out2)
+    assert bool((h_out[:, :U] == 0).all())
