@@ -6,9 +6,14 @@
 
 One "step" = one pass of the hot path over one batch of synthetic input.  Workloads:
 
-  roi_features  BASELINE.json configs[1]: 8 images x 1000 RoIs (FPN P2-P5 of a 1024x1024 image,
-                256 ch, fp32) -> PyramidROIAlign -> [8000, 7, 7, 256].  With N GPUs every rank
-                owns its own 8 images (weak scaling, images sharded, no collective).
+  captions      (default) the BASELINE metric "RoI captions/sec": per GPU 8 images x 1000 RoIs
+                (configs[1]'s RoI stage: FPN P2-P5 of a 1024x1024 image, 256 ch fp32) ->
+                PyramidROIAlign -> RoI head -> v1 inject-LSTM greedy decoding (configs[0]/[4]'s
+                decoder: hidden 512, vocab 10k, embedding 300, P = 15) -> [8000, 15] token ids.
+                bf16 tensor-core decoder, fp32 ROIAlign arithmetic.
+  roi_features  BASELINE.json configs[1] alone: 8 images x 1000 RoIs -> [8000, 7, 7, 256] fp32.
+
+With N GPUs every rank owns its own 8 images (weak scaling, images sharded, no collective).
 
 `value` is measured with inputs resident in HBM; `e2e` goes through the host-buffer C-ABI entry
 point with pinned host buffers (H2D of the pyramid and D2H of the features inside the timed
@@ -37,19 +42,24 @@ CHANNELS = 256
 IMAGES_PER_GPU = 8
 ROIS_PER_IMAGE = 1000
 SEED_CFG2 = 1002           # 1000 + config index
+SEED_DECODER = 1005
+VOCAB, EMBED, UNITS, PADDING = 10000, 300, 512, 15
+# head 27.79 + hoisted 6.29 MFLOP once, 29.05 MFLOP per step, P = 15
+FLOP_PER_ROI_GREEDY = 27787264 + 4194304 + 2097152 + PADDING * (1228800 + 2097152 + 4194304 + 1048576 + 20480000)
 
 
 # --------------------------------------------------------------------------------------------
 # helpers
 # --------------------------------------------------------------------------------------------
 
-def measured_peaks():
+def measured_peaks(key="hbm_gbs"):
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(p[key]), "measured (MEASURED_PEAKS.json %s)" % key
+    fallback = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+    return fallback[key], "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler(threading.Thread):
@@ -138,7 +148,7 @@ def dist_env():
 # our arm
 # --------------------------------------------------------------------------------------------
 
-def run_ours(args):
+def run_ours_roi_features(args):
     import torch
     import torch.distributed as dist
     import image_captioning_b200 as pkg
@@ -347,21 +357,244 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------
+# captions workload (default): ROIAlign -> head -> greedy decode
+# --------------------------------------------------------------------------------------------
+
+def _decoder_weights():
+    from image_captioning_b200 import synth
+    return synth.synth_weights_v1(np.random.default_rng(SEED_DECODER), V=VOCAB, E=EMBED, U=UNITS, C=CHANNELS)
+
+
+def run_ours_captions(args):
+    import torch
+    import torch.distributed as dist
+    import image_captioning_b200 as pkg
+    from image_captioning_b200 import synth
+
+    rank, local_rank, world = dist_env()
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sms, cc = pkg._lib.device_info()
+
+    B, N = IMAGES_PER_GPU, ROIS_PER_IMAGE
+    R = B * N
+    rng = np.random.default_rng(SEED_CFG2 + 7919 * rank)
+    boxes_np = synth.synth_boxes(rng, B, N, float(IMAGE_SHAPE[0]))
+    gen = torch.Generator(device=dev).manual_seed(SEED_CFG2 + rank)
+    fms = [torch.randn((B, IMAGE_SHAPE[0] >> l, IMAGE_SHAPE[1] >> l, CHANNELS), device=dev, generator=gen)
+           for l in range(2, 6)]
+    boxes = torch.from_numpy(boxes_np).to(dev)
+    w = _decoder_weights()
+    cfg = pkg.DenseCapConfig(VOCAB, w["imgcap_embedding_layer/embeddings"], 1, PADDING)
+    model = pkg.build_lstm_model([POOL[0], POOL[1], CHANNELS], cfg, UNITS, "inference", dtype="bfloat16", device=dev)
+    model.set_weights(w)
+    feats = torch.empty((R, POOL[0], POOL[1], CHANNELS), dtype=torch.bfloat16, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    _, levels = pkg.pyramid_roi_align(boxes, fms, POOL, IMAGE_SHAPE, out_dtype=torch.bfloat16, out=feats,
+                                      return_levels=True)
+    tokens = model.generate(feats)
+    tokens_fused = model.caption_rois(boxes, fms, IMAGE_SHAPE)          # the single-call public API
+    torch.cuda.synchronize()
+    same_as_fused = bool(torch.equal(tokens, tokens_fused))
+    for _ in range(max(args.warmup, 3)):
+        pkg.pyramid_roi_align(boxes, fms, POOL, IMAGE_SHAPE, out_dtype=torch.bfloat16, out=feats)
+        model.generate(feats)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    barrier()
+    for i in range(K):
+        ev[i][0].record()
+        pkg.pyramid_roi_align(boxes, fms, POOL, IMAGE_SHAPE, out_dtype=torch.bfloat16, out=feats)
+        ev[i][1].record()
+        tokens = model.generate(feats)
+        ev[i][2].record()
+    barrier()
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    roi_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    dec_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    clocks = sampler.summary()
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / K
+    value = R * world / (ms_per_step * 1e-3)
+
+    # rooflines: decoder GEMMs (tensor, dominant share of the step) and ROIAlign (HBM)
+    flops = FLOP_PER_ROI_GREEDY * R
+    tf_peak, tf_src = measured_peaks("bf16_tflops_sustained")
+    tf_burst, _ = measured_peaks("bf16_tflops")
+    achieved_tf = flops / (dec_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (head + 15 decode steps: %d launches per step)"
+                % (4 + 4 * PADDING), "achieved": round(achieved_tf, 1), "peak": tf_peak, "peak_source": tf_src,
+                "unit": "TFLOP/s", "frac": round(achieved_tf / tf_peak, 4),
+                "frac_of_burst_%.0f" % tf_burst: round(achieved_tf / tf_burst, 4),
+                "traffic": None, "algorithmic_flops_per_step": flops, "decoder_ms": round(dec_ms, 4),
+                "share_of_step": round(dec_ms / (roi_ms + dec_ms), 3)}
+    t_unique = tap_unique_pixels(boxes_np, levels.cpu().numpy(), [tuple(f.shape[1:3]) for f in fms], POOL)
+    alg_bytes = 4 * CHANNELS * t_unique + 2 * CHANNELS * POOL[0] * POOL[1] * R        # fp32 taps in, bf16 rows out
+    hbm_peak, hbm_src = measured_peaks("hbm_gbs")
+    achieved_gb = alg_bytes / (roi_ms * 1e-3) / 1e9
+    roofline_hbm = {"bound": "hbm", "kernel": "roi_prepare_kernel + roi_align_stream_kernel (bf16 output)",
+                    "achieved": round(achieved_gb, 1), "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
+                    "frac": round(achieved_gb / hbm_peak, 4), "frac_of_nominal_8000": round(achieved_gb / 8000.0, 4),
+                    "traffic": None, "algorithmic_bytes_per_step": alg_bytes, "t_unique_pixels": t_unique,
+                    "roi_align_ms": round(roi_ms, 4), "share_of_step": round(roi_ms / (roi_ms + dec_ms), 3)}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                tr = json.load(f)
+            roofline["traffic"] = tr.get("gemm_dram_bytes_per_step")
+            roofline_hbm["traffic"] = tr.get("roi_align_bf16_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    line = {
+        "metric": "roi_captions_per_sec", "value": round(value, 1), "unit": "RoI captions/s",
+        "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "captions: per GPU %d images x %d RoIs (cfg2 RoI stage, P2-P5 of 1024x1024, 256 ch "
+                               "fp32) -> PyramidROIAlign -> RoI head -> v1 inject-LSTM greedy decode (hidden %d, "
+                               "vocab %d, embedding %d, P=%d)" % (B, N, UNITS, VOCAB, EMBED, PADDING),
+                   "rois_per_step": R * world, "sharding": "images per rank, no collective",
+                   "precision": "ROIAlign fp32 arithmetic with bf16 output; decoder bf16 operands, fp32 accumulate/state",
+                   "l2": "inputs larger than L2 (pyramid %d MB per GPU; decoder weights + activations %d MB)"
+                         % (sum(f.numel() for f in fms) * 4 // 2 ** 20, (63 + R * (12544 * 2 + 4 * 2048 * 2) // 2 ** 20)),
+                   "sm_count": sms, "cc": cc, "public_api_matches": same_as_fused},
+        "clocks": clocks, "gpu_launches": K * (2 + 8 + 6 * PADDING), "roofline": roofline,
+        "roofline_hbm": roofline_hbm,
+    }
+    if not args.no_e2e:
+        e2e_steps = max(1, min(K, args.e2e_steps))
+        h_boxes = torch.from_numpy(boxes_np).pin_memory()
+        h_fms = [f.cpu().pin_memory() for f in fms]
+        h_np = [f.numpy() for f in h_fms]
+        model.caption_rois(h_boxes.numpy(), h_np, IMAGE_SHAPE)          # warm-up (allocations)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            h_tok = model.caption_rois(h_boxes.numpy(), h_np, IMAGE_SHAPE)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        agree = float((torch.from_numpy(h_tok).to(dev) == tokens).float().mean().item())
+        line["e2e"] = {"value": round(R * world / e2e_s, 1), "unit": "RoI captions/s",
+                       "h2d_bytes_per_step": int(sum(f.numel() * 4 for f in h_fms) + h_boxes.numel() * 4),
+                       "d2h_bytes_per_step": int(R * PADDING * 4), "steps": e2e_steps,
+                       "token_agreement_with_device_run": round(agree, 5),
+                       "api": "dc_caption_rois_host (pinned host pyramid + boxes in, token ids out; "
+                              "image-by-image upload overlapped with ROIAlign + decode)"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_captions(boxes_np[:1], [f[:1].cpu().numpy() for f in fms], w, 12.0)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _cpu_caption_pass(boxes_np, fms_np, w, out, scratch):
+    """The reference's CPU algorithm restated (oracle/): literal PyramidROIAlign (C/OpenMP) ->
+    head -> v1 greedy (numpy fp32 on the BLAS threads; incremental batched scan, i.e. the
+    best-effort vectorised form, NOT the reference's batch-1 O(P^2) loop)."""
+    from tests import _c_oracle
+    from oracle import decoder as dec
+    _c_oracle.pyramid_roi_align(boxes_np, fms_np, POOL, IMAGE_SHAPE, literal=True, out=out, scratch=scratch)
+    tok, _ = dec.greedy_v1(dec.head(out, w), w, PADDING, return_logits=True)
+    return tok
+
+
+def cpu_baseline_captions(boxes_np, fms_np, w, budget_s, n_rois=250):
+    from tests import _c_oracle
+    b = np.ascontiguousarray(boxes_np[:, :n_rois])
+    out = np.empty((n_rois, POOL[0], POOL[1], CHANNELS), np.float32)
+    scratch = np.empty_like(out)
+    _cpu_caption_pass(b, fms_np, w, out, scratch)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        _cpu_caption_pass(b, fms_np, w, out, scratch)
+        done += 1
+        el = time.perf_counter() - t0
+        if el > budget_s:
+            break
+    return {"value": round(done * n_rois / el, 1), "unit": "RoI captions/s", "cores": _c_oracle.num_threads(),
+            "kind": "port", "seconds": round(el, 2),
+            "sample": "%d passes over 1 image x %d RoIs of the same workload: literal PyramidROIAlign (C/OpenMP) + "
+                      "head + v1 greedy P=%d as a batched incremental numpy/BLAS scan (the reference itself runs "
+                      "batch 1 and O(P^2) LSTM steps, which is slower)" % (done, n_rois, PADDING)}
+
+
+def run_reference_captions(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from image_captioning_b200 import synth
+    from tests import _c_oracle
+    rng = np.random.default_rng(SEED_CFG2)
+    n_rois = 250
+    boxes_np = synth.synth_boxes(rng, 1, n_rois, float(IMAGE_SHAPE[0]))
+    fms = [rng.standard_normal((1, IMAGE_SHAPE[0] >> l, IMAGE_SHAPE[1] >> l, CHANNELS), dtype=np.float32)
+           for l in range(2, 6)]
+    w = _decoder_weights()
+    out = np.empty((n_rois, POOL[0], POOL[1], CHANNELS), np.float32)
+    scratch = np.empty_like(out)
+    for _ in range(max(1, min(args.warmup, 2))):
+        _cpu_caption_pass(boxes_np, fms, w, out, scratch)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _cpu_caption_pass(boxes_np, fms, w, out, scratch)
+    el = time.perf_counter() - t0
+    value = args.steps * n_rois / el
+    sample = ("1 image x %d RoIs per step (bounded sample of the captions workload): literal PyramidROIAlign "
+              "(C/OpenMP) + head + v1 greedy P=%d, batched incremental numpy/BLAS scan" % (n_rois, PADDING))
+    line = {"impl": "reference", "metric": "roi_captions_per_sec", "value": round(value, 1),
+            "unit": "RoI captions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(el / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "captions (bounded sample: 1 image x %d RoIs per step)" % n_rois},
+            "cpu_baseline": {"value": round(value, 1), "unit": "RoI captions/s", "cores": _c_oracle.num_threads(),
+                             "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 1), "unit": "RoI captions/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "note": "the reference is TF-1.x/Keras Python and cannot be installed here (no TensorFlow); this arm "
+                    "times the CPU restatement of its algorithm (oracle/) on all host threads"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="roi_features")
+    ap.add_argument("--workload", default="captions", choices=["captions", "roi_features"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        (run_reference_captions if args.workload == "captions" else run_reference)(args)
+    elif args.workload == "captions":
+        run_ours_captions(args)
     else:
-        run_ours(args)
+        run_ours_roi_features(args)
 
 
 if __name__ == "__main__":

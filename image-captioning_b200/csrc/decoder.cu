@@ -79,7 +79,12 @@ void Decoder::declare_all() {
 }
 
 Decoder::~Decoder() {
+    drop_graphs();
+    if (graph_stream) cudaStreamDestroy(graph_stream);
+    if (graph_ev_in) cudaEventDestroy(graph_ev_in);
+    if (graph_ev_out) cudaEventDestroy(graph_ev_out);
     free_bf16();
+    if (roi_buf) cudaFree(roi_buf);
     for (auto &w : weights)
         if (w.dev) cudaFree(w.dev);
     for (void *p : owned) cudaFree(p);
@@ -106,6 +111,7 @@ __global__ void bn_fold_kernel(const float *gamma, const float *beta, const floa
 }
 
 int Decoder::finalize(cudaStream_t s) {
+    drop_graphs();
     for (auto &w : weights)
         if (!w.dev)
             return set_error(DC_ERR_STATE, "weight '%s' has not been set", w.name.c_str());
@@ -156,6 +162,7 @@ int Decoder::finalize(cudaStream_t s) {
 // ------------------------------------------------------------------------------------------
 int Decoder::reserve(int rows) {
     if (rows <= cap) return DC_OK;
+    drop_graphs();
     for (void *p : ws_owned) cudaFree(p);
     ws_owned.clear();
     cap = 0;
@@ -289,7 +296,7 @@ int Decoder::greedy(const void *feats, int kind, int B, int32_t *tokens, float *
     DC_REQUIRE(feats && tokens, "null pointer argument");
     if (int rc = reserve(B)) return rc;
     const int P = cfg.padding, V = cfg.vocab;
-    if (cfg.dtype == DC_DTYPE_BF16 && !probs) return greedy_bf16(feats, kind, B, tokens, s);
+    if (cfg.dtype == DC_DTYPE_BF16 && !probs) return greedy_bf16_graphed(feats, kind, B, tokens, s);
     if (int rc = head(feats, kind, B, ws.F, s)) return rc;
     if (int rc = v1_hoist(B, s)) return rc;
     if (int rc = v1_reset_state(B, s)) return rc;
@@ -347,6 +354,20 @@ int Decoder::beam(const void *feats, int kind, int B, int k, int32_t *tokens, do
     }
     DC_CHECK_CUDA(cudaMemcpyAsync(tokens, hist, sizeof(int32_t) * (size_t)R * P, cudaMemcpyDeviceToDevice, s));
     DC_CHECK_CUDA(cudaMemcpyAsync(scores, sc, sizeof(double) * R, cudaMemcpyDeviceToDevice, s));
+    return DC_OK;
+}
+
+// RoI feature buffer for the fused ROIAlign -> decoder pipeline ([R, pool*pool*channels], bf16 or fp32)
+int Decoder::roi_feature_buffer(int R, void **out) {
+    const size_t elems = (size_t)R * cfg.pool * cfg.pool * cfg.channels;
+    const size_t bytes = elems * (cfg.dtype == DC_DTYPE_BF16 ? 2 : 4);
+    if (bytes > roi_buf_bytes) {
+        if (roi_buf) cudaFree(roi_buf);
+        roi_buf = nullptr; roi_buf_bytes = 0;
+        DC_CHECK_CUDA(cudaMalloc(&roi_buf, bytes));
+        roi_buf_bytes = bytes;
+    }
+    *out = roi_buf;
     return DC_OK;
 }
 
@@ -459,7 +480,6 @@ int Decoder::v2_greedy(const void *feats, int kind, int B, int32_t *tokens, floa
 // ------------------------------------------------------------------------------------------
 using namespace dcap;
 
-struct DcDecoder { Decoder impl; };
 
 extern "C" int dc_decoder_create(const DcDecoderConfig *cfg, DcDecoder **out) {
     DC_REQUIRE(cfg && out, "null pointer argument");

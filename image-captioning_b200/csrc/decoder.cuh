@@ -1,6 +1,8 @@
 // Decoder handle (see decoder.cu).
 #pragma once
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -42,6 +44,16 @@ struct Decoder {
     float *w1cat = nullptr, *w2cat = nullptr;
     float *rep_g1f = nullptr, *rep_d1f = nullptr;
     Bf16State *bf = nullptr;
+    void *roi_buf = nullptr;
+    // CUDA graphs of the bf16 greedy loop, keyed by (feats, kind, B, tokens); captured on the second
+    // call with the same key and replayed afterwards (removes ~100 launches of host overhead per call)
+    typedef std::tuple<const void *, int, int, void *> GraphKey;
+    std::map<GraphKey, cudaGraphExec_t> graphs;
+    std::map<GraphKey, int> graph_calls;
+    cudaStream_t graph_stream = nullptr;
+    cudaEvent_t graph_ev_in = nullptr, graph_ev_out = nullptr;
+    bool use_graphs = true;
+    size_t roi_buf_bytes = 0;
 
     ~Decoder();
     void declare(const std::string &name, std::vector<int64_t> shape);
@@ -52,6 +64,7 @@ struct Decoder {
     int finalize(cudaStream_t s);
     int reserve(int rows);
     int ensure_rep(int R);
+    int roi_feature_buffer(int R, void **out);
     int check_ready(int B);
 
     int linear_f32(const float *x, int ldx, int M, const float *Wk, int K, int N, const float *bias,
@@ -78,8 +91,12 @@ struct Decoder {
     int reset_state_bf16(int R, cudaStream_t s);
     int v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_t s);
     int greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s);
+    int greedy_bf16_graphed(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s);
+    void drop_graphs();
     int beam_gather_bf16(int R, int k, cudaStream_t s);
     void free_bf16();
 };
 
 }  // namespace dcap
+
+struct DcDecoder { dcap::Decoder impl; };

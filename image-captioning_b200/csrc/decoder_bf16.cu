@@ -12,6 +12,8 @@
 #include "decoder.cuh"
 #include "gemm_tc.cuh"
 
+#include <stdlib.h>
+
 namespace dcap {
 
 struct Bf16State {
@@ -206,6 +208,62 @@ int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cu
         if (int rc = gemm_bf16_tc(op(bf->d, kDense), op(bf->wd2, kDense), e, B, V, kDense, kEpiArgmax, s)) return rc;
         if (int rc = argmax_merge(bf->partial, B, slots, tokens + t, P, ws.tok, nullptr, s)) return rc;
     }
+    return DC_OK;
+}
+
+void Decoder::drop_graphs() {
+    for (auto &kv : graphs) cudaGraphExecDestroy(kv.second);
+    graphs.clear();
+    graph_calls.clear();
+}
+
+// Replays (or, on the second call with the same arguments, captures) the whole greedy sequence as
+// one CUDA graph.  Capture runs on a private non-blocking stream (the caller's stream may be the
+// legacy default stream, which cannot be captured); events order it after / before the caller's
+// stream.
+int Decoder::greedy_bf16_graphed(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s) {
+    static const bool env_off = getenv("DCAP_NO_GRAPHS") != nullptr;
+    if (!use_graphs || env_off) return greedy_bf16(feats, kind, B, tokens, s);
+    // the graph writes the ids into the handle's own buffer (hist_a) so that the key does not depend
+    // on the caller's output pointer; a small device-to-device copy delivers them
+    int32_t *internal = ws.hist_a;
+    const GraphKey key(feats, kind, B, (void *)internal);
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+        if (++graph_calls[key] < 2) return greedy_bf16(feats, kind, B, tokens, s);   // first call: eager
+        if (!graph_stream) {
+            DC_CHECK_CUDA(cudaStreamCreateWithFlags(&graph_stream, cudaStreamNonBlocking));
+            DC_CHECK_CUDA(cudaEventCreateWithFlags(&graph_ev_in, cudaEventDisableTiming));
+            DC_CHECK_CUDA(cudaEventCreateWithFlags(&graph_ev_out, cudaEventDisableTiming));
+        }
+        if (graphs.size() >= 16) drop_graphs();
+        cudaGraph_t g = nullptr;
+        DC_CHECK_CUDA(cudaStreamBeginCapture(graph_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = greedy_bf16(feats, kind, B, internal, graph_stream);
+        const cudaError_t e = cudaStreamEndCapture(graph_stream, &g);
+        if (rc != DC_OK || e != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            use_graphs = false;                                     // fall back to eager launches for good
+            return greedy_bf16(feats, kind, B, tokens, s);
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ei = cudaGraphInstantiate(&exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ei != cudaSuccess) {
+            cudaGetLastError();
+            use_graphs = false;
+            return greedy_bf16(feats, kind, B, tokens, s);
+        }
+        it = graphs.emplace(key, exec).first;
+    }
+    DC_CHECK_CUDA(cudaEventRecord(graph_ev_in, s));
+    DC_CHECK_CUDA(cudaStreamWaitEvent(graph_stream, graph_ev_in, 0));
+    DC_CHECK_CUDA(cudaGraphLaunch(it->second, graph_stream));
+    DC_CHECK_CUDA(cudaMemcpyAsync(tokens, internal, sizeof(int32_t) * (size_t)B * cfg.padding,
+                                  cudaMemcpyDeviceToDevice, graph_stream));
+    DC_CHECK_CUDA(cudaEventRecord(graph_ev_out, graph_stream));
+    DC_CHECK_CUDA(cudaStreamWaitEvent(s, graph_ev_out, 0));
     return DC_OK;
 }
 

@@ -473,8 +473,29 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols]
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols].
+// Encoding a map costs a driver call (~microseconds); the decoder re-uses a handful of
+// (pointer, shape) combinations every step, so encoded maps are memoised.
+struct TmapKey {
+    const void *ptr; long long rows, cols, ld; int box_rows;
+    bool operator<(const TmapKey &o) const {
+        if (ptr != o.ptr) return ptr < o.ptr;
+        if (rows != o.rows) return rows < o.rows;
+        if (cols != o.cols) return cols < o.cols;
+        if (ld != o.ld) return ld < o.ld;
+        return box_rows < o.box_rows;
+    }
+};
+
 int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long rows, long long cols, long long ld, int box_rows) {
+    static std::map<TmapKey, CUtensorMap> cache;
+    static std::mutex mu;
+    const TmapKey key{ptr, rows, cols, ld, box_rows};
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *map = it->second; return DC_OK; }
+    }
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(DC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     DC_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, "TMA operand must be 16-byte aligned with ld %% 8 == 0");
@@ -486,6 +507,11 @@ int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long rows, long long 
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(DC_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (cache.size() > 4096) cache.clear();
+        cache[key] = *map;
+    }
     return DC_OK;
 }
 

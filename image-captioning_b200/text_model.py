@@ -307,6 +307,44 @@ class RoiCaptionModel(_ModelBase):
             return tokens.cpu().numpy(), scores.cpu().numpy()
         return tokens, scores
 
+    def caption_rois(self, boxes, feature_maps, image_shape):
+        """generate_features + predict in one call: ROIAlign -> head -> greedy ids [B*N, P].
+        torch CUDA inputs run on the device (dc_caption_rois); numpy inputs go through the
+        host-buffer pipeline (dc_caption_rois_host)."""
+        self._ready()
+        P = self.config.PADDING_SIZE
+        on_dev = all(isinstance(t, torch.Tensor) and t.is_cuda for t in [boxes] + list(feature_maps))
+        if on_dev:
+            b = boxes.detach().to(torch.float32).contiguous()
+            fms = [f.detach().to(torch.float32).contiguous() for f in feature_maps]
+        else:
+            to_np = lambda a: a.numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+            b = np.ascontiguousarray(to_np(boxes), dtype=np.float32)
+            fms = [np.ascontiguousarray(to_np(f), dtype=np.float32) for f in feature_maps]
+        if b.ndim != 3 or b.shape[2] != 4 or len(fms) != 4:
+            raise ValueError("expected boxes [B,N,4] and 4 feature maps")
+        for f in fms:
+            if f.ndim != 4 or f.shape[0] != b.shape[0] or f.shape[3] != self._cfg.channels:
+                raise ValueError("feature maps must be [B,h,w,%d]" % self._cfg.channels)
+        B, N = b.shape[:2]
+        hs = (ctypes.c_int * 4)(*[f.shape[1] for f in fms])
+        ws = (ctypes.c_int * 4)(*[f.shape[2] for f in fms])
+        if on_dev:
+            tokens = torch.empty((B * N, P), dtype=torch.int32, device=self.device)
+            ptrs = (ctypes.c_void_p * 4)(*[f.data_ptr() for f in fms])
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.dc_caption_rois(self._h, ctypes.c_void_p(b.data_ptr()), ptrs, hs, ws, B, N,
+                                                     int(image_shape[0]), int(image_shape[1]),
+                                                     ctypes.c_void_p(tokens.data_ptr()), self._stream()))
+            return tokens
+        tokens = np.empty((B * N, P), np.int32)
+        ptrs = (ctypes.c_void_p * 4)(*[f.ctypes.data for f in fms])
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_caption_rois_host(self._h, ctypes.c_void_p(b.ctypes.data), ptrs, hs, ws, B, N,
+                                                      int(image_shape[0]), int(image_shape[1]),
+                                                      ctypes.c_void_p(tokens.ctypes.data)))
+        return tokens
+
     def head_features(self, features):
         """`features_new` of build_lstm_model (:249-262): [N,1024]."""
         self._ready()

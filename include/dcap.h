@@ -183,6 +183,26 @@ int dc_decoder_greedy_host(DcDecoder *dec, const float *feats, int feats_kind, i
                            int32_t *tokens, float *probs);
 
 /* ------------------------------------------------------------------------------------------
+ * End-to-end: PyramidROIAlign -> RoI head -> greedy decoding in one call
+ * ---------------------------------------------------------------------------------------- */
+
+/* generate_features(...) followed by model.predict(features) as the reference's evaluation loop
+ * runs them per image (evaluate_models/eval_text_generation_model.py:138-148): boxes
+ * [n_images, n_boxes, 4] normalised, 4 NHWC fp32 maps (channels = the decoder's `channels`,
+ * pool = its `pool`), tokens [n_images*n_boxes, P] int32.  The RoI features stay in HBM (bf16
+ * for a bf16 decoder).  Device pointers; asynchronous on `stream`. */
+int dc_caption_rois(DcDecoder *dec, const float *boxes, const float *const fmaps[4],
+                    const int fm_h[4], const int fm_w[4], int n_images, int n_boxes, int img_h,
+                    int img_w, int32_t *tokens, void *stream);
+
+/* Host-buffer form: HOST pointers (pinned memory makes the copies asynchronous); the pyramid is
+ * uploaded image by image while the previous image is aligned and decoded; returns when `tokens`
+ * is complete. */
+int dc_caption_rois_host(DcDecoder *dec, const float *boxes, const float *const fmaps[4],
+                         const int fm_h[4], const int fm_w[4], int n_images, int n_boxes, int img_h,
+                         int img_w, int32_t *tokens);
+
+/* ------------------------------------------------------------------------------------------
  * Dense contraction primitives (exported so that tests can pin the GEMM kernels in isolation;
  * the decoder calls the same code).  They replace the MatMul ops behind KL.Dense / KL.LSTM /
  * KL.Conv2D(valid, full-window) on this path (text_generation_model.py:141-154, 251-262).

@@ -189,3 +189,21 @@ def test_bf16_ragged_batch_sizes():
     for n in (1, 127, 129):
         assert np.array_equal(m.generate(feat[:n]), full[:n])
     assert m.generate(feat[:0]).shape == (0, P)
+
+
+def test_caption_rois_end_to_end_matches_two_stage_path():
+    """dc_caption_rois / dc_caption_rois_host == ROIAlign followed by generate (fp32: also == oracle)."""
+    import image_captioning_b200 as pkg
+    from oracle import roi_align as ra
+    rng = np.random.default_rng(41)
+    V, E, U, C, P, B, N = 300, 24, 64, 16, 6, 3, 40
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    boxes = synth.synth_boxes(rng, B, N, 1024.0)
+    fms = [rng.standard_normal((B, 64 >> i, 64 >> i, C)).astype(np.float32) for i in range(4)]
+    m = _model_v1(w, P, V, E, U, C)
+    feats, _ = ra.pyramid_roi_align(boxes, fms, (7, 7), (1024, 1024, 3))
+    want, _ = dec.greedy_v1(dec.head(feats[0], w), w, P)
+    got_host = m.caption_rois(boxes, fms, (1024, 1024, 3))
+    assert isinstance(got_host, np.ndarray) and np.array_equal(got_host, want)
+    got_dev = m.caption_rois(torch.from_numpy(boxes).cuda(), [torch.from_numpy(f).cuda() for f in fms], (1024, 1024, 3))
+    assert np.array_equal(got_dev.cpu().numpy(), want)
