@@ -21,6 +21,7 @@ struct Bf16State {
     __nv_bfloat16 *w_head1 = nullptr, *w_head2 = nullptr;
     __nv_bfloat16 *w1cat = nullptr, *w1f = nullptr, *w2cat = nullptr, *wd1h = nullptr, *wd1f = nullptr, *wd2 = nullptr;
     float *b1_i = nullptr, *b2_i = nullptr;          // gate-interleaved LSTM biases
+    __nv_bfloat16 *emb = nullptr;                    // [V, Epad] bf16 embedding table (zero padded)
     int Epad = 0;
     // activations
     __nv_bfloat16 *roi = nullptr, *a1 = nullptr, *Fb = nullptr, *d = nullptr;
@@ -45,6 +46,15 @@ __global__ void build_kmajor_kernel(const float *__restrict__ src, int n_src, in
     const int n = (int)(idx / K), k = (int)(idx - (long long)n * K);
     const int col = interleave_units ? (n & 3) * interleave_units + (n >> 2) : n;
     dst[(long long)n * ld_dst + k_off + k] = __float2bfloat16_rn(src[(long long)(row_off + k) * n_src + col]);
+}
+
+// dst[r, c] = bf16(src[r, c]) for c < cols; dst rows are ld_dst wide (padding pre-zeroed)
+__global__ void pad_rows_bf16_kernel(const float *__restrict__ src, int rows, int cols,
+                                     __nv_bfloat16 *__restrict__ dst, int ld_dst) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * cols) return;
+    const int r = (int)(idx / cols), c = (int)(idx - (long long)r * cols);
+    dst[(long long)r * ld_dst + c] = __float2bfloat16_rn(src[idx]);
 }
 
 __global__ void interleave_bias_kernel(const float *__restrict__ src, int units, float *__restrict__ dst) {
@@ -75,6 +85,7 @@ int Decoder::finalize_bf16(cudaStream_t s) {
     rc |= A16(&b.w2cat, (size_t)4 * U * 2 * U);
     rc |= A16(&b.wd1h, (size_t)kDense * U); rc |= A16(&b.wd1f, (size_t)kDense * F);
     rc |= A16(&b.wd2, (size_t)V * kDense);
+    rc |= A16(&b.emb, (size_t)V * b.Epad);
     rc |= dev_alloc((void **)&b.b1_i, sizeof(float) * 4 * U, owned);
     rc |= dev_alloc((void **)&b.b2_i, sizeof(float) * 4 * U, owned);
     if (rc) return rc;
@@ -89,6 +100,11 @@ int Decoder::finalize_bf16(cudaStream_t s) {
     rc |= build_kmajor(W("imgcap_lstm_d1/kernel"), kDense, 0, U, kDense, 0, b.wd1h, U, 0, s);
     rc |= build_kmajor(W("imgcap_lstm_d1/kernel"), kDense, U, F, kDense, 0, b.wd1f, F, 0, s);
     rc |= build_kmajor(W("imgcap_lstm_d2/kernel"), V, 0, kDense, V, 0, b.wd2, kDense, 0, s);
+    if (rc) return rc;
+    DC_CHECK_CUDA(cudaMemsetAsync(b.emb, 0, 2 * (size_t)V * b.Epad, s));
+    pad_rows_bf16_kernel<<<(unsigned)ceil_div<long long>((long long)V * E, 256), 256, 0, s>>>(
+        W("imgcap_embedding_layer/embeddings"), V, E, b.emb, b.Epad);
+    DC_CHECK_LAUNCH();
     if (rc) return rc;
     interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm1/bias"), U, b.b1_i);
     interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm2/bias"), U, b.b2_i);
@@ -162,11 +178,13 @@ int Decoder::reset_state_bf16(int R, cudaStream_t s) {
 }
 
 // the three GEMMs up to the Dense(1024) activations; leaves d (bf16) ready for the vocab GEMM
-static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, cudaStream_t s) {
+static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, bool gather, cudaStream_t s) {
     Bf16State &b = *D.bf;
     const DcDecoderConfig &cfg = D.cfg;
     const int E = cfg.embed, U = cfg.units, V = cfg.vocab, K1 = b.Epad + U, p = b.parity;
-    if (int rc = embed_gather(D.W("imgcap_embedding_layer/embeddings"), D.ws.tok, R, E, V, b.X1[p], K1, true, s)) return rc;
+    // gather == false: the embedding rows were already placed in X1[p] by the previous step's merge kernel
+    if (gather)
+        if (int rc = embed_gather(D.W("imgcap_embedding_layer/embeddings"), D.ws.tok, R, E, V, b.X1[p], K1, true, s)) return rc;
     TcEpilogue c1;
     c1.addend = g1f; c1.ld_addend = 4 * U; c1.cell_c = D.ws.c1; c1.cell_units = U; c1.cell_tok = D.ws.tok;
     c1.cell_h_prev = b.X1[p] + b.Epad; c1.ld_h_prev = K1;
@@ -187,7 +205,7 @@ static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, cuda
 
 // generic step (predict surface / beam): logits are materialised in ws.logits (fp32)
 int Decoder::v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_t s) {
-    if (int rc = step_core(*this, R, g1f, d1f, s)) return rc;
+    if (int rc = step_core(*this, R, g1f, d1f, true, s)) return rc;
     TcEpilogue e;
     e.bias = W("imgcap_lstm_d2/bias"); e.out_f32 = ws.logits; e.ld_f32 = cfg.vocab;
     return gemm_bf16_tc(op(bf->d, kDense), op(bf->wd2, kDense), e, R, cfg.vocab, kDense, kEpiStore, s);
@@ -202,11 +220,14 @@ int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cu
     if (int rc = fill_i32(ws.tok, B, 1, s)) return rc;
     const int slots = gemm_tc_argmax_tiles(V);
     for (int t = 0; t < P; ++t) {
-        if (int rc = step_core(*this, B, ws.g1f, ws.d1f, s)) return rc;
+        if (int rc = step_core(*this, B, ws.g1f, ws.d1f, t == 0, s)) return rc;
         TcEpilogue e;
         e.bias = W("imgcap_lstm_d2/bias"); e.partial = bf->partial;
         if (int rc = gemm_bf16_tc(op(bf->d, kDense), op(bf->wd2, kDense), e, B, V, kDense, kEpiArgmax, s)) return rc;
-        if (int rc = argmax_merge(bf->partial, B, slots, tokens + t, P, ws.tok, nullptr, s)) return rc;
+        // token of this step + its embedding row, written into the operand buffer of step t+1
+        const bool more = t + 1 < P;
+        if (int rc = argmax_merge(bf->partial, B, slots, tokens + t, P, ws.tok, nullptr, s, more ? bf->emb : nullptr,
+                                  bf->Epad, more ? bf->X1[bf->parity] : nullptr, bf->Epad + cfg.units)) return rc;
     }
     return DC_OK;
 }

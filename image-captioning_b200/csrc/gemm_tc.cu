@@ -144,15 +144,13 @@ constexpr int kBlockK = 64;                 // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kEpiWarps = 8;                // 2 per TMEM lane quarter: each owns half of the tile's columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kStageLd = 20;                // floats per staging row (16 columns + pad; 16-byte aligned)
 
 template <int kBlockN>
 struct TcSmem {
     static constexpr int kStageA = kBlockM * kBlockK * 2;
     static constexpr int kStageB = kBlockN * kBlockK * 2;
     static constexpr int kStages = (kBlockN == 256) ? 4 : 6;
-    static constexpr int kStaging = kEpiWarps * 32 * kStageLd * 4;
-    static constexpr int kBytes = kStages * (kStageA + kStageB) + kStaging + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kBytes = kStages * (kStageA + kStageB) + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // 32 lanes x 16 consecutive fp32 columns
@@ -169,16 +167,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// MUFU.TANH: max relative error 2^-11, well inside the bf16 operand rounding (2^-9) of this path
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float hard_sigmoid_tc(float x) {
     return fminf(fmaxf(__fadd_rn(__fmul_rn(0.2f, x), 0.5f), 0.f), 1.f);
 }
 
-// Epilogue of one (warp, column-half) region: rows = the warp's 32 TMEM lanes, columns
-// [col_begin, col_begin + kCols) of the tile.  Accumulators are pulled 16 columns at a time and,
-// for the storing epilogues, transposed through a warp-private padded shared-memory slab so that
-// global accesses are row-contiguous (4 lanes x 16 B per row, 8 rows per instruction).
+// Epilogue of one (warp, column-half) region: rows = the warp's 32 TMEM lanes (lane i <-> row i),
+// columns [n_base, n_base + kCols) of the tile, pulled 32 columns at a time with tcgen05.ld.
 template <int kCols, int kEpi>
-__device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t taddr, float *stage, int lane,
+__device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t taddr, int lane,
                                                 int m_base, int n_base, int M, int N, int part_slot,
                                                 int part_slots) {
     if constexpr (kEpi == kEpiArgmax || kEpi == kEpiArgmaxSum) {
@@ -215,124 +218,171 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
             float4 *dst = reinterpret_cast<float4 *>(ep.partial) + (long long)m * part_slots + part_slot;
             *dst = make_float4(best, __int_as_float(best_i), sum, 0.f);
         }
-    } else {
-        const int sub_row = lane >> 2, colq = lane & 3;
+    } else if constexpr (kEpi == kEpiStore) {
+        // Thread-per-row: lane i owns row m_base+i and pulls 32 consecutive columns straight out of
+        // TMEM, so its global accesses are whole 32-byte sectors of its own row (128 B of fp32 /
+        // 64 B of bf16 per chunk).  The addend of the NEXT chunk is requested before the current
+        // chunk's tcgen05.ld, which keeps one full round trip to L2/HBM in flight per lane.
+        const int m = m_base + lane;
+        const bool valid = m < M;
+        const long long mr = valid ? m : (long long)(M - 1);
+        const float *add_row = ep.addend ? ep.addend + mr * ep.ld_addend : nullptr;
+        const bool bf16_vec8 = ep.out_bf16 && ((ep.ld_bf16 & 7) == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0);
+        float4 a_nxt[8];
+        auto load_addend = [&](int nb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a_nxt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (add_row && nb + 4 * j + 4 <= N)
+                    a_nxt[j] = __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j));
+            }
+        };
+        load_addend(n_base);
 #pragma unroll 1
-        for (int c0 = 0; c0 < kCols; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr + c0, v);
+        for (int c0 = 0; c0 < kCols; c0 += 32) {
             const int nb = n_base + c0;
-            if (nb >= N) continue;                                   // warp-uniform
+            if (nb >= N) break;                                      // warp-uniform
+            float4 a_cur[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float4 *>(stage + lane * kStageLd + 4 * j) =
-                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            __syncwarp();
-            const int n = nb + 4 * colq;
+            for (int j = 0; j < 8; ++j) a_cur[j] = a_nxt[j];
+            if (c0 + 32 < kCols && nb + 32 < N) load_addend(nb + 32);
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+            if (nb + 32 <= N) {
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int row = it * 8 + sub_row;
-                const int m = m_base + row;
-                float4 x = *reinterpret_cast<const float4 *>(stage + row * kStageLd + 4 * colq);
-                if constexpr (kEpi == kEpiStore) {
-                    if (m < M && n < N) {
-                        const bool full = n + 4 <= N;
-                        float xs[4] = {x.x, x.y, x.z, x.w};
-                        if (full) {
-                            if (ep.bias) {
-                                const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.bias + n));
-                                xs[0] += t.x; xs[1] += t.y; xs[2] += t.z; xs[3] += t.w;
-                            }
-                            if (ep.addend) {
-                                const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.addend + (long long)m * ep.ld_addend + n));
-                                xs[0] += t.x; xs[1] += t.y; xs[2] += t.z; xs[3] += t.w;
-                            }
-                            if (ep.scale) {
-                                const float4 sc = __ldg(reinterpret_cast<const float4 *>(ep.scale + n));
-                                const float4 sh = __ldg(reinterpret_cast<const float4 *>(ep.shift + n));
-                                xs[0] = xs[0] * sc.x + sh.x; xs[1] = xs[1] * sc.y + sh.y;
-                                xs[2] = xs[2] * sc.z + sh.z; xs[3] = xs[3] * sc.w + sh.w;
-                            }
+                for (int j = 0; j < 8; ++j) {
+                    float xs[4] = {v[4 * j] + a_cur[j].x, v[4 * j + 1] + a_cur[j].y, v[4 * j + 2] + a_cur[j].z,
+                                   v[4 * j + 3] + a_cur[j].w};
+                    const int n = nb + 4 * j;
+                    if (ep.bias) {
+                        const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.bias + n));
+                        xs[0] += t.x; xs[1] += t.y; xs[2] += t.z; xs[3] += t.w;
+                    }
+                    if (ep.scale) {
+                        const float4 sc = __ldg(reinterpret_cast<const float4 *>(ep.scale + n));
+                        const float4 sh = __ldg(reinterpret_cast<const float4 *>(ep.shift + n));
+                        xs[0] = xs[0] * sc.x + sh.x; xs[1] = xs[1] * sc.y + sh.y;
+                        xs[2] = xs[2] * sc.z + sh.z; xs[3] = xs[3] * sc.w + sh.w;
+                    }
+                    if (ep.relu) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) xs[q] = fmaxf(xs[q], 0.f);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[4 * j + q] = xs[q];
+                }
+                if (valid) {
+                    if (ep.out_f32) {
+                        float4 *dst = reinterpret_cast<float4 *>(ep.out_f32 + (long long)m * ep.ld_f32 + nb);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    if (ep.out_bf16) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            pk[j] = *reinterpret_cast<uint32_t *>(&t);
+                        }
+                        __nv_bfloat16 *dst = ep.out_bf16 + (long long)m * ep.ld_bf16 + nb;
+                        if (bf16_vec8) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                reinterpret_cast<uint4 *>(dst)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                if (n + j < N) {
-                                    if (ep.bias) xs[j] += __ldg(ep.bias + n + j);
-                                    if (ep.addend) xs[j] += __ldg(ep.addend + (long long)m * ep.ld_addend + n + j);
-                                    if (ep.scale) xs[j] = xs[j] * __ldg(ep.scale + n + j) + __ldg(ep.shift + n + j);
-                                }
-                            }
+                            for (int j = 0; j < 8; ++j)
+                                reinterpret_cast<uint2 *>(dst)[j] = make_uint2(pk[2 * j], pk[2 * j + 1]);
                         }
-                        if (ep.relu) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) xs[j] = fmaxf(xs[j], 0.f);
-                        }
-                        if (full) {
-                            if (ep.out_f32)
-                                *reinterpret_cast<float4 *>(ep.out_f32 + (long long)m * ep.ld_f32 + n) =
-                                    make_float4(xs[0], xs[1], xs[2], xs[3]);
-                            if (ep.out_bf16) {
-                                __nv_bfloat162 p0 = __floats2bfloat162_rn(xs[0], xs[1]);
-                                __nv_bfloat162 p1 = __floats2bfloat162_rn(xs[2], xs[3]);
-                                *reinterpret_cast<uint2 *>(ep.out_bf16 + (long long)m * ep.ld_bf16 + n) =
-                                    make_uint2(*reinterpret_cast<uint32_t *>(&p0), *reinterpret_cast<uint32_t *>(&p1));
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                if (n + j < N) {
-                                    if (ep.out_f32) ep.out_f32[(long long)m * ep.ld_f32 + n + j] = xs[j];
-                                    if (ep.out_bf16) ep.out_bf16[(long long)m * ep.ld_bf16 + n + j] = __float2bfloat16_rn(xs[j]);
-                                }
-                            }
-                        }
-                    }
-                } else {   // kEpiCell: columns are gate-interleaved, this lane holds (i,f,g,o) of one unit
-                    const int u = n >> 2;
-                    float c_new = 0.f, h_new = 0.f;
-                    const bool valid = m < M;                         // N is a multiple of 4 units by construction
-                    if (valid) {
-                        float4 z = x;
-                        if (ep.addend) {
-                            const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.addend + (long long)m * ep.ld_addend + n));
-                            z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w;
-                        }
-                        if (ep.bias) {
-                            const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.bias + n));
-                            z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w;
-                        }
-                        const float c_old = ep.cell_c[(long long)m * ep.cell_units + u];
-                        const bool masked = ep.cell_tok && __ldg(ep.cell_tok + m) == 0;
-                        if (masked) {                                // K.rnn mask: carry (h, c)
-                            c_new = c_old;
-                            h_new = __bfloat162float(ep.cell_h_prev[(long long)m * ep.ld_h_prev + u]);
-                        } else {
-                            const float ig = hard_sigmoid_tc(z.x), fg = hard_sigmoid_tc(z.y);
-                            const float gg = tanhf(z.z), og = hard_sigmoid_tc(z.w);
-                            c_new = __fadd_rn(__fmul_rn(fg, c_old), __fmul_rn(ig, gg));
-                            h_new = __fmul_rn(og, tanhf(c_new));
-                        }
-                    }
-                    // gather the 4 units of this row-chunk into the colq==0 lane: 16-B / 8-B stores
-                    float cq[4], hq[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        cq[j] = __shfl_sync(0xffffffffu, c_new, (lane & ~3) + j);
-                        hq[j] = __shfl_sync(0xffffffffu, h_new, (lane & ~3) + j);
-                    }
-                    if (valid && colq == 0) {
-                        const int u0 = nb >> 2;
-                        *reinterpret_cast<float4 *>(ep.cell_c + (long long)m * ep.cell_units + u0) =
-                            make_float4(cq[0], cq[1], cq[2], cq[3]);
-                        __nv_bfloat162 p0 = __floats2bfloat162_rn(hq[0], hq[1]);
-                        __nv_bfloat162 p1 = __floats2bfloat162_rn(hq[2], hq[3]);
-                        const uint2 hv = make_uint2(*reinterpret_cast<uint32_t *>(&p0), *reinterpret_cast<uint32_t *>(&p1));
-                        if (ep.cell_h_a) *reinterpret_cast<uint2 *>(ep.cell_h_a + (long long)m * ep.ld_h_a + u0) = hv;
-                        if (ep.cell_h_b) *reinterpret_cast<uint2 *>(ep.cell_h_b + (long long)m * ep.ld_h_b + u0) = hv;
                     }
                 }
+            } else if (valid) {
+                // ragged last chunk of the last N tile: element-wise
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = nb + j;
+                    if (n >= N) continue;
+                    float x = v[j];
+                    if (add_row) x += __ldg(add_row + n);
+                    if (ep.bias) x += __ldg(ep.bias + n);
+                    if (ep.scale) x = x * __ldg(ep.scale + n) + __ldg(ep.shift + n);
+                    if (ep.relu) x = fmaxf(x, 0.f);
+                    if (ep.out_f32) ep.out_f32[(long long)m * ep.ld_f32 + n] = x;
+                    if (ep.out_bf16) ep.out_bf16[(long long)m * ep.ld_bf16 + n] = __float2bfloat16_rn(x);
+                }
             }
-            __syncwarp();
+        }
+    } else {
+        // kEpiCell, thread-per-row: columns are gate-interleaved, so the 32 columns of a chunk are
+        // the (i,f,g,o) pre-activations of 8 consecutive units of this lane's row.  Per chunk a
+        // lane reads 128 B of addend + 32 B of c, writes 32 B of c and 16 B of h (whole sectors);
+        // the next chunk's operands are requested before the current chunk is computed.
+        const int m = m_base + lane;
+        const bool valid = m < M;
+        const long long mr = valid ? m : (long long)(M - 1);
+        const float *add_row = ep.addend ? ep.addend + mr * ep.ld_addend : nullptr;
+        float *c_row = ep.cell_c + mr * ep.cell_units;
+        const bool masked = ep.cell_tok && __ldg(ep.cell_tok + mr) == 0;
+        float4 a_nxt[8], c_nxt[2];
+        auto load_operands = [&](int nb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                a_nxt[j] = add_row ? __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            c_nxt[0] = *reinterpret_cast<const float4 *>(c_row + (nb >> 2));
+            c_nxt[1] = *reinterpret_cast<const float4 *>(c_row + (nb >> 2) + 4);
+        };
+        if (n_base < N) load_operands(n_base);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kCols; c0 += 32) {
+            const int nb = n_base + c0;
+            if (nb >= N) break;                                      // warp-uniform; N % 32 == 0 here
+            float4 a_cur[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a_cur[j] = a_nxt[j];
+            const float c_old[8] = {c_nxt[0].x, c_nxt[0].y, c_nxt[0].z, c_nxt[0].w,
+                                    c_nxt[1].x, c_nxt[1].y, c_nxt[1].z, c_nxt[1].w};
+            if (c0 + 32 < kCols && nb + 32 < N) load_operands(nb + 32);
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+            const int u0 = nb >> 2;
+            float c_new[8], h_new[8];
+            if (!masked) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 z = make_float4(v[4 * j] + a_cur[j].x, v[4 * j + 1] + a_cur[j].y, v[4 * j + 2] + a_cur[j].z,
+                                           v[4 * j + 3] + a_cur[j].w);
+                    if (ep.bias) {
+                        const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.bias + nb + 4 * j));
+                        z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w;
+                    }
+                    const float ig = hard_sigmoid_tc(z.x), fg = hard_sigmoid_tc(z.y);
+                    const float gg = tanh_fast(z.z), og = hard_sigmoid_tc(z.w);
+                    c_new[j] = __fadd_rn(__fmul_rn(fg, c_old[j]), __fmul_rn(ig, gg));
+                    h_new[j] = __fmul_rn(og, tanh_fast(c_new[j]));
+                }
+            } else {                                                 // K.rnn mask: carry (h, c)
+                const uint4 hp = *reinterpret_cast<const uint4 *>(ep.cell_h_prev + mr * ep.ld_h_prev + u0);
+                const uint32_t hw[4] = {hp.x, hp.y, hp.z, hp.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    c_new[j] = c_old[j];
+                    h_new[j] = __uint_as_float((j & 1) ? (hw[j >> 1] & 0xffff0000u) : (hw[j >> 1] << 16));
+                }
+            }
+            if (valid) {
+                reinterpret_cast<float4 *>(c_row + u0)[0] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
+                reinterpret_cast<float4 *>(c_row + u0)[1] = make_float4(c_new[4], c_new[5], c_new[6], c_new[7]);
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __nv_bfloat162 t = __floats2bfloat162_rn(h_new[2 * j], h_new[2 * j + 1]);
+                    pk[j] = *reinterpret_cast<uint32_t *>(&t);
+                }
+                const uint4 hv = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (ep.cell_h_a) *reinterpret_cast<uint4 *>(ep.cell_h_a + (long long)m * ep.ld_h_a + u0) = hv;
+                if (ep.cell_h_b) *reinterpret_cast<uint4 *>(ep.cell_h_b + (long long)m * ep.ld_h_b + u0) = hv;
+            }
         }
     }
 }
@@ -348,8 +398,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + kStages * S::kStageA;
-    float *staging = reinterpret_cast<float *>(smem + kStages * (S::kStageA + S::kStageB));
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * (S::kStageA + S::kStageB) + S::kStaging);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * (S::kStageA + S::kStageB));
     uint64_t *empty_bar = full_bar + kStages;
     uint64_t *tmem_full = empty_bar + kStages;
     uint64_t *tmem_empty = tmem_full + 2;
@@ -428,7 +477,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
         const int half = e >> 2;                                       // which half of the tile's columns
         constexpr int kCols = kBlockN / 2;
-        float *stage_w = staging + e * 32 * kStageLd;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -437,7 +485,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * kCols;
-            epilogue_region<kCols, kEpi>(ep, taddr, stage_w, lane, m0 + quarter * 32, n0 + half * kCols, M, N,
+            epilogue_region<kCols, kEpi>(ep, taddr, lane, m0 + quarter * 32, n0 + half * kCols, M, N,
                                          tile_n * 2 + half, tiles_n * 2);
             tc_fence_before();
             __syncwarp();
@@ -552,7 +600,11 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
         DC_REQUIRE(ep.cell_c && ep.cell_units * 4 == N && N % 16 == 0, "cell epilogue: N must be 4*units, units %% 4 == 0");
         DC_REQUIRE(!ep.cell_tok || ep.cell_h_prev, "cell epilogue: masking needs the previous h");
         DC_REQUIRE(!ep.addend || (((uintptr_t)ep.addend & 15) == 0 && ep.ld_addend % 4 == 0), "addend alignment");
-        DC_REQUIRE((!ep.cell_h_a || ep.ld_h_a % 4 == 0) && (!ep.cell_h_b || ep.ld_h_b % 4 == 0), "h destination alignment");
+        DC_REQUIRE(ep.cell_units % 8 == 0, "cell epilogue: units must be a multiple of 8");
+        DC_REQUIRE((!ep.cell_h_a || (ep.ld_h_a % 8 == 0 && ((uintptr_t)ep.cell_h_a & 15) == 0)) &&
+                   (!ep.cell_h_b || (ep.ld_h_b % 8 == 0 && ((uintptr_t)ep.cell_h_b & 15) == 0)) &&
+                   (!ep.cell_h_prev || (ep.ld_h_prev % 8 == 0 && ((uintptr_t)ep.cell_h_prev & 15) == 0)),
+                   "cell epilogue: h buffers must be 16-byte aligned with ld %% 8 == 0");
         return wide ? launch_tc<256, kEpiCell>(ma, mb, ep, M, N, K, stream)
                     : launch_tc<128, kEpiCell>(ma, mb, ep, M, N, K, stream);
     }
@@ -567,34 +619,67 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
 
 int gemm_tc_argmax_tiles(int N) { return 2 * ceil_div(N, N > 128 ? 256 : 128); }
 
-// merge the per-tile partials: token = first arg-max over tiles; optional max probability
-__global__ void argmax_merge_kernel(const float4 *__restrict__ partial, int rows, int tiles,
-                                    int32_t *__restrict__ tok_out, int tok_stride, int32_t *__restrict__ tok_cur,
-                                    float *__restrict__ maxprob) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// Merge the per-tile partials of the arg-max epilogue, one warp per row: token = first arg-max
+// over tiles, optional softmax probability of that token, and (optionally) the embedding row of the
+// token copied as bf16 into the next step's gate-GEMM operand (Embedding lookup of the greedy
+// feedback, text_generation_model.py:147,222-225).
+__global__ void __launch_bounds__(256) argmax_merge_kernel(const float4 *__restrict__ partial, int rows, int tiles,
+                                                           int32_t *__restrict__ tok_out, int tok_stride,
+                                                           int32_t *__restrict__ tok_cur, float *__restrict__ maxprob,
+                                                           const uint4 *__restrict__ emb, int emb_ld8,
+                                                           uint4 *__restrict__ x_out, long long ld_x8) {
+    const int r = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
     if (r >= rows) return;
     float best = -INFINITY, sum = 0.f;
     int bi = 0x7fffffff;
-    for (int t = 0; t < tiles; ++t) {
+    for (int t = lane; t < tiles; t += 32) {
         const float4 p = __ldg(partial + (long long)r * tiles + t);
         const int idx = __float_as_int(p.y);
-        if (p.x > best) {                       // tiles are visited in column order: strict > keeps the first
+        if (p.x > best) {
             sum = sum * __expf(best - p.x) + p.z;
             best = p.x; bi = idx;
+        } else if (p.x == best) {
+            sum += p.z; bi = min(bi, idx);
         } else {
             sum += p.z * __expf(p.x - best);
         }
     }
-    if (tok_out) tok_out[(long long)r * tok_stride] = bi;
-    if (tok_cur) tok_cur[r] = bi;
-    if (maxprob) maxprob[r] = 1.0f / sum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const float os = __shfl_xor_sync(0xffffffffu, sum, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best) {
+            sum = sum * __expf(best - ob) + os;
+            best = ob; bi = oi;
+        } else if (ob == best) {
+            sum += os; bi = min(bi, oi);                 // ties: the smaller column index wins
+        } else {
+            sum += os * __expf(ob - best);
+        }
+    }
+    if (lane == 0) {
+        if (tok_out) tok_out[(long long)r * tok_stride] = bi;
+        if (tok_cur) tok_cur[r] = bi;
+        if (maxprob) maxprob[r] = 1.0f / sum;
+    }
+    if (emb) {
+        const uint4 *src = emb + (long long)bi * emb_ld8;
+        uint4 *dst = x_out + (long long)r * ld_x8;
+        for (int j = lane; j < emb_ld8; j += 32) dst[j] = __ldg(src + j);
+    }
 }
 
 int argmax_merge(const float *partial, int rows, int tiles, int32_t *tok_out, int tok_stride, int32_t *tok_cur,
-                 float *maxprob, cudaStream_t s) {
+                 float *maxprob, cudaStream_t s, const __nv_bfloat16 *emb, int emb_ld, __nv_bfloat16 *x_out,
+                 long long ld_x) {
     if (rows <= 0) return DC_OK;
-    argmax_merge_kernel<<<ceil_div(rows, 128), 128, 0, s>>>(reinterpret_cast<const float4 *>(partial), rows, tiles,
-                                                           tok_out, tok_stride, tok_cur, maxprob);
+    DC_REQUIRE(!emb || (emb_ld % 8 == 0 && ld_x % 8 == 0 && x_out), "argmax_merge: embedding rows must be 16-byte multiples");
+    argmax_merge_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(reinterpret_cast<const float4 *>(partial), rows, tiles,
+                                                         tok_out, tok_stride, tok_cur, maxprob,
+                                                         reinterpret_cast<const uint4 *>(emb), emb_ld / 8,
+                                                         reinterpret_cast<uint4 *>(x_out), ld_x / 8);
     DC_CHECK_LAUNCH();
     return DC_OK;
 }

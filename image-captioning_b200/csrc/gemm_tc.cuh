@@ -38,6 +38,7 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
                  cudaStream_t stream);
 int gemm_tc_argmax_tiles(int N);
 int argmax_merge(const float *partial, int rows, int tiles, int32_t *tok_out, int tok_stride, int32_t *tok_cur,
-                 float *maxprob, cudaStream_t s);
+                 float *maxprob, cudaStream_t s, const __nv_bfloat16 *emb = nullptr, int emb_ld = 0,
+                 __nv_bfloat16 *x_out = nullptr, long long ld_x = 0);
 
 }  // namespace dcap
