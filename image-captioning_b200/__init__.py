@@ -8,4 +8,4 @@ from . import _lib                                            # noqa: F401
 from .roi_align import PyramidROIAlign, pyramid_roi_align, fpn_levels    # noqa: F401
 from . import synth  # noqa: F401
 from .text_model import (DenseCapConfig, build_lstm_model, build_model, RoiCaptionModel,   # noqa: F401
-                         InjectModelV2)
+                         InjectModelV2, Adam, roi_caption_loss)

@@ -64,6 +64,11 @@ SIGNATURES = {
     "dc_gemm_bf16": (ctypes.c_int, [c_void, ctypes.c_int64, c_void, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_int, c_void, c_void, ctypes.c_int64, ctypes.c_int, c_void,
                                     ctypes.c_int64, c_void, ctypes.c_int64, c_void]),
+    "dc_gemm_bf16_ex": (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_int, c_void, ctypes.c_int64, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void, c_void, ctypes.c_int64,
+                                       ctypes.c_int, ctypes.c_int, c_void, ctypes.c_int64, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, c_void, ctypes.c_int64, c_void, ctypes.c_int64,
+                                       c_void]),
     "dc_gemm_bf16_argmax": (ctypes.c_int, [c_void, ctypes.c_int64, c_void, ctypes.c_int64, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, c_void, c_void, c_void, c_void]),
     "dc_gemm_bf16_lstm_cell": (ctypes.c_int, [c_void, ctypes.c_int64, c_void, ctypes.c_int64, ctypes.c_int,
@@ -75,6 +80,15 @@ SIGNATURES = {
     "dc_caption_rois_host": (ctypes.c_int, [c_void, c_void, c_void * 4, ctypes.c_int * 4, ctypes.c_int * 4] +
                              [ctypes.c_int] * 4 + [c_void]),
     "dc_decoder_greedy_host": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void]),
+    "dc_decoder_train_step": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void,
+                                             ctypes.c_float, c_void, c_void]),
+    "dc_decoder_teacher_forced": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void]),
+    "dc_adam_step": (ctypes.c_int, [c_void, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                    ctypes.c_int, ctypes.c_int64, ctypes.c_float, c_void]),
+    "dc_decoder_grad_buffer": (ctypes.c_int, [c_void, ctypes.POINTER(c_void), ctypes.POINTER(ctypes.c_int64)]),
+    "dc_decoder_param_buffer": (ctypes.c_int, [c_void, ctypes.POINTER(c_void), ctypes.POINTER(ctypes.c_int64)]),
+    "dc_decoder_weight_offset": (ctypes.c_int64, [c_void, ctypes.c_int]),
+    "dc_decoder_get_grad": (ctypes.c_int, [c_void, ctypes.c_char_p, c_void, ctypes.c_int64]),
 }
 
 

@@ -66,6 +66,23 @@ extern "C" int dc_gemm_bf16(const uint16_t *A, int64_t lda, const uint16_t *Bt, 
     return gemm_bf16_tc(a, b, ep, M, N, K, kEpiStore, (cudaStream_t)stream);
 }
 
+extern "C" int dc_gemm_bf16_ex(const uint16_t *A, int64_t lda, int a_mn, const uint16_t *B, int64_t ldb, int b_mn,
+                               int M, int N, int K, const float *bias, const float *addend, int64_t ld_addend,
+                               int addend_mod, int relu, const uint16_t *mask_src, int64_t ld_mask,
+                               int deint_units, int atomic, int split_k, float *out_f32, int64_t ld_f32,
+                               uint16_t *out_bf16, int64_t ld_bf16, void *stream) {
+    TcOperand a, b;
+    a.ptr = reinterpret_cast<const __nv_bfloat16 *>(A); a.ld = lda; a.mn_major = a_mn != 0;
+    b.ptr = reinterpret_cast<const __nv_bfloat16 *>(B); b.ld = ldb; b.mn_major = b_mn != 0;
+    TcEpilogue ep;
+    ep.bias = bias; ep.addend = addend; ep.ld_addend = ld_addend; ep.addend_mod = addend_mod; ep.relu = relu;
+    ep.mask_src = reinterpret_cast<const __nv_bfloat16 *>(mask_src); ep.ld_mask = ld_mask;
+    ep.deint_units = deint_units; ep.atomic = atomic;
+    ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
+    ep.out_bf16 = reinterpret_cast<__nv_bfloat16 *>(out_bf16); ep.ld_bf16 = ld_bf16;
+    return gemm_bf16_tc(a, b, ep, M, N, K, kEpiStore, (cudaStream_t)stream, split_k);
+}
+
 extern "C" int dc_gemm_bf16_argmax(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M, int N,
                                    int K, const float *bias, int32_t *tokens, float *maxprob, void *stream) {
     if (M <= 0) return DC_OK;

@@ -78,15 +78,37 @@ void Decoder::declare_all() {
     }
 }
 
+// arena offsets: trainable tensors first, each 256-byte aligned (sizes here are multiples anyway)
+int Decoder::layout_arena() {
+    int64_t off = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (auto &w : weights) {
+            const bool frozen = w.name.find("/moving_") != std::string::npos || w.name.find("/embeddings") != std::string::npos;
+            w.trainable = !frozen;
+            if ((pass == 0) != w.trainable) continue;
+            w.offset = off;
+            off += (w.numel + 63) / 64 * 64;
+        }
+        if (pass == 0) n_train = off;
+    }
+    n_total = off;
+    DC_CHECK_CUDA(cudaMalloc((void **)&arena, sizeof(float) * (size_t)n_total));
+    DC_CHECK_CUDA(cudaMemset(arena, 0, sizeof(float) * (size_t)n_total));
+    for (auto &w : weights) w.dev = arena + w.offset;
+    return DC_OK;
+}
+
 Decoder::~Decoder() {
     drop_graphs();
+    free_train();
     if (graph_stream) cudaStreamDestroy(graph_stream);
     if (graph_ev_in) cudaEventDestroy(graph_ev_in);
     if (graph_ev_out) cudaEventDestroy(graph_ev_out);
     free_bf16();
     if (roi_buf) cudaFree(roi_buf);
-    for (auto &w : weights)
-        if (w.dev) cudaFree(w.dev);
+    if (arena) cudaFree(arena);
+    for (float *p : {grads, adam_m, adam_v, adam_vhat})
+        if (p) cudaFree(p);
     for (void *p : owned) cudaFree(p);
     for (void *p : ws_owned) cudaFree(p);
 }
@@ -113,27 +135,38 @@ __global__ void bn_fold_kernel(const float *gamma, const float *beta, const floa
 int Decoder::finalize(cudaStream_t s) {
     drop_graphs();
     for (auto &w : weights)
-        if (!w.dev)
+        if (!w.is_set)
             return set_error(DC_ERR_STATE, "weight '%s' has not been set", w.name.c_str());
-    for (void *p : owned) cudaFree(p);
-    owned.clear();
+    if (int rc = refresh_derived(s)) return rc;
+    DC_CHECK_CUDA(cudaStreamSynchronize(s));
+    finalized = true;
+    return DC_OK;
+}
+
+// (Re)builds every buffer derived from the fp32 master weights: folded BatchNorm, stacked fp32
+// operands, bf16 K-major copies.  Buffers are allocated on the first call and re-used afterwards
+// (their addresses are baked into captured CUDA graphs), so the optimiser can call this every step.
+int Decoder::refresh_derived(cudaStream_t s) {
+    const bool fresh = owned.empty();
     const int F = cfg.feat, E = cfg.embed, U = cfg.units;
     for (int i = 0; i < 2; ++i) {
-        float *sc, *sh;
-        if (int rc = dev_alloc((void **)&sc, sizeof(float) * F, owned)) return rc;
-        if (int rc = dev_alloc((void **)&sh, sizeof(float) * F, owned)) return rc;
+        if (fresh) {
+            if (int rc = dev_alloc((void **)&bn_scale[i], sizeof(float) * F, owned)) return rc;
+            if (int rc = dev_alloc((void **)&bn_shift[i], sizeof(float) * F, owned)) return rc;
+        }
         const std::string bn = i == 0 ? "mrcnn_class_bn1" : "mrcnn_class_bn2";
         bn_fold_kernel<<<ceil_div(F, 256), 256, 0, s>>>(
             W((bn + "/gamma").c_str()), W((bn + "/beta").c_str()), W((bn + "/moving_mean").c_str()),
-            W((bn + "/moving_variance").c_str()), kBnEps, F, sc, sh);
+            W((bn + "/moving_variance").c_str()), kBnEps, F, bn_scale[i], bn_shift[i]);
         DC_CHECK_LAUNCH();
-        bn_scale[i] = sc;
-        bn_shift[i] = sh;
     }
+    if (cfg.dtype == DC_DTYPE_BF16) return refresh_bf16(fresh, s);
     if (cfg.arch == DC_ARCH_V1) {
         // stacked operands: [W1[:E] ; U1]  and  [W2 ; U2]
-        if (int rc = dev_alloc((void **)&w1cat, sizeof(float) * (size_t)(E + U) * 4 * U, owned)) return rc;
-        if (int rc = dev_alloc((void **)&w2cat, sizeof(float) * (size_t)(2 * U) * 4 * U, owned)) return rc;
+        if (fresh) {
+            if (int rc = dev_alloc((void **)&w1cat, sizeof(float) * (size_t)(E + U) * 4 * U, owned)) return rc;
+            if (int rc = dev_alloc((void **)&w2cat, sizeof(float) * (size_t)(2 * U) * 4 * U, owned)) return rc;
+        }
         DC_CHECK_CUDA(cudaMemcpyAsync(w1cat, W("imgcap_lstm1/kernel"), sizeof(float) * (size_t)E * 4 * U,
                                       cudaMemcpyDeviceToDevice, s));
         DC_CHECK_CUDA(cudaMemcpyAsync(w1cat + (size_t)E * 4 * U, W("imgcap_lstm1/recurrent_kernel"),
@@ -144,16 +177,13 @@ int Decoder::finalize(cudaStream_t s) {
                                       sizeof(float) * (size_t)U * 4 * U, cudaMemcpyDeviceToDevice, s));
     } else {
         const int Wu = cfg.word_units;
-        if (int rc = dev_alloc((void **)&w1cat, sizeof(float) * (size_t)(E + Wu) * 4 * Wu, owned)) return rc;
+        if (fresh)
+            if (int rc = dev_alloc((void **)&w1cat, sizeof(float) * (size_t)(E + Wu) * 4 * Wu, owned)) return rc;
         DC_CHECK_CUDA(cudaMemcpyAsync(w1cat, W("lstm_1/kernel"), sizeof(float) * (size_t)E * 4 * Wu,
                                       cudaMemcpyDeviceToDevice, s));
         DC_CHECK_CUDA(cudaMemcpyAsync(w1cat + (size_t)E * 4 * Wu, W("lstm_1/recurrent_kernel"),
                                       sizeof(float) * (size_t)Wu * 4 * Wu, cudaMemcpyDeviceToDevice, s));
     }
-    if (cfg.dtype == DC_DTYPE_BF16)
-        if (int rc = finalize_bf16(s)) return rc;
-    DC_CHECK_CUDA(cudaStreamSynchronize(s));
-    finalized = true;
     return DC_OK;
 }
 
@@ -499,6 +529,7 @@ extern "C" int dc_decoder_create(const DcDecoderConfig *cfg, DcDecoder **out) {
     d->impl.cfg = *cfg;
     d->impl.device = dev;
     d->impl.declare_all();
+    if (int rc = d->impl.layout_arena()) { delete d; return rc; }
     *out = d;
     return DC_OK;
 }
@@ -526,8 +557,9 @@ extern "C" int dc_decoder_set_weight(DcDecoder *dec, const char *name, const flo
     DC_REQUIRE(w != nullptr, "unknown weight '%s'", name);
     DC_REQUIRE(w->numel == numel, "weight '%s' expects %lld values, got %lld", name, (long long)w->numel,
                (long long)numel);
-    if (!w->dev) DC_CHECK_CUDA(cudaMalloc((void **)&w->dev, sizeof(float) * (size_t)numel));
     DC_CHECK_CUDA(cudaMemcpy(w->dev, host, sizeof(float) * (size_t)numel, cudaMemcpyHostToDevice));
+    w->is_set = true;
+    if (w->name.find("/embeddings") != std::string::npos) dec->impl.emb_dirty = true;
     dec->impl.finalized = false;
     return DC_OK;
 }
@@ -538,7 +570,7 @@ extern "C" int dc_decoder_get_weight(DcDecoder *dec, const char *name, float *ho
     DC_REQUIRE(w != nullptr, "unknown weight '%s'", name);
     DC_REQUIRE(w->numel == numel, "weight '%s' holds %lld values, got %lld", name, (long long)w->numel,
                (long long)numel);
-    if (!w->dev) return set_error(DC_ERR_STATE, "weight '%s' has not been set", name);
+    if (!w->is_set) return set_error(DC_ERR_STATE, "weight '%s' has not been set", name);
     DC_CHECK_CUDA(cudaMemcpy(host, w->dev, sizeof(float) * (size_t)numel, cudaMemcpyDeviceToHost));
     return DC_OK;
 }

@@ -17,7 +17,10 @@ struct Weight {
     std::string name;
     std::vector<int64_t> shape;
     int64_t numel = 0;
-    float *dev = nullptr;         // fp32, Keras layout
+    float *dev = nullptr;         // fp32, Keras layout; points into Decoder::arena
+    int64_t offset = 0;           // floats from the start of the arena
+    bool trainable = true;        // frozen: embeddings (trainable=False) and BatchNorm moving statistics
+    bool is_set = false;
 };
 
 struct Workspace {
@@ -38,6 +41,7 @@ struct Decoder {
     std::vector<Weight> weights;
     std::vector<void *> owned, ws_owned;
     bool finalized = false;
+    bool emb_dirty = true;        // the bf16 embedding table must be rebuilt at the next refresh
     int cap = 0, rep_cap = 0;
     Workspace ws;
     float *bn_scale[2] = {nullptr, nullptr}, *bn_shift[2] = {nullptr, nullptr};
@@ -54,14 +58,21 @@ struct Decoder {
     cudaEvent_t graph_ev_in = nullptr, graph_ev_out = nullptr;
     bool use_graphs = true;
     size_t roi_buf_bytes = 0;
+    // One flat fp32 arena for all weights: trainable tensors first (declaration order), frozen ones
+    // after, so that gradients / optimiser state / the NCCL all-reduce are single contiguous ranges.
+    float *arena = nullptr;
+    int64_t n_train = 0, n_total = 0;
+    float *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr, *adam_vhat = nullptr;   // [n_train], lazily allocated
 
     ~Decoder();
     void declare(const std::string &name, std::vector<int64_t> shape);
     void declare_all();
+    int layout_arena();
     Weight *find(const std::string &name);
     const float *W(const char *name);
     int dev_alloc(void **p, size_t bytes, std::vector<void *> &list);
     int finalize(cudaStream_t s);
+    int refresh_derived(cudaStream_t s);
     int reserve(int rows);
     int ensure_rep(int R);
     int roi_feature_buffer(int R, void **out);
@@ -84,7 +95,7 @@ struct Decoder {
     int v2_greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s);
 
     // bf16 / tcgen05 path (decoder_bf16.cu)
-    int finalize_bf16(cudaStream_t s);
+    int refresh_bf16(bool fresh, cudaStream_t s);
     int reserve_bf16(size_t R);
     int head_bf16(const void *feats, int kind, int B, float *out, cudaStream_t s);
     int v1_hoist_bf16(int B, cudaStream_t s);
@@ -95,6 +106,17 @@ struct Decoder {
     void drop_graphs();
     int beam_gather_bf16(int R, int k, cudaStream_t s);
     void free_bf16();
+
+    // training step (train.cu; bf16 v1 decoder only)
+    int train_forward(const void *feats, int kind, int B, const int32_t *gt, const int32_t *targets, cudaStream_t s);
+    int teacher_forced_probs(const void *feats, int kind, int B, const int32_t *gt, float *probs, cudaStream_t s);
+    int train_step(const void *feats, int kind, int B, const int32_t *gt, const int32_t *targets, float inv_count,
+                   float *loss, cudaStream_t s);
+    int adam_step(float lr, float beta1, float beta2, float eps, int amsgrad, long long t, float grad_scale,
+                  cudaStream_t s);
+    int ensure_grads();
+    int refresh_train_weights(cudaStream_t s);
+    void free_train();
 };
 
 }  // namespace dcap

@@ -11,24 +11,11 @@
 // per step because the GEMM that consumes h_{t-1} also produces h_t).
 #include "decoder.cuh"
 #include "gemm_tc.cuh"
+#include "decoder_bf16.cuh"
 
 #include <stdlib.h>
 
 namespace dcap {
-
-struct Bf16State {
-    // weights (bf16, K-major)
-    __nv_bfloat16 *w_head1 = nullptr, *w_head2 = nullptr;
-    __nv_bfloat16 *w1cat = nullptr, *w1f = nullptr, *w2cat = nullptr, *wd1h = nullptr, *wd1f = nullptr, *wd2 = nullptr;
-    float *b1_i = nullptr, *b2_i = nullptr;          // gate-interleaved LSTM biases
-    __nv_bfloat16 *emb = nullptr;                    // [V, Epad] bf16 embedding table (zero padded)
-    int Epad = 0;
-    // activations
-    __nv_bfloat16 *roi = nullptr, *a1 = nullptr, *Fb = nullptr, *d = nullptr;
-    __nv_bfloat16 *X1[2] = {nullptr, nullptr}, *X2[2] = {nullptr, nullptr};
-    float *partial = nullptr;
-    int parity = 0;
-};
 
 void Decoder::free_bf16() {
     delete bf;
@@ -71,7 +58,7 @@ static int build_kmajor(const float *src, int n_src, int row_off, int K, int N, 
     return DC_OK;
 }
 
-int Decoder::finalize_bf16(cudaStream_t s) {
+int Decoder::refresh_bf16(bool fresh, cudaStream_t s) {
     if (!bf) bf = new Bf16State();
     Bf16State &b = *bf;
     const int F = cfg.feat, E = cfg.embed, U = cfg.units, V = cfg.vocab;
@@ -80,16 +67,26 @@ int Decoder::finalize_bf16(cudaStream_t s) {
     const int K1 = b.Epad + U;
     auto A16 = [&](__nv_bfloat16 **p, size_t n) { return dev_alloc((void **)p, 2 * n, owned); };
     int rc = 0;
-    rc |= A16(&b.w_head1, (size_t)F * Kin); rc |= A16(&b.w_head2, (size_t)F * F);
-    rc |= A16(&b.w1cat, (size_t)4 * U * K1); rc |= A16(&b.w1f, (size_t)4 * U * F);
-    rc |= A16(&b.w2cat, (size_t)4 * U * 2 * U);
-    rc |= A16(&b.wd1h, (size_t)kDense * U); rc |= A16(&b.wd1f, (size_t)kDense * F);
-    rc |= A16(&b.wd2, (size_t)V * kDense);
-    rc |= A16(&b.emb, (size_t)V * b.Epad);
-    rc |= dev_alloc((void **)&b.b1_i, sizeof(float) * 4 * U, owned);
-    rc |= dev_alloc((void **)&b.b2_i, sizeof(float) * 4 * U, owned);
-    if (rc) return rc;
-    DC_CHECK_CUDA(cudaMemsetAsync(b.w1cat, 0, 2 * (size_t)4 * U * K1, s));      // zero the E..Epad padding
+    if (fresh) {
+        rc |= A16(&b.w_head1, (size_t)F * Kin); rc |= A16(&b.w_head2, (size_t)F * F);
+        rc |= A16(&b.w1cat, (size_t)4 * U * K1); rc |= A16(&b.w1f, (size_t)4 * U * F);
+        rc |= A16(&b.w2cat, (size_t)4 * U * 2 * U);
+        rc |= A16(&b.wd1h, (size_t)kDense * U); rc |= A16(&b.wd1f, (size_t)kDense * F);
+        rc |= A16(&b.wd2, (size_t)V * kDense);
+        rc |= A16(&b.emb, (size_t)V * b.Epad);
+        rc |= dev_alloc((void **)&b.b1_i, sizeof(float) * 4 * U, owned);
+        rc |= dev_alloc((void **)&b.b2_i, sizeof(float) * 4 * U, owned);
+        if (rc) return rc;
+        DC_CHECK_CUDA(cudaMemsetAsync(b.w1cat, 0, 2 * (size_t)4 * U * K1, s));      // zero the E..Epad padding
+    }
+    if (emb_dirty) {
+        // the embedding table is frozen (trainable=False): rebuilt only when it is set
+        emb_dirty = false;
+        DC_CHECK_CUDA(cudaMemsetAsync(b.emb, 0, 2 * (size_t)V * b.Epad, s));
+        pad_rows_bf16_kernel<<<(unsigned)ceil_div<long long>((long long)V * E, 256), 256, 0, s>>>(
+            W("imgcap_embedding_layer/embeddings"), V, E, b.emb, b.Epad);
+        DC_CHECK_LAUNCH();
+    }
     rc |= build_kmajor(W("mrcnn_class_conv1/kernel"), F, 0, Kin, F, 0, b.w_head1, Kin, 0, s);
     rc |= build_kmajor(W("mrcnn_class_conv2/kernel"), F, 0, F, F, 0, b.w_head2, F, 0, s);
     rc |= build_kmajor(W("imgcap_lstm1/kernel"), 4 * U, 0, E, 4 * U, U, b.w1cat, K1, 0, s);
@@ -101,14 +98,10 @@ int Decoder::finalize_bf16(cudaStream_t s) {
     rc |= build_kmajor(W("imgcap_lstm_d1/kernel"), kDense, U, F, kDense, 0, b.wd1f, F, 0, s);
     rc |= build_kmajor(W("imgcap_lstm_d2/kernel"), V, 0, kDense, V, 0, b.wd2, kDense, 0, s);
     if (rc) return rc;
-    DC_CHECK_CUDA(cudaMemsetAsync(b.emb, 0, 2 * (size_t)V * b.Epad, s));
-    pad_rows_bf16_kernel<<<(unsigned)ceil_div<long long>((long long)V * E, 256), 256, 0, s>>>(
-        W("imgcap_embedding_layer/embeddings"), V, E, b.emb, b.Epad);
-    DC_CHECK_LAUNCH();
-    if (rc) return rc;
     interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm1/bias"), U, b.b1_i);
     interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm2/bias"), U, b.b2_i);
     DC_CHECK_LAUNCH();
+    if (b.train) return refresh_train_weights(s);
     return DC_OK;
 }
 

@@ -1,0 +1,40 @@
+// State of the bf16 / tcgen05 decoder path (decoder_bf16.cu) and of the training step (train.cu).
+#pragma once
+#include "decoder.cuh"
+#include "gemm_tc.cuh"
+
+namespace dcap {
+
+struct TrainState;                // train.cu
+
+struct Bf16State {
+    // weights (bf16, K-major)
+    __nv_bfloat16 *w_head1 = nullptr, *w_head2 = nullptr;
+    __nv_bfloat16 *w1cat = nullptr, *w1f = nullptr, *w2cat = nullptr, *wd1h = nullptr, *wd1f = nullptr, *wd2 = nullptr;
+    float *b1_i = nullptr, *b2_i = nullptr;          // gate-interleaved LSTM biases
+    __nv_bfloat16 *emb = nullptr;                    // [V, Epad] bf16 embedding table (zero padded)
+    int Epad = 0;
+    // activations
+    __nv_bfloat16 *roi = nullptr, *a1 = nullptr, *Fb = nullptr, *d = nullptr;
+    __nv_bfloat16 *X1[2] = {nullptr, nullptr}, *X2[2] = {nullptr, nullptr};
+    float *partial = nullptr;
+    int parity = 0;
+    // backward-pass operand copies: plain bf16 casts of the Keras [in, out] tensors, which are the
+    // K-major B operands of dX = dY * W^T (N = in, K = out); built by refresh_train_weights() (train.cu)
+    __nv_bfloat16 *wd2_k = nullptr;      // [1024, V]   imgcap_lstm_d2/kernel
+    __nv_bfloat16 *wd1h_k = nullptr;     // [U, 1024]   imgcap_lstm_d1/kernel[:U]
+    __nv_bfloat16 *wd1f_k = nullptr;     // [F, 1024]   imgcap_lstm_d1/kernel[U:]
+    __nv_bfloat16 *w2cat_k = nullptr;    // [2U, 4U]    [imgcap_lstm2/kernel ; recurrent_kernel]
+    __nv_bfloat16 *u1_k = nullptr;       // [U, 4U]     imgcap_lstm1/recurrent_kernel
+    __nv_bfloat16 *w1f_k = nullptr;      // [F, 4U]     imgcap_lstm1/kernel[E:]
+    __nv_bfloat16 *wc2_k = nullptr;      // [F, F]      mrcnn_class_conv2/kernel
+    TrainState *train = nullptr;
+};
+
+inline TcOperand tc_op(const __nv_bfloat16 *p, long long ld, bool mn_major = false) {
+    TcOperand o;
+    o.ptr = p; o.ld = ld; o.mn_major = mn_major;
+    return o;
+}
+
+}  // namespace dcap

@@ -113,25 +113,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // ------------------------------------------------------------------------------------------------
 // descriptors
 // ------------------------------------------------------------------------------------------------
-// Shared-memory matrix descriptor, K-major operand tile [rows][64 bf16] written by TMA with
-// CU_TENSOR_MAP_SWIZZLE_128B: 8-row groups of 1024 B (stride-dimension byte offset = 1024),
-// leading-dimension offset unused for swizzled K-major (set to 1), version 1 (sm_100),
-// layout type 2 = SWIZZLE_128B.  Fields are in 16-byte units.
-__device__ __forceinline__ uint64_t make_smem_desc_k_sw128(uint32_t smem_addr) {
+// Shared-memory matrix descriptors (fields in 16-byte units; version 1 = sm_100; layout type 2 =
+// SWIZZLE_128B).  Both operand forms are staged by TMA with CU_TENSOR_MAP_SWIZZLE_128B as 8 KB
+// slabs of 64 rows x 128 bytes:
+//   K-major  operand tile [rows][64 k]   : a slab row is one operand row (64 k values); 8-row groups
+//                                          are 1024 B apart (SBO = 1024); LBO unused (1); a k-step of
+//                                          16 elements advances the start address by 32 B.
+//   MN-major operand tile [64 k][64 mn]  : a slab row is one k (64 consecutive operand rows);
+//                                          8-k groups are 1024 B apart (SBO = 1024); the next 64
+//                                          operand rows live in the next slab (LBO = 8192); a k-step
+//                                          of 16 advances the start address by 16 rows = 2048 B.
+// (canonical layouts: Swizzle<3,4,3> o ((8,n),2):((8,SBO),1) and ((8,n),(8,k)):((1,LBO),(8,SBO)).)
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address      bits [0,14)
-    d |= (uint64_t)1 << 16;                               // leading byte off.  bits [16,30)
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;                // leading byte off.  bits [16,30)
     d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte off.   bits [32,46)
     d |= (uint64_t)1 << 46;                               // descriptor version bits [46,48)
     d |= (uint64_t)2 << 61;                               // SWIZZLE_128B       bits [61,64)
     return d;
 }
 
-// Instruction descriptor for kind::f16: D fp32, A/B bf16, both K-major, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+// Instruction descriptor for kind::f16: D fp32, A/B bf16, M x N tile; bit 15 / 16 = A / B MN-major.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
     return (1u << 4)                        // c_format  = F32
            | (1u << 7)                      // a_format  = BF16
            | (1u << 10)                     // b_format  = BF16
+           | ((uint32_t)(a_mn & 1) << 15)
+           | ((uint32_t)(b_mn & 1) << 16)
            | ((uint32_t)(N >> 3) << 17)     // n_dim
            | ((uint32_t)(M >> 4) << 24);    // m_dim
 }
@@ -142,8 +151,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                 // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
+constexpr int kSlab = 64 * 128;             // 8 KB: 64 rows x 128 B
 constexpr int kEpiWarps = 8;                // 2 per TMEM lane quarter: each owns half of the tile's columns
 constexpr int kThreads = 64 + 32 * kEpiWarps;
+
+struct TcGeom {
+    int M, N, K;
+    int a_mn, b_mn;          // operand majorness
+    int splits, kb_per;      // split-K: k-blocks [s*kb_per, min((s+1)*kb_per, num_kb)) per work unit
+};
 
 template <int kBlockN>
 struct TcSmem {
@@ -152,20 +168,6 @@ struct TcSmem {
     static constexpr int kStages = (kBlockN == 256) ? 4 : 6;
     static constexpr int kBytes = kStages * (kStageA + kStageB) + 1024 /*align*/ + 256 /*barriers*/;
 };
-
-// 32 lanes x 16 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // MUFU.TANH: max relative error 2^-11, well inside the bf16 operand rounding (2^-9) of this path
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -178,13 +180,25 @@ __device__ __forceinline__ float hard_sigmoid_tc(float x) {
     return fminf(fmaxf(__fadd_rn(__fmul_rn(0.2f, x), 0.5f), 0.f), 1.f);
 }
 
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // Epilogue of one (warp, column-half) region: rows = the warp's 32 TMEM lanes (lane i <-> row i),
 // columns [n_base, n_base + kCols) of the tile, pulled 32 columns at a time with tcgen05.ld.
+// Every variant is thread-per-row: a lane's global accesses are whole 32-byte sectors of its own
+// row, and the operands of the FIRST chunk are requested before the wait on the accumulator
+// barrier, those of chunk c+1 before chunk c is computed.
 template <int kCols, int kEpi>
-__device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t taddr, int lane,
-                                                int m_base, int n_base, int M, int N, int part_slot,
-                                                int part_slots) {
+__device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t taddr, int lane, int m_base, int n_base,
+                                                int M, int N, int part_slot, int part_slots, bool atomic,
+                                                uint64_t *full_bar, uint32_t full_phase) {
+    auto wait_acc = [&]() {
+        mbar_wait(full_bar, full_phase);
+        tc_fence_after();
+    };
     if constexpr (kEpi == kEpiArgmax || kEpi == kEpiArgmaxSum) {
+        wait_acc();
         // per-row statistics over this region: max, first arg-max (, sum exp(v - max))
         float best = -INFINITY, sum = 0.f;
         int best_i = 0x7fffffff;
@@ -219,33 +233,44 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
             *dst = make_float4(best, __int_as_float(best_i), sum, 0.f);
         }
     } else if constexpr (kEpi == kEpiStore) {
-        // Thread-per-row: lane i owns row m_base+i and pulls 32 consecutive columns straight out of
-        // TMEM, so its global accesses are whole 32-byte sectors of its own row (128 B of fp32 /
-        // 64 B of bf16 per chunk).  The addend of the NEXT chunk is requested before the current
-        // chunk's tcgen05.ld, which keeps one full round trip to L2/HBM in flight per lane.
         const int m = m_base + lane;
         const bool valid = m < M;
         const long long mr = valid ? m : (long long)(M - 1);
-        const float *add_row = ep.addend ? ep.addend + mr * ep.ld_addend : nullptr;
+        const float *add_row = ep.addend ? ep.addend + (ep.addend_mod > 0 ? mr % ep.addend_mod : mr) * ep.ld_addend : nullptr;
+        const __nv_bfloat16 *mask_row = ep.mask_src ? ep.mask_src + mr * ep.ld_mask : nullptr;
         const bool bf16_vec8 = ep.out_bf16 && ((ep.ld_bf16 & 7) == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0);
         float4 a_nxt[8];
-        auto load_addend = [&](int nb) {
+        uint4 k_nxt[4];
+        auto load_operands = [&](int nb) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 a_nxt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (add_row && nb + 4 * j + 4 <= N)
                     a_nxt[j] = __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j));
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                k_nxt[j] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);     // bf16 1.0: keep
+                if (mask_row && nb + 8 * j + 8 <= N)
+                    k_nxt[j] = __ldg(reinterpret_cast<const uint4 *>(mask_row + nb + 8 * j));
+            }
         };
-        load_addend(n_base);
+        if (n_base < N) load_operands(n_base);
+        wait_acc();
 #pragma unroll 1
         for (int c0 = 0; c0 < kCols; c0 += 32) {
             const int nb = n_base + c0;
             if (nb >= N) break;                                      // warp-uniform
             float4 a_cur[8];
+            uint32_t k_cur[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) a_cur[j] = a_nxt[j];
-            if (c0 + 32 < kCols && nb + 32 < N) load_addend(nb + 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                k_cur[4 * j] = k_nxt[j].x; k_cur[4 * j + 1] = k_nxt[j].y;
+                k_cur[4 * j + 2] = k_nxt[j].z; k_cur[4 * j + 3] = k_nxt[j].w;
+            }
+            if (c0 + 32 < kCols && nb + 32 < N) load_operands(nb + 32);
             float v[32];
             tmem_ld32(taddr + c0, v);
             if (nb + 32 <= N) {
@@ -268,14 +293,41 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
 #pragma unroll
                         for (int q = 0; q < 4; ++q) xs[q] = fmaxf(xs[q], 0.f);
                     }
+                    if (mask_row) {
+                        // ReLU backward: the forward activation (bf16, >= 0) is positive iff it passed
+                        const uint32_t w0 = k_cur[2 * j], w1 = k_cur[2 * j + 1];
+                        if ((w0 & 0x7fffu) == 0 || (w0 & 0x8000u)) xs[0] = 0.f;
+                        if ((w0 & 0x7fff0000u) == 0 || (w0 & 0x80000000u)) xs[1] = 0.f;
+                        if ((w1 & 0x7fffu) == 0 || (w1 & 0x8000u)) xs[2] = 0.f;
+                        if ((w1 & 0x7fff0000u) == 0 || (w1 & 0x80000000u)) xs[3] = 0.f;
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) v[4 * j + q] = xs[q];
                 }
                 if (valid) {
                     if (ep.out_f32) {
-                        float4 *dst = reinterpret_cast<float4 *>(ep.out_f32 + (long long)m * ep.ld_f32 + nb);
+                        if (ep.deint_units > 0) {
+                            // columns 4u+g of this chunk -> 8 consecutive units of each of the 4 gate blocks
+                            const int u0 = nb >> 2;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            for (int g = 0; g < 4; ++g) {
+                                float *dst = ep.out_f32 + (long long)m * ep.ld_f32 + (long long)g * ep.deint_units + u0;
+                                if (atomic) {
+                                    red_add_v4(dst, v[g], v[4 + g], v[8 + g], v[12 + g]);
+                                    red_add_v4(dst + 4, v[16 + g], v[20 + g], v[24 + g], v[28 + g]);
+                                } else {
+                                    reinterpret_cast<float4 *>(dst)[0] = make_float4(v[g], v[4 + g], v[8 + g], v[12 + g]);
+                                    reinterpret_cast<float4 *>(dst)[1] = make_float4(v[16 + g], v[20 + g], v[24 + g], v[28 + g]);
+                                }
+                            }
+                        } else {
+                            float *dst = ep.out_f32 + (long long)m * ep.ld_f32 + nb;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (atomic) red_add_v4(dst + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                else reinterpret_cast<float4 *>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            }
+                        }
                     }
                     if (ep.out_bf16) {
                         uint32_t pk[16];
@@ -297,7 +349,7 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
                     }
                 }
             } else if (valid) {
-                // ragged last chunk of the last N tile: element-wise
+                // ragged last chunk of the last N tile: element-wise (never with deint / mask)
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = nb + j;
@@ -307,23 +359,28 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
                     if (ep.bias) x += __ldg(ep.bias + n);
                     if (ep.scale) x = x * __ldg(ep.scale + n) + __ldg(ep.shift + n);
                     if (ep.relu) x = fmaxf(x, 0.f);
-                    if (ep.out_f32) ep.out_f32[(long long)m * ep.ld_f32 + n] = x;
+                    if (mask_row && !(__bfloat162float(mask_row[n]) > 0.f)) x = 0.f;
+                    if (ep.out_f32) {
+                        if (atomic) atomicAdd(ep.out_f32 + (long long)m * ep.ld_f32 + n, x);
+                        else ep.out_f32[(long long)m * ep.ld_f32 + n] = x;
+                    }
                     if (ep.out_bf16) ep.out_bf16[(long long)m * ep.ld_bf16 + n] = __float2bfloat16_rn(x);
                 }
             }
         }
     } else {
-        // kEpiCell, thread-per-row: columns are gate-interleaved, so the 32 columns of a chunk are
-        // the (i,f,g,o) pre-activations of 8 consecutive units of this lane's row.  Per chunk a
-        // lane reads 128 B of addend + 32 B of c, writes 32 B of c and 16 B of h (whole sectors);
-        // the next chunk's operands are requested before the current chunk is computed.
+        // kEpiCell: columns are gate-interleaved, so the 32 columns of a chunk are the (i,f,g,o)
+        // pre-activations of 8 consecutive units of this lane's row.  Per chunk a lane reads 128 B of
+        // addend + 32 B of c, writes 32 B of c and 16 B of h (whole sectors).
         const int m = m_base + lane;
         const bool valid = m < M;
         const long long mr = valid ? m : (long long)(M - 1);
-        const float *add_row = ep.addend ? ep.addend + mr * ep.ld_addend : nullptr;
-        float *c_row = ep.cell_c + mr * ep.cell_units;
+        const float *add_row = ep.addend ? ep.addend + (ep.addend_mod > 0 ? mr % ep.addend_mod : mr) * ep.ld_addend : nullptr;
+        const float *c_row = ep.cell_c + mr * ep.cell_units;
+        float *c_dst = (ep.cell_c_out ? ep.cell_c_out : ep.cell_c) + mr * ep.cell_units;
         const bool masked = ep.cell_tok && __ldg(ep.cell_tok + mr) == 0;
         float4 a_nxt[8], c_nxt[2];
+        uint4 h_nxt = make_uint4(0, 0, 0, 0);
         auto load_operands = [&](int nb) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -331,8 +388,10 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
             c_nxt[0] = *reinterpret_cast<const float4 *>(c_row + (nb >> 2));
             c_nxt[1] = *reinterpret_cast<const float4 *>(c_row + (nb >> 2) + 4);
+            if (masked) h_nxt = *reinterpret_cast<const uint4 *>(ep.cell_h_prev + mr * ep.ld_h_prev + (nb >> 2));
         };
         if (n_base < N) load_operands(n_base);
+        wait_acc();
 #pragma unroll 1
         for (int c0 = 0; c0 < kCols; c0 += 32) {
             const int nb = n_base + c0;
@@ -342,37 +401,33 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
             for (int j = 0; j < 8; ++j) a_cur[j] = a_nxt[j];
             const float c_old[8] = {c_nxt[0].x, c_nxt[0].y, c_nxt[0].z, c_nxt[0].w,
                                     c_nxt[1].x, c_nxt[1].y, c_nxt[1].z, c_nxt[1].w};
+            const uint32_t hw[4] = {h_nxt.x, h_nxt.y, h_nxt.z, h_nxt.w};
             if (c0 + 32 < kCols && nb + 32 < N) load_operands(nb + 32);
             float v[32];
             tmem_ld32(taddr + c0, v);
             const int u0 = nb >> 2;
             float c_new[8], h_new[8];
-            if (!masked) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float4 z = make_float4(v[4 * j] + a_cur[j].x, v[4 * j + 1] + a_cur[j].y, v[4 * j + 2] + a_cur[j].z,
-                                           v[4 * j + 3] + a_cur[j].w);
-                    if (ep.bias) {
-                        const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.bias + nb + 4 * j));
-                        z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w;
-                    }
-                    const float ig = hard_sigmoid_tc(z.x), fg = hard_sigmoid_tc(z.y);
-                    const float gg = tanh_fast(z.z), og = hard_sigmoid_tc(z.w);
-                    c_new[j] = __fadd_rn(__fmul_rn(fg, c_old[j]), __fmul_rn(ig, gg));
-                    h_new[j] = __fmul_rn(og, tanh_fast(c_new[j]));
+            for (int j = 0; j < 8; ++j) {
+                float4 z = make_float4(v[4 * j] + a_cur[j].x, v[4 * j + 1] + a_cur[j].y, v[4 * j + 2] + a_cur[j].z,
+                                       v[4 * j + 3] + a_cur[j].w);
+                if (ep.bias) {
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.bias + nb + 4 * j));
+                    z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w;
                 }
-            } else {                                                 // K.rnn mask: carry (h, c)
-                const uint4 hp = *reinterpret_cast<const uint4 *>(ep.cell_h_prev + mr * ep.ld_h_prev + u0);
-                const uint32_t hw[4] = {hp.x, hp.y, hp.z, hp.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                const float ig = hard_sigmoid_tc(z.x), fg = hard_sigmoid_tc(z.y);
+                const float gg = tanh_fast(z.z), og = hard_sigmoid_tc(z.w);
+                v[4 * j] = ig; v[4 * j + 1] = fg; v[4 * j + 2] = gg; v[4 * j + 3] = og;
+                c_new[j] = __fadd_rn(__fmul_rn(fg, c_old[j]), __fmul_rn(ig, gg));
+                h_new[j] = __fmul_rn(og, tanh_fast(c_new[j]));
+                if (masked) {                                        // K.rnn mask: carry (h, c)
                     c_new[j] = c_old[j];
                     h_new[j] = __uint_as_float((j & 1) ? (hw[j >> 1] & 0xffff0000u) : (hw[j >> 1] << 16));
                 }
             }
             if (valid) {
-                reinterpret_cast<float4 *>(c_row + u0)[0] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
-                reinterpret_cast<float4 *>(c_row + u0)[1] = make_float4(c_new[4], c_new[5], c_new[6], c_new[7]);
+                reinterpret_cast<float4 *>(c_dst + u0)[0] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
+                reinterpret_cast<float4 *>(c_dst + u0)[1] = make_float4(c_new[4], c_new[5], c_new[6], c_new[7]);
                 uint32_t pk[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -382,6 +437,11 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
                 const uint4 hv = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 if (ep.cell_h_a) *reinterpret_cast<uint4 *>(ep.cell_h_a + (long long)m * ep.ld_h_a + u0) = hv;
                 if (ep.cell_h_b) *reinterpret_cast<uint4 *>(ep.cell_h_b + (long long)m * ep.ld_h_b + u0) = hv;
+                if (ep.cell_gates_out) {                             // saved for the backward pass
+                    float4 *g = reinterpret_cast<float4 *>(ep.cell_gates_out + (long long)m * ep.ld_gates_out + nb);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) g[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
             }
         }
     }
@@ -390,7 +450,7 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
 template <int kBlockN, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const TcEpilogue ep, int M, int N, int K) {
+                    const TcEpilogue ep, const TcGeom g) {
     using S = TcSmem<kBlockN>;
     constexpr int kStages = S::kStages;
     constexpr uint32_t kTmemCols = 2 * kBlockN;                  // two accumulator buffers (power of 2)
@@ -404,10 +464,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t *tmem_empty = tmem_full + 2;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
+    const int M = g.M, N = g.N, K = g.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (N + kBlockN - 1) / kBlockN;
     const int tiles_m = (M + kBlockM - 1) / kBlockM;
-    const int num_tiles = tiles_m * tiles_n;
+    const int num_units = tiles_m * tiles_n * g.splits;
     const int num_kb = (K + kBlockK - 1) / kBlockK;
 
     if (warp == 0 && lane == 0) {
@@ -429,13 +490,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int tile = unit / g.splits, split = unit - tile * g.splits;
                 const int m0 = (tile / tiles_n) * kBlockM, n0 = (tile % tiles_n) * kBlockN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = split * g.kb_per, kb1 = min(kb0 + g.kb_per, num_kb);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], S::kStageA + S::kStageB);
-                    tma_load_2d(&map_a, &full_bar[stage], smem_a + stage * S::kStageA, kb * kBlockK, m0);
-                    tma_load_2d(&map_b, &full_bar[stage], smem_b + stage * S::kStageB, kb * kBlockK, n0);
+                    uint8_t *da = smem_a + stage * S::kStageA, *db = smem_b + stage * S::kStageB;
+                    if (!g.a_mn) {
+                        tma_load_2d(&map_a, &full_bar[stage], da, kb * kBlockK, m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < kBlockM / 64; ++c)
+                            tma_load_2d(&map_a, &full_bar[stage], da + c * kSlab, m0 + 64 * c, kb * kBlockK);
+                    }
+                    if (!g.b_mn) {
+                        tma_load_2d(&map_b, &full_bar[stage], db, kb * kBlockK, n0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < kBlockN / 64; ++c)
+                            tma_load_2d(&map_b, &full_bar[stage], db + c * kSlab, n0 + 64 * c, kb * kBlockK);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -444,25 +520,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, kBlockN);
+            const uint32_t idesc = make_idesc_bf16(kBlockM, kBlockN, g.a_mn, g.b_mn);
+            // per-operand descriptor constants: leading byte offset and start-address step per 16 k
+            const uint32_t a_lbo = g.a_mn ? kSlab : 16, b_lbo = g.b_mn ? kSlab : 16;
+            const uint32_t a_step = g.a_mn ? (16 * 128) >> 4 : 32 >> 4, b_step = g.b_mn ? (16 * 128) >> 4 : 32 >> 4;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int split = unit % g.splits;
+                const int kb0 = split * g.kb_per, kb1 = min(kb0 + g.kb_per, num_kb);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);             // epilogue drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kBlockN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);                // TMA bytes landed
                     tc_fence_after();
-                    const uint64_t a_desc = make_smem_desc_k_sw128(smem_u32(smem_a + stage * S::kStageA));
-                    const uint64_t b_desc = make_smem_desc_k_sw128(smem_u32(smem_b + stage * S::kStageB));
+                    const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * S::kStageA), a_lbo);
+                    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * S::kStageB), b_lbo);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        // advance 16 elements (32 B) along K inside the 128-byte swizzle row: +2 in 16-B units
-                        umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-                    }
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_bf16(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, (kb > kb0) || k != 0);
                     umma_commit(&empty_bar[stage]);                    // frees the smem slot when MMAs finish
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -477,16 +556,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
         const int half = e >> 2;                                       // which half of the tile's columns
         constexpr int kCols = kBlockN / 2;
+        const bool atomic = ep.atomic != 0 || g.splits > 1;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            const int tile = unit / g.splits;
             const int tile_n = tile % tiles_n;
             const int m0 = (tile / tiles_n) * kBlockM, n0 = tile_n * kBlockN;
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * kCols;
             epilogue_region<kCols, kEpi>(ep, taddr, lane, m0 + quarter * 32, n0 + half * kCols, M, N,
-                                         tile_n * 2 + half, tiles_n * 2);
+                                         tile_n * 2 + half, tiles_n * 2, atomic, &tmem_full[acc], acc_phase);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -521,24 +600,26 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols].
+// 2-D bf16 row-major [outer, inner] with leading dimension ld (elements); box = [box_outer, 64].
+// K-major operand: inner = K, outer = operand rows, box_outer = tile rows.
+// MN-major operand: inner = operand rows, outer = K, box_outer = 64 (one slab).
 // Encoding a map costs a driver call (~microseconds); the decoder re-uses a handful of
 // (pointer, shape) combinations every step, so encoded maps are memoised.
 struct TmapKey {
-    const void *ptr; long long rows, cols, ld; int box_rows;
+    const void *ptr; long long outer, inner, ld; int box_outer;
     bool operator<(const TmapKey &o) const {
         if (ptr != o.ptr) return ptr < o.ptr;
-        if (rows != o.rows) return rows < o.rows;
-        if (cols != o.cols) return cols < o.cols;
+        if (outer != o.outer) return outer < o.outer;
+        if (inner != o.inner) return inner < o.inner;
         if (ld != o.ld) return ld < o.ld;
-        return box_rows < o.box_rows;
+        return box_outer < o.box_outer;
     }
 };
 
-int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long rows, long long cols, long long ld, int box_rows) {
+int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long outer, long long inner, long long ld, int box_outer) {
     static std::map<TmapKey, CUtensorMap> cache;
     static std::mutex mu;
-    const TmapKey key{ptr, rows, cols, ld, box_rows};
+    const TmapKey key{ptr, outer, inner, ld, box_outer};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -547,9 +628,9 @@ int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long rows, long long 
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(DC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     DC_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, "TMA operand must be 16-byte aligned with ld %% 8 == 0");
-    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -564,7 +645,7 @@ int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long rows, long long 
 }
 
 template <int kBlockN, int kEpi>
-static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcEpilogue &ep, int M, int N, int K,
+static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcEpilogue &ep, const TcGeom &g,
                      cudaStream_t stream) {
     using S = TcSmem<kBlockN>;
     static bool attr_set = false;
@@ -573,48 +654,77 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcEpilo
         DC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
         attr_set = true;
     }
-    const int tiles = ceil_div(M, kBlockM) * ceil_div(N, kBlockN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, kThreads, S::kBytes, stream>>>(ma, mb, ep, M, N, K);
+    const int units = ceil_div(g.M, kBlockM) * ceil_div(g.N, kBlockN) * g.splits;
+    const int grid = units < sm_count() ? units : sm_count();
+    kern<<<grid, kThreads, S::kBytes, stream>>>(ma, mb, ep, g);
     DC_CHECK_LAUNCH();
     return DC_OK;
 }
 
 int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, int M, int N, int K, int epi,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, int split_k) {
     if (M <= 0 || N <= 0) return DC_OK;
     DC_REQUIRE(K > 0 && A.ptr && B.ptr, "gemm_bf16_tc: bad arguments");
-    const bool wide = N > 128;
+    const int sms = sm_count();
+    const int num_kb = ceil_div(K, kBlockK);
+    const int tiles_m = ceil_div(M, kBlockM);
+    // tile width: 256 columns unless that leaves most SMs without a tile and 128 fills more of them
+    bool wide = N > 128;
+    if (wide && epi != kEpiArgmax && epi != kEpiArgmaxSum) {
+        const int t256 = tiles_m * ceil_div(N, 256), t128 = tiles_m * ceil_div(N, 128);
+        if (t256 * 4 < sms * 3 && t128 > t256) wide = false;
+    }
+    const int tiles = tiles_m * ceil_div(N, wide ? 256 : 128);
+    TcGeom g;
+    g.M = M; g.N = N; g.K = K; g.a_mn = A.mn_major ? 1 : 0; g.b_mn = B.mn_major ? 1 : 0;
+    g.splits = 1;
+    if (epi == kEpiStore && ep.atomic && ep.out_f32 && !ep.out_bf16) {
+        int want = split_k;
+        if (want <= 0) {                      // fill ~2 waves, keep >= 8 k-blocks per unit
+            want = (2 * sms + tiles - 1) / tiles;
+            const int cap = num_kb / 8 > 0 ? num_kb / 8 : 1;
+            if (want > cap) want = cap;
+        }
+        if (want > num_kb) want = num_kb;
+        if (want < 1) want = 1;
+        g.splits = want;
+    }
+    g.kb_per = ceil_div(num_kb, g.splits);
+    g.splits = ceil_div(num_kb, g.kb_per);        // no empty work unit
     CUtensorMap ma, mb;
-    if (int rc = make_tmap_bf16(&ma, A.ptr, M, K, A.ld, kBlockM)) return rc;
-    if (int rc = make_tmap_bf16(&mb, B.ptr, N, K, B.ld, wide ? 256 : 128)) return rc;
+    if (A.mn_major) { if (int rc = make_tmap_bf16(&ma, A.ptr, K, M, A.ld, 64)) return rc; }
+    else            { if (int rc = make_tmap_bf16(&ma, A.ptr, M, K, A.ld, kBlockM)) return rc; }
+    if (B.mn_major) { if (int rc = make_tmap_bf16(&mb, B.ptr, K, N, B.ld, 64)) return rc; }
+    else            { if (int rc = make_tmap_bf16(&mb, B.ptr, N, K, B.ld, wide ? 256 : 128)) return rc; }
     if (epi == kEpiStore) {
         DC_REQUIRE(ep.out_f32 || ep.out_bf16, "gemm_bf16_tc: no output");
         DC_REQUIRE(!ep.out_f32 || (((uintptr_t)ep.out_f32 & 15) == 0 && ep.ld_f32 % 4 == 0), "fp32 output alignment");
         DC_REQUIRE(!ep.out_bf16 || (((uintptr_t)ep.out_bf16 & 7) == 0 && ep.ld_bf16 % 4 == 0), "bf16 output alignment");
         DC_REQUIRE(!ep.addend || (((uintptr_t)ep.addend & 15) == 0 && ep.ld_addend % 4 == 0), "addend alignment");
-        return wide ? launch_tc<256, kEpiStore>(ma, mb, ep, M, N, K, stream)
-                    : launch_tc<128, kEpiStore>(ma, mb, ep, M, N, K, stream);
+        DC_REQUIRE(!ep.mask_src || ((((uintptr_t)ep.mask_src & 15) == 0) && ep.ld_mask % 8 == 0 && N % 32 == 0),
+                   "mask source must be 16-byte aligned, ld %% 8 == 0, N %% 32 == 0");
+        DC_REQUIRE(ep.deint_units == 0 || (ep.out_f32 && !ep.out_bf16 && N == 4 * ep.deint_units && ep.deint_units % 8 == 0),
+                   "de-interleaved store needs fp32 output with N == 4*units, units %% 8 == 0");
+        return wide ? launch_tc<256, kEpiStore>(ma, mb, ep, g, stream) : launch_tc<128, kEpiStore>(ma, mb, ep, g, stream);
     }
     if (epi == kEpiCell) {
-        DC_REQUIRE(ep.cell_c && ep.cell_units * 4 == N && N % 16 == 0, "cell epilogue: N must be 4*units, units %% 4 == 0");
+        DC_REQUIRE(ep.cell_c && ep.cell_units * 4 == N && N % 32 == 0, "cell epilogue: N must be 4*units, units %% 8 == 0");
         DC_REQUIRE(!ep.cell_tok || ep.cell_h_prev, "cell epilogue: masking needs the previous h");
         DC_REQUIRE(!ep.addend || (((uintptr_t)ep.addend & 15) == 0 && ep.ld_addend % 4 == 0), "addend alignment");
-        DC_REQUIRE(ep.cell_units % 8 == 0, "cell epilogue: units must be a multiple of 8");
         DC_REQUIRE((!ep.cell_h_a || (ep.ld_h_a % 8 == 0 && ((uintptr_t)ep.cell_h_a & 15) == 0)) &&
                    (!ep.cell_h_b || (ep.ld_h_b % 8 == 0 && ((uintptr_t)ep.cell_h_b & 15) == 0)) &&
                    (!ep.cell_h_prev || (ep.ld_h_prev % 8 == 0 && ((uintptr_t)ep.cell_h_prev & 15) == 0)),
                    "cell epilogue: h buffers must be 16-byte aligned with ld %% 8 == 0");
-        return wide ? launch_tc<256, kEpiCell>(ma, mb, ep, M, N, K, stream)
-                    : launch_tc<128, kEpiCell>(ma, mb, ep, M, N, K, stream);
+        DC_REQUIRE(!ep.cell_gates_out || (((uintptr_t)ep.cell_gates_out & 15) == 0 && ep.ld_gates_out % 4 == 0),
+                   "cell epilogue: gate buffer alignment");
+        return wide ? launch_tc<256, kEpiCell>(ma, mb, ep, g, stream) : launch_tc<128, kEpiCell>(ma, mb, ep, g, stream);
     }
     DC_REQUIRE((epi == kEpiArgmax || epi == kEpiArgmaxSum) && ep.partial && ep.bias,
                "gemm_bf16_tc: arg-max epilogue needs bias and partial buffer");
     if (epi == kEpiArgmax)
-        return wide ? launch_tc<256, kEpiArgmax>(ma, mb, ep, M, N, K, stream)
-                    : launch_tc<128, kEpiArgmax>(ma, mb, ep, M, N, K, stream);
-    return wide ? launch_tc<256, kEpiArgmaxSum>(ma, mb, ep, M, N, K, stream)
-                : launch_tc<128, kEpiArgmaxSum>(ma, mb, ep, M, N, K, stream);
+        return wide ? launch_tc<256, kEpiArgmax>(ma, mb, ep, g, stream) : launch_tc<128, kEpiArgmax>(ma, mb, ep, g, stream);
+    return wide ? launch_tc<256, kEpiArgmaxSum>(ma, mb, ep, g, stream)
+                : launch_tc<128, kEpiArgmaxSum>(ma, mb, ep, g, stream);
 }
 
 int gemm_tc_argmax_tiles(int N) { return 2 * ceil_div(N, N > 128 ? 256 : 128); }

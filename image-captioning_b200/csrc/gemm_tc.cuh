@@ -10,8 +10,13 @@ constexpr int kEpiArgmaxSum = 2;    // ... + sum exp(v - max) (softmax probabili
 constexpr int kEpiCell = 3;         // fused Keras LSTM cell on gate-interleaved columns
 
 struct TcOperand {
-    const __nv_bfloat16 *ptr = nullptr;   // [rows, K] row-major, K contiguous
+    // K-major (default): [rows, K] row-major, K contiguous, ld = row stride.
+    // MN-major: the operand as it lies in memory when the GEMM contracts over ROWS, i.e.
+    // [K, rows] row-major (rows contiguous), ld = stride between consecutive k.  This is what the
+    // weight-gradient GEMMs X^T * dY consume: no activation is ever transposed in memory.
+    const __nv_bfloat16 *ptr = nullptr;
     long long ld = 0;                     // elements; multiple of 8
+    bool mn_major = false;
 };
 
 struct TcEpilogue {
@@ -23,6 +28,11 @@ struct TcEpilogue {
     int relu = 0;
     float *out_f32 = nullptr; long long ld_f32 = 0;
     __nv_bfloat16 *out_bf16 = nullptr; long long ld_bf16 = 0;
+    // kEpiStore extras (training)
+    int addend_mod = 0;                   // > 0: addend row = m % addend_mod (per-RoI term broadcast over time)
+    int deint_units = 0;                  // > 0: fp32 output column 4u+g is written to column g*units+u
+    const __nv_bfloat16 *mask_src = nullptr; long long ld_mask = 0;   // v = mask_src[m,n] > 0 ? v : 0 (ReLU backward)
+    int atomic = 0;                       // fp32 output is accumulated with red.global.add (implied by split-K)
     float *partial = nullptr;             // arg-max epilogues: [M, slots] float4 {max, argmax bits, sumexp, -}
     // kEpiCell: column n = 4*unit + gate (i,f,g,o); z = acc + addend + bias
     float *cell_c = nullptr;              // [M, cell_units] fp32, updated in place
@@ -31,11 +41,14 @@ struct TcEpilogue {
     const __nv_bfloat16 *cell_h_prev = nullptr; long long ld_h_prev = 0;   // previous h (for masked rows)
     __nv_bfloat16 *cell_h_a = nullptr; long long ld_h_a = 0;               // destinations of the new h
     __nv_bfloat16 *cell_h_b = nullptr; long long ld_h_b = 0;
+    float *cell_c_out = nullptr;          // null: c updated in place; else new c written here (training: time-major)
+    float *cell_gates_out = nullptr; long long ld_gates_out = 0;   // optional [M, 4*units] post-activation (i,f,g,o)
 };
 
 // D = epilogue(A * B^T): A [M,K], B [N,K], both bf16 K-major.
+// split_k: 0 = choose automatically (only kEpiStore with ep.atomic may split), 1 = never split.
 int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, int M, int N, int K, int epi,
-                 cudaStream_t stream);
+                 cudaStream_t stream, int split_k = 1);
 int gemm_tc_argmax_tiles(int N);
 int argmax_merge(const float *partial, int rows, int tiles, int32_t *tok_out, int tok_stride, int32_t *tok_cur,
                  float *maxprob, cudaStream_t s, const __nv_bfloat16 *emb = nullptr, int emb_ld = 0,

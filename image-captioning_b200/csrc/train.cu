@@ -1,0 +1,730 @@
+// Training step of the v1 "inject" caption model (bf16 tensor-core path, fp32 master weights).
+//
+// Reference (paths relative to /root/reference/dense_img_cap_separate_models):
+//   training graph   text_generation_model.py:159-189 (build_roi_caption_model_training), :264-277
+//   loss             text_generation_model.py:286-294 (roi_caption_loss -> K.categorical_crossentropy)
+//   optimiser        text_generation_model.py:425     (keras.optimizers.Adam(amsgrad=True))
+//   data generator   text_generation_model.py:332-371 (targets = shift-left(gt) ++ [0])
+//
+// The reference evaluates the word model once per prefix position (O(P^2) LSTM steps); the
+// causal, post-padded, masked structure makes that equal to ONE teacher-forced masked scan over
+// gt[:, 0..P-1] (oracle/decoder.py asserts the two forms identical), which is what runs here.
+//
+// Layout: every per-(time, RoI) activation is TIME-MAJOR, row = t*B + b.  The two recurrent GEMMs
+// (LSTM1, LSTM2: fused cell epilogues) run per step; everything that does not depend on the
+// recurrence is ONE GEMM over all P*B rows: dense1, the vocabulary projection, their data
+// gradients, and every weight gradient (X^T * dY with MN-major UMMA operands straight from the
+// saved activations, split-K + red.global.add).  The [P*B, V] one-hot targets are never built: the
+// fused softmax / cross-entropy kernel takes integer targets and overwrites the logits' role with
+// dlogits in bf16.
+//
+// Deviation: recurrent_dropout is not applied (the reference draws a fresh
+// per-gate mask per prefix position through TimeDistributed's K.rnn branch, which a single scan
+// cannot reproduce and TF's RNG stream could not be matched anyway); parity is defined with
+// dropout off.
+#include "decoder.cuh"
+#include "decoder_bf16.cuh"
+#include "gemm_tc.cuh"
+
+#include <math.h>
+
+namespace dcap {
+
+struct TrainState {
+    int B = 0, T = 0;                       // capacity the buffers were sized for
+    std::vector<void *> owned;
+    int32_t *tok_tm = nullptr, *tgt_tm = nullptr;                  // [T, B]
+    __nv_bfloat16 *X1 = nullptr, *X2 = nullptr;                    // [(T+1), B, K1] / [(T+1), B, 2U]
+    float *c1 = nullptr, *c2 = nullptr;                            // [(T+1), B, U]
+    float *gates1 = nullptr, *gates2 = nullptr;                    // [T, B, 4U] post-activation, gate-interleaved
+    __nv_bfloat16 *d_all = nullptr;                                // [T*B, 1024] relu(dense1)
+    float *logits = nullptr;                                       // [T*B, V]
+    __nv_bfloat16 *dz = nullptr;                                   // [T*B, V]   dlogits
+    __nv_bfloat16 *dd = nullptr;                                   // [T*B, 1024]
+    float *dh2d = nullptr;                                         // [T*B, U]   dense-path gradient of h2_t
+    __nv_bfloat16 *dz1_all = nullptr, *dz2_all = nullptr;          // [T*B, 4U]  Keras block order i|f|c|o
+    float *ddsum = nullptr, *dz1sum = nullptr;                     // [B, 1024] / [B, 4U] sums over time
+    __nv_bfloat16 *ddsum_b = nullptr, *dz1sum_b = nullptr;
+    float *dxh2 = nullptr, *dh1p = nullptr;                        // [B, 2U] / [B, U] per-step data gradients
+    float *carry1 = nullptr, *carry2 = nullptr, *dc1 = nullptr, *dc2 = nullptr;   // [B, U]
+    float *dF = nullptr, *da1 = nullptr;                           // [B, F]
+    __nv_bfloat16 *dzh2 = nullptr, *dzh1 = nullptr;                // [B, F] head pre-activation gradients
+    __nv_bfloat16 *x0 = nullptr;                                   // [B, Kin] bf16 copy of fp32 RoI features
+    float *rowloss = nullptr;                                      // [T*B]
+    const __nv_bfloat16 *x0_used = nullptr;                        // bf16 RoI features the last forward consumed
+};
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+void Decoder::free_train() {
+    if (bf && bf->train) {
+        for (void *p : bf->train->owned) cudaFree(p);
+        delete bf->train;
+        bf->train = nullptr;
+    }
+}
+
+int Decoder::ensure_grads() {
+    if (grads) return DC_OK;
+    const size_t bytes = sizeof(float) * (size_t)n_train;
+    for (float **p : {&grads, &adam_m, &adam_v, &adam_vhat}) {
+        DC_CHECK_CUDA(cudaMalloc((void **)p, bytes));
+        DC_CHECK_CUDA(cudaMemset(*p, 0, bytes));
+    }
+    return DC_OK;
+}
+
+// bf16 casts of the Keras-layout tensors used as K-major B operands by the data-gradient GEMMs
+int Decoder::refresh_train_weights(cudaStream_t s) {
+    Bf16State &b = *bf;
+    const size_t F = cfg.feat, E = cfg.embed, U = cfg.units, V = cfg.vocab;
+    if (!b.wd2_k) {
+        auto A16 = [&](__nv_bfloat16 **p, size_t n) { return dev_alloc((void **)p, 2 * n, owned); };
+        int rc = 0;
+        rc |= A16(&b.wd2_k, (size_t)kDense * V); rc |= A16(&b.wd1h_k, U * kDense); rc |= A16(&b.wd1f_k, F * kDense);
+        rc |= A16(&b.w2cat_k, 2 * U * 4 * U); rc |= A16(&b.u1_k, U * 4 * U); rc |= A16(&b.w1f_k, F * 4 * U);
+        rc |= A16(&b.wc2_k, F * F);
+        if (rc) return rc;
+    }
+    int rc = 0;
+    rc |= f32_to_bf16(W("imgcap_lstm_d2/kernel"), b.wd2_k, (long long)kDense * V, s);
+    rc |= f32_to_bf16(W("imgcap_lstm_d1/kernel"), b.wd1h_k, (long long)U * kDense, s);
+    rc |= f32_to_bf16(W("imgcap_lstm_d1/kernel") + U * kDense, b.wd1f_k, (long long)F * kDense, s);
+    // lstm2 kernel and recurrent_kernel are adjacent in the arena: [W2 ; U2] is one range
+    DC_REQUIRE(W("imgcap_lstm2/recurrent_kernel") == W("imgcap_lstm2/kernel") + U * 4 * U, "arena layout");
+    rc |= f32_to_bf16(W("imgcap_lstm2/kernel"), b.w2cat_k, (long long)2 * U * 4 * U, s);
+    rc |= f32_to_bf16(W("imgcap_lstm1/recurrent_kernel"), b.u1_k, (long long)U * 4 * U, s);
+    rc |= f32_to_bf16(W("imgcap_lstm1/kernel") + E * 4 * U, b.w1f_k, (long long)F * 4 * U, s);
+    rc |= f32_to_bf16(W("mrcnn_class_conv2/kernel"), b.wc2_k, (long long)F * F, s);
+    return rc;
+}
+
+static int train_reserve(Decoder &D, int B, int T) {
+    Bf16State &b = *D.bf;
+    if (b.train && b.train->B >= B && b.train->T >= T) return DC_OK;
+    D.free_train();
+    b.train = new TrainState();
+    TrainState &t = *b.train;
+    const DcDecoderConfig &c = D.cfg;
+    const size_t U = c.units, F = c.feat, V = c.vocab, K1 = b.Epad + U, Kin = (size_t)c.pool * c.pool * c.channels;
+    const size_t Bp = round_up(B, 128), R = (size_t)T * Bp;
+    auto A = [&](void **p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+        if (e != cudaSuccess) return set_error(DC_ERR_CUDA, "training workspace allocation failed: %s", cudaGetErrorString(e));
+        t.owned.push_back(*p);
+        return DC_OK;
+    };
+    int rc = 0;
+    rc |= A((void **)&t.tok_tm, 4 * R); rc |= A((void **)&t.tgt_tm, 4 * R);
+    rc |= A((void **)&t.X1, 2 * (R + Bp) * K1); rc |= A((void **)&t.X2, 2 * (R + Bp) * 2 * U);
+    rc |= A((void **)&t.c1, 4 * (R + Bp) * U); rc |= A((void **)&t.c2, 4 * (R + Bp) * U);
+    rc |= A((void **)&t.gates1, 4 * R * 4 * U); rc |= A((void **)&t.gates2, 4 * R * 4 * U);
+    rc |= A((void **)&t.d_all, 2 * R * kDense);
+    rc |= A((void **)&t.logits, 4 * R * V); rc |= A((void **)&t.dz, 2 * R * V);
+    rc |= A((void **)&t.dd, 2 * R * kDense); rc |= A((void **)&t.dh2d, 4 * R * U);
+    rc |= A((void **)&t.dz1_all, 2 * R * 4 * U); rc |= A((void **)&t.dz2_all, 2 * R * 4 * U);
+    rc |= A((void **)&t.ddsum, 4 * Bp * kDense); rc |= A((void **)&t.dz1sum, 4 * Bp * 4 * U);
+    rc |= A((void **)&t.ddsum_b, 2 * Bp * kDense); rc |= A((void **)&t.dz1sum_b, 2 * Bp * 4 * U);
+    rc |= A((void **)&t.dxh2, 4 * Bp * 2 * U); rc |= A((void **)&t.dh1p, 4 * Bp * U);
+    rc |= A((void **)&t.carry1, 4 * Bp * U); rc |= A((void **)&t.carry2, 4 * Bp * U);
+    rc |= A((void **)&t.dc1, 4 * Bp * U); rc |= A((void **)&t.dc2, 4 * Bp * U);
+    rc |= A((void **)&t.dF, 4 * Bp * F); rc |= A((void **)&t.da1, 4 * Bp * F);
+    rc |= A((void **)&t.dzh2, 2 * Bp * F); rc |= A((void **)&t.dzh1, 2 * Bp * F);
+    rc |= A((void **)&t.x0, 2 * Bp * Kin);
+    rc |= A((void **)&t.rowloss, 4 * R);
+    if (rc) { D.free_train(); return rc; }
+    t.B = B; t.T = T;
+    return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+
+// gt [B, T] (ids as the data generator yields them) -> time-major token / target columns.
+// targets == nullptr: targets = shift-left(gt) ++ [0]  (text_generation_model.py:352-358)
+__global__ void time_major_tokens_kernel(const int32_t *__restrict__ gt, const int32_t *__restrict__ targets, int B,
+                                         int T, int V, int32_t *__restrict__ tok_tm, int32_t *__restrict__ tgt_tm) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * T) return;
+    const int t = idx / B, b = idx - t * B;
+    int w = gt[(long long)b * T + t];
+    w = w < 0 ? 0 : (w >= V ? V - 1 : w);
+    tok_tm[idx] = w;
+    int y = targets ? targets[(long long)b * T + t] : (t + 1 < T ? gt[(long long)b * T + t + 1] : 0);
+    tgt_tm[idx] = y >= V ? V - 1 : y;                     // negative target = position ignored
+}
+
+// X[r, 0:Epad] = emb_bf16[tok[r], 0:Epad]  (frozen embedding, zero padded to Epad)
+__global__ void gather_embedding_rows_kernel(const uint4 *__restrict__ emb, int emb_ld8, const int32_t *__restrict__ tok,
+                                             long long rows, uint4 *__restrict__ X, long long ld8) {
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const uint4 *src = emb + (long long)tok[r] * emb_ld8;
+    uint4 *dst = X + r * ld8;
+    for (int j = lane; j < emb_ld8; j += 32) dst[j] = __ldg(src + j);
+}
+
+// Fused softmax + Keras categorical_crossentropy (forward value and gradient w.r.t. the logits) on
+// integer targets; one CTA per (time, RoI) row.
+//   p = softmax(z); loss_row = -log(clip(p_y, 1e-7, 1-1e-7)); dz = (p - onehot(y)) * inv_count, and
+//   zero when the clip is active (the clip has zero gradient) or the position is ignored (y < 0).
+__global__ void __launch_bounds__(256) softmax_xent_kernel(const float *__restrict__ logits, long long ld, int V,
+                                                           const int32_t *__restrict__ tgt, float inv_count,
+                                                           __nv_bfloat16 *__restrict__ dz, long long ld_dz,
+                                                           float *__restrict__ rowloss) {
+    const long long r = blockIdx.x;
+    const float *z = logits + r * ld;
+    __nv_bfloat16 *g = dz + r * ld_dz;
+    const int y = tgt[r];
+    __shared__ float red[2][8];
+    float mx = -INFINITY, sum = 0.f;
+    for (int j = threadIdx.x * 4; j < V; j += 256 * 4) {
+        float v[4];
+        if (j + 4 <= V) {
+            const float4 q = *reinterpret_cast<const float4 *>(z + j);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+            for (int i = 0; i < 4; ++i) v[i] = (j + i < V) ? z[j + i] : -INFINITY;
+        }
+        const float m4 = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+        if (m4 > mx) { sum *= __expf(mx - m4); mx = m4; }
+        for (int i = 0; i < 4; ++i) sum += __expf(v[i] - mx);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
+        const float nm = fmaxf(mx, om);
+        sum = sum * __expf(mx - nm) + os * __expf(om - nm);
+        mx = nm;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = mx; red[1][warp] = sum; }
+    __syncthreads();
+    float gm = red[0][0];
+    for (int i = 1; i < 8; ++i) gm = fmaxf(gm, red[0][i]);
+    float gs = 0.f;
+    for (int i = 0; i < 8; ++i) gs += red[1][i] * __expf(red[0][i] - gm);
+    const float inv = 1.0f / gs;
+    bool live = y >= 0;
+    if (live) {
+        const float py = __expf(z[y] - gm) * inv;
+        if (threadIdx.x == 0) rowloss[r] = -logf(fminf(fmaxf(py, 1e-7f), 1.0f - 1e-7f));
+        live = py > 1e-7f && py < 1.0f - 1e-7f;
+    } else if (threadIdx.x == 0) {
+        rowloss[r] = 0.f;
+    }
+    const float sc = live ? inv_count : 0.f;
+    for (int j = threadIdx.x * 4; j < V; j += 256 * 4) {
+        if (j + 4 <= V) {
+            const float4 q = *reinterpret_cast<const float4 *>(z + j);
+            float p[4] = {__expf(q.x - gm) * inv, __expf(q.y - gm) * inv, __expf(q.z - gm) * inv, __expf(q.w - gm) * inv};
+            if (y >= j && y < j + 4) p[y - j] -= 1.0f;
+            __nv_bfloat162 lo = __floats2bfloat162_rn(p[0] * sc, p[1] * sc), hi = __floats2bfloat162_rn(p[2] * sc, p[3] * sc);
+            uint2 pk = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+            *reinterpret_cast<uint2 *>(g + j) = pk;
+        } else {
+            for (int i = 0; j + i < V; ++i) {
+                float p = __expf(z[j + i] - gm) * inv;
+                if (y == j + i) p -= 1.0f;
+                g[j + i] = __float2bfloat16_rn(p * sc);
+            }
+        }
+    }
+}
+
+// loss = sum(rowloss) * inv_count, deterministic (one CTA, fixed order)
+__global__ void __launch_bounds__(1024) reduce_loss_kernel(const float *__restrict__ rowloss, long long n, float inv_count,
+                                                           float *__restrict__ loss) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) acc += (double)rowloss[i];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = red[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) *loss = (float)(acc * (double)inv_count);
+    }
+}
+
+// out[c] += sum_r src[r, c]; grid (column strips of 256, row chunks); src bf16 or fp32
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T *__restrict__ src, long long rows, int cols, long long ld,
+                                                     int rows_per_block, float *__restrict__ out) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= cols) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float acc = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+        if constexpr (sizeof(T) == 2) acc += __bfloat162float(src[r * ld + c]);
+        else acc += src[r * ld + c];
+    }
+    atomicAdd(out + c, acc);
+}
+
+template <typename T>
+static int colsum(const T *src, long long rows, int cols, long long ld, float *out, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return DC_OK;
+    const int rpb = 256;
+    dim3 grid(ceil_div(cols, 256), (unsigned)ceil_div<long long>(rows, rpb));
+    colsum_kernel<T><<<grid, 256, 0, s>>>(src, rows, cols, ld, rpb, out);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
+// sum over time of a time-major bf16 tensor: out[b, n] = sum_t src[(t*B + b), n]
+__global__ void time_sum_kernel(const __nv_bfloat16 *__restrict__ src, int B, int T, int N, float *__restrict__ out_f32,
+                                __nv_bfloat16 *__restrict__ out_bf16) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * N) return;
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) acc += __bfloat162float(src[(long long)t * B * N + idx]);
+    out_f32[idx] = acc;
+    out_bf16[idx] = __float2bfloat16_rn(acc);
+}
+
+__global__ void f32_to_bf16_rows_kernel(const float *__restrict__ src, long long n, __nv_bfloat16 *__restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// Backward of one Keras LSTM cell step for 4 consecutive units of one row.
+//   gates      [B, 4U] post-activation (i, f, g, o), gate-interleaved (column 4u+gate), saved by the forward epilogue
+//   c_prev/c_new  the cell state before / after the step
+//   dh = dh_a (+ dh_b) + carry;  masked row (tok == 0): dz = 0, carry <- dh, dc unchanged
+//   else: dz (Keras block order i|f|c|o, bf16), dc <- dc_prev, carry <- 0, dzsum += dz (optional)
+__global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(int B, int U, const float *__restrict__ gates,
+                                                            const float *__restrict__ c_prev, const float *__restrict__ c_new,
+                                                            const int32_t *__restrict__ tok, const float *__restrict__ dh_a,
+                                                            int ld_a, const float *__restrict__ dh_b, int ld_b,
+                                                            float *__restrict__ carry, float *__restrict__ dc,
+                                                            __nv_bfloat16 *__restrict__ dz, float *__restrict__ dzsum) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int uq = U >> 2;
+    if (idx >= (long long)B * uq) return;
+    const int b = (int)(idx / uq), u0 = (int)(idx - (long long)b * uq) * 4;
+    const long long so = (long long)b * U + u0;
+    float4 dh = *reinterpret_cast<const float4 *>(dh_a + (long long)b * ld_a + u0);
+    if (dh_b) {
+        const float4 t = *reinterpret_cast<const float4 *>(dh_b + (long long)b * ld_b + u0);
+        dh.x += t.x; dh.y += t.y; dh.z += t.z; dh.w += t.w;
+    }
+    {
+        const float4 t = *reinterpret_cast<const float4 *>(carry + so);
+        dh.x += t.x; dh.y += t.y; dh.z += t.z; dh.w += t.w;
+    }
+    __nv_bfloat16 *dzr = dz + (long long)b * 4 * U + u0;
+    if (tok[b] == 0) {
+        *reinterpret_cast<float4 *>(carry + so) = dh;
+        const uint2 zero = make_uint2(0u, 0u);
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<uint2 *>(dzr + (long long)g * U) = zero;
+        return;
+    }
+    *reinterpret_cast<float4 *>(carry + so) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 dcv = *reinterpret_cast<const float4 *>(dc + so);
+    const float4 cpv = *reinterpret_cast<const float4 *>(c_prev + so);
+    const float4 cnv = *reinterpret_cast<const float4 *>(c_new + so);
+    const float dhs[4] = {dh.x, dh.y, dh.z, dh.w}, dcs[4] = {dcv.x, dcv.y, dcv.z, dcv.w};
+    const float cps[4] = {cpv.x, cpv.y, cpv.z, cpv.w}, cns[4] = {cnv.x, cnv.y, cnv.z, cnv.w};
+    float dzi[4], dzf[4], dzg[4], dzo[4], dcp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 gt = *reinterpret_cast<const float4 *>(gates + (long long)b * 4 * U + 4 * (u0 + j));
+        const float ig = gt.x, fg = gt.y, gg = gt.z, og = gt.w;
+        const float tc = tanhf(cns[j]);
+        const float dcn = dcs[j] + dhs[j] * og * (1.f - tc * tc);
+        // hard_sigmoid'(z) = 0.2 inside the linear range, i.e. where the activation is strictly in (0, 1)
+        dzi[j] = (ig > 0.f && ig < 1.f) ? 0.2f * dcn * gg : 0.f;
+        dzf[j] = (fg > 0.f && fg < 1.f) ? 0.2f * dcn * cps[j] : 0.f;
+        dzg[j] = dcn * ig * (1.f - gg * gg);
+        dzo[j] = (og > 0.f && og < 1.f) ? 0.2f * dhs[j] * tc : 0.f;
+        dcp[j] = dcn * fg;
+    }
+    *reinterpret_cast<float4 *>(dc + so) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+    const float *blocks[4] = {dzi, dzf, dzg, dzo};
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(blocks[g][0], blocks[g][1]), hi = __floats2bfloat162_rn(blocks[g][2], blocks[g][3]);
+        *reinterpret_cast<uint2 *>(dzr + (long long)g * U) = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+        if (dzsum) {
+            float4 *sp = reinterpret_cast<float4 *>(dzsum + (long long)b * 4 * U + (long long)g * U + u0);
+            float4 a = *sp;
+            a.x += blocks[g][0]; a.y += blocks[g][1]; a.z += blocks[g][2]; a.w += blocks[g][3];
+            *sp = a;
+        }
+    }
+}
+
+// Backward through relu(BatchNorm_frozen(z)) of the RoI head (modified_dense_model.py:52-62: BN runs
+// with training=False, gamma/beta stay trainable): y = z*s + (beta - mean*s), s = gamma*rsqrt(var+eps).
+//   dy = dx where act > 0;  dz = dy*s (bf16, the conv data/weight gradient operand)
+//   dbeta += sum dy;  dgamma += sum dy*(z-mean)*rsqrt(var+eps) = sum dy*(act-beta)/gamma;  dbias += sum dz
+// block (32, 8): a 32-column strip x rows_per_block rows.
+__global__ void __launch_bounds__(256) bn_relu_bwd_kernel(const float *__restrict__ dx, const __nv_bfloat16 *__restrict__ act,
+                                                          int B, int N, const float *__restrict__ scale,
+                                                          const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                          int rows_per_block, __nv_bfloat16 *__restrict__ dz,
+                                                          float *__restrict__ dgamma, float *__restrict__ dbeta,
+                                                          float *__restrict__ dbias) {
+    const int n = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, B);
+    __shared__ float red[3][8][33];
+    float sg = 0.f, sb = 0.f, sz = 0.f;
+    if (n < N) {
+        const float s = scale[n], ga = gamma[n], be = beta[n];
+        const float inv_g = ga != 0.f ? 1.0f / ga : 0.f;
+        for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+            const long long o = (long long)r * N + n;
+            const float a = __bfloat162float(act[o]);
+            const float dy = a > 0.f ? dx[o] : 0.f;
+            const float v = dy * s;
+            dz[o] = __float2bfloat16_rn(v);
+            sb += dy; sg += dy * (a - be) * inv_g; sz += v;
+        }
+    }
+    red[0][threadIdx.y][threadIdx.x] = sg; red[1][threadIdx.y][threadIdx.x] = sb; red[2][threadIdx.y][threadIdx.x] = sz;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float a = 0.f, b2 = 0.f, c = 0.f;
+        for (int i = 0; i < 8; ++i) { a += red[0][i][threadIdx.x]; b2 += red[1][i][threadIdx.x]; c += red[2][i][threadIdx.x]; }
+        atomicAdd(dgamma + n, a); atomicAdd(dbeta + n, b2); atomicAdd(dbias + n, c);
+    }
+}
+
+// keras.optimizers.Adam.get_updates (amsgrad optional), SURVEY.md A11:
+//   m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g^2;  vhat = max(vhat, v);  p -= lr_t * m / (sqrt(vhat) + eps)
+// with lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed on the host in double; g is scaled by grad_scale first
+// (1/world after a sum all-reduce).
+__global__ void adam_amsgrad_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                    float *__restrict__ v, float *__restrict__ vhat, long long n, float lr_t, float b1,
+                                    float b2, float eps, int amsgrad, float grad_scale) {
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;                                   // n is a multiple of 64
+    const float4 g4 = *reinterpret_cast<const float4 *>(g + i);
+    float4 m4 = *reinterpret_cast<float4 *>(m + i), v4 = *reinterpret_cast<float4 *>(v + i);
+    float4 h4 = *reinterpret_cast<float4 *>(vhat + i), p4 = *reinterpret_cast<float4 *>(p + i);
+    const float gs[4] = {g4.x * grad_scale, g4.y * grad_scale, g4.z * grad_scale, g4.w * grad_scale};
+    float ms[4] = {m4.x, m4.y, m4.z, m4.w}, vs[4] = {v4.x, v4.y, v4.z, v4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
+    float ps[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ms[j] = __fadd_rn(__fmul_rn(b1, ms[j]), __fmul_rn(1.f - b1, gs[j]));
+        vs[j] = __fadd_rn(__fmul_rn(b2, vs[j]), __fmul_rn(1.f - b2, __fmul_rn(gs[j], gs[j])));
+        float den;
+        if (amsgrad) { hs[j] = fmaxf(hs[j], vs[j]); den = __fadd_rn(sqrtf(hs[j]), eps); }
+        else den = __fadd_rn(sqrtf(vs[j]), eps);
+        ps[j] = __fsub_rn(ps[j], __fdiv_rn(__fmul_rn(lr_t, ms[j]), den));
+    }
+    *reinterpret_cast<float4 *>(m + i) = make_float4(ms[0], ms[1], ms[2], ms[3]);
+    *reinterpret_cast<float4 *>(v + i) = make_float4(vs[0], vs[1], vs[2], vs[3]);
+    if (amsgrad) *reinterpret_cast<float4 *>(vhat + i) = make_float4(hs[0], hs[1], hs[2], hs[3]);
+    *reinterpret_cast<float4 *>(p + i) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the step
+// ------------------------------------------------------------------------------------------------
+// Teacher-forced forward up to the logits [T*B, V] (time-major) with every activation the backward needs.
+int Decoder::train_forward(const void *feats, int kind, int B, const int32_t *gt, const int32_t *targets, cudaStream_t s) {
+    if (int rc = check_ready(B)) return rc;
+    DC_REQUIRE(cfg.arch == DC_ARCH_V1 && cfg.dtype == DC_DTYPE_BF16, "the training graph is served by the bf16 v1 decoder");
+    DC_REQUIRE(cfg.vocab % 8 == 0, "training needs VOCABULARY_SIZE %% 8 == 0 (vector gradient stores)");
+    DC_REQUIRE(B > 0 && feats && gt, "null pointer argument / empty batch");
+    if (int rc = reserve(B)) return rc;
+    Bf16State &b = *bf;
+    const int T = cfg.padding, U = cfg.units, V = cfg.vocab;
+    const int K1 = b.Epad + U, Kin = cfg.pool * cfg.pool * cfg.channels;
+    if (int rc = train_reserve(*this, B, T)) return rc;
+    TrainState &t = *b.train;
+    const long long R = (long long)T * B;
+    const bool train_head = kind != DC_FEATS_HEAD_F32;
+
+    // ---------------- forward ----------------
+    time_major_tokens_kernel<<<ceil_div((int)R, 256), 256, 0, s>>>(gt, targets, B, T, V, t.tok_tm, t.tgt_tm);
+    DC_CHECK_LAUNCH();
+    const __nv_bfloat16 *x0 = nullptr;
+    if (kind == DC_FEATS_ROI_BF16) {
+        x0 = reinterpret_cast<const __nv_bfloat16 *>(feats);
+    } else if (kind == DC_FEATS_ROI_F32) {
+        if (int rc = f32_to_bf16((const float *)feats, t.x0, (long long)B * Kin, s)) return rc;
+        x0 = t.x0;
+    }
+    if (int rc = head(train_head ? (const void *)x0 : feats, train_head ? DC_FEATS_ROI_BF16 : kind, B, ws.F, s)) return rc;
+    if (int rc = v1_hoist_bf16(B, s)) return rc;                       // ws.g1f (gate-interleaved, + b1), ws.d1f (+ bd1)
+
+    // slot 0 of the state buffers = zero state; embedding rows of every (t, b) gathered at once
+    DC_CHECK_CUDA(cudaMemsetAsync(t.X1, 0, 2 * (size_t)B * K1, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(t.X2, 0, 2 * (size_t)B * 2 * U, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(t.c1, 0, 4 * (size_t)B * U, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(t.c2, 0, 4 * (size_t)B * U, s));
+    gather_embedding_rows_kernel<<<(unsigned)ceil_div<long long>(R * 32, 256), 256, 0, s>>>(
+        reinterpret_cast<const uint4 *>(b.emb), b.Epad / 8, t.tok_tm, R, reinterpret_cast<uint4 *>(t.X1), K1 / 8);
+    DC_CHECK_LAUNCH();
+    for (int st = 0; st < T; ++st) {
+        __nv_bfloat16 *x1 = t.X1 + (size_t)st * B * K1, *x1n = x1 + (size_t)B * K1;
+        __nv_bfloat16 *x2 = t.X2 + (size_t)st * B * 2 * U, *x2n = x2 + (size_t)B * 2 * U;
+        const int32_t *tok = t.tok_tm + (size_t)st * B;
+        TcEpilogue c1;
+        c1.addend = ws.g1f; c1.ld_addend = 4 * U; c1.cell_units = U; c1.cell_tok = tok;
+        c1.cell_c = t.c1 + (size_t)st * B * U; c1.cell_c_out = t.c1 + (size_t)(st + 1) * B * U;
+        c1.cell_h_prev = x1 + b.Epad; c1.ld_h_prev = K1;
+        c1.cell_h_a = x1n + b.Epad; c1.ld_h_a = K1;
+        c1.cell_h_b = x2; c1.ld_h_b = 2 * U;
+        c1.cell_gates_out = t.gates1 + (size_t)st * B * 4 * U; c1.ld_gates_out = 4 * U;
+        if (int rc = gemm_bf16_tc(tc_op(x1, K1), tc_op(b.w1cat, K1), c1, B, 4 * U, K1, kEpiCell, s)) return rc;
+        TcEpilogue c2;
+        c2.bias = b.b2_i; c2.cell_units = U; c2.cell_tok = tok;
+        c2.cell_c = t.c2 + (size_t)st * B * U; c2.cell_c_out = t.c2 + (size_t)(st + 1) * B * U;
+        c2.cell_h_prev = x2 + U; c2.ld_h_prev = 2 * U;
+        c2.cell_h_a = x2n + U; c2.ld_h_a = 2 * U;
+        c2.cell_gates_out = t.gates2 + (size_t)st * B * 4 * U; c2.ld_gates_out = 4 * U;
+        if (int rc = gemm_bf16_tc(tc_op(x2, 2 * U), tc_op(b.w2cat, 2 * U), c2, B, 4 * U, 2 * U, kEpiCell, s)) return rc;
+    }
+    // h2_t of row (t, b) lives in X2 slot t+1, columns U..2U: one strided view over all T*B rows
+    const __nv_bfloat16 *h2_all = t.X2 + (size_t)B * 2 * U + U;
+    {
+        TcEpilogue e;
+        e.addend = ws.d1f; e.ld_addend = kDense; e.addend_mod = B; e.relu = 1; e.out_bf16 = t.d_all; e.ld_bf16 = kDense;
+        if (int rc = gemm_bf16_tc(tc_op(h2_all, 2 * U), tc_op(b.wd1h, U), e, (int)R, kDense, U, kEpiStore, s)) return rc;
+        TcEpilogue v;
+        v.bias = W("imgcap_lstm_d2/bias"); v.out_f32 = t.logits; v.ld_f32 = V;
+        if (int rc = gemm_bf16_tc(tc_op(t.d_all, kDense), tc_op(b.wd2, kDense), v, (int)R, V, kDense, kEpiStore, s)) return rc;
+    }
+    t.x0_used = x0;
+    return DC_OK;
+}
+
+int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, const int32_t *targets, float inv_count,
+                        float *loss, cudaStream_t s) {
+    DC_REQUIRE(loss, "null loss pointer");
+    if (int rc = train_forward(feats, kind, B, gt, targets, s)) return rc;
+    if (int rc = ensure_grads()) return rc;
+    Bf16State &b = *bf;
+    if (!b.wd2_k)
+        if (int rc = refresh_train_weights(s)) return rc;
+    const int T = cfg.padding, U = cfg.units, F = cfg.feat, E = cfg.embed, V = cfg.vocab;
+    const int K1 = b.Epad + U, Kin = cfg.pool * cfg.pool * cfg.channels;
+    TrainState &t = *b.train;
+    const long long R = (long long)T * B;
+    if (inv_count <= 0.f) inv_count = 1.0f / (float)R;
+    const bool train_head = kind != DC_FEATS_HEAD_F32;
+    const __nv_bfloat16 *x0 = t.x0_used;
+    const __nv_bfloat16 *h2_all = t.X2 + (size_t)B * 2 * U + U;
+    auto G = [&](const char *name) { return grads + find(name)->offset; };
+    DC_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n_train, s));
+
+    softmax_xent_kernel<<<(unsigned)R, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
+    DC_CHECK_LAUNCH();
+    reduce_loss_kernel<<<1, 1024, 0, s>>>(t.rowloss, R, inv_count, loss);
+    DC_CHECK_LAUNCH();
+
+    // ---------------- backward: time-batched part ----------------
+    auto wgrad = [&](const __nv_bfloat16 *X, long long ldx, int M, const __nv_bfloat16 *dY, long long ldy, int N,
+                     long long rows, float *out, long long ldo) {
+        TcEpilogue e;
+        e.out_f32 = out; e.ld_f32 = ldo; e.atomic = 1;
+        return gemm_bf16_tc(tc_op(X, ldx, true), tc_op(dY, ldy, true), e, M, N, (int)rows, kEpiStore, s, 0);
+    };
+    // dense2: dWd2 = d^T dz, dbd2 = colsum(dz), dd = (dz Wd2^T) * [d > 0]
+    if (int rc = wgrad(t.d_all, kDense, kDense, t.dz, V, V, R, G("imgcap_lstm_d2/kernel"), V)) return rc;
+    if (int rc = colsum(t.dz, R, V, V, G("imgcap_lstm_d2/bias"), s)) return rc;
+    {
+        TcEpilogue e;
+        e.mask_src = t.d_all; e.ld_mask = kDense; e.out_bf16 = t.dd; e.ld_bf16 = kDense;
+        if (int rc = gemm_bf16_tc(tc_op(t.dz, V), tc_op(b.wd2_k, V), e, (int)R, kDense, V, kEpiStore, s)) return rc;
+    }
+    time_sum_kernel<<<(unsigned)ceil_div<long long>((long long)B * kDense, 256), 256, 0, s>>>(t.dd, B, T, kDense, t.ddsum,
+                                                                                             t.ddsum_b);
+    DC_CHECK_LAUNCH();
+    // dense1: rows [0,U) of the kernel see h2_t, rows [U, U+F) the (time-constant) RoI feature
+    if (int rc = wgrad(h2_all, 2 * U, U, t.dd, kDense, kDense, R, G("imgcap_lstm_d1/kernel"), kDense)) return rc;
+    if (int rc = wgrad(b.Fb, F, F, t.ddsum_b, kDense, kDense, B, G("imgcap_lstm_d1/kernel") + (size_t)U * kDense, kDense)) return rc;
+    if (int rc = colsum(t.ddsum, B, kDense, kDense, G("imgcap_lstm_d1/bias"), s)) return rc;
+    {
+        TcEpilogue e;
+        e.out_f32 = t.dh2d; e.ld_f32 = U;
+        if (int rc = gemm_bf16_tc(tc_op(t.dd, kDense), tc_op(b.wd1h_k, kDense), e, (int)R, U, kDense, kEpiStore, s)) return rc;
+    }
+
+    // ---------------- backward: BPTT ----------------
+    for (float *p : {t.carry1, t.carry2, t.dc1, t.dc2})
+        DC_CHECK_CUDA(cudaMemsetAsync(p, 0, 4 * (size_t)B * U, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(t.dz1sum, 0, 4 * (size_t)B * 4 * U, s));
+    const unsigned cb_grid = (unsigned)ceil_div<long long>((long long)B * (U / 4), 256);
+    for (int st = T - 1; st >= 0; --st) {
+        const int32_t *tok = t.tok_tm + (size_t)st * B;
+        const bool last = st == T - 1;
+        __nv_bfloat16 *dz2 = t.dz2_all + (size_t)st * B * 4 * U, *dz1 = t.dz1_all + (size_t)st * B * 4 * U;
+        lstm_cell_bwd_kernel<<<cb_grid, 256, 0, s>>>(B, U, t.gates2 + (size_t)st * B * 4 * U, t.c2 + (size_t)st * B * U,
+                                                     t.c2 + (size_t)(st + 1) * B * U, tok, t.dh2d + (size_t)st * B * U, U,
+                                                     last ? nullptr : t.dxh2 + U, 2 * U, t.carry2, t.dc2, dz2, nullptr);
+        DC_CHECK_LAUNCH();
+        {   // [dh1_t | dh2_{t-1}] = dz2 [W2 ; U2]^T
+            TcEpilogue e;
+            e.out_f32 = t.dxh2; e.ld_f32 = 2 * U;
+            if (int rc = gemm_bf16_tc(tc_op(dz2, 4 * U), tc_op(b.w2cat_k, 4 * U), e, B, 2 * U, 4 * U, kEpiStore, s)) return rc;
+        }
+        lstm_cell_bwd_kernel<<<cb_grid, 256, 0, s>>>(B, U, t.gates1 + (size_t)st * B * 4 * U, t.c1 + (size_t)st * B * U,
+                                                     t.c1 + (size_t)(st + 1) * B * U, tok, t.dxh2, 2 * U,
+                                                     last ? nullptr : t.dh1p, U, t.carry1, t.dc1, dz1, t.dz1sum);
+        DC_CHECK_LAUNCH();
+        if (st > 0) {   // dh1_{t-1} = dz1 U1^T
+            TcEpilogue e;
+            e.out_f32 = t.dh1p; e.ld_f32 = U;
+            if (int rc = gemm_bf16_tc(tc_op(dz1, 4 * U), tc_op(b.u1_k, 4 * U), e, B, U, 4 * U, kEpiStore, s)) return rc;
+        }
+    }
+    f32_to_bf16_rows_kernel<<<(unsigned)ceil_div<long long>((long long)B * 4 * U, 256), 256, 0, s>>>(t.dz1sum, (long long)B * 4 * U,
+                                                                                                    t.dz1sum_b);
+    DC_CHECK_LAUNCH();
+
+    // ---------------- backward: LSTM weight gradients (one GEMM over all T*B rows each) ----------------
+    // [dW2 ; dU2] = [h1_t | h2_{t-1}]^T dz2  (kernel and recurrent_kernel gradients are adjacent)
+    if (int rc = wgrad(t.X2, 2 * U, 2 * U, t.dz2_all, 4 * U, 4 * U, R, G("imgcap_lstm2/kernel"), 4 * U)) return rc;
+    if (int rc = colsum(t.dz2_all, R, 4 * U, 4 * U, G("imgcap_lstm2/bias"), s)) return rc;
+    // dW1[:E] = emb_t^T dz1 ; dU1 = h1_{t-1}^T dz1 ; dW1[E:] = f^T sum_t dz1
+    if (int rc = wgrad(t.X1, K1, E, t.dz1_all, 4 * U, 4 * U, R, G("imgcap_lstm1/kernel"), 4 * U)) return rc;
+    if (int rc = wgrad(t.X1 + b.Epad, K1, U, t.dz1_all, 4 * U, 4 * U, R, G("imgcap_lstm1/recurrent_kernel"), 4 * U)) return rc;
+    if (int rc = wgrad(b.Fb, F, F, t.dz1sum_b, 4 * U, 4 * U, B, G("imgcap_lstm1/kernel") + (size_t)E * 4 * U, 4 * U)) return rc;
+    if (int rc = colsum(t.dz1sum, B, 4 * U, 4 * U, G("imgcap_lstm1/bias"), s)) return rc;
+
+    if (!train_head) return DC_OK;
+    // ---------------- backward: RoI head ----------------
+    {   // dF = (sum_t dd) Wd1[U:]^T + (sum_t dz1) W1[E:]^T
+        TcEpilogue e;
+        e.out_f32 = t.dF; e.ld_f32 = F;
+        if (int rc = gemm_bf16_tc(tc_op(t.ddsum_b, kDense), tc_op(b.wd1f_k, kDense), e, B, F, kDense, kEpiStore, s)) return rc;
+        TcEpilogue e2;
+        e2.addend = t.dF; e2.ld_addend = F; e2.out_f32 = t.dF; e2.ld_f32 = F;
+        if (int rc = gemm_bf16_tc(tc_op(t.dz1sum_b, 4 * U), tc_op(b.w1f_k, 4 * U), e2, B, F, 4 * U, kEpiStore, s)) return rc;
+    }
+    const dim3 bn_grid(ceil_div(F, 32), ceil_div(B, 256)), bn_block(32, 8);
+    bn_relu_bwd_kernel<<<bn_grid, bn_block, 0, s>>>(t.dF, b.Fb, B, F, bn_scale[1], W("mrcnn_class_bn2/gamma"),
+                                                    W("mrcnn_class_bn2/beta"), 256, t.dzh2, G("mrcnn_class_bn2/gamma"),
+                                                    G("mrcnn_class_bn2/beta"), G("mrcnn_class_conv2/bias"));
+    DC_CHECK_LAUNCH();
+    if (int rc = wgrad(b.a1, F, F, t.dzh2, F, F, B, G("mrcnn_class_conv2/kernel"), F)) return rc;
+    {
+        TcEpilogue e;
+        e.out_f32 = t.da1; e.ld_f32 = F;
+        if (int rc = gemm_bf16_tc(tc_op(t.dzh2, F), tc_op(b.wc2_k, F), e, B, F, F, kEpiStore, s)) return rc;
+    }
+    bn_relu_bwd_kernel<<<bn_grid, bn_block, 0, s>>>(t.da1, b.a1, B, F, bn_scale[0], W("mrcnn_class_bn1/gamma"),
+                                                    W("mrcnn_class_bn1/beta"), 256, t.dzh1, G("mrcnn_class_bn1/gamma"),
+                                                    G("mrcnn_class_bn1/beta"), G("mrcnn_class_conv1/bias"));
+    DC_CHECK_LAUNCH();
+    return wgrad(x0, Kin, Kin, t.dzh1, F, F, B, G("mrcnn_class_conv1/kernel"), F);
+}
+
+// probs[b, t, :] = softmax(logits[t*B + b, :]): the Keras output layout [B, P, V] of the training graph
+__global__ void __launch_bounds__(256) softmax_rows_to_bpv_kernel(const float *__restrict__ logits, int B, int T, int V,
+                                                                  float *__restrict__ probs) {
+    const int r = blockIdx.x, t = r / B, b = r - t * B;
+    const float *z = logits + (long long)r * V;
+    float *p = probs + ((long long)b * T + t) * V;
+    __shared__ float red[8];
+    __shared__ float bc;
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < V; j += 256) mx = fmaxf(mx, z[j]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) { float m = red[0]; for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]); bc = m; }
+    __syncthreads();
+    mx = bc;
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < V; j += 256) sum += expf(z[j] - mx);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { float a = 0.f; for (int i = 0; i < 8; ++i) a += red[i]; bc = a; }
+    __syncthreads();
+    const float inv = 1.0f / bc;
+    for (int j = threadIdx.x; j < V; j += 256) p[j] = expf(z[j] - mx) * inv;
+}
+
+int Decoder::teacher_forced_probs(const void *feats, int kind, int B, const int32_t *gt, float *probs, cudaStream_t s) {
+    DC_REQUIRE(probs, "null pointer argument");
+    if (int rc = train_forward(feats, kind, B, gt, nullptr, s)) return rc;
+    softmax_rows_to_bpv_kernel<<<B * cfg.padding, 256, 0, s>>>(bf->train->logits, B, cfg.padding, cfg.vocab, probs);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
+int Decoder::adam_step(float lr, float beta1, float beta2, float eps, int amsgrad, long long t, float grad_scale,
+                       cudaStream_t s) {
+    DC_REQUIRE(grads, "dc_adam_step before any dc_decoder_train_step");
+    DC_REQUIRE(t >= 1, "iteration count starts at 1");
+    const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t));
+    const long long n = n_train;
+    adam_amsgrad_kernel<<<(unsigned)ceil_div<long long>(n / 4, 256), 256, 0, s>>>(arena, grads, adam_m, adam_v, adam_vhat, n,
+                                                                                 (float)lr_t, beta1, beta2, eps, amsgrad,
+                                                                                 grad_scale);
+    DC_CHECK_LAUNCH();
+    // folded BN + bf16 operand copies (forward and backward layouts) are rebuilt IN PLACE, so captured
+    // inference graphs stay valid
+    return refresh_derived(s);
+}
+
+}  // namespace dcap
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace dcap;
+
+extern "C" int dc_decoder_train_step(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *gt,
+                                     const int32_t *targets, float inv_count, float *loss, void *stream) {
+    DC_REQUIRE(dec, "null decoder");
+    return dec->impl.train_step(feats, feats_kind, B, gt, targets, inv_count, loss, (cudaStream_t)stream);
+}
+
+extern "C" int dc_decoder_teacher_forced(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *gt,
+                                        float *probs, void *stream) {
+    DC_REQUIRE(dec, "null decoder");
+    return dec->impl.teacher_forced_probs(feats, feats_kind, B, gt, probs, (cudaStream_t)stream);
+}
+
+extern "C" int dc_adam_step(DcDecoder *dec, float lr, float beta1, float beta2, float epsilon, int amsgrad,
+                            int64_t iteration, float grad_scale, void *stream) {
+    DC_REQUIRE(dec, "null decoder");
+    if (int rc = dec->impl.check_ready(0)) return rc;
+    return dec->impl.adam_step(lr, beta1, beta2, epsilon, amsgrad, iteration, grad_scale, (cudaStream_t)stream);
+}
+
+extern "C" int dc_decoder_grad_buffer(DcDecoder *dec, float **ptr, int64_t *numel) {
+    DC_REQUIRE(dec && ptr && numel, "null pointer argument");
+    if (int rc = dec->impl.ensure_grads()) return rc;
+    *ptr = dec->impl.grads;
+    *numel = dec->impl.n_train;
+    return DC_OK;
+}
+
+extern "C" int dc_decoder_param_buffer(DcDecoder *dec, float **ptr, int64_t *numel) {
+    DC_REQUIRE(dec && ptr && numel, "null pointer argument");
+    *ptr = dec->impl.arena;
+    *numel = dec->impl.n_train;
+    return DC_OK;
+}
+
+extern "C" int64_t dc_decoder_weight_offset(const DcDecoder *dec, int index) {
+    if (!dec || index < 0 || index >= (int)dec->impl.weights.size()) return -1;
+    const Weight &w = dec->impl.weights[index];
+    return w.trainable ? w.offset : -1;
+}
+
+extern "C" int dc_decoder_get_grad(DcDecoder *dec, const char *name, float *host, int64_t numel) {
+    DC_REQUIRE(dec && name && host, "null pointer argument");
+    Weight *w = dec->impl.find(name);
+    DC_REQUIRE(w != nullptr, "unknown weight '%s'", name);
+    DC_REQUIRE(w->trainable, "weight '%s' is frozen (no gradient)", name);
+    DC_REQUIRE(w->numel == numel, "weight '%s' holds %lld values, got %lld", name, (long long)w->numel, (long long)numel);
+    DC_REQUIRE(dec->impl.grads, "no gradients yet: call dc_decoder_train_step first");
+    DC_CHECK_CUDA(cudaMemcpy(host, dec->impl.grads + w->offset, sizeof(float) * (size_t)numel, cudaMemcpyDeviceToHost));
+    return DC_OK;
+}

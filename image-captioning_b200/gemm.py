@@ -45,6 +45,24 @@ def gemm_bf16(a, bt, bias=None, addend=None, relu=False, out_dtype=torch.float32
     return out
 
 
+def gemm_bf16_ex(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, addend=None, addend_mod=0, relu=False,
+                 mask_src=None, deint_units=0, atomic=False, split_k=1, out=None, out_dtype=torch.float32):
+    """General tcgen05 GEMM (dc_gemm_bf16_ex).  K-major operand: [rows, K]; MN-major: [K, rows]."""
+    lib = _lib.load()
+    if out is None:
+        out = (torch.zeros if atomic else torch.empty)((M, N), dtype=out_dtype, device=a.device)
+    f32 = out if out.dtype == torch.float32 else None
+    b16 = out if out.dtype == torch.bfloat16 else None
+    with torch.cuda.device(a.device):
+        _lib.check(lib.dc_gemm_bf16_ex(
+            _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), M, N, K, _p(bias), _p(addend),
+            addend.stride(0) if addend is not None else 0, int(addend_mod), int(relu), _p(mask_src),
+            mask_src.stride(0) if mask_src is not None else 0, int(deint_units), int(atomic), int(split_k),
+            _p(f32), out.stride(0) if f32 is not None else 0, _p(b16), out.stride(0) if b16 is not None else 0,
+            _s(a.device)))
+    return out
+
+
 def gemm_bf16_argmax(a, bt, bias, want_prob=False):
     lib = _lib.load()
     M, K = a.shape

@@ -58,6 +58,43 @@ class DenseCapConfig(object):
             self.PADDING_SIZE = int(padding_size)
 
 
+class Adam(object):
+    """keras.optimizers.Adam as the reference constructs it (text_generation_model.py:425,
+    text_generation_model_v2.py:266): same arguments and defaults as Keras 2.1 (epsilon=None means
+    K.epsilon() = 1e-7; `decay` rescales lr by 1/(1 + decay*iterations))."""
+
+    def __init__(self, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=None, decay=0.0, amsgrad=False):
+        self.lr, self.beta_1, self.beta_2 = float(lr), float(beta_1), float(beta_2)
+        self.epsilon = 1e-7 if epsilon is None else float(epsilon)
+        self.decay, self.amsgrad = float(decay), bool(amsgrad)
+        self.iterations = 0
+
+    def current_lr(self):
+        return self.lr / (1.0 + self.decay * self.iterations) if self.decay > 0 else self.lr
+
+
+def roi_caption_loss(y_true=None, y_pred=None):
+    """Marker for compile(loss=roi_caption_loss) (text_generation_model.py:286-294).  The loss is
+    evaluated inside the fused training step (dc_decoder_train_step); it is not a host function."""
+    raise NotImplementedError("roi_caption_loss is fused into the training step; use train_on_batch / evaluate")
+
+
+class History(object):
+    """What fit_generator returns (keras.callbacks.History): .history = {'loss': [...], 'val_loss': [...]}."""
+
+    def __init__(self):
+        self.epoch, self.history = [], {}
+
+
+class _DeviceArray(object):
+    """A raw device range exposed through __cuda_array_interface__ (zero-copy torch view)."""
+
+    def __init__(self, ptr, numel, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2}
+
+
 class _DcDecoderConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in ("arch", "dtype", "vocab", "embed", "feat", "units",
                                             "word_units", "pool", "channels", "padding")]
@@ -344,6 +381,176 @@ class RoiCaptionModel(_ModelBase):
                                                       int(image_shape[0]), int(image_shape[1]),
                                                       ctypes.c_void_p(tokens.ctypes.data)))
         return tokens
+
+    # ---- training surface (text_generation_model.py:424-426, 470-472) ----
+    def compile(self, optimizer="adam", loss=None, metrics=None, **kwargs):
+        """model.compile(optimizer=Adam(amsgrad=True), loss=roi_caption_loss)."""
+        if isinstance(optimizer, str):
+            if optimizer.lower() != "adam":
+                raise ValueError("only the Adam optimiser of the reference is implemented")
+            optimizer = Adam()
+        if not isinstance(optimizer, Adam):
+            raise ValueError("optimizer must be image_captioning_b200.Adam (mirror of keras.optimizers.Adam)")
+        ok = loss is None or loss is roi_caption_loss or loss in ("categorical_crossentropy", "roi_caption_loss") \
+            or getattr(loss, "__name__", "") in ("roi_caption_loss", "categorical_crossentropy")
+        if not ok:
+            raise ValueError("loss must be roi_caption_loss / categorical_crossentropy (fused in the training step)")
+        if self.dtype != DTYPE_BF16:
+            raise ValueError("the training step runs on the bf16 tensor-core path: build the model with dtype='bfloat16'")
+        self.optimizer, self.loss = optimizer, loss
+
+    def _ids_to_device(self, a, name):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        if t.dim() != 2 or t.shape[1] != self.config.PADDING_SIZE:
+            raise ValueError("%s must be [N, PADDING_SIZE=%d], got %s" % (name, self.config.PADDING_SIZE, tuple(t.shape)))
+        return t.to(self.device).to(torch.int32).contiguous()
+
+    def _targets_to_device(self, y):
+        """One-hot [N,P,V] (what the reference's generator yields, :354-358; an all-zero row means
+        'no target', :287) or class ids [N,P] (negative = no target)."""
+        if y is None:
+            return None
+        t = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y))
+        if t.dim() == 3:
+            t = t.to(self.device)
+            ids = t.argmax(-1).to(torch.int32)
+            ids = torch.where(t.sum(-1) > 0, ids, torch.full_like(ids, -1))
+            return ids.contiguous()
+        return self._ids_to_device(t, "targets")
+
+    def grad_buffer(self):
+        """Zero-copy torch view of the flat fp32 gradient buffer over all trainable tensors (what a
+        data-parallel host all-reduces between train_step_device and apply_gradients)."""
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_grad_buffer(self._h, ctypes.byref(p), ctypes.byref(n)))
+            return torch.as_tensor(_DeviceArray(p.value, n.value, self), device=self.device)
+
+    def param_buffer(self):
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_param_buffer(self._h, ctypes.byref(p), ctypes.byref(n)))
+            return torch.as_tensor(_DeviceArray(p.value, n.value, self), device=self.device)
+
+    def get_gradients(self):
+        """{weight name: gradient array} of the last training step (trainable tensors, Keras layout)."""
+        out = {}
+        for n in self.weight_names:
+            if "/moving_" in n or n.endswith("/embeddings"):
+                continue
+            g = np.empty(self._shapes[n], np.float32)
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.dc_decoder_get_grad(self._h, n.encode(), ctypes.c_void_p(g.ctypes.data),
+                                                         ctypes.c_int64(g.size)))
+            out[n] = g
+        return out
+
+    def train_step_device(self, features, gt_captions, targets=None, inv_count=0.0, loss_out=None):
+        """Forward + loss + backward on device tensors; gradients stay in grad_buffer().  Returns the
+        device scalar  sum_positions(-log p_y) * inv_count  (inv_count <= 0: 1/(N*P)).  No host sync."""
+        self._ready()
+        t, kind, _ = self._feats_to_device(features)
+        gt = self._ids_to_device(gt_captions, "gt_captions")
+        tg = self._targets_to_device(targets)
+        if gt.shape[0] != t.shape[0] or (tg is not None and tg.shape != gt.shape):
+            raise ValueError("features, gt_captions and targets disagree on the batch size")
+        loss = torch.empty((), dtype=torch.float32, device=self.device) if loss_out is None else loss_out
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_train_step(
+                self._h, ctypes.c_void_p(t.data_ptr()), kind, t.shape[0], ctypes.c_void_p(gt.data_ptr()),
+                ctypes.c_void_p(tg.data_ptr()) if tg is not None else None, ctypes.c_float(inv_count),
+                ctypes.c_void_p(loss.data_ptr()), self._stream()))
+        return loss
+
+    def apply_gradients(self, grad_scale=1.0):
+        """One optimiser update from grad_buffer() (Keras Adam / AMSGrad formula)."""
+        if self.optimizer is None:
+            raise RuntimeError("compile() the model first")
+        o = self.optimizer
+        lr = o.current_lr()
+        o.iterations += 1
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_adam_step(self._h, ctypes.c_float(lr), ctypes.c_float(o.beta_1),
+                                              ctypes.c_float(o.beta_2), ctypes.c_float(o.epsilon), int(o.amsgrad),
+                                              ctypes.c_int64(o.iterations), ctypes.c_float(grad_scale), self._stream()))
+
+    def train_on_batch(self, x, y=None, sample_weight=None, class_weight=None):
+        """Keras train_on_batch([features, gt_captions], one_hot_targets) -> scalar loss."""
+        if self.optimizer is None:
+            raise RuntimeError("compile() the model first")
+        if sample_weight is not None or class_weight is not None:
+            raise NotImplementedError("sample/class weights are not used by the reference")
+        feats, gt = x
+        tg = self._targets_to_device(y)
+        inv = 0.0
+        if tg is not None:
+            cnt = int((tg >= 0).sum().item())                       # roi_caption_loss averages over rows with a target
+            if cnt == 0:
+                return 0.0
+            inv = 1.0 / cnt
+        loss = self.train_step_device(feats, gt, tg, inv)
+        self.apply_gradients()
+        return float(loss.item())
+
+    def test_on_batch(self, x, y=None, sample_weight=None):
+        feats, gt = x
+        tg = self._targets_to_device(y)
+        inv = 0.0
+        if tg is not None:
+            cnt = int((tg >= 0).sum().item())
+            if cnt == 0:
+                return 0.0
+            inv = 1.0 / cnt
+        return float(self.train_step_device(feats, gt, tg, inv).item())
+
+    def predict_teacher_forced(self, x):
+        """predict([features, gt_captions]) of the training graph: [N,P,V] word probabilities."""
+        self._ready()
+        feats, gt = x
+        t, kind, was_numpy = self._feats_to_device(feats)
+        g = self._ids_to_device(gt, "gt_captions")
+        probs = torch.empty((t.shape[0], self.config.PADDING_SIZE, self.config.VOCABULARY_SIZE), dtype=torch.float32,
+                            device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_teacher_forced(self._h, ctypes.c_void_p(t.data_ptr()), kind, t.shape[0],
+                                                           ctypes.c_void_p(g.data_ptr()),
+                                                           ctypes.c_void_p(probs.data_ptr()), self._stream()))
+        return probs.cpu().numpy() if was_numpy else probs
+
+    def fit_generator(self, generator, steps_per_epoch=None, epochs=1, verbose=1, callbacks=None,
+                      validation_data=None, validation_steps=None, max_queue_size=10, workers=1,
+                      use_multiprocessing=False, shuffle=True, initial_epoch=0, **kwargs):
+        """Keras fit_generator as the reference calls it (text_generation_model.py:470-472): the
+        generator yields ([features, gt_captions], one_hot_targets); validation_data is one such
+        batch (next(val_generator)) or a generator.  Callbacks receive Keras' on_epoch_end(epoch,
+        logs) if they define it (ModelCheckpoint / CSVLogger stand-ins)."""
+        if steps_per_epoch is None:
+            raise ValueError("steps_per_epoch is required for a generator")
+        hist = History()
+        for cb in callbacks or []:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+        for epoch in range(initial_epoch, epochs):
+            losses = []
+            for _ in range(steps_per_epoch):
+                x, y = next(generator)[:2]
+                losses.append(self.train_on_batch(x, y))
+            logs = {"loss": float(np.mean(losses))}
+            if validation_data is not None:
+                if isinstance(validation_data, (tuple, list)):
+                    logs["val_loss"] = self.test_on_batch(validation_data[0], validation_data[1])
+                else:
+                    vs = [self.test_on_batch(*next(validation_data)[:2]) for _ in range(validation_steps or 1)]
+                    logs["val_loss"] = float(np.mean(vs))
+            hist.epoch.append(epoch)
+            for k, v in logs.items():
+                hist.history.setdefault(k, []).append(v)
+            if verbose:
+                print("Epoch %d/%d - " % (epoch + 1, epochs) + " - ".join("%s: %.4f" % kv for kv in logs.items()))
+            for cb in callbacks or []:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, logs)
+        return hist
 
     def head_features(self, features):
         """`features_new` of build_lstm_model (:249-262): [N,1024]."""

@@ -183,6 +183,47 @@ int dc_decoder_greedy_host(DcDecoder *dec, const float *feats, int feats_kind, i
                            int32_t *tokens, float *probs);
 
 /* ------------------------------------------------------------------------------------------
+ * Training step of the v1 model (bf16 decoder only): replaces model.compile(Adam(amsgrad=True),
+ * roi_caption_loss) + fit_generator / train_on_batch of build_lstm_model(mode='training'),
+ * text_generation_model.py:159-189, 264-294, 424-426, 470-472.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Forward (teacher-forced masked scan over gt, equal to the reference's per-prefix evaluation) +
+ * roi_caption_loss + backward.  Gradients of every trainable tensor are left in the handle's flat
+ * gradient buffer (dc_decoder_grad_buffer), Keras layout, same offsets as the parameters.
+ *   feats    per feats_kind; DC_FEATS_HEAD_F32 trains the word model only (head frozen / absent)
+ *   gt       [B, P] int32 caption ids as the data generator yields them (1, w.., 2, 0-pad; :111-114)
+ *   targets  [B, P] int32 class id per position, or NULL = shift-left(gt) ++ [0] (:352-358);
+ *            a negative id marks a position with an all-zero target row (excluded by the loss, :287)
+ *   inv_count  1 / (number of positions the loss averages over, GLOBALLY when the batch is sharded
+ *            over ranks); <= 0 means 1/(B*P)
+ *   loss     device float: sum over this call's positions of -log(clip(p_y,1e-7,1-1e-7)) * inv_count
+ * VOCABULARY_SIZE must be a multiple of 8.  recurrent_dropout is not applied. */
+int dc_decoder_train_step(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *gt,
+                          const int32_t *targets, float inv_count, float *loss, void *stream);
+
+/* model.predict([features, gt_captions]) of the TRAINING graph (text_generation_model.py:264-277):
+ * teacher-forced word probabilities, probs [B, P, V] fp32 (device). */
+int dc_decoder_teacher_forced(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *gt,
+                              float *probs, void *stream);
+
+/* keras.optimizers.Adam(lr, beta_1, beta_2, epsilon, amsgrad).get_updates on the flat parameter
+ * buffer (text_generation_model.py:425): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m, v, vhat = max(vhat, v);
+ * p -= lr_t*m/(sqrt(vhat)+epsilon).  `iteration` t starts at 1.  Gradients are multiplied by
+ * grad_scale first (1/world_size after a sum all-reduce).  Re-derives the operand copies. */
+int dc_adam_step(DcDecoder *dec, float lr, float beta1, float beta2, float epsilon, int amsgrad,
+                 int64_t iteration, float grad_scale, void *stream);
+
+/* Flat fp32 device buffers over all TRAINABLE tensors (BatchNorm moving statistics and the frozen
+ * embedding excluded): the gradient buffer is what a data-parallel host all-reduces (NCCL) between
+ * dc_decoder_train_step and dc_adam_step; dc_decoder_weight_offset gives each tensor's offset
+ * (in floats; -1 for frozen tensors). */
+int dc_decoder_grad_buffer(DcDecoder *dec, float **ptr, int64_t *numel);
+int dc_decoder_param_buffer(DcDecoder *dec, float **ptr, int64_t *numel);
+int64_t dc_decoder_weight_offset(const DcDecoder *dec, int index);
+int dc_decoder_get_grad(DcDecoder *dec, const char *name, float *host, int64_t numel);
+
+/* ------------------------------------------------------------------------------------------
  * End-to-end: PyramidROIAlign -> RoI head -> greedy decoding in one call
  * ---------------------------------------------------------------------------------------- */
 
@@ -220,6 +261,22 @@ int dc_gemm_f32(const float *A, int64_t lda, int trans_a, const float *B, int64_
 int dc_gemm_bf16(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M, int N, int K,
                  const float *bias, const float *addend, int64_t ld_addend, int relu,
                  float *out_f32, int64_t ld_f32, uint16_t *out_bf16, int64_t ld_bf16, void *stream);
+
+/* General form used by the training step (all of dc_gemm_bf16 plus):
+ *   a_mn / b_mn   operand is MN-major: stored [K, rows] row-major (rows contiguous), ld = stride
+ *                 between consecutive k.  Weight gradients X^T*dY read X [R,in] and dY [R,out] as they
+ *                 lie in memory (both MN-major, K = R) -- nothing is transposed in HBM.
+ *   atomic        fp32 output is ACCUMULATED (red.global.add); with split_k != 1 the K range is
+ *                 split over CTAs (0 = automatic).  Output must be zeroed / hold the running sum.
+ *   addend_mod    > 0: addend row index is m % addend_mod (per-RoI term broadcast over time steps)
+ *   deint_units   > 0: N == 4*units gate-interleaved columns (4u+g) are written to the Keras
+ *                 block layout (g*units+u)
+ *   mask_src      bf16 [M, ld_mask]: result is zeroed where mask_src <= 0 (ReLU backward)        */
+int dc_gemm_bf16_ex(const uint16_t *A, int64_t lda, int a_mn, const uint16_t *B, int64_t ldb, int b_mn,
+                    int M, int N, int K, const float *bias, const float *addend, int64_t ld_addend,
+                    int addend_mod, int relu, const uint16_t *mask_src, int64_t ld_mask, int deint_units,
+                    int atomic, int split_k, float *out_f32, int64_t ld_f32, uint16_t *out_bf16,
+                    int64_t ld_bf16, void *stream);
 
 /* bf16 tcgen05 GEMM with the fused arg-max epilogue (Dense(V) + softmax + tf.argmax of the greedy
  * loop, text_generation_model.py:144,222-225): tokens[m] = first arg-max over n of

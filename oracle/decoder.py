@@ -333,11 +333,21 @@ def train_loss_and_grads_v1(feat, gt, w, train_head=True):
         df += dx[:, E:]
         dh1 = np.where(m, dhp, dh1); dc1 = np.where(m, dcp, dc1)
     if train_head:
-        dz2 = df * (f > 0) * s2
+        # BatchNorm runs with training=False but gamma / beta stay trainable
+        # (modified_dense_model.py:52-62): y = (z - mean) * gamma * r + beta, r = rsqrt(var + eps)
+        dy2 = df * (f > 0)
+        r2 = 1.0 / np.sqrt(W["mrcnn_class_bn2/moving_variance"] + BN_EPS)
+        G["mrcnn_class_bn2/gamma"] = (dy2 * (z2 - W["mrcnn_class_bn2/moving_mean"]) * r2).sum(0)
+        G["mrcnn_class_bn2/beta"] = dy2.sum(0)
+        dz2 = dy2 * s2
         G["mrcnn_class_conv2/kernel"] = (a1.T @ dz2).reshape(W["mrcnn_class_conv2/kernel"].shape)
         G["mrcnn_class_conv2/bias"] = dz2.sum(0)
         da1 = dz2 @ k2.T
-        dz1 = da1 * (a1 > 0) * s1
+        dy1 = da1 * (a1 > 0)
+        r1 = 1.0 / np.sqrt(W["mrcnn_class_bn1/moving_variance"] + BN_EPS)
+        G["mrcnn_class_bn1/gamma"] = (dy1 * (z1 - W["mrcnn_class_bn1/moving_mean"]) * r1).sum(0)
+        G["mrcnn_class_bn1/beta"] = dy1.sum(0)
+        dz1 = dy1 * s1
         G["mrcnn_class_conv1/kernel"] = (x0.T @ dz1).reshape(W["mrcnn_class_conv1/kernel"].shape)
         G["mrcnn_class_conv1/bias"] = dz1.sum(0)
     return loss, G

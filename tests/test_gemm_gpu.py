@@ -118,3 +118,49 @@ def test_tcgen05_gemm_lstm_cell_epilogue(M, U, K):
     torch.testing.assert_close(h_out[:, U:].float(), h_want.to(torch.bfloat16).float(), rtol=2e-2, atol=1e-2)
     assert torch.equal(h_out[:, U:], h_out2)
     assert bool((h_out[:, :U] == 0).all())
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("M,N,K", [(304, 2048, 4096), (512, 1024, 1000), (832, 256, 8192 + 64)])
+def test_tcgen05_gemm_mn_major_operands(M, N, K, a_mn, b_mn):
+    """MN-major UMMA operands: X^T * dY straight from the [R, in] / [R, out] activations."""
+    from image_captioning_b200 import gemm
+    a = _rand((M, K), 61).to(torch.bfloat16)
+    b = _rand((N, K), 62).to(torch.bfloat16)
+    want = a.float() @ b.float().t()
+    a_op = a.t().contiguous() if a_mn else a
+    b_op = b.t().contiguous() if b_mn else b
+    got = gemm.gemm_bf16_ex(a_op, b_op, M, N, K, a_mn=a_mn, b_mn=b_mn)
+    torch.testing.assert_close(got, want, rtol=2e-3, atol=2e-3 * K ** 0.5)
+
+
+@pytest.mark.parametrize("split", [0, 3, 7])
+def test_tcgen05_gemm_split_k_atomic_and_deinterleave(split):
+    from image_captioning_b200 import gemm
+    M, U, K = 304, 64, 9000
+    N = 4 * U
+    a = _rand((K, M), 63).to(torch.bfloat16)           # MN-major A: [K, M]
+    b = _rand((K, N), 64).to(torch.bfloat16)           # MN-major B: [K, N], gate-interleaved columns
+    want_i = a.float().t() @ b.float()                 # [M, N] interleaved
+    perm = (torch.arange(4, device="cuda")[None, :] * U + torch.arange(U, device="cuda")[:, None]).reshape(-1)
+    want = torch.empty_like(want_i)
+    want[:, perm] = want_i                             # column 4u+g -> g*U+u
+    base = _rand((M, N), 65)
+    out = base.clone()
+    gemm.gemm_bf16_ex(a, b, M, N, K, a_mn=True, b_mn=True, deint_units=U, atomic=True, split_k=split, out=out)
+    torch.testing.assert_close(out - base, want, rtol=2e-3, atol=0.3)
+
+
+def test_tcgen05_gemm_relu_mask_and_addend_mod():
+    from image_captioning_b200 import gemm
+    M, N, K, B = 700, 1024, 520, 100
+    a = _rand((M, K), 66).to(torch.bfloat16)
+    b = _rand((N, K), 67).to(torch.bfloat16)
+    addend = _rand((B, N), 68)
+    act = torch.relu(_rand((M, N), 69)).to(torch.bfloat16)
+    want = a.float() @ b.float().t() + addend[torch.arange(M, device="cuda") % B]
+    got = gemm.gemm_bf16_ex(a, b, M, N, K, addend=addend, addend_mod=B)
+    torch.testing.assert_close(got, want, rtol=2e-3, atol=0.1)
+    got = gemm.gemm_bf16_ex(a, b, M, N, K, mask_src=act, out_dtype=torch.bfloat16)
+    want_m = torch.where(act.float() > 0, a.float() @ b.float().t(), torch.zeros((), device="cuda"))
+    torch.testing.assert_close(got.float(), want_m.to(torch.bfloat16).float(), rtol=2e-2, atol=0.2)

@@ -84,7 +84,9 @@ def test_bptt_gradients_match_finite_differences():
               ("imgcap_lstm2/recurrent_kernel", (2, 9)), ("imgcap_lstm1/kernel", (5, 20)),
               ("imgcap_lstm1/kernel", (100, 33)), ("imgcap_lstm1/recurrent_kernel", (1, 50)),
               ("imgcap_lstm1/bias", (17,)), ("mrcnn_class_conv2/kernel", (0, 0, 3, 4)),
-              ("mrcnn_class_conv1/kernel", (1, 0, 2, 7)), ("mrcnn_class_conv1/bias", (3,))]
+              ("mrcnn_class_conv1/kernel", (1, 0, 2, 7)), ("mrcnn_class_conv1/bias", (3,)),
+              ("mrcnn_class_bn1/gamma", (11,)), ("mrcnn_class_bn1/beta", (12,)), ("mrcnn_class_bn2/gamma", (5,)),
+              ("mrcnn_class_bn2/beta", (6,)), ("imgcap_lstm_d2/bias", (9,)), ("imgcap_lstm_d1/bias", (100,))]
     eps = 1e-5
     for name, idx in checks:
         w2 = dict(w); a = w[name].copy(); a[idx] += eps; w2[name] = a
