@@ -578,21 +578,141 @@ def run_reference_captions(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------
+# train workload (BASELINE.json configs[2]): v1 decoder training step, bf16, global batch 4096,
+# P = 16, data-parallel with one NCCL gradient all-reduce per step
+# --------------------------------------------------------------------------------------------
+TRAIN_BATCH, TRAIN_P = 4096, 16
+FLOP_PER_ROI_FWD_TRAIN = 27787264 + 4194304 + 2097152 + TRAIN_P * (1228800 + 2097152 + 4194304 + 1048576 + 20480000)
+
+
+def run_ours_train(args):
+    import torch
+    import torch.distributed as dist
+    import image_captioning_b200 as pkg
+    from image_captioning_b200 import synth, parallel
+
+    rank, local_rank, world = dist_env()
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sms, cc = pkg._lib.device_info()
+    lo, hi = parallel.shard_bounds(TRAIN_BATCH, rank, world)         # global batch split evenly: strong scaling
+    Bl = hi - lo
+    # random initialisation as at the start of training (Glorot / orthogonal, no trained-like logit sharpening)
+    w = synth.synth_weights_v1(np.random.default_rng(SEED_DECODER), V=VOCAB, E=EMBED, U=UNITS, C=CHANNELS,
+                               trained_like=False)
+    cfg = pkg.DenseCapConfig(VOCAB, w["imgcap_embedding_layer/embeddings"], Bl, TRAIN_P)
+    model = pkg.build_lstm_model([POOL[0], POOL[1], CHANNELS], cfg, UNITS, "training", dtype="bfloat16", device=dev)
+    model.set_weights(w)
+    model.compile(optimizer=pkg.Adam(amsgrad=True), loss=pkg.roi_caption_loss)
+    trainer = parallel.DataParallelTrainer(model)
+    rng = np.random.default_rng(1003)
+    gt_np = synth.synth_captions(rng, TRAIN_BATCH, TRAIN_P, VOCAB)[lo:hi]
+    gen = torch.Generator(device=dev).manual_seed(1003 + rank)
+    feats = torch.randn((Bl, POOL[0], POOL[1], CHANNELS), device=dev, generator=gen)       # fp32 RoI features (ROIAlign output)
+    gt = torch.from_numpy(gt_np).to(dev).to(torch.int32)
+    npos = float(TRAIN_BATCH * TRAIN_P)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses = []
+    for _ in range(max(args.warmup, 3)):
+        losses.append(trainer.train_step(feats, gt, None, npos))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    K = args.steps
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(K):
+        losses.append(trainer.train_step(feats, gt, None, npos))
+        ev[i + 1].record()
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    clocks = sampler.summary()
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / K
+    value = TRAIN_BATCH / (ms_per_step * 1e-3)
+    flops = 3.0 * FLOP_PER_ROI_FWD_TRAIN * Bl
+    tf_peak, tf_src = measured_peaks("bf16_tflops_sustained")
+    achieved = flops / (ms_per_step * 1e-3) / 1e12
+    loss_hist = [float(l.item()) for l in losses]
+    line = {
+        "metric": "train_rois_per_sec", "value": round(value, 1), "unit": "RoI/s", "n_gpus": world, "steps": K,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "cfg3 train: v1 inject-LSTM decoder training step (head trainable), global batch %d RoIs "
+                               "x P=%d, hidden %d, vocab %d, embedding %d; bf16 operands / fp32 master weights; "
+                               "forward + roi_caption_loss + BPTT + NCCL gradient all-reduce + Keras AMSGrad update"
+                               % (TRAIN_BATCH, TRAIN_P, UNITS, VOCAB, EMBED),
+                   "rois_per_step": TRAIN_BATCH, "rois_per_rank": Bl, "sharding": "global batch split over ranks; "
+                   "one all-reduce(sum) of %d fp32 gradients per step" % model.grad_buffer().numel(),
+                   "l2": "activations larger than L2 (logits %d MB per rank)" % (Bl * TRAIN_P * VOCAB * 4 // 2 ** 20),
+                   "sm_count": sms, "cc": cc, "loss_first": round(loss_hist[0], 4), "loss_last": round(loss_hist[-1], 4)},
+        "clocks": clocks, "gpu_launches": K * 130,
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (forward scan + time-batched dense/vocab GEMMs + "
+                     "dgrad/wgrad GEMMs)", "achieved": round(achieved, 1), "peak": tf_peak, "peak_source": tf_src,
+                     "unit": "TFLOP/s", "frac": round(achieved / tf_peak, 4), "traffic": None,
+                     "algorithmic_flops_per_step_per_rank": flops,
+                     "note": "whole step time (GEMMs + softmax/xent + cell backward + optimiser + all-reduce) against 3x forward FLOPs"},
+    }
+    if not args.no_e2e:
+        e2e_steps = max(1, min(K, args.e2e_steps))
+        h_feats = feats.cpu().pin_memory()
+        h_gt = gt.cpu().pin_memory()
+        d_feats, d_gt = torch.empty_like(feats), torch.empty_like(gt)
+
+        def e2e_step():
+            d_feats.copy_(h_feats, non_blocking=True)
+            d_gt.copy_(h_gt, non_blocking=True)
+            return float(trainer.train_step(d_feats, d_gt, None, npos).item())       # loss read back = D2H + sync
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        line["e2e"] = {"value": round(TRAIN_BATCH / float(t.item()), 1), "unit": "RoI/s",
+                       "h2d_bytes_per_step": int(h_feats.numel() * 4 + h_gt.numel() * 4), "d2h_bytes_per_step": 4,
+                       "steps": e2e_steps, "api": "RoiCaptionModel.train_step_device + DataParallelTrainer (pinned host "
+                       "features + captions in, scalar loss out)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="captions", choices=["captions", "roi_features"])
+    ap.add_argument("--workload", default="captions", choices=["captions", "roi_features", "train"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
-        (run_reference_captions if args.workload == "captions" else run_reference)(args)
+        (run_reference if args.workload == "roi_features" else run_reference_captions)(args)
     elif args.workload == "captions":
         run_ours_captions(args)
+    elif args.workload == "train":
+        run_ours_train(args)
     else:
         run_ours_roi_features(args)
 

@@ -1,0 +1,116 @@
+"""One process per GPU: the replacement of the reference's in-process ``ParallelModel``
+(/root/reference/dense_img_cap_separate_models/parallel_model.py:22-102: tf.split of the inputs
+over towers that share variables, outputs concatenated on the CPU).
+
+The path shards by construction: RoIs are independent and a RoI needs only
+its own image's pyramid, so inference shards IMAGES (ROIAlign, captions) or RoI ROWS (beam over
+pre-extracted features) across ranks with no data-path collective; weights are replicated.  The
+only exchange step is the decoder-training gradient: every rank runs the training step on its
+slice of the global batch with the loss normalised by the GLOBAL position count, the flat fp32
+gradient buffer is summed with ONE NCCL all-reduce over NVLink/NVSwitch, and every rank applies
+the same optimiser update (replicas stay bit-identical: the all-reduce result is identical on all
+ranks and the update is deterministic).
+
+``torch.distributed`` is plumbing only (rendezvous + the NCCL communicator); under ``gloo`` on CPU
+the same host logic is exercised by tests/test_parallel.py with a stand-in model.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous, balanced split of n items: the first n % world ranks get one extra item."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError("rank %d outside world of %d" % (rank, world))
+    q, r = divmod(int(n), world)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def shard(seq, rank, world):
+    """The slice of ``seq`` (images, RoI rows, captions ...) this rank owns."""
+    lo, hi = shard_bounds(len(seq), rank, world)
+    return seq[lo:hi]
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def gather_rows(local, total_rows, group=None):
+    """Concatenate per-rank result rows (token ids, scores) in rank order on every rank.  Used only
+    to assemble the final report -- never on the data path.  ``local`` holds this rank's
+    shard_bounds(total_rows) rows."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    sizes = [hi - lo for lo, hi in (shard_bounds(total_rows, r, world) for r in range(world))]
+    pad = max(sizes)                                        # equal-sized messages (shards differ by <= 1 row)
+    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[:local.shape[0]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], 0)
+
+
+class DataParallelTrainer(object):
+    """Data-parallel ``train_on_batch`` over the ranks of ``group``.
+
+    ``model`` needs the training surface of RoiCaptionModel: ``train_step_device(features, gt,
+    targets, inv_count) -> device scalar``, ``grad_buffer() -> flat fp32 tensor`` and
+    ``apply_gradients(grad_scale)``.  Semantics equal ONE process training on the concatenated
+    global batch: loss = mean over all positions of all ranks."""
+
+    def __init__(self, model, group=None, bucket_mb=0):
+        self.model, self.group = model, group
+        self.rank, self.world = _world(group)
+        self.bucket_elems = int(bucket_mb * (1 << 20) // 4)
+
+    def broadcast_parameters(self, src=0):
+        """Make every replica start from rank ``src``'s trainable weights (Keras towers share variables)."""
+        if self.world > 1:
+            dist.broadcast(self.model.param_buffer(), src, group=self.group)
+
+    def _count_positions(self, gt, targets):
+        if targets is None:
+            n = float(gt.shape[0] * gt.shape[1])
+        else:
+            t = torch.as_tensor(targets)
+            # one-hot rows [N,P,V]: a position counts when its row is not all-zero; ids [N,P]: when >= 0
+            n = float((t.sum(-1) > 0).sum()) if t.dim() == 3 else float((t >= 0).sum())
+        return torch.tensor([n], dtype=torch.float64)
+
+    def train_step(self, features, gt, targets=None, global_positions=None):
+        """Local forward/backward + gradient all-reduce + update.  Returns the GLOBAL mean loss as a
+        device scalar (no host sync).  ``global_positions``: number of loss positions over all
+        ranks; derived with one tiny all-reduce if not given."""
+        if global_positions is None:
+            cnt = self._count_positions(gt, targets)
+            if self.world > 1:
+                g = self.model.grad_buffer()
+                cnt = cnt.to(g.device)
+                dist.all_reduce(cnt, group=self.group)
+            global_positions = float(cnt.item())
+        if global_positions <= 0:
+            return torch.zeros(())
+        loss = self.model.train_step_device(features, gt, targets, 1.0 / global_positions)
+        if self.world > 1:
+            g = self.model.grad_buffer()
+            if self.bucket_elems > 0:
+                # reverse-layer order (vocabulary projection first) so the last-produced head
+                # gradients are the last bucket on the wire
+                hs = [dist.all_reduce(g[max(0, e - self.bucket_elems):e], group=self.group, async_op=True)
+                      for e in range(g.numel(), 0, -self.bucket_elems)]
+                for h in hs:
+                    h.wait()
+            else:
+                dist.all_reduce(g, group=self.group)
+            dist.all_reduce(loss, group=self.group)
+        self.model.apply_gradients(1.0)
+        return loss
+
+    def train_on_batch(self, x, y=None):
+        feats, gt = x
+        return float(self.train_step(feats, gt, y).item())
