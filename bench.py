@@ -696,13 +696,113 @@ def run_ours_train(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------
+# beam workload (BASELINE.json configs[3]): width-3 beam decoding of 100k pre-extracted 1024-d RoI
+# feature vectors, rows sharded over ranks (no collective)
+# --------------------------------------------------------------------------------------------
+BEAM_ROIS, BEAM_K, BEAM_CHUNK = 100000, 3, 16384
+# hoisted terms once + (1 + (P-2)*k) word-model rows of 29.05 MFLOP (first step has one live beam)
+FLOP_PER_ROI_BEAM = 4194304 + 2097152 + (1 + (PADDING - 2) * BEAM_K) * (1228800 + 2097152 + 4194304 + 1048576 + 20480000)
+
+
+def run_ours_beam(args):
+    import torch
+    import torch.distributed as dist
+    import image_captioning_b200 as pkg
+    from image_captioning_b200 import parallel
+
+    rank, local_rank, world = dist_env()
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sms, cc = pkg._lib.device_info()
+    lo, hi = parallel.shard_bounds(BEAM_ROIS, rank, world)
+    n = hi - lo
+    w = _decoder_weights()
+    cfg = pkg.DenseCapConfig(VOCAB, w["imgcap_embedding_layer/embeddings"], 1, PADDING)
+    model = pkg.build_lstm_model([POOL[0], POOL[1], CHANNELS], cfg, UNITS, "inference", dtype="bfloat16", device=dev)
+    model.set_weights(w)
+    gen = torch.Generator(device=dev).manual_seed(1004 + rank)
+    feats = torch.relu(torch.randn((n, 1024), device=dev, generator=gen))       # post-ReLU head features
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(min(args.warmup, 3), 1)):
+        tokens, scores = model.beam_search(feats, beam_width=BEAM_K, chunk=BEAM_CHUNK)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    K = args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        tokens, scores = model.beam_search(feats, beam_width=BEAM_K, chunk=BEAM_CHUNK)
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    clocks = sampler.summary()
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / K
+    value = BEAM_ROIS / (ms_per_step * 1e-3)
+    flops = FLOP_PER_ROI_BEAM * n
+    tf_peak, tf_src = measured_peaks("bf16_tflops_sustained")
+    achieved = flops / (ms_per_step * 1e-3) / 1e12
+    chunks = (n + BEAM_CHUNK - 1) // BEAM_CHUNK
+    line = {
+        "metric": "beam_captions_per_sec", "value": round(value, 1), "unit": "RoI captions/s", "n_gpus": world, "steps": K,
+        "warmup": max(min(args.warmup, 3), 1), "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "cfg4 beam: width-%d beam decoding (probability-sum scores, P=%d) of %d pre-extracted 1024-d "
+                               "RoI feature vectors, hidden %d, vocab %d; rows sharded over ranks, %d-RoI chunks"
+                               % (BEAM_K, PADDING, BEAM_ROIS, UNITS, VOCAB, BEAM_CHUNK),
+                   "rois_per_step": BEAM_ROIS, "rois_per_rank": n, "sharding": "contiguous RoI rows per rank, no collective",
+                   "l2": "inputs larger than L2 (features %d MB, beam state %d MB per chunk)"
+                         % (n * 4096 // 2 ** 20, BEAM_CHUNK * BEAM_K * (832 + 1024) * 4 // 2 ** 20),
+                   "sm_count": sms, "cc": cc},
+        "clocks": clocks, "gpu_launches": K * chunks * (8 + 8 * (PADDING - 1)),
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (gate GEMMs + fused cell, dense1, vocabulary GEMM + "
+                     "fused top-k epilogue)", "achieved": round(achieved, 1), "peak": tf_peak, "peak_source": tf_src,
+                     "unit": "TFLOP/s", "frac": round(achieved / tf_peak, 4), "traffic": None,
+                     "algorithmic_flops_per_step_per_rank": flops},
+    }
+    if not args.no_e2e:
+        h_feats = feats.cpu().pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        d = h_feats.to(dev, non_blocking=True)
+        tk, sc = model.beam_search(d, beam_width=BEAM_K, chunk=BEAM_CHUNK)
+        h_tok, h_sc = tk.cpu(), sc.cpu()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        line["e2e"] = {"value": round(BEAM_ROIS / float(t.item()), 1), "unit": "RoI captions/s",
+                       "h2d_bytes_per_step": int(h_feats.numel() * 4),
+                       "d2h_bytes_per_step": int(h_tok.numel() * 4 + h_sc.numel() * 8), "steps": 1,
+                       "api": "RoiCaptionModel.beam_search (host features in, [N,k,P] ids + [N,k] scores out)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="captions", choices=["captions", "roi_features", "train"])
+    ap.add_argument("--workload", default="captions", choices=["captions", "roi_features", "train", "beam"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer leg")
@@ -713,6 +813,8 @@ def main():
         run_ours_captions(args)
     elif args.workload == "train":
         run_ours_train(args)
+    elif args.workload == "beam":
+        run_ours_beam(args)
     else:
         run_ours_roi_features(args)
 

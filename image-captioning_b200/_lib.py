@@ -71,6 +71,8 @@ SIGNATURES = {
                                        c_void]),
     "dc_gemm_bf16_argmax": (ctypes.c_int, [c_void, ctypes.c_int64, c_void, ctypes.c_int64, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int, c_void, c_void, c_void, c_void]),
+    "dc_gemm_bf16_topk": (ctypes.c_int, [c_void, ctypes.c_int64, c_void, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, c_void, ctypes.c_int, c_void, c_void, c_void]),
     "dc_gemm_bf16_lstm_cell": (ctypes.c_int, [c_void, ctypes.c_int64, c_void, ctypes.c_int64, ctypes.c_int,
                                               ctypes.c_int, ctypes.c_int, c_void, ctypes.c_int64, c_void, c_void,
                                               c_void, c_void, ctypes.c_int64, c_void, ctypes.c_int64, c_void,

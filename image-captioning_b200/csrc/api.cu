@@ -102,6 +102,26 @@ extern "C" int dc_gemm_bf16_argmax(const uint16_t *A, int64_t lda, const uint16_
     return rc;
 }
 
+extern "C" int dc_gemm_bf16_topk(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M, int N, int K,
+                                 const float *bias, int k, int32_t *idx, float *prob, void *stream) {
+    if (M <= 0) return DC_OK;
+    DC_REQUIRE(idx && prob && bias, "null pointer argument");
+    DC_REQUIRE(k >= 1 && k <= kTopKMax && k <= N, "k=%d outside [1,%d]", k, kTopKMax);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int slots = gemm_tc_argmax_tiles(N);
+    float *partial = nullptr;
+    DC_CHECK_CUDA(cudaMallocAsync((void **)&partial, sizeof(float) * (2 + 2 * k) * (size_t)M * slots, s));
+    TcOperand a, b;
+    a.ptr = reinterpret_cast<const __nv_bfloat16 *>(A); a.ld = lda;
+    b.ptr = reinterpret_cast<const __nv_bfloat16 *>(Bt); b.ld = ldb;
+    TcEpilogue ep;
+    ep.bias = bias; ep.partial = partial; ep.topk = k;
+    int rc = gemm_bf16_tc(a, b, ep, M, N, K, kEpiTopK, s);
+    if (rc == DC_OK) rc = topk_merge(partial, M, slots, k, idx, prob, s);
+    cudaFreeAsync(partial, s);
+    return rc;
+}
+
 extern "C" int dc_gemm_bf16_lstm_cell(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M,
                                       int units, int K, const float *addend, int64_t ld_addend,
                                       const float *bias, const int32_t *tok, float *c,

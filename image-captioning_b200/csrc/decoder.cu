@@ -342,16 +342,17 @@ int Decoder::greedy(const void *feats, int kind, int B, int32_t *tokens, float *
 int Decoder::beam(const void *feats, int kind, int B, int k, int32_t *tokens, double *scores, cudaStream_t s) {
     if (int rc = check_ready(B)) return rc;
     DC_REQUIRE(cfg.arch == DC_ARCH_V1, "dc_decoder_beam needs a v1 decoder");
-    DC_REQUIRE(k >= 1 && k <= kMaxBeam, "beam width %d outside [1,%d]", k, kMaxBeam);
-    DC_REQUIRE(cfg.dtype == DC_DTYPE_F32, "beam search is served by the fp32 decoder in this build");
+    DC_REQUIRE(k >= 1 && k <= kMaxBeam && k <= cfg.vocab, "beam width %d outside [1,%d]", k, kMaxBeam);
     if (B == 0) return DC_OK;
     DC_REQUIRE(feats && tokens && scores, "null pointer argument");
+    DC_REQUIRE((long long)B * k < (1ll << 31), "too many beam rows in one call");
+    if (cfg.dtype == DC_DTYPE_BF16) return beam_bf16(feats, kind, B, k, tokens, scores, s);
     const int R = B * k;
     if (int rc = reserve(R)) return rc;
     const int P = cfg.padding, V = cfg.vocab, E = cfg.embed, U = cfg.units;
     if (int rc = head(feats, kind, B, ws.F, s)) return rc;
     if (int rc = v1_hoist(B, s)) return rc;
-    // replicate the per-RoI constant terms per beam (a1 / d are free at this point)
+    // replicate the per-RoI constant terms per beam
     if (int rc = ensure_rep(R)) return rc;
     repeat_rows_kernel<<<R, 128, 0, s>>>(ws.g1f, 4 * U, k, R, rep_g1f);
     repeat_rows_kernel<<<R, 128, 0, s>>>(ws.d1f, kDense, k, R, rep_d1f);
@@ -374,7 +375,6 @@ int Decoder::beam(const void *feats, int kind, int B, int k, int32_t *tokens, do
         rc |= beam_gather(R, k, U, ws.parent, ws.c1, U, ws.c1b, U, 4, s);
         rc |= beam_gather(R, k, U, ws.parent, ws.c2, U, ws.c2b, U, 4, s);
         rc |= beam_gather(R, k, P, ws.parent, hist, P, hist_n, P, 4, s);
-        if (cfg.dtype == DC_DTYPE_BF16) rc |= beam_gather_bf16(R, k, s);
         if (rc) return rc;
         std::swap(ws.xh1, ws.xh1b); std::swap(ws.xh2, ws.xh2b);
         std::swap(ws.c1, ws.c1b); std::swap(ws.c2, ws.c2b);

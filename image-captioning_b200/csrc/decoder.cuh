@@ -104,7 +104,7 @@ struct Decoder {
     int greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s);
     int greedy_bf16_graphed(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s);
     void drop_graphs();
-    int beam_gather_bf16(int R, int k, cudaStream_t s);
+    int beam_bf16(const void *feats, int kind, int B, int k, int32_t *tokens, double *scores, cudaStream_t s);
     void free_bf16();
 
     // training step (train.cu; bf16 v1 decoder only)

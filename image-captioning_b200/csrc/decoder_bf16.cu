@@ -107,6 +107,7 @@ int Decoder::refresh_bf16(bool fresh, cudaStream_t s) {
 
 int Decoder::reserve_bf16(size_t R) {
     Bf16State &b = *bf;
+    b.topk_partial = nullptr; b.topk_cap = 0;            // lived in the workspace that was just released
     const size_t F = cfg.feat, U = cfg.units;
     const size_t Kin = (size_t)cfg.pool * cfg.pool * cfg.channels;
     const size_t K1 = b.Epad + U;
@@ -171,7 +172,8 @@ int Decoder::reset_state_bf16(int R, cudaStream_t s) {
 }
 
 // the three GEMMs up to the Dense(1024) activations; leaves d (bf16) ready for the vocab GEMM
-static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, bool gather, cudaStream_t s) {
+// addend_div > 0: rows are (RoI, beam) pairs and the per-RoI terms g1f / d1f are indexed by row / addend_div
+static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, bool gather, cudaStream_t s, int addend_div = 0) {
     Bf16State &b = *D.bf;
     const DcDecoderConfig &cfg = D.cfg;
     const int E = cfg.embed, U = cfg.units, V = cfg.vocab, K1 = b.Epad + U, p = b.parity;
@@ -179,7 +181,7 @@ static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, bool
     if (gather)
         if (int rc = embed_gather(D.W("imgcap_embedding_layer/embeddings"), D.ws.tok, R, E, V, b.X1[p], K1, true, s)) return rc;
     TcEpilogue c1;
-    c1.addend = g1f; c1.ld_addend = 4 * U; c1.cell_c = D.ws.c1; c1.cell_units = U; c1.cell_tok = D.ws.tok;
+    c1.addend = g1f; c1.ld_addend = 4 * U; c1.addend_div = addend_div; c1.cell_c = D.ws.c1; c1.cell_units = U; c1.cell_tok = D.ws.tok;
     c1.cell_h_prev = b.X1[p] + b.Epad; c1.ld_h_prev = K1;
     c1.cell_h_a = b.X1[p ^ 1] + b.Epad; c1.ld_h_a = K1;
     c1.cell_h_b = b.X2[p]; c1.ld_h_b = 2 * U;
@@ -190,7 +192,7 @@ static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, bool
     c2.cell_h_a = b.X2[p ^ 1] + U; c2.ld_h_a = 2 * U;
     if (int rc = gemm_bf16_tc(op(b.X2[p], 2 * U), op(b.w2cat, 2 * U), c2, R, 4 * U, 2 * U, kEpiCell, s)) return rc;
     TcEpilogue d1;
-    d1.addend = d1f; d1.ld_addend = kDense; d1.relu = 1; d1.out_bf16 = b.d; d1.ld_bf16 = kDense;
+    d1.addend = d1f; d1.ld_addend = kDense; d1.addend_div = addend_div; d1.relu = 1; d1.out_bf16 = b.d; d1.ld_bf16 = kDense;
     if (int rc = gemm_bf16_tc(op(b.X2[p ^ 1] + U, 2 * U), op(b.wd1h, U), d1, R, kDense, U, kEpiStore, s)) return rc;
     b.parity ^= 1;
     return DC_OK;
@@ -281,11 +283,85 @@ int Decoder::greedy_bf16_graphed(const void *feats, int kind, int B, int32_t *to
     return DC_OK;
 }
 
-// beam search keeps its state permutation on the fp32 buffers; mirror it on the bf16 operand
-// buffers (h1 inside X1, [h1|h2] inside X2)
-int Decoder::beam_gather_bf16(int R, int k, cudaStream_t s) {
-    (void)R; (void)k; (void)s;
-    return set_error(DC_ERR_UNSUPPORTED, "beam search is served by the fp32 decoder in this build");
+// ------------------------------------------------------------------------------------------------
+// beam search (gen_captions, image captioning/test.py:23-64) on the tensor-core path
+// ------------------------------------------------------------------------------------------------
+// Children inherit the parent's post-step state: one CTA per beam row copies h1, h2 (bf16, inside the
+// GEMM operand buffers), c1, c2 (fp32) and the token history from row (b, parent[b, j]), then appends
+// the new token.  dst buffers are the "other parity" operand buffers / spare state buffers.
+struct BeamPermute {
+    const int32_t *parent, *new_tok;
+    const __nv_bfloat16 *h1_src, *h2_src; __nv_bfloat16 *h1_dst, *h2_dst;
+    long long ld1, ld2;
+    const float *c1_src, *c2_src; float *c1_dst, *c2_dst;
+    const int32_t *hist_src; int32_t *hist_dst, *tok;
+    int k, U, P, col;
+};
+
+__global__ void __launch_bounds__(128) beam_permute_kernel(const BeamPermute a, int rows) {
+    const int r = blockIdx.x;
+    if (r >= rows) return;
+    const long long sr = (long long)(r / a.k) * a.k + a.parent[r];
+    const int u8 = a.U >> 3, u4 = a.U >> 2;
+    const uint4 *h1s = reinterpret_cast<const uint4 *>(a.h1_src + sr * a.ld1), *h2s = reinterpret_cast<const uint4 *>(a.h2_src + sr * a.ld2);
+    uint4 *h1d = reinterpret_cast<uint4 *>(a.h1_dst + (long long)r * a.ld1), *h2d = reinterpret_cast<uint4 *>(a.h2_dst + (long long)r * a.ld2);
+    const float4 *c1s = reinterpret_cast<const float4 *>(a.c1_src + sr * a.U), *c2s = reinterpret_cast<const float4 *>(a.c2_src + sr * a.U);
+    float4 *c1d = reinterpret_cast<float4 *>(a.c1_dst + (long long)r * a.U), *c2d = reinterpret_cast<float4 *>(a.c2_dst + (long long)r * a.U);
+    for (int i = threadIdx.x; i < u8; i += blockDim.x) { h1d[i] = h1s[i]; h2d[i] = h2s[i]; }
+    for (int i = threadIdx.x; i < u4; i += blockDim.x) { c1d[i] = c1s[i]; c2d[i] = c2s[i]; }
+    const int nt = a.new_tok[r];
+    for (int i = threadIdx.x; i < a.P; i += blockDim.x)
+        a.hist_dst[(long long)r * a.P + i] = (i == a.col) ? nt : a.hist_src[sr * a.P + i];
+    if (threadIdx.x == 0) a.tok[r] = nt;
+}
+
+int Decoder::beam_bf16(const void *feats, int kind, int B, int k, int32_t *tokens, double *scores, cudaStream_t s) {
+    const int R = B * k;
+    if (int rc = reserve(R)) return rc;
+    Bf16State &b = *bf;
+    const int P = cfg.padding, V = cfg.vocab, U = cfg.units, K1 = b.Epad + U;
+    const int slots = gemm_tc_argmax_tiles(V);
+    const size_t part_floats = (size_t)R * slots * (2 + 2 * k);
+    if (part_floats > b.topk_cap) {                      // top-k partials: [R, slots, 2 + 2k] floats
+        if (int rc = dev_alloc((void **)&b.topk_partial, sizeof(float) * part_floats, ws_owned)) return rc;
+        b.topk_cap = part_floats;
+    }
+    // head + hoisted per-RoI terms on B rows; the step GEMMs read them with addend row = beam row / k
+    if (int rc = head(feats, kind, B, ws.F, s)) return rc;
+    if (int rc = v1_hoist(B, s)) return rc;
+    if (int rc = v1_reset_state(R, s)) return rc;
+    if (int rc = fill_i32(ws.tok, R, 1, s)) return rc;                  // <start> = 1
+    DC_CHECK_CUDA(cudaMemsetAsync(ws.score_a, 0, sizeof(double) * R, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(ws.hist_a, 0, sizeof(int32_t) * (size_t)R * P, s));
+    if (int rc = set_token_column(ws.hist_a, R, P, 0, ws.tok, s)) return rc;
+    int32_t *hist = ws.hist_a, *hist_n = ws.hist_b;
+    double *sc = ws.score_a, *sc_n = ws.score_b;
+    for (int t = 0; t + 1 < P; ++t) {
+        if (int rc = step_core(*this, R, ws.g1f, ws.d1f, true, s, k)) return rc;
+        TcEpilogue e;
+        e.bias = W("imgcap_lstm_d2/bias"); e.partial = b.topk_partial; e.topk = k;
+        if (int rc = gemm_bf16_tc(op(b.d, kDense), op(b.wd2, kDense), e, R, V, kDense, kEpiTopK, s)) return rc;
+        if (int rc = topk_merge(b.topk_partial, R, slots, k, ws.cand_idx, ws.cand_p, s)) return rc;
+        if (int rc = beam_select(B, k, t == 0 ? 1 : k, ws.cand_idx, ws.cand_p, sc, sc_n, ws.parent, ws.newtok, s)) return rc;
+        // after step_core the live state sits in X1[parity] (h1) / X2[parity] (h2): permute it into the other
+        // parity's buffers and make those current
+        const int p = b.parity;
+        BeamPermute a;
+        a.parent = ws.parent; a.new_tok = ws.newtok;
+        a.h1_src = b.X1[p] + b.Epad; a.h1_dst = b.X1[p ^ 1] + b.Epad; a.ld1 = K1;
+        a.h2_src = b.X2[p] + U; a.h2_dst = b.X2[p ^ 1] + U; a.ld2 = 2 * U;
+        a.c1_src = ws.c1; a.c1_dst = ws.c1b; a.c2_src = ws.c2; a.c2_dst = ws.c2b;
+        a.hist_src = hist; a.hist_dst = hist_n; a.tok = ws.tok;
+        a.k = k; a.U = U; a.P = P; a.col = t + 1;
+        beam_permute_kernel<<<R, 128, 0, s>>>(a, R);
+        DC_CHECK_LAUNCH();
+        b.parity ^= 1;
+        std::swap(ws.c1, ws.c1b); std::swap(ws.c2, ws.c2b);
+        std::swap(hist, hist_n); std::swap(sc, sc_n);
+    }
+    DC_CHECK_CUDA(cudaMemcpyAsync(tokens, hist, sizeof(int32_t) * (size_t)R * P, cudaMemcpyDeviceToDevice, s));
+    DC_CHECK_CUDA(cudaMemcpyAsync(scores, sc, sizeof(double) * R, cudaMemcpyDeviceToDevice, s));
+    return DC_OK;
 }
 
 }  // namespace dcap

@@ -18,6 +18,8 @@ struct Bf16State {
     __nv_bfloat16 *roi = nullptr, *a1 = nullptr, *Fb = nullptr, *d = nullptr;
     __nv_bfloat16 *X1[2] = {nullptr, nullptr}, *X2[2] = {nullptr, nullptr};
     float *partial = nullptr;
+    float *topk_partial = nullptr;                   // beam search: [rows, slots, 2 + 2k]
+    size_t topk_cap = 0;
     int parity = 0;
     // backward-pass operand copies: plain bf16 casts of the Keras [in, out] tensors, which are the
     // K-major B operands of dX = dY * W^T (N = in, K = out); built by refresh_train_weights() (train.cu)

@@ -232,11 +232,63 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
             float4 *dst = reinterpret_cast<float4 *>(ep.partial) + (long long)m * part_slots + part_slot;
             *dst = make_float4(best, __int_as_float(best_i), sum, 0.f);
         }
+    } else if constexpr (kEpi == kEpiTopK) {
+        wait_acc();
+        // per-row statistics over this region: running max / sum exp and the k best (value, index) pairs in
+        // descending lexicographic order (value, then index: among equal values the LARGER index ranks higher)
+        float tv[kTopKMax];
+        int ti[kTopKMax];
+#pragma unroll
+        for (int q = 0; q < kTopKMax; ++q) { tv[q] = -INFINITY; ti[q] = -1; }
+        float best = -INFINITY, sum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kCols; c0 += 32) {
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+            const int nb = n_base + c0;
+            if (nb < N) {
+                float cmax = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = nb + j;
+                    const float x = (n < N) ? v[j] + __ldg(ep.bias + n) : -INFINITY;
+                    v[j] = x;
+                    cmax = fmaxf(cmax, x);
+                }
+                if (cmax > best) { sum *= __expf(best - cmax); best = cmax; }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float x = v[j];
+                    sum += __expf(x - best);
+                    // columns arrive in increasing index order: x displaces the current k-th best when x >= it
+                    if (nb + j < N && x >= tv[kTopKMax - 1]) {
+                        float cv = x;
+                        int ci = nb + j;
+#pragma unroll
+                        for (int q = 0; q < kTopKMax; ++q) {
+                            if (cv >= tv[q]) {                       // later index wins ties
+                                const float t1 = tv[q]; const int t2 = ti[q];
+                                tv[q] = cv; ti[q] = ci; cv = t1; ci = t2;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        const int m = m_base + lane;
+        if (m < M) {
+            const int stride = 2 + 2 * ep.topk;
+            float *dst = ep.partial + ((long long)m * part_slots + part_slot) * stride;
+            dst[0] = best; dst[1] = sum;
+#pragma unroll
+            for (int q = 0; q < kTopKMax; ++q)
+                if (q < ep.topk) { dst[2 + 2 * q] = tv[q]; dst[3 + 2 * q] = __int_as_float(ti[q]); }
+        }
     } else if constexpr (kEpi == kEpiStore) {
         const int m = m_base + lane;
         const bool valid = m < M;
         const long long mr = valid ? m : (long long)(M - 1);
-        const float *add_row = ep.addend ? ep.addend + (ep.addend_mod > 0 ? mr % ep.addend_mod : mr) * ep.ld_addend : nullptr;
+        const float *add_row = ep.addend ? ep.addend + (ep.addend_mod > 0 ? mr % ep.addend_mod : (ep.addend_div > 0 ? mr / ep.addend_div : mr)) * ep.ld_addend : nullptr;
         const __nv_bfloat16 *mask_row = ep.mask_src ? ep.mask_src + mr * ep.ld_mask : nullptr;
         const bool bf16_vec8 = ep.out_bf16 && ((ep.ld_bf16 & 7) == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0);
         float4 a_nxt[8];
@@ -375,7 +427,7 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
         const int m = m_base + lane;
         const bool valid = m < M;
         const long long mr = valid ? m : (long long)(M - 1);
-        const float *add_row = ep.addend ? ep.addend + (ep.addend_mod > 0 ? mr % ep.addend_mod : mr) * ep.ld_addend : nullptr;
+        const float *add_row = ep.addend ? ep.addend + (ep.addend_mod > 0 ? mr % ep.addend_mod : (ep.addend_div > 0 ? mr / ep.addend_div : mr)) * ep.ld_addend : nullptr;
         const float *c_row = ep.cell_c + mr * ep.cell_units;
         float *c_dst = (ep.cell_c_out ? ep.cell_c_out : ep.cell_c) + mr * ep.cell_units;
         const bool masked = ep.cell_tok && __ldg(ep.cell_tok + mr) == 0;
@@ -670,7 +722,7 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
     const int tiles_m = ceil_div(M, kBlockM);
     // tile width: 256 columns unless that leaves most SMs without a tile and 128 fills more of them
     bool wide = N > 128;
-    if (wide && epi != kEpiArgmax && epi != kEpiArgmaxSum) {
+    if (wide && epi != kEpiArgmax && epi != kEpiArgmaxSum && epi != kEpiTopK) {
         const int t256 = tiles_m * ceil_div(N, 256), t128 = tiles_m * ceil_div(N, 128);
         if (t256 * 4 < sms * 3 && t128 > t256) wide = false;
     }
@@ -718,6 +770,10 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
         DC_REQUIRE(!ep.cell_gates_out || (((uintptr_t)ep.cell_gates_out & 15) == 0 && ep.ld_gates_out % 4 == 0),
                    "cell epilogue: gate buffer alignment");
         return wide ? launch_tc<256, kEpiCell>(ma, mb, ep, g, stream) : launch_tc<128, kEpiCell>(ma, mb, ep, g, stream);
+    }
+    if (epi == kEpiTopK) {
+        DC_REQUIRE(ep.partial && ep.bias && ep.topk >= 1 && ep.topk <= kTopKMax, "top-k epilogue needs bias, partial buffer, 1 <= k <= %d", kTopKMax);
+        return wide ? launch_tc<256, kEpiTopK>(ma, mb, ep, g, stream) : launch_tc<128, kEpiTopK>(ma, mb, ep, g, stream);
     }
     DC_REQUIRE((epi == kEpiArgmax || epi == kEpiArgmaxSum) && ep.partial && ep.bias,
                "gemm_bf16_tc: arg-max epilogue needs bias and partial buffer");
@@ -790,6 +846,76 @@ int argmax_merge(const float *partial, int rows, int tiles, int32_t *tok_out, in
                                                          tok_out, tok_stride, tok_cur, maxprob,
                                                          reinterpret_cast<const uint4 *>(emb), emb_ld / 8,
                                                          reinterpret_cast<uint4 *>(x_out), ld_x / 8);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
+// Merge of the kEpiTopK partials, one warp per row.  Each lane first reduces its slots (lane, lane+32, ...)
+// to a sorted list of k, then k rounds of a warp-wide lexicographic arg-max pop the global order.
+__global__ void __launch_bounds__(256) topk_merge_kernel(const float *__restrict__ partial, int rows, int slots, int k,
+                                                         int32_t *__restrict__ idx_out, float *__restrict__ p_out) {
+    const int r = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const int stride = 2 + 2 * k;
+    float tv[kTopKMax];
+    int ti[kTopKMax];
+#pragma unroll
+    for (int q = 0; q < kTopKMax; ++q) { tv[q] = -INFINITY; ti[q] = -1; }
+    float best = -INFINITY, sum = 0.f;
+    for (int t = lane; t < slots; t += 32) {
+        const float *p = partial + ((long long)r * slots + t) * stride;
+        const float mx = p[0], sm = p[1];
+        if (mx > best) { sum = sum * __expf(best - mx) + sm; best = mx; }
+        else if (mx > -INFINITY) sum += sm * __expf(mx - best);
+        for (int c = 0; c < k; ++c) {
+            float cv = p[2 + 2 * c];
+            int ci = __float_as_int(p[3 + 2 * c]);
+            if (ci < 0) break;
+#pragma unroll
+            for (int q = 0; q < kTopKMax; ++q) {
+                if (cv > tv[q] || (cv == tv[q] && ci > ti[q])) {
+                    const float t1 = tv[q]; const int t2 = ti[q];
+                    tv[q] = cv; ti[q] = ci; cv = t1; ci = t2;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
+        const float nm = fmaxf(best, ob);
+        sum = (best > -INFINITY ? sum * __expf(best - nm) : 0.f) + (ob > -INFINITY ? os * __expf(ob - nm) : 0.f);
+        best = nm;
+    }
+    float keep_v = 0.f;
+    int keep_i = 0;
+    for (int round = 0; round < k; ++round) {
+        float hv = tv[0];
+        int hi = ti[0], hl = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, hv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, hi, o), ol = __shfl_xor_sync(0xffffffffu, hl, o);
+            if (ov > hv || (ov == hv && oi > hi)) { hv = ov; hi = oi; hl = ol; }
+        }
+        if (lane == hl) {                                   // pop the winner's head
+#pragma unroll
+            for (int q = 0; q + 1 < kTopKMax; ++q) { tv[q] = tv[q + 1]; ti[q] = ti[q + 1]; }
+            tv[kTopKMax - 1] = -INFINITY; ti[kTopKMax - 1] = -1;
+        }
+        if (lane == k - 1 - round) { keep_v = hv; keep_i = hi; }      // ascending output order
+    }
+    if (lane < k) {
+        idx_out[(long long)r * k + lane] = keep_i;
+        p_out[(long long)r * k + lane] = __expf(keep_v - best) / sum;
+    }
+}
+
+int topk_merge(const float *partial, int rows, int slots, int k, int32_t *idx_out, float *p_out, cudaStream_t s) {
+    if (rows <= 0) return DC_OK;
+    DC_REQUIRE(k >= 1 && k <= kTopKMax, "beam width %d outside [1,%d]", k, kTopKMax);
+    topk_merge_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(partial, rows, slots, k, idx_out, p_out);
     DC_CHECK_LAUNCH();
     return DC_OK;
 }

@@ -8,6 +8,8 @@ constexpr int kEpiStore = 0;
 constexpr int kEpiArgmax = 1;       // max + first arg-max
 constexpr int kEpiArgmaxSum = 2;    // ... + sum exp(v - max) (softmax probability of the arg-max)
 constexpr int kEpiCell = 3;         // fused Keras LSTM cell on gate-interleaved columns
+constexpr int kEpiTopK = 4;         // per row and column region: max, sum exp, the k best (value, index) pairs (beam search)
+constexpr int kTopKMax = 8;
 
 struct TcOperand {
     // K-major (default): [rows, K] row-major, K contiguous, ld = row stride.
@@ -30,10 +32,13 @@ struct TcEpilogue {
     __nv_bfloat16 *out_bf16 = nullptr; long long ld_bf16 = 0;
     // kEpiStore extras (training)
     int addend_mod = 0;                   // > 0: addend row = m % addend_mod (per-RoI term broadcast over time)
+    int addend_div = 0;                   // > 0: addend row = m / addend_div (per-RoI term shared by the beams of a RoI)
     int deint_units = 0;                  // > 0: fp32 output column 4u+g is written to column g*units+u
     const __nv_bfloat16 *mask_src = nullptr; long long ld_mask = 0;   // v = mask_src[m,n] > 0 ? v : 0 (ReLU backward)
     int atomic = 0;                       // fp32 output is accumulated with red.global.add (implied by split-K)
     float *partial = nullptr;             // arg-max epilogues: [M, slots] float4 {max, argmax bits, sumexp, -}
+                                          // top-k epilogue: [M, slots, 2 + 2*topk] {max, sumexp, (value, index bits) x topk}
+    int topk = 0;
     // kEpiCell: column n = 4*unit + gate (i,f,g,o); z = acc + addend + bias
     float *cell_c = nullptr;              // [M, cell_units] fp32, updated in place
     int cell_units = 0;
@@ -50,6 +55,9 @@ struct TcEpilogue {
 int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, int M, int N, int K, int epi,
                  cudaStream_t stream, int split_k = 1);
 int gemm_tc_argmax_tiles(int N);
+// merges the kEpiTopK partials: per row the k largest softmax probabilities in ASCENDING order (ties: the larger
+// index ranks higher, as a stable ascending argsort followed by [-k:]) -> idx_out / p_out [rows, k]
+int topk_merge(const float *partial, int rows, int slots, int k, int32_t *idx_out, float *p_out, cudaStream_t s);
 int argmax_merge(const float *partial, int rows, int tiles, int32_t *tok_out, int tok_stride, int32_t *tok_cur,
                  float *maxprob, cudaStream_t s, const __nv_bfloat16 *emb = nullptr, int emb_ld = 0,
                  __nv_bfloat16 *x_out = nullptr, long long ld_x = 0);

@@ -75,6 +75,19 @@ def gemm_bf16_argmax(a, bt, bias, want_prob=False):
     return (tok, prob) if want_prob else tok
 
 
+def gemm_bf16_topk(a, bt, bias, k):
+    """Fused vocabulary GEMM + softmax top-k (ascending): (idx [M,k] int32, prob [M,k] fp32)."""
+    lib = _lib.load()
+    M, K = a.shape
+    N = bt.shape[0]
+    idx = torch.empty((M, k), dtype=torch.int32, device=a.device)
+    prob = torch.empty((M, k), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.dc_gemm_bf16_topk(_p(a), a.stride(0), _p(bt), bt.stride(0), M, N, K, _p(bias), int(k), _p(idx),
+                                         _p(prob), _s(a.device)))
+    return idx, prob
+
+
 def gemm_bf16_lstm_cell(a, bt_interleaved, units, c, h_prev, h_out, addend=None, bias=None, tok=None, h_out2=None):
     """Fused gates GEMM + Keras LSTM cell (gate-interleaved columns); c updated in place."""
     lib = _lib.load()

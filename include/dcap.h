@@ -285,6 +285,13 @@ int dc_gemm_bf16_ex(const uint16_t *A, int64_t lda, int a_mn, const uint16_t *B,
 int dc_gemm_bf16_argmax(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M, int N,
                         int K, const float *bias, int32_t *tokens, float *maxprob, void *stream);
 
+/* bf16 tcgen05 GEMM with the fused top-k epilogue (Dense(V) + softmax + np.argsort(p)[-k:] of the beam
+ * step, image captioning/test.py:41-48): per row the k largest softmax probabilities of
+ * (A*Bt^T + bias) in ASCENDING order, ties ranked like a stable ascending argsort (the larger index is
+ * the better candidate).  idx [M,k] int32, prob [M,k] fp32; 1 <= k <= 8.  The [M,N] logits are never written. */
+int dc_gemm_bf16_topk(const uint16_t *A, int64_t lda, const uint16_t *Bt, int64_t ldb, int M, int N, int K,
+                      const float *bias, int k, int32_t *idx, float *prob, void *stream);
+
 /* bf16 tcgen05 GEMM with the fused Keras LSTM cell epilogue (KL.LSTM step,
  * text_generation_model.py:141-142): z = A*Bt^T + addend + bias with GATE-INTERLEAVED columns
  * (column 4*u+g holds gate g in {i,f,c,o} of unit u, i.e. Bt row 4*u+g is column g*units+u of the

@@ -75,6 +75,35 @@ def test_tcgen05_gemm_argmax_epilogue(M, N, K):
     torch.testing.assert_close(prob, torch.softmax(logits, -1).max(-1).values, rtol=2e-3, atol=1e-6)
 
 
+@pytest.mark.parametrize("M,N,K,k", [(1000, 10000, 1024, 3), (130, 300, 128, 5), (64, 128, 64, 8), (200, 520, 64, 1)])
+def test_tcgen05_gemm_topk_epilogue(M, N, K, k):
+    from image_captioning_b200 import gemm
+    a = _rand((M, K), 34, torch.bfloat16)
+    bt = _rand((N, K), 35, torch.bfloat16)
+    bias = _rand((N,), 36)
+    idx, prob = gemm.gemm_bf16_topk(a, bt, bias, k)
+    logits = gemm.gemm_bf16(a, bt, bias=bias)                   # same kernel, store epilogue
+    p = torch.softmax(logits, -1)
+    want_p, want_i = torch.topk(logits, k, dim=-1)              # random logits: no ties
+    assert torch.equal(idx, want_i.flip(-1).to(torch.int32))    # ascending order, best last
+    torch.testing.assert_close(prob, torch.gather(p, 1, want_i.flip(-1)), rtol=2e-3, atol=1e-7)
+
+
+def test_topk_larger_index_wins_ties():
+    """np.argsort(p, stable)[-k:]: among equal probabilities the larger index is the better candidate."""
+    from image_captioning_b200 import gemm
+    M, N, K = 64, 600, 64
+    a = torch.zeros((M, K), device="cuda", dtype=torch.bfloat16)
+    bt = _rand((N, K), 41, torch.bfloat16)
+    bias = torch.zeros((N,), device="cuda")
+    bias[[17, 300, 301, 555]] = 1.0                              # four equal maxima across tiles / chunks
+    idx, prob = gemm.gemm_bf16_topk(a, bt, bias, 3)
+    assert bool((idx == torch.tensor([300, 301, 555], device="cuda", dtype=torch.int32)).all())
+    idx5, _ = gemm.gemm_bf16_topk(a, bt, bias, 5)
+    assert bool((idx5[:, 1:] == torch.tensor([17, 300, 301, 555], device="cuda", dtype=torch.int32)).all())
+    assert bool((idx5[:, 0] == 599).all())                       # all remaining logits tie at 0: largest index
+
+
 def test_argmax_first_index_on_ties():
     from image_captioning_b200 import gemm
     M, N, K = 64, 600, 64
