@@ -17,6 +17,7 @@
 #include "gemm_tc.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 
@@ -62,6 +63,21 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// smem tile -> global through the tensor map (clipped at the tensor bounds); bulk_group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+// same, but global += smem (fp32): the split-K / accumulating weight-gradient path
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -159,14 +175,20 @@ struct TcGeom {
     int M, N, K;
     int a_mn, b_mn;          // operand majorness
     int splits, kb_per;      // split-K: k-blocks [s*kb_per, min((s+1)*kb_per, num_kb)) per work unit
+    int tma_out;             // store epilogue output path: 0 = per-thread stores, 1 = fp32 via TMA, 2 = bf16 via TMA
 };
+
+constexpr int kOutStage = 4096;             // per epilogue warp: 32 rows x 128 B, SWIZZLE_128B
 
 template <int kBlockN>
 struct TcSmem {
     static constexpr int kStageA = kBlockM * kBlockK * 2;
     static constexpr int kStageB = kBlockN * kBlockK * 2;
     static constexpr int kStages = (kBlockN == 256) ? 4 : 6;
-    static constexpr int kBytes = kStages * (kStageA + kStageB) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kBarOff = kStages * (kStageA + kStageB);
+    static constexpr int kOutOff = kBarOff + 1024;                       // barriers live in their own 1 KB
+    static constexpr int kBaseBytes = kOutOff + 1024 /*align*/;            // without output staging (keeps more L1)
+    static constexpr int kBytes = kBaseBytes + kEpiWarps * kOutStage;
 };
 
 // MUFU.TANH: max relative error 2^-11, well inside the bf16 operand rounding (2^-9) of this path
@@ -192,7 +214,8 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
 template <int kCols, int kEpi>
 __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t taddr, int lane, int m_base, int n_base,
                                                 int M, int N, int part_slot, int part_slots, bool atomic,
-                                                uint64_t *full_bar, uint32_t full_phase) {
+                                                uint64_t *full_bar, uint32_t full_phase, uint8_t *stage,
+                                                const CUtensorMap *map_o, int tma_out) {
     auto wait_acc = [&]() {
         mbar_wait(full_bar, full_phase);
         tc_fence_after();
@@ -284,13 +307,19 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
             for (int q = 0; q < kTopKMax; ++q)
                 if (q < ep.topk) { dst[2 + 2 * q] = tv[q]; dst[3 + 2 * q] = __int_as_float(ti[q]); }
         }
-    } else if constexpr (kEpi == kEpiStore) {
+    } else if constexpr (kEpi == kEpiStore || kEpi == kEpiStoreTmaF32 || kEpi == kEpiStoreTmaB16) {
         const int m = m_base + lane;
         const bool valid = m < M;
         const long long mr = valid ? m : (long long)(M - 1);
         const float *add_row = ep.addend ? ep.addend + (ep.addend_mod > 0 ? mr % ep.addend_mod : (ep.addend_div > 0 ? mr / ep.addend_div : mr)) * ep.ld_addend : nullptr;
         const __nv_bfloat16 *mask_row = ep.mask_src ? ep.mask_src + mr * ep.ld_mask : nullptr;
         const bool bf16_vec8 = ep.out_bf16 && ((ep.ld_bf16 & 7) == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0);
+        // Output path.  tma_out != 0: the warp's 32 x 32 fp32 (or 32 x 64 bf16) sub-tile is staged in a
+        // 128-byte-swizzled shared-memory buffer and leaves the SM as ONE bulk tensor store (or fp32
+        // reduce-add for accumulating outputs): full 128-byte lines per row instead of 32 scattered
+        // 16-byte pieces per store instruction, and the bounds are clipped by the TMA unit.
+        constexpr bool tma_f32 = kEpi == kEpiStoreTmaF32, tma_b16 = kEpi == kEpiStoreTmaB16;
+        uint8_t *my_row = stage + lane * 128;
         float4 a_nxt[8];
         uint4 k_nxt[4];
         auto load_operands = [&](int nb) {
@@ -325,7 +354,8 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
             if (c0 + 32 < kCols && nb + 32 < N) load_operands(nb + 32);
             float v[32];
             tmem_ld32(taddr + c0, v);
-            if (nb + 32 <= N) {
+            const bool full = nb + 32 <= N;
+            if (full) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float xs[4] = {v[4 * j] + a_cur[j].x, v[4 * j + 1] + a_cur[j].y, v[4 * j + 2] + a_cur[j].z,
@@ -356,67 +386,112 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
 #pragma unroll
                     for (int q = 0; q < 4; ++q) v[4 * j + q] = xs[q];
                 }
-                if (valid) {
-                    if (ep.out_f32) {
-                        if (ep.deint_units > 0) {
-                            // columns 4u+g of this chunk -> 8 consecutive units of each of the 4 gate blocks
-                            const int u0 = nb >> 2;
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                float *dst = ep.out_f32 + (long long)m * ep.ld_f32 + (long long)g * ep.deint_units + u0;
-                                if (atomic) {
-                                    red_add_v4(dst, v[g], v[4 + g], v[8 + g], v[12 + g]);
-                                    red_add_v4(dst + 4, v[16 + g], v[20 + g], v[24 + g], v[28 + g]);
-                                } else {
-                                    reinterpret_cast<float4 *>(dst)[0] = make_float4(v[g], v[4 + g], v[8 + g], v[12 + g]);
-                                    reinterpret_cast<float4 *>(dst)[1] = make_float4(v[16 + g], v[20 + g], v[24 + g], v[28 + g]);
-                                }
-                            }
-                        } else {
-                            float *dst = ep.out_f32 + (long long)m * ep.ld_f32 + nb;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                if (atomic) red_add_v4(dst + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                                else reinterpret_cast<float4 *>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                            }
-                        }
-                    }
-                    if (ep.out_bf16) {
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                            pk[j] = *reinterpret_cast<uint32_t *>(&t);
-                        }
-                        __nv_bfloat16 *dst = ep.out_bf16 + (long long)m * ep.ld_bf16 + nb;
-                        if (bf16_vec8) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                reinterpret_cast<uint4 *>(dst)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                reinterpret_cast<uint2 *>(dst)[j] = make_uint2(pk[2 * j], pk[2 * j + 1]);
-                        }
-                    }
-                }
-            } else if (valid) {
-                // ragged last chunk of the last N tile: element-wise (never with deint / mask)
+            } else {
+                // ragged last chunk of the last N tile: element-wise (never with deint); columns >= N become 0
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = nb + j;
-                    if (n >= N) continue;
-                    float x = v[j];
-                    if (add_row) x += __ldg(add_row + n);
-                    if (ep.bias) x += __ldg(ep.bias + n);
-                    if (ep.scale) x = x * __ldg(ep.scale + n) + __ldg(ep.shift + n);
-                    if (ep.relu) x = fmaxf(x, 0.f);
-                    if (mask_row && !(__bfloat162float(mask_row[n]) > 0.f)) x = 0.f;
-                    if (ep.out_f32) {
-                        if (atomic) atomicAdd(ep.out_f32 + (long long)m * ep.ld_f32 + n, x);
-                        else ep.out_f32[(long long)m * ep.ld_f32 + n] = x;
+                    float x = 0.f;
+                    if (n < N) {
+                        x = v[j];
+                        if (add_row) x += __ldg(add_row + n);
+                        if (ep.bias) x += __ldg(ep.bias + n);
+                        if (ep.scale) x = x * __ldg(ep.scale + n) + __ldg(ep.shift + n);
+                        if (ep.relu) x = fmaxf(x, 0.f);
+                        if (mask_row && !(__bfloat162float(mask_row[n]) > 0.f)) x = 0.f;
                     }
-                    if (ep.out_bf16) ep.out_bf16[(long long)m * ep.ld_bf16 + n] = __float2bfloat16_rn(x);
+                    v[j] = x;
+                }
+            }
+            // ---- fp32 output ----
+            if constexpr (tma_f32) {
+                if (lane == 0) tma_store_wait_read();                // previous bulk store has drained the buffer
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4 *>(my_row + ((j ^ (lane & 7)) << 4)) =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (atomic) tma_reduce_add_2d(map_o, stage, nb, m_base);
+                    else tma_store_2d(map_o, stage, nb, m_base);
+                    tma_store_commit();
+                }
+            } else if (!tma_b16 && ep.out_f32 && valid) {
+                if (!full) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = nb + j;
+                        if (n >= N) continue;
+                        if (atomic) atomicAdd(ep.out_f32 + (long long)m * ep.ld_f32 + n, v[j]);
+                        else ep.out_f32[(long long)m * ep.ld_f32 + n] = v[j];
+                    }
+                } else if (ep.deint_units > 0) {
+                    // columns 4u+g of this chunk -> 8 consecutive units of each of the 4 gate blocks
+                    const int u0 = nb >> 2;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float *dst = ep.out_f32 + (long long)m * ep.ld_f32 + (long long)g * ep.deint_units + u0;
+                        if (atomic) {
+                            red_add_v4(dst, v[g], v[4 + g], v[8 + g], v[12 + g]);
+                            red_add_v4(dst + 4, v[16 + g], v[20 + g], v[24 + g], v[28 + g]);
+                        } else {
+                            reinterpret_cast<float4 *>(dst)[0] = make_float4(v[g], v[4 + g], v[8 + g], v[12 + g]);
+                            reinterpret_cast<float4 *>(dst)[1] = make_float4(v[16 + g], v[20 + g], v[24 + g], v[28 + g]);
+                        }
+                    }
+                } else {
+                    float *dst = ep.out_f32 + (long long)m * ep.ld_f32 + nb;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (atomic) red_add_v4(dst + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        else reinterpret_cast<float4 *>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+            }
+            // ---- bf16 output ----
+            if (tma_b16 || (!tma_f32 && ep.out_bf16 && valid)) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                    pk[j] = *reinterpret_cast<uint32_t *>(&t);
+                }
+                if constexpr (tma_b16) {
+                    // two 32-column chunks share one 64-column (128-byte) staging row
+                    const int half = (c0 >> 5) & 1;
+                    if (half == 0) {
+                        if (lane == 0) tma_store_wait_read();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4 *>(my_row + (((half * 4 + j) ^ (lane & 7)) << 4)) =
+                            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    if (half == 1 || nb + 32 >= N) {
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(map_o, stage, nb - half * 32, m_base);
+                            tma_store_commit();
+                        }
+                    }
+                } else if (!full) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < N) ep.out_bf16[(long long)m * ep.ld_bf16 + nb + j] = __float2bfloat16_rn(v[j]);
+                } else if constexpr (!tma_b16) {
+                    __nv_bfloat16 *dst = ep.out_bf16 + (long long)m * ep.ld_bf16 + nb;
+                    if (bf16_vec8) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            reinterpret_cast<uint4 *>(dst)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            reinterpret_cast<uint2 *>(dst)[j] = make_uint2(pk[2 * j], pk[2 * j + 1]);
+                    }
                 }
             }
         }
@@ -502,7 +577,7 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
 template <int kBlockN, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const TcEpilogue ep, const TcGeom g) {
+                    const __grid_constant__ CUtensorMap map_o, const TcEpilogue ep, const TcGeom g) {
     using S = TcSmem<kBlockN>;
     constexpr int kStages = S::kStages;
     constexpr uint32_t kTmemCols = 2 * kBlockN;                  // two accumulator buffers (power of 2)
@@ -510,7 +585,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *smem_a = smem;
     uint8_t *smem_b = smem + kStages * S::kStageA;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * (S::kStageA + S::kStageB));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::kBarOff);
     uint64_t *empty_bar = full_bar + kStages;
     uint64_t *tmem_full = empty_bar + kStages;
     uint64_t *tmem_empty = tmem_full + 2;
@@ -526,6 +601,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
+        if (g.tma_out) tma_prefetch_desc(&map_o);
         for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -617,12 +693,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int m0 = (tile / tiles_n) * kBlockM, n0 = tile_n * kBlockN;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * kCols;
             epilogue_region<kCols, kEpi>(ep, taddr, lane, m0 + quarter * 32, n0 + half * kCols, M, N,
-                                         tile_n * 2 + half, tiles_n * 2, atomic, &tmem_full[acc], acc_phase);
+                                         tile_n * 2 + half, tiles_n * 2, atomic, &tmem_full[acc], acc_phase,
+                                         smem + S::kOutOff + e * kOutStage, &map_o, g.tma_out);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (g.tma_out && lane == 0) tma_store_wait_all();            // bulk stores issued by this lane are complete
     }
     tc_fence_before();
     __syncthreads();
@@ -658,20 +736,24 @@ static EncodeTiledFn encode_fn() {
 // Encoding a map costs a driver call (~microseconds); the decoder re-uses a handful of
 // (pointer, shape) combinations every step, so encoded maps are memoised.
 struct TmapKey {
-    const void *ptr; long long outer, inner, ld; int box_outer;
+    const void *ptr; long long outer, inner, ld; int box_outer, box_inner, esize;
     bool operator<(const TmapKey &o) const {
         if (ptr != o.ptr) return ptr < o.ptr;
         if (outer != o.outer) return outer < o.outer;
         if (inner != o.inner) return inner < o.inner;
         if (ld != o.ld) return ld < o.ld;
-        return box_outer < o.box_outer;
+        if (box_outer != o.box_outer) return box_outer < o.box_outer;
+        if (box_inner != o.box_inner) return box_inner < o.box_inner;
+        return esize < o.esize;
     }
 };
 
-int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long outer, long long inner, long long ld, int box_outer) {
+// esize 2 = bf16, 4 = fp32; box = [box_outer, box_inner] elements with box_inner * esize == 128 bytes (one swizzle row)
+static int make_tmap(CUtensorMap *map, const void *ptr, long long outer, long long inner, long long ld, int box_outer,
+                     int box_inner, int esize) {
     static std::map<TmapKey, CUtensorMap> cache;
     static std::mutex mu;
-    const TmapKey key{ptr, outer, inner, ld, box_outer};
+    const TmapKey key{ptr, outer, inner, ld, box_outer, box_inner, esize};
     {
         std::lock_guard<std::mutex> g(mu);
         auto it = cache.find(key);
@@ -679,12 +761,12 @@ int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long outer, long long
     }
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(DC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    DC_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 2) % 16 == 0, "TMA operand must be 16-byte aligned with ld %% 8 == 0");
+    DC_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * esize) % 16 == 0, "TMA tensor must be 16-byte aligned with a row stride that is a multiple of 16 bytes");
     cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_outer};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * esize};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
+    CUresult r = fn(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(DC_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
@@ -696,9 +778,13 @@ int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long outer, long long
     return DC_OK;
 }
 
+int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long outer, long long inner, long long ld, int box_outer) {
+    return make_tmap(map, ptr, outer, inner, ld, box_outer, kBlockK, 2);
+}
+
 template <int kBlockN, int kEpi>
-static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcEpilogue &ep, const TcGeom &g,
-                     cudaStream_t stream) {
+static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const TcEpilogue &ep,
+                     const TcGeom &g, cudaStream_t stream) {
     using S = TcSmem<kBlockN>;
     static bool attr_set = false;
     auto kern = gemm_bf16_tc_kernel<kBlockN, kEpi>;
@@ -708,7 +794,7 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcEpilo
     }
     const int units = ceil_div(g.M, kBlockM) * ceil_div(g.N, kBlockN) * g.splits;
     const int grid = units < sm_count() ? units : sm_count();
-    kern<<<grid, kThreads, S::kBytes, stream>>>(ma, mb, ep, g);
+    kern<<<grid, kThreads, g.tma_out ? S::kBytes : S::kBaseBytes, stream>>>(ma, mb, mo, ep, g);
     DC_CHECK_LAUNCH();
     return DC_OK;
 }
@@ -730,6 +816,7 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
     TcGeom g;
     g.M = M; g.N = N; g.K = K; g.a_mn = A.mn_major ? 1 : 0; g.b_mn = B.mn_major ? 1 : 0;
     g.splits = 1;
+    g.tma_out = 0;
     if (epi == kEpiStore && ep.atomic && ep.out_f32 && !ep.out_bf16) {
         int want = split_k;
         if (want <= 0) {                      // fill ~2 waves, keep >= 8 k-blocks per unit
@@ -757,7 +844,29 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
                    "mask source must be 16-byte aligned, ld %% 8 == 0, N %% 32 == 0");
         DC_REQUIRE(ep.deint_units == 0 || (ep.out_f32 && !ep.out_bf16 && N == 4 * ep.deint_units && ep.deint_units % 8 == 0),
                    "de-interleaved store needs fp32 output with N == 4*units, units %% 8 == 0");
-        return wide ? launch_tc<256, kEpiStore>(ma, mb, ep, g, stream) : launch_tc<128, kEpiStore>(ma, mb, ep, g, stream);
+        // bulk tensor stores through shared memory for ONE plain output (fp32 preferred); a second output,
+        // de-interleaved columns and unaligned leading dimensions keep the per-thread stores
+        // Which outputs take the TMA path (bit mask, tunable for experiments): 1 = plain fp32, 2 = plain bf16,
+        // 4 = outputs whose epilogue also reads a per-row addend / mask, 8 = accumulating (reduce-add) fp32.
+        // Default 11: epilogues with per-row operand loads keep the smaller shared-memory footprint (the
+        // staging buffers cost 32 KB of L1, which those loads need more than they gain from bulk stores).
+        static const int tma_mask = getenv("DCAP_TMA_STORE_MASK") ? atoi(getenv("DCAP_TMA_STORE_MASK")) : 11;
+        CUtensorMap mo = ma;
+        const bool row_ops = ep.addend || ep.mask_src;
+        const bool accum = ep.atomic || g.splits > 1;
+        bool want = ep.deint_units == 0 && (!row_ops || (tma_mask & 4)) && (!accum || (tma_mask & 8));
+        if (want && ep.out_f32 && (accum || (tma_mask & 1))) {
+            if (int rc = make_tmap(&mo, ep.out_f32, M, N, ep.ld_f32, 32, 32, 4)) return rc;
+            g.tma_out = 1;
+        } else if (want && !ep.out_f32 && (tma_mask & 2) && ep.ld_bf16 % 8 == 0 && ((uintptr_t)ep.out_bf16 & 15) == 0) {
+            if (int rc = make_tmap(&mo, ep.out_bf16, M, N, ep.ld_bf16, 32, 64, 2)) return rc;
+            g.tma_out = 2;
+        }
+        if (g.tma_out == 1)
+            return wide ? launch_tc<256, kEpiStoreTmaF32>(ma, mb, mo, ep, g, stream) : launch_tc<128, kEpiStoreTmaF32>(ma, mb, mo, ep, g, stream);
+        if (g.tma_out == 2)
+            return wide ? launch_tc<256, kEpiStoreTmaB16>(ma, mb, mo, ep, g, stream) : launch_tc<128, kEpiStoreTmaB16>(ma, mb, mo, ep, g, stream);
+        return wide ? launch_tc<256, kEpiStore>(ma, mb, mo, ep, g, stream) : launch_tc<128, kEpiStore>(ma, mb, mo, ep, g, stream);
     }
     if (epi == kEpiCell) {
         DC_REQUIRE(ep.cell_c && ep.cell_units * 4 == N && N % 32 == 0, "cell epilogue: N must be 4*units, units %% 8 == 0");
@@ -769,18 +878,18 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
                    "cell epilogue: h buffers must be 16-byte aligned with ld %% 8 == 0");
         DC_REQUIRE(!ep.cell_gates_out || (((uintptr_t)ep.cell_gates_out & 15) == 0 && ep.ld_gates_out % 4 == 0),
                    "cell epilogue: gate buffer alignment");
-        return wide ? launch_tc<256, kEpiCell>(ma, mb, ep, g, stream) : launch_tc<128, kEpiCell>(ma, mb, ep, g, stream);
+        return wide ? launch_tc<256, kEpiCell>(ma, mb, ma, ep, g, stream) : launch_tc<128, kEpiCell>(ma, mb, ma, ep, g, stream);
     }
     if (epi == kEpiTopK) {
         DC_REQUIRE(ep.partial && ep.bias && ep.topk >= 1 && ep.topk <= kTopKMax, "top-k epilogue needs bias, partial buffer, 1 <= k <= %d", kTopKMax);
-        return wide ? launch_tc<256, kEpiTopK>(ma, mb, ep, g, stream) : launch_tc<128, kEpiTopK>(ma, mb, ep, g, stream);
+        return wide ? launch_tc<256, kEpiTopK>(ma, mb, ma, ep, g, stream) : launch_tc<128, kEpiTopK>(ma, mb, ma, ep, g, stream);
     }
     DC_REQUIRE((epi == kEpiArgmax || epi == kEpiArgmaxSum) && ep.partial && ep.bias,
                "gemm_bf16_tc: arg-max epilogue needs bias and partial buffer");
     if (epi == kEpiArgmax)
-        return wide ? launch_tc<256, kEpiArgmax>(ma, mb, ep, g, stream) : launch_tc<128, kEpiArgmax>(ma, mb, ep, g, stream);
-    return wide ? launch_tc<256, kEpiArgmaxSum>(ma, mb, ep, g, stream)
-                : launch_tc<128, kEpiArgmaxSum>(ma, mb, ep, g, stream);
+        return wide ? launch_tc<256, kEpiArgmax>(ma, mb, ma, ep, g, stream) : launch_tc<128, kEpiArgmax>(ma, mb, ma, ep, g, stream);
+    return wide ? launch_tc<256, kEpiArgmaxSum>(ma, mb, ma, ep, g, stream)
+                : launch_tc<128, kEpiArgmaxSum>(ma, mb, ma, ep, g, stream);
 }
 
 int gemm_tc_argmax_tiles(int N) { return 2 * ceil_div(N, N > 128 ? 256 : 128); }

@@ -10,6 +10,9 @@ constexpr int kEpiArgmaxSum = 2;    // ... + sum exp(v - max) (softmax probabili
 constexpr int kEpiCell = 3;         // fused Keras LSTM cell on gate-interleaved columns
 constexpr int kEpiTopK = 4;         // per row and column region: max, sum exp, the k best (value, index) pairs (beam search)
 constexpr int kTopKMax = 8;
+// internal variants of kEpiStore chosen by gemm_bf16_tc: the output leaves through shared memory + TMA bulk stores
+constexpr int kEpiStoreTmaF32 = 5;
+constexpr int kEpiStoreTmaB16 = 6;
 
 struct TcOperand {
     // K-major (default): [rows, K] row-major, K contiguous, ld = row stride.
