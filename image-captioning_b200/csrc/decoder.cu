@@ -134,6 +134,7 @@ __global__ void bn_fold_kernel(const float *gamma, const float *beta, const floa
 
 int Decoder::finalize(cudaStream_t s) {
     drop_graphs();
+    invalidate_train_copy();                  // weights were set from the host: the bf16 mirror is stale
     for (auto &w : weights)
         if (!w.is_set)
             return set_error(DC_ERR_STATE, "weight '%s' has not been set", w.name.c_str());

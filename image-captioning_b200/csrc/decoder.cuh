@@ -116,6 +116,7 @@ struct Decoder {
                   cudaStream_t s);
     int ensure_grads();
     int refresh_train_weights(cudaStream_t s);
+    void invalidate_train_copy();
     void free_train();
 };
 

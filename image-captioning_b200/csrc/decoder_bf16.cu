@@ -24,15 +24,26 @@ void Decoder::free_bf16() {
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// dst[n, k_off + k] = src[(row_off + k) * n_src + colmap(n)], colmap = gate interleave or identity
-__global__ void build_kmajor_kernel(const float *__restrict__ src, int n_src, int row_off, int K, int N,
-                                    int interleave_units, __nv_bfloat16 *__restrict__ dst, long long ld_dst,
-                                    int k_off) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)N * K) return;
-    const int n = (int)(idx / K), k = (int)(idx - (long long)n * K);
+// dst[n, k_off + k] = bf16(src[(row_off + k) * n_src + colmap(n)]), colmap = gate interleave (n = 4u+g ->
+// g*units + u) or identity: the Keras [in, out] kernel re-laid as the K-major [N, K] TMA operand.
+// 32 x 32 tiles through shared memory: reads run along n (whole sectors), writes along k.
+__global__ void __launch_bounds__(256) build_kmajor_kernel(const float *__restrict__ src, int n_src, int row_off, int K, int N,
+                                                           int interleave_units, __nv_bfloat16 *__restrict__ dst,
+                                                           long long ld_dst, int k_off) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    const int n = n0 + threadIdx.x;
     const int col = interleave_units ? (n & 3) * interleave_units + (n >> 2) : n;
-    dst[(long long)n * ld_dst + k_off + k] = __float2bfloat16_rn(src[(long long)(row_off + k) * n_src + col]);
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int k = k0 + i;
+        tile[i][threadIdx.x] = (k < K && n < N) ? src[(long long)(row_off + k) * n_src + col] : 0.f;
+    }
+    __syncthreads();
+    const int k = k0 + threadIdx.x;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int nn = n0 + i;
+        if (k < K && nn < N) dst[(long long)nn * ld_dst + k_off + k] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
 }
 
 // dst[r, c] = bf16(src[r, c]) for c < cols; dst rows are ld_dst wide (padding pre-zeroed)
@@ -51,9 +62,8 @@ __global__ void interleave_bias_kernel(const float *__restrict__ src, int units,
 
 static int build_kmajor(const float *src, int n_src, int row_off, int K, int N, int interleave_units,
                         __nv_bfloat16 *dst, long long ld_dst, int k_off, cudaStream_t s) {
-    const long long total = (long long)N * K;
-    build_kmajor_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, s>>>(src, n_src, row_off, K, N,
-                                                                                   interleave_units, dst, ld_dst, k_off);
+    const dim3 grid(ceil_div(K, 32), ceil_div(N, 32)), block(32, 8);
+    build_kmajor_kernel<<<grid, block, 0, s>>>(src, n_src, row_off, K, N, interleave_units, dst, ld_dst, k_off);
     DC_CHECK_LAUNCH();
     return DC_OK;
 }
@@ -101,7 +111,6 @@ int Decoder::refresh_bf16(bool fresh, cudaStream_t s) {
     interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm1/bias"), U, b.b1_i);
     interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm2/bias"), U, b.b2_i);
     DC_CHECK_LAUNCH();
-    if (b.train) return refresh_train_weights(s);
     return DC_OK;
 }
 

@@ -21,8 +21,11 @@ struct Bf16State {
     float *topk_partial = nullptr;                   // beam search: [rows, slots, 2 + 2k]
     size_t topk_cap = 0;
     int parity = 0;
-    // backward-pass operand copies: plain bf16 casts of the Keras [in, out] tensors, which are the
-    // K-major B operands of dX = dY * W^T (N = in, K = out); built by refresh_train_weights() (train.cu)
+    // backward-pass operand copies: a bf16 mirror of the whole trainable arena (same offsets; written by the
+    // optimiser kernel itself, or by one cast after set_weights); the Keras [in, out] tensors inside it are
+    // the K-major B operands of dX = dY * W^T (N = in, K = out).  Pointers set by refresh_train_weights().
+    __nv_bfloat16 *arena_k = nullptr;
+    bool arena_k_valid = false;
     __nv_bfloat16 *wd2_k = nullptr;      // [1024, V]   imgcap_lstm_d2/kernel
     __nv_bfloat16 *wd1h_k = nullptr;     // [U, 1024]   imgcap_lstm_d1/kernel[:U]
     __nv_bfloat16 *wd1f_k = nullptr;     // [F, 1024]   imgcap_lstm_d1/kernel[U:]

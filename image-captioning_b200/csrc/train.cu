@@ -74,29 +74,32 @@ int Decoder::ensure_grads() {
     return DC_OK;
 }
 
-// bf16 casts of the Keras-layout tensors used as K-major B operands by the data-gradient GEMMs
+// bf16 mirror of the trainable arena: the Keras-layout tensors inside it are the K-major B operands of the
+// data-gradient GEMMs.  After an optimiser step the mirror is already current (adam_amsgrad_kernel writes it).
 int Decoder::refresh_train_weights(cudaStream_t s) {
     Bf16State &b = *bf;
-    const size_t F = cfg.feat, E = cfg.embed, U = cfg.units, V = cfg.vocab;
-    if (!b.wd2_k) {
-        auto A16 = [&](__nv_bfloat16 **p, size_t n) { return dev_alloc((void **)p, 2 * n, owned); };
-        int rc = 0;
-        rc |= A16(&b.wd2_k, (size_t)kDense * V); rc |= A16(&b.wd1h_k, U * kDense); rc |= A16(&b.wd1f_k, F * kDense);
-        rc |= A16(&b.w2cat_k, 2 * U * 4 * U); rc |= A16(&b.u1_k, U * 4 * U); rc |= A16(&b.w1f_k, F * 4 * U);
-        rc |= A16(&b.wc2_k, F * F);
-        if (rc) return rc;
+    const size_t E = cfg.embed, U = cfg.units;
+    if (!b.arena_k)
+        if (int rc = dev_alloc((void **)&b.arena_k, 2 * (size_t)n_train, owned)) return rc;
+    if (!b.arena_k_valid) {
+        if (int rc = f32_to_bf16(arena, b.arena_k, n_train, s)) return rc;
+        b.arena_k_valid = true;
     }
-    int rc = 0;
-    rc |= f32_to_bf16(W("imgcap_lstm_d2/kernel"), b.wd2_k, (long long)kDense * V, s);
-    rc |= f32_to_bf16(W("imgcap_lstm_d1/kernel"), b.wd1h_k, (long long)U * kDense, s);
-    rc |= f32_to_bf16(W("imgcap_lstm_d1/kernel") + U * kDense, b.wd1f_k, (long long)F * kDense, s);
+    auto K = [&](const char *name) { return b.arena_k + find(name)->offset; };
     // lstm2 kernel and recurrent_kernel are adjacent in the arena: [W2 ; U2] is one range
     DC_REQUIRE(W("imgcap_lstm2/recurrent_kernel") == W("imgcap_lstm2/kernel") + U * 4 * U, "arena layout");
-    rc |= f32_to_bf16(W("imgcap_lstm2/kernel"), b.w2cat_k, (long long)2 * U * 4 * U, s);
-    rc |= f32_to_bf16(W("imgcap_lstm1/recurrent_kernel"), b.u1_k, (long long)U * 4 * U, s);
-    rc |= f32_to_bf16(W("imgcap_lstm1/kernel") + E * 4 * U, b.w1f_k, (long long)F * 4 * U, s);
-    rc |= f32_to_bf16(W("mrcnn_class_conv2/kernel"), b.wc2_k, (long long)F * F, s);
-    return rc;
+    b.wd2_k = K("imgcap_lstm_d2/kernel");
+    b.wd1h_k = K("imgcap_lstm_d1/kernel");
+    b.wd1f_k = K("imgcap_lstm_d1/kernel") + U * kDense;
+    b.w2cat_k = K("imgcap_lstm2/kernel");
+    b.u1_k = K("imgcap_lstm1/recurrent_kernel");
+    b.w1f_k = K("imgcap_lstm1/kernel") + E * 4 * U;
+    b.wc2_k = K("mrcnn_class_conv2/kernel");
+    return DC_OK;
+}
+
+void Decoder::invalidate_train_copy() {
+    if (bf) bf->arena_k_valid = false;
 }
 
 static int train_reserve(Decoder &D, int B, int T) {
@@ -230,6 +233,92 @@ __global__ void __launch_bounds__(256) softmax_xent_kernel(const float *__restri
                 g[j + i] = __float2bfloat16_rn(p * sc);
             }
         }
+    }
+}
+
+// Same arithmetic, kRows consecutive rows per CTA with every row held in registers (one global read per
+// logit) and the COLUMN SUMS of dz -- the gradient of the vocabulary bias -- accumulated in registers
+// across the CTA's rows and flushed with one vector reduce-add per thread and column group: the separate
+// pass over the 1.3 GB of dz that a column-sum kernel needs does not exist.  V <= kChunks * 1024, V % 4 == 0.
+template <int kChunks>
+__global__ void __launch_bounds__(256) softmax_xent_colsum_kernel(const float *__restrict__ logits, long long ld, int V,
+                                                                  const int32_t *__restrict__ tgt, float inv_count,
+                                                                  __nv_bfloat16 *__restrict__ dz, long long ld_dz,
+                                                                  float *__restrict__ rowloss, long long rows,
+                                                                  int rows_per_cta, float *__restrict__ dbias) {
+    __shared__ float red[2][2][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[kChunks][4];
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+    for (long long r = r0; r < r1; ++r) {
+        const float *z = logits + r * ld;
+        float4 q[kChunks];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k) {
+            const int j = k * 1024 + threadIdx.x * 4;
+            q[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (j < V) q[k] = __ldcs(reinterpret_cast<const float4 *>(z + j));
+            mx = fmaxf(mx, fmaxf(fmaxf(q[k].x, q[k].y), fmaxf(q[k].z, q[k].w)));
+        }
+        float sum = 0.f;
+        if (mx > -INFINITY) {                                          // a thread with no column of this row holds -inf
+#pragma unroll
+            for (int k = 0; k < kChunks; ++k)
+                sum += __expf(q[k].x - mx) + __expf(q[k].y - mx) + __expf(q[k].z - mx) + __expf(q[k].w - mx);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
+            const float nm = fmaxf(mx, om);
+            sum = (mx > -INFINITY ? sum * __expf(mx - nm) : 0.f) + (om > -INFINITY ? os * __expf(om - nm) : 0.f);
+            mx = nm;
+        }
+        const int pb = (int)(r & 1);                                   // double-buffered: one barrier per row
+        if (lane == 0) { red[pb][0][warp] = mx; red[pb][1][warp] = sum; }
+        __syncthreads();
+        float gm = red[pb][0][0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) gm = fmaxf(gm, red[pb][0][i]);
+        float gs = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (red[pb][0][i] > -INFINITY) gs += red[pb][1][i] * __expf(red[pb][0][i] - gm);
+        const float inv = 1.0f / gs;
+        const int y = tgt[r];
+        bool live = y >= 0;
+        if (live) {
+            const float py = __expf(z[y] - gm) * inv;
+            if (threadIdx.x == 0) rowloss[r] = -logf(fminf(fmaxf(py, 1e-7f), 1.0f - 1e-7f));
+            live = py > 1e-7f && py < 1.0f - 1e-7f;
+        } else if (threadIdx.x == 0) {
+            rowloss[r] = 0.f;
+        }
+        const float sc = live ? inv_count : 0.f;
+        __nv_bfloat16 *g = dz + r * ld_dz;
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k) {
+            const int j = k * 1024 + threadIdx.x * 4;
+            if (j < V) {
+                float p[4] = {__expf(q[k].x - gm) * inv, __expf(q[k].y - gm) * inv, __expf(q[k].z - gm) * inv,
+                              __expf(q[k].w - gm) * inv};
+                if (y >= j && y < j + 4) p[y - j] -= 1.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { p[i] *= sc; acc[k][i] += p[i]; }
+                __nv_bfloat162 lo = __floats2bfloat162_rn(p[0], p[1]), hi = __floats2bfloat162_rn(p[2], p[3]);
+                *reinterpret_cast<uint2 *>(g + j) = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+        const int j = k * 1024 + threadIdx.x * 4;
+        if (j < V)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbias + j), "f"(acc[k][0]), "f"(acc[k][1]),
+                         "f"(acc[k][2]), "f"(acc[k][3]) : "memory");
     }
 }
 
@@ -401,7 +490,7 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_kernel(const float *__restric
 // (1/world after a sum all-reduce).
 __global__ void adam_amsgrad_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                                     float *__restrict__ v, float *__restrict__ vhat, long long n, float lr_t, float b1,
-                                    float b2, float eps, int amsgrad, float grad_scale) {
+                                    float b2, float eps, int amsgrad, float grad_scale, __nv_bfloat16 *__restrict__ p_b16) {
     const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;                                   // n is a multiple of 64
     const float4 g4 = *reinterpret_cast<const float4 *>(g + i);
@@ -423,6 +512,10 @@ __global__ void adam_amsgrad_kernel(float *__restrict__ p, const float *__restri
     *reinterpret_cast<float4 *>(v + i) = make_float4(vs[0], vs[1], vs[2], vs[3]);
     if (amsgrad) *reinterpret_cast<float4 *>(vhat + i) = make_float4(hs[0], hs[1], hs[2], hs[3]);
     *reinterpret_cast<float4 *>(p + i) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+    if (p_b16) {                                          // bf16 mirror used by the next step's data-gradient GEMMs
+        __nv_bfloat162 lo = __floats2bfloat162_rn(ps[0], ps[1]), hi = __floats2bfloat162_rn(ps[2], ps[3]);
+        *reinterpret_cast<uint2 *>(p_b16 + i) = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -504,8 +597,7 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     if (int rc = train_forward(feats, kind, B, gt, targets, s)) return rc;
     if (int rc = ensure_grads()) return rc;
     Bf16State &b = *bf;
-    if (!b.wd2_k)
-        if (int rc = refresh_train_weights(s)) return rc;
+    if (int rc = refresh_train_weights(s)) return rc;
     const int T = cfg.padding, U = cfg.units, F = cfg.feat, E = cfg.embed, V = cfg.vocab;
     const int K1 = b.Epad + U, Kin = cfg.pool * cfg.pool * cfg.channels;
     TrainState &t = *b.train;
@@ -517,7 +609,17 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     auto G = [&](const char *name) { return grads + find(name)->offset; };
     DC_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n_train, s));
 
-    softmax_xent_kernel<<<(unsigned)R, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
+    // softmax + cross-entropy + dlogits (+ the vocabulary-bias gradient when the row fits in registers)
+    bool bias_done = false;
+    {
+        const int rpc = 32;
+        const unsigned grid = (unsigned)ceil_div<long long>(R, rpc);
+        float *db = G("imgcap_lstm_d2/bias");
+        if (V <= 2048) { softmax_xent_colsum_kernel<2><<<grid, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss, R, rpc, db); bias_done = true; }
+        else if (V <= 10240) { softmax_xent_colsum_kernel<10><<<grid, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss, R, rpc, db); bias_done = true; }
+        else if (V <= 16384) { softmax_xent_colsum_kernel<16><<<grid, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss, R, rpc, db); bias_done = true; }
+        else softmax_xent_kernel<<<(unsigned)R, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
+    }
     DC_CHECK_LAUNCH();
     reduce_loss_kernel<<<1, 1024, 0, s>>>(t.rowloss, R, inv_count, loss);
     DC_CHECK_LAUNCH();
@@ -531,7 +633,8 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     };
     // dense2: dWd2 = d^T dz, dbd2 = colsum(dz), dd = (dz Wd2^T) * [d > 0]
     if (int rc = wgrad(t.d_all, kDense, kDense, t.dz, V, V, R, G("imgcap_lstm_d2/kernel"), V)) return rc;
-    if (int rc = colsum(t.dz, R, V, V, G("imgcap_lstm_d2/bias"), s)) return rc;
+    if (!bias_done)
+        if (int rc = colsum(t.dz, R, V, V, G("imgcap_lstm_d2/bias"), s)) return rc;
     {
         TcEpilogue e;
         e.mask_src = t.d_all; e.ld_mask = kDense; e.out_bf16 = t.dd; e.ld_bf16 = kDense;
@@ -664,8 +767,9 @@ int Decoder::adam_step(float lr, float beta1, float beta2, float eps, int amsgra
     const long long n = n_train;
     adam_amsgrad_kernel<<<(unsigned)ceil_div<long long>(n / 4, 256), 256, 0, s>>>(arena, grads, adam_m, adam_v, adam_vhat, n,
                                                                                  (float)lr_t, beta1, beta2, eps, amsgrad,
-                                                                                 grad_scale);
+                                                                                 grad_scale, bf ? bf->arena_k : nullptr);
     DC_CHECK_LAUNCH();
+    if (bf && bf->arena_k) bf->arena_k_valid = true;
     // folded BN + bf16 operand copies (forward and backward layouts) are rebuilt IN PLACE, so captured
     // inference graphs stay valid
     return refresh_derived(s);
