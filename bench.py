@@ -609,7 +609,7 @@ def run_ours_train(args):
     model = pkg.build_lstm_model([POOL[0], POOL[1], CHANNELS], cfg, UNITS, "training", dtype="bfloat16", device=dev)
     model.set_weights(w)
     model.compile(optimizer=pkg.Adam(amsgrad=True), loss=pkg.roi_caption_loss)
-    trainer = parallel.DataParallelTrainer(model)
+    trainer = parallel.DataParallelTrainer(model, overlap=os.environ.get("DCAP_NO_OVERLAP") is None)
     rng = np.random.default_rng(1003)
     gt_np = synth.synth_captions(rng, TRAIN_BATCH, TRAIN_P, VOCAB)[lo:hi]
     gen = torch.Generator(device=dev).manual_seed(1003 + rank)

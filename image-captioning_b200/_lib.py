@@ -89,6 +89,9 @@ SIGNATURES = {
                                     ctypes.c_int, ctypes.c_int64, ctypes.c_float, c_void]),
     "dc_decoder_grad_buffer": (ctypes.c_int, [c_void, ctypes.POINTER(c_void), ctypes.POINTER(ctypes.c_int64)]),
     "dc_decoder_param_buffer": (ctypes.c_int, [c_void, ctypes.POINTER(c_void), ctypes.POINTER(ctypes.c_int64)]),
+    "dc_decoder_grad_bucket": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                              ctypes.POINTER(ctypes.c_int64)]),
+    "dc_decoder_wait_grad_bucket": (ctypes.c_int, [c_void, ctypes.c_int, c_void]),
     "dc_decoder_weight_offset": (ctypes.c_int64, [c_void, ctypes.c_int]),
     "dc_decoder_get_grad": (ctypes.c_int, [c_void, ctypes.c_char_p, c_void, ctypes.c_int64]),
 }

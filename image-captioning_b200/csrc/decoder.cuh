@@ -117,6 +117,8 @@ struct Decoder {
     int ensure_grads();
     int refresh_train_weights(cudaStream_t s);
     void invalidate_train_copy();
+    int grad_bucket(int i, int64_t *offset, int64_t *numel);
+    int wait_grad_bucket(int i, cudaStream_t waiter);
     void free_train();
 };
 

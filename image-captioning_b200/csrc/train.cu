@@ -52,6 +52,7 @@ struct TrainState {
     __nv_bfloat16 *x0 = nullptr;                                   // [B, Kin] bf16 copy of fp32 RoI features
     float *rowloss = nullptr;                                      // [T*B]
     const __nv_bfloat16 *x0_used = nullptr;                        // bf16 RoI features the last forward consumed
+    cudaEvent_t bucket_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // gradient bucket i is complete on the step's stream
 };
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -59,6 +60,8 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 void Decoder::free_train() {
     if (bf && bf->train) {
         for (void *p : bf->train->owned) cudaFree(p);
+        for (cudaEvent_t e : bf->train->bucket_ev)
+            if (e) cudaEventDestroy(e);
         delete bf->train;
         bf->train = nullptr;
     }
@@ -136,6 +139,11 @@ static int train_reserve(Decoder &D, int B, int T) {
     rc |= A((void **)&t.x0, 2 * Bp * Kin);
     rc |= A((void **)&t.rowloss, 4 * R);
     if (rc) { D.free_train(); return rc; }
+    for (int i = 0; i < 4; ++i)
+        if (cudaEventCreateWithFlags(&t.bucket_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            D.free_train();
+            return set_error(DC_ERR_CUDA, "event creation failed");
+        }
     t.B = B; t.T = T;
     return DC_OK;
 }
@@ -635,6 +643,7 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     if (int rc = wgrad(t.d_all, kDense, kDense, t.dz, V, V, R, G("imgcap_lstm_d2/kernel"), V)) return rc;
     if (!bias_done)
         if (int rc = colsum(t.dz, R, V, V, G("imgcap_lstm_d2/bias"), s)) return rc;
+    DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[0], s));                 // bucket 0: vocabulary projection
     {
         TcEpilogue e;
         e.mask_src = t.d_all; e.ld_mask = kDense; e.out_bf16 = t.dd; e.ld_bf16 = kDense;
@@ -647,6 +656,7 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     if (int rc = wgrad(h2_all, 2 * U, U, t.dd, kDense, kDense, R, G("imgcap_lstm_d1/kernel"), kDense)) return rc;
     if (int rc = wgrad(b.Fb, F, F, t.ddsum_b, kDense, kDense, B, G("imgcap_lstm_d1/kernel") + (size_t)U * kDense, kDense)) return rc;
     if (int rc = colsum(t.ddsum, B, kDense, kDense, G("imgcap_lstm_d1/bias"), s)) return rc;
+    DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[1], s));                 // bucket 1: dense1
     {
         TcEpilogue e;
         e.out_f32 = t.dh2d; e.ld_f32 = U;
@@ -694,8 +704,12 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     if (int rc = wgrad(t.X1 + b.Epad, K1, U, t.dz1_all, 4 * U, 4 * U, R, G("imgcap_lstm1/recurrent_kernel"), 4 * U)) return rc;
     if (int rc = wgrad(b.Fb, F, F, t.dz1sum_b, 4 * U, 4 * U, B, G("imgcap_lstm1/kernel") + (size_t)E * 4 * U, 4 * U)) return rc;
     if (int rc = colsum(t.dz1sum, B, 4 * U, 4 * U, G("imgcap_lstm1/bias"), s)) return rc;
+    DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[2], s));                 // bucket 2: both LSTMs
 
-    if (!train_head) return DC_OK;
+    if (!train_head) {
+        DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[3], s));             // head gradients stay zero
+        return DC_OK;
+    }
     // ---------------- backward: RoI head ----------------
     {   // dF = (sum_t dd) Wd1[U:]^T + (sum_t dz1) W1[E:]^T
         TcEpilogue e;
@@ -720,7 +734,30 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
                                                     W("mrcnn_class_bn1/beta"), 256, t.dzh1, G("mrcnn_class_bn1/gamma"),
                                                     G("mrcnn_class_bn1/beta"), G("mrcnn_class_conv1/bias"));
     DC_CHECK_LAUNCH();
-    return wgrad(x0, Kin, Kin, t.dzh1, F, F, B, G("mrcnn_class_conv1/kernel"), F);
+    if (int rc = wgrad(x0, Kin, Kin, t.dzh1, F, F, B, G("mrcnn_class_conv1/kernel"), F)) return rc;
+    DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[3], s));                 // bucket 3: RoI head
+    return DC_OK;
+}
+
+// Gradient buckets in the order the backward pass completes them (reverse layer order); each is ONE
+// contiguous range of the flat gradient buffer because the arena keeps declaration order.
+int Decoder::grad_bucket(int i, int64_t *offset, int64_t *numel) {
+    DC_REQUIRE(i >= 0 && i < 4 && offset && numel, "gradient bucket index outside [0,4)");
+    DC_REQUIRE(cfg.arch == DC_ARCH_V1, "gradient buckets are defined for the v1 model");
+    auto off = [&](const char *n) { return find(n)->offset; };
+    const int64_t head0 = off("mrcnn_class_conv1/kernel"), lstm0 = off("imgcap_lstm1/kernel"),
+                  d1 = off("imgcap_lstm_d1/kernel"), d2 = off("imgcap_lstm_d2/kernel");
+    DC_REQUIRE(head0 == 0 && head0 < lstm0 && lstm0 < d1 && d1 < d2 && d2 < n_train, "unexpected arena order");
+    const int64_t lo[4] = {d2, d1, lstm0, head0}, hi[4] = {n_train, d2, d1, lstm0};
+    *offset = lo[i]; *numel = hi[i] - lo[i];
+    return DC_OK;
+}
+
+int Decoder::wait_grad_bucket(int i, cudaStream_t waiter) {
+    DC_REQUIRE(i >= 0 && i < 4, "gradient bucket index outside [0,4)");
+    DC_REQUIRE(bf && bf->train && bf->train->bucket_ev[i], "no training step has run on this handle");
+    DC_CHECK_CUDA(cudaStreamWaitEvent(waiter, bf->train->bucket_ev[i], 0));
+    return DC_OK;
 }
 
 // probs[b, t, :] = softmax(logits[t*B + b, :]): the Keras output layout [B, P, V] of the training graph
@@ -807,6 +844,16 @@ extern "C" int dc_decoder_grad_buffer(DcDecoder *dec, float **ptr, int64_t *nume
     *ptr = dec->impl.grads;
     *numel = dec->impl.n_train;
     return DC_OK;
+}
+
+extern "C" int dc_decoder_grad_bucket(DcDecoder *dec, int index, int64_t *offset, int64_t *numel) {
+    DC_REQUIRE(dec, "null decoder");
+    return dec->impl.grad_bucket(index, offset, numel);
+}
+
+extern "C" int dc_decoder_wait_grad_bucket(DcDecoder *dec, int index, void *waiting_stream) {
+    DC_REQUIRE(dec, "null decoder");
+    return dec->impl.wait_grad_bucket(index, (cudaStream_t)waiting_stream);
 }
 
 extern "C" int dc_decoder_param_buffer(DcDecoder *dec, float **ptr, int64_t *numel) {

@@ -63,8 +63,9 @@ class DataParallelTrainer(object):
     ``apply_gradients(grad_scale)``.  Semantics equal ONE process training on the concatenated
     global batch: loss = mean over all positions of all ranks."""
 
-    def __init__(self, model, group=None, bucket_mb=0):
+    def __init__(self, model, group=None, bucket_mb=0, overlap=True):
         self.model, self.group = model, group
+        self.overlap, self._comm, self._buckets = overlap, None, None
         self.rank, self.world = _world(group)
         self.bucket_elems = int(bucket_mb * (1 << 20) // 4)
 
@@ -98,7 +99,20 @@ class DataParallelTrainer(object):
         loss = self.model.train_step_device(features, gt, targets, 1.0 / global_positions)
         if self.world > 1:
             g = self.model.grad_buffer()
-            if self.bucket_elems > 0:
+            if self.overlap and hasattr(self.model, "wait_grad_bucket"):
+                # The step above is only ENQUEUED on the compute stream.  Each gradient bucket is
+                # all-reduced on the communication stream as soon as the backward pass has produced
+                # it (vocabulary projection first), i.e. under the remaining BPTT / head kernels.
+                cur = torch.cuda.current_stream(g.device)
+                if self._comm is None:
+                    self._comm = torch.cuda.Stream(device=g.device)
+                    self._buckets = self.model.grad_buckets()
+                for i, (off, n) in enumerate(self._buckets):
+                    self.model.wait_grad_bucket(i, self._comm)
+                    with torch.cuda.stream(self._comm):
+                        dist.all_reduce(g[off:off + n], group=self.group)
+                cur.wait_stream(self._comm)
+            elif self.bucket_elems > 0:
                 # reverse-layer order (vocabulary projection first) so the last-produced head
                 # gradients are the last bucket on the wire
                 hs = [dist.all_reduce(g[max(0, e - self.bucket_elems):e], group=self.group, async_op=True)

@@ -426,6 +426,20 @@ class RoiCaptionModel(_ModelBase):
             _lib.check(self._lib.dc_decoder_grad_buffer(self._h, ctypes.byref(p), ctypes.byref(n)))
             return torch.as_tensor(_DeviceArray(p.value, n.value, self), device=self.device)
 
+    def grad_buckets(self):
+        """[(offset, numel)] of the gradient buckets in the order the backward pass completes them."""
+        out = []
+        for i in range(4):
+            o, n = ctypes.c_int64(), ctypes.c_int64()
+            _lib.check(self._lib.dc_decoder_grad_bucket(self._h, i, ctypes.byref(o), ctypes.byref(n)))
+            out.append((o.value, n.value))
+        return out
+
+    def wait_grad_bucket(self, index, stream):
+        """Make torch stream `stream` wait until bucket `index` of the last training step is complete."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_wait_grad_bucket(self._h, int(index), ctypes.c_void_p(stream.cuda_stream)))
+
     def param_buffer(self):
         p, n = ctypes.c_void_p(), ctypes.c_int64()
         with torch.cuda.device(self.device):

@@ -220,6 +220,14 @@ int dc_adam_step(DcDecoder *dec, float lr, float beta1, float beta2, float epsil
  * (in floats; -1 for frozen tensors). */
 int dc_decoder_grad_buffer(DcDecoder *dec, float **ptr, int64_t *numel);
 int dc_decoder_param_buffer(DcDecoder *dec, float **ptr, int64_t *numel);
+/* The backward pass finishes the gradients in reverse layer order; bucket `index` in [0,4) = {vocabulary
+ * projection, dense1, both LSTMs, RoI head} is one contiguous [offset, offset+numel) range of the
+ * gradient buffer.  dc_decoder_wait_grad_bucket makes `waiting_stream` wait (cudaStreamWaitEvent) until
+ * the LAST dc_decoder_train_step has produced that bucket, so a communication stream can all-reduce
+ * bucket i while the step's stream is still computing bucket i+1. */
+#define DC_GRAD_BUCKETS 4
+int dc_decoder_grad_bucket(DcDecoder *dec, int index, int64_t *offset, int64_t *numel);
+int dc_decoder_wait_grad_bucket(DcDecoder *dec, int index, void *waiting_stream);
 int64_t dc_decoder_weight_offset(const DcDecoder *dec, int index);
 int dc_decoder_get_grad(DcDecoder *dec, const char *name, float *host, int64_t numel);
 

@@ -178,3 +178,27 @@ def test_shard_gradients_sum_to_the_full_batch_gradient():
     assert abs(loss - full_loss) <= 1e-5 * abs(full_loss)
     err = float((parts - full).norm() / full.norm())
     assert err <= 2e-3, err                              # bf16 rounding of time-summed operands differs per shard
+
+
+def test_gradient_buckets_partition_the_buffer_and_signal_completion():
+    """The all-reduce overlap contract: 4 contiguous buckets in backward-completion order covering the
+    whole gradient buffer; a side stream that waits on bucket i sees that bucket's final values."""
+    pkg, rng, w, feat, gt, m = _setup(38, 48)
+    m.train_step_device(feat, gt)
+    buckets = m.grad_buckets()
+    n = m.grad_buffer().numel()
+    spans = sorted(buckets)
+    assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+    assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(3))
+    assert buckets[0][0] > buckets[1][0] > buckets[2][0] > buckets[3][0] == 0      # reverse layer order
+    side = torch.cuda.Stream()
+    early = []
+    m.train_step_device(feat, gt)                                                   # enqueued, not synchronised
+    for i, (off, cnt) in enumerate(buckets):
+        m.wait_grad_bucket(i, side)
+        with torch.cuda.stream(side):
+            early.append(m.grad_buffer()[off:off + cnt].clone())
+    torch.cuda.synchronize()
+    final = m.grad_buffer()
+    for (off, cnt), e in zip(buckets, early):
+        assert torch.equal(e, final[off:off + cnt])
