@@ -175,20 +175,25 @@ struct TcGeom {
     int M, N, K;
     int a_mn, b_mn;          // operand majorness
     int splits, kb_per;      // split-K: k-blocks [s*kb_per, min((s+1)*kb_per, num_kb)) per work unit
+    int split_major;         // work-unit order: 1 = unit -> (split, tile) with CTAs that run together sharing a K range
     int tma_out;             // store epilogue output path: 0 = per-thread stores, 1 = fp32 via TMA, 2 = bf16 via TMA
 };
 
 constexpr int kOutStage = 4096;             // per epilogue warp: 32 rows x 128 B, SWIZZLE_128B
 
-template <int kBlockN>
+constexpr int kCellAddBytes = 128 * 128 * 4;      // fp32 addend of a 128 x 128 tile: 4 boxes of [128 rows x 32 cols]
+constexpr int kCellCBytes = 128 * 32 * 4;         // fp32 cell state of the tile's 32 units
+
+template <int kBlockN, int kEpi = kEpiStore>
 struct TcSmem {
+    static constexpr bool kCellTma = kEpi == kEpiCellTma;
     static constexpr int kStageA = kBlockM * kBlockK * 2;
     static constexpr int kStageB = kBlockN * kBlockK * 2;
-    static constexpr int kStages = (kBlockN == 256) ? 4 : 6;
+    static constexpr int kStages = (kBlockN == 256 || kCellTma) ? 4 : 6;
     static constexpr int kBarOff = kStages * (kStageA + kStageB);
     static constexpr int kOutOff = kBarOff + 1024;                       // barriers live in their own 1 KB
-    static constexpr int kBaseBytes = kOutOff + 1024 /*align*/;            // without output staging (keeps more L1)
-    static constexpr int kBytes = kBaseBytes + kEpiWarps * kOutStage;
+    static constexpr int kBaseBytes = kOutOff + 1024 /*align*/ + (kCellTma ? kCellAddBytes + kCellCBytes : 0);
+    static constexpr int kBytes = kBaseBytes + (kCellTma ? 0 : kEpiWarps * kOutStage);   // + output staging (TMA stores)
 };
 
 // MUFU.TANH: max relative error 2^-11, well inside the bf16 operand rounding (2^-9) of this path
@@ -544,7 +549,10 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
                 }
                 const float ig = hard_sigmoid_tc(z.x), fg = hard_sigmoid_tc(z.y);
                 const float gg = tanh_fast(z.z), og = hard_sigmoid_tc(z.w);
-                v[4 * j] = ig; v[4 * j + 1] = fg; v[4 * j + 2] = gg; v[4 * j + 3] = og;
+                // saved (bf16) copies: an unsaturated hard-sigmoid (< 1) must not round up to 1, the backward
+                // pass reads "strictly inside (0,1)" as "derivative 0.2"
+                v[4 * j] = ig < 1.f ? fminf(ig, 0.99609375f) : 1.f; v[4 * j + 1] = fg < 1.f ? fminf(fg, 0.99609375f) : 1.f;
+                v[4 * j + 2] = gg; v[4 * j + 3] = og < 1.f ? fminf(og, 0.99609375f) : 1.f;
                 c_new[j] = __fadd_rn(__fmul_rn(fg, c_old[j]), __fmul_rn(ig, gg));
                 h_new[j] = __fmul_rn(og, tanh_fast(c_new[j]));
                 if (masked) {                                        // K.rnn mask: carry (h, c)
@@ -564,10 +572,108 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
                 const uint4 hv = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 if (ep.cell_h_a) *reinterpret_cast<uint4 *>(ep.cell_h_a + (long long)m * ep.ld_h_a + u0) = hv;
                 if (ep.cell_h_b) *reinterpret_cast<uint4 *>(ep.cell_h_b + (long long)m * ep.ld_h_b + u0) = hv;
-                if (ep.cell_gates_out) {                             // saved for the backward pass
-                    float4 *g = reinterpret_cast<float4 *>(ep.cell_gates_out + (long long)m * ep.ld_gates_out + nb);
+                if (ep.cell_gates_out) {                             // saved for the backward pass (bf16: 64 B per row and chunk)
+                    uint4 *g = reinterpret_cast<uint4 *>(ep.cell_gates_out + (long long)m * ep.ld_gates_out + nb);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) g[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
+                            w[q] = *reinterpret_cast<uint32_t *>(&t);
+                        }
+                        g[j] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Fused Keras LSTM cell epilogue, shared-memory operand variant (kEpiCellTma, 128-wide tiles): the tile's fp32
+// addend [128 x 128] and cell state [128 x 32 units] were staged by the TMA producer (128-byte swizzle) while the
+// tile's MMAs ran, so the only global LOADS left on the epilogue's critical path are the rare masked rows'
+// previous h.  Lane i owns row i of the warp's 32 rows; 16-byte piece j of a 128-byte staged row sits at
+// piece (j ^ (row & 7)) -- conflict-free for 8 consecutive lanes.
+template <int kCols>
+__device__ __forceinline__ void epilogue_cell_tma(const TcEpilogue &ep, uint32_t taddr, int lane, int m_base, int n_base,
+                                                  int col_in_tile, int row_in_tile, int M, int N, uint64_t *full_bar,
+                                                  uint32_t full_phase, uint64_t *add_full, uint32_t add_phase,
+                                                  const uint8_t *smem_add, const uint8_t *smem_c) {
+    const int m = m_base + lane;
+    const bool valid = m < M;
+    const long long mr = valid ? m : (long long)(M - 1);
+    float *c_dst = (ep.cell_c_out ? ep.cell_c_out : ep.cell_c) + mr * ep.cell_units;
+    const bool masked = ep.cell_tok && __ldg(ep.cell_tok + mr) == 0;
+    const bool has_add = ep.addend != nullptr;
+    const uint32_t sw = (uint32_t)row_in_tile & 7u;
+    const uint8_t *crow = smem_c + row_in_tile * 128;
+    mbar_wait(add_full, add_phase);                                  // staged operands have landed
+    mbar_wait(full_bar, full_phase);                                 // accumulator complete
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < kCols; c0 += 32) {
+        const int nb = n_base + c0;
+        if (nb >= N) break;                                          // warp-uniform; N % 32 == 0 here
+        const int ct = col_in_tile + c0;                             // column inside the 128-wide tile
+        const uint8_t *arow = smem_add + (ct >> 5) * (kCellAddBytes / 4) + row_in_tile * 128;
+        float4 a_cur[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            a_cur[j] = has_add ? *reinterpret_cast<const float4 *>(arow + (((uint32_t)j ^ sw) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t cp = (uint32_t)ct >> 4;                       // first 16-byte piece of the chunk's 8 units
+        const float4 c_lo = *reinterpret_cast<const float4 *>(crow + ((cp ^ sw) << 4));
+        const float4 c_hi = *reinterpret_cast<const float4 *>(crow + (((cp + 1) ^ sw) << 4));
+        const float c_old[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
+        uint4 hq = make_uint4(0, 0, 0, 0);
+        if (masked) hq = *reinterpret_cast<const uint4 *>(ep.cell_h_prev + mr * ep.ld_h_prev + (nb >> 2));
+        const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        const int u0 = nb >> 2;
+        float c_new[8], h_new[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 z = make_float4(v[4 * j] + a_cur[j].x, v[4 * j + 1] + a_cur[j].y, v[4 * j + 2] + a_cur[j].z,
+                                   v[4 * j + 3] + a_cur[j].w);
+            if (ep.bias) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(ep.bias + nb + 4 * j));
+                z.x += t.x; z.y += t.y; z.z += t.z; z.w += t.w;
+            }
+            const float ig = hard_sigmoid_tc(z.x), fg = hard_sigmoid_tc(z.y);
+            const float gg = tanh_fast(z.z), og = hard_sigmoid_tc(z.w);
+            v[4 * j] = ig < 1.f ? fminf(ig, 0.99609375f) : 1.f; v[4 * j + 1] = fg < 1.f ? fminf(fg, 0.99609375f) : 1.f;
+            v[4 * j + 2] = gg; v[4 * j + 3] = og < 1.f ? fminf(og, 0.99609375f) : 1.f;
+            c_new[j] = __fadd_rn(__fmul_rn(fg, c_old[j]), __fmul_rn(ig, gg));
+            h_new[j] = __fmul_rn(og, tanh_fast(c_new[j]));
+            if (masked) {                                            // K.rnn mask: carry (h, c)
+                c_new[j] = c_old[j];
+                h_new[j] = __uint_as_float((j & 1) ? (hw[j >> 1] & 0xffff0000u) : (hw[j >> 1] << 16));
+            }
+        }
+        if (valid) {
+            reinterpret_cast<float4 *>(c_dst + u0)[0] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
+            reinterpret_cast<float4 *>(c_dst + u0)[1] = make_float4(c_new[4], c_new[5], c_new[6], c_new[7]);
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(h_new[2 * j], h_new[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t *>(&t);
+            }
+            const uint4 hv = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (ep.cell_h_a) *reinterpret_cast<uint4 *>(ep.cell_h_a + (long long)m * ep.ld_h_a + u0) = hv;
+            if (ep.cell_h_b) *reinterpret_cast<uint4 *>(ep.cell_h_b + (long long)m * ep.ld_h_b + u0) = hv;
+            if (ep.cell_gates_out) {
+                uint4 *g = reinterpret_cast<uint4 *>(ep.cell_gates_out + (long long)m * ep.ld_gates_out + nb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        __nv_bfloat162 t = __floats2bfloat162_rn(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]);
+                        w[q] = *reinterpret_cast<uint32_t *>(&t);
+                    }
+                    g[j] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
         }
@@ -577,9 +683,11 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
 template <int kBlockN, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_o, const TcEpilogue ep, const TcGeom g) {
-    using S = TcSmem<kBlockN>;
+                    const __grid_constant__ CUtensorMap map_o, const __grid_constant__ CUtensorMap map_c,
+                    const TcEpilogue ep, const TcGeom g) {
+    using S = TcSmem<kBlockN, kEpi>;
     constexpr int kStages = S::kStages;
+    constexpr bool kCellTma = S::kCellTma;
     constexpr uint32_t kTmemCols = 2 * kBlockN;                  // two accumulator buffers (power of 2)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -589,13 +697,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t *empty_bar = full_bar + kStages;
     uint64_t *tmem_full = empty_bar + kStages;
     uint64_t *tmem_empty = tmem_full + 2;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    uint64_t *add_full = tmem_empty + 2;                           // cell-TMA variant: addend + c tile landed / consumed
+    uint64_t *add_empty = add_full + 1;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(add_empty + 1);
+    uint8_t *smem_add = smem + S::kOutOff;                         // cell-TMA variant only (no output staging there)
+    uint8_t *smem_c = smem_add + kCellAddBytes;
 
     const int M = g.M, N = g.N, K = g.K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (N + kBlockN - 1) / kBlockN;
     const int tiles_m = (M + kBlockM - 1) / kBlockM;
-    const int num_units = tiles_m * tiles_n * g.splits;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_units = num_tiles * g.splits;          // unit = split * num_tiles + tile: CTAs running together share a K range (L2 reuse of the operand slabs)
     const int num_kb = (K + kBlockK - 1) / kBlockK;
 
     if (warp == 0 && lane == 0) {
@@ -604,6 +717,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (g.tma_out) tma_prefetch_desc(&map_o);
         for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kEpiWarps); }
+        mbar_init(add_full, 1); mbar_init(add_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -618,8 +732,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            [[maybe_unused]] uint32_t add_phase = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                const int tile = unit / g.splits, split = unit - tile * g.splits;
+                const int split = g.split_major ? unit / num_tiles : unit % g.splits;
+                const int tile = g.split_major ? unit - split * num_tiles : unit / g.splits;
                 const int m0 = (tile / tiles_n) * kBlockM, n0 = (tile % tiles_n) * kBlockN;
                 const int kb0 = split * g.kb_per, kb1 = min(kb0 + g.kb_per, num_kb);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -642,6 +758,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                if constexpr (kCellTma) {
+                    // the tile's fp32 addend (4 boxes of 32 columns) and cell state (its 32 units), issued after the
+                    // operand loads so that waiting for the previous tile's epilogue does not starve the MMA
+                    mbar_wait(add_empty, add_phase ^ 1);
+                    mbar_expect_tx(add_full, (ep.addend ? kCellAddBytes : 0) + kCellCBytes);
+                    if (ep.addend) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            tma_load_2d(&map_o, add_full, smem_add + b * (kCellAddBytes / 4), n0 + 32 * b, m0);
+                    }
+                    tma_load_2d(&map_c, add_full, smem_c, n0 >> 2, m0);
+                    add_phase ^= 1;
+                }
             }
         }
         __syncwarp();
@@ -657,7 +786,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                const int split = unit % g.splits;
+                const int split = g.split_major ? unit / num_tiles : unit % g.splits;
                 const int kb0 = split * g.kb_per, kb1 = min(kb0 + g.kb_per, num_kb);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);             // epilogue drained this buffer
                 tc_fence_after();
@@ -687,11 +816,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const bool atomic = ep.atomic != 0 || g.splits > 1;
         int acc = 0;
         uint32_t acc_phase = 0;
+        [[maybe_unused]] uint32_t add_phase = 0;
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-            const int tile = unit / g.splits;
+            const int tile = g.split_major ? unit % num_tiles : unit / g.splits;
             const int tile_n = tile % tiles_n;
             const int m0 = (tile / tiles_n) * kBlockM, n0 = tile_n * kBlockN;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * kCols;
+            if constexpr (kCellTma) {
+                epilogue_cell_tma<kCols>(ep, taddr, lane, m0 + quarter * 32, n0 + half * kCols, half * kCols, quarter * 32 + lane,
+                                         M, N, &tmem_full[acc], acc_phase, add_full, add_phase, smem_add, smem_c);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(add_empty);                 // this warp no longer reads the staged tile
+                add_phase ^= 1;
+            } else
             epilogue_region<kCols, kEpi>(ep, taddr, lane, m0 + quarter * 32, n0 + half * kCols, M, N,
                                          tile_n * 2 + half, tiles_n * 2, atomic, &tmem_full[acc], acc_phase,
                                          smem + S::kOutOff + e * kOutStage, &map_o, g.tma_out);
@@ -784,8 +921,8 @@ int make_tmap_bf16(CUtensorMap *map, const void *ptr, long long outer, long long
 
 template <int kBlockN, int kEpi>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const TcEpilogue &ep,
-                     const TcGeom &g, cudaStream_t stream) {
-    using S = TcSmem<kBlockN>;
+                     const TcGeom &g, cudaStream_t stream, const CUtensorMap *mc = nullptr) {
+    using S = TcSmem<kBlockN, kEpi>;
     static bool attr_set = false;
     auto kern = gemm_bf16_tc_kernel<kBlockN, kEpi>;
     if (!attr_set) {
@@ -794,7 +931,7 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const CUtenso
     }
     const int units = ceil_div(g.M, kBlockM) * ceil_div(g.N, kBlockN) * g.splits;
     const int grid = units < sm_count() ? units : sm_count();
-    kern<<<grid, kThreads, g.tma_out ? S::kBytes : S::kBaseBytes, stream>>>(ma, mb, mo, ep, g);
+    kern<<<grid, kThreads, g.tma_out ? S::kBytes : S::kBaseBytes, stream>>>(ma, mb, mo, mc ? *mc : ma, ep, g);
     DC_CHECK_LAUNCH();
     return DC_OK;
 }
@@ -817,6 +954,8 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
     g.M = M; g.N = N; g.K = K; g.a_mn = A.mn_major ? 1 : 0; g.b_mn = B.mn_major ? 1 : 0;
     g.splits = 1;
     g.tma_out = 0;
+    static const int split_major_env = getenv("DCAP_SPLIT_MAJOR") ? atoi(getenv("DCAP_SPLIT_MAJOR")) : 1;
+    g.split_major = split_major_env;
     if (epi == kEpiStore && ep.atomic && ep.out_f32 && !ep.out_bf16) {
         int want = split_k;
         if (want <= 0) {                      // fill ~2 waves, keep >= 8 k-blocks per unit
@@ -876,8 +1015,22 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
                    (!ep.cell_h_b || (ep.ld_h_b % 8 == 0 && ((uintptr_t)ep.cell_h_b & 15) == 0)) &&
                    (!ep.cell_h_prev || (ep.ld_h_prev % 8 == 0 && ((uintptr_t)ep.cell_h_prev & 15) == 0)),
                    "cell epilogue: h buffers must be 16-byte aligned with ld %% 8 == 0");
-        DC_REQUIRE(!ep.cell_gates_out || (((uintptr_t)ep.cell_gates_out & 15) == 0 && ep.ld_gates_out % 4 == 0),
+        DC_REQUIRE(!ep.cell_gates_out || (((uintptr_t)ep.cell_gates_out & 15) == 0 && ep.ld_gates_out % 8 == 0),
                    "cell epilogue: gate buffer alignment");
+        // shared-memory operand variant: 128-wide tiles, addend + cell state staged by TMA (see epilogue_cell_tma)
+        static const bool cell_tma_off = getenv("DCAP_CELL_TMA") && atoi(getenv("DCAP_CELL_TMA")) == 0;
+        // (measured: pays when there is an fp32 addend to stage -- 44 -> 39 us at 8000 x 2048 x 832; without one the
+        // 128 x 256 tiles win because they read the B operand from shared memory half as often)
+        const bool cell_tma = !cell_tma_off && ep.addend && !g.a_mn && !g.b_mn && N % 128 == 0 && ep.addend_mod == 0 && ep.addend_div == 0 &&
+                              ((uintptr_t)ep.cell_c & 15) == 0 && ep.cell_units % 4 == 0;
+        if (cell_tma) {
+            CUtensorMap mb128, madd = ma, mc;
+            if (int rc = make_tmap_bf16(&mb128, B.ptr, N, K, B.ld, 128)) return rc;
+            if (ep.addend)
+                if (int rc = make_tmap(&madd, ep.addend, M, N, ep.ld_addend, 128, 32, 4)) return rc;
+            if (int rc = make_tmap(&mc, ep.cell_c, M, ep.cell_units, ep.cell_units, 128, 32, 4)) return rc;
+            return launch_tc<128, kEpiCellTma>(ma, mb128, madd, ep, g, stream, &mc);
+        }
         return wide ? launch_tc<256, kEpiCell>(ma, mb, ma, ep, g, stream) : launch_tc<128, kEpiCell>(ma, mb, ma, ep, g, stream);
     }
     if (epi == kEpiTopK) {

@@ -13,6 +13,8 @@ constexpr int kTopKMax = 8;
 // internal variants of kEpiStore chosen by gemm_bf16_tc: the output leaves through shared memory + TMA bulk stores
 constexpr int kEpiStoreTmaF32 = 5;
 constexpr int kEpiStoreTmaB16 = 6;
+// internal variant of kEpiCell: 128-wide tiles, the tile's addend and cell state are staged in shared memory by TMA
+constexpr int kEpiCellTma = 7;
 
 struct TcOperand {
     // K-major (default): [rows, K] row-major, K contiguous, ld = row stride.
@@ -50,7 +52,7 @@ struct TcEpilogue {
     __nv_bfloat16 *cell_h_a = nullptr; long long ld_h_a = 0;               // destinations of the new h
     __nv_bfloat16 *cell_h_b = nullptr; long long ld_h_b = 0;
     float *cell_c_out = nullptr;          // null: c updated in place; else new c written here (training: time-major)
-    float *cell_gates_out = nullptr; long long ld_gates_out = 0;   // optional [M, 4*units] post-activation (i,f,g,o)
+    __nv_bfloat16 *cell_gates_out = nullptr; long long ld_gates_out = 0;   // optional [M, 4*units] bf16 post-activation (i,f,g,o)
 };
 
 // D = epilogue(A * B^T): A [M,K], B [N,K], both bf16 K-major.

@@ -27,6 +27,7 @@
 #include "gemm_tc.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace dcap {
 
@@ -36,7 +37,7 @@ struct TrainState {
     int32_t *tok_tm = nullptr, *tgt_tm = nullptr;                  // [T, B]
     __nv_bfloat16 *X1 = nullptr, *X2 = nullptr;                    // [(T+1), B, K1] / [(T+1), B, 2U]
     float *c1 = nullptr, *c2 = nullptr;                            // [(T+1), B, U]
-    float *gates1 = nullptr, *gates2 = nullptr;                    // [T, B, 4U] post-activation, gate-interleaved
+    __nv_bfloat16 *gates1 = nullptr, *gates2 = nullptr;            // [T, B, 4U] bf16 post-activation (i,f,g,o), gate-interleaved
     __nv_bfloat16 *d_all = nullptr;                                // [T*B, 1024] relu(dense1)
     float *logits = nullptr;                                       // [T*B, V]
     __nv_bfloat16 *dz = nullptr;                                   // [T*B, V]   dlogits
@@ -124,7 +125,7 @@ static int train_reserve(Decoder &D, int B, int T) {
     rc |= A((void **)&t.tok_tm, 4 * R); rc |= A((void **)&t.tgt_tm, 4 * R);
     rc |= A((void **)&t.X1, 2 * (R + Bp) * K1); rc |= A((void **)&t.X2, 2 * (R + Bp) * 2 * U);
     rc |= A((void **)&t.c1, 4 * (R + Bp) * U); rc |= A((void **)&t.c2, 4 * (R + Bp) * U);
-    rc |= A((void **)&t.gates1, 4 * R * 4 * U); rc |= A((void **)&t.gates2, 4 * R * 4 * U);
+    rc |= A((void **)&t.gates1, 2 * R * 4 * U); rc |= A((void **)&t.gates2, 2 * R * 4 * U);
     rc |= A((void **)&t.d_all, 2 * R * kDense);
     rc |= A((void **)&t.logits, 4 * R * V); rc |= A((void **)&t.dz, 2 * R * V);
     rc |= A((void **)&t.dd, 2 * R * kDense); rc |= A((void **)&t.dh2d, 4 * R * U);
@@ -244,92 +245,6 @@ __global__ void __launch_bounds__(256) softmax_xent_kernel(const float *__restri
     }
 }
 
-// Same arithmetic, kRows consecutive rows per CTA with every row held in registers (one global read per
-// logit) and the COLUMN SUMS of dz -- the gradient of the vocabulary bias -- accumulated in registers
-// across the CTA's rows and flushed with one vector reduce-add per thread and column group: the separate
-// pass over the 1.3 GB of dz that a column-sum kernel needs does not exist.  V <= kChunks * 1024, V % 4 == 0.
-template <int kChunks>
-__global__ void __launch_bounds__(256) softmax_xent_colsum_kernel(const float *__restrict__ logits, long long ld, int V,
-                                                                  const int32_t *__restrict__ tgt, float inv_count,
-                                                                  __nv_bfloat16 *__restrict__ dz, long long ld_dz,
-                                                                  float *__restrict__ rowloss, long long rows,
-                                                                  int rows_per_cta, float *__restrict__ dbias) {
-    __shared__ float red[2][2][8];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float acc[kChunks][4];
-#pragma unroll
-    for (int k = 0; k < kChunks; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
-    const long long r0 = (long long)blockIdx.x * rows_per_cta;
-    const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
-    for (long long r = r0; r < r1; ++r) {
-        const float *z = logits + r * ld;
-        float4 q[kChunks];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k) {
-            const int j = k * 1024 + threadIdx.x * 4;
-            q[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            if (j < V) q[k] = __ldcs(reinterpret_cast<const float4 *>(z + j));
-            mx = fmaxf(mx, fmaxf(fmaxf(q[k].x, q[k].y), fmaxf(q[k].z, q[k].w)));
-        }
-        float sum = 0.f;
-        if (mx > -INFINITY) {                                          // a thread with no column of this row holds -inf
-#pragma unroll
-            for (int k = 0; k < kChunks; ++k)
-                sum += __expf(q[k].x - mx) + __expf(q[k].y - mx) + __expf(q[k].z - mx) + __expf(q[k].w - mx);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
-            const float nm = fmaxf(mx, om);
-            sum = (mx > -INFINITY ? sum * __expf(mx - nm) : 0.f) + (om > -INFINITY ? os * __expf(om - nm) : 0.f);
-            mx = nm;
-        }
-        const int pb = (int)(r & 1);                                   // double-buffered: one barrier per row
-        if (lane == 0) { red[pb][0][warp] = mx; red[pb][1][warp] = sum; }
-        __syncthreads();
-        float gm = red[pb][0][0];
-#pragma unroll
-        for (int i = 1; i < 8; ++i) gm = fmaxf(gm, red[pb][0][i]);
-        float gs = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (red[pb][0][i] > -INFINITY) gs += red[pb][1][i] * __expf(red[pb][0][i] - gm);
-        const float inv = 1.0f / gs;
-        const int y = tgt[r];
-        bool live = y >= 0;
-        if (live) {
-            const float py = __expf(z[y] - gm) * inv;
-            if (threadIdx.x == 0) rowloss[r] = -logf(fminf(fmaxf(py, 1e-7f), 1.0f - 1e-7f));
-            live = py > 1e-7f && py < 1.0f - 1e-7f;
-        } else if (threadIdx.x == 0) {
-            rowloss[r] = 0.f;
-        }
-        const float sc = live ? inv_count : 0.f;
-        __nv_bfloat16 *g = dz + r * ld_dz;
-#pragma unroll
-        for (int k = 0; k < kChunks; ++k) {
-            const int j = k * 1024 + threadIdx.x * 4;
-            if (j < V) {
-                float p[4] = {__expf(q[k].x - gm) * inv, __expf(q[k].y - gm) * inv, __expf(q[k].z - gm) * inv,
-                              __expf(q[k].w - gm) * inv};
-                if (y >= j && y < j + 4) p[y - j] -= 1.0f;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { p[i] *= sc; acc[k][i] += p[i]; }
-                __nv_bfloat162 lo = __floats2bfloat162_rn(p[0], p[1]), hi = __floats2bfloat162_rn(p[2], p[3]);
-                *reinterpret_cast<uint2 *>(g + j) = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < kChunks; ++k) {
-        const int j = k * 1024 + threadIdx.x * 4;
-        if (j < V)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbias + j), "f"(acc[k][0]), "f"(acc[k][1]),
-                         "f"(acc[k][2]), "f"(acc[k][3]) : "memory");
-    }
-}
-
 // loss = sum(rowloss) * inv_count, deterministic (one CTA, fixed order)
 __global__ void __launch_bounds__(1024) reduce_loss_kernel(const float *__restrict__ rowloss, long long n, float inv_count,
                                                            float *__restrict__ loss) {
@@ -393,7 +308,7 @@ __global__ void f32_to_bf16_rows_kernel(const float *__restrict__ src, long long
 //   c_prev/c_new  the cell state before / after the step
 //   dh = dh_a (+ dh_b) + carry;  masked row (tok == 0): dz = 0, carry <- dh, dc unchanged
 //   else: dz (Keras block order i|f|c|o, bf16), dc <- dc_prev, carry <- 0, dzsum += dz (optional)
-__global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(int B, int U, const float *__restrict__ gates,
+__global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(int B, int U, const __nv_bfloat16 *__restrict__ gates,
                                                             const float *__restrict__ c_prev, const float *__restrict__ c_new,
                                                             const int32_t *__restrict__ tok, const float *__restrict__ dh_a,
                                                             int ld_a, const float *__restrict__ dh_b, int ld_b,
@@ -427,10 +342,13 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(int B, int U, const 
     const float dhs[4] = {dh.x, dh.y, dh.z, dh.w}, dcs[4] = {dcv.x, dcv.y, dcv.z, dcv.w};
     const float cps[4] = {cpv.x, cpv.y, cpv.z, cpv.w}, cns[4] = {cnv.x, cnv.y, cnv.z, cnv.w};
     float dzi[4], dzf[4], dzg[4], dzo[4], dcp[4];
+    const uint4 *gp = reinterpret_cast<const uint4 *>(gates + (long long)b * 4 * U + 4 * u0);      // 4 units x 4 gates bf16
+    const uint4 gq[2] = {gp[0], gp[1]};
+    const uint32_t gw[8] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float4 gt = *reinterpret_cast<const float4 *>(gates + (long long)b * 4 * U + 4 * (u0 + j));
-        const float ig = gt.x, fg = gt.y, gg = gt.z, og = gt.w;
+        const float ig = __uint_as_float(gw[2 * j] << 16), fg = __uint_as_float(gw[2 * j] & 0xffff0000u);
+        const float gg = __uint_as_float(gw[2 * j + 1] << 16), og = __uint_as_float(gw[2 * j + 1] & 0xffff0000u);
         const float tc = tanhf(cns[j]);
         const float dcn = dcs[j] + dhs[j] * og * (1.f - tc * tc);
         // hard_sigmoid'(z) = 0.2 inside the linear range, i.e. where the activation is strictly in (0, 1)
@@ -617,17 +535,10 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     auto G = [&](const char *name) { return grads + find(name)->offset; };
     DC_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n_train, s));
 
-    // softmax + cross-entropy + dlogits (+ the vocabulary-bias gradient when the row fits in registers)
-    bool bias_done = false;
-    {
-        const int rpc = 32;
-        const unsigned grid = (unsigned)ceil_div<long long>(R, rpc);
-        float *db = G("imgcap_lstm_d2/bias");
-        if (V <= 2048) { softmax_xent_colsum_kernel<2><<<grid, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss, R, rpc, db); bias_done = true; }
-        else if (V <= 10240) { softmax_xent_colsum_kernel<10><<<grid, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss, R, rpc, db); bias_done = true; }
-        else if (V <= 16384) { softmax_xent_colsum_kernel<16><<<grid, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss, R, rpc, db); bias_done = true; }
-        else softmax_xent_kernel<<<(unsigned)R, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
-    }
+    // softmax + cross-entropy + dlogits: one CTA per row keeps ~10 rows in flight per SM, which is what makes
+    // this kernel run at HBM speed (a variant that kept rows in registers and accumulated the vocabulary-bias
+    // gradient in place was latency-bound on its per-row barrier and measured 0.7 ms SLOWER per step)
+    softmax_xent_kernel<<<(unsigned)R, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
     DC_CHECK_LAUNCH();
     reduce_loss_kernel<<<1, 1024, 0, s>>>(t.rowloss, R, inv_count, loss);
     DC_CHECK_LAUNCH();
@@ -641,8 +552,7 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     };
     // dense2: dWd2 = d^T dz, dbd2 = colsum(dz), dd = (dz Wd2^T) * [d > 0]
     if (int rc = wgrad(t.d_all, kDense, kDense, t.dz, V, V, R, G("imgcap_lstm_d2/kernel"), V)) return rc;
-    if (!bias_done)
-        if (int rc = colsum(t.dz, R, V, V, G("imgcap_lstm_d2/bias"), s)) return rc;
+    if (int rc = colsum(t.dz, R, V, V, G("imgcap_lstm_d2/bias"), s)) return rc;
     DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[0], s));                 // bucket 0: vocabulary projection
     {
         TcEpilogue e;
