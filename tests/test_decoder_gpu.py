@@ -234,3 +234,20 @@ def test_caption_rois_end_to_end_matches_two_stage_path():
     assert isinstance(got_host, np.ndarray) and np.array_equal(got_host, want)
     got_dev = m.caption_rois(torch.from_numpy(boxes).cuda(), [torch.from_numpy(f).cuda() for f in fms], (1024, 1024, 3))
     assert np.array_equal(got_dev.cpu().numpy(), want)
+
+
+def test_fp32_path_matches_golden_decoder_vectors(golden_dir):
+    """CUDA fp32 path against the committed golden vectors (tests/golden/decoder_small.npz)."""
+    import os
+    g = np.load(os.path.join(golden_dir, "decoder_small.npz"))
+    rng = np.random.default_rng(20261018)
+    V, E, U, C, P = 96, 16, 64, 8, 6
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    m = _model_v1(w, P, V, E, U, C)
+    np.testing.assert_allclose(m.head_features(g["feat"]), g["head"], rtol=2e-4, atol=2e-5)
+    tok, probs = m.generate(g["feat"], return_probs=True)
+    assert np.array_equal(tok, g["greedy_tok"])
+    np.testing.assert_allclose(probs, g["greedy_probs"], rtol=PROB_RTOL, atol=PROB_ATOL)
+    bt, bs = m.beam_search(g["feat"], beam_width=3)
+    assert np.array_equal(bt, g["beam_tok"])
+    np.testing.assert_allclose(bs, g["beam_scores"], rtol=1e-5)

@@ -128,3 +128,21 @@ def test_beam_width1_equals_greedy_and_scores_accumulate():
     bt3, bs3 = dec.beam_v1(f, w, P, 3)
     assert (np.diff(bs3, axis=1) >= 0).all()            # ascending, best last
     assert (bs3[:, -1] >= bs[:, 0] - 1e-9).all()
+
+
+def test_oracle_reproduces_golden_decoder_vectors(golden_dir):
+    """tests/golden/decoder_small.npz freezes the oracle (parity unpinned by the reference)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("gen_golden_decoder", os.path.join(golden_dir, "gen_golden_decoder.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.build()
+    g = np.load(os.path.join(golden_dir, "decoder_small.npz"))
+    for k in ("greedy_tok", "beam_tok", "v2_tok", "gt"):
+        assert np.array_equal(now[k], g[k]), k
+    for k in ("head", "greedy_probs", "teacher_forced_probs", "beam_scores", "adam_p1", "adam_m1", "adam_v1", "v2_probs_last"):
+        np.testing.assert_allclose(now[k], g[k], rtol=1e-5, atol=1e-8, err_msg=k)
+    assert abs(float(now["loss"]) - float(g["loss"])) < 1e-6
+    np.testing.assert_allclose(now["grad_l2"], g["grad_l2"], rtol=1e-9)
+    np.testing.assert_allclose(now["grad_sum"], g["grad_sum"], rtol=1e-7, atol=1e-12)
