@@ -9,3 +9,5 @@ from .roi_align import PyramidROIAlign, pyramid_roi_align, fpn_levels    # noqa:
 from . import synth  # noqa: F401
 from .text_model import (DenseCapConfig, build_lstm_model, build_model, RoiCaptionModel,   # noqa: F401
                          InjectModelV2, Adam, roi_caption_loss)
+from .postprocess import refine_generations, caption_text    # noqa: F401
+from . import parallel    # noqa: F401

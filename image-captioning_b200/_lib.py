@@ -52,6 +52,9 @@ SIGNATURES = {
     "dc_decoder_finalize": (ctypes.c_int, [c_void, c_void]),
     "dc_head_forward": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void]),
     "dc_decoder_greedy": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void]),
+    "dc_decoder_greedy_scored": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void]),
+    "dc_refine_generations": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
+                                             c_void, c_void, c_void]),
     "dc_decoder_beam": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void,
                                        c_void, c_void]),
     "dc_decoder_v2_predict": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_void, ctypes.c_int,

@@ -320,14 +320,27 @@ int Decoder::check_ready(int B) {
     return DC_OK;
 }
 
-int Decoder::greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s) {
+// scores[r] (+)= log(maxprob[r]): the caption score of refine_generations (sum over steps of log max p)
+__global__ void accumulate_log_kernel(float *__restrict__ scores, const float *__restrict__ maxprob, int rows, int first) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) scores[r] = (first ? 0.f : scores[r]) + logf(maxprob[r]);
+}
+
+int accumulate_log(float *scores, const float *maxprob, int rows, bool first, cudaStream_t s) {
+    accumulate_log_kernel<<<ceil_div(rows, 256), 256, 0, s>>>(scores, maxprob, rows, first ? 1 : 0);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
+int Decoder::greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, float *scores) {
     if (int rc = check_ready(B)) return rc;
     DC_REQUIRE(cfg.arch == DC_ARCH_V1, "dc_decoder_greedy needs a v1 decoder");
     if (B == 0) return DC_OK;
     DC_REQUIRE(feats && tokens, "null pointer argument");
     if (int rc = reserve(B)) return rc;
     const int P = cfg.padding, V = cfg.vocab;
-    if (cfg.dtype == DC_DTYPE_BF16 && !probs) return greedy_bf16_graphed(feats, kind, B, tokens, s);
+    if (cfg.dtype == DC_DTYPE_BF16 && !probs && !scores) return greedy_bf16_graphed(feats, kind, B, tokens, s);
+    if (cfg.dtype == DC_DTYPE_BF16 && !probs) return greedy_bf16(feats, kind, B, tokens, s, scores);
     if (int rc = head(feats, kind, B, ws.F, s)) return rc;
     if (int rc = v1_hoist(B, s)) return rc;
     if (int rc = v1_reset_state(B, s)) return rc;
@@ -335,7 +348,9 @@ int Decoder::greedy(const void *feats, int kind, int B, int32_t *tokens, float *
     for (int t = 0; t < P; ++t) {
         if (int rc = v1_step(B, ws.g1f, ws.d1f, s)) return rc;
         if (int rc = softmax_argmax(ws.logits, V, B, V, probs ? probs + (size_t)t * V : nullptr,
-                                    (long long)P * V, tokens + t, P, ws.tok, nullptr, s)) return rc;
+                                    (long long)P * V, tokens + t, P, ws.tok, scores ? ws.cand_p : nullptr, s)) return rc;
+        if (scores)
+            if (int rc = accumulate_log(scores, ws.cand_p, B, t == 0, s)) return rc;
     }
     return DC_OK;
 }
@@ -594,6 +609,13 @@ extern "C" int dc_decoder_greedy(DcDecoder *dec, const void *feats, int kind, in
                                  float *probs, void *stream) {
     DC_REQUIRE(dec, "null decoder");
     return dec->impl.greedy(feats, kind, B, tokens, probs, (cudaStream_t)stream);
+}
+
+extern "C" int dc_decoder_greedy_scored(DcDecoder *dec, const void *feats, int kind, int B, int32_t *tokens,
+                                        float *scores, void *stream) {
+    DC_REQUIRE(dec, "null decoder");
+    DC_REQUIRE(scores || B == 0, "null pointer argument");
+    return dec->impl.greedy(feats, kind, B, tokens, nullptr, (cudaStream_t)stream, scores);
 }
 
 extern "C" int dc_decoder_beam(DcDecoder *dec, const void *feats, int kind, int B, int k, int32_t *tokens,

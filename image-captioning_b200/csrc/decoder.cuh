@@ -34,6 +34,7 @@ struct Workspace {
 };
 
 struct Bf16State;                 // decoder_bf16.cu
+int accumulate_log(float *scores, const float *maxprob, int rows, bool first, cudaStream_t s);   // decoder.cu
 
 struct Decoder {
     DcDecoderConfig cfg{};
@@ -85,7 +86,7 @@ struct Decoder {
     int v1_hoist(int B, cudaStream_t s);
     int v1_reset_state(int R, cudaStream_t s);
     int v1_step(int R, const float *g1f, const float *d1f, cudaStream_t s);
-    int greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s);
+    int greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, float *scores = nullptr);
     int beam(const void *feats, int kind, int B, int k, int32_t *tokens, double *scores, cudaStream_t s);
     int v2_reset(int B, cudaStream_t s);
     int v2_word_step(int B, cudaStream_t s);
@@ -101,7 +102,7 @@ struct Decoder {
     int v1_hoist_bf16(int B, cudaStream_t s);
     int reset_state_bf16(int R, cudaStream_t s);
     int v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_t s);
-    int greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s);
+    int greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s, float *scores = nullptr);
     int greedy_bf16_graphed(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s);
     void drop_graphs();
     int beam_bf16(const void *feats, int kind, int B, int k, int32_t *tokens, double *scores, cudaStream_t s);

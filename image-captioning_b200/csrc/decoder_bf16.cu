@@ -216,7 +216,7 @@ int Decoder::v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_
 }
 
 // greedy fast path: tokens only, the [B,V] logits never exist
-int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s) {
+int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s, float *scores) {
     const int P = cfg.padding, V = cfg.vocab;
     if (int rc = head(feats, kind, B, ws.F, s)) return rc;
     if (int rc = v1_hoist(B, s)) return rc;
@@ -227,11 +227,15 @@ int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cu
         if (int rc = step_core(*this, B, ws.g1f, ws.d1f, t == 0, s)) return rc;
         TcEpilogue e;
         e.bias = W("imgcap_lstm_d2/bias"); e.partial = bf->partial;
-        if (int rc = gemm_bf16_tc(op(bf->d, kDense), op(bf->wd2, kDense), e, B, V, kDense, kEpiArgmax, s)) return rc;
+        // caption scores need the softmax probability of the arg-max: the epilogue also sums exp(v - max)
+        if (int rc = gemm_bf16_tc(op(bf->d, kDense), op(bf->wd2, kDense), e, B, V, kDense, scores ? kEpiArgmaxSum : kEpiArgmax, s)) return rc;
         // token of this step + its embedding row, written into the operand buffer of step t+1
         const bool more = t + 1 < P;
-        if (int rc = argmax_merge(bf->partial, B, slots, tokens + t, P, ws.tok, nullptr, s, more ? bf->emb : nullptr,
-                                  bf->Epad, more ? bf->X1[bf->parity] : nullptr, bf->Epad + cfg.units)) return rc;
+        if (int rc = argmax_merge(bf->partial, B, slots, tokens + t, P, ws.tok, scores ? ws.cand_p : nullptr, s,
+                                  more ? bf->emb : nullptr, bf->Epad, more ? bf->X1[bf->parity] : nullptr,
+                                  bf->Epad + cfg.units)) return rc;
+        if (scores)
+            if (int rc = accumulate_log(scores, ws.cand_p, B, t == 0, s)) return rc;
     }
     return DC_OK;
 }

@@ -289,26 +289,36 @@ class RoiCaptionModel(_ModelBase):
         self.mode = mode
         super().__init__(ARCH_V1, config, units, list(features_input), dtype, device=device)
 
-    def generate(self, features, return_probs=False, chunk=None):
-        """Greedy captions: token ids [N,P] (int32) and optionally the [N,P,V] probabilities.
+    def generate(self, features, return_probs=False, chunk=None, return_scores=False):
+        """Greedy captions: token ids [N,P] (int32) and optionally the [N,P,V] probabilities or the
+        caption scores [N] = sum_t log max_v p (the score refine_generations ranks by,
+        evaluate_models/test_score_dense_captions.py:256-258).
         torch CUDA in -> torch CUDA out; numpy in -> numpy out."""
         self._ready()
         t, kind, was_numpy = self._feats_to_device(features)
         N, P, V = t.shape[0], self.config.PADDING_SIZE, self.config.VOCABULARY_SIZE
         tokens = torch.empty((N, P), dtype=torch.int32, device=self.device)
         probs = torch.empty((N, P, V), dtype=torch.float32, device=self.device) if return_probs else None
+        scores = torch.empty((N,), dtype=torch.float32, device=self.device) if return_scores else None
         chunk = N if not chunk else int(chunk)
         with torch.cuda.device(self.device):
             for i in range(0, N, max(chunk, 1)):
                 j = min(N, i + chunk)
+                if scores is not None and probs is None:
+                    _lib.check(self._lib.dc_decoder_greedy_scored(
+                        self._h, ctypes.c_void_p(t[i:j].data_ptr()), kind, j - i,
+                        ctypes.c_void_p(tokens[i:j].data_ptr()), ctypes.c_void_p(scores[i:j].data_ptr()), self._stream()))
+                    continue
                 _lib.check(self._lib.dc_decoder_greedy(
                     self._h, ctypes.c_void_p(t[i:j].data_ptr()), kind, j - i,
                     ctypes.c_void_p(tokens[i:j].data_ptr()),
                     ctypes.c_void_p(probs[i:j].data_ptr()) if probs is not None else None, self._stream()))
+        if scores is not None and probs is not None:
+            scores = torch.log(probs.max(-1).values).sum(-1)
+        outs = [tokens] + ([probs] if return_probs else []) + ([scores] if return_scores else [])
         if was_numpy:
-            tokens = tokens.cpu().numpy()
-            probs = probs.cpu().numpy() if probs is not None else None
-        return (tokens, probs) if return_probs else tokens
+            outs = [o.cpu().numpy() for o in outs]
+        return outs[0] if len(outs) == 1 else tuple(outs)
 
     def predict(self, x, batch_size=None, verbose=0):
         """Keras predict of the inference model: [N,P,V] word probabilities

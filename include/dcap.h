@@ -160,6 +160,12 @@ int dc_head_forward(DcDecoder *dec, const void *feats, int feats_kind, int B, fl
 int dc_decoder_greedy(DcDecoder *dec, const void *feats, int feats_kind, int B, int32_t *tokens,
                       float *probs, void *stream);
 
+/* Greedy captioning that also returns the caption score of refine_generations
+ * (evaluate_models/test_score_dense_captions.py:256-258): scores[b] = sum over the P steps of
+ * log(max_v p) -- without materialising the [B,P,V] probabilities.  scores [B] fp32 (device). */
+int dc_decoder_greedy_scored(DcDecoder *dec, const void *feats, int feats_kind, int B, int32_t *tokens,
+                             float *scores, void *stream);
+
 /* Beam search with the semantics of gen_captions (image captioning/test.py:23-64) applied to the
  * v1 decoder: width k, scores are SUMS OF PROBABILITIES (fp64 accumulation of fp32), children
  * pooled in generation order, stable ascending sort, keep the last k, no end-token handling.
@@ -250,6 +256,19 @@ int dc_caption_rois(DcDecoder *dec, const float *boxes, const float *const fmaps
 int dc_caption_rois_host(DcDecoder *dec, const float *boxes, const float *const fmaps[4],
                          const int fm_h[4], const int fm_w[4], int n_images, int n_boxes, int img_h,
                          int img_w, int32_t *tokens);
+
+/* ------------------------------------------------------------------------------------------
+ * Caption post-processing (the step after the decoder in the dense-captioning evaluation path)
+ * ---------------------------------------------------------------------------------------- */
+
+/* refine_generations (evaluate_models/test_score_dense_captions.py:245-283) with non_max_suppression
+ * (evaluate_models/utils.py:69-104) and that copy's overlap measure 2*I/(A+B) (utils.py:30-48), per image:
+ * RoIs are visited in descending caption score (equal scores: larger index first), a visited RoI suppresses
+ * every later one whose overlap exceeds nms_threshold, and the first max_keep survivors are returned.
+ *   boxes [n_images, n_boxes, 4] fp32 (y1,x1,y2,x2), scores [n_images, n_boxes] fp32 (device)
+ *   keep [n_images, max_keep] int32 indices into the image's boxes (-1 padded), n_keep [n_images] int32 */
+int dc_refine_generations(const float *boxes, const float *scores, int n_images, int n_boxes,
+                          float nms_threshold, int max_keep, int32_t *keep, int32_t *n_keep, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contraction primitives (exported so that tests can pin the GEMM kernels in isolation;
