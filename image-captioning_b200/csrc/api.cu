@@ -3,6 +3,7 @@
 #include "gemm.cuh"
 #include "gemm_tc.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace dcap {
 
@@ -10,6 +11,16 @@ char *err_buf() {
     static thread_local char buf[512] = {0};
     return buf;
 }
+
+static thread_local bool tls_pdl_scope = false;
+
+bool pdl_enabled() {
+    static const bool on = !(getenv("DCAP_PDL") && atoi(getenv("DCAP_PDL")) == 0);
+    return on && tls_pdl_scope;
+}
+
+PdlScope::PdlScope() : prev(tls_pdl_scope) { tls_pdl_scope = true; }
+PdlScope::~PdlScope() { tls_pdl_scope = prev; }
 
 int set_error(int code, const char *fmt, ...) {
     va_list ap;

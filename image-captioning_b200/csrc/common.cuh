@@ -43,4 +43,32 @@ inline int sm_count() {
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may become resident while
+// the previous kernel of the stream is still draining; it must execute pdl_wait() before it touches
+// anything that kernel wrote.  Everything before the wait (barrier init, TMEM allocation, descriptor
+// prefetch) overlaps the predecessor's tail.  Both calls are no-ops under a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();          // api.cu: true inside a PdlScope unless DCAP_PDL=0
+// Enables PDL launches on this thread for its lifetime.  Used by the training step (eager launches of >100
+// short dependent kernels: -2 % per step); NOT by the CUDA-graph-captured greedy loop, where programmatic
+// edges measured slower (+2 %).
+struct PdlScope {
+    bool prev;
+    PdlScope();
+    ~PdlScope();
+};
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace dcap

@@ -726,6 +726,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // everything above overlapped the previous kernel's tail (programmatic dependent launch); from here on
+    // its results are read
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -931,8 +935,8 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const CUtenso
     }
     const int units = ceil_div(g.M, kBlockM) * ceil_div(g.N, kBlockN) * g.splits;
     const int grid = units < sm_count() ? units : sm_count();
-    kern<<<grid, kThreads, g.tma_out ? S::kBytes : S::kBaseBytes, stream>>>(ma, mb, mo, mc ? *mc : ma, ep, g);
-    DC_CHECK_LAUNCH();
+    DC_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)(g.tma_out ? S::kBytes : S::kBaseBytes), stream, ma, mb, mo,
+                             mc ? *mc : ma, ep, g));
     return DC_OK;
 }
 
@@ -1058,6 +1062,8 @@ __global__ void __launch_bounds__(256) argmax_merge_kernel(const float4 *__restr
                                                            uint4 *__restrict__ x_out, long long ld_x8) {
     const int r = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_wait();
+    pdl_launch_dependents();
     if (r >= rows) return;
     float best = -INFINITY, sum = 0.f;
     int bi = 0x7fffffff;
@@ -1104,11 +1110,10 @@ int argmax_merge(const float *partial, int rows, int tiles, int32_t *tok_out, in
                  long long ld_x) {
     if (rows <= 0) return DC_OK;
     DC_REQUIRE(!emb || (emb_ld % 8 == 0 && ld_x % 8 == 0 && x_out), "argmax_merge: embedding rows must be 16-byte multiples");
-    argmax_merge_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(reinterpret_cast<const float4 *>(partial), rows, tiles,
-                                                         tok_out, tok_stride, tok_cur, maxprob,
-                                                         reinterpret_cast<const uint4 *>(emb), emb_ld / 8,
-                                                         reinterpret_cast<uint4 *>(x_out), ld_x / 8);
-    DC_CHECK_LAUNCH();
+    DC_CHECK_CUDA(launch_pdl(argmax_merge_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, s,
+                             reinterpret_cast<const float4 *>(partial), rows, tiles, tok_out, tok_stride, tok_cur, maxprob,
+                             reinterpret_cast<const uint4 *>(emb), emb_ld / 8, reinterpret_cast<uint4 *>(x_out),
+                             (long long)(ld_x / 8)));
     return DC_OK;
 }
 

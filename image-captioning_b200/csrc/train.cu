@@ -449,6 +449,7 @@ __global__ void adam_amsgrad_kernel(float *__restrict__ p, const float *__restri
 // ------------------------------------------------------------------------------------------------
 // Teacher-forced forward up to the logits [T*B, V] (time-major) with every activation the backward needs.
 int Decoder::train_forward(const void *feats, int kind, int B, const int32_t *gt, const int32_t *targets, cudaStream_t s) {
+    PdlScope pdl;                                          // chained GEMMs overlap their prologues with the predecessor's tail
     if (int rc = check_ready(B)) return rc;
     DC_REQUIRE(cfg.arch == DC_ARCH_V1 && cfg.dtype == DC_DTYPE_BF16, "the training graph is served by the bf16 v1 decoder");
     DC_REQUIRE(cfg.vocab % 8 == 0, "training needs VOCABULARY_SIZE %% 8 == 0 (vector gradient stores)");
@@ -520,6 +521,7 @@ int Decoder::train_forward(const void *feats, int kind, int B, const int32_t *gt
 int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, const int32_t *targets, float inv_count,
                         float *loss, cudaStream_t s) {
     DC_REQUIRE(loss, "null loss pointer");
+    PdlScope pdl;
     if (int rc = train_forward(feats, kind, B, gt, targets, s)) return rc;
     if (int rc = ensure_grads()) return rc;
     Bf16State &b = *bf;
