@@ -316,6 +316,8 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(int B, int U, const 
                                                             __nv_bfloat16 *__restrict__ dz, float *__restrict__ dzsum) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int uq = U >> 2;
+    pdl_wait();                                           // launched with PDL between the BPTT GEMMs
+    pdl_launch_dependents();
     if (idx >= (long long)B * uq) return;
     const int b = (int)(idx / uq), u0 = (int)(idx - (long long)b * uq) * 4;
     const long long so = (long long)b * U + u0;
@@ -584,19 +586,19 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
         const int32_t *tok = t.tok_tm + (size_t)st * B;
         const bool last = st == T - 1;
         __nv_bfloat16 *dz2 = t.dz2_all + (size_t)st * B * 4 * U, *dz1 = t.dz1_all + (size_t)st * B * 4 * U;
-        lstm_cell_bwd_kernel<<<cb_grid, 256, 0, s>>>(B, U, t.gates2 + (size_t)st * B * 4 * U, t.c2 + (size_t)st * B * U,
-                                                     t.c2 + (size_t)(st + 1) * B * U, tok, t.dh2d + (size_t)st * B * U, U,
-                                                     last ? nullptr : t.dxh2 + U, 2 * U, t.carry2, t.dc2, dz2, nullptr);
-        DC_CHECK_LAUNCH();
+        DC_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(cb_grid), dim3(256), 0, s, B, U,
+                                 (const __nv_bfloat16 *)(t.gates2 + (size_t)st * B * 4 * U), (const float *)(t.c2 + (size_t)st * B * U),
+                                 (const float *)(t.c2 + (size_t)(st + 1) * B * U), tok, (const float *)(t.dh2d + (size_t)st * B * U), U,
+                                 (const float *)(last ? nullptr : t.dxh2 + U), 2 * U, t.carry2, t.dc2, dz2, (float *)nullptr));
         {   // [dh1_t | dh2_{t-1}] = dz2 [W2 ; U2]^T
             TcEpilogue e;
             e.out_f32 = t.dxh2; e.ld_f32 = 2 * U;
             if (int rc = gemm_bf16_tc(tc_op(dz2, 4 * U), tc_op(b.w2cat_k, 4 * U), e, B, 2 * U, 4 * U, kEpiStore, s)) return rc;
         }
-        lstm_cell_bwd_kernel<<<cb_grid, 256, 0, s>>>(B, U, t.gates1 + (size_t)st * B * 4 * U, t.c1 + (size_t)st * B * U,
-                                                     t.c1 + (size_t)(st + 1) * B * U, tok, t.dxh2, 2 * U,
-                                                     last ? nullptr : t.dh1p, U, t.carry1, t.dc1, dz1, t.dz1sum);
-        DC_CHECK_LAUNCH();
+        DC_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(cb_grid), dim3(256), 0, s, B, U,
+                                 (const __nv_bfloat16 *)(t.gates1 + (size_t)st * B * 4 * U), (const float *)(t.c1 + (size_t)st * B * U),
+                                 (const float *)(t.c1 + (size_t)(st + 1) * B * U), tok, (const float *)t.dxh2, 2 * U,
+                                 (const float *)(last ? nullptr : t.dh1p), U, t.carry1, t.dc1, dz1, t.dz1sum));
         if (st > 0) {   // dh1_{t-1} = dz1 U1^T
             TcEpilogue e;
             e.out_f32 = t.dh1p; e.ld_f32 = U;
