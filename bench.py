@@ -476,7 +476,10 @@ def run_ours_captions(args):
                    "l2": "inputs larger than L2 (pyramid %d MB per GPU; decoder weights + activations %d MB)"
                          % (sum(f.numel() for f in fms) * 4 // 2 ** 20, (63 + R * (12544 * 2 + 4 * 2048 * 2) // 2 ** 20)),
                    "sm_count": sms, "cc": cc, "public_api_matches": same_as_fused},
-        "clocks": clocks, "gpu_launches": K * (2 + 8 + 6 * PADDING), "roofline": roofline,
+        "clocks": clocks,
+        # per step: roi_prepare + roi_align_stream, head (2 GEMMs), bf16 cast, 2 hoisted-term GEMMs, token fill,
+        # first embedding gather, then P x (2 gate GEMMs + dense1 + vocabulary GEMM + merge) -- profiles/r1_launches_captions.txt
+        "gpu_launches": K * (2 + 7 + 5 * PADDING), "roofline": roofline,
         "roofline_hbm": roofline_hbm,
     }
     if not args.no_e2e:
@@ -659,7 +662,7 @@ def run_ours_train(args):
                    "one all-reduce(sum) of %d fp32 gradients per step" % model.grad_buffer().numel(),
                    "l2": "activations larger than L2 (logits %d MB per rank)" % (Bl * TRAIN_P * VOCAB * 4 // 2 ** 20),
                    "sm_count": sms, "cc": cc, "loss_first": round(loss_hist[0], 4), "loss_last": round(loss_hist[-1], 4)},
-        "clocks": clocks, "gpu_launches": K * 130,
+        "clocks": clocks, "gpu_launches": K * 144,      # profiles/r1_launches_train.txt
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (forward scan + time-batched dense/vocab GEMMs + "
                      "dgrad/wgrad GEMMs)", "achieved": round(achieved, 1), "peak": tf_peak, "peak_source": tf_src,
                      "unit": "TFLOP/s", "frac": round(achieved / tf_peak, 4), "traffic": None,
