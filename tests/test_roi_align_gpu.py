@@ -149,3 +149,47 @@ def test_full_size_properties():
     # (1) linearity: align(2*F) == 2*align(F) exactly (power-of-two scaling commutes with rounding)
     o2 = pkg.pyramid_roi_align(tb, [f * 2 for f in fa], (7, 7), (1024, 1024, 3))
     assert torch.equal(o2, oa * 2)
+
+
+def test_full_size_cfg2_permutation_padding_and_bf16_properties():
+    """BASELINE configs[1] at full size (8 images x 1000 RoIs, P2-P5 of 1024^2, 256 ch): the CPU oracle
+    checks a seeded sample of RoIs bit for bit; the whole output is checked through size-independent
+    properties -- box-permutation equivariance, image independence, exact scaling by a power of two,
+    zero (padded) boxes reading P2[img, 0, 0, :], levels equal to the standalone level kernel."""
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(1002)
+    B, N, C = 8, 1000, 256
+    boxes = synth.synth_boxes(rng, B, N, 1024.0)
+    gen = torch.Generator(device="cuda").manual_seed(1002)
+    fms = [torch.randn((B, 1024 >> l, 1024 >> l, C), device="cuda", generator=gen) for l in range(2, 6)]
+    tb = torch.from_numpy(boxes).cuda()
+    out, lv = pkg.pyramid_roi_align(tb, fms, (7, 7), (1024, 1024, 3), return_levels=True)
+    assert tuple(out.shape) == (B * N, 7, 7, C)
+    assert torch.equal(lv.reshape(-1), pkg.fpn_levels(tb.reshape(-1, 4), (1024, 1024, 3)).reshape(-1))
+    # (1) oracle on a sample: image 3, 64 RoIs
+    sel = rng.choice(N, 64, replace=False)
+    fm3 = [f[3:4].cpu().numpy() for f in fms]
+    want, lv_want = ra.pyramid_roi_align(boxes[3:4, sel], fm3, (7, 7), (1024, 1024, 3))
+    got = out.reshape(B, N, 7, 7, C)[3, sel].cpu().numpy()
+    assert np.array_equal(lv.reshape(B, N)[3, sel].cpu().numpy(), lv_want.reshape(-1))
+    assert np.array_equal(got.view(np.uint32), want[0].view(np.uint32))
+    # (2) permuting the boxes of every image permutes the output rows
+    perm = torch.from_numpy(rng.permutation(N)).cuda()
+    out_p = pkg.pyramid_roi_align(tb[:, perm].contiguous(), fms, (7, 7), (1024, 1024, 3))
+    assert torch.equal(out_p.reshape(B, N, -1), out.reshape(B, N, -1)[:, perm])
+    # (3) images are independent: image 5 alone gives the same rows
+    out_5 = pkg.pyramid_roi_align(tb[5:6].contiguous(), [f[5:6].contiguous() for f in fms], (7, 7), (1024, 1024, 3))
+    assert torch.equal(out_5, out.reshape(B, N, 7, 7, C)[5])
+    # (4) scaling the maps by 2^k is exact in fp32 (every op is a rounded linear combination)
+    out_s = pkg.pyramid_roi_align(tb, [f * 4.0 for f in fms], (7, 7), (1024, 1024, 3))
+    assert torch.equal(out_s, out * 4.0)
+    # (5) zero (padded) boxes read the P2 origin pixel of their image in every bin
+    zero = (tb.reshape(-1, 4) == 0).all(1).reshape(B, N)
+    assert int(zero.sum()) > 0
+    o5 = out.reshape(B, N, 49, C)
+    for b in range(B):
+        rows = o5[b][zero[b]]
+        assert torch.equal(rows, fms[0][b, 0, 0].expand_as(rows))
+    # (6) bf16 output = round-to-nearest-even of the fp32 output
+    out_b = pkg.pyramid_roi_align(tb, fms, (7, 7), (1024, 1024, 3), out_dtype=torch.bfloat16)
+    assert torch.equal(out_b, out.to(torch.bfloat16))
