@@ -211,6 +211,81 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Top-k epilogue body for one (warp, column region): per row (lane) the running max / sum exp and the K best
+// (value, index) pairs in descending lexicographic order (value, then index: among equal values the LARGER
+// index ranks higher, as np.argsort(p)[-k:] of a stable sort does).  Lane = row, so a data-dependent
+// insertion branch would be taken by some lane at almost every element; instead every element goes through a
+// branch-free K-slot insertion network (K compares + 2K selects).  Two independent lists (even / odd columns)
+// halve the dependent chain; they are merged once at the end of the region.
+template <int K>
+__device__ __forceinline__ void topk_insert_ge(float (&tv)[K], int (&ti)[K], float x, int n) {
+    bool c[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) c[q] = x >= tv[q];                  // NaN (masked column) never enters; ties: the later column wins
+#pragma unroll
+    for (int q = K - 1; q > 0; --q) {
+        tv[q] = c[q - 1] ? tv[q - 1] : (c[q] ? x : tv[q]);
+        ti[q] = c[q - 1] ? ti[q - 1] : (c[q] ? n : ti[q]);
+    }
+    tv[0] = c[0] ? x : tv[0];
+    ti[0] = c[0] ? n : ti[0];
+}
+
+template <int kCols, int K>
+__device__ __forceinline__ void topk_region(const TcEpilogue &ep, uint32_t taddr, int lane, int m_base, int n_base, int M,
+                                            int N, int part_slot, int part_slots) {
+    float ta[K], tb[K];
+    int ia[K], ib[K];
+#pragma unroll
+    for (int q = 0; q < K; ++q) { ta[q] = tb[q] = -INFINITY; ia[q] = ib[q] = -1; }
+    float best = -INFINITY, sum = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kCols; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        const int nb = n_base + c0;
+        if (nb < N) {
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = nb + j;
+                const float x = (n < N) ? v[j] + __ldg(ep.bias + n) : -INFINITY;
+                v[j] = x;
+                cmax = fmaxf(cmax, x);
+            }
+            if (cmax > best) { sum *= __expf(best - cmax); best = cmax; }
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                sum += __expf(v[j] - best) + __expf(v[j + 1] - best);
+                topk_insert_ge<K>(ta, ia, nb + j < N ? v[j] : __int_as_float(0x7fc00000), nb + j);
+                topk_insert_ge<K>(tb, ib, nb + j + 1 < N ? v[j + 1] : __int_as_float(0x7fc00000), nb + j + 1);
+            }
+        }
+    }
+    // merge the odd-column list into the even-column one (full lexicographic compare: indices interleave)
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+        float iv = tb[p];
+        int ii = ib[p];
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+            const bool up = ii >= 0 && (iv > ta[q] || (iv == ta[q] && ii > ia[q]));
+            const float t1 = ta[q]; const int t2 = ia[q];
+            ta[q] = up ? iv : t1; ia[q] = up ? ii : t2;
+            iv = up ? t1 : iv; ii = up ? t2 : ii;
+        }
+    }
+    const int m = m_base + lane;
+    if (m < M) {
+        const int stride = 2 + 2 * ep.topk;
+        float *dst = ep.partial + ((long long)m * part_slots + part_slot) * stride;
+        dst[0] = best; dst[1] = sum;
+#pragma unroll
+        for (int q = 0; q < K; ++q)
+            if (q < ep.topk) { dst[2 + 2 * q] = ta[q]; dst[3 + 2 * q] = __int_as_float(ia[q]); }
+    }
+}
+
 // Epilogue of one (warp, column-half) region: rows = the warp's 32 TMEM lanes (lane i <-> row i),
 // columns [n_base, n_base + kCols) of the tile, pulled 32 columns at a time with tcgen05.ld.
 // Every variant is thread-per-row: a lane's global accesses are whole 32-byte sectors of its own
@@ -262,56 +337,12 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
         }
     } else if constexpr (kEpi == kEpiTopK) {
         wait_acc();
-        // per-row statistics over this region: running max / sum exp and the k best (value, index) pairs in
-        // descending lexicographic order (value, then index: among equal values the LARGER index ranks higher)
-        float tv[kTopKMax];
-        int ti[kTopKMax];
-#pragma unroll
-        for (int q = 0; q < kTopKMax; ++q) { tv[q] = -INFINITY; ti[q] = -1; }
-        float best = -INFINITY, sum = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kCols; c0 += 32) {
-            float v[32];
-            tmem_ld32(taddr + c0, v);
-            const int nb = n_base + c0;
-            if (nb < N) {
-                float cmax = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = nb + j;
-                    const float x = (n < N) ? v[j] + __ldg(ep.bias + n) : -INFINITY;
-                    v[j] = x;
-                    cmax = fmaxf(cmax, x);
-                }
-                if (cmax > best) { sum *= __expf(best - cmax); best = cmax; }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float x = v[j];
-                    sum += __expf(x - best);
-                    // columns arrive in increasing index order: x displaces the current k-th best when x >= it
-                    if (nb + j < N && x >= tv[kTopKMax - 1]) {
-                        float cv = x;
-                        int ci = nb + j;
-#pragma unroll
-                        for (int q = 0; q < kTopKMax; ++q) {
-                            if (cv >= tv[q]) {                       // later index wins ties
-                                const float t1 = tv[q]; const int t2 = ti[q];
-                                tv[q] = cv; ti[q] = ci; cv = t1; ci = t2;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        const int m = m_base + lane;
-        if (m < M) {
-            const int stride = 2 + 2 * ep.topk;
-            float *dst = ep.partial + ((long long)m * part_slots + part_slot) * stride;
-            dst[0] = best; dst[1] = sum;
-#pragma unroll
-            for (int q = 0; q < kTopKMax; ++q)
-                if (q < ep.topk) { dst[2 + 2 * q] = tv[q]; dst[3 + 2 * q] = __int_as_float(ti[q]); }
-        }
+        const int k = ep.topk;
+        if (k <= 1) topk_region<kCols, 1>(ep, taddr, lane, m_base, n_base, M, N, part_slot, part_slots);
+        else if (k == 2) topk_region<kCols, 2>(ep, taddr, lane, m_base, n_base, M, N, part_slot, part_slots);
+        else if (k == 3) topk_region<kCols, 3>(ep, taddr, lane, m_base, n_base, M, N, part_slot, part_slots);
+        else if (k == 4) topk_region<kCols, 4>(ep, taddr, lane, m_base, n_base, M, N, part_slot, part_slots);
+        else topk_region<kCols, kTopKMax>(ep, taddr, lane, m_base, n_base, M, N, part_slot, part_slots);
     } else if constexpr (kEpi == kEpiStore || kEpi == kEpiStoreTmaF32 || kEpi == kEpiStoreTmaB16) {
         const int m = m_base + lane;
         const bool valid = m < M;
