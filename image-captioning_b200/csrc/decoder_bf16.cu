@@ -309,12 +309,14 @@ struct BeamPermute {
     const float *c1_src, *c2_src; float *c1_dst, *c2_dst;
     const int32_t *hist_src; int32_t *hist_dst, *tok;
     int k, U, P, col;
+    int compact;          // first step: the state rows are per RoI (row b), not per beam (row b*k + parent)
 };
 
 __global__ void __launch_bounds__(128) beam_permute_kernel(const BeamPermute a, int rows) {
     const int r = blockIdx.x;
     if (r >= rows) return;
-    const long long sr = (long long)(r / a.k) * a.k + a.parent[r];
+    const long long sr = a.compact ? (long long)(r / a.k) : (long long)(r / a.k) * a.k + a.parent[r];
+    const long long hr = a.compact ? (long long)r : sr;               // history rows always exist per beam
     const int u8 = a.U >> 3, u4 = a.U >> 2;
     const uint4 *h1s = reinterpret_cast<const uint4 *>(a.h1_src + sr * a.ld1), *h2s = reinterpret_cast<const uint4 *>(a.h2_src + sr * a.ld2);
     uint4 *h1d = reinterpret_cast<uint4 *>(a.h1_dst + (long long)r * a.ld1), *h2d = reinterpret_cast<uint4 *>(a.h2_dst + (long long)r * a.ld2);
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(128) beam_permute_kernel(const BeamPermute a, 
     for (int i = threadIdx.x; i < u4; i += blockDim.x) { c1d[i] = c1s[i]; c2d[i] = c2s[i]; }
     const int nt = a.new_tok[r];
     for (int i = threadIdx.x; i < a.P; i += blockDim.x)
-        a.hist_dst[(long long)r * a.P + i] = (i == a.col) ? nt : a.hist_src[sr * a.P + i];
+        a.hist_dst[(long long)r * a.P + i] = (i == a.col) ? nt : a.hist_src[hr * a.P + i];
     if (threadIdx.x == 0) a.tok[r] = nt;
 }
 
@@ -350,12 +352,16 @@ int Decoder::beam_bf16(const void *feats, int kind, int B, int k, int32_t *token
     int32_t *hist = ws.hist_a, *hist_n = ws.hist_b;
     double *sc = ws.score_a, *sc_n = ws.score_b;
     for (int t = 0; t + 1 < P; ++t) {
-        if (int rc = step_core(*this, R, ws.g1f, ws.d1f, true, s, k)) return rc;
+        // step 0: every beam of a RoI is the same (<start>, zero state), so it runs ONCE per RoI (B rows, per-RoI
+        // addends read directly) and the permutation below fans the state out to the k beams
+        const bool first = t == 0;
+        const int rows = first ? B : R;
+        if (int rc = step_core(*this, rows, ws.g1f, ws.d1f, true, s, first ? 0 : k)) return rc;
         TcEpilogue e;
         e.bias = W("imgcap_lstm_d2/bias"); e.partial = b.topk_partial; e.topk = k;
-        if (int rc = gemm_bf16_tc(op(b.d, kDense), op(b.wd2, kDense), e, R, V, kDense, kEpiTopK, s)) return rc;
-        if (int rc = topk_merge(b.topk_partial, R, slots, k, ws.cand_idx, ws.cand_p, s)) return rc;
-        if (int rc = beam_select(B, k, t == 0 ? 1 : k, ws.cand_idx, ws.cand_p, sc, sc_n, ws.parent, ws.newtok, s)) return rc;
+        if (int rc = gemm_bf16_tc(op(b.d, kDense), op(b.wd2, kDense), e, rows, V, kDense, kEpiTopK, s)) return rc;
+        if (int rc = topk_merge(b.topk_partial, rows, slots, k, ws.cand_idx, ws.cand_p, s)) return rc;
+        if (int rc = beam_select(B, k, first ? 1 : k, ws.cand_idx, ws.cand_p, sc, sc_n, ws.parent, ws.newtok, s, first)) return rc;
         // after step_core the live state sits in X1[parity] (h1) / X2[parity] (h2): permute it into the other
         // parity's buffers and make those current
         const int p = b.parity;
@@ -365,7 +371,7 @@ int Decoder::beam_bf16(const void *feats, int kind, int B, int k, int32_t *token
         a.h2_src = b.X2[p] + U; a.h2_dst = b.X2[p ^ 1] + U; a.ld2 = 2 * U;
         a.c1_src = ws.c1; a.c1_dst = ws.c1b; a.c2_src = ws.c2; a.c2_dst = ws.c2b;
         a.hist_src = hist; a.hist_dst = hist_n; a.tok = ws.tok;
-        a.k = k; a.U = U; a.P = P; a.col = t + 1;
+        a.k = k; a.U = U; a.P = P; a.col = t + 1; a.compact = first ? 1 : 0;
         beam_permute_kernel<<<R, 128, 0, s>>>(a, R);
         DC_CHECK_LAUNCH();
         b.parity ^= 1;

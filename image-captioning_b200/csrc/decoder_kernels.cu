@@ -213,7 +213,8 @@ int topk_softmax(const float *logits, int ld, int rows, int V, int k, int32_t *i
 
 // One thread per RoI: pool the children of the active beams in generation order, stable
 // ascending sort by score (double accumulation of fp32 probabilities), keep the last k.
-__global__ void beam_select_kernel(int n_roi, int k, int n_active, const int32_t *__restrict__ cand_idx,
+// compact != 0 (first step computed once per RoI): candidate row of RoI b is b, not b*k
+__global__ void beam_select_kernel(int n_roi, int k, int n_active, int compact, const int32_t *__restrict__ cand_idx,
                                    const float *__restrict__ cand_p, const double *__restrict__ score_in,
                                    double *__restrict__ score_out, int32_t *__restrict__ parent,
                                    int32_t *__restrict__ new_tok) {
@@ -225,9 +226,10 @@ __global__ void beam_select_kernel(int n_roi, int k, int n_active, const int32_t
     for (int j = 0; j < n_active; ++j)
         for (int c = 0; c < k; ++c) {
             const long long row = (long long)b * k + j;
-            sc[n] = score_in[row] + (double)cand_p[row * k + c];
+            const long long crow = compact ? (long long)b : row;
+            sc[n] = score_in[row] + (double)cand_p[crow * k + c];
             par[n] = j;
-            tk[n] = cand_idx[row * k + c];
+            tk[n] = cand_idx[crow * k + c];
             ++n;
         }
     // stable insertion sort, ascending
@@ -247,9 +249,9 @@ __global__ void beam_select_kernel(int n_roi, int k, int n_active, const int32_t
 
 int beam_select(int n_roi, int k, int n_active, const int32_t *cand_idx, const float *cand_p,
                 const double *score_in, double *score_out, int32_t *parent, int32_t *new_tok,
-                cudaStream_t s) {
+                cudaStream_t s, bool compact) {
     if (n_roi <= 0) return DC_OK;
-    beam_select_kernel<<<ceil_div(n_roi, 128), 128, 0, s>>>(n_roi, k, n_active, cand_idx, cand_p,
+    beam_select_kernel<<<ceil_div(n_roi, 128), 128, 0, s>>>(n_roi, k, n_active, compact ? 1 : 0, cand_idx, cand_p,
                                                            score_in, score_out, parent, new_tok);
     DC_CHECK_LAUNCH();
     return DC_OK;

@@ -28,7 +28,7 @@ int topk_softmax(const float *logits, int ld, int rows, int V, int k, int32_t *i
                  cudaStream_t s);
 int beam_select(int n_roi, int k, int n_active, const int32_t *cand_idx, const float *cand_p,
                 const double *score_in, double *score_out, int32_t *parent, int32_t *new_tok,
-                cudaStream_t s);
+                cudaStream_t s, bool compact = false);
 int beam_gather(int rows, int k, int width, const int32_t *parent, const void *src, int ld_src,
                 void *dst, int ld_dst, int elem_bytes, cudaStream_t s);
 int fill_i32(int32_t *p, long long n, int32_t v, cudaStream_t s);
