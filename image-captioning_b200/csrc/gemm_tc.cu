@@ -983,7 +983,8 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const CUtenso
 //
 // Barriers: TMA loads of BOTH CTAs complete on the LEADER's full barrier (armed by the leader's producer
 // with the bytes of both); tcgen05.commit multicasts to both CTAs' empty / tmem-full barriers; the
-// epilogue warps of both CTAs arrive on the leader's tmem-empty barrier.  K-major operands, no split-K.
+// epilogue warps of both CTAs arrive on the leader's tmem-empty barrier.  K-major or MN-major operands, split-K
+// with reduce-add epilogues as in the single-CTA kernel.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -1068,6 +1069,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     const int tiles_n = (N + kBlockN - 1) / kBlockN;
     const int tiles_m = (M + 2 * kBlockM - 1) / (2 * kBlockM);
     const int num_tiles = tiles_m * tiles_n;
+    const int num_units = num_tiles * g.splits;          // unit = split * num_tiles + tile (split-K: CTAs running together share a K range)
     const int num_kb = (K + kBlockK - 1) / kBlockK;
 
     if (warp == 0 && lane == 0) {
@@ -1092,15 +1094,28 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            for (int unit = pair; unit < num_units; unit += num_pairs) {
+                const int split = unit / num_tiles, tile = unit - split * num_tiles;
                 const int m0 = (tile / tiles_n) * (2 * kBlockM) + (int)rank * kBlockM;
                 const int nb0 = (tile % tiles_n) * kBlockN + (int)rank * 128;       // this CTA's half of the B tile
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = split * g.kb_per, kb1 = min(kb0 + g.kb_per, num_kb);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (S::kStageA + S::kStageB));   // bytes of both CTAs
                     const uint32_t bar = mapa_u32(&full_bar[stage], 0);
-                    tma_load_2d_2sm(&map_a, bar, smem_a + stage * S::kStageA, kb * kBlockK, m0);
-                    tma_load_2d_2sm(&map_b, bar, smem_b + stage * S::kStageB, kb * kBlockK, nb0);
+                    uint8_t *da = smem_a + stage * S::kStageA, *db = smem_b + stage * S::kStageB;
+                    if (!g.a_mn) {
+                        tma_load_2d_2sm(&map_a, bar, da, kb * kBlockK, m0);
+                    } else {                                           // MN-major: two [64 k x 64 m] slabs
+                        tma_load_2d_2sm(&map_a, bar, da, m0, kb * kBlockK);
+                        tma_load_2d_2sm(&map_a, bar, da + kSlab, m0 + 64, kb * kBlockK);
+                    }
+                    if (!g.b_mn) {
+                        tma_load_2d_2sm(&map_b, bar, db, kb * kBlockK, nb0);
+                    } else {
+                        tma_load_2d_2sm(&map_b, bar, db, nb0, kb * kBlockK);
+                        tma_load_2d_2sm(&map_b, bar, db + kSlab, nb0 + 64, kb * kBlockK);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -1109,23 +1124,27 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = make_idesc_bf16(2 * kBlockM, kBlockN, 0, 0);
+            const uint32_t idesc = make_idesc_bf16(2 * kBlockM, kBlockN, g.a_mn, g.b_mn);
+            const uint32_t a_lbo = g.a_mn ? kSlab : 16, b_lbo = g.b_mn ? kSlab : 16;
+            const uint32_t a_step = g.a_mn ? (16 * 128) >> 4 : 32 >> 4, b_step = g.b_mn ? (16 * 128) >> 4 : 32 >> 4;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            for (int unit = pair; unit < num_units; unit += num_pairs) {
+                const int split = unit / num_tiles;
+                const int kb0 = split * g.kb_per, kb1 = min(kb0 + g.kb_per, num_kb);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);             // both CTAs' epilogues drained this buffer
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kBlockN;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);                // both CTAs' TMA bytes landed
                     tc_fence_after();
-                    const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * S::kStageA), 16);
-                    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * S::kStageB), 16);
+                    const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * S::kStageA), a_lbo);
+                    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * S::kStageB), b_lbo);
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                        umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, kb > 0 || k != 0);
+                        umma_bf16_2sm(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, kb > kb0 || k != 0);
                     umma_commit_2sm(&empty_bar[stage]);                // frees the slot in both CTAs
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
@@ -1140,10 +1159,11 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int quarter = warp & 3;
         const int half = e >> 2;
         constexpr int kCols = kBlockN / 2;
-        const bool atomic = ep.atomic != 0;
+        const bool atomic = ep.atomic != 0 || g.splits > 1;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        for (int unit = pair; unit < num_units; unit += num_pairs) {
+            const int tile = unit % num_tiles;
             const int tile_n = tile % tiles_n;
             const int m0 = (tile / tiles_n) * (2 * kBlockM) + (int)rank * kBlockM, n0 = tile_n * kBlockN;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * kCols;
@@ -1176,7 +1196,7 @@ static int launch_tc2(const CUtensorMap &ma, const CUtensorMap &mb, const CUtens
         DC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
         attr_set = true;
     }
-    const int tiles = ceil_div(g.M, 2 * kBlockM) * ceil_div(g.N, 256);
+    const int tiles = ceil_div(g.M, 2 * kBlockM) * ceil_div(g.N, 256) * g.splits;
     const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads);
@@ -1211,10 +1231,16 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
     g.tma_out = 0;
     static const int split_major_env = getenv("DCAP_SPLIT_MAJOR") ? atoi(getenv("DCAP_SPLIT_MAJOR")) : 1;
     g.split_major = split_major_env;
+    // CTA-pair variant (cta_group::2, 256 x 256 tiles).  Measured (same box, A/B): greedy decoder 3.92 -> 3.70 ms
+    // per 8000 RoIs, training step 9.15 -> 8.85 ms, beam search 229 -> 215 ms.
+    static const int two_cta_env = getenv("DCAP_2CTA") ? atoi(getenv("DCAP_2CTA")) : 1;     // 0 = off, n = minimum number of pair tiles
+    const int tiles2 = ceil_div(M, 256) * ceil_div(N, 256);
+    const bool two_cta = two_cta_env != 0 && N >= 256 && tiles2 >= two_cta_env;
     if (epi == kEpiStore && ep.atomic && ep.out_f32 && !ep.out_bf16) {
         int want = split_k;
-        if (want <= 0) {                      // fill ~2 waves, keep >= 8 k-blocks per unit
-            want = (2 * sms + tiles - 1) / tiles;
+        if (want <= 0) {                      // fill ~2 waves of CTAs (CTA pairs), keep >= 8 k-blocks per unit
+            const int slots = two_cta ? sms / 2 : sms, t = two_cta ? tiles2 : tiles;
+            want = (2 * slots + t - 1) / t;
             const int cap = num_kb / 8 > 0 ? num_kb / 8 : 1;
             if (want > cap) want = cap;
         }
@@ -1229,13 +1255,8 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
     else            { if (int rc = make_tmap_bf16(&ma, A.ptr, M, K, A.ld, kBlockM)) return rc; }
     if (B.mn_major) { if (int rc = make_tmap_bf16(&mb, B.ptr, K, N, B.ld, 64)) return rc; }
     else            { if (int rc = make_tmap_bf16(&mb, B.ptr, N, K, B.ld, wide ? 256 : 128)) return rc; }
-    // CTA-pair variant (cta_group::2, 256 x 256 tiles): K-major operands, no split-K.  Measured (same box, A/B):
-    // greedy decoder 3.92 -> 3.70 ms per 8000 RoIs, training step 9.15 -> 8.85 ms, beam search 229 -> 215 ms.
-    static const int two_cta_env = getenv("DCAP_2CTA") ? atoi(getenv("DCAP_2CTA")) : 1;     // 0 = off, n = minimum number of pair tiles
-    const bool two_cta = two_cta_env != 0 && !g.a_mn && !g.b_mn && g.splits == 1 && !ep.atomic && N >= 256 &&
-                         ceil_div(M, 256) * ceil_div(N, 256) >= two_cta_env;
-    CUtensorMap mb2 = mb;
-    if (two_cta)
+    CUtensorMap mb2 = mb;                         // K-major B of the pair kernel: each CTA loads 128 of the tile's 256 rows
+    if (two_cta && !B.mn_major)
         if (int rc = make_tmap_bf16(&mb2, B.ptr, N, K, B.ld, 128)) return rc;
     if (epi == kEpiStore) {
         DC_REQUIRE(ep.out_f32 || ep.out_bf16, "gemm_bf16_tc: no output");
