@@ -90,9 +90,16 @@ __device__ __forceinline__ unsigned morton4(unsigned v) {   // spread 4 bits: ab
     return v;
 }
 
+// kSmemCache: the image's boxes and their (key, rank, level) stay in dynamic shared memory between the two
+// phases (32 B per box) instead of a global scratch round trip per record entry -- the second phase was
+// latency-bound on it (18 -> ~7 us per launch at 1000 boxes per image).
+template <bool kSmemCache>
 __global__ void __launch_bounds__(kPrepThreads) roi_prepare_kernel(const RoiPrepParams p) {
     __shared__ int s_hist[kBuckets];
     __shared__ int s_warp_sum[kPrepThreads / 32];
+    extern __shared__ float4 s_dyn[];                      // [n_boxes] boxes, then [n_boxes] int4 {key, rank, level, -}
+    float4 *s_box = s_dyn;
+    int4 *s_kr = reinterpret_cast<int4 *>(s_dyn + (kSmemCache ? p.n_boxes : 0));
     const int tid = threadIdx.x;
     const long long img = blockIdx.x;
     const int rec_len = 1 + p.ph + p.pw;
@@ -112,7 +119,8 @@ __global__ void __launch_bounds__(kPrepThreads) roi_prepare_kernel(const RoiPrep
         const unsigned ty = min(15u, (unsigned)(cy * 16.f)), tx = min(15u, (unsigned)(cx * 16.f));
         const int key = (lv - 2) * 256 + (int)((morton4(ty) << 1) | morton4(tx));
         const int rank = atomicAdd(&s_hist[key], 1);
-        p.scratch[roi] = make_int4(key, rank, lv, 0);
+        if constexpr (kSmemCache) { s_box[i] = box; s_kr[i] = make_int4(key, rank, lv, 0); }
+        else p.scratch[roi] = make_int4(key, rank, lv, 0);
     }
     __syncthreads();
     // exclusive scan of the 1024 bucket counts (one bucket per thread)
@@ -147,8 +155,8 @@ __global__ void __launch_bounds__(kPrepThreads) roi_prepare_kernel(const RoiPrep
         const int i = idx / rec_len;
         const int e = idx - i * rec_len;
         const long long roi = img * p.n_boxes + i;
-        const int4 kr = p.scratch[roi];
-        const float4 box = __ldg(reinterpret_cast<const float4 *>(p.boxes) + roi);
+        const int4 kr = kSmemCache ? s_kr[i] : p.scratch[roi];
+        const float4 box = kSmemCache ? s_box[i] : __ldg(reinterpret_cast<const float4 *>(p.boxes) + roi);
         const int lv = kr.z, li = lv - 2;
         int H, W;
         const float *base;
@@ -240,6 +248,7 @@ roi_align_stream_kernel(const RoiStreamParams p) {
     const int nwarp = blockDim.x >> 5;
     const int rec_len = 1 + p.ph + p.pw;
     const int bins = p.ph * p.pw;
+    pdl_wait();                       // launched with programmatic dependent launch right behind roi_prepare_kernel
 
     for (int spos = blockIdx.x; spos < p.total; spos += gridDim.x) {
         const int4 *rec = p.records + (long long)spos * rec_len;
@@ -348,10 +357,21 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
     pp.records = reinterpret_cast<int4 *>(ws);
     pp.scratch = reinterpret_cast<int4 *>(ws + rec_bytes);
     pp.levels = levels;
-    roi_prepare_kernel<<<n_images, kPrepThreads, 0, stream>>>(pp);
+    const size_t prep_smem = (size_t)n_boxes * 32;
+    if (prep_smem <= 160 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(roi_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            attr_set = true;
+        }
+        roi_prepare_kernel<true><<<n_images, kPrepThreads, prep_smem, stream>>>(pp);
+    } else {
+        roi_prepare_kernel<false><<<n_images, kPrepThreads, 0, stream>>>(pp);
+    }
     cudaError_t e = cudaGetLastError();
 
     if (e == cudaSuccess) {
+        PdlScope pdl;                 // the stream kernel's launch overlaps the tail of the prepare kernel
         RoiStreamParams sp;
         sp.records = pp.records;
         sp.c4 = channels / 4;
@@ -368,15 +388,15 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
         const long long mg = (long long)sm_count() * ctas;
         const int g2 = (int)(total < mg ? total : mg);
         switch (variant) {
-            case 1: roi_align_stream_kernel<4, 128, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
-            case 2: roi_align_stream_kernel<2, 64, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
-            case 3: roi_align_stream_kernel<2, 80, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
-            case 4: roi_align_stream_kernel<1, 40, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
-            case 5: roi_align_stream_kernel<2, 72, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
-            case 6: roi_align_stream_kernel<1, 48, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
-            default: roi_align_stream_kernel<4, 96, kBf16><<<g2, warps * 32, 0, stream>>>(sp); break;
+            case 1: e = launch_pdl(roi_align_stream_kernel<4, 128, kBf16>, dim3(g2), dim3(warps * 32), 0, stream, sp); break;
+            case 2: e = launch_pdl(roi_align_stream_kernel<2, 64, kBf16>, dim3(g2), dim3(warps * 32), 0, stream, sp); break;
+            case 3: e = launch_pdl(roi_align_stream_kernel<2, 80, kBf16>, dim3(g2), dim3(warps * 32), 0, stream, sp); break;
+            case 4: e = launch_pdl(roi_align_stream_kernel<1, 40, kBf16>, dim3(g2), dim3(warps * 32), 0, stream, sp); break;
+            case 5: e = launch_pdl(roi_align_stream_kernel<2, 72, kBf16>, dim3(g2), dim3(warps * 32), 0, stream, sp); break;
+            case 6: e = launch_pdl(roi_align_stream_kernel<1, 48, kBf16>, dim3(g2), dim3(warps * 32), 0, stream, sp); break;
+            default: e = launch_pdl(roi_align_stream_kernel<4, 96, kBf16>, dim3(g2), dim3(warps * 32), 0, stream, sp); break;
         }
-        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaGetLastError();
     }
     cudaFreeAsync(ws, stream);
     if (e != cudaSuccess)
