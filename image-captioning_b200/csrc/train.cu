@@ -46,7 +46,7 @@ struct TrainState {
     __nv_bfloat16 *dz1_all = nullptr, *dz2_all = nullptr;          // [T*B, 4U]  Keras block order i|f|c|o
     float *ddsum = nullptr, *dz1sum = nullptr;                     // [B, 1024] / [B, 4U] sums over time
     __nv_bfloat16 *ddsum_b = nullptr, *dz1sum_b = nullptr;
-    float *dxh2 = nullptr, *dh1p = nullptr;                        // [B, 2U] / [B, U] per-step data gradients
+    float *dxh2 = nullptr, *dh1p = nullptr;                        // [T, B, 2U] (kept per step: the two layers' chains run concurrently) / [B, U]
     float *carry1 = nullptr, *carry2 = nullptr, *dc1 = nullptr, *dc2 = nullptr;   // [B, U]
     float *dF = nullptr, *da1 = nullptr;                           // [B, F]
     __nv_bfloat16 *dzh2 = nullptr, *dzh1 = nullptr;                // [B, F] head pre-activation gradients
@@ -54,6 +54,11 @@ struct TrainState {
     float *rowloss = nullptr;                                      // [T*B]
     const __nv_bfloat16 *x0_used = nullptr;                        // bf16 RoI features the last forward consumed
     cudaEvent_t bucket_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // gradient bucket i is complete on the step's stream
+    // wavefront over the two LSTM layers: layer 1 of step t+1 and layer 2 of step t are independent (teacher forcing),
+    // so each layer's chain of short kernels runs on its own stream, linked by one event per time step
+    cudaStream_t side = nullptr;
+    std::vector<cudaEvent_t> step_ev;                              // [T] chain A -> chain B hand-over per time step
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
 };
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -63,6 +68,11 @@ void Decoder::free_train() {
         for (void *p : bf->train->owned) cudaFree(p);
         for (cudaEvent_t e : bf->train->bucket_ev)
             if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : bf->train->step_ev)
+            if (e) cudaEventDestroy(e);
+        if (bf->train->fork_ev) cudaEventDestroy(bf->train->fork_ev);
+        if (bf->train->join_ev) cudaEventDestroy(bf->train->join_ev);
+        if (bf->train->side) cudaStreamDestroy(bf->train->side);
         delete bf->train;
         bf->train = nullptr;
     }
@@ -132,7 +142,7 @@ static int train_reserve(Decoder &D, int B, int T) {
     rc |= A((void **)&t.dz1_all, 2 * R * 4 * U); rc |= A((void **)&t.dz2_all, 2 * R * 4 * U);
     rc |= A((void **)&t.ddsum, 4 * Bp * kDense); rc |= A((void **)&t.dz1sum, 4 * Bp * 4 * U);
     rc |= A((void **)&t.ddsum_b, 2 * Bp * kDense); rc |= A((void **)&t.dz1sum_b, 2 * Bp * 4 * U);
-    rc |= A((void **)&t.dxh2, 4 * Bp * 2 * U); rc |= A((void **)&t.dh1p, 4 * Bp * U);
+    rc |= A((void **)&t.dxh2, 4 * R * 2 * U); rc |= A((void **)&t.dh1p, 4 * Bp * U);
     rc |= A((void **)&t.carry1, 4 * Bp * U); rc |= A((void **)&t.carry2, 4 * Bp * U);
     rc |= A((void **)&t.dc1, 4 * Bp * U); rc |= A((void **)&t.dc2, 4 * Bp * U);
     rc |= A((void **)&t.dF, 4 * Bp * F); rc |= A((void **)&t.da1, 4 * Bp * F);
@@ -140,11 +150,16 @@ static int train_reserve(Decoder &D, int B, int T) {
     rc |= A((void **)&t.x0, 2 * Bp * Kin);
     rc |= A((void **)&t.rowloss, 4 * R);
     if (rc) { D.free_train(); return rc; }
-    for (int i = 0; i < 4; ++i)
-        if (cudaEventCreateWithFlags(&t.bucket_ev[i], cudaEventDisableTiming) != cudaSuccess) {
-            D.free_train();
-            return set_error(DC_ERR_CUDA, "event creation failed");
-        }
+    bool ev_ok = cudaStreamCreateWithFlags(&t.side, cudaStreamNonBlocking) == cudaSuccess;
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&t.fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    ev_ok = ev_ok && cudaEventCreateWithFlags(&t.join_ev, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 4 && ev_ok; ++i) ev_ok = cudaEventCreateWithFlags(&t.bucket_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    t.step_ev.assign(T, nullptr);
+    for (int i = 0; i < T && ev_ok; ++i) ev_ok = cudaEventCreateWithFlags(&t.step_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ev_ok) {
+        D.free_train();
+        return set_error(DC_ERR_CUDA, "stream / event creation failed");
+    }
     t.B = B; t.T = T;
     return DC_OK;
 }
@@ -486,6 +501,12 @@ int Decoder::train_forward(const void *feats, int kind, int B, const int32_t *gt
     gather_embedding_rows_kernel<<<(unsigned)ceil_div<long long>(R * 32, 256), 256, 0, s>>>(
         reinterpret_cast<const uint4 *>(b.emb), b.Epad / 8, t.tok_tm, R, reinterpret_cast<uint4 *>(t.X1), K1 / 8);
     DC_CHECK_LAUNCH();
+    // Wavefront: LSTM1 of step t+1 needs only LSTM1 of step t (the tokens are given), LSTM2 of step t needs LSTM1 of
+    // step t and LSTM2 of step t-1.  Chain A (LSTM1) runs on `s`, chain B (LSTM2) on the side stream one step behind;
+    // their persistent GEMMs interleave at CTA granularity and fill each other's tails (a single chain of these
+    // 1.7-wave launches leaves most SMs idle most of the time).
+    static const bool no_wave = getenv("DCAP_NO_WAVEFRONT") != nullptr;
+    cudaStream_t s2 = no_wave ? s : t.side;
     for (int st = 0; st < T; ++st) {
         __nv_bfloat16 *x1 = t.X1 + (size_t)st * B * K1, *x1n = x1 + (size_t)B * K1;
         __nv_bfloat16 *x2 = t.X2 + (size_t)st * B * 2 * U, *x2n = x2 + (size_t)B * 2 * U;
@@ -498,13 +519,21 @@ int Decoder::train_forward(const void *feats, int kind, int B, const int32_t *gt
         c1.cell_h_b = x2; c1.ld_h_b = 2 * U;
         c1.cell_gates_out = t.gates1 + (size_t)st * B * 4 * U; c1.ld_gates_out = 4 * U;
         if (int rc = gemm_bf16_tc(tc_op(x1, K1), tc_op(b.w1cat, K1), c1, B, 4 * U, K1, kEpiCell, s)) return rc;
+        if (!no_wave) {
+            DC_CHECK_CUDA(cudaEventRecord(t.step_ev[st], s));
+            DC_CHECK_CUDA(cudaStreamWaitEvent(s2, t.step_ev[st], 0));
+        }
         TcEpilogue c2;
         c2.bias = b.b2_i; c2.cell_units = U; c2.cell_tok = tok;
         c2.cell_c = t.c2 + (size_t)st * B * U; c2.cell_c_out = t.c2 + (size_t)(st + 1) * B * U;
         c2.cell_h_prev = x2 + U; c2.ld_h_prev = 2 * U;
         c2.cell_h_a = x2n + U; c2.ld_h_a = 2 * U;
         c2.cell_gates_out = t.gates2 + (size_t)st * B * 4 * U; c2.ld_gates_out = 4 * U;
-        if (int rc = gemm_bf16_tc(tc_op(x2, 2 * U), tc_op(b.w2cat, 2 * U), c2, B, 4 * U, 2 * U, kEpiCell, s)) return rc;
+        if (int rc = gemm_bf16_tc(tc_op(x2, 2 * U), tc_op(b.w2cat, 2 * U), c2, B, 4 * U, 2 * U, kEpiCell, s2)) return rc;
+    }
+    if (!no_wave) {
+        DC_CHECK_CUDA(cudaEventRecord(t.join_ev, s2));
+        DC_CHECK_CUDA(cudaStreamWaitEvent(s, t.join_ev, 0));
     }
     // h2_t of row (t, b) lives in X2 slot t+1, columns U..2U: one strided view over all T*B rows
     const __nv_bfloat16 *h2_all = t.X2 + (size_t)B * 2 * U + U;
@@ -578,26 +607,45 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     }
 
     // ---------------- backward: BPTT ----------------
+    // Layer 2's backward chain never needs layer 1 (gradients only flow downwards), so it runs on the side stream
+    // and hands dL/dh1_t (the first U columns of its per-step data gradient, kept for every t) to layer 1's chain
+    // on `s` through one event per step: the two chains of short kernels overlap.
     for (float *p : {t.carry1, t.carry2, t.dc1, t.dc2})
         DC_CHECK_CUDA(cudaMemsetAsync(p, 0, 4 * (size_t)B * U, s));
     DC_CHECK_CUDA(cudaMemsetAsync(t.dz1sum, 0, 4 * (size_t)B * 4 * U, s));
+    static const bool no_wave = getenv("DCAP_NO_WAVEFRONT") != nullptr;
+    cudaStream_t s2 = no_wave ? s : t.side;
+    if (!no_wave) {
+        DC_CHECK_CUDA(cudaEventRecord(t.fork_ev, s));                  // dh2d, zeroed carries are ready
+        DC_CHECK_CUDA(cudaStreamWaitEvent(s2, t.fork_ev, 0));
+    }
     const unsigned cb_grid = (unsigned)ceil_div<long long>((long long)B * (U / 4), 256);
-    for (int st = T - 1; st >= 0; --st) {
+    for (int st = T - 1; st >= 0; --st) {                              // chain B: layer 2
         const int32_t *tok = t.tok_tm + (size_t)st * B;
         const bool last = st == T - 1;
-        __nv_bfloat16 *dz2 = t.dz2_all + (size_t)st * B * 4 * U, *dz1 = t.dz1_all + (size_t)st * B * 4 * U;
-        DC_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(cb_grid), dim3(256), 0, s, B, U,
+        __nv_bfloat16 *dz2 = t.dz2_all + (size_t)st * B * 4 * U;
+        float *dx = t.dxh2 + (size_t)st * B * 2 * U;                   // [dh1_t | dh2_{t-1}] of this step
+        DC_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(cb_grid), dim3(256), 0, s2, B, U,
                                  (const __nv_bfloat16 *)(t.gates2 + (size_t)st * B * 4 * U), (const float *)(t.c2 + (size_t)st * B * U),
                                  (const float *)(t.c2 + (size_t)(st + 1) * B * U), tok, (const float *)(t.dh2d + (size_t)st * B * U), U,
-                                 (const float *)(last ? nullptr : t.dxh2 + U), 2 * U, t.carry2, t.dc2, dz2, (float *)nullptr));
+                                 (const float *)(last ? nullptr : dx + (size_t)B * 2 * U + U), 2 * U, t.carry2, t.dc2, dz2,
+                                 (float *)nullptr));
         {   // [dh1_t | dh2_{t-1}] = dz2 [W2 ; U2]^T
             TcEpilogue e;
-            e.out_f32 = t.dxh2; e.ld_f32 = 2 * U;
-            if (int rc = gemm_bf16_tc(tc_op(dz2, 4 * U), tc_op(b.w2cat_k, 4 * U), e, B, 2 * U, 4 * U, kEpiStore, s)) return rc;
+            e.out_f32 = dx; e.ld_f32 = 2 * U;
+            if (int rc = gemm_bf16_tc(tc_op(dz2, 4 * U), tc_op(b.w2cat_k, 4 * U), e, B, 2 * U, 4 * U, kEpiStore, s2)) return rc;
         }
+        if (!no_wave) DC_CHECK_CUDA(cudaEventRecord(t.step_ev[st], s2));
+    }
+    for (int st = T - 1; st >= 0; --st) {                              // chain A: layer 1
+        const int32_t *tok = t.tok_tm + (size_t)st * B;
+        const bool last = st == T - 1;
+        __nv_bfloat16 *dz1 = t.dz1_all + (size_t)st * B * 4 * U;
+        const float *dx = t.dxh2 + (size_t)st * B * 2 * U;
+        if (!no_wave) DC_CHECK_CUDA(cudaStreamWaitEvent(s, t.step_ev[st], 0));
         DC_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(cb_grid), dim3(256), 0, s, B, U,
                                  (const __nv_bfloat16 *)(t.gates1 + (size_t)st * B * 4 * U), (const float *)(t.c1 + (size_t)st * B * U),
-                                 (const float *)(t.c1 + (size_t)(st + 1) * B * U), tok, (const float *)t.dxh2, 2 * U,
+                                 (const float *)(t.c1 + (size_t)(st + 1) * B * U), tok, dx, 2 * U,
                                  (const float *)(last ? nullptr : t.dh1p), U, t.carry1, t.dc1, dz1, t.dz1sum));
         if (st > 0) {   // dh1_{t-1} = dz1 U1^T
             TcEpilogue e;
