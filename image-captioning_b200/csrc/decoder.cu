@@ -497,7 +497,7 @@ int Decoder::v2_predict(const void *feats, int kind, const int32_t *words, int B
     return softmax_argmax(ws.logits, cfg.vocab, B, cfg.vocab, probs, cfg.vocab, nullptr, 0, nullptr, nullptr, s);
 }
 
-int Decoder::v2_greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s) {
+int Decoder::v2_greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, const int32_t *start) {
     if (int rc = check_ready(B)) return rc;
     DC_REQUIRE(cfg.arch == DC_ARCH_V2_INJECT, "dc_decoder_v2_greedy needs a v2 inject decoder");
     DC_REQUIRE(cfg.dtype == DC_DTYPE_F32, "the v2 model is served by the fp32 path");
@@ -507,7 +507,9 @@ int Decoder::v2_greedy(const void *feats, int kind, int B, int32_t *tokens, floa
     const int P = cfg.padding, V = cfg.vocab;
     if (int rc = v2_reset(B, s)) return rc;
     if (int rc = v2_head_into_xin(feats, kind, B, s)) return rc;
-    if (int rc = fill_i32(ws.tok, B, 0, s)) return rc;          // argmax(zeros(V)) = 0 -> masked
+    if (start) {                                                 // eval_text_generation_model_v2.py:176-186: prev = [gt[0]]
+        DC_CHECK_CUDA(cudaMemcpyAsync(ws.tok, start, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, s));
+    } else if (int rc = fill_i32(ws.tok, B, 0, s)) return rc;   // argmax(zeros(V)) = 0 -> masked
     for (int t = 0; t + 1 < P; ++t) {
         // the padded window never truncates: the sequence has at most P-1 ids,
         // so consuming one new id per step equals re-running the LSTM over the whole prefix
@@ -634,6 +636,12 @@ extern "C" int dc_decoder_v2_greedy(DcDecoder *dec, const void *feats, int kind,
                                     float *probs, void *stream) {
     DC_REQUIRE(dec, "null decoder");
     return dec->impl.v2_greedy(feats, kind, B, tokens, probs, (cudaStream_t)stream);
+}
+
+extern "C" int dc_decoder_v2_greedy_from(DcDecoder *dec, const void *feats, int kind, int B, const int32_t *start,
+                                         int32_t *tokens, float *probs, void *stream) {
+    DC_REQUIRE(dec, "null decoder");
+    return dec->impl.v2_greedy(feats, kind, B, tokens, probs, (cudaStream_t)stream, start);
 }
 
 extern "C" int dc_decoder_greedy_host(DcDecoder *dec, const float *feats, int kind, int B, int32_t *tokens,

@@ -93,7 +93,7 @@ struct Decoder {
     int v2_output(int B, cudaStream_t s);
     int v2_head_into_xin(const void *feats, int kind, int B, cudaStream_t s);
     int v2_predict(const void *feats, int kind, const int32_t *words, int B, int L, float *probs, cudaStream_t s);
-    int v2_greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s);
+    int v2_greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, const int32_t *start = nullptr);
 
     // bf16 / tcgen05 path (decoder_bf16.cu)
     int refresh_bf16(bool fresh, cudaStream_t s);

@@ -612,17 +612,26 @@ class InjectModelV2(_ModelBase):
                 w.shape[1], ctypes.c_void_p(probs.data_ptr()), self._stream()))
         return probs.cpu().numpy() if was_numpy else probs
 
-    def generate(self, features, return_probs=False):
-        """The reference's greedy loop (test_score_dense_captions.py:216-225): P-1 ids per RoI."""
+    def generate(self, features, return_probs=False, start_tokens=None):
+        """The reference's greedy loop (test_score_dense_captions.py:216-225): P-1 ids per RoI, started from
+        [0] (argmax of the all-zero start vector) or, with ``start_tokens`` [N], from a given first word
+        (eval_text_generation_model_v2.py:176-186 starts from the ground-truth first word)."""
         self._ready()
         t, kind, was_numpy = self._feats_to_device(features)
         N, P, V = t.shape[0], self.config.PADDING_SIZE, self.config.VOCABULARY_SIZE
         tokens = torch.empty((N, P - 1), dtype=torch.int32, device=self.device)
         probs = torch.empty((N, P - 1, V), dtype=torch.float32, device=self.device) if return_probs else None
+        st = None
+        if start_tokens is not None:
+            st = torch.as_tensor(np.asarray(start_tokens) if not isinstance(start_tokens, torch.Tensor) else start_tokens)
+            if st.dim() != 1 or st.shape[0] != N:
+                raise ValueError("start_tokens must be [N]")
+            st = st.to(self.device).to(torch.int32).contiguous()
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.dc_decoder_v2_greedy(
-                self._h, ctypes.c_void_p(t.data_ptr()), kind, N, ctypes.c_void_p(tokens.data_ptr()),
-                ctypes.c_void_p(probs.data_ptr()) if probs is not None else None, self._stream()))
+            _lib.check(self._lib.dc_decoder_v2_greedy_from(
+                self._h, ctypes.c_void_p(t.data_ptr()), kind, N, ctypes.c_void_p(st.data_ptr()) if st is not None else None,
+                ctypes.c_void_p(tokens.data_ptr()), ctypes.c_void_p(probs.data_ptr()) if probs is not None else None,
+                self._stream()))
         if was_numpy:
             tokens = tokens.cpu().numpy()
             probs = probs.cpu().numpy() if probs is not None else None

@@ -184,6 +184,11 @@ int dc_decoder_v2_predict(DcDecoder *dec, const void *feats, int feats_kind, con
 int dc_decoder_v2_greedy(DcDecoder *dec, const void *feats, int feats_kind, int B,
                          int32_t *tokens, float *probs, void *stream);
 
+/* Same loop started from a given first word per RoI (evaluate_models/eval_text_generation_model_v2.py:176-186:
+ * prev = [gt_caption[0]]): start [B] int32 ids (device), NULL = all zeros (the loop above). */
+int dc_decoder_v2_greedy_from(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *start,
+                              int32_t *tokens, float *probs, void *stream);
+
 /* Host-buffer forms (what Keras predict callers see): HOST pointers in and out, copies inside. */
 int dc_decoder_greedy_host(DcDecoder *dec, const float *feats, int feats_kind, int B,
                            int32_t *tokens, float *probs);

@@ -383,11 +383,13 @@ def v2_inject_predict(feat, words, w, dtype=F32, return_logits=False):
     return z if return_logits else softmax(z)
 
 
-def greedy_v2(feat, w, P, dtype=F32):
+def greedy_v2(feat, w, P, dtype=F32, start=None):
     """test_score_dense_captions.py:216-225: start [argmax(zeros)] = [0]; P-1 predicts; the
-    padded window keeps the LAST P ids.  Returns (tokens [B,P-1], probs [B,P-1,V])."""
+    padded window keeps the LAST P ids.  ``start`` [B]: first word per RoI instead of 0
+    (eval_text_generation_model_v2.py:176-186: prev = [gt[0]]).
+    Returns (tokens [B,P-1], probs [B,P-1,V])."""
     B = feat.shape[0]
-    seqs = [[0] for _ in range(B)]
+    seqs = [[0 if start is None else int(start[i])] for i in range(B)]
     toks, outs = [], []
     for _ in range(P - 1):
         p = v2_inject_predict(feat, pad_sequences_pre(seqs, P), w, dtype)

@@ -178,6 +178,27 @@ def test_v2_inject_predict_and_greedy():
         pkg.build_model((7, 7, C), (P,), cfg, units, inject=False)
 
 
+def test_v2_greedy_from_ground_truth_first_word():
+    """eval_text_generation_model_v2.py:176-186 starts the loop from the caption's first word."""
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(27)
+    V, E, units, C, P, B = 300, 20, 64, 8, 8, 7
+    w = synth.synth_weights_v2(rng, V=V, E=E, units=units, C=C)
+    cfg = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], 1, P)
+    m = pkg.build_model((7, 7, C), (P,), cfg, units, inject=True)
+    m.set_weights(w)
+    feat = rng.standard_normal((B, 7, 7, C)).astype(np.float32)
+    start = rng.integers(1, V, B).astype(np.int32)
+    start[2] = 0                                            # a masked first word behaves like the default loop
+    tok_want, p_want = dec.greedy_v2(feat, w, P, start=start)
+    tok, probs = m.generate(feat, return_probs=True, start_tokens=start)
+    assert np.array_equal(tok, tok_want)
+    np.testing.assert_allclose(probs, p_want, rtol=PROB_RTOL, atol=PROB_ATOL)
+    assert np.array_equal(m.generate(feat)[2], tok[2])
+    with pytest.raises(ValueError):
+        m.generate(feat, start_tokens=start[:3])
+
+
 def test_bf16_greedy_agreement_with_fp32_oracle():
     """north_star bar for the bf16 path: log-probabilities within 2e-2 absolute of the fp32 model
     (on positions fed the same prefix) and >= 99 % greedy-token agreement."""
