@@ -325,8 +325,13 @@ class RoiCaptionModel(_ModelBase):
         (evaluate_models/eval_text_generation_model.py:141).  As in Keras the sample count must be
         a multiple of config.BATCH_SIZE (the graph bakes the batch in, :211)."""
         if self.mode != "inference":
-            raise RuntimeError("predict() on the training graph needs [features, gt_captions]; "
-                               "use predict_teacher_forced")
+            # the training graph's inputs are [features, gt_captions] (text_generation_model.py:264-277)
+            if not isinstance(x, (list, tuple)) or len(x) != 2:
+                raise ValueError("the training graph predicts from [features, gt_captions]")
+            if len(x[0]) % self.config.BATCH_SIZE != 0:
+                raise ValueError("number of samples %d is not a multiple of config.BATCH_SIZE %d"
+                                 % (len(x[0]), self.config.BATCH_SIZE))
+            return self.predict_teacher_forced(x)
         n = len(x)
         if n % self.config.BATCH_SIZE != 0:
             raise ValueError("number of samples %d is not a multiple of config.BATCH_SIZE %d"

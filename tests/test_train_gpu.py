@@ -61,6 +61,8 @@ def test_teacher_forced_forward_matches_oracle():
     assert (got.argmax(-1) == want.argmax(-1)).mean() >= 0.99
     # masked step (token 0) re-emits the previous distribution
     np.testing.assert_allclose(got[1, 2], got[1, 1], rtol=1e-6)
+    # Keras surface: predict([features, gt_captions]) on the training graph is the same thing
+    assert np.array_equal(m.predict([feat, gt], batch_size=B), got)
 
 
 def test_loss_and_gradients_match_fp64_oracle():
