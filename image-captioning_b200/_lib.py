@@ -42,6 +42,8 @@ SIGNATURES = {
     "dc_pyramid_roi_align_host_f32": (ctypes.c_int, [c_void, c_void * 4, ctypes.c_int * 4,
                                                      ctypes.c_int * 4] + [ctypes.c_int] * 7 +
                                       [c_void, c_void]),
+    "dc_pyramid_roi_align_backward_f32": (ctypes.c_int, [c_void, c_void, c_void * 4, ctypes.c_int * 4, ctypes.c_int * 4] +
+                                          [ctypes.c_int] * 7 + [c_void]),
     "dc_decoder_create": (ctypes.c_int, [c_void, c_void]),
     "dc_decoder_destroy": (ctypes.c_int, [c_void]),
     "dc_decoder_weight_count": (ctypes.c_int, [c_void]),

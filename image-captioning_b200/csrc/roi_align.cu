@@ -298,6 +298,53 @@ roi_align_stream_kernel(const RoiStreamParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward: gradient w.r.t. the feature maps, the mirror image of the gather.
+// TF's CropAndResizeGradImage per in-range sample: dtop = (1-ly)*g, dbottom = ly*g,
+// d[top,left] += (1-lx)*dtop, d[top,right] += lx*dtop, likewise for the bottom row; boxes get no gradient
+// (tf.stop_gradient, modified_dense_model.py:379-380).  Same records / locality order / warp mapping as the
+// forward kernel; the scatter uses 128-bit vector reductions (red.global.add.v4.f32), so the taps that
+// overlapping RoIs share are combined in L2.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add4(float4 *p, float s, const float4 &g) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(s * g.x), "f"(s * g.y), "f"(s * g.z), "f"(s * g.w)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(224) roi_align_backward_kernel(const RoiStreamParams p, const float4 *__restrict__ grad_out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarp = blockDim.x >> 5;
+    const int rec_len = 1 + p.ph + p.pw;
+    const int bins = p.ph * p.pw;
+    pdl_wait();
+    for (int spos = blockIdx.x; spos < p.total; spos += gridDim.x) {
+        const int4 *rec = p.records + (long long)spos * rec_len;
+        const int4 hd = __ldg(rec);
+        float4 *fm = reinterpret_cast<float4 *>(((unsigned long long)(unsigned)hd.x) | ((unsigned long long)(unsigned)hd.y << 32));
+        const long long g_roi = (long long)hd.z * bins * p.c4;
+        for (int by = warp; by < p.ph; by += nwarp) {
+            const int4 ye = __ldg(rec + 1 + by);
+            if (!ye.w) continue;                                       // whole sample row out of range: no gradient
+            const float ly = __int_as_float(ye.z);
+            float4 *row_t = fm + ye.x, *row_b = fm + ye.y;
+            for (int bx = 0; bx < p.pw; ++bx) {
+                const int4 xe = __ldg(rec + 1 + p.ph + bx);
+                if (!xe.w) continue;
+                const float lx = __int_as_float(xe.z);
+                const float wt = __fsub_rn(1.f, ly), wl = __fsub_rn(1.f, lx);
+                for (int c = lane; c < p.c4; c += 32) {
+                    const float4 g = __ldg(grad_out + g_roi + ((long long)by * p.pw + bx) * p.c4 + c);
+                    red_add4(row_t + xe.x + c, __fmul_rn(wl, wt), g);
+                    red_add4(row_t + xe.y + c, __fmul_rn(lx, wt), g);
+                    red_add4(row_b + xe.x + c, __fmul_rn(wl, ly), g);
+                    red_add4(row_b + xe.y + c, __fmul_rn(lx, ly), g);
+                }
+            }
+        }
+    }
+}
+
 static int validate(const float *boxes, const float *const fmaps[4], const int fm_h[4],
                     const int fm_w[4], int n_images, int n_boxes, int channels, int pool_h,
                     int pool_w, int img_h, int img_w, const void *out) {
@@ -441,6 +488,51 @@ extern "C" int dc_pyramid_roi_align_bf16out(const float *boxes, const float *con
                "bf16 output needs channels %% 8 == 0");
     return launch<true>(boxes, fmaps, fm_h, fm_w, n_images, n_boxes, channels, pool_h, pool_w,
                         img_h, img_w, out, levels, (cudaStream_t)stream);
+}
+
+extern "C" int dc_pyramid_roi_align_backward_f32(const float *boxes, const float *grad_out, float *const d_fmaps[4],
+                                                 const int fm_h[4], const int fm_w[4], int n_images, int n_boxes,
+                                                 int channels, int pool_h, int pool_w, int img_h, int img_w, void *stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const float *maps[4] = {d_fmaps ? d_fmaps[0] : nullptr, d_fmaps ? d_fmaps[1] : nullptr, d_fmaps ? d_fmaps[2] : nullptr,
+                            d_fmaps ? d_fmaps[3] : nullptr};
+    int rc = validate(boxes, d_fmaps ? maps : nullptr, fm_h, fm_w, n_images, n_boxes, channels, pool_h, pool_w, img_h, img_w, grad_out);
+    if (rc != DC_OK) return rc;
+    const long long total = (long long)n_images * n_boxes;
+    if (total == 0) return DC_OK;
+    DC_REQUIRE(total < (1ll << 31), "n_images*n_boxes must fit in int32");
+    const int rec_len = 1 + pool_h + pool_w;
+    const size_t rec_bytes = sizeof(int4) * (size_t)total * rec_len;
+    char *ws = nullptr;
+    DC_CHECK_CUDA(cudaMallocAsync((void **)&ws, rec_bytes + sizeof(int4) * (size_t)total, stream));
+    RoiPrepParams pp;
+    pp.boxes = boxes;
+    for (int l = 0; l < 4; ++l) { pp.fm[l] = maps[l]; pp.fm_h[l] = fm_h[l]; pp.fm_w[l] = fm_w[l]; }
+    pp.n_boxes = n_boxes; pp.c4 = channels / 4; pp.ph = pool_h; pp.pw = pool_w;
+    pp.denom = level_denominator(img_h, img_w);
+    pp.records = reinterpret_cast<int4 *>(ws);
+    pp.scratch = reinterpret_cast<int4 *>(ws + rec_bytes);
+    pp.levels = nullptr;
+    const size_t prep_smem = (size_t)n_boxes * 32;
+    if (prep_smem <= 160 * 1024) {
+        cudaFuncSetAttribute(roi_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        roi_prepare_kernel<true><<<n_images, kPrepThreads, prep_smem, stream>>>(pp);
+    } else {
+        roi_prepare_kernel<false><<<n_images, kPrepThreads, 0, stream>>>(pp);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        RoiStreamParams sp;
+        sp.records = pp.records; sp.c4 = channels / 4; sp.parts = (sp.c4 + 31) / 32; sp.ph = pool_h; sp.pw = pool_w;
+        sp.out = nullptr; sp.total = (int)total;
+        const int warps = pool_h < 7 ? pool_h : 7;
+        const long long mg = (long long)sm_count() * 8;
+        roi_align_backward_kernel<<<(int)(total < mg ? total : mg), warps * 32, 0, stream>>>(sp, reinterpret_cast<const float4 *>(grad_out));
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(ws, stream);
+    if (e != cudaSuccess) return set_error(DC_ERR_CUDA, "roi align backward launch failed: %s", cudaGetErrorString(e));
+    return DC_OK;
 }
 
 // Host-buffer form: image-by-image pipeline.  Stream A uploads image i's four maps, stream B runs

@@ -99,6 +99,56 @@ def pyramid_roi_align(boxes, feature_maps, pool_shape, image_shape, out_dtype=to
     return (out, levels) if return_levels else out
 
 
+def pyramid_roi_align_backward(boxes, grad_out, fm_shapes, pool_shape, image_shape, grads=None):
+    """Gradient of the layer with respect to its four feature maps (the boxes get none: the reference
+    wraps them in tf.stop_gradient, modified_dense_model.py:379-380).  boxes [B,N,4], grad_out
+    [B*N, ph, pw, C] CUDA fp32; fm_shapes = [(H_l, W_l)] * 4.  Returns 4 tensors [B, H_l, W_l, C]
+    (``grads``: existing tensors to ACCUMULATE into)."""
+    lib = _lib.load()
+    if not all(isinstance(t, torch.Tensor) and t.is_cuda for t in (boxes, grad_out)):
+        raise TypeError("pyramid_roi_align_backward expects CUDA tensors (no CPU fallback)")
+    dev = boxes.device
+    boxes = boxes.detach().to(torch.float32).contiguous()
+    B, N = boxes.shape[:2]
+    ph, pw = int(pool_shape[0]), int(pool_shape[1])
+    g = grad_out.detach().to(torch.float32).contiguous()
+    C = g.shape[-1]
+    if g.numel() != B * N * ph * pw * C or len(fm_shapes) != 4:
+        raise ValueError("grad_out must be [B*N, ph, pw, C] and fm_shapes four (H, W) pairs")
+    if grads is None:
+        grads = [torch.zeros((B, int(h), int(w), C), dtype=torch.float32, device=dev) for h, w in fm_shapes]
+    ptrs = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in grads])
+    hs = (ctypes.c_int * 4)(*[int(h) for h, _ in fm_shapes])
+    ws = (ctypes.c_int * 4)(*[int(w) for _, w in fm_shapes])
+    with torch.cuda.device(dev):
+        _lib.check(lib.dc_pyramid_roi_align_backward_f32(_as_ptr(boxes), _as_ptr(g), ptrs, hs, ws, B, N, C, ph, pw,
+                                                         int(image_shape[0]), int(image_shape[1]), _stream_ptr(dev)))
+    return grads
+
+
+class _PyramidROIAlignFn(torch.autograd.Function):
+    """autograd bridge: forward = dc_pyramid_roi_align_f32, backward = dc_pyramid_roi_align_backward_f32."""
+
+    @staticmethod
+    def forward(ctx, boxes, pool_shape, image_shape, *fms):
+        ctx.save_for_backward(boxes)
+        ctx.meta = (tuple(pool_shape), tuple(image_shape), [tuple(f.shape[1:3]) for f in fms])
+        return pyramid_roi_align(boxes, list(fms), pool_shape, image_shape)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (boxes,) = ctx.saved_tensors
+        pool, ishape, shapes = ctx.meta
+        grads = pyramid_roi_align_backward(boxes, grad_out, shapes, pool, ishape)
+        return (None, None, None) + tuple(grads)
+
+
+def pyramid_roi_align_autograd(boxes, feature_maps, pool_shape, image_shape):
+    """Differentiable (w.r.t. the feature maps) form of pyramid_roi_align for torch users -- what the joint
+    model of dense_img_cap/dense_model.py:738-755 needs to train through the layer."""
+    return _PyramidROIAlignFn.apply(boxes, tuple(pool_shape), tuple(image_shape), *feature_maps)
+
+
 class PyramidROIAlign(object):
     """Implements ROI Pooling on multiple levels of the feature pyramid.
 

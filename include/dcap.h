@@ -85,6 +85,18 @@ int dc_pyramid_roi_align_bf16out(const float *boxes, const float *const fmaps[4]
                                  uint16_t *out, int32_t *levels, void *stream);
 
 /*
+ * Gradient of PyramidROIAlign with respect to the four feature maps (TF CropAndResizeGradImage summed over the
+ * per-level crops; the boxes receive no gradient: tf.stop_gradient, evaluate_models/modified_dense_model.py:379-380).
+ * This is what the joint model of dense_img_cap/dense_model.py:738-755 back-propagates through the layer.
+ *   grad_out  [n_images*n_boxes, pool_h, pool_w, channels] fp32 (device), (image, box) order
+ *   d_fmaps   HOST array of 4 DEVICE pointers [n_images, fm_h[l], fm_w[l], channels] fp32, ACCUMULATED into
+ *             (the caller zeroes them or passes running sums); fp32 atomic accumulation, order not deterministic
+ */
+int dc_pyramid_roi_align_backward_f32(const float *boxes, const float *grad_out, float *const d_fmaps[4],
+                                      const int fm_h[4], const int fm_w[4], int n_images, int n_boxes,
+                                      int channels, int pool_h, int pool_w, int img_h, int img_w, void *stream);
+
+/*
  * Host-buffer form of dc_pyramid_roi_align_f32 (what `generate_features` /
  * `keras_model.predict` callers see, evaluate_models/generate_one_roi_features.py:69-76):
  * all pointers are HOST memory (pinned memory makes the copies asynchronous); the call stages the

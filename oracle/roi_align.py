@@ -262,3 +262,50 @@ def unique_tap_pixels(boxes, fm_shapes, pool_shape, image_shape):
         key = (ii[ok] * H + yy[ok]) * W + xx[ok]
         total += np.unique(key).size
     return int(total)
+
+
+# ----------------------------------------------------------------------------------------
+# backward: gradient of PyramidROIAlign w.r.t. the feature maps
+# ----------------------------------------------------------------------------------------
+
+def pyramid_roi_align_backward(boxes, grad_out, fm_shapes, pool_shape, image_shape, dtype=np.float64):
+    """Restates TF's CropAndResizeGradImage for the layer's 4 per-level crops (the boxes get no gradient:
+    tf.stop_gradient, modified_dense_model.py:379-380).  For every in-range sample
+        dtop = (1 - y_lerp) * g,  dbottom = y_lerp * g
+        d[top, left] += (1 - x_lerp) * dtop,  d[top, right] += x_lerp * dtop   (same for bottom)
+    boxes [B,N,4]; grad_out [B*N, ph, pw, C] in (image, box) order; fm_shapes = [(H_l, W_l)] * 4.
+    Returns 4 arrays [B, H_l, W_l, C] (accumulated in `dtype`; the CUDA kernel accumulates with fp32
+    atomics, so parity is to ~1e-5 relative, not bit-exact)."""
+    B, N = boxes.shape[:2]
+    ph, pw = pool_shape
+    C = grad_out.shape[-1]
+    levels = fpn_level(boxes, image_shape)
+    grads = [np.zeros((B, h, w, C), dtype) for h, w in fm_shapes]
+    g = grad_out.reshape(B, N, ph, pw, C)
+    for b in range(B):
+        for n in range(N):
+            li = int(levels[b, n]) - 2
+            H, W = fm_shapes[li]
+            y1, x1, y2, x2 = [F32(v) for v in boxes[b, n]]
+            Hm1, Wm1 = F32(H - 1), F32(W - 1)
+            hs = ((y2 - y1) * Hm1) / F32(ph - 1) if ph > 1 else F32(0)
+            ws = ((x2 - x1) * Wm1) / F32(pw - 1) if pw > 1 else F32(0)
+            for iy in range(ph):
+                in_y = y1 * Hm1 + F32(iy) * hs if ph > 1 else F32(0.5) * (y1 + y2) * Hm1
+                if not (in_y >= 0 and in_y <= Hm1):
+                    continue
+                t, bo = int(np.floor(in_y)), int(np.ceil(in_y))
+                ly = F32(in_y - F32(np.floor(in_y)))
+                for ix in range(pw):
+                    in_x = x1 * Wm1 + F32(ix) * ws if pw > 1 else F32(0.5) * (x1 + x2) * Wm1
+                    if not (in_x >= 0 and in_x <= Wm1):
+                        continue
+                    l, r = int(np.floor(in_x)), int(np.ceil(in_x))
+                    lx = F32(in_x - F32(np.floor(in_x)))
+                    gv = g[b, n, iy, ix].astype(dtype)
+                    dtop, dbot = (1 - dtype(ly)) * gv, dtype(ly) * gv
+                    grads[li][b, t, l] += (1 - dtype(lx)) * dtop
+                    grads[li][b, t, r] += dtype(lx) * dtop
+                    grads[li][b, bo, l] += (1 - dtype(lx)) * dbot
+                    grads[li][b, bo, r] += dtype(lx) * dbot
+    return grads

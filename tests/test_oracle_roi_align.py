@@ -144,3 +144,19 @@ def test_unique_tap_pixels_small():
     assert ra.unique_tap_pixels(boxes, fm_shapes, (7, 7), (1024, 1024, 3)) == 1
     boxes[0, 1] = [0, 0, 1, 1]                                    # full image -> P5 (1x1 map)
     assert ra.unique_tap_pixels(boxes, fm_shapes, (7, 7), (1024, 1024, 3)) == 2
+
+
+def test_backward_oracle_is_the_adjoint_of_the_forward():
+    """<g, align(F)> == <backward(g), F>: the restated CropAndResizeGradImage is the transpose of the gather."""
+    rng = np.random.default_rng(5)
+    B, N, C = 1, 12, 4
+    from image_captioning_b200 import synth
+    boxes = synth.synth_boxes(rng, B, N, 1024.0)
+    shapes = [(16 >> i, 16 >> i) for i in range(4)]
+    fms = [rng.standard_normal((B, h, w, C)).astype(np.float32) for h, w in shapes]
+    g = rng.standard_normal((B * N, 7, 7, C)).astype(np.float32)
+    out, _ = ra.pyramid_roi_align(boxes, fms, (7, 7), (1024, 1024, 3))
+    grads = ra.pyramid_roi_align_backward(boxes, g, shapes, (7, 7), (1024, 1024, 3))
+    lhs = float((out[0].astype(np.float64) * g).sum())
+    rhs = float(sum((gr * f.astype(np.float64)).sum() for gr, f in zip(grads, fms)))
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))

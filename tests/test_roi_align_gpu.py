@@ -193,3 +193,34 @@ def test_full_size_cfg2_permutation_padding_and_bf16_properties():
     # (6) bf16 output = round-to-nearest-even of the fp32 output
     out_b = pkg.pyramid_roi_align(tb, fms, (7, 7), (1024, 1024, 3), out_dtype=torch.bfloat16)
     assert torch.equal(out_b, out.to(torch.bfloat16))
+
+
+def test_backward_matches_oracle_and_autograd():
+    """Gradient w.r.t. the feature maps against the fp64 oracle restatement of TF's
+    CropAndResizeGradImage, and through torch autograd: <grad_out, align(F)> is linear in F, so its gradient
+    is exactly the backward of grad_out."""
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(91)
+    B, N, C = 2, 60, 16
+    boxes = synth.synth_boxes(rng, B, N, 1024.0)
+    boxes[0, 5] = [0.9, 0.9, 1.2, 1.3]                     # samples outside the map: no gradient from them
+    shapes = [(32 >> i, 32 >> i) for i in range(4)]
+    fms = [rng.standard_normal((B, h, w, C)).astype(np.float32) for h, w in shapes]
+    gout = rng.standard_normal((B * N, 7, 7, C)).astype(np.float32)
+    want = ra.pyramid_roi_align_backward(boxes, gout, shapes, (7, 7), (1024, 1024, 3))
+    tb, tg = torch.from_numpy(boxes).cuda(), torch.from_numpy(gout).cuda()
+    got = pkg.pyramid_roi_align_backward(tb, tg, shapes, (7, 7), (1024, 1024, 3))
+    for g, w in zip(got, want):
+        scale = max(float(np.abs(w).max()), 1e-6)
+        np.testing.assert_allclose(g.cpu().numpy(), w, rtol=1e-5, atol=1e-5 * scale)
+    # accumulate-into semantics
+    again = pkg.pyramid_roi_align_backward(tb, tg, shapes, (7, 7), (1024, 1024, 3), grads=[g.clone() for g in got])
+    for a, g in zip(again, got):
+        torch.testing.assert_close(a, 2 * g, rtol=1e-5, atol=1e-5)
+    # autograd bridge
+    tf = [torch.from_numpy(f).cuda().requires_grad_(True) for f in fms]
+    out = pkg.pyramid_roi_align_autograd(tb, tf, (7, 7), (1024, 1024, 3))
+    (out * tg).sum().backward()
+    for f, w in zip(tf, want):
+        scale = max(float(np.abs(w).max()), 1e-6)
+        np.testing.assert_allclose(f.grad.cpu().numpy(), w, rtol=1e-5, atol=1e-5 * scale)
