@@ -429,12 +429,6 @@ int Decoder::ensure_rep(int R) {
 // ------------------------------------------------------------------------------------------
 // v2 inject
 // ------------------------------------------------------------------------------------------
-__global__ void token_column_kernel(const int32_t *__restrict__ words, int rows, int L, int col,
-                                    int32_t *__restrict__ tok) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < rows) tok[r] = words[(long long)r * L + col];
-}
-
 int Decoder::v2_reset(int B, cudaStream_t s) {
     const size_t E = cfg.embed, Wu = cfg.word_units, F = cfg.feat;
     DC_CHECK_CUDA(cudaMemsetAsync(ws.xh1, 0, sizeof(float) * B * (E + Wu), s));
@@ -481,16 +475,15 @@ int Decoder::v2_predict(const void *feats, int kind, const int32_t *words, int B
                         cudaStream_t s) {
     if (int rc = check_ready(B)) return rc;
     DC_REQUIRE(cfg.arch == DC_ARCH_V2_INJECT, "dc_decoder_v2_predict needs a v2 inject decoder");
-    DC_REQUIRE(cfg.dtype == DC_DTYPE_F32, "the v2 model is served by the fp32 path");
     DC_REQUIRE(L >= 0, "negative sequence length");
     if (B == 0) return DC_OK;
     DC_REQUIRE(feats && probs && (words || L == 0), "null pointer argument");
     if (int rc = reserve(B)) return rc;
+    if (cfg.dtype == DC_DTYPE_BF16) return v2_predict_bf16(feats, kind, words, B, L, probs, s);
     if (int rc = v2_reset(B, s)) return rc;
     if (int rc = v2_head_into_xin(feats, kind, B, s)) return rc;
     for (int t = 0; t < L; ++t) {
-        token_column_kernel<<<ceil_div(B, 256), 256, 0, s>>>(words, B, L, t, ws.tok);
-        DC_CHECK_LAUNCH();
+        if (int rc = token_column(words, B, L, t, ws.tok, s)) return rc;
         if (int rc = v2_word_step(B, s)) return rc;
     }
     if (int rc = v2_output(B, s)) return rc;
@@ -500,10 +493,10 @@ int Decoder::v2_predict(const void *feats, int kind, const int32_t *words, int B
 int Decoder::v2_greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, const int32_t *start) {
     if (int rc = check_ready(B)) return rc;
     DC_REQUIRE(cfg.arch == DC_ARCH_V2_INJECT, "dc_decoder_v2_greedy needs a v2 inject decoder");
-    DC_REQUIRE(cfg.dtype == DC_DTYPE_F32, "the v2 model is served by the fp32 path");
     if (B == 0) return DC_OK;
     DC_REQUIRE(feats && tokens, "null pointer argument");
     if (int rc = reserve(B)) return rc;
+    if (cfg.dtype == DC_DTYPE_BF16) return v2_greedy_bf16(feats, kind, B, tokens, probs, s, start);
     const int P = cfg.padding, V = cfg.vocab;
     if (int rc = v2_reset(B, s)) return rc;
     if (int rc = v2_head_into_xin(feats, kind, B, s)) return rc;
@@ -537,9 +530,9 @@ extern "C" int dc_decoder_create(const DcDecoderConfig *cfg, DcDecoder **out) {
                cfg->channels > 0 && cfg->padding > 0, "non-positive decoder dimension");
     DC_REQUIRE(cfg->arch == DC_ARCH_V1 || cfg->word_units > 0, "v2 needs word_units > 0");
     if (cfg->dtype == DC_DTYPE_BF16) {
-        DC_REQUIRE(cfg->arch == DC_ARCH_V1, "bf16 serves the v1 decoder only");
         DC_REQUIRE(cfg->units % 64 == 0 && cfg->feat % 64 == 0 && (cfg->pool * cfg->pool * cfg->channels) % 64 == 0,
                    "bf16 path needs units, feat and pool*pool*channels to be multiples of 64");
+        DC_REQUIRE(cfg->arch == DC_ARCH_V1 || cfg->word_units % 64 == 0, "bf16 v2 path needs word_units %% 64 == 0");
     }
     int dev = 0;
     DC_CHECK_CUDA(cudaGetDevice(&dev));

@@ -105,6 +105,11 @@ struct Decoder {
     int greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s, float *scores = nullptr);
     int greedy_bf16_graphed(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s);
     void drop_graphs();
+    int v2_begin_bf16(const void *feats, int kind, int B, cudaStream_t s);
+    int v2_word_step_bf16(int B, bool gather, cudaStream_t s);
+    int v2_image_step_bf16(int B, cudaStream_t s);
+    int v2_predict_bf16(const void *feats, int kind, const int32_t *words, int B, int L, float *probs, cudaStream_t s);
+    int v2_greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, const int32_t *start);
     int beam_bf16(const void *feats, int kind, int B, int k, int32_t *tokens, double *scores, cudaStream_t s);
     void free_bf16();
 

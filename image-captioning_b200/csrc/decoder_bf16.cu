@@ -74,9 +74,41 @@ int Decoder::refresh_bf16(bool fresh, cudaStream_t s) {
     const int F = cfg.feat, E = cfg.embed, U = cfg.units, V = cfg.vocab;
     const int Kin = cfg.pool * cfg.pool * cfg.channels;
     b.Epad = round_up(E, 64);
-    const int K1 = b.Epad + U;
     auto A16 = [&](__nv_bfloat16 **p, size_t n) { return dev_alloc((void **)p, 2 * n, owned); };
     int rc = 0;
+    if (cfg.arch == DC_ARCH_V2_INJECT) {
+        // word LSTM(Wu) on [emb | h], image LSTM(U) on [head | word vector] (one step from the zero state, so its
+        // recurrent kernel never contributes), Dense(V)
+        const int Wu = cfg.word_units, Kw = b.Epad + Wu;
+        if (fresh) {
+            rc |= A16(&b.w_head1, (size_t)F * Kin); rc |= A16(&b.w_head2, (size_t)F * F);
+            rc |= A16(&b.v2_w1cat, (size_t)4 * Wu * Kw); rc |= A16(&b.v2_wimg, (size_t)4 * U * (F + Wu));
+            rc |= A16(&b.v2_wd, (size_t)V * U); rc |= A16(&b.emb, (size_t)V * b.Epad);
+            rc |= dev_alloc((void **)&b.v2_bw, sizeof(float) * 4 * Wu, owned);
+            rc |= dev_alloc((void **)&b.v2_bimg, sizeof(float) * 4 * U, owned);
+            if (rc) return rc;
+            DC_CHECK_CUDA(cudaMemsetAsync(b.v2_w1cat, 0, 2 * (size_t)4 * Wu * Kw, s));
+        }
+        if (emb_dirty) {
+            emb_dirty = false;
+            DC_CHECK_CUDA(cudaMemsetAsync(b.emb, 0, 2 * (size_t)V * b.Epad, s));
+            pad_rows_bf16_kernel<<<(unsigned)ceil_div<long long>((long long)V * E, 256), 256, 0, s>>>(
+                W("imgcap_embedding_layer/embeddings"), V, E, b.emb, b.Epad);
+            DC_CHECK_LAUNCH();
+        }
+        rc |= build_kmajor(W("mrcnn_class_conv1/kernel"), F, 0, Kin, F, 0, b.w_head1, Kin, 0, s);
+        rc |= build_kmajor(W("mrcnn_class_conv2/kernel"), F, 0, F, F, 0, b.w_head2, F, 0, s);
+        rc |= build_kmajor(W("lstm_1/kernel"), 4 * Wu, 0, E, 4 * Wu, Wu, b.v2_w1cat, Kw, 0, s);
+        rc |= build_kmajor(W("lstm_1/recurrent_kernel"), 4 * Wu, 0, Wu, 4 * Wu, Wu, b.v2_w1cat, Kw, b.Epad, s);
+        rc |= build_kmajor(W("imgcap_lstm/kernel"), 4 * U, 0, F + Wu, 4 * U, U, b.v2_wimg, F + Wu, 0, s);
+        rc |= build_kmajor(W("imgcap_d1/kernel"), V, 0, U, V, 0, b.v2_wd, U, 0, s);
+        if (rc) return rc;
+        interleave_bias_kernel<<<ceil_div(4 * Wu, 256), 256, 0, s>>>(W("lstm_1/bias"), Wu, b.v2_bw);
+        interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm/bias"), U, b.v2_bimg);
+        DC_CHECK_LAUNCH();
+        return DC_OK;
+    }
+    const int K1 = b.Epad + U;
     if (fresh) {
         rc |= A16(&b.w_head1, (size_t)F * Kin); rc |= A16(&b.w_head2, (size_t)F * F);
         rc |= A16(&b.w1cat, (size_t)4 * U * K1); rc |= A16(&b.w1f, (size_t)4 * U * F);
@@ -122,6 +154,17 @@ int Decoder::reserve_bf16(size_t R) {
     const size_t K1 = b.Epad + U;
     auto A16 = [&](__nv_bfloat16 **p, size_t n) { return dev_alloc((void **)p, 2 * n, ws_owned); };
     int rc = 0;
+    if (cfg.arch == DC_ARCH_V2_INJECT) {
+        const size_t Wu = cfg.word_units;
+        rc |= A16(&b.roi, R * Kin); rc |= A16(&b.a1, R * F); rc |= A16(&b.Fb, R * F);
+        for (int i = 0; i < 2; ++i) rc |= A16(&b.X1[i], R * (b.Epad + Wu));
+        rc |= A16(&b.v2_xin, R * (F + Wu)); rc |= A16(&b.v2_hb, R * U);
+        rc |= dev_alloc((void **)&b.v2_czero, sizeof(float) * R * U, ws_owned);
+        rc |= dev_alloc((void **)&b.partial, sizeof(float) * 4 * R * gemm_tc_argmax_tiles(cfg.vocab), ws_owned);
+        if (rc) return rc;
+        DC_CHECK_CUDA(cudaMemset(b.v2_czero, 0, sizeof(float) * R * U));
+        return DC_OK;
+    }
     rc |= A16(&b.roi, R * Kin); rc |= A16(&b.a1, R * F); rc |= A16(&b.Fb, R * F); rc |= A16(&b.d, R * kDense);
     for (int i = 0; i < 2; ++i) { rc |= A16(&b.X1[i], R * K1); rc |= A16(&b.X2[i], R * 2 * U); }
     rc |= dev_alloc((void **)&b.partial, sizeof(float) * 4 * R * gemm_tc_argmax_tiles(cfg.vocab), ws_owned);
@@ -380,6 +423,95 @@ int Decoder::beam_bf16(const void *feats, int kind, int B, int k, int32_t *token
     }
     DC_CHECK_CUDA(cudaMemcpyAsync(tokens, hist, sizeof(int32_t) * (size_t)R * P, cudaMemcpyDeviceToDevice, s));
     DC_CHECK_CUDA(cudaMemcpyAsync(scores, sc, sizeof(double) * R, cudaMemcpyDeviceToDevice, s));
+    return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// v2 inject model (text_generation_model_v2.py:140-166) on the tensor-core path
+// ------------------------------------------------------------------------------------------------
+int Decoder::v2_begin_bf16(const void *feats, int kind, int B, cudaStream_t s) {
+    Bf16State &b = *bf;
+    const size_t F = cfg.feat, Wu = cfg.word_units, Kw = b.Epad + Wu;
+    if (int rc = head(feats, kind, B, ws.F, s)) return rc;
+    // xin = [head feature | word vector]: the word-vector half starts at zero (all-masked prefix)
+    DC_CHECK_CUDA(cudaMemsetAsync(b.v2_xin, 0, 2 * (size_t)B * (F + Wu), s));
+    pad_rows_bf16_kernel<<<(unsigned)ceil_div<long long>((long long)B * F, 256), 256, 0, s>>>(ws.F, B, (int)F, b.v2_xin, (int)(F + Wu));
+    DC_CHECK_LAUNCH();
+    for (int i = 0; i < 2; ++i) DC_CHECK_CUDA(cudaMemsetAsync(b.X1[i], 0, 2 * (size_t)B * Kw, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(ws.c1, 0, sizeof(float) * (size_t)B * Wu, s));
+    b.parity = 0;
+    return DC_OK;
+}
+
+// consume ws.tok with the word LSTM (masked): state in X1[parity][:, Epad:] / ws.c1; h mirrored into xin[:, F:]
+int Decoder::v2_word_step_bf16(int B, bool gather, cudaStream_t s) {
+    Bf16State &b = *bf;
+    const int E = cfg.embed, V = cfg.vocab, F = cfg.feat, Wu = cfg.word_units, Kw = b.Epad + Wu, p = b.parity;
+    if (gather)
+        if (int rc = embed_gather(W("imgcap_embedding_layer/embeddings"), ws.tok, B, E, V, b.X1[p], Kw, true, s)) return rc;
+    TcEpilogue c;
+    c.bias = b.v2_bw; c.cell_c = ws.c1; c.cell_units = Wu; c.cell_tok = ws.tok;
+    c.cell_h_prev = b.X1[p] + b.Epad; c.ld_h_prev = Kw;
+    c.cell_h_a = b.X1[p ^ 1] + b.Epad; c.ld_h_a = Kw;
+    c.cell_h_b = b.v2_xin + F; c.ld_h_b = F + Wu;
+    if (int rc = gemm_bf16_tc(op(b.X1[p], Kw), op(b.v2_w1cat, Kw), c, B, 4 * Wu, Kw, kEpiCell, s)) return rc;
+    b.parity ^= 1;
+    return DC_OK;
+}
+
+// [head ; wv] -> LSTM(units), one step from the zero state -> h (bf16) ready for the Dense(V) GEMM
+int Decoder::v2_image_step_bf16(int B, cudaStream_t s) {
+    Bf16State &b = *bf;
+    const int F = cfg.feat, Wu = cfg.word_units, U = cfg.units;
+    TcEpilogue c;
+    c.bias = b.v2_bimg; c.cell_c = b.v2_czero; c.cell_c_out = ws.c2; c.cell_units = U;
+    c.cell_h_a = b.v2_hb; c.ld_h_a = U;
+    return gemm_bf16_tc(op(b.v2_xin, F + Wu), op(b.v2_wimg, F + Wu), c, B, 4 * U, F + Wu, kEpiCell, s);
+}
+
+int Decoder::v2_predict_bf16(const void *feats, int kind, const int32_t *words, int B, int L, float *probs, cudaStream_t s) {
+    Bf16State &b = *bf;
+    const int U = cfg.units, V = cfg.vocab;
+    if (int rc = v2_begin_bf16(feats, kind, B, s)) return rc;
+    for (int t = 0; t < L; ++t) {
+        if (int rc = token_column(words, B, L, t, ws.tok, s)) return rc;
+        if (int rc = v2_word_step_bf16(B, true, s)) return rc;
+    }
+    if (int rc = v2_image_step_bf16(B, s)) return rc;
+    TcEpilogue e;
+    e.bias = W("imgcap_d1/bias"); e.out_f32 = ws.logits; e.ld_f32 = V;
+    if (int rc = gemm_bf16_tc(op(b.v2_hb, U), op(b.v2_wd, U), e, B, V, U, kEpiStore, s)) return rc;
+    return softmax_argmax(ws.logits, V, B, V, probs, V, nullptr, 0, nullptr, nullptr, s);
+}
+
+int Decoder::v2_greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s,
+                            const int32_t *start) {
+    Bf16State &b = *bf;
+    const int P = cfg.padding, U = cfg.units, V = cfg.vocab, Wu = cfg.word_units;
+    if (int rc = v2_begin_bf16(feats, kind, B, s)) return rc;
+    if (start) DC_CHECK_CUDA(cudaMemcpyAsync(ws.tok, start, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, s));
+    else if (int rc = fill_i32(ws.tok, B, 0, s)) return rc;           // argmax(zeros(V)) = 0 -> masked
+    const int slots = gemm_tc_argmax_tiles(V);
+    for (int t = 0; t + 1 < P; ++t) {
+        // the pre-padded window never truncates inside the reference loop (at most P-1 ids), so consuming one
+        // new id per step equals re-running the word LSTM over the whole prefix
+        if (int rc = v2_word_step_bf16(B, probs != nullptr || t == 0, s)) return rc;
+        if (int rc = v2_image_step_bf16(B, s)) return rc;
+        if (probs) {
+            TcEpilogue e;
+            e.bias = W("imgcap_d1/bias"); e.out_f32 = ws.logits; e.ld_f32 = V;
+            if (int rc = gemm_bf16_tc(op(b.v2_hb, U), op(b.v2_wd, U), e, B, V, U, kEpiStore, s)) return rc;
+            if (int rc = softmax_argmax(ws.logits, V, B, V, probs + (size_t)t * V, (long long)(P - 1) * V, tokens + t, P - 1,
+                                        ws.tok, nullptr, s)) return rc;
+        } else {
+            TcEpilogue e;
+            e.bias = W("imgcap_d1/bias"); e.partial = b.partial;
+            if (int rc = gemm_bf16_tc(op(b.v2_hb, U), op(b.v2_wd, U), e, B, V, U, kEpiArgmax, s)) return rc;
+            const bool more = t + 2 < P;
+            if (int rc = argmax_merge(b.partial, B, slots, tokens + t, P - 1, ws.tok, nullptr, s, more ? b.emb : nullptr,
+                                      b.Epad, more ? b.X1[b.parity] : nullptr, b.Epad + Wu)) return rc;
+        }
+    }
     return DC_OK;
 }
 

@@ -33,6 +33,11 @@ struct Bf16State {
     __nv_bfloat16 *u1_k = nullptr;       // [U, 4U]     imgcap_lstm1/recurrent_kernel
     __nv_bfloat16 *w1f_k = nullptr;      // [F, 4U]     imgcap_lstm1/kernel[E:]
     __nv_bfloat16 *wc2_k = nullptr;      // [F, F]      mrcnn_class_conv2/kernel
+    // v2 inject model (text_generation_model_v2.py:140-166) on the tensor-core path
+    __nv_bfloat16 *v2_w1cat = nullptr, *v2_wimg = nullptr, *v2_wd = nullptr;   // [4Wu, Epad+Wu], [4U, F+Wu] gate-interleaved; [V, U]
+    float *v2_bw = nullptr, *v2_bimg = nullptr;                                 // gate-interleaved biases
+    __nv_bfloat16 *v2_xin = nullptr, *v2_hb = nullptr;                          // [R, F+Wu] = [head | word vector], [R, U]
+    float *v2_czero = nullptr;                                                  // [R, U] zeros: the image LSTM starts from the zero state
     TrainState *train = nullptr;
 };
 

@@ -308,6 +308,18 @@ int set_token_column(int32_t *tokens, int rows, int stride, int col, const int32
     return DC_OK;
 }
 
+// tok[r] = words[r, col]: one time step of the [rows, L] word-id matrix (v2 predict)
+__global__ void token_column_kernel(const int32_t *__restrict__ words, int rows, int L, int col, int32_t *__restrict__ tok) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) tok[r] = words[(long long)r * L + col];
+}
+int token_column(const int32_t *words, int rows, int L, int col, int32_t *tok, cudaStream_t s) {
+    if (rows <= 0) return DC_OK;
+    token_column_kernel<<<ceil_div(rows, 256), 256, 0, s>>>(words, rows, L, col, tok);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
 template <typename T>
 __global__ void f32_to_kernel(const float *__restrict__ src, T *__restrict__ dst, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

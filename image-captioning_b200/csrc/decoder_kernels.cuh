@@ -33,6 +33,7 @@ int beam_gather(int rows, int k, int width, const int32_t *parent, const void *s
                 void *dst, int ld_dst, int elem_bytes, cudaStream_t s);
 int fill_i32(int32_t *p, long long n, int32_t v, cudaStream_t s);
 int set_token_column(int32_t *tokens, int rows, int stride, int col, const int32_t *src, cudaStream_t s);
+int token_column(const int32_t *words, int rows, int L, int col, int32_t *tok, cudaStream_t s);
 int f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t s);
 int transpose_f32(const float *in, int rows, int cols, void *out, int ld_out, bool bf16, cudaStream_t s);
 

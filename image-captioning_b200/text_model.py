@@ -595,9 +595,9 @@ class RoiCaptionModel(_ModelBase):
 class InjectModelV2(_ModelBase):
     """build_model(features_shape, word_shape, config, units, inject=True) result."""
 
-    def __init__(self, features_shape, word_shape, config, units, device=None):
+    def __init__(self, features_shape, word_shape, config, units, device=None, dtype="float32"):
         self.word_shape = tuple(word_shape)
-        super().__init__(ARCH_V2_INJECT, config, units, list(features_shape), "float32", word_units=1024,
+        super().__init__(ARCH_V2_INJECT, config, units, list(features_shape), dtype, word_units=1024,
                          device=device)
 
     def predict(self, x, batch_size=None, verbose=0):
@@ -648,9 +648,9 @@ def build_lstm_model(features_input, config, units, mode, dtype="float32", devic
     return RoiCaptionModel(features_input, config, units, mode, dtype=dtype, device=device)
 
 
-def build_model(features_shape, word_shape, config, units, inject=True, device=None):
-    """Same signature as the reference (text_generation_model_v2.py:140).  Only the inject
-    variant ("m1") is on the hot path; the merge variant is out of scope."""
+def build_model(features_shape, word_shape, config, units, inject=True, device=None, dtype="float32"):
+    """Same signature as the reference (text_generation_model_v2.py:140) plus `dtype`/`device`.  Only the
+    inject variant ("m1") is on the hot path; the merge variant is out of scope."""
     if not inject:
         raise NotImplementedError("merge model (inject=False) is outside the hot path")
-    return InjectModelV2(features_shape, word_shape, config, units, device=device)
+    return InjectModelV2(features_shape, word_shape, config, units, device=device, dtype=dtype)

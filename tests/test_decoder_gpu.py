@@ -199,6 +199,37 @@ def test_v2_greedy_from_ground_truth_first_word():
         m.generate(feat, start_tokens=start[:3])
 
 
+def test_v2_inject_bf16_path_agreement_with_fp32_oracle():
+    """v2 inject model at the reference's shapes (word LSTM 1024, image LSTM 256, vocab 10k, P = 10) on the
+    tensor-core path: >= 99 % greedy-token agreement with the fp32 oracle, log-probabilities within 2e-2
+    where the prefix agrees; predict([features, words]) likewise; fused arg-max path == materialised path."""
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(1006)
+    V, E, units, C, P, B = 10000, 300, 256, 256, 10, 96
+    w = synth.synth_weights_v2(rng, V=V, E=E, units=units, C=C)
+    cfg = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], 1, P)
+    m = pkg.build_model((7, 7, C), (P,), cfg, units, inject=True, dtype="bfloat16")
+    m.set_weights(w)
+    feat = rng.standard_normal((B, 7, 7, C)).astype(np.float32)
+    tok_want, p_want = dec.greedy_v2(feat, w, P)
+    tok, probs = m.generate(feat, return_probs=True)
+    tok_fast = m.generate(feat)
+    assert np.array_equal(tok, tok_fast)
+    agree = tok == tok_want
+    assert agree.mean() >= 0.99, agree.mean()
+    prefix_ok = np.concatenate([np.ones((B, 1), bool), np.cumprod(agree[:, :-1], 1).astype(bool)], 1)
+    big = p_want > np.exp(-12.0)
+    err = np.abs(np.log(np.maximum(probs, 1e-30)) - np.log(np.maximum(p_want, 1e-30)))[prefix_ok[:, :, None] & big]
+    assert err.max() <= 2e-2, err.max()
+    words = dec.pad_sequences_pre([[0] + tok_want[i, :4].tolist() for i in range(B)], P)
+    pp = m.predict([feat, words])
+    pw = dec.v2_inject_predict(feat, words, w)
+    e2 = np.abs(np.log(np.maximum(pp, 1e-30)) - np.log(np.maximum(pw, 1e-30)))[pw > np.exp(-12.0)]
+    assert e2.max() <= 2e-2, e2.max()
+    start = rng.integers(1, V, B).astype(np.int32)
+    assert (m.generate(feat, start_tokens=start) == dec.greedy_v2(feat, w, P, start=start)[0]).mean() >= 0.99
+
+
 def test_bf16_greedy_agreement_with_fp32_oracle():
     """north_star bar for the bf16 path: log-probabilities within 2e-2 absolute of the fp32 model
     (on positions fed the same prefix) and >= 99 % greedy-token agreement."""
