@@ -64,7 +64,7 @@ SIGNATURES = {
     "dc_decoder_v2_greedy": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void,
                                             c_void]),
     "dc_decoder_v2_greedy_from": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void,
-                                                 c_void]),
+                                                 c_void, c_void]),
     "dc_gemm_f32": (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_int, c_void, ctypes.c_int64, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void, c_void, ctypes.c_int64,
                                    ctypes.c_int, ctypes.c_int, c_void, ctypes.c_int64, c_void]),

@@ -490,13 +490,14 @@ int Decoder::v2_predict(const void *feats, int kind, const int32_t *words, int B
     return softmax_argmax(ws.logits, cfg.vocab, B, cfg.vocab, probs, cfg.vocab, nullptr, 0, nullptr, nullptr, s);
 }
 
-int Decoder::v2_greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, const int32_t *start) {
+int Decoder::v2_greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, const int32_t *start,
+                       float *scores) {
     if (int rc = check_ready(B)) return rc;
     DC_REQUIRE(cfg.arch == DC_ARCH_V2_INJECT, "dc_decoder_v2_greedy needs a v2 inject decoder");
     if (B == 0) return DC_OK;
     DC_REQUIRE(feats && tokens, "null pointer argument");
     if (int rc = reserve(B)) return rc;
-    if (cfg.dtype == DC_DTYPE_BF16) return v2_greedy_bf16(feats, kind, B, tokens, probs, s, start);
+    if (cfg.dtype == DC_DTYPE_BF16) return v2_greedy_bf16(feats, kind, B, tokens, probs, s, start, scores);
     const int P = cfg.padding, V = cfg.vocab;
     if (int rc = v2_reset(B, s)) return rc;
     if (int rc = v2_head_into_xin(feats, kind, B, s)) return rc;
@@ -509,7 +510,9 @@ int Decoder::v2_greedy(const void *feats, int kind, int B, int32_t *tokens, floa
         if (int rc = v2_word_step(B, s)) return rc;
         if (int rc = v2_output(B, s)) return rc;
         if (int rc = softmax_argmax(ws.logits, V, B, V, probs ? probs + (size_t)t * V : nullptr,
-                                    (long long)(P - 1) * V, tokens + t, P - 1, ws.tok, nullptr, s)) return rc;
+                                    (long long)(P - 1) * V, tokens + t, P - 1, ws.tok, scores ? ws.cand_p : nullptr, s)) return rc;
+        if (scores)
+            if (int rc = accumulate_log(scores, ws.cand_p, B, t == 0, s)) return rc;
     }
     return DC_OK;
 }
@@ -632,9 +635,9 @@ extern "C" int dc_decoder_v2_greedy(DcDecoder *dec, const void *feats, int kind,
 }
 
 extern "C" int dc_decoder_v2_greedy_from(DcDecoder *dec, const void *feats, int kind, int B, const int32_t *start,
-                                         int32_t *tokens, float *probs, void *stream) {
+                                         int32_t *tokens, float *probs, float *scores, void *stream) {
     DC_REQUIRE(dec, "null decoder");
-    return dec->impl.v2_greedy(feats, kind, B, tokens, probs, (cudaStream_t)stream, start);
+    return dec->impl.v2_greedy(feats, kind, B, tokens, probs, (cudaStream_t)stream, start, scores);
 }
 
 extern "C" int dc_decoder_greedy_host(DcDecoder *dec, const float *feats, int kind, int B, int32_t *tokens,

@@ -93,7 +93,8 @@ struct Decoder {
     int v2_output(int B, cudaStream_t s);
     int v2_head_into_xin(const void *feats, int kind, int B, cudaStream_t s);
     int v2_predict(const void *feats, int kind, const int32_t *words, int B, int L, float *probs, cudaStream_t s);
-    int v2_greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, const int32_t *start = nullptr);
+    int v2_greedy(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, const int32_t *start = nullptr,
+                  float *scores = nullptr);
 
     // bf16 / tcgen05 path (decoder_bf16.cu)
     int refresh_bf16(bool fresh, cudaStream_t s);
@@ -109,7 +110,8 @@ struct Decoder {
     int v2_word_step_bf16(int B, bool gather, cudaStream_t s);
     int v2_image_step_bf16(int B, cudaStream_t s);
     int v2_predict_bf16(const void *feats, int kind, const int32_t *words, int B, int L, float *probs, cudaStream_t s);
-    int v2_greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, const int32_t *start);
+    int v2_greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s, const int32_t *start,
+                       float *scores);
     int beam_bf16(const void *feats, int kind, int B, int k, int32_t *tokens, double *scores, cudaStream_t s);
     void free_bf16();
 

@@ -485,7 +485,7 @@ int Decoder::v2_predict_bf16(const void *feats, int kind, const int32_t *words, 
 }
 
 int Decoder::v2_greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, float *probs, cudaStream_t s,
-                            const int32_t *start) {
+                            const int32_t *start, float *scores) {
     Bf16State &b = *bf;
     const int P = cfg.padding, U = cfg.units, V = cfg.vocab, Wu = cfg.word_units;
     if (int rc = v2_begin_bf16(feats, kind, B, s)) return rc;
@@ -502,15 +502,17 @@ int Decoder::v2_greedy_bf16(const void *feats, int kind, int B, int32_t *tokens,
             e.bias = W("imgcap_d1/bias"); e.out_f32 = ws.logits; e.ld_f32 = V;
             if (int rc = gemm_bf16_tc(op(b.v2_hb, U), op(b.v2_wd, U), e, B, V, U, kEpiStore, s)) return rc;
             if (int rc = softmax_argmax(ws.logits, V, B, V, probs + (size_t)t * V, (long long)(P - 1) * V, tokens + t, P - 1,
-                                        ws.tok, nullptr, s)) return rc;
+                                        ws.tok, scores ? ws.cand_p : nullptr, s)) return rc;
         } else {
             TcEpilogue e;
             e.bias = W("imgcap_d1/bias"); e.partial = b.partial;
-            if (int rc = gemm_bf16_tc(op(b.v2_hb, U), op(b.v2_wd, U), e, B, V, U, kEpiArgmax, s)) return rc;
+            if (int rc = gemm_bf16_tc(op(b.v2_hb, U), op(b.v2_wd, U), e, B, V, U, scores ? kEpiArgmaxSum : kEpiArgmax, s)) return rc;
             const bool more = t + 2 < P;
-            if (int rc = argmax_merge(b.partial, B, slots, tokens + t, P - 1, ws.tok, nullptr, s, more ? b.emb : nullptr,
-                                      b.Epad, more ? b.X1[b.parity] : nullptr, b.Epad + Wu)) return rc;
+            if (int rc = argmax_merge(b.partial, B, slots, tokens + t, P - 1, ws.tok, scores ? ws.cand_p : nullptr, s,
+                                      more ? b.emb : nullptr, b.Epad, more ? b.X1[b.parity] : nullptr, b.Epad + Wu)) return rc;
         }
+        if (scores)
+            if (int rc = accumulate_log(scores, ws.cand_p, B, t == 0, s)) return rc;
     }
     return DC_OK;
 }

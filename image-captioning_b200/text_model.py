@@ -617,7 +617,7 @@ class InjectModelV2(_ModelBase):
                 w.shape[1], ctypes.c_void_p(probs.data_ptr()), self._stream()))
         return probs.cpu().numpy() if was_numpy else probs
 
-    def generate(self, features, return_probs=False, start_tokens=None):
+    def generate(self, features, return_probs=False, start_tokens=None, return_scores=False):
         """The reference's greedy loop (test_score_dense_captions.py:216-225): P-1 ids per RoI, started from
         [0] (argmax of the all-zero start vector) or, with ``start_tokens`` [N], from a given first word
         (eval_text_generation_model_v2.py:176-186 starts from the ground-truth first word)."""
@@ -632,15 +632,16 @@ class InjectModelV2(_ModelBase):
             if st.dim() != 1 or st.shape[0] != N:
                 raise ValueError("start_tokens must be [N]")
             st = st.to(self.device).to(torch.int32).contiguous()
+        scores = torch.empty((N,), dtype=torch.float32, device=self.device) if return_scores else None
         with torch.cuda.device(self.device):
             _lib.check(self._lib.dc_decoder_v2_greedy_from(
                 self._h, ctypes.c_void_p(t.data_ptr()), kind, N, ctypes.c_void_p(st.data_ptr()) if st is not None else None,
                 ctypes.c_void_p(tokens.data_ptr()), ctypes.c_void_p(probs.data_ptr()) if probs is not None else None,
-                self._stream()))
+                ctypes.c_void_p(scores.data_ptr()) if scores is not None else None, self._stream()))
+        outs = [tokens] + ([probs] if return_probs else []) + ([scores] if return_scores else [])
         if was_numpy:
-            tokens = tokens.cpu().numpy()
-            probs = probs.cpu().numpy() if probs is not None else None
-        return (tokens, probs) if return_probs else tokens
+            outs = [o.cpu().numpy() for o in outs]
+        return outs[0] if len(outs) == 1 else tuple(outs)
 
 
 def build_lstm_model(features_input, config, units, mode, dtype="float32", device=None):

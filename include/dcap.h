@@ -197,9 +197,11 @@ int dc_decoder_v2_greedy(DcDecoder *dec, const void *feats, int feats_kind, int 
                          int32_t *tokens, float *probs, void *stream);
 
 /* Same loop started from a given first word per RoI (evaluate_models/eval_text_generation_model_v2.py:176-186:
- * prev = [gt_caption[0]]): start [B] int32 ids (device), NULL = all zeros (the loop above). */
+ * prev = [gt_caption[0]]): start [B] int32 ids (device), NULL = all zeros (the loop above).  scores (optional,
+ * [B] fp32): the caption score refine_generations ranks by, sum over the P-1 steps of log max p
+ * (test_score_dense_captions.py:256-258), without materialising the probabilities. */
 int dc_decoder_v2_greedy_from(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *start,
-                              int32_t *tokens, float *probs, void *stream);
+                              int32_t *tokens, float *probs, float *scores, void *stream);
 
 /* Host-buffer forms (what Keras predict callers see): HOST pointers in and out, copies inside. */
 int dc_decoder_greedy_host(DcDecoder *dec, const float *feats, int feats_kind, int B,

@@ -72,3 +72,33 @@ def test_fused_caption_scores(dtype):
     assert np.array_equal(tok, tok2)
     want = pp.caption_scores(probs)
     np.testing.assert_allclose(scores, want, rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_v2_dense_captioning_flow_scores_and_refine(dtype):
+    """The evaluation flow of test_score_dense_captions.py:207-237 for one image on the device: v2 greedy with
+    fused caption scores -> refine_generations (NMS + top-100) -> caption text cut at ' .'."""
+    import image_captioning_b200 as pkg
+    from image_captioning_b200 import synth
+    from oracle import decoder as dec
+    rng = np.random.default_rng(3)
+    V, E, units, C, P, N = 2000, 300, 256, 256, 10, 200
+    w = synth.synth_weights_v2(rng, V=V, E=E, units=units, C=C)
+    cfg = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], 1, P)
+    m = pkg.build_model((7, 7, C), (P,), cfg, units, inject=True, dtype=dtype)
+    m.set_weights(w)
+    feat = rng.standard_normal((N, 7, 7, C)).astype(np.float32)
+    rois = _boxes(rng, N)
+    tok, scores = m.generate(feat, return_scores=True)
+    tok2, probs = m.generate(feat, return_probs=True)
+    assert np.array_equal(tok, tok2)
+    np.testing.assert_allclose(scores, pp.caption_scores(probs), rtol=2e-3, atol=2e-3)
+    keep = pkg.refine_generations(rois, scores, 0.7, 100)
+    assert np.array_equal(keep, pp.refine_generations(rois, scores, 0.7, 100))
+    if dtype == "float32":
+        tok_want, p_want = dec.greedy_v2(feat[:16], w, P)
+        assert np.array_equal(tok[:16], tok_want)
+    id_to_word = {i: ("." if i == 2 else "w%d" % i) for i in range(V)}
+    text = pkg.caption_text(tok[keep[0]], id_to_word)
+    assert " ." not in text and text == pp.caption_text(tok[keep[0]], id_to_word)
