@@ -11,4 +11,5 @@ from . import synth  # noqa: F401
 from .text_model import (DenseCapConfig, build_lstm_model, build_model, RoiCaptionModel,   # noqa: F401
                          InjectModelV2, Adam, roi_caption_loss)
 from .postprocess import refine_generations, caption_text    # noqa: F401
+from .proposals import ProposalLayer, ProposalConfig, generate_pyramid_anchors, normalize_boxes   # noqa: F401
 from . import parallel    # noqa: F401

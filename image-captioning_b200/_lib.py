@@ -57,6 +57,11 @@ SIGNATURES = {
     "dc_decoder_greedy_scored": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void]),
     "dc_refine_generations": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                              c_void, c_void, c_void]),
+    "dc_proposal_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "dc_proposal_layer": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, ctypes.c_float,
+                                         ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_float, c_void, c_void, c_void,
+                                         c_void, ctypes.c_size_t, c_void]),
+    "dc_normalize_boxes": (ctypes.c_int, [c_void, ctypes.c_int64, ctypes.c_float, ctypes.c_float, c_void, c_void]),
     "dc_decoder_beam": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void,
                                        c_void, c_void]),
     "dc_decoder_v2_predict": (ctypes.c_int, [c_void, c_void, ctypes.c_int, c_void, ctypes.c_int,

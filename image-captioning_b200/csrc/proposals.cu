@@ -1,0 +1,429 @@
+// Box front-end of the RoI path: the RPN proposal filter that produces the
+// boxes PyramidROIAlign consumes when use_generated_rois is set, and the GT-box normalisation used otherwise.
+// Replaces ProposalLayer.call (/root/reference/dense_img_cap_separate_models/modified_dense_model.py:247-303:
+// tf.nn.top_k(6000) -> gather -> apply_box_deltas_graph (:179-200) -> clip_boxes_graph (:203-218) ->
+// / [h,w,h,w] -> tf.image.non_max_suppression -> zero pad) and the Lambda at :1523-1526.
+//
+// Three launches per batch, all HBM/L2-latency-bound integer and fp32 work (no tensor cores):
+//
+//   1. proposal_select_kernel: one CLUSTER of 8 CTAs per image.  Every CTA reads its eighth of the image's
+//      foreground scores ONCE into shared memory as order-preserving 32-bit keys; an 8-bit x 4-pass radix
+//      select finds the pre_nms_limit-th largest key with the per-pass histograms summed over the cluster in
+//      CTA 0's shared memory (DSMEM atomics); the selected (key, anchor) pairs are compacted straight into
+//      CTA 0's shared memory (DSMEM stores; ties at the threshold: lowest anchor index first, as top_k),
+//      bitonic-sorted there, and CTA 0 refines / clips / normalises the boxes in that order.
+//   2. proposal_iou_mask_kernel: 64x64 tiles of the upper triangle of the IoU > threshold relation as bit masks.
+//   3. proposal_nms_scan_kernel: one CTA per image walks the boxes in score order 64 at a time (the 64-step
+//      dependency chain runs in registers of one warp, the survivors' mask rows are OR-ed by the whole CTA),
+//      stops at proposal_count, gathers the survivors and zero-pads.
+//
+// fp32 arithmetic op for op as the TF graph (explicit _rn intrinsics: no FMA contraction); tf.exp is the
+// correctly rounded fp32 exponential (fp64 exp rounded once), as in oracle/proposals.py.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace dcap {
+
+constexpr int kSelThreads = 1024;
+constexpr int kSelCluster = 8;
+constexpr int kMaxPreNms = 8192;
+constexpr int kSelMaxChunk = 36 * 1024;          // keys cached in shared memory per CTA (144 KB) -> 294912 anchors per image
+constexpr int kScanThreads = 256;
+
+// Descending-score order as ascending-key order reversed: larger score <-> larger key.  -0 == +0; NaN sorts last.
+__device__ __forceinline__ uint32_t score_key(float s) {
+    if (s != s) return 0u;
+    const uint32_t u = __float_as_uint(s + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct SelSmem {
+    unsigned long long sort[kMaxPreNms];      // (key << 32) | ~anchor, only CTA 0's copy is used
+    unsigned int hist[2][256];                // cluster-wide histogram of the current digit (CTA 0's copy), double buffered
+    unsigned int lhist[256];                  // this CTA's histogram
+    unsigned int n_gt[kSelCluster], n_eq[kSelCluster];   // per-CTA counts, replicated in every CTA
+    unsigned int warp_cnt[kSelThreads / 32];
+    unsigned int sel_bin, sel_above, ctr;
+};
+
+template <bool kCache>
+__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
+proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__restrict__ rpn_bbox,
+                       const float4 *__restrict__ anchors, int n_anchors, int k_eff, float4 std_dev, float img_h,
+                       float img_w, float4 *__restrict__ ws_boxes, int32_t *__restrict__ ws_index) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    SelSmem &sm = *reinterpret_cast<SelSmem *>(sm_raw);
+    uint32_t *s_key = reinterpret_cast<uint32_t *>(sm_raw + sizeof(SelSmem));
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int img = blockIdx.x / kSelCluster;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    SelSmem *sm0 = cluster.map_shared_rank(&sm, 0);
+
+    const int chunk = ceil_div(n_anchors, kSelCluster);
+    const int lo = min(rank * chunk, n_anchors), n_local = min(lo + chunk, n_anchors) - lo;
+    const float *score = rpn_probs + ((long long)img * n_anchors + lo) * 2 + 1;      // foreground column of [A, 2]
+    auto key_at = [&](int i) -> uint32_t { return kCache ? s_key[i] : score_key(__ldg(score + 2 * (long long)i)); };
+    if (kCache) {
+        // [A,2] rows are 8 bytes: read whole float2 rows (coalesced) and keep the foreground half
+        const float2 *rows = reinterpret_cast<const float2 *>(rpn_probs) + (long long)img * n_anchors + lo;
+        for (int i = tid; i < n_local; i += kSelThreads) s_key[i] = score_key(__ldg(rows + i).y);
+    }
+
+    // ---- radix select: the k_eff-th largest key ------------------------------------------------------------
+    uint32_t prefix = 0, mask = 0;
+    unsigned int remaining = (unsigned int)k_eff;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        unsigned int *hist0 = sm0->hist[pass & 1];
+        if (tid < 256) {
+            sm.lhist[tid] = 0;
+            if (rank == 0) sm.hist[pass & 1][tid] = 0;
+        }
+        cluster.sync();                                     // zeroed before any remote add; also orders s_key writes
+        for (int base = 0; base < n_local; base += kSelThreads) {
+            const int i = base + tid;
+            uint32_t key = 0;
+            bool p = i < n_local;
+            if (p) { key = key_at(i); p = (key & mask) == prefix; }
+            const unsigned int bal = __ballot_sync(0xffffffffu, p);
+            if (p) {
+                const unsigned int bin = (key >> shift) & 255u;
+                const unsigned int peers = __match_any_sync(bal, bin);
+                if (lane == __ffs(peers) - 1) atomicAdd(&sm.lhist[bin], (unsigned int)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (tid < 256 && sm.lhist[tid]) atomicAdd(hist0 + tid, sm.lhist[tid]);       // DSMEM
+        cluster.sync();
+        if (warp == 0) {
+            // lane l owns bins [8l, 8l+8); walk from the top bin down
+            unsigned int h[8], mine = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = hist0[lane * 8 + j]; mine += h[j]; }
+            unsigned int above = 0;                           // keys in the bins of higher lanes (uniform shuffle loop)
+            for (int l = 31; l >= 0; --l) {
+                const unsigned int v = __shfl_sync(0xffffffffu, mine, l);
+                if (l > lane) above += v;
+            }
+            if (above < remaining && remaining <= above + mine) {
+                unsigned int a = above;
+                for (int j = 7; j >= 0; --j) {
+                    if (remaining <= a + h[j]) { sm.sel_bin = lane * 8 + j; sm.sel_above = a; break; }
+                    a += h[j];
+                }
+            }
+        }
+        __syncthreads();
+        remaining -= sm.sel_above;
+        prefix |= sm.sel_bin << shift;
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    const uint32_t thr_key = prefix;                         // keys > thr_key are all taken; `remaining` ties are needed
+
+    // ---- counts per CTA -> every CTA knows every CTA's counts ----------------------------------------------
+    if (tid == 0) sm.ctr = 0;
+    if (tid < 2) sm.warp_cnt[tid] = 0;
+    __syncthreads();
+    {
+        unsigned int gt = 0, eq = 0;
+        for (int i = tid; i < n_local; i += kSelThreads) {
+            const uint32_t key = key_at(i);
+            gt += key > thr_key;
+            eq += key == thr_key;
+        }
+        gt = __reduce_add_sync(0xffffffffu, gt);
+        eq = __reduce_add_sync(0xffffffffu, eq);
+        if (lane == 0) { atomicAdd(&sm.warp_cnt[0], gt); atomicAdd(&sm.warp_cnt[1], eq); }
+    }
+    __syncthreads();
+    if (tid < kSelCluster) {
+        SelSmem *peer = cluster.map_shared_rank(&sm, tid);
+        peer->n_gt[rank] = sm.warp_cnt[0];
+        peer->n_eq[rank] = sm.warp_cnt[1];
+    }
+    cluster.sync();
+    unsigned int base_pos = 0, eq_before = 0;
+    for (int r = 0; r < rank; ++r) {
+        const unsigned int q = min(sm.n_eq[r], remaining > eq_before ? remaining - eq_before : 0u);
+        base_pos += sm.n_gt[r] + q;
+        eq_before += sm.n_eq[r];
+    }
+    const unsigned int quota = min(sm.n_eq[rank], remaining > eq_before ? remaining - eq_before : 0u);
+    const unsigned int my_gt = sm.n_gt[rank];
+    __syncthreads();
+
+    // ---- compaction into CTA 0's sort buffer -----------------------------------------------------------------
+    // keys above the threshold: any order (they are sorted afterwards); ties: the first `quota` in anchor order
+    unsigned int eq_run = 0;                                   // ties seen so far in this CTA (uniform)
+    for (int base = 0; base < n_local; base += kSelThreads) {
+        const int i = base + tid;
+        uint32_t key = 0;
+        if (i < n_local) key = key_at(i);
+        const bool gt = i < n_local && key > thr_key;
+        const bool eq = i < n_local && key == thr_key && eq_run < quota;
+        const unsigned long long comp = ((unsigned long long)key << 32) | (0xffffffffu - (uint32_t)(lo + i));
+        const unsigned int bal_gt = __ballot_sync(0xffffffffu, gt);
+        if (gt) {
+            unsigned int pos = 0;
+            const int leader = __ffs(bal_gt) - 1;
+            if (lane == leader) pos = atomicAdd(&sm.ctr, (unsigned int)__popc(bal_gt));
+            pos = __shfl_sync(bal_gt, pos, leader) + __popc(bal_gt & ((1u << lane) - 1u));
+            sm0->sort[base_pos + pos] = comp;
+        }
+        if (eq_run < quota) {                                  // uniform
+            const unsigned int bal_eq = __ballot_sync(0xffffffffu, eq);
+            if (lane == 0) sm.warp_cnt[warp] = __popc(bal_eq);
+            __syncthreads();
+            unsigned int before = 0, total = 0;
+            for (int wi = 0; wi < kSelThreads / 32; ++wi) {
+                const unsigned int c = sm.warp_cnt[wi];
+                before += wi < warp ? c : 0u;
+                total += c;
+            }
+            const unsigned int r = eq_run + before + __popc(bal_eq & ((1u << lane) - 1u));
+            if (eq && r < quota) sm0->sort[base_pos + my_gt + r] = comp;
+            eq_run += total;
+            __syncthreads();
+        }
+    }
+    int n_pad = 2;
+    while (n_pad < k_eff) n_pad <<= 1;
+    if (rank == 0)
+        for (int i = k_eff + tid; i < n_pad; i += kSelThreads) sm.sort[i] = 0ull;
+    cluster.sync();                                            // all remote stores have landed
+    if (rank != 0) return;
+
+    // ---- CTA 0: sort descending by (key, ~anchor) = score descending, anchor ascending ----------------------
+    for (int k = 2; k <= n_pad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (n_pad >> 1); t += kSelThreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));       // index with bit j clear
+                const int l = i | j;
+                const unsigned long long a = sm.sort[i], b = sm.sort[l];
+                const bool desc = (i & k) == 0;
+                if (desc ? a < b : a > b) { sm.sort[i] = b; sm.sort[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- refine, clip, normalise (modified_dense_model.py:179-218, :287) ------------------------------------
+    for (int i = tid; i < k_eff; i += kSelThreads) {
+        const uint32_t a_idx = 0xffffffffu - (uint32_t)sm.sort[i];
+        const float4 a = __ldg(anchors + a_idx);               // (y1, x1, y2, x2) pixels
+        float4 d = __ldg(rpn_bbox + (long long)img * n_anchors + a_idx);
+        d.x = __fmul_rn(d.x, std_dev.x); d.y = __fmul_rn(d.y, std_dev.y);
+        d.z = __fmul_rn(d.z, std_dev.z); d.w = __fmul_rn(d.w, std_dev.w);
+        float height = __fsub_rn(a.z, a.x), width = __fsub_rn(a.w, a.y);
+        float cy = __fadd_rn(a.x, __fmul_rn(0.5f, height)), cx = __fadd_rn(a.y, __fmul_rn(0.5f, width));
+        cy = __fadd_rn(cy, __fmul_rn(d.x, height));
+        cx = __fadd_rn(cx, __fmul_rn(d.y, width));
+        height = __fmul_rn(height, (float)exp((double)d.z));
+        width = __fmul_rn(width, (float)exp((double)d.w));
+        float y1 = __fsub_rn(cy, __fmul_rn(0.5f, height)), x1 = __fsub_rn(cx, __fmul_rn(0.5f, width));
+        float y2 = __fadd_rn(y1, height), x2 = __fadd_rn(x1, width);
+        y1 = fmaxf(fminf(y1, img_h), 0.f); x1 = fmaxf(fminf(x1, img_w), 0.f);
+        y2 = fmaxf(fminf(y2, img_h), 0.f); x2 = fmaxf(fminf(x2, img_w), 0.f);
+        ws_boxes[(long long)img * k_eff + i] = make_float4(__fdiv_rn(y1, img_h), __fdiv_rn(x1, img_w),
+                                                           __fdiv_rn(y2, img_h), __fdiv_rn(x2, img_w));
+        ws_index[(long long)img * k_eff + i] = (int32_t)a_idx;
+    }
+}
+
+// tf.image.non_max_suppression's IOU() (non_max_suppression_op.cc): corners min/max-normalised by the caller.
+struct NmsBox { float ymin, xmin, ymax, xmax, area; };
+
+__device__ __forceinline__ NmsBox nms_box(float4 b) {
+    NmsBox r;
+    r.ymin = fminf(b.x, b.z); r.ymax = fmaxf(b.x, b.z);
+    r.xmin = fminf(b.y, b.w); r.xmax = fmaxf(b.y, b.w);
+    r.area = __fmul_rn(__fsub_rn(r.ymax, r.ymin), __fsub_rn(r.xmax, r.xmin));
+    return r;
+}
+
+// mask[img][i][cb] bit t: box cb*64+t (t-th of column block cb, later than i in score order) has IoU(i, .) > thr
+__global__ void __launch_bounds__(64) proposal_iou_mask_kernel(const float4 *__restrict__ ws_boxes, int n, int n_blk, float thr,
+                                                               unsigned long long *__restrict__ mask) {
+    const int cb = blockIdx.x, rb = blockIdx.y, img = blockIdx.z, t = threadIdx.x;
+    if (cb < rb) return;                                       // lower triangle is never read
+    __shared__ float s_col[5][64];
+    const float4 *boxes = ws_boxes + (long long)img * n;
+    const int cj = cb * 64 + t;
+    NmsBox c = nms_box(cj < n ? __ldg(boxes + cj) : make_float4(0.f, 0.f, 0.f, 0.f));
+    s_col[0][t] = c.ymin; s_col[1][t] = c.xmin; s_col[2][t] = c.ymax; s_col[3][t] = c.xmax; s_col[4][t] = c.area;
+    __syncthreads();
+    const int i = rb * 64 + t;
+    if (i >= n) return;
+    const NmsBox r = nms_box(__ldg(boxes + i));
+    unsigned long long bits = 0;
+    if (r.area > 0.f) {
+        const int j0 = cb == rb ? t + 1 : 0;
+        const int j1 = min(64, n - cb * 64);
+        for (int j = j0; j < j1; ++j) {
+            const float area_j = s_col[4][j];
+            const float ih = fmaxf(__fsub_rn(fminf(r.ymax, s_col[2][j]), fmaxf(r.ymin, s_col[0][j])), 0.f);
+            const float iw = fmaxf(__fsub_rn(fminf(r.xmax, s_col[3][j]), fmaxf(r.xmin, s_col[1][j])), 0.f);
+            const float inter = __fmul_rn(ih, iw);
+            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(r.area, area_j), inter));
+            if (area_j > 0.f && iou > thr) bits |= 1ull << j;
+        }
+    }
+    mask[((long long)img * n + i) * n_blk + cb] = bits;
+}
+
+__global__ void __launch_bounds__(kScanThreads) proposal_nms_scan_kernel(const float4 *__restrict__ ws_boxes,
+                                                                         const int32_t *__restrict__ ws_index,
+                                                                         const unsigned long long *__restrict__ mask, int n,
+                                                                         int n_blk, int proposal_count, float4 *__restrict__ proposals,
+                                                                         int32_t *__restrict__ n_valid,
+                                                                         int32_t *__restrict__ anchor_index) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    unsigned long long *s_removed = reinterpret_cast<unsigned long long *>(sm_raw);    // [n_blk]
+    int *s_keep = reinterpret_cast<int *>(s_removed + n_blk);                            // [proposal_count]
+    __shared__ unsigned long long s_diag[64];
+    __shared__ unsigned long long s_kept_bits;
+    __shared__ int s_count;
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long *m = mask + (long long)img * n * n_blk;
+    for (int c = tid; c < n_blk; c += kScanThreads) s_removed[c] = 0ull;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    int count0 = 0;                                            // survivors before this block (replicated, uniform)
+    for (int blk = 0; blk < n_blk; ++blk) {
+        const int i0 = blk * 64, rows = min(64, n - i0);
+        if (tid < 64) s_diag[tid] = tid < rows ? __ldg(m + (long long)(i0 + tid) * n_blk + blk) : 0ull;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long r = s_removed[blk], kept = 0ull;
+            int count = count0;
+            for (int t = 0; t < rows && count < proposal_count; ++t) {
+                if (!((r >> t) & 1ull)) {
+                    kept |= 1ull << t;
+                    ++count;
+                    r |= s_diag[t];
+                }
+            }
+            s_kept_bits = kept;
+            s_count = count;
+        }
+        __syncthreads();
+        const unsigned long long kept = s_kept_bits;
+        const int count = s_count;
+        if (tid < 64 && ((kept >> tid) & 1ull)) s_keep[count0 + __popcll(kept & ((1ull << tid) - 1ull))] = i0 + tid;
+        if (count >= proposal_count) break;                    // uniform
+        for (int c = blk + 1 + tid; c < n_blk; c += kScanThreads) {
+            unsigned long long acc = s_removed[c], bits = kept;
+            while (bits) {
+                const int t = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                acc |= __ldg(m + (long long)(i0 + t) * n_blk + c);
+            }
+            s_removed[c] = acc;
+        }
+        count0 = count;
+        __syncthreads();
+    }
+    __syncthreads();
+    const int count = s_count;
+    for (int j = tid; j < proposal_count; j += kScanThreads) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        int a = -1;
+        if (j < count) {
+            const int i = s_keep[j];
+            v = ws_boxes[(long long)img * n + i];
+            a = ws_index[(long long)img * n + i];
+        }
+        proposals[(long long)img * proposal_count + j] = v;
+        if (anchor_index) anchor_index[(long long)img * proposal_count + j] = a;
+    }
+    if (tid == 0 && n_valid) n_valid[img] = count;
+}
+
+__global__ void normalize_boxes_kernel(const float4 *__restrict__ in, long long n, float h, float w, float4 *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 b = in[i];
+    out[i] = make_float4(__fdiv_rn(b.x, h), __fdiv_rn(b.y, w), __fdiv_rn(b.z, h), __fdiv_rn(b.w, w));
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace dcap
+
+using namespace dcap;
+
+extern "C" size_t dc_proposal_workspace_bytes(int n_images, int n_anchors, int pre_nms_limit) {
+    if (n_images <= 0 || n_anchors <= 0 || pre_nms_limit <= 0) return 0;
+    const size_t k = (size_t)(pre_nms_limit < n_anchors ? pre_nms_limit : n_anchors);
+    const size_t n_blk = (k + 63) / 64;
+    return align256((size_t)n_images * k * sizeof(float4)) + align256((size_t)n_images * k * sizeof(int32_t)) +
+           align256((size_t)n_images * k * n_blk * sizeof(unsigned long long));
+}
+
+extern "C" int dc_proposal_layer(const float *rpn_probs, const float *rpn_bbox, const float *anchors, int n_images,
+                                 int n_anchors, const float *bbox_std_dev, float image_h, float image_w, int pre_nms_limit,
+                                 int proposal_count, float nms_threshold, float *proposals, int32_t *n_valid,
+                                 int32_t *anchor_index, void *workspace, size_t workspace_bytes, void *stream) {
+    DC_REQUIRE(n_images >= 0 && n_anchors >= 1 && proposal_count >= 1 && pre_nms_limit >= 1, "bad n_images / n_anchors / counts");
+    if (n_images == 0) return DC_OK;
+    DC_REQUIRE(rpn_probs && rpn_bbox && anchors && bbox_std_dev && proposals && workspace, "null pointer argument");
+    DC_REQUIRE((((uintptr_t)rpn_probs & 7) | ((uintptr_t)rpn_bbox & 15) | ((uintptr_t)anchors & 15) | ((uintptr_t)proposals & 15) |
+                ((uintptr_t)workspace & 15)) == 0, "rpn_probs must be 8-byte, rpn_bbox / anchors / proposals / workspace 16-byte aligned");
+    DC_REQUIRE(image_h > 0.f && image_w > 0.f, "image size must be positive");
+    const int k = pre_nms_limit < n_anchors ? pre_nms_limit : n_anchors;
+    DC_REQUIRE(k <= kMaxPreNms, "pre_nms_limit=%d exceeds %d", k, kMaxPreNms);
+    DC_REQUIRE(workspace_bytes >= dc_proposal_workspace_bytes(n_images, n_anchors, pre_nms_limit),
+               "workspace too small: %zu < %zu bytes", workspace_bytes, dc_proposal_workspace_bytes(n_images, n_anchors, pre_nms_limit));
+    const int n_blk = (k + 63) / 64;
+    unsigned char *ws = static_cast<unsigned char *>(workspace);
+    float4 *ws_boxes = reinterpret_cast<float4 *>(ws);
+    ws += align256((size_t)n_images * k * sizeof(float4));
+    int32_t *ws_index = reinterpret_cast<int32_t *>(ws);
+    ws += align256((size_t)n_images * k * sizeof(int32_t));
+    unsigned long long *ws_mask = reinterpret_cast<unsigned long long *>(ws);
+    cudaStream_t s = (cudaStream_t)stream;
+
+    const int chunk = (n_anchors + kSelCluster - 1) / kSelCluster;
+    const bool cache = chunk <= kSelMaxChunk;
+    const size_t smem = sizeof(SelSmem) + (cache ? (size_t)chunk * sizeof(uint32_t) : 0);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DC_CHECK_CUDA(cudaFuncSetAttribute(proposal_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(sizeof(SelSmem) + (size_t)kSelMaxChunk * sizeof(uint32_t))));
+        DC_CHECK_CUDA(cudaFuncSetAttribute(proposal_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
+        attr_set = true;
+    }
+    const float4 std_dev = make_float4(bbox_std_dev[0], bbox_std_dev[1], bbox_std_dev[2], bbox_std_dev[3]);
+    if (cache)
+        proposal_select_kernel<true><<<n_images * kSelCluster, kSelThreads, smem, s>>>(
+            rpn_probs, reinterpret_cast<const float4 *>(rpn_bbox), reinterpret_cast<const float4 *>(anchors), n_anchors, k, std_dev,
+            image_h, image_w, ws_boxes, ws_index);
+    else
+        proposal_select_kernel<false><<<n_images * kSelCluster, kSelThreads, smem, s>>>(
+            rpn_probs, reinterpret_cast<const float4 *>(rpn_bbox), reinterpret_cast<const float4 *>(anchors), n_anchors, k, std_dev,
+            image_h, image_w, ws_boxes, ws_index);
+    DC_CHECK_LAUNCH();
+    proposal_iou_mask_kernel<<<dim3(n_blk, n_blk, n_images), 64, 0, s>>>(ws_boxes, k, n_blk, nms_threshold, ws_mask);
+    DC_CHECK_LAUNCH();
+    const size_t scan_smem = (size_t)n_blk * sizeof(unsigned long long) + (size_t)proposal_count * sizeof(int);
+    DC_REQUIRE(scan_smem <= 48 * 1024, "proposal_count=%d too large", proposal_count);
+    proposal_nms_scan_kernel<<<n_images, kScanThreads, scan_smem, s>>>(ws_boxes, ws_index, ws_mask, k, n_blk, proposal_count,
+                                                                      reinterpret_cast<float4 *>(proposals), n_valid, anchor_index);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
+extern "C" int dc_normalize_boxes(const float *boxes, int64_t n_boxes, float image_h, float image_w, float *out, void *stream) {
+    DC_REQUIRE(n_boxes >= 0 && image_h > 0.f && image_w > 0.f, "bad n_boxes / image size");
+    if (n_boxes == 0) return DC_OK;
+    DC_REQUIRE(boxes && out && (((uintptr_t)boxes | (uintptr_t)out) & 15) == 0, "boxes / out must be non-null and 16-byte aligned");
+    normalize_boxes_kernel<<<(unsigned int)((n_boxes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(boxes), n_boxes, image_h, image_w, reinterpret_cast<float4 *>(out));
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}

@@ -290,6 +290,31 @@ int dc_refine_generations(const float *boxes, const float *scores, int n_images,
                           float nms_threshold, int max_keep, int32_t *keep, int32_t *n_keep, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Box front-end: what produces the boxes PyramidROIAlign consumes.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces ProposalLayer.call (modified_dense_model.py:247-303): per image, the pre_nms_limit best anchors
+ * by foreground score (tf.nn.top_k: descending, lower index first among equals), deltas * bbox_std_dev applied
+ * to them (apply_box_deltas_graph :179-200), clipped to [0,h]x[0,w] (clip_boxes_graph :203-218), divided by
+ * [h,w,h,w], greedy NMS with tf.image.non_max_suppression's IoU rule (suppress when IoU > nms_threshold),
+ * at most proposal_count survivors in score order, zero padded.
+ *   rpn_probs [n_images, n_anchors, 2] fp32 (bg, fg), rpn_bbox [n_images, n_anchors, 4] fp32,
+ *   anchors [n_anchors, 4] fp32 pixels (y1,x1,y2,x2), bbox_std_dev: 4 HOST floats (config.RPN_BBOX_STD_DEV)
+ *   proposals [n_images, proposal_count, 4] fp32; optional n_valid [n_images] int32 and
+ *   anchor_index [n_images, proposal_count] int32 (-1 padded; which anchor each proposal came from)
+ *   workspace: device scratch of at least dc_proposal_workspace_bytes(...) bytes, 16-byte aligned.
+ * pre_nms_limit (the reference's constant 6000) may not exceed 8192. */
+size_t dc_proposal_workspace_bytes(int n_images, int n_anchors, int pre_nms_limit);
+int dc_proposal_layer(const float *rpn_probs, const float *rpn_bbox, const float *anchors, int n_images,
+                      int n_anchors, const float *bbox_std_dev, float image_h, float image_w, int pre_nms_limit,
+                      int proposal_count, float nms_threshold, float *proposals, int32_t *n_valid,
+                      int32_t *anchor_index, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Replaces the Lambda `x / image_scale` (modified_dense_model.py:1523-1526): pixel boxes (y1,x1,y2,x2) ->
+ * normalised coordinates, fp32 division by [h,w,h,w].  boxes / out: [n_boxes, 4] fp32 device (may alias). */
+int dc_normalize_boxes(const float *boxes, int64_t n_boxes, float image_h, float image_w, float *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Dense contraction primitives (exported so that tests can pin the GEMM kernels in isolation;
  * the decoder calls the same code).  They replace the MatMul ops behind KL.Dense / KL.LSTM /
  * KL.Conv2D(valid, full-window) on this path (text_generation_model.py:141-154, 251-262).

@@ -1,0 +1,110 @@
+"""Generates tests/golden/reference_numpy.npz by RUNNING the reference's own numpy code in this container.
+
+The reference's Keras/TensorFlow graph cannot run here, but a few functions on and next to the path are
+plain numpy inside modules that merely import TensorFlow / scipy.misc / skimage at the top.  This script
+stubs those imports, loads the reference modules from /root/reference (nothing is copied into the repo)
+and records their outputs on seeded inputs:
+
+  * evaluate_models/utils.py: compute_iou (the Dice overlap of this copy), compute_overlaps,
+    non_max_suppression                                    -> pins oracle/postprocess.py
+  * evaluate_models/test_score_dense_captions.py: the body of refine_generations (:245-283), extracted
+    with ast and executed against the reference's non_max_suppression    -> pins oracle.postprocess.refine_generations
+  * dense_img_cap_separate_models/utils.py: generate_pyramid_anchors, apply_box_deltas (numpy twin of
+    apply_box_deltas_graph)                                -> pins oracle/proposals.py
+
+Scores are made distinct: numpy's default argsort is not stable, so tie order is not a property of the
+reference.  Run from the repo root (only where /root/reference exists):
+    python tests/golden/gen_golden_reference_numpy.py
+"""
+import ast
+import hashlib
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = "/root/reference"
+
+
+def _stub(name):
+    m = types.ModuleType(name)
+    m.__path__ = []
+    sys.modules[name] = m
+    return m
+
+
+for name in ("tensorflow", "scipy.misc", "skimage", "skimage.color", "skimage.io"):
+    if name not in sys.modules or name == "scipy.misc":
+        _stub(name)
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+ev = _load(os.path.join(REF, "evaluate_models", "utils.py"), "ref_eval_utils")
+dn = _load(os.path.join(REF, "dense_img_cap_separate_models", "utils.py"), "ref_dense_utils")
+
+# refine_generations is a method of a class in a module with heavy imports: take the function node only
+src = open(os.path.join(REF, "evaluate_models", "test_score_dense_captions.py")).read()
+fn = [n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "refine_generations"][0]
+ns = {"np": np, "non_max_suppression": ev.non_max_suppression}
+exec(compile(ast.Module(body=[fn], type_ignores=[]), "refine_generations", "exec"), ns)
+ref_refine = ns["refine_generations"]
+
+rng = np.random.default_rng(20261019)
+out = {}
+
+# ---- post-processing ------------------------------------------------------------------------------
+cases = []
+for n, thr in ((1, 0.5), (17, 0.5), (200, 0.5), (200, 0.3), (300, 0.7)):
+    c = rng.uniform(0.15, 0.85, (n, 2))
+    half = rng.uniform(0.01, 0.25, (n, 2))
+    boxes = np.concatenate([c - half, c + half], 1).astype(np.float32)
+    P, V = 5, 12
+    probs = rng.dirichlet(np.ones(V) * 0.3, (n, P)).astype(np.float32)
+    scores = np.sum(np.log(np.max(probs, axis=2)), axis=1)
+    assert len(np.unique(scores)) == n
+    keep = ev.non_max_suppression(boxes, scores, thr)
+
+    class Cfg:
+        DETECTION_NMS_THRESHOLD = thr
+        DETECTION_MAX_INSTANCES = 100 if n != 300 else 20
+    rois, caps = ref_refine(None, boxes, probs, None, Cfg)
+    cases.append((boxes, probs, scores, keep, rois, caps, thr, Cfg.DETECTION_MAX_INSTANCES))
+for i, (boxes, probs, scores, keep, rois, caps, thr, mx) in enumerate(cases):
+    out["pp%d_boxes" % i], out["pp%d_probs" % i], out["pp%d_scores" % i] = boxes, probs, scores
+    out["pp%d_nms_keep" % i], out["pp%d_refined_rois" % i] = keep, rois
+    out["pp%d_refined_first_probs" % i] = caps[:, 0, :]
+    out["pp%d_params" % i] = np.array([thr, mx], np.float64)
+b1 = cases[1][0]
+area = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+out["overlaps_17"] = ev.compute_overlaps(b1, b1[:5])
+out["iou_17_row0"] = ev.compute_iou(b1[0], b1, area[0], area)
+
+# ---- anchors --------------------------------------------------------------------------------------
+scales, ratios, strides = (32, 64, 128, 256, 512), [0.5, 1, 2], [4, 8, 16, 32, 64]
+small = np.array([[int(np.ceil(128 / s)), int(np.ceil(128 / s))] for s in strides])
+full = np.array([[int(np.ceil(1024 / s)), int(np.ceil(1024 / s))] for s in strides])
+out["anchors_128"] = dn.generate_pyramid_anchors(scales, ratios, small, strides, 1)
+a_full = dn.generate_pyramid_anchors(scales, ratios, full, strides, 1)
+out["anchors_1024_shape"] = np.array(a_full.shape)
+out["anchors_1024_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(a_full.astype(np.float32)).tobytes()).digest(), np.uint8)
+out["anchors_128_stride2"] = dn.generate_pyramid_anchors(scales[:2], ratios, small[:2], strides[:2], 2)
+
+# ---- box deltas (numpy twin of apply_box_deltas_graph) ------------------------------------------
+anc = out["anchors_128"].astype(np.float32)
+deltas = (rng.standard_normal(anc.shape) * np.array([0.1, 0.1, 0.2, 0.2]) * 3).astype(np.float32)
+out["deltas_128"] = deltas
+out["refined_128"] = dn.apply_box_deltas(anc, deltas)
+assert out["refined_128"].dtype == np.float32
+
+path = os.path.join(ROOT, "tests", "golden", "reference_numpy.npz")
+np.savez_compressed(path, **out)
+print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")

@@ -1,0 +1,64 @@
+"""The oracle against outputs of the REFERENCE'S OWN numpy code (tests/golden/reference_numpy.npz, produced by
+tests/golden/gen_golden_reference_numpy.py, which imports /root/reference with TensorFlow stubbed out).
+These are the pinned parts of the oracle: post-processing NMS / refine_generations, the anchor generator and
+the box-delta arithmetic.  CPU only."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import postprocess as pp
+from oracle import proposals as pr
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_numpy.npz"))
+N_PP = 5
+
+
+@pytest.mark.parametrize("i", range(N_PP))
+def test_nms_and_refine_generations_equal_the_reference(i):
+    boxes, probs, scores = G["pp%d_boxes" % i], G["pp%d_probs" % i], G["pp%d_scores" % i]
+    thr, mx = G["pp%d_params" % i]
+    got_scores = pp.caption_scores(probs)
+    assert np.array_equal(got_scores.view(np.uint32), scores.view(np.uint32))
+    assert np.array_equal(pp.non_max_suppression(boxes, scores, thr), G["pp%d_nms_keep" % i])
+    keep = pp.refine_generations(boxes, scores, thr, int(mx))
+    assert np.array_equal(boxes[keep], G["pp%d_refined_rois" % i])
+    assert np.array_equal(probs[keep][:, 0, :], G["pp%d_refined_first_probs" % i])
+
+
+def test_dice_overlap_equals_the_reference():
+    b = G["pp1_boxes"]
+    area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    got = pp.compute_overlap(b[0], b, area[0], area)
+    assert np.array_equal(got.view(np.uint32), G["iou_17_row0"].view(np.uint32))
+    for j in range(5):
+        np.testing.assert_array_equal(pp.compute_overlap(b[j], b, area[j], area).astype(np.float64), G["overlaps_17"][:, j])
+
+
+def test_anchor_generator_equals_the_reference():
+    scales, ratios, strides = (32, 64, 128, 256, 512), [0.5, 1, 2], [4, 8, 16, 32, 64]
+    small = [[-(-128 // s)] * 2 for s in strides]
+    full = [[-(-1024 // s)] * 2 for s in strides]
+    assert np.array_equal(pr.generate_pyramid_anchors(scales, ratios, small, strides, 1), G["anchors_128"])
+    assert np.array_equal(pr.generate_pyramid_anchors(scales[:2], ratios, small[:2], strides[:2], 2), G["anchors_128_stride2"])
+    a = pr.generate_pyramid_anchors(scales, ratios, full, strides, 1)
+    assert list(a.shape) == list(G["anchors_1024_shape"]) == [261888, 4]
+    digest = hashlib.sha256(np.ascontiguousarray(a.astype(np.float32)).tobytes()).digest()
+    assert digest == G["anchors_1024_sha256"].tobytes()
+    # the product's host-side generator (image_captioning_b200.proposals) is the same function of the config
+    from image_captioning_b200 import proposals as prod
+    assert np.array_equal(prod.generate_pyramid_anchors(scales, ratios, full, strides, 1), a)
+
+
+def test_box_deltas_equal_the_reference():
+    """Same arithmetic, op by op: with numpy's own fp32 exp the reference's numpy twin is reproduced bit for bit.
+    With the correctly rounded exp the oracle defines (numpy's SIMD expf is up to 2 ulp away from it) a corner
+    moves by at most a few ulp of the box coordinates."""
+    anc = G["anchors_128"].astype(np.float32)
+    want = G["refined_128"]
+    got = pr.apply_box_deltas(anc, G["deltas_128"], exp=np.exp)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    got = pr.apply_box_deltas(anc, G["deltas_128"])
+    scale = np.maximum(np.abs(want).max(1, keepdims=True), 1.0)
+    assert (np.abs(got - want) / scale).max() <= 4 * np.finfo(np.float32).eps
