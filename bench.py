@@ -799,13 +799,128 @@ def run_ours_beam(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------
+# proposals workload: the box front-end that feeds PyramidROIAlign when RPN
+# proposals are used -- ProposalLayer on the reference's configuration, images sharded over ranks
+# --------------------------------------------------------------------------------------------
+PROP_IMAGES, PROP_COUNT, PROP_LIMIT, PROP_NMS = 32, 1000, 6000, 0.7
+
+
+def _rpn_like(gen, n_images, n_anchors, dev):
+    import torch
+    fg = torch.sigmoid(torch.randn((n_images, n_anchors), device=dev, generator=gen) * 2.5 - 4.0)
+    probs = torch.stack([1 - fg, fg], -1).contiguous()
+    bbox = torch.randn((n_images, n_anchors, 4), device=dev, generator=gen) * 1.5
+    return probs, bbox
+
+
+def run_ours_proposals(args):
+    import torch
+    import torch.distributed as dist
+    import image_captioning_b200 as pkg
+
+    rank, local_rank, world = dist_env()
+    if args.gpus != world and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sms, cc = pkg._lib.device_info()
+    cfg = pkg.ProposalConfig()
+    anchors = cfg.anchors()
+    A = anchors.shape[0]
+    layer = pkg.ProposalLayer(PROP_COUNT, PROP_NMS, anchors, cfg)
+    gen = torch.Generator(device=dev).manual_seed(1005 + rank)
+    probs, bbox = _rpn_like(gen, PROP_IMAGES, A, dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        rois = layer([probs, bbox])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    K = args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        rois = layer([probs, bbox])
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    clocks = sampler.summary()
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / K
+    value = PROP_IMAGES * world / (ms_per_step * 1e-3)
+    # algorithmic bytes per image: the [A,2] score rows once, the gathered delta + anchor rows of the candidates,
+    # the IoU bit masks written and (at most) read once, the padded output
+    n_blk = (PROP_LIMIT + 63) // 64
+    bytes_img = A * 8 + PROP_LIMIT * 32 + 2 * (PROP_LIMIT * n_blk * 8 // 2) + PROP_COUNT * 16
+    hbm_peak, hbm_src = measured_peaks("hbm_gbs")
+    achieved = bytes_img * PROP_IMAGES / (ms_per_step * 1e-3) / 1e9
+    line = {
+        "metric": "proposal_images_per_sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "proposals: ProposalLayer on %d images per GPU, %d anchors of a 1024x1024 image, top %d -> "
+                               "refine/clip -> NMS %.1f -> %d proposals" % (PROP_IMAGES, A, PROP_LIMIT, PROP_NMS, PROP_COUNT),
+                   "images_per_step": PROP_IMAGES * world, "sharding": "images per rank, no collective",
+                   "l2": "inputs larger than L2 (%d MB of RPN outputs per step)" % (PROP_IMAGES * A * 24 // 2 ** 20),
+                   "sm_count": sms, "cc": cc},
+        "clocks": clocks, "gpu_launches": K * 3,
+        "roofline": {"bound": "hbm", "kernel": "proposal_select_kernel + proposal_iou_mask_kernel + proposal_nms_scan_kernel "
+                     "(latency-bound: the NMS scan is a serial chain per image)", "achieved": round(achieved, 1), "peak": hbm_peak,
+                     "peak_source": hbm_src, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None,
+                     "algorithmic_bytes_per_image": bytes_img},
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import proposals as opr
+        p_np, b_np = probs[:2].cpu().numpy(), bbox[:2].cpu().numpy()
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 10.0:
+            want = opr.proposal_layer(p_np, b_np, anchors, PROP_COUNT, PROP_NMS, cfg.IMAGE_SHAPE)
+            n += 2
+        dt = time.perf_counter() - t0
+        got = rois[:2].cpu().numpy()
+        line["cpu_baseline"] = {"value": round(n / dt, 2), "unit": "images/s", "cores": 1, "kind": "port",
+                                "sample": "%d images of the same workload through oracle/proposals.py (numpy)" % n,
+                                "bit_exact_vs_gpu": bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))}
+    if not args.no_e2e:
+        h_p, h_b = probs.cpu().pin_memory(), bbox.cpu().pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            r = layer([h_p.to(dev, non_blocking=True), h_b.to(dev, non_blocking=True)])
+            h_r = r.cpu()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        line["e2e"] = {"value": round(PROP_IMAGES * world / float(t.item()), 1), "unit": "images/s",
+                       "h2d_bytes_per_step": int(h_p.numel() * 4 + h_b.numel() * 4), "d2h_bytes_per_step": int(h_r.numel() * 4),
+                       "steps": args.e2e_steps, "api": "ProposalLayer.__call__ (pinned host RPN outputs in, proposals out)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="captions", choices=["captions", "roi_features", "train", "beam"])
+    ap.add_argument("--workload", default="captions", choices=["captions", "roi_features", "train", "beam", "proposals"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer leg")
@@ -818,6 +933,8 @@ def main():
         run_ours_train(args)
     elif args.workload == "beam":
         run_ours_beam(args)
+    elif args.workload == "proposals":
+        run_ours_proposals(args)
     else:
         run_ours_roi_features(args)
 
