@@ -40,6 +40,12 @@ __device__ __forceinline__ uint32_t score_key(float s) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// std::min / std::max as TF's C++ kernels (and Eigen's scalar min/max behind tf.minimum / tf.maximum) evaluate them:
+// the FIRST argument is returned when the comparison is false, so a NaN first argument propagates and equal
+// operands (+-0) return the first.  fminf/fmaxf would drop the NaN.
+__device__ __forceinline__ float std_min(float a, float b) { return b < a ? b : a; }
+__device__ __forceinline__ float std_max(float a, float b) { return a < b ? b : a; }
+
 struct SelSmem {
     unsigned long long sort[kMaxPreNms];      // (key << 32) | ~anchor, only CTA 0's copy is used
     unsigned int hist[2][256];                // cluster-wide histogram of the current digit (CTA 0's copy), double buffered
@@ -227,8 +233,8 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
         width = __fmul_rn(width, (float)exp((double)d.w));
         float y1 = __fsub_rn(cy, __fmul_rn(0.5f, height)), x1 = __fsub_rn(cx, __fmul_rn(0.5f, width));
         float y2 = __fadd_rn(y1, height), x2 = __fadd_rn(x1, width);
-        y1 = fmaxf(fminf(y1, img_h), 0.f); x1 = fmaxf(fminf(x1, img_w), 0.f);
-        y2 = fmaxf(fminf(y2, img_h), 0.f); x2 = fmaxf(fminf(x2, img_w), 0.f);
+        y1 = std_max(std_min(y1, img_h), 0.f); x1 = std_max(std_min(x1, img_w), 0.f);
+        y2 = std_max(std_min(y2, img_h), 0.f); x2 = std_max(std_min(x2, img_w), 0.f);
         ws_boxes[(long long)img * k_eff + i] = make_float4(__fdiv_rn(y1, img_h), __fdiv_rn(x1, img_w),
                                                            __fdiv_rn(y2, img_h), __fdiv_rn(x2, img_w));
         ws_index[(long long)img * k_eff + i] = (int32_t)a_idx;
@@ -240,8 +246,8 @@ struct NmsBox { float ymin, xmin, ymax, xmax, area; };
 
 __device__ __forceinline__ NmsBox nms_box(float4 b) {
     NmsBox r;
-    r.ymin = fminf(b.x, b.z); r.ymax = fmaxf(b.x, b.z);
-    r.xmin = fminf(b.y, b.w); r.xmax = fmaxf(b.y, b.w);
+    r.ymin = std_min(b.x, b.z); r.ymax = std_max(b.x, b.z);
+    r.xmin = std_min(b.y, b.w); r.xmax = std_max(b.y, b.w);
     r.area = __fmul_rn(__fsub_rn(r.ymax, r.ymin), __fsub_rn(r.xmax, r.xmin));
     return r;
 }
@@ -266,8 +272,8 @@ __global__ void __launch_bounds__(64) proposal_iou_mask_kernel(const float4 *__r
         const int j1 = min(64, n - cb * 64);
         for (int j = j0; j < j1; ++j) {
             const float area_j = s_col[4][j];
-            const float ih = fmaxf(__fsub_rn(fminf(r.ymax, s_col[2][j]), fmaxf(r.ymin, s_col[0][j])), 0.f);
-            const float iw = fmaxf(__fsub_rn(fminf(r.xmax, s_col[3][j]), fmaxf(r.xmin, s_col[1][j])), 0.f);
+            const float ih = std_max(__fsub_rn(std_min(r.ymax, s_col[2][j]), std_max(r.ymin, s_col[0][j])), 0.f);
+            const float iw = std_max(__fsub_rn(std_min(r.xmax, s_col[3][j]), std_max(r.xmin, s_col[1][j])), 0.f);
             const float inter = __fmul_rn(ih, iw);
             const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(r.area, area_j), inter));
             if (area_j > 0.f && iou > thr) bits |= 1ull << j;

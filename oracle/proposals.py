@@ -82,8 +82,19 @@ def clip_boxes(boxes, window):
     """modified_dense_model.py:203-218: max(min(v, hi), lo) per corner."""
     wy1, wx1, wy2, wx2 = [F32(v) for v in window]
     b = np.asarray(boxes, F32)
-    return np.stack([np.maximum(np.minimum(b[:, 0], wy2), wy1), np.maximum(np.minimum(b[:, 1], wx2), wx1),
-                     np.maximum(np.minimum(b[:, 2], wy2), wy1), np.maximum(np.minimum(b[:, 3], wx2), wx1)], 1)
+    return np.stack([std_max(std_min(b[:, 0], wy2), wy1), std_max(std_min(b[:, 1], wx2), wx1),
+                     std_max(std_min(b[:, 2], wy2), wy1), std_max(std_min(b[:, 3], wx2), wx1)], 1)
+
+
+def std_min(a, b):
+    """std::min(a, b) / Eigen's scalar min as TF's C++ evaluates it: ``b < a ? b : a`` (a NaN first argument
+    propagates; equal operands return the first)."""
+    return np.where(np.less(b, a), b, a).astype(F32)
+
+
+def std_max(a, b):
+    """std::max(a, b): ``a < b ? b : a``."""
+    return np.where(np.less(a, b), b, a).astype(F32)
 
 
 def top_k_indices(scores, k):
@@ -93,19 +104,19 @@ def top_k_indices(scores, k):
 
 
 def tf_iou(a, b):
-    """non_max_suppression_op.cc IOU() in fp32."""
-    ymin_a, ymax_a = min(a[0], a[2]), max(a[0], a[2])
-    xmin_a, xmax_a = min(a[1], a[3]), max(a[1], a[3])
-    ymin_b, ymax_b = min(b[0], b[2]), max(b[0], b[2])
-    xmin_b, xmax_b = min(b[1], b[3]), max(b[1], b[3])
-    area_a = F32(ymax_a - ymin_a) * F32(xmax_a - xmin_a)
-    area_b = F32(ymax_b - ymin_b) * F32(xmax_b - xmin_b)
+    """non_max_suppression_op.cc IOU() in fp32 (scalar form; ``a`` is the earlier / selected box)."""
+    a, b = np.asarray(a, F32), np.asarray(b, F32)
+    ymin_a, ymax_a, xmin_a, xmax_a = std_min(a[0], a[2]), std_max(a[0], a[2]), std_min(a[1], a[3]), std_max(a[1], a[3])
+    ymin_b, ymax_b, xmin_b, xmax_b = std_min(b[0], b[2]), std_max(b[0], b[2]), std_min(b[1], b[3]), std_max(b[1], b[3])
+    area_a = (ymax_a - ymin_a) * (xmax_a - xmin_a)
+    area_b = (ymax_b - ymin_b) * (xmax_b - xmin_b)
     if area_a <= 0 or area_b <= 0:
         return F32(0)
-    ih = max(F32(min(ymax_a, ymax_b) - max(ymin_a, ymin_b)), F32(0))
-    iw = max(F32(min(xmax_a, xmax_b) - max(xmin_a, xmin_b)), F32(0))
-    inter = F32(ih * iw)
-    return F32(inter / F32(F32(area_a + area_b) - inter))
+    ih = std_max(std_min(ymax_a, ymax_b) - std_max(ymin_a, ymin_b), F32(0))
+    iw = std_max(std_min(xmax_a, xmax_b) - std_max(xmin_a, xmin_b), F32(0))
+    inter = ih * iw
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return F32(inter / ((area_a + area_b) - inter))
 
 
 def tf_non_max_suppression(boxes, scores, max_output_size, iou_threshold):
@@ -113,8 +124,8 @@ def tf_non_max_suppression(boxes, scores, max_output_size, iou_threshold):
     remaining candidates; same decisions as the candidate-vs-selected loop)."""
     b = np.asarray(boxes, F32)
     order = np.argsort(-np.asarray(scores, F32), kind="stable")
-    ymin, ymax = np.minimum(b[:, 0], b[:, 2]), np.maximum(b[:, 0], b[:, 2])
-    xmin, xmax = np.minimum(b[:, 1], b[:, 3]), np.maximum(b[:, 1], b[:, 3])
+    ymin, ymax = std_min(b[:, 0], b[:, 2]), std_max(b[:, 0], b[:, 2])
+    xmin, xmax = std_min(b[:, 1], b[:, 3]), std_max(b[:, 1], b[:, 3])
     area = (ymax - ymin) * (xmax - xmin)
     alive = np.ones(len(b), bool)
     thr = F32(iou_threshold)
@@ -129,10 +140,10 @@ def tf_non_max_suppression(boxes, scores, max_output_size, iou_threshold):
         rest = rest[alive[rest]]
         if area[i] <= 0 or rest.size == 0:
             continue
-        ih = np.maximum(np.minimum(ymax[i], ymax[rest]) - np.maximum(ymin[i], ymin[rest]), F32(0))
-        iw = np.maximum(np.minimum(xmax[i], xmax[rest]) - np.maximum(xmin[i], xmin[rest]), F32(0))
-        inter = ih * iw
         with np.errstate(divide="ignore", invalid="ignore"):
+            ih = std_max(std_min(ymax[i], ymax[rest]) - std_max(ymin[i], ymin[rest]), F32(0))
+            iw = std_max(std_min(xmax[i], xmax[rest]) - std_max(xmin[i], xmin[rest]), F32(0))
+            inter = ih * iw
             iou = inter / ((area[i] + area[rest]) - inter)
         iou = np.where(area[rest] <= 0, F32(0), iou)
         alive[rest[iou > thr]] = False

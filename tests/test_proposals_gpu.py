@@ -92,6 +92,27 @@ def test_small_pyramids_degenerate_boxes_and_short_inputs():
     _check(layer, probs[:1, :1].copy(), bbox[:1, :1].copy(), anchors[:1], 3, 0.7, cfg.IMAGE_SHAPE)
 
 
+def test_overflowing_deltas_propagate_inf_and_nan_like_the_graph():
+    """exp overflow gives +inf sizes and inf - inf = NaN corners; tf.minimum / tf.maximum (and numpy) propagate the
+    NaN through the clip, and a NaN box is never suppressed and never suppresses."""
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(66)
+    cfg = pkg.ProposalConfig(IMAGE_MAX_DIM=128)
+    anchors = cfg.anchors()
+    probs, bbox = _rpn_like(rng, 1, anchors)
+    bbox[0, ::11, 2] = 1000.0                                         # exp(200) = inf in fp32
+    bbox[0, 5::11, 3] = -1000.0                                       # exp(-200) = 0
+    layer = pkg.ProposalLayer(300, 0.7, anchors, cfg)
+    out, n_valid, index = layer([probs, bbox], return_details=True)
+    with np.errstate(all="ignore"):
+        want, picked = pr.proposal_layer(probs, bbox, anchors, 300, 0.7, cfg.IMAGE_SHAPE, return_indices=True)
+    assert np.isnan(want).any()
+    assert np.array_equal(index[0, :len(picked[0])], picked[0])
+    assert np.array_equal(np.isnan(out), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(out[ok].view(np.uint32), want[ok].view(np.uint32))
+
+
 def test_anchor_counts_that_do_not_fit_the_shared_memory_cache_use_the_streaming_path():
     import image_captioning_b200 as pkg
     rng = np.random.default_rng(63)
