@@ -252,35 +252,68 @@ __device__ __forceinline__ NmsBox nms_box(float4 b) {
     return r;
 }
 
-// mask[img][i][cb] bit t: box cb*64+t (t-th of column block cb, later than i in score order) has IoU(i, .) > thr
-__global__ void __launch_bounds__(64) proposal_iou_mask_kernel(const float4 *__restrict__ ws_boxes, int n, int n_blk, float thr,
-                                                               unsigned long long *__restrict__ mask) {
-    const int cb = blockIdx.x, rb = blockIdx.y, img = blockIdx.z, t = threadIdx.x;
-    if (cb < rb) return;                                       // lower triangle is never read
-    __shared__ float s_col[5][64];
+constexpr int kMaskColBlocks = 4;                               // a CTA covers 64 rows x (4 x 64) columns
+
+// mask[img][i][cb] bit t: box cb*64+t (later than i in score order) has IoU(i, .) > thr.  Only the upper triangle
+// (cb >= i / 64) is written and read.
+//
+// Inner loop diet (this kernel is issue-bound: 18 M box pairs per image):
+//  * fminf/fmaxf instead of the std::min/std::max selects: they differ only when a NaN is involved, and a box with
+//    a NaN corner has area NaN or 0 under either rule, i.e. it never suppresses and is never suppressed;
+//  * `inter / denom > thr` is decided without the division whenever inter is clear of thr * denom by more than the
+//    rounding of both sides (1e-6 relative); only the remaining sliver takes the IEEE division, so the decision is
+//    bit-identical to the fp32 quotient's.
+__global__ void __launch_bounds__(64 * kMaskColBlocks) proposal_iou_mask_kernel(const float4 *__restrict__ ws_boxes, int n, int n_blk,
+                                                                                float thr, unsigned long long *__restrict__ mask) {
+    const int rb = blockIdx.y, img = blockIdx.z, t = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    const int cb0 = blockIdx.x * kMaskColBlocks;
+    if (cb0 + kMaskColBlocks - 1 < rb) return;                  // whole tile below the diagonal
+    __shared__ float4 s_box[kMaskColBlocks][64];                // (ymin, xmin, ymax, xmax)
+    __shared__ float s_area[kMaskColBlocks][64];
     const float4 *boxes = ws_boxes + (long long)img * n;
+    const int cb = cb0 + sub;
     const int cj = cb * 64 + t;
-    NmsBox c = nms_box(cj < n ? __ldg(boxes + cj) : make_float4(0.f, 0.f, 0.f, 0.f));
-    s_col[0][t] = c.ymin; s_col[1][t] = c.xmin; s_col[2][t] = c.ymax; s_col[3][t] = c.xmax; s_col[4][t] = c.area;
+    const NmsBox c = nms_box(cj < n ? __ldg(boxes + cj) : make_float4(0.f, 0.f, 0.f, 0.f));
+    // columns that can never be suppressed (past the end, empty or NaN boxes: IOU() returns 0 for them and the
+    // threshold is >= 0) become an empty box at +inf: intersection exactly 0 with everything
+    const bool valid = cj < n && c.area > 0.f;
+    s_box[sub][t] = valid ? make_float4(c.ymin, c.xmin, c.ymax, c.xmax) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    s_area[sub][t] = valid ? c.area : 0.f;
     __syncthreads();
     const int i = rb * 64 + t;
-    if (i >= n) return;
+    if (i >= n || cb < rb || cb >= n_blk) return;
     const NmsBox r = nms_box(__ldg(boxes + i));
-    unsigned long long bits = 0;
+    unsigned long long bits = 0, unsure = 0;
     if (r.area > 0.f) {
-        const int j0 = cb == rb ? t + 1 : 0;
-        const int j1 = min(64, n - cb * 64);
-        for (int j = j0; j < j1; ++j) {
-            const float area_j = s_col[4][j];
-            const float ih = std_max(__fsub_rn(std_min(r.ymax, s_col[2][j]), std_max(r.ymin, s_col[0][j])), 0.f);
-            const float iw = std_max(__fsub_rn(std_min(r.xmax, s_col[3][j]), std_max(r.xmin, s_col[1][j])), 0.f);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            const float4 q = s_box[sub][j];
+            const float ih = fmaxf(__fsub_rn(fminf(r.ymax, q.z), fmaxf(r.ymin, q.x)), 0.f);
+            const float iw = fmaxf(__fsub_rn(fminf(r.xmax, q.w), fmaxf(r.xmin, q.y)), 0.f);
             const float inter = __fmul_rn(ih, iw);
-            const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(r.area, area_j), inter));
-            if (area_j > 0.f && iou > thr) bits |= 1ull << j;
+            const float denom = __fsub_rn(__fadd_rn(r.area, s_area[sub][j]), inter);
+            const float p = __fmul_rn(thr, denom);
+            const bool over = inter > __fmaf_rn(p, 1.000001f, 1e-30f);
+            const bool under = inter < __fmul_rn(p, 0.999999f) || inter == 0.f;
+            if (over) bits |= 1ull << j;
+            if (!over && !under) unsure |= 1ull << j;
         }
+        while (unsure) {                                         // the sliver around the threshold: IEEE division
+            const int j = __ffsll((long long)unsure) - 1;
+            unsure &= unsure - 1;
+            const float4 q = s_box[sub][j];
+            const float ih = fmaxf(__fsub_rn(fminf(r.ymax, q.z), fmaxf(r.ymin, q.x)), 0.f);
+            const float iw = fmaxf(__fsub_rn(fminf(r.xmax, q.w), fmaxf(r.xmin, q.y)), 0.f);
+            const float inter = __fmul_rn(ih, iw);
+            const float denom = __fsub_rn(__fadd_rn(r.area, s_area[sub][j]), inter);
+            if (__fdiv_rn(inter, denom) > thr) bits |= 1ull << j;
+        }
+        if (cb == rb) bits &= ~((2ull << t) - 1ull);            // only boxes later in score order
     }
     mask[((long long)img * n + i) * n_blk + cb] = bits;
 }
+
+constexpr int kScanBatch = 8;                                   // mask rows fetched per round trip in the OR phase
 
 __global__ void __launch_bounds__(kScanThreads) proposal_nms_scan_kernel(const float4 *__restrict__ ws_boxes,
                                                                          const int32_t *__restrict__ ws_index,
@@ -291,43 +324,61 @@ __global__ void __launch_bounds__(kScanThreads) proposal_nms_scan_kernel(const f
     extern __shared__ __align__(16) unsigned char sm_raw[];
     unsigned long long *s_removed = reinterpret_cast<unsigned long long *>(sm_raw);    // [n_blk]
     int *s_keep = reinterpret_cast<int *>(s_removed + n_blk);                            // [proposal_count]
-    __shared__ unsigned long long s_diag[64];
+    __shared__ unsigned long long s_diag[2][64];
     __shared__ unsigned long long s_kept_bits;
     __shared__ int s_count;
     const int img = blockIdx.x, tid = threadIdx.x;
     const unsigned long long *m = mask + (long long)img * n * n_blk;
     for (int c = tid; c < n_blk; c += kScanThreads) s_removed[c] = 0ull;
     if (tid == 0) s_count = 0;
+    if (tid < 64) s_diag[0][tid] = tid < n ? __ldg(m + (long long)tid * n_blk) : 0ull;
     __syncthreads();
     int count0 = 0;                                            // survivors before this block (replicated, uniform)
     for (int blk = 0; blk < n_blk; ++blk) {
         const int i0 = blk * 64, rows = min(64, n - i0);
-        if (tid < 64) s_diag[tid] = tid < rows ? __ldg(m + (long long)(i0 + tid) * n_blk + blk) : 0ull;
-        __syncthreads();
+        // the next block's diagonal words do not depend on this block's outcome: fetch them under the serial chain
+        unsigned long long next_diag = 0ull;
+        if (tid < 64 && blk + 1 < n_blk && i0 + 64 + tid < n) next_diag = __ldg(m + (long long)(i0 + 64 + tid) * n_blk + blk + 1);
         if (tid == 0) {
             unsigned long long r = s_removed[blk], kept = 0ull;
             int count = count0;
-            for (int t = 0; t < rows && count < proposal_count; ++t) {
-                if (!((r >> t) & 1ull)) {
-                    kept |= 1ull << t;
-                    ++count;
-                    r |= s_diag[t];
-                }
+            const unsigned long long *diag = s_diag[blk & 1];
+            // visit only the survivors: the next one is the lowest bit that is neither removed nor already passed
+            unsigned long long todo = rows < 64 ? (1ull << rows) - 1ull : ~0ull;
+            while (count < proposal_count) {
+                const unsigned long long avail = ~r & todo;
+                if (!avail) break;
+                const int t = __ffsll((long long)avail) - 1;
+                kept |= 1ull << t;
+                ++count;
+                r |= diag[t];
+                todo &= ~((2ull << t) - 1ull);
             }
             s_kept_bits = kept;
             s_count = count;
         }
+        if (tid < 64) s_diag[(blk + 1) & 1][tid] = next_diag;
         __syncthreads();
         const unsigned long long kept = s_kept_bits;
         const int count = s_count;
         if (tid < 64 && ((kept >> tid) & 1ull)) s_keep[count0 + __popcll(kept & ((1ull << tid) - 1ull))] = i0 + tid;
         if (count >= proposal_count) break;                    // uniform
+        // OR the survivors' mask rows into the removed set of the later blocks, kScanBatch rows per round trip
         for (int c = blk + 1 + tid; c < n_blk; c += kScanThreads) {
             unsigned long long acc = s_removed[c], bits = kept;
             while (bits) {
-                const int t = __ffsll((long long)bits) - 1;
-                bits &= bits - 1;
-                acc |= __ldg(m + (long long)(i0 + t) * n_blk + c);
+                unsigned long long w[kScanBatch];
+#pragma unroll
+                for (int q = 0; q < kScanBatch; ++q) {
+                    w[q] = 0ull;
+                    if (bits) {
+                        const int t = __ffsll((long long)bits) - 1;
+                        bits &= bits - 1;
+                        w[q] = __ldg(m + (long long)(i0 + t) * n_blk + c);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < kScanBatch; ++q) acc |= w[q];
             }
             s_removed[c] = acc;
         }
@@ -381,6 +432,7 @@ extern "C" int dc_proposal_layer(const float *rpn_probs, const float *rpn_bbox, 
     DC_REQUIRE((((uintptr_t)rpn_probs & 7) | ((uintptr_t)rpn_bbox & 15) | ((uintptr_t)anchors & 15) | ((uintptr_t)proposals & 15) |
                 ((uintptr_t)workspace & 15)) == 0, "rpn_probs must be 8-byte, rpn_bbox / anchors / proposals / workspace 16-byte aligned");
     DC_REQUIRE(image_h > 0.f && image_w > 0.f, "image size must be positive");
+    DC_REQUIRE(nms_threshold >= 0.f && nms_threshold <= 1.f, "nms_threshold must lie in [0, 1] (as tf.image.non_max_suppression requires)");
     const int k = pre_nms_limit < n_anchors ? pre_nms_limit : n_anchors;
     DC_REQUIRE(k <= kMaxPreNms, "pre_nms_limit=%d exceeds %d", k, kMaxPreNms);
     DC_REQUIRE(workspace_bytes >= dc_proposal_workspace_bytes(n_images, n_anchors, pre_nms_limit),
@@ -414,7 +466,7 @@ extern "C" int dc_proposal_layer(const float *rpn_probs, const float *rpn_bbox, 
             rpn_probs, reinterpret_cast<const float4 *>(rpn_bbox), reinterpret_cast<const float4 *>(anchors), n_anchors, k, std_dev,
             image_h, image_w, ws_boxes, ws_index);
     DC_CHECK_LAUNCH();
-    proposal_iou_mask_kernel<<<dim3(n_blk, n_blk, n_images), 64, 0, s>>>(ws_boxes, k, n_blk, nms_threshold, ws_mask);
+    proposal_iou_mask_kernel<<<dim3((n_blk + kMaskColBlocks - 1) / kMaskColBlocks, n_blk, n_images), 64 * kMaskColBlocks, 0, s>>>(ws_boxes, k, n_blk, nms_threshold, ws_mask);
     DC_CHECK_LAUNCH();
     const size_t scan_smem = (size_t)n_blk * sizeof(unsigned long long) + (size_t)proposal_count * sizeof(int);
     DC_REQUIRE(scan_smem <= 48 * 1024, "proposal_count=%d too large", proposal_count);
