@@ -9,10 +9,12 @@
 //   1. proposal_select_kernel: one CLUSTER of 8 CTAs per image.  Every CTA reads its eighth of the image's
 //      foreground scores ONCE into shared memory as order-preserving 32-bit keys; an 8-bit x 4-pass radix
 //      select finds the pre_nms_limit-th largest key with the per-pass histograms summed over the cluster in
-//      CTA 0's shared memory (DSMEM atomics); the selected (key, anchor) pairs are compacted straight into
-//      CTA 0's shared memory (DSMEM stores; ties at the threshold: lowest anchor index first, as top_k),
-//      bitonic-sorted there, and CTA 0 refines / clips / normalises the boxes in that order.
-//   2. proposal_iou_mask_kernel: 64x64 tiles of the upper triangle of the IoU > threshold relation as bit masks.
+//      CTA 0's shared memory (DSMEM atomics).  Each CTA then compacts ITS candidates (ties at the threshold:
+//      lowest anchor index first, as top_k) and bitonic-sorts them locally as 64-bit (key, ~anchor) words; the
+//      eight sorted lists are merged by ranking -- a candidate's final position is its own index plus the number
+//      of larger words in the other seven lists, found by interleaved binary searches over DSMEM -- and each
+//      CTA refines / clips / normalises its own candidates' boxes and writes them to their score-ordered slots.
+//   2. proposal_iou_mask_kernel: 64x256 tiles of the upper triangle of the IoU > threshold relation as bit masks.
 //   3. proposal_nms_scan_kernel: one CTA per image walks the boxes in score order 64 at a time (the 64-step
 //      dependency chain runs in registers of one warp, the survivors' mask rows are OR-ed by the whole CTA),
 //      stops at proposal_count, gathers the survivors and zero-pads.
@@ -46,10 +48,12 @@ __device__ __forceinline__ uint32_t score_key(float s) {
 __device__ __forceinline__ float std_min(float a, float b) { return b < a ? b : a; }
 __device__ __forceinline__ float std_max(float a, float b) { return a < b ? b : a; }
 
+constexpr int kHistCopies = 8;                  // replicated per-CTA histograms: RPN scores share few top bytes
+
 struct SelSmem {
-    unsigned long long sort[kMaxPreNms];      // (key << 32) | ~anchor, only CTA 0's copy is used
+    unsigned long long sort[kMaxPreNms];      // this CTA's candidates as (key << 32) | ~anchor, sorted descending
     unsigned int hist[2][256];                // cluster-wide histogram of the current digit (CTA 0's copy), double buffered
-    unsigned int lhist[256];                  // this CTA's histogram
+    unsigned int lhist[kHistCopies][256];     // this CTA's histogram, one copy per warp & 7
     unsigned int n_gt[kSelCluster], n_eq[kSelCluster];   // per-CTA counts, replicated in every CTA
     unsigned int warp_cnt[kSelThreads / 32];
     unsigned int sel_bin, sel_above, ctr;
@@ -67,7 +71,7 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
     const int rank = (int)cluster.block_rank();
     const int img = blockIdx.x / kSelCluster;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    SelSmem *sm0 = cluster.map_shared_rank(&sm, 0);
+    SelSmem *sm0 = cluster.map_shared_rank(&sm, 0);            // holds the cluster-wide digit histograms
 
     const int chunk = ceil_div(n_anchors, kSelCluster);
     const int lo = min(rank * chunk, n_anchors), n_local = min(lo + chunk, n_anchors) - lo;
@@ -85,10 +89,8 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
         unsigned int *hist0 = sm0->hist[pass & 1];
-        if (tid < 256) {
-            sm.lhist[tid] = 0;
-            if (rank == 0) sm.hist[pass & 1][tid] = 0;
-        }
+        for (int i = tid; i < kHistCopies * 256; i += kSelThreads) (&sm.lhist[0][0])[i] = 0;
+        if (rank == 0 && tid < 256) sm.hist[pass & 1][tid] = 0;
         cluster.sync();                                     // zeroed before any remote add; also orders s_key writes
         for (int base = 0; base < n_local; base += kSelThreads) {
             const int i = base + tid;
@@ -99,11 +101,16 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
             if (p) {
                 const unsigned int bin = (key >> shift) & 255u;
                 const unsigned int peers = __match_any_sync(bal, bin);
-                if (lane == __ffs(peers) - 1) atomicAdd(&sm.lhist[bin], (unsigned int)__popc(peers));
+                if (lane == __ffs(peers) - 1) atomicAdd(&sm.lhist[warp & (kHistCopies - 1)][bin], (unsigned int)__popc(peers));
             }
         }
         __syncthreads();
-        if (tid < 256 && sm.lhist[tid]) atomicAdd(hist0 + tid, sm.lhist[tid]);       // DSMEM
+        if (tid < 256) {
+            unsigned int c = 0;
+#pragma unroll
+            for (int r = 0; r < kHistCopies; ++r) c += sm.lhist[r][tid];
+            if (c) atomicAdd(hist0 + tid, c);                                           // DSMEM
+        }
         cluster.sync();
         if (warp == 0) {
             // lane l owns bins [8l, 8l+8); walk from the top bin down
@@ -153,18 +160,20 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
         peer->n_eq[rank] = sm.warp_cnt[1];
     }
     cluster.sync();
-    unsigned int base_pos = 0, eq_before = 0;
-    for (int r = 0; r < rank; ++r) {
+    unsigned int eq_before = 0, n_sel[kSelCluster];            // candidates per CTA (every CTA derives all of them)
+    unsigned int my_gt = 0, quota = 0;
+#pragma unroll
+    for (int r = 0; r < kSelCluster; ++r) {
         const unsigned int q = min(sm.n_eq[r], remaining > eq_before ? remaining - eq_before : 0u);
-        base_pos += sm.n_gt[r] + q;
+        n_sel[r] = sm.n_gt[r] + q;
         eq_before += sm.n_eq[r];
+        if (r == rank) { my_gt = sm.n_gt[r]; quota = q; }
     }
-    const unsigned int quota = min(sm.n_eq[rank], remaining > eq_before ? remaining - eq_before : 0u);
-    const unsigned int my_gt = sm.n_gt[rank];
+    const unsigned int n_mine = my_gt + quota;
     __syncthreads();
 
-    // ---- compaction into CTA 0's sort buffer -----------------------------------------------------------------
-    // keys above the threshold: any order (they are sorted afterwards); ties: the first `quota` in anchor order
+    // ---- compaction into this CTA's sort buffer ---------------------------------------------------------------
+    // keys above the threshold: any order (they are sorted next); ties: the first `quota` in anchor order
     unsigned int eq_run = 0;                                   // ties seen so far in this CTA (uniform)
     for (int base = 0; base < n_local; base += kSelThreads) {
         const int i = base + tid;
@@ -179,7 +188,7 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
             const int leader = __ffs(bal_gt) - 1;
             if (lane == leader) pos = atomicAdd(&sm.ctr, (unsigned int)__popc(bal_gt));
             pos = __shfl_sync(bal_gt, pos, leader) + __popc(bal_gt & ((1u << lane) - 1u));
-            sm0->sort[base_pos + pos] = comp;
+            sm.sort[pos] = comp;
         }
         if (eq_run < quota) {                                  // uniform
             const unsigned int bal_eq = __ballot_sync(0xffffffffu, eq);
@@ -192,19 +201,17 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
                 total += c;
             }
             const unsigned int r = eq_run + before + __popc(bal_eq & ((1u << lane) - 1u));
-            if (eq && r < quota) sm0->sort[base_pos + my_gt + r] = comp;
+            if (eq && r < quota) sm.sort[my_gt + r] = comp;
             eq_run += total;
             __syncthreads();
         }
     }
-    int n_pad = 2;
-    while (n_pad < k_eff) n_pad <<= 1;
-    if (rank == 0)
-        for (int i = k_eff + tid; i < n_pad; i += kSelThreads) sm.sort[i] = 0ull;
-    cluster.sync();                                            // all remote stores have landed
-    if (rank != 0) return;
-
-    // ---- CTA 0: sort descending by (key, ~anchor) = score descending, anchor ascending ----------------------
+    // ---- local sort, descending by (key, ~anchor) = score descending, anchor ascending --------------------------
+    // every real word is > 0 (~anchor >= 1), so zero padding sorts last; the padded length is a power of two
+    auto pad_len = [](unsigned int c) { int p = 2; while (p < (int)c) p <<= 1; return p; };
+    const int n_pad = pad_len(n_mine);
+    for (int i = (int)n_mine + tid; i < n_pad; i += kSelThreads) sm.sort[i] = 0ull;
+    __syncthreads();
     for (int k = 2; k <= n_pad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < (n_pad >> 1); t += kSelThreads) {
@@ -217,10 +224,38 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
             __syncthreads();
         }
     }
+    cluster.sync();                                            // every CTA's sorted list is visible cluster-wide
 
-    // ---- refine, clip, normalise (modified_dense_model.py:179-218, :287) ------------------------------------
-    for (int i = tid; i < k_eff; i += kSelThreads) {
-        const uint32_t a_idx = 0xffffffffu - (uint32_t)sm.sort[i];
+    // ---- merge by ranking: position = own index + number of larger words in each of the other seven lists ------
+    // (all words are distinct: the anchor index is part of them); the seven binary searches run interleaved so
+    // that their DSMEM round trips overlap.  Then refine / clip / normalise the box (modified_dense_model.py:
+    // 179-218, :287) and write it to its final, score-ordered slot.
+    const unsigned long long *lists[kSelCluster];
+    int pads[kSelCluster], max_pad = 0;
+#pragma unroll
+    for (int r = 0; r < kSelCluster; ++r) {
+        lists[r] = cluster.map_shared_rank(&sm, r)->sort;
+        pads[r] = (r == rank || n_sel[r] == 0) ? 0 : pad_len(n_sel[r]);
+        max_pad = max(max_pad, pads[r]);
+    }
+    for (int e = tid; e < (int)n_mine; e += kSelThreads) {
+        const unsigned long long comp = sm.sort[e];
+        int pos[kSelCluster];
+#pragma unroll
+        for (int r = 0; r < kSelCluster; ++r) pos[r] = 0;
+        for (int step = max_pad >> 1; step > 0; step >>= 1) {
+            unsigned long long v[kSelCluster];
+#pragma unroll
+            for (int r = 0; r < kSelCluster; ++r) v[r] = step < pads[r] ? lists[r][pos[r] + step - 1] : 0ull;
+#pragma unroll
+            for (int r = 0; r < kSelCluster; ++r) pos[r] += v[r] > comp ? step : 0;
+        }
+        int final_pos = e;
+#pragma unroll
+        for (int r = 0; r < kSelCluster; ++r)
+            if (pads[r]) final_pos += pos[r] + (lists[r][pos[r]] > comp ? 1 : 0);
+
+        const uint32_t a_idx = 0xffffffffu - (uint32_t)comp;
         const float4 a = __ldg(anchors + a_idx);               // (y1, x1, y2, x2) pixels
         float4 d = __ldg(rpn_bbox + (long long)img * n_anchors + a_idx);
         d.x = __fmul_rn(d.x, std_dev.x); d.y = __fmul_rn(d.y, std_dev.y);
@@ -235,10 +270,11 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
         float y2 = __fadd_rn(y1, height), x2 = __fadd_rn(x1, width);
         y1 = std_max(std_min(y1, img_h), 0.f); x1 = std_max(std_min(x1, img_w), 0.f);
         y2 = std_max(std_min(y2, img_h), 0.f); x2 = std_max(std_min(x2, img_w), 0.f);
-        ws_boxes[(long long)img * k_eff + i] = make_float4(__fdiv_rn(y1, img_h), __fdiv_rn(x1, img_w),
-                                                           __fdiv_rn(y2, img_h), __fdiv_rn(x2, img_w));
-        ws_index[(long long)img * k_eff + i] = (int32_t)a_idx;
+        ws_boxes[(long long)img * k_eff + final_pos] = make_float4(__fdiv_rn(y1, img_h), __fdiv_rn(x1, img_w),
+                                                                   __fdiv_rn(y2, img_h), __fdiv_rn(x2, img_w));
+        ws_index[(long long)img * k_eff + final_pos] = (int32_t)a_idx;
     }
+    cluster.sync();                                            // no CTA leaves while its list may still be read
 }
 
 // tf.image.non_max_suppression's IOU() (non_max_suppression_op.cc): corners min/max-normalised by the caller.
@@ -313,7 +349,7 @@ __global__ void __launch_bounds__(64 * kMaskColBlocks) proposal_iou_mask_kernel(
     mask[((long long)img * n + i) * n_blk + cb] = bits;
 }
 
-constexpr int kScanBatch = 8;                                   // mask rows fetched per round trip in the OR phase
+constexpr int kScanBatch = 4;                                   // mask words in flight per thread in the OR phase
 
 __global__ void __launch_bounds__(kScanThreads) proposal_nms_scan_kernel(const float4 *__restrict__ ws_boxes,
                                                                          const int32_t *__restrict__ ws_index,
@@ -363,24 +399,29 @@ __global__ void __launch_bounds__(kScanThreads) proposal_nms_scan_kernel(const f
         const int count = s_count;
         if (tid < 64 && ((kept >> tid) & 1ull)) s_keep[count0 + __popcll(kept & ((1ull << tid) - 1ull))] = i0 + tid;
         if (count >= proposal_count) break;                    // uniform
-        // OR the survivors' mask rows into the removed set of the later blocks, kScanBatch rows per round trip
-        for (int c = blk + 1 + tid; c < n_blk; c += kScanThreads) {
-            unsigned long long acc = s_removed[c], bits = kept;
-            while (bits) {
+        __syncthreads();                                       // s_keep of this block is read below
+        // OR the survivors' mask rows into the removed set of the later blocks: one (row, column) word per thread
+        // and round, kScanBatch independent fetches in flight per thread
+        {
+            const int n_kept = count - count0, n_cols = n_blk - blk - 1, total = n_kept * n_cols;
+            for (int base = tid; base < total; base += kScanThreads * kScanBatch) {
                 unsigned long long w[kScanBatch];
+                int col[kScanBatch];
 #pragma unroll
                 for (int q = 0; q < kScanBatch; ++q) {
+                    const int idx = base + q * kScanThreads;
                     w[q] = 0ull;
-                    if (bits) {
-                        const int t = __ffsll((long long)bits) - 1;
-                        bits &= bits - 1;
-                        w[q] = __ldg(m + (long long)(i0 + t) * n_blk + c);
+                    col[q] = 0;
+                    if (idx < total) {
+                        const int row = s_keep[count0 + idx / n_cols];
+                        col[q] = blk + 1 + idx % n_cols;
+                        w[q] = __ldg(m + (long long)row * n_blk + col[q]);
                     }
                 }
 #pragma unroll
-                for (int q = 0; q < kScanBatch; ++q) acc |= w[q];
+                for (int q = 0; q < kScanBatch; ++q)
+                    if (w[q]) atomicOr(&s_removed[col[q]], w[q]);
             }
-            s_removed[c] = acc;
         }
         count0 = count;
         __syncthreads();
