@@ -806,12 +806,36 @@ def run_ours_beam(args):
 PROP_IMAGES, PROP_COUNT, PROP_LIMIT, PROP_NMS = 32, 1000, 6000, 0.7
 
 
-def _rpn_like(gen, n_images, n_anchors, dev):
+def _rpn_like(gen, n_images, anchors, dev, n_objects=40):
+    """RPN-like synthetic outputs: per image a few dozen "objects"; an anchor's foreground score falls off with
+    its distance and scale mismatch to the nearest object, and its deltas regress towards that object (plus
+    noise).  The top-6000 anchors therefore cluster around the objects and NMS has real work (with i.i.d. boxes
+    almost nothing is suppressed and the scan would stop after ~1000 boxes)."""
     import torch
-    fg = torch.sigmoid(torch.randn((n_images, n_anchors), device=dev, generator=gen) * 2.5 - 4.0)
-    probs = torch.stack([1 - fg, fg], -1).contiguous()
-    bbox = torch.randn((n_images, n_anchors, 4), device=dev, generator=gen) * 1.5
-    return probs, bbox
+    a = torch.from_numpy(anchors.astype(np.float32)).to(dev)
+    ah, aw = a[:, 2] - a[:, 0], a[:, 3] - a[:, 1]
+    acy, acx = a[:, 0] + 0.5 * ah, a[:, 1] + 0.5 * aw
+    asz = torch.sqrt(ah * aw)
+    A = a.shape[0]
+    probs = torch.empty((n_images, A, 2), device=dev)
+    bbox = torch.empty((n_images, A, 4), device=dev)
+    std = torch.tensor([0.1, 0.1, 0.2, 0.2], device=dev)
+    for b in range(n_images):
+        oc = torch.rand((n_objects, 2), device=dev, generator=gen) * 1024.0
+        osz = torch.exp(torch.rand((n_objects,), device=dev, generator=gen) * (np.log(512.0) - np.log(32.0)) + np.log(32.0))
+        oasp = torch.exp((torch.rand((n_objects,), device=dev, generator=gen) - 0.5) * 1.2)
+        d2 = ((acy[:, None] - oc[None, :, 0]) ** 2 + (acx[:, None] - oc[None, :, 1]) ** 2) / (osz[None] ** 2)
+        aff = torch.exp(-3.0 * d2 - torch.log2(asz[:, None] / osz[None]) ** 2)
+        best, which = aff.max(1)
+        logit = 9.0 * best - 6.0 + 0.7 * torch.randn((A,), device=dev, generator=gen)
+        fg = torch.sigmoid(logit)
+        probs[b, :, 0], probs[b, :, 1] = 1 - fg, fg
+        oh, ow = osz[which] * torch.sqrt(oasp[which]), osz[which] / torch.sqrt(oasp[which])
+        tgt = torch.stack([(oc[which, 0] - acy) / ah, (oc[which, 1] - acx) / aw, torch.log(oh / ah), torch.log(ow / aw)], 1)
+        near = (best > 0.05).float()[:, None]                  # far anchors regress nothing in particular
+        noise = torch.randn((A, 4), device=dev, generator=gen)
+        bbox[b] = (tgt * near + noise * (0.2 + 0.4 * (1 - near))) / std
+    return probs.contiguous(), bbox.contiguous()
 
 
 def run_ours_proposals(args):
@@ -832,7 +856,7 @@ def run_ours_proposals(args):
     A = anchors.shape[0]
     layer = pkg.ProposalLayer(PROP_COUNT, PROP_NMS, anchors, cfg)
     gen = torch.Generator(device=dev).manual_seed(1005 + rank)
-    probs, bbox = _rpn_like(gen, PROP_IMAGES, A, dev)
+    probs, bbox = _rpn_like(gen, PROP_IMAGES, anchors, dev)
 
     def barrier():
         if world > 1:
@@ -871,7 +895,8 @@ def run_ours_proposals(args):
         "warmup": W, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "proposals: ProposalLayer on %d images per GPU, %d anchors of a 1024x1024 image, top %d -> "
-                               "refine/clip -> NMS %.1f -> %d proposals" % (PROP_IMAGES, A, PROP_LIMIT, PROP_NMS, PROP_COUNT),
+                               "refine/clip -> NMS %.1f -> %d proposals; synthetic RPN outputs clustered around 40 objects per image"
+                               % (PROP_IMAGES, A, PROP_LIMIT, PROP_NMS, PROP_COUNT),
                    "images_per_step": PROP_IMAGES * world, "sharding": "images per rank, no collective",
                    "l2": "inputs larger than L2 (%d MB of RPN outputs per step)" % (PROP_IMAGES * A * 24 // 2 ** 20),
                    "sm_count": sms, "cc": cc},
@@ -881,18 +906,8 @@ def run_ours_proposals(args):
                      "peak_source": hbm_src, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None,
                      "algorithmic_bytes_per_image": bytes_img},
     }
-    if rank == 0 and not args.no_cpu_baseline:
-        from oracle import proposals as opr
-        p_np, b_np = probs[:2].cpu().numpy(), bbox[:2].cpu().numpy()
-        t0, n = time.perf_counter(), 0
-        while time.perf_counter() - t0 < 10.0:
-            want = opr.proposal_layer(p_np, b_np, anchors, PROP_COUNT, PROP_NMS, cfg.IMAGE_SHAPE)
-            n += 2
-        dt = time.perf_counter() - t0
-        got = rois[:2].cpu().numpy()
-        line["cpu_baseline"] = {"value": round(n / dt, 2), "unit": "images/s", "cores": 1, "kind": "port",
-                                "sample": "%d images of the same workload through oracle/proposals.py (numpy)" % n,
-                                "bit_exact_vs_gpu": bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))}
+    n_valid = layer([probs, bbox], return_details=True)[1]
+    line["config"]["proposals_found_per_image"] = [int(n_valid.min()), float(n_valid.float().mean()), int(n_valid.max())]
     if not args.no_e2e:
         h_p, h_b = probs.cpu().pin_memory(), bbox.cpu().pin_memory()
         barrier()
@@ -908,6 +923,18 @@ def run_ours_proposals(args):
         line["e2e"] = {"value": round(PROP_IMAGES * world / float(t.item()), 1), "unit": "images/s",
                        "h2d_bytes_per_step": int(h_p.numel() * 4 + h_b.numel() * 4), "d2h_bytes_per_step": int(h_r.numel() * 4),
                        "steps": args.e2e_steps, "api": "ProposalLayer.__call__ (pinned host RPN outputs in, proposals out)"}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import proposals as opr
+        p_np, b_np = probs[:2].cpu().numpy(), bbox[:2].cpu().numpy()
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 10.0:
+            want = opr.proposal_layer(p_np, b_np, anchors, PROP_COUNT, PROP_NMS, cfg.IMAGE_SHAPE)
+            n += 2
+        dt = time.perf_counter() - t0
+        got = rois[:2].cpu().numpy()
+        line["cpu_baseline"] = {"value": round(n / dt, 2), "unit": "images/s", "cores": 1, "kind": "port",
+                                "sample": "%d images of the same workload through oracle/proposals.py (numpy)" % n,
+                                "bit_exact_vs_gpu": bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
