@@ -10,7 +10,8 @@
 //      foreground scores ONCE into shared memory as order-preserving 32-bit keys; an 8-bit x 4-pass radix
 //      select finds the pre_nms_limit-th largest key with the per-pass histograms summed over the cluster in
 //      CTA 0's shared memory (DSMEM atomics).  Each CTA then compacts ITS candidates (ties at the threshold:
-//      lowest anchor index first, as top_k) and bitonic-sorts them locally as 64-bit (key, ~anchor) words; the
+//      lowest anchor index first, as top_k), deals them evenly over the cluster (DSMEM stores) and every CTA
+//      bitonic-sorts its share as 64-bit (key, ~anchor) words; the
 //      eight sorted lists are merged by ranking -- a candidate's final position is its own index plus the number
 //      of larger words in the other seven lists, found by interleaved binary searches over DSMEM -- and each
 //      CTA refines / clips / normalises its own candidates' boxes and writes them to their score-ordered slots.
@@ -32,7 +33,7 @@ namespace dcap {
 constexpr int kSelThreads = 1024;
 constexpr int kSelCluster = 8;
 constexpr int kMaxPreNms = 8192;
-constexpr int kSelMaxChunk = 36 * 1024;          // keys cached in shared memory per CTA (144 KB) -> 294912 anchors per image
+constexpr int kSelMaxChunk = 48 * 1024;          // keys cached in shared memory per CTA (192 KB) -> 393216 anchors per image
 constexpr int kScanThreads = 256;
 
 // Descending-score order as ascending-key order reversed: larger score <-> larger key.  -0 == +0; NaN sorts last.
@@ -51,7 +52,7 @@ __device__ __forceinline__ float std_max(float a, float b) { return a < b ? b : 
 constexpr int kHistCopies = 8;                  // replicated per-CTA histograms: RPN scores share few top bytes
 
 struct SelSmem {
-    unsigned long long sort[kMaxPreNms];      // this CTA's candidates as (key << 32) | ~anchor, sorted descending
+    unsigned long long sort[kMaxPreNms / kSelCluster];   // this CTA's share of the candidates as (key << 32) | ~anchor, sorted descending
     unsigned int hist[2][256];                // cluster-wide histogram of the current digit (CTA 0's copy), double buffered
     unsigned int lhist[kHistCopies][256];     // this CTA's histogram, one copy per warp & 7
     unsigned int n_gt[kSelCluster], n_eq[kSelCluster];   // per-CTA counts, replicated in every CTA
@@ -160,20 +161,30 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
         peer->n_eq[rank] = sm.warp_cnt[1];
     }
     cluster.sync();
-    unsigned int eq_before = 0, n_sel[kSelCluster];            // candidates per CTA (every CTA derives all of them)
-    unsigned int my_gt = 0, quota = 0;
+    // Candidates are re-dealt evenly over the cluster before sorting (RPN scores cluster spatially, so one CTA's
+    // slice may hold most of them): CTA r's candidates take the virtual slots [base, base + count) of a k_eff-long
+    // array, and virtual slot v lives in CTA v / per at index v % per.
+    unsigned int eq_before = 0, base_pos = 0, my_gt = 0, quota = 0;
 #pragma unroll
     for (int r = 0; r < kSelCluster; ++r) {
         const unsigned int q = min(sm.n_eq[r], remaining > eq_before ? remaining - eq_before : 0u);
-        n_sel[r] = sm.n_gt[r] + q;
-        eq_before += sm.n_eq[r];
         if (r == rank) { my_gt = sm.n_gt[r]; quota = q; }
+        if (r < rank) base_pos += sm.n_gt[r] + q;
+        eq_before += sm.n_eq[r];
     }
-    const unsigned int n_mine = my_gt + quota;
+    const unsigned int per = (unsigned int)ceil_div(k_eff, kSelCluster);
+    unsigned int n_sel[kSelCluster];                           // candidates per CTA after the deal
+#pragma unroll
+    for (int r = 0; r < kSelCluster; ++r)
+        n_sel[r] = (unsigned int)max(0, min((int)per, k_eff - r * (int)per));
+    const unsigned int n_mine = (unsigned int)max(0, min((int)per, k_eff - rank * (int)per));
+    auto deal = [&](unsigned int v, unsigned long long comp) {
+        cluster.map_shared_rank(&sm, v / per)->sort[v % per] = comp;                    // DSMEM store
+    };
     __syncthreads();
 
-    // ---- compaction into this CTA's sort buffer ---------------------------------------------------------------
-    // keys above the threshold: any order (they are sorted next); ties: the first `quota` in anchor order
+    // ---- compaction: keys above the threshold in any order (they are sorted next); ties: the first `quota` in
+    // anchor order -------------------------------------------------------------------------------------------
     unsigned int eq_run = 0;                                   // ties seen so far in this CTA (uniform)
     for (int base = 0; base < n_local; base += kSelThreads) {
         const int i = base + tid;
@@ -188,7 +199,7 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
             const int leader = __ffs(bal_gt) - 1;
             if (lane == leader) pos = atomicAdd(&sm.ctr, (unsigned int)__popc(bal_gt));
             pos = __shfl_sync(bal_gt, pos, leader) + __popc(bal_gt & ((1u << lane) - 1u));
-            sm.sort[pos] = comp;
+            deal(base_pos + pos, comp);
         }
         if (eq_run < quota) {                                  // uniform
             const unsigned int bal_eq = __ballot_sync(0xffffffffu, eq);
@@ -201,11 +212,12 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
                 total += c;
             }
             const unsigned int r = eq_run + before + __popc(bal_eq & ((1u << lane) - 1u));
-            if (eq && r < quota) sm.sort[my_gt + r] = comp;
+            if (eq && r < quota) deal(base_pos + my_gt + r, comp);
             eq_run += total;
             __syncthreads();
         }
     }
+    cluster.sync();                                            // every dealt candidate has landed
     // ---- local sort, descending by (key, ~anchor) = score descending, anchor ascending --------------------------
     // every real word is > 0 (~anchor >= 1), so zero padding sorts last; the padded length is a power of two
     auto pad_len = [](unsigned int c) { int p = 2; while (p < (int)c) p <<= 1; return p; };

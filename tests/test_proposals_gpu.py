@@ -116,9 +116,9 @@ def test_overflowing_deltas_propagate_inf_and_nan_like_the_graph():
 def test_anchor_counts_that_do_not_fit_the_shared_memory_cache_use_the_streaming_path():
     import image_captioning_b200 as pkg
     rng = np.random.default_rng(63)
-    cfg = pkg.ProposalConfig(IMAGE_MAX_DIM=1152)                      # 331452 anchors > 8 * 36864
+    cfg = pkg.ProposalConfig(IMAGE_MAX_DIM=1280)                      # 409200 anchors > 8 * 49152
     anchors = cfg.anchors()
-    assert anchors.shape[0] > 8 * 36 * 1024
+    assert anchors.shape[0] > 8 * 48 * 1024
     probs, bbox = _rpn_like(rng, 1, anchors)
     layer = pkg.ProposalLayer(500, 0.7, anchors, cfg)
     _check(layer, probs, bbox, anchors, 500, 0.7, cfg.IMAGE_SHAPE)
