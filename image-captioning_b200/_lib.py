@@ -57,7 +57,7 @@ SIGNATURES = {
     "dc_decoder_greedy_scored": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void]),
     "dc_refine_generations": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                              c_void, c_void, c_void]),
-    "dc_proposal_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "dc_proposal_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "dc_proposal_layer": (ctypes.c_int, [c_void, c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, ctypes.c_float,
                                          ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_float, c_void, c_void, c_void,
                                          c_void, ctypes.c_size_t, c_void]),

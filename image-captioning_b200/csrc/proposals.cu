@@ -4,7 +4,8 @@
 // tf.nn.top_k(6000) -> gather -> apply_box_deltas_graph (:179-200) -> clip_boxes_graph (:203-218) ->
 // / [h,w,h,w] -> tf.image.non_max_suppression -> zero pad) and the Lambda at :1523-1526.
 //
-// Three launches per batch, all HBM/L2-latency-bound integer and fp32 work (no tensor cores):
+// Three kernels (select once; masks + scan per band of candidates), all latency- or issue-bound integer and fp32
+// work (no tensor cores):
 //
 //   1. proposal_select_kernel: one CLUSTER of 8 CTAs per image.  Every CTA reads its eighth of the image's
 //      foreground scores ONCE into shared memory as order-preserving 32-bit keys; an 8-bit x 4-pass radix
@@ -19,6 +20,7 @@
 //   3. proposal_nms_scan_kernel: one CTA per image walks the boxes in score order 64 at a time (the 64-step
 //      dependency chain runs in registers of one warp, the survivors' mask rows are OR-ed by the whole CTA),
 //      stops at proposal_count, gathers the survivors and zero-pads.
+//   2 and 3 alternate over bands of 16 x 64 candidates; an image that has all its proposals skips the later bands.
 //
 // fp32 arithmetic op for op as the TF graph (explicit _rn intrinsics: no FMA contraction); tf.exp is the
 // correctly rounded fp32 exponential (fp64 exp rounded once), as in oracle/proposals.py.
@@ -34,7 +36,9 @@ constexpr int kSelThreads = 1024;
 constexpr int kSelCluster = 8;
 constexpr int kMaxPreNms = 8192;
 constexpr int kSelMaxChunk = 48 * 1024;          // keys cached in shared memory per CTA (192 KB) -> 393216 anchors per image
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 1024;               // the OR phase wants many independent fetches in flight
+constexpr int kBandBlocks = 16;                  // NMS runs in bands of 16 x 64 candidates (mask launch + scan launch per band),
+constexpr int kMaxBands = 4;                     // the last band taking whatever is left
 
 // Descending-score order as ascending-key order reversed: larger score <-> larger key.  -0 == +0; NaN sorts last.
 __device__ __forceinline__ uint32_t score_key(float s) {
@@ -311,11 +315,16 @@ constexpr int kMaskColBlocks = 4;                               // a CTA covers 
 //  * `inter / denom > thr` is decided without the division whenever inter is clear of thr * denom by more than the
 //    rounding of both sides (1e-6 relative); only the remaining sliver takes the IEEE division, so the decision is
 //    bit-identical to the fp32 quotient's.
+// The rows are processed in BANDS of row blocks (rb0 .. rb0 + gridDim.y), each band followed by the scan over the
+// same rows: once an image has its proposal_count survivors (`done`), the later bands of that image return at once
+// -- the scan stops early on real RPN outputs, and the mask rows past that point would never be read.
 __global__ void __launch_bounds__(64 * kMaskColBlocks) proposal_iou_mask_kernel(const float4 *__restrict__ ws_boxes, int n, int n_blk,
-                                                                                float thr, unsigned long long *__restrict__ mask) {
-    const int rb = blockIdx.y, img = blockIdx.z, t = threadIdx.x & 63, sub = threadIdx.x >> 6;
+                                                                                float thr, unsigned long long *__restrict__ mask,
+                                                                                int rb0, const int32_t *__restrict__ done) {
+    const int rb = rb0 + blockIdx.y, img = blockIdx.z, t = threadIdx.x & 63, sub = threadIdx.x >> 6;
     const int cb0 = blockIdx.x * kMaskColBlocks;
     if (cb0 + kMaskColBlocks - 1 < rb) return;                  // whole tile below the diagonal
+    if (done && done[img]) return;                              // this image already has all its proposals
     __shared__ float4 s_box[kMaskColBlocks][64];                // (ymin, xmin, ymax, xmax)
     __shared__ float s_area[kMaskColBlocks][64];
     const float4 *boxes = ws_boxes + (long long)img * n;
@@ -363,10 +372,19 @@ __global__ void __launch_bounds__(64 * kMaskColBlocks) proposal_iou_mask_kernel(
 
 constexpr int kScanBatch = 4;                                   // mask words in flight per thread in the OR phase
 
+// Scan state carried from one band to the next (global memory, per image).
+struct ScanState {
+    unsigned long long *removed;   // [n_images, n_blk]
+    int32_t *keep;                 // [n_images, proposal_count] sorted positions of the survivors
+    int32_t *count;                // [n_images]
+    int32_t *done;                 // [n_images] 1 once the output has been written
+};
+
 __global__ void __launch_bounds__(kScanThreads) proposal_nms_scan_kernel(const float4 *__restrict__ ws_boxes,
                                                                          const int32_t *__restrict__ ws_index,
                                                                          const unsigned long long *__restrict__ mask, int n,
-                                                                         int n_blk, int proposal_count, float4 *__restrict__ proposals,
+                                                                         int n_blk, int proposal_count, int blk0, int blk1,
+                                                                         ScanState st, float4 *__restrict__ proposals,
                                                                          int32_t *__restrict__ n_valid,
                                                                          int32_t *__restrict__ anchor_index) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -376,17 +394,22 @@ __global__ void __launch_bounds__(kScanThreads) proposal_nms_scan_kernel(const f
     __shared__ unsigned long long s_kept_bits;
     __shared__ int s_count;
     const int img = blockIdx.x, tid = threadIdx.x;
+    const bool first = blk0 == 0, last = blk1 >= n_blk;
+    if (!first && st.done[img]) return;                        // finished in an earlier band (uniform)
     const unsigned long long *m = mask + (long long)img * n * n_blk;
-    for (int c = tid; c < n_blk; c += kScanThreads) s_removed[c] = 0ull;
-    if (tid == 0) s_count = 0;
-    if (tid < 64) s_diag[0][tid] = tid < n ? __ldg(m + (long long)tid * n_blk) : 0ull;
+    int count0 = first ? 0 : st.count[img];                    // survivors before this block (replicated, uniform)
+    for (int c = tid; c < n_blk; c += kScanThreads) s_removed[c] = first ? 0ull : st.removed[(long long)img * n_blk + c];
+    if (!first)
+        for (int j = tid; j < count0; j += kScanThreads) s_keep[j] = st.keep[(long long)img * proposal_count + j];
+    if (tid == 0) s_count = count0;
+    if (tid < 64) s_diag[blk0 & 1][tid] = blk0 * 64 + tid < n ? __ldg(m + (long long)(blk0 * 64 + tid) * n_blk + blk0) : 0ull;
     __syncthreads();
-    int count0 = 0;                                            // survivors before this block (replicated, uniform)
-    for (int blk = 0; blk < n_blk; ++blk) {
+    for (int blk = blk0; blk < blk1; ++blk) {
         const int i0 = blk * 64, rows = min(64, n - i0);
         // the next block's diagonal words do not depend on this block's outcome: fetch them under the serial chain
+        // (within the band: the next band's mask rows do not exist yet)
         unsigned long long next_diag = 0ull;
-        if (tid < 64 && blk + 1 < n_blk && i0 + 64 + tid < n) next_diag = __ldg(m + (long long)(i0 + 64 + tid) * n_blk + blk + 1);
+        if (tid < 64 && blk + 1 < blk1 && i0 + 64 + tid < n) next_diag = __ldg(m + (long long)(i0 + 64 + tid) * n_blk + blk + 1);
         if (tid == 0) {
             unsigned long long r = s_removed[blk], kept = 0ull;
             int count = count0;
@@ -410,7 +433,7 @@ __global__ void __launch_bounds__(kScanThreads) proposal_nms_scan_kernel(const f
         const unsigned long long kept = s_kept_bits;
         const int count = s_count;
         if (tid < 64 && ((kept >> tid) & 1ull)) s_keep[count0 + __popcll(kept & ((1ull << tid) - 1ull))] = i0 + tid;
-        if (count >= proposal_count) break;                    // uniform
+        if (count >= proposal_count) { count0 = count; break; }  // uniform
         __syncthreads();                                       // s_keep of this block is read below
         // OR the survivors' mask rows into the removed set of the later blocks: one (row, column) word per thread
         // and round, kScanBatch independent fetches in flight per thread
@@ -439,7 +462,13 @@ __global__ void __launch_bounds__(kScanThreads) proposal_nms_scan_kernel(const f
         __syncthreads();
     }
     __syncthreads();
-    const int count = s_count;
+    const int count = count0;
+    if (count < proposal_count && !last) {                     // carry the state into the next band
+        for (int c = tid; c < n_blk; c += kScanThreads) st.removed[(long long)img * n_blk + c] = s_removed[c];
+        for (int j = tid; j < count; j += kScanThreads) st.keep[(long long)img * proposal_count + j] = s_keep[j];
+        if (tid == 0) { st.count[img] = count; st.done[img] = 0; }
+        return;
+    }
     for (int j = tid; j < proposal_count; j += kScanThreads) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         int a = -1;
@@ -451,7 +480,10 @@ __global__ void __launch_bounds__(kScanThreads) proposal_nms_scan_kernel(const f
         proposals[(long long)img * proposal_count + j] = v;
         if (anchor_index) anchor_index[(long long)img * proposal_count + j] = a;
     }
-    if (tid == 0 && n_valid) n_valid[img] = count;
+    if (tid == 0) {
+        if (n_valid) n_valid[img] = count;
+        st.done[img] = 1;
+    }
 }
 
 __global__ void normalize_boxes_kernel(const float4 *__restrict__ in, long long n, float h, float w, float4 *__restrict__ out) {
@@ -467,12 +499,15 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 using namespace dcap;
 
-extern "C" size_t dc_proposal_workspace_bytes(int n_images, int n_anchors, int pre_nms_limit) {
-    if (n_images <= 0 || n_anchors <= 0 || pre_nms_limit <= 0) return 0;
+extern "C" size_t dc_proposal_workspace_bytes(int n_images, int n_anchors, int pre_nms_limit, int proposal_count) {
+    if (n_images <= 0 || n_anchors <= 0 || pre_nms_limit <= 0 || proposal_count <= 0) return 0;
     const size_t k = (size_t)(pre_nms_limit < n_anchors ? pre_nms_limit : n_anchors);
     const size_t n_blk = (k + 63) / 64;
     return align256((size_t)n_images * k * sizeof(float4)) + align256((size_t)n_images * k * sizeof(int32_t)) +
-           align256((size_t)n_images * k * n_blk * sizeof(unsigned long long));
+           align256((size_t)n_images * k * n_blk * sizeof(unsigned long long)) +
+           align256((size_t)n_images * n_blk * sizeof(unsigned long long)) +                // scan state: removed set,
+           align256((size_t)n_images * (size_t)proposal_count * sizeof(int32_t)) +          // survivors so far,
+           2 * align256((size_t)n_images * sizeof(int32_t));                                // count, done
 }
 
 extern "C" int dc_proposal_layer(const float *rpn_probs, const float *rpn_bbox, const float *anchors, int n_images,
@@ -488,8 +523,9 @@ extern "C" int dc_proposal_layer(const float *rpn_probs, const float *rpn_bbox, 
     DC_REQUIRE(nms_threshold >= 0.f && nms_threshold <= 1.f, "nms_threshold must lie in [0, 1] (as tf.image.non_max_suppression requires)");
     const int k = pre_nms_limit < n_anchors ? pre_nms_limit : n_anchors;
     DC_REQUIRE(k <= kMaxPreNms, "pre_nms_limit=%d exceeds %d", k, kMaxPreNms);
-    DC_REQUIRE(workspace_bytes >= dc_proposal_workspace_bytes(n_images, n_anchors, pre_nms_limit),
-               "workspace too small: %zu < %zu bytes", workspace_bytes, dc_proposal_workspace_bytes(n_images, n_anchors, pre_nms_limit));
+    DC_REQUIRE(workspace_bytes >= dc_proposal_workspace_bytes(n_images, n_anchors, pre_nms_limit, proposal_count),
+               "workspace too small: %zu < %zu bytes", workspace_bytes,
+               dc_proposal_workspace_bytes(n_images, n_anchors, pre_nms_limit, proposal_count));
     const int n_blk = (k + 63) / 64;
     unsigned char *ws = static_cast<unsigned char *>(workspace);
     float4 *ws_boxes = reinterpret_cast<float4 *>(ws);
@@ -497,6 +533,15 @@ extern "C" int dc_proposal_layer(const float *rpn_probs, const float *rpn_bbox, 
     int32_t *ws_index = reinterpret_cast<int32_t *>(ws);
     ws += align256((size_t)n_images * k * sizeof(int32_t));
     unsigned long long *ws_mask = reinterpret_cast<unsigned long long *>(ws);
+    ws += align256((size_t)n_images * k * n_blk * sizeof(unsigned long long));
+    ScanState st;
+    st.removed = reinterpret_cast<unsigned long long *>(ws);
+    ws += align256((size_t)n_images * n_blk * sizeof(unsigned long long));
+    st.keep = reinterpret_cast<int32_t *>(ws);
+    ws += align256((size_t)n_images * (size_t)proposal_count * sizeof(int32_t));
+    st.count = reinterpret_cast<int32_t *>(ws);
+    ws += align256((size_t)n_images * sizeof(int32_t));
+    st.done = reinterpret_cast<int32_t *>(ws);
     cudaStream_t s = (cudaStream_t)stream;
 
     const int chunk = (n_anchors + kSelCluster - 1) / kSelCluster;
@@ -519,13 +564,20 @@ extern "C" int dc_proposal_layer(const float *rpn_probs, const float *rpn_bbox, 
             rpn_probs, reinterpret_cast<const float4 *>(rpn_bbox), reinterpret_cast<const float4 *>(anchors), n_anchors, k, std_dev,
             image_h, image_w, ws_boxes, ws_index);
     DC_CHECK_LAUNCH();
-    proposal_iou_mask_kernel<<<dim3((n_blk + kMaskColBlocks - 1) / kMaskColBlocks, n_blk, n_images), 64 * kMaskColBlocks, 0, s>>>(ws_boxes, k, n_blk, nms_threshold, ws_mask);
-    DC_CHECK_LAUNCH();
     const size_t scan_smem = (size_t)n_blk * sizeof(unsigned long long) + (size_t)proposal_count * sizeof(int);
     DC_REQUIRE(scan_smem <= 48 * 1024, "proposal_count=%d too large", proposal_count);
-    proposal_nms_scan_kernel<<<n_images, kScanThreads, scan_smem, s>>>(ws_boxes, ws_index, ws_mask, k, n_blk, proposal_count,
-                                                                      reinterpret_cast<float4 *>(proposals), n_valid, anchor_index);
-    DC_CHECK_LAUNCH();
+    // bands of kBandBlocks row blocks: IoU masks of the band, then the scan over it; later bands of an image that
+    // already has its proposal_count survivors return immediately
+    for (int b0 = 0, band = 0; b0 < n_blk; ++band) {
+        const int b1 = (band == kMaxBands - 1 || b0 + kBandBlocks >= n_blk) ? n_blk : b0 + kBandBlocks;
+        proposal_iou_mask_kernel<<<dim3((n_blk + kMaskColBlocks - 1) / kMaskColBlocks, b1 - b0, n_images), 64 * kMaskColBlocks, 0, s>>>(
+            ws_boxes, k, n_blk, nms_threshold, ws_mask, b0, b0 == 0 ? nullptr : st.done);
+        DC_CHECK_LAUNCH();
+        proposal_nms_scan_kernel<<<n_images, kScanThreads, scan_smem, s>>>(ws_boxes, ws_index, ws_mask, k, n_blk, proposal_count, b0, b1, st,
+                                                                          reinterpret_cast<float4 *>(proposals), n_valid, anchor_index);
+        DC_CHECK_LAUNCH();
+        b0 = b1;
+    }
     return DC_OK;
 }
 

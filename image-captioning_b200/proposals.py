@@ -95,7 +95,7 @@ class ProposalLayer(object):
         B = probs.shape[0]
         if dev not in self._dev_anchors:
             self._dev_anchors[dev] = torch.from_numpy(self.anchors).to(dev)
-        need = int(lib.dc_proposal_workspace_bytes(B, A, self.PRE_NMS_LIMIT))
+        need = int(lib.dc_proposal_workspace_bytes(B, A, self.PRE_NMS_LIMIT, self.proposal_count))
         ws = self._ws.get(dev)
         if ws is None or ws.numel() < need:
             ws = self._ws[dev] = torch.empty((need,), dtype=torch.uint8, device=dev)

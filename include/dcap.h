@@ -304,7 +304,7 @@ int dc_refine_generations(const float *boxes, const float *scores, int n_images,
  *   anchor_index [n_images, proposal_count] int32 (-1 padded; which anchor each proposal came from)
  *   workspace: device scratch of at least dc_proposal_workspace_bytes(...) bytes, 16-byte aligned.
  * pre_nms_limit (the reference's constant 6000) may not exceed 8192. */
-size_t dc_proposal_workspace_bytes(int n_images, int n_anchors, int pre_nms_limit);
+size_t dc_proposal_workspace_bytes(int n_images, int n_anchors, int pre_nms_limit, int proposal_count);
 int dc_proposal_layer(const float *rpn_probs, const float *rpn_bbox, const float *anchors, int n_images,
                       int n_anchors, const float *bbox_std_dev, float image_h, float image_w, int pre_nms_limit,
                       int proposal_count, float nms_threshold, float *proposals, int32_t *n_valid,
