@@ -703,7 +703,7 @@ def run_ours_train(args):
 # beam workload (BASELINE.json configs[3]): width-3 beam decoding of 100k pre-extracted 1024-d RoI
 # feature vectors, rows sharded over ranks (no collective)
 # --------------------------------------------------------------------------------------------
-BEAM_ROIS, BEAM_K, BEAM_CHUNK = 100000, 3, 16384
+BEAM_ROIS, BEAM_K, BEAM_CHUNK = 100000, 3, int(os.environ.get("DCAP_BEAM_CHUNK", "33334"))
 # hoisted terms once + (1 + (P-2)*k) word-model rows of 29.05 MFLOP (first step has one live beam)
 FLOP_PER_ROI_BEAM = 4194304 + 2097152 + (1 + (PADDING - 2) * BEAM_K) * (1228800 + 2097152 + 4194304 + 1048576 + 20480000)
 
