@@ -13,3 +13,4 @@ from .text_model import (DenseCapConfig, build_lstm_model, build_model, RoiCapti
 from .postprocess import refine_generations, caption_text    # noqa: F401
 from .proposals import ProposalLayer, ProposalConfig, generate_pyramid_anchors, normalize_boxes   # noqa: F401
 from . import parallel    # noqa: F401
+from . import data    # noqa: F401

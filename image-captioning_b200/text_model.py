@@ -224,8 +224,12 @@ class _ModelBase(object):
     def load_weights(self, path, by_name=False, skip_mismatch=False):
         """by_name=True loads only the tensors present in the file (as the reference does with
         mask_rcnn_coco.h5 to fill the head, text_generation_model.py:468)."""
-        with np.load(path) as z:
-            found = {k.replace("__", "/"): z[k] for k in z.files}
+        if str(path).endswith((".h5", ".hdf5")):
+            from . import data                               # Keras HDF5 (needs h5py; raises ImportError without it)
+            found = data.load_keras_h5_weights(path)
+        else:
+            with np.load(path) as z:
+                found = {k.replace("__", "/"): z[k] for k in z.files}
         for n, v in found.items():
             if n not in self._shapes:
                 if by_name:

@@ -12,6 +12,11 @@ and records their outputs on seeded inputs:
   * dense_img_cap_separate_models/utils.py: generate_pyramid_anchors, apply_box_deltas (numpy twin of
     apply_box_deltas_graph)                                -> pins oracle/proposals.py
 
+  * dense_img_cap_separate_models/preprocess.py: load_corpus, encode_caption (nltk stubbed with the product's
+    regular-expression tokenizer: the token FILTERING is what is pinned), and, extracted with ast from
+    text_generation_model.py / text_generation_model_v2.py, data_generator (:330-372) and load_sequences
+    (:128-137) run on a small fake dataset                  -> pins image_captioning_b200/data.py
+
 Scores are made distinct: numpy's default argsort is not stable, so tie order is not a property of the
 reference.  Run from the repo root (only where /root/reference exists):
     python tests/golden/gen_golden_reference_numpy.py
@@ -104,6 +109,66 @@ deltas = (rng.standard_normal(anc.shape) * np.array([0.1, 0.1, 0.2, 0.2]) * 3).a
 out["deltas_128"] = deltas
 out["refined_128"] = dn.apply_box_deltas(anc, deltas)
 assert out["refined_128"].dtype == np.float32
+
+# ---- data formats -----------------------------------------------------------------------------------
+sys.path.insert(0, ROOT)
+import importlib
+data_mod = importlib.import_module("image_captioning_b200.data")
+nltk = _stub("nltk"); tok = _stub("nltk.tokenize"); tok.word_tokenize = data_mod.tokenize; nltk.tokenize = tok
+np.float = float                                           # preprocess.py predates numpy 1.20
+pre = _load(os.path.join(REF, "dense_img_cap_separate_models", "preprocess.py"), "ref_preprocess")
+vocab_tokens = ["a", "man", "dog", "red", "on", "the", "grass", "frisbee", "with", "'s", "two", "playing"]
+emb = {t: rng.standard_normal(6) for t in vocab_tokens}
+np.random.seed(11)
+w2i, i2w, mat = pre.load_corpus(vocab_tokens, emb, 6)
+out["corpus_matrix"] = mat
+out["corpus_words"] = np.array([i2w[i] for i in range(len(i2w))])
+captions = ["A man's dog on the grass.", "Two dogs playing with a red frisbee", "zebra", "The man, the dog; the GRASS!"]
+out["captions_text"] = np.array(captions)
+enc = [pre.encode_caption(c, w2i) for c in captions]
+out["captions_encoded"] = np.array([",".join(str(int(v)) for v in e) for e in enc])
+
+
+def _extract(path, name):
+    tree = ast.parse(open(path).read())
+    return [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == name][0]
+
+
+P, V = 6, len(w2i)
+caps_by_image = {7: np.array([[1, 4, 5, 2, 0, 0], [1, 3, 2, 0, 0, 0]], np.float32), 9: np.array([[1, 8, 9, 10, 11, 2]], np.float32)}
+feats_by_image = {k: rng.standard_normal((v.shape[0], 2, 2, 3)).astype(np.float32) for k, v in caps_by_image.items()}
+
+
+class FakeDataset:
+    _image_ids = [7, 9]
+    rois = [(k, i, caps_by_image[k][i]) for k in (7, 9) for i in range(caps_by_image[k].shape[0])]
+
+    def load_captions_and_rois(self, image_id):
+        c = caps_by_image[image_id].astype(np.int64)
+        onehot = np.zeros(c.shape + (V,))
+        np.put_along_axis(onehot, c[..., None], 1.0, -1)
+        return None, onehot
+
+
+class Cfg2:
+    VOCABULARY_SIZE = V
+
+
+ns = {"np": np, "generate_features": lambda dataset, image_id, model: feats_by_image[image_id]}
+exec(compile(ast.Module(body=[_extract(os.path.join(REF, "dense_img_cap_separate_models", "text_generation_model.py"), "data_generator")],
+                        type_ignores=[]), "data_generator", "exec"), ns)
+gen = ns["data_generator"](FakeDataset(), None, Cfg2, 2, shuffle=False)
+batches = [next(gen) for _ in range(3)]                      # 3 RoIs, batch 2: wraps around
+out["gen_features"] = np.stack([b[0][0] for b in batches])
+out["gen_words"] = np.stack([b[0][1] for b in batches])
+out["gen_targets"] = np.stack([b[1] for b in batches])
+out["gen_caps_7"], out["gen_caps_9"] = caps_by_image[7], caps_by_image[9]
+out["gen_feats_7"], out["gen_feats_9"] = feats_by_image[7], feats_by_image[9]
+ns2 = {"np": np, "tqdm": lambda x: x}
+exec(compile(ast.Module(body=[_extract(os.path.join(REF, "dense_img_cap_separate_models", "text_generation_model_v2.py"), "load_sequences")],
+                        type_ignores=[]), "load_sequences", "exec"), ns2)
+seqs = ns2["load_sequences"](FakeDataset())
+out["v2_sequences"] = np.array(["%d|%d|%s|%d" % (a, b, ",".join(str(int(t)) for t in c), int(d)) for a, b, c, d in seqs])
 
 path = os.path.join(ROOT, "tests", "golden", "reference_numpy.npz")
 np.savez_compressed(path, **out)

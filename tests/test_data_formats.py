@@ -1,0 +1,142 @@
+"""Host-side data formats (image_captioning_b200/data.py) against the reference's own code where it runs here
+(tests/golden/reference_numpy.npz: load_corpus, encode_caption's token filtering, data_generator, load_sequences)
+and against the layouts the reference reads (region_descriptions.json, the vocabulary pickles, Keras HDF5 groups).
+CPU only."""
+import json
+import os
+import pickle
+
+import numpy as np
+
+from image_captioning_b200 import data
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_numpy.npz"))
+TOKENS = ["a", "man", "dog", "red", "on", "the", "grass", "frisbee", "with", "'s", "two", "playing"]
+
+
+def _vocab():
+    words = [str(w) for w in G["corpus_words"]]
+    return {w: i for i, w in enumerate(words)}, dict(enumerate(words))
+
+
+def test_load_corpus_equals_the_reference():
+    emb = {w: G["corpus_matrix"][i + 3] for i, w in enumerate(TOKENS)}
+    np.random.seed(11)
+    w2i, i2w, mat = data.load_corpus(TOKENS, emb, 6)
+    assert np.array_equal(mat, G["corpus_matrix"])
+    assert [i2w[i] for i in range(len(i2w))] == [str(w) for w in G["corpus_words"]]
+    assert w2i["<unk>"] == 0 and w2i["<start>"] == 1 and w2i["<end>"] == 2 and w2i["a"] == 3
+    assert not mat[0].any() and (np.abs(mat[1:3]) <= 0.5).all()
+
+
+def test_encode_caption_drops_unknown_words_like_the_reference():
+    w2i, i2w = _vocab()
+    for text, want in zip(G["captions_text"], G["captions_encoded"]):
+        got = data.encode_caption(str(text), w2i)
+        assert ",".join(str(int(v)) for v in got) == str(want)
+    assert data.tokenize("A man's dog, isn't it?") == ["a", "man", "'s", "dog", ",", "is", "n't", "it", "?"]
+    assert data.decode_caption([1, 3, 4, 2, 0], i2w) == "<start> a man <end> <unk>"
+    assert data.decode_caption([3, 4, 2, 0], i2w, stop="<end>") == "a man"
+
+
+def test_frame_caption_start_end_cut_and_post_padding():
+    assert data.frame_caption([5, 6], 6).tolist() == [1, 5, 6, 2, 0, 0]
+    assert data.frame_caption([5, 6, 7, 8, 9, 10], 6).tolist() == [1, 5, 6, 7, 8, 2]      # cut to P - 2 words
+    assert data.frame_caption([5, 6, 7, 8], 6).tolist() == [1, 5, 6, 7, 8, 2]
+    assert data.frame_caption([5], 6).dtype == np.float32
+
+
+def test_region_descriptions_dataset_and_generator(tmp_path):
+    w2i, _ = _vocab()
+    doc = [{"id": 7, "regions": [{"x": 10, "y": 20, "width": 30, "height": 40, "phrase": "a man on the grass"},
+                                 {"x": 1, "y": 2, "width": 3, "height": 4, "phrase": "zebra"},
+                                 {"x": 5, "y": 6, "width": 7, "height": 8, "phrase": "Red dog."}]},
+           {"id": 9, "regions": [{"x": 0, "y": 0, "width": 9, "height": 9, "phrase": "two playing with a frisbee"}]},
+           {"id": 11, "regions": []}]
+    path = tmp_path / "region_descriptions.json"
+    path.write_text(json.dumps(doc))
+    ds = data.RegionCaptionDataset(w2i, 6)
+    ds.load_visual_genome(str(path), image_ids=[7, 9])
+    assert ds.image_ids == [7, 9]
+    rois, caps = ds.load_captions_and_rois(7)
+    assert rois.tolist() == [[20, 10, 60, 40], [6, 5, 14, 12]]            # the out-of-vocabulary region is skipped
+    assert caps.tolist() == [[1, 3, 4, 7, 8, 2], [1, 6, 5, 2, 0, 0]] and caps.dtype == np.float32
+    rois_o, caps_o = ds.load_original_captions_and_rois(7)
+    assert rois_o.shape == (3, 4) and caps_o[1] == ["zebra"]
+    ds.add_rois(data.create_roi_info(ds))
+    assert [(a, b) for a, b, _ in ds.rois] == [(7, 0), (7, 1), (9, 0)]
+    calls = []
+
+    def feats(image_id):
+        calls.append(image_id)
+        return np.full((2, 7, 7, 4), image_id, np.float32)
+
+    class Cfg:
+        VOCABULARY_SIZE = len(w2i)
+    gen = data.data_generator(ds, feats, Cfg, 2)
+    (f, words), tgt = next(gen)
+    assert f.shape == (2, 7, 7, 4) and words.tolist() == caps.tolist() and calls == [7]     # one extraction per image
+    assert tgt.tolist() == [[3, 4, 7, 8, 2, 0], [6, 5, 2, 0, 0, 0]] and tgt.dtype == np.int32
+
+
+def test_data_generator_equals_the_reference():
+    caps = {7: G["gen_caps_7"], 9: G["gen_caps_9"]}
+    feats = {7: G["gen_feats_7"], 9: G["gen_feats_9"]}
+
+    class DS:
+        image_ids = [7, 9]
+        rois = [(k, i, caps[k][i]) for k in (7, 9) for i in range(caps[k].shape[0])]
+
+        def load_captions_and_rois(self, image_id):
+            return None, caps[image_id]
+
+    class Cfg:
+        VOCABULARY_SIZE = G["gen_targets"].shape[-1]
+    gen = data.data_generator(DS(), lambda i: feats[i], Cfg, 2, one_hot=True)
+    ids = data.data_generator(DS(), lambda i: feats[i], Cfg, 2)
+    for b in range(3):
+        (f, w), t = next(gen)
+        assert np.array_equal(f, G["gen_features"][b]) and np.array_equal(w, G["gen_words"][b])
+        assert np.array_equal(t, G["gen_targets"][b]) and t.dtype == G["gen_targets"].dtype
+        assert np.array_equal(next(ids)[1], t.argmax(-1))
+    seqs = data.load_sequences(DS())
+    got = ["%d|%d|%s|%d" % (a, b, ",".join(str(int(v)) for v in c), d) for a, b, c, d in seqs]
+    assert got == [str(v) for v in G["v2_sequences"]]
+
+
+def test_vocabulary_pickles_round_trip(tmp_path):
+    w2i, i2w = _vocab()
+    paths = [str(tmp_path / n) for n in ("id_to_word.pickle", "word_to_id.pickle", "embedding_matrix.pickle")]
+    for p, obj in zip(paths, (i2w, w2i, G["corpus_matrix"])):
+        with open(p, "wb") as f:
+            pickle.dump(obj, f, protocol=pickle.HIGHEST_PROTOCOL)
+    a, b, m = data.load_vocabulary(*paths)
+    assert a == w2i and b == i2w and np.array_equal(m, G["corpus_matrix"])
+
+
+class _Node(dict):
+    def __init__(self, items=(), **attrs):
+        super().__init__(items)
+        self.attrs = attrs
+
+
+def test_keras_h5_group_walker_on_a_stand_in():
+    k1 = np.arange(12, dtype=np.float64).reshape(3, 4)
+    layer = _Node({"mrcnn_class_conv1/kernel:0": k1, "mrcnn_class_conv1/bias:0": np.ones(4)},
+                  weight_names=[b"mrcnn_class_conv1/kernel:0", b"mrcnn_class_conv1/bias:0"])
+    lstm = _Node({"imgcap_lstm1/kernel:0": np.zeros((2, 8))}, weight_names=[b"imgcap_lstm1/kernel:0"])
+    root = _Node({"mrcnn_class_conv1": layer, "imgcap_lstm1": lstm, "input_1": _Node(weight_names=[])},
+                 layer_names=[b"input_1", b"mrcnn_class_conv1", b"imgcap_lstm1"])
+    for top in (root, _Node({"model_weights": root})):
+        w = data.weights_from_h5_group(top)
+        assert sorted(w) == ["imgcap_lstm1/kernel", "mrcnn_class_conv1/bias", "mrcnn_class_conv1/kernel"]
+        assert w["mrcnn_class_conv1/kernel"].dtype == np.float32 and np.array_equal(w["mrcnn_class_conv1/kernel"], k1)
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        try:
+            data.load_keras_h5_weights("missing.h5")
+        except ImportError as e:
+            assert "h5py" in str(e)
+        else:
+            raise AssertionError("expected ImportError without h5py")
