@@ -17,8 +17,12 @@ numpy fp32 restatement (optionally fp64 "shadow" by passing ``dtype=np.float64``
 (all paths relative to /root/reference).  Keras-2.1 / TF-1.x internals (LSTMCell with
 implementation=1 and hard_sigmoid, K.rnn mask handling, BatchNormalization inference,
 categorical_crossentropy, Adam) are restated from their published behaviour because their
-source is not under /root/reference.  PARITY UNPINNED: the reference holds no tests, golden
-vectors, weights or vocabularies for this path and cannot be imported here (no TF/Keras).
+source is not under /root/reference.  PARITY UNPINNED for the network arithmetic: the reference
+holds no tests, golden vectors, weights or vocabularies for this path and cannot be imported here
+(no TF/Keras).  PINNED: the two decoding loops that are plain Python around model.predict -- the
+beam search gen_captions and the v2 greedy loop -- are run from /root/reference with a stand-in
+predict() by tests/golden/gen_golden_reference_numpy.py, and beam_v1 / greedy_v2 reproduce their
+outputs exactly (tests/test_reference_golden.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
 """

@@ -170,6 +170,75 @@ exec(compile(ast.Module(body=[_extract(os.path.join(REF, "dense_img_cap_separate
 seqs = ns2["load_sequences"](FakeDataset())
 out["v2_sequences"] = np.array(["%d|%d|%s|%d" % (a, b, ",".join(str(int(t)) for t in c), int(d)) for a, b, c, d in seqs])
 
+# ---- beam search control flow -----------------------------------------------------------------------
+# gen_captions ("image captioning/test.py":23-64) is plain Python around model.predict: run it with a stand-in model
+# whose predict() is the oracle's v1 word model (float64 copy of the fp32 probabilities, so that the score sums are
+# float64 under numpy 1.x and 2.x alike) -> pins the candidate / pooling / sorting / scoring logic of oracle.beam_v1
+import contextlib
+import io
+from oracle import decoder as dec
+from image_captioning_b200 import synth
+BV, BP, BK, BR = 40, 6, 3, 5
+wb = synth.synth_weights_v1(np.random.default_rng(77), V=BV, E=6, F=16, U=8, pool=2, C=4, trained_like=False)
+fb = dec.head(np.random.default_rng(78).standard_normal((BR, 2, 2, 4)).astype(np.float32), wb)
+
+
+class FakeModel:
+    def predict(self, inputs):
+        f, cap = np.asarray(inputs[0], np.float32), np.asarray(inputs[1])[0]
+        st = dec.V1State(1, 8)
+        for t in cap[cap != 0]:                                # pre-padding zeros are masked steps: state untouched
+            p = dec.v1_step(f, np.array([t]), st, wb)
+        return p.astype(np.float64)
+
+
+class FakeTokenizer:
+    def texts_to_sequences(self, texts):
+        return [[1]]
+
+
+ns3 = {"np": np, "pad_sequences": lambda sequences, maxlen, padding: dec.pad_sequences_pre(sequences, maxlen),
+       "make_caption_human_readable": lambda caption, index_to_word: ""}
+exec(compile(ast.Module(body=[_extract(os.path.join(REF, "image captioning", "test.py"), "gen_captions")], type_ignores=[]),
+             "gen_captions", "exec"), ns3)
+btok, bsc = np.zeros((BR, BK, BP), np.int32), np.zeros((BR, BK))
+for r in range(BR):
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = ns3["gen_captions"]({"max_caption_length": BP}, FakeModel(), fb[r], FakeTokenizer(), BK, None)
+    for j, (cap, sc) in enumerate(res):
+        btok[r, j], bsc[r, j] = cap, sc
+out["beam_ref_tokens"], out["beam_ref_scores"] = btok, bsc
+out["beam_params"] = np.array([BV, BP, BK, BR])
+
+# ---- v2 greedy loop control flow ------------------------------------------------------------------------
+# the per-RoI loop of evaluate_models/test_score_dense_captions.py:214-225 (start word zeros(V) -> id 0, P-1 predicts over
+# the pre-padded argmax history, probabilities collected), extracted as an AST statement and run with a stand-in
+# model.predict (the oracle's v2 inject model) -> pins the loop logic of oracle.greedy_v2
+score_src = open(os.path.join(REF, "evaluate_models", "test_score_dense_captions.py")).read()
+line_no = 1 + [i for i, l in enumerate(score_src.split("\n")) if l.strip() == "for j in range(img_boxes.shape[0]):"][0]
+loop = [n for n in ast.walk(ast.parse(score_src)) if isinstance(n, ast.For) and n.lineno == line_no][0]
+GV, GP, GR = 30, 6, 4
+wg = synth.synth_weights_v2(np.random.default_rng(79), V=GV, E=6, F=16, units=8, pool=2, C=4, trained_like=False)
+featg = np.random.default_rng(80).standard_normal((GR, 2, 2, 4)).astype(np.float32)
+
+
+class V2Model:
+    def predict(self, inputs):
+        return dec.v2_inject_predict(np.asarray(inputs[0], np.float32), np.asarray(inputs[1]), wg)
+
+
+class Self:
+    class config:
+        VOCABULARY_SIZE, PADDING_SIZE = GV, GP
+    model = V2Model()
+
+
+ns4 = {"np": np, "self": Self, "img_boxes": np.zeros((GR, 4)), "img_features": featg, "caps": [],
+       "pad_sequences": lambda seqs, maxlen: dec.pad_sequences_pre(seqs, maxlen)}
+exec(compile(ast.Module(body=[loop], type_ignores=[]), "v2_greedy_loop", "exec"), ns4)
+out["v2_loop_probs"] = np.array(ns4["caps"])                   # [R, P-1, V]
+out["v2_loop_params"] = np.array([GV, GP, GR])
+
 path = os.path.join(ROOT, "tests", "golden", "reference_numpy.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")

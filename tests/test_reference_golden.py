@@ -62,3 +62,32 @@ def test_box_deltas_equal_the_reference():
     got = pr.apply_box_deltas(anc, G["deltas_128"])
     scale = np.maximum(np.abs(want).max(1, keepdims=True), 1.0)
     assert (np.abs(got - want) / scale).max() <= 4 * np.finfo(np.float32).eps
+
+
+def test_beam_search_equals_the_reference_control_flow():
+    """gen_captions ("image captioning/test.py":23-64) run with a stand-in model.predict (the oracle's word model):
+    candidates, pooling order, stable sort, float64 probability sums and the kept beams equal oracle.beam_v1's."""
+    from image_captioning_b200 import synth
+    from oracle import decoder as dec
+    V, P, K, R = [int(v) for v in G["beam_params"]]
+    w = synth.synth_weights_v1(np.random.default_rng(77), V=V, E=6, F=16, U=8, pool=2, C=4, trained_like=False)
+    f = dec.head(np.random.default_rng(78).standard_normal((R, 2, 2, 4)).astype(np.float32), w)
+    tok, sc = dec.beam_v1(f, w, P, K)
+    assert np.array_equal(tok, G["beam_ref_tokens"])
+    assert np.array_equal(sc, G["beam_ref_scores"])
+    assert len(np.unique(G["beam_ref_tokens"])) > 4                    # not a degenerate fixture
+
+
+def test_v2_greedy_loop_equals_the_reference_control_flow():
+    """The per-RoI loop of evaluate_models/test_score_dense_captions.py:214-225 run with a stand-in model.predict (the
+    oracle's v2 inject model): start id 0, P-1 predicts over the pre-padded argmax history == oracle.greedy_v2."""
+    from image_captioning_b200 import synth
+    from oracle import decoder as dec
+    V, P, R = [int(v) for v in G["v2_loop_params"]]
+    w = synth.synth_weights_v2(np.random.default_rng(79), V=V, E=6, F=16, units=8, pool=2, C=4, trained_like=False)
+    feat = np.random.default_rng(80).standard_normal((R, 2, 2, 4)).astype(np.float32)
+    tok, probs = dec.greedy_v2(feat, w, P)
+    want = G["v2_loop_probs"]
+    assert probs.shape == want.shape == (R, P - 1, V)
+    assert np.array_equal(tok, want.argmax(-1))
+    np.testing.assert_allclose(probs, want, rtol=2e-6, atol=1e-9)     # batch-of-R vs batch-of-1 matmuls
