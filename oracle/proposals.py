@@ -17,11 +17,15 @@ Third-party pieces (TensorFlow 1.x, not vendored and not installed here; the ref
     IoU uses min/max-normalised corners and is 0 when either area is <= 0; stops at max_output_size.
     Equal scores: restated as a STABLE order (the order top_k delivered).
   * tf.exp: restated as the correctly rounded fp32 exponential (computed in fp64, rounded once);
-    Eigen's vectorised expf is within 1 ulp of that.
+    TF's Eigen expf may differ from that in the last ulp (unknowable without TF).
 
-PINNED PARTS: the anchor generator and the numpy twin of apply_box_deltas (utils.py:107-128) are
-checked against the reference's own numpy code, run here through tests/golden/gen_golden_reference_numpy.py
-(tests/golden/reference_numpy.npz).  top_k / NMS / the layer as a whole: PARITY UNPINNED (TensorFlow absent).
+PINNED PARTS (tests/golden/gen_golden_reference_numpy.py -> tests/golden/reference_numpy.npz): the anchor
+generator and the numpy twin of apply_box_deltas (utils.py:107-128) against the reference's own numpy code;
+and the LAYER'S GLUE -- ProposalLayer.call with apply_box_deltas_graph, clip_boxes_graph and utils.batch_slice
+is EXECUTED from /root/reference over a numpy stand-in for its TF ops (tests/golden/tf_numpy_shim.py, with
+top_k_indices / exp_f32 / tf_non_max_suppression / std_min / std_max below as the primitives) and
+proposal_layer() reproduces its output bit for bit.  UNPINNED (TensorFlow absent): the arithmetic inside
+tf.nn.top_k (tie order), tf.exp and tf.image.non_max_suppression themselves.
 """
 import numpy as np
 

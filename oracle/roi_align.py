@@ -5,12 +5,17 @@ imported only by ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-
 legs -- never by the product path in ``image-captioning_b200/`` (which has no CPU
 fallback and fails loudly when the CUDA library is missing).
 
-PARITY UNPINNED: the reference has no tests / golden vectors for this path and its
-arithmetic lives in TensorFlow 1.x (``tf.image.crop_and_resize``, ``tf.log``, ``tf.round``),
-which is neither vendored under /root/reference nor installable here.  The restatement
-follows the reference call sites line by line and TF's published CropAndResize CPU
+PARITY UNPINNED for the op arithmetic: the reference has no tests / golden vectors for this
+path and its arithmetic lives in TensorFlow 1.x (``tf.image.crop_and_resize``, ``tf.log``,
+``tf.round``), which is neither vendored under /root/reference nor installable here.  The
+restatement follows the reference call sites line by line and TF's published CropAndResize CPU
 semantics; it is cross-checked in tests against two independent transcriptions
 (TVM's ``crop_and_resize_python`` and ``torch.nn.functional.grid_sample``).
+PINNED: the layer's glue.  tests/golden/gen_golden_reference_numpy.py EXECUTES the reference's
+``PyramidROIAlign.call`` from /root/reference over a numpy stand-in for its TF ops
+(tests/golden/tf_numpy_shim.py, with ``crop_and_resize`` below as the primitive), and
+``pyramid_roi_align_literal`` / ``pyramid_roi_align`` reproduce its output bit for bit on the
+golden inputs (level formula, per-level dispatch, concat, top_k re-sort; degenerate boxes too).
 
 Reference lines followed (paths relative to /root/reference):
   * ``log2_graph``                      evaluate_models/modified_dense_model.py:313-315

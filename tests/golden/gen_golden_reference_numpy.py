@@ -12,6 +12,11 @@ and records their outputs on seeded inputs:
   * dense_img_cap_separate_models/utils.py: generate_pyramid_anchors, apply_box_deltas (numpy twin of
     apply_box_deltas_graph)                                -> pins oracle/proposals.py
 
+  * evaluate_models/modified_dense_model.py: class PyramidROIAlign (+ log2_graph), and
+    dense_img_cap_separate_models/modified_dense_model.py: class ProposalLayer (+ apply_box_deltas_graph,
+    clip_boxes_graph, utils.batch_slice), extracted with ast and EXECUTED over the numpy stand-in for TensorFlow of
+    tf_numpy_shim.py (primitives = the oracle's restatements; the glue around them is what is pinned)
+                                                           -> pins oracle.pyramid_roi_align_literal / proposal_layer
   * dense_img_cap_separate_models/preprocess.py: load_corpus, encode_caption (nltk stubbed with the product's
     regular-expression tokenizer: the token FILTERING is what is pinned), and, extracted with ast from
     text_generation_model.py / text_generation_model_v2.py, data_generator (:330-372) and load_sequences
@@ -41,9 +46,15 @@ def _stub(name):
     return m
 
 
-for name in ("tensorflow", "scipy.misc", "skimage", "skimage.color", "skimage.io"):
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import tf_numpy_shim as shim  # noqa: E402
+
+for name in ("scipy.misc", "skimage", "skimage.color", "skimage.io"):
     if name not in sys.modules or name == "scipy.misc":
         _stub(name)
+tf = shim.make_tf()                                         # numpy stand-in for the TF graph ops (tf_numpy_shim.py)
+sys.modules["tensorflow"] = tf
 
 
 def _load(path, name):
@@ -111,7 +122,6 @@ out["refined_128"] = dn.apply_box_deltas(anc, deltas)
 assert out["refined_128"].dtype == np.float32
 
 # ---- data formats -----------------------------------------------------------------------------------
-sys.path.insert(0, ROOT)
 import importlib
 data_mod = importlib.import_module("image_captioning_b200.data")
 nltk = _stub("nltk"); tok = _stub("nltk.tokenize"); tok.word_tokenize = data_mod.tokenize; nltk.tokenize = tok
@@ -238,6 +248,50 @@ ns4 = {"np": np, "self": Self, "img_boxes": np.zeros((GR, 4)), "img_features": f
 exec(compile(ast.Module(body=[loop], type_ignores=[]), "v2_greedy_loop", "exec"), ns4)
 out["v2_loop_probs"] = np.array(ns4["caps"])                   # [R, P-1, V]
 out["v2_loop_params"] = np.array([GV, GP, GR])
+
+# ---- the two TF layers on the path, executed over the numpy stand-in ----------------------------------------
+def _extract_defs(path, names):
+    tree = ast.parse(open(path).read())
+    return [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+
+
+KE = types.SimpleNamespace(Layer=shim.Layer)
+ns5 = {"tf": tf, "np": np, "KE": KE}
+exec(compile(ast.Module(body=_extract_defs(os.path.join(REF, "evaluate_models", "modified_dense_model.py"),
+                                           ("log2_graph", "PyramidROIAlign")), type_ignores=[]), "PyramidROIAlign", "exec"), ns5)
+gr = np.load(os.path.join(ROOT, "tests", "golden", "roi_align_small.npz"))
+layer = ns5["PyramidROIAlign"]([7, 7], tuple(int(v) for v in gr["image_shape"]))
+pooled_ref = np.asarray(layer.call([shim.tensor(gr["boxes"])] + [shim.tensor(gr[k]) for k in ("p2", "p3", "p4", "p5")]))
+assert pooled_ref.shape == gr["pooled"].shape and pooled_ref.dtype == np.float32
+out["roi_align_layer_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(pooled_ref).tobytes()).digest(), np.uint8)
+out["roi_align_layer_equals_oracle_golden"] = np.array(np.array_equal(pooled_ref.view(np.uint32), gr["pooled"].view(np.uint32)))
+assert layer.compute_output_shape([(2, 48, 4), (2, 32, 32, 8)]) == (2, 48, 7, 7, 8)
+
+ns6 = {"tf": tf, "np": np, "KE": KE, "utils": dn}
+exec(compile(ast.Module(body=_extract_defs(os.path.join(REF, "dense_img_cap_separate_models", "modified_dense_model.py"),
+                                           ("apply_box_deltas_graph", "clip_boxes_graph", "ProposalLayer")), type_ignores=[]),
+             "ProposalLayer", "exec"), ns6)
+
+
+class PCfg:
+    RPN_BBOX_STD_DEV = np.array([0.1, 0.1, 0.2, 0.2])
+    IMAGES_PER_GPU = 2
+    IMAGE_SHAPE = np.array([128, 128, 3])
+
+
+anchors_p = out["anchors_128"][1800:3400]              # P2 tail + all of P3: 1600 anchors keep the fixture small
+A = anchors_p.shape[0]
+fgp = (1.0 / (1.0 + np.exp(-(rng.standard_normal((2, A)) * 2.5 - 3.0)))).astype(np.float32)
+fgp = np.round(fgp, 3)                                       # score ties
+probs_p = np.stack([1 - fgp, fgp], -1).astype(np.float32)
+bbox_p = (rng.standard_normal((2, A, 4)) * 1.5).astype(np.float32)
+bbox_p[0, ::9] = [0.0, 0.0, -80.0, -80.0]                    # degenerate boxes
+bbox_p[1, ::7, :2] = 40.0                                    # pushed out of the image, clipped to a corner
+player = ns6["ProposalLayer"](proposal_count=1500, nms_threshold=0.7, anchors=anchors_p, config=PCfg)   # > survivors: padding
+prop_ref = np.asarray(player.call([shim.tensor(probs_p), shim.tensor(bbox_p)]))
+assert prop_ref.shape == (2, 1500, 4) and prop_ref.dtype == np.float32 and player.compute_output_shape(None) == (None, 1500, 4)
+out["proposal_probs"], out["proposal_bbox"], out["proposal_ref"] = probs_p, bbox_p, prop_ref
+out["proposal_anchor_slice"] = np.array([1800, 3400])
 
 path = os.path.join(ROOT, "tests", "golden", "reference_numpy.npz")
 np.savez_compressed(path, **out)

@@ -91,3 +91,31 @@ def test_v2_greedy_loop_equals_the_reference_control_flow():
     assert probs.shape == want.shape == (R, P - 1, V)
     assert np.array_equal(tok, want.argmax(-1))
     np.testing.assert_allclose(probs, want, rtol=2e-6, atol=1e-9)     # batch-of-R vs batch-of-1 matmuls
+
+
+def test_pyramid_roi_align_glue_equals_the_reference_layer():
+    """PyramidROIAlign.call (evaluate_models/modified_dense_model.py:342-416) EXECUTED from the reference source over a
+    numpy stand-in for its TF ops (tests/golden/tf_numpy_shim.py; crop_and_resize = the oracle's restatement): level
+    formula, per-level dispatch, concat and the top_k re-sort reproduce the oracle's literal and direct forms bit for bit."""
+    from oracle import roi_align as ra
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "roi_align_small.npz"))
+    assert bool(G["roi_align_layer_equals_oracle_golden"])
+    fms = [g[k] for k in ("p2", "p3", "p4", "p5")]
+    shape = tuple(int(v) for v in g["image_shape"])
+    for fn in (ra.pyramid_roi_align_literal, ra.pyramid_roi_align):
+        out, _ = fn(g["boxes"], fms, (7, 7), shape)
+        assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).digest() == G["roi_align_layer_sha256"].tobytes()
+
+
+def test_proposal_layer_glue_equals_the_reference_layer():
+    """ProposalLayer.call (dense_img_cap_separate_models/modified_dense_model.py:247-303, with apply_box_deltas_graph,
+    clip_boxes_graph and utils.batch_slice) EXECUTED from the reference source over the numpy stand-in (top_k order,
+    exp and non_max_suppression = the oracle's restatements): std-dev scaling, gather order, delta arithmetic, clip,
+    normalisation, NMS call and zero padding reproduce oracle.proposal_layer bit for bit."""
+    lo, hi = G["proposal_anchor_slice"]
+    anchors = G["anchors_128"][lo:hi]
+    want = G["proposal_ref"]
+    got = pr.proposal_layer(G["proposal_probs"], G["proposal_bbox"], anchors, want.shape[1], 0.7, (128, 128, 3))
+    assert got.dtype == want.dtype and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    n_valid = (np.abs(want).sum(-1) > 0).sum(1)
+    assert (n_valid > 100).all() and (n_valid < want.shape[1]).all()           # real proposals and real zero padding
