@@ -19,10 +19,16 @@ implementation=1 and hard_sigmoid, K.rnn mask handling, BatchNormalization infer
 categorical_crossentropy, Adam) are restated from their published behaviour because their
 source is not under /root/reference.  PARITY UNPINNED for the network arithmetic: the reference
 holds no tests, golden vectors, weights or vocabularies for this path and cannot be imported here
-(no TF/Keras).  PINNED: the two decoding loops that are plain Python around model.predict -- the
-beam search gen_captions and the v2 greedy loop -- are run from /root/reference with a stand-in
-predict() by tests/golden/gen_golden_reference_numpy.py, and beam_v1 / greedy_v2 reproduce their
-outputs exactly (tests/test_reference_golden.py).
+(no TF/Keras).  PINNED (tests/golden/gen_golden_reference_numpy.py -> tests/test_reference_golden.py):
+  * the two decoding loops that are plain Python around model.predict -- beam search gen_captions and
+    the v2 greedy loop -- run from /root/reference with a stand-in predict(): beam_v1 / greedy_v2
+    reproduce their outputs exactly;
+  * the model WIRING: word_generation_model, ROICaptionInferenceLayer.call,
+    build_roi_caption_model_training, roi_caption_loss, build_lstm_model (both modes) and the v2
+    build_model are executed from the reference source over eager stand-ins for the Keras layers
+    (tests/golden/tf_numpy_shim.py; layer numerics = the primitives below): greedy_v1_literal,
+    train_forward_v1_literal, roi_caption_loss, head and v2_inject_predict reproduce them.
+What remains unpinned are the Keras/TF primitives themselves (LSTM cell, Dense, BatchNorm, crossentropy, Adam).
 
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
 """

@@ -293,6 +293,105 @@ assert prop_ref.shape == (2, 1500, 4) and prop_ref.dtype == np.float32 and playe
 out["proposal_probs"], out["proposal_bbox"], out["proposal_ref"] = probs_p, bbox_p, prop_ref
 out["proposal_anchor_slice"] = np.array([1800, 3400])
 
+# ---- v1 caption models: the reference's WIRING executed over eager stand-ins for the Keras layers ---------------
+# word_generation_model, ROICaptionInferenceLayer (greedy decoding), build_roi_caption_model_training (teacher forcing)
+# and roi_caption_loss are run from the reference source; layer numerics = the oracle's restatements.
+KL, KM, K = shim.make_keras(tf)
+tg_path = os.path.join(REF, "dense_img_cap_separate_models", "text_generation_model.py")
+ns7 = {"tf": tf, "np": np, "KL": KL, "KM": KM, "K": K}
+exec(compile(ast.Module(body=_extract_defs(tg_path, ("word_generation_model", "build_roi_caption_model_training",
+                                                     "ROICaptionInferenceLayer", "roi_caption_loss")), type_ignores=[]),
+             "text_generation_model", "exec"), ns7)
+CV, CP, CB, CU, CF = 30, 5, 3, 8, 16
+wc = synth.synth_weights_v1(np.random.default_rng(81), V=CV, E=6, F=CF, U=CU, pool=2, C=4, trained_like=False)
+shim.WEIGHTS.update(wc)
+fc = dec.head(np.random.default_rng(82).standard_normal((CB, 2, 2, 4)).astype(np.float32), wc)
+gtc = synth.synth_captions(np.random.default_rng(83), CB, CP, CV)
+gtc[1, 2] = 0                                                  # a masked step in the middle of a caption
+
+
+class CCfg:
+    BATCH_SIZE, PADDING_SIZE, VOCABULARY_SIZE, EMBEDDING_SIZE = CB, CP, CV, 6
+    EMBEDDING_WEIGHTS = wc["imgcap_embedding_layer/embeddings"]
+
+
+ref_wgm = ns7["word_generation_model"]
+
+
+def recallable_word_model(features_input, lstm_units, config):
+    """The reference builds the word model once and calls it many times; the eager stand-in re-runs the reference's
+    builder on every call with the call's input fed to its KL.Input."""
+    def call(x):
+        shim.FEEDS["word_model_input"] = np.asarray(x)
+        return ref_wgm(features_input, lstm_units, config).outputs
+    return call
+
+
+ns7["word_generation_model"] = recallable_word_model
+word_model = recallable_word_model([CF + CP], CU, CCfg)
+greedy_probs = np.asarray(ns7["ROICaptionInferenceLayer"](word_model, CCfg).call(shim.tensor(fc)))
+shim.FEEDS["input_imgcap_caption_features"] = np.concatenate([fc[:, None, :], gtc[:, None, :]], -1)     # [B, 1, F + P]
+train_probs = np.asarray(ns7["build_roi_caption_model_training"]([1, CF + CP], CU, CCfg).outputs)
+ids_c = dec.targets_from_captions(gtc)
+onehot_c = np.zeros((CB, CP, CV), np.float32)
+np.put_along_axis(onehot_c, ids_c[..., None].astype(np.int64), 1.0, -1)
+onehot_c[2, 3:] = 0.0                                          # positions without a target are excluded from the mean
+out["v1_greedy_probs"], out["v1_train_probs"], out["v1_gt"] = greedy_probs, train_probs, gtc
+out["v1_loss"] = np.asarray(ns7["roi_caption_loss"](shim.tensor(onehot_c), shim.tensor(train_probs)), np.float32)
+out["v1_loss_all_masked"] = np.asarray(ns7["roi_caption_loss"](shim.tensor(onehot_c * 0), shim.tensor(train_probs)), np.float32)
+out["v1_params"] = np.array([CV, CP, CB, CU, CF])
+
+# the whole models: build_lstm_model (RoI head -> TimeDistributed caption layer / training graph) and the v2 build_model
+ns7["BatchNorm"] = ns8_bn = None
+bn_ns = {"KL": KL}
+exec(compile(ast.Module(body=_extract_defs(os.path.join(REF, "dense_img_cap_separate_models", "modified_dense_model.py"), ("BatchNorm",)),
+                        type_ignores=[]), "BatchNorm", "exec"), bn_ns)
+ns7["BatchNorm"] = bn_ns["BatchNorm"]
+exec(compile(ast.Module(body=_extract_defs(tg_path, ("build_lstm_model",)), type_ignores=[]), "build_lstm_model", "exec"), ns7)
+ref_train_builder = ns7["build_roi_caption_model_training"]
+
+
+def recallable_training_model(features_input, lstm_units, config):
+    m = KM.Model(None, None)
+
+    def recall(x):
+        shim.FEEDS["input_imgcap_caption_features"] = np.asarray(x)
+        return ref_train_builder(features_input, lstm_units, config).outputs
+    m.recall = recall
+    return m
+
+
+ns7["build_roi_caption_model_training"] = recallable_training_model
+CCfg.POOL_SIZE = 2
+wc2 = synth.synth_weights_v1(np.random.default_rng(84), V=CV, E=6, F=1024, U=CU, pool=2, C=4, trained_like=False)   # the head's 1024
+shim.WEIGHTS.clear()                                                                                                 # filters are hardcoded
+shim.WEIGHTS.update(wc2)
+CCfg.EMBEDDING_WEIGHTS = wc2["imgcap_embedding_layer/embeddings"]
+featc = np.random.default_rng(82).standard_normal((CB, 2, 2, 4)).astype(np.float32)
+shim.FEEDS["input_imgcap_lstm_features"] = featc
+shim.FEEDS["input_imgcap_lstm_gt_captions"] = gtc
+out["v1_model_inference"] = np.asarray(ns7["build_lstm_model"]([2, 2, 4], CCfg, CU, "inference").outputs)
+out["v1_model_training"] = np.asarray(ns7["build_lstm_model"]([2, 2, 4], CCfg, CU, "training").outputs)
+
+v2_path = os.path.join(REF, "dense_img_cap_separate_models", "text_generation_model_v2.py")
+ns8 = {"tf": tf, "np": np, "KL": KL, "KM": KM, "BatchNorm": bn_ns["BatchNorm"]}
+exec(compile(ast.Module(body=_extract_defs(v2_path, ("build_model",)), type_ignores=[]), "build_model_v2", "exec"), ns8)
+wg2 = synth.synth_weights_v2(np.random.default_rng(85), V=GV, E=6, F=1024, units=8, pool=2, C=4, trained_like=False)
+shim.WEIGHTS.clear()
+shim.WEIGHTS.update(wg2)
+KL._counters.clear()
+
+
+class V2Cfg:
+    POOL_SIZE, VOCABULARY_SIZE, EMBEDDING_SIZE = 2, GV, 6
+    EMBEDDING_WEIGHTS = wg2["imgcap_embedding_layer/embeddings"]
+
+
+words_v2 = dec.pad_sequences_pre([[0], [3, 7], [5, 0, 9, 2], [1, 2, 3, 4, 5, 6, 7]], GP)
+shim.FEEDS["imgcap_features"], shim.FEEDS["__unnamed__"] = featg, [words_v2.astype(np.float32)]
+out["v2_model_probs"] = np.asarray(ns8["build_model"]([2, 2, 4], [GP], V2Cfg, 8, inject=True).outputs)
+out["v2_model_words"] = words_v2
+
 path = os.path.join(ROOT, "tests", "golden", "reference_numpy.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes;", len(out), "arrays")

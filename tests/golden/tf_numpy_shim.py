@@ -15,9 +15,18 @@ from oracle import proposals as opr
 from oracle import roi_align as ora
 
 
+class _Shape(tuple):
+    def as_list(self):
+        return list(self)
+
+
 class T(np.ndarray):
     """ndarray with TF's coercion rule: Python scalars and plain ndarrays take the TENSOR's dtype (no promotion)."""
     __array_priority__ = 100
+
+    @property
+    def shape(self):
+        return _Shape(np.ndarray.shape.__get__(self))
 
     def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kw):
         dts = {i.dtype for i in inputs if isinstance(i, T)}
@@ -84,7 +93,7 @@ def make_tf():
     tf.round = lambda x: tensor(np.round(_plain(x)))
     tf.minimum = _minmax(opr.std_min, np.minimum)
     tf.maximum = _minmax(opr.std_max, np.maximum)
-    tf.squeeze = lambda x, axis=None: tensor(np.squeeze(_plain(x), axis=axis))
+    tf.squeeze = lambda x, axis=None: tensor(np.squeeze(_plain(x), axis=tuple(axis) if isinstance(axis, list) else axis))
     tf.equal = lambda a, b: tensor(_plain(a) == b)
     tf.where = lambda c: tensor(np.argwhere(_plain(c)).astype(np.int64))
     tf.gather_nd = lambda p, ix: tensor(_plain(p)[tuple(_plain(ix).T)])
@@ -108,3 +117,163 @@ class Layer(object):
 
     def __call__(self, inputs):
         return self.call(inputs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Eager stand-ins for the Keras layers the v1 caption models are wired from (text_generation_model.py:130-232).
+# A "model" is built by RUNNING the reference's builder function on real arrays: KL.Input hands back the array
+# registered under its name in FEEDS, every layer computes at once, and KM.Model just keeps the outputs.  Layer
+# numerics (Embedding lookup + mask, masked LSTM scan, Dense + activation) are the oracle's restatements, with the
+# trainable weights looked up by Keras name in WEIGHTS; what is pinned is the WIRING the reference code does.
+# ---------------------------------------------------------------------------------------------------
+FEEDS, WEIGHTS = {}, {}
+
+
+def _with_mask(x, mask):
+    x = tensor(x)
+    x._keras_mask = mask
+    return x
+
+
+def _mask_of(x):
+    return getattr(x, "_keras_mask", None)
+
+
+def make_keras(tf):
+    from oracle import decoder as dec
+
+    counters = collections.Counter()
+
+    def auto_name(kind, name):
+        if name is not None:
+            return name
+        counters[kind] += 1
+        return "%s_%d" % (kind, counters[kind])                # Keras' automatic layer names
+
+    def Input(batch_shape=None, shape=None, name=None, **kw):
+        x = tensor(FEEDS[name] if name is not None else FEEDS["__unnamed__"].pop(0))
+        assert batch_shape is None or list(x.shape) == list(batch_shape), (name, x.shape, batch_shape)
+        assert shape is None or list(x.shape[1:]) == list(shape), (name, x.shape, shape)
+        return x
+
+    class Conv2D(object):
+        """Only what the RoI head needs: 'valid' convolution whose window covers the whole input (7x7 on 7x7, 1x1 on 1x1)."""
+        def __init__(self, filters, kernel_size, padding="valid", trainable=True, name=None):
+            self.filters, self.kernel_size, self.name = filters, tuple(kernel_size), name
+            assert padding == "valid"
+
+        def __call__(self, x):
+            x = _plain(x)
+            k, b = WEIGHTS[self.name + "/kernel"], WEIGHTS[self.name + "/bias"]
+            assert x.shape[1:3] == self.kernel_size == k.shape[:2] and k.shape[3] == self.filters, (x.shape, k.shape)
+            return tensor((x.reshape(x.shape[0], -1) @ k.reshape(-1, k.shape[-1]) + b)[:, None, None, :])
+
+    class BatchNormalization(object):
+        def __init__(self, axis=-1, trainable=True, name=None):
+            self.name = name
+            assert axis in (3, -1)
+
+        def call(self, inputs, training=None):
+            assert training is False                             # the reference's BatchNorm subclass hardcodes it
+            g, b, m, v = (WEIGHTS["%s/%s" % (self.name, n)] for n in ("gamma", "beta", "moving_mean", "moving_variance"))
+            return tensor(dec.batchnorm_inference(_plain(inputs), g, b, m, v))
+
+        def __call__(self, x):
+            return self.call(x)
+
+    class Activation(object):
+        def __init__(self, kind):
+            assert kind == "relu"
+
+        def __call__(self, x):
+            return tensor(np.maximum(_plain(x), 0))
+
+    class Lambda(object):
+        def __init__(self, fn, name=None, **kw):
+            self.fn = fn
+
+        def __call__(self, x):
+            return self.fn(x)
+
+    class Embedding(object):
+        def __init__(self, input_dim, output_dim, weights=None, trainable=True, mask_zero=False, name=None):
+            self.table, self.mask_zero = np.asarray(weights[0], np.float32), mask_zero
+            assert self.table.shape == (input_dim, output_dim)
+
+        def __call__(self, ids):
+            ids = _plain(ids).astype(np.int32)
+            return _with_mask(self.table[ids], (ids != 0) if self.mask_zero else None)
+
+    class LSTM(object):
+        def __init__(self, units, recurrent_dropout=0.0, return_sequences=False, name=None):
+            self.units, self.seq, self.name = units, return_sequences, auto_name("lstm", name)
+
+        def __call__(self, x):
+            mask = _mask_of(x)
+            x = _plain(x)
+            if mask is None:
+                mask = np.ones(x.shape[:2], bool)
+            k, r, b = (WEIGHTS["%s/%s" % (self.name, n)] for n in ("kernel", "recurrent_kernel", "bias"))
+            assert r.shape[0] == self.units
+            out = dec.lstm_masked(x, mask, k, r, b, self.seq)
+            return _with_mask(out, mask if self.seq else None)
+
+    class Dense(object):
+        def __init__(self, units, activation=None, name=None):
+            self.units, self.activation, self.name = units, activation, name
+
+        def __call__(self, x):
+            k, b = WEIGHTS[self.name + "/kernel"], WEIGHTS[self.name + "/bias"]
+            assert k.shape[1] == self.units
+            z = _plain(x) @ k + b
+            return tensor({"relu": lambda v: np.maximum(v, 0), "softmax": dec.softmax, None: lambda v: v}[self.activation](z))
+
+    class Concatenate(object):
+        def __init__(self, axis=-1, name=None):
+            self.axis = axis
+
+        def __call__(self, xs):
+            masks = [m for m in (_mask_of(x) for x in xs) if m is not None]
+            return _with_mask(np.concatenate([_plain(x) for x in xs], self.axis), masks[0] if masks else None)
+
+    class RepeatVector(object):
+        def __init__(self, n):
+            self.n = n
+
+        def __call__(self, x):
+            return tensor(np.repeat(_plain(x)[:, None, :], self.n, 1))
+
+    class TimeDistributed(object):
+        def __init__(self, layer, name=None):
+            self.layer = layer
+            if getattr(layer, "name", "") is None:              # weights are matched through the wrapper's name
+                layer.name = name
+
+        def __call__(self, x):
+            return tensor(np.stack([_plain(self.layer(tensor(_plain(x)[:, t]))) for t in range(x.shape[1])], 1))
+
+    class Model(object):
+        def __init__(self, inputs, outputs, name=None):
+            self.inputs, self.outputs, self.name = inputs, outputs, name
+
+        def __call__(self, x):                                  # a built model re-applied (TimeDistributed): see recallable()
+            return self.recall(x)
+
+    KL = types.SimpleNamespace(Input=Input, Lambda=Lambda, Embedding=Embedding, LSTM=LSTM, Dense=Dense, Concatenate=Concatenate,
+                               RepeatVector=RepeatVector, TimeDistributed=TimeDistributed, Layer=Layer, Conv2D=Conv2D,
+                               BatchNormalization=BatchNormalization, Activation=Activation, _counters=counters)
+    KM = types.SimpleNamespace(Model=Model)
+    K = types.SimpleNamespace(
+        squeeze=lambda x, axis: tensor(np.squeeze(_plain(x), axis)),
+        switch=lambda c, a, b: a if bool(c) else b,
+        mean=lambda x: tensor(np.mean(_plain(x), dtype=_plain(x).dtype)),
+        categorical_crossentropy=lambda target, output: tensor(
+            -np.sum(_plain(target) * np.log(np.clip(_plain(output) / _plain(output).sum(-1, keepdims=True),
+                                                    np.float32(1e-7), np.float32(1 - 1e-7))), -1)))
+    tf.ones = lambda shape: tensor(np.ones([int(s) for s in shape], np.float32))
+    tf.zeros = lambda shape: tensor(np.zeros([int(s) for s in shape], np.float32))
+    tf.argmax = lambda x, axis=None: tensor(np.argmax(_plain(x), axis=axis).astype(np.int64))
+    tf.reduce_sum = lambda x, axis=None: tensor(np.sum(_plain(x), axis=axis, dtype=_plain(x).dtype))
+    tf.size = lambda x: np.size(x)
+    tf.constant = lambda v: tensor(np.float32(v))
+    return KL, KM, K
