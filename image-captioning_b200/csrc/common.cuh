@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 
 #include "../../include/dcap.h"
 
@@ -42,6 +43,21 @@ inline int sm_count() {
 
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+// cudaFuncSetAttribute is per DEVICE: a process that drives several GPUs through this library must opt every kernel
+// into its large dynamic shared memory on each of them.  `seen` is one static per call site; f() is idempotent, so
+// two threads racing on the first call may both run it.
+template <typename F>
+inline cudaError_t once_per_device(std::atomic<unsigned long long> &seen, F &&f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (seen.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = f();
+    if (e == cudaSuccess) seen.fetch_or(bit, std::memory_order_release);
+    return e;
+}
 
 // Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may become resident while
 // the previous kernel of the stream is still draining; it must execute pdl_wait() before it touches

@@ -958,12 +958,9 @@ template <int kBlockN, int kEpi>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const TcEpilogue &ep,
                      const TcGeom &g, cudaStream_t stream, const CUtensorMap *mc = nullptr) {
     using S = TcSmem<kBlockN, kEpi>;
-    static bool attr_set = false;
+    static std::atomic<unsigned long long> attr_set{0};
     auto kern = gemm_bf16_tc_kernel<kBlockN, kEpi>;
-    if (!attr_set) {
-        DC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
-        attr_set = true;
-    }
+    DC_CHECK_CUDA(once_per_device(attr_set, [&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes); }));
     const int units = ceil_div(g.M, kBlockM) * ceil_div(g.N, kBlockN) * g.splits;
     const int grid = units < sm_count() ? units : sm_count();
     DC_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)(g.tma_out ? S::kBytes : S::kBaseBytes), stream, ma, mb, mo,
@@ -1189,13 +1186,12 @@ template <int kEpi>
 static int launch_tc2(const CUtensorMap &ma, const CUtensorMap &mb, const CUtensorMap &mo, const TcEpilogue &ep,
                       const TcGeom &g, cudaStream_t stream) {
     using S = TcSmem2;
-    static bool attr_set = false;
+    static std::atomic<unsigned long long> attr_set{0};
     auto kern = gemm_bf16_tc2_kernel<kEpi>;
-    if (!attr_set) {
-        DC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
-        DC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
-        attr_set = true;
-    }
+    DC_CHECK_CUDA(once_per_device(attr_set, [&] {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
+        return e != cudaSuccess ? e : cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+    }));
     const int tiles = ceil_div(g.M, 2 * kBlockM) * ceil_div(g.N, 256) * g.splits;
     const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
     cudaLaunchConfig_t cfg = {};

@@ -114,11 +114,10 @@ extern "C" int dc_refine_generations(const float *boxes, const float *scores, in
     while (n_pad < n_boxes) n_pad <<= 1;
     const size_t smem = (size_t)n_pad * (4 + 4 + 16 + 4 + 1 + 4) + 16;
     DC_REQUIRE(smem <= 200 * 1024, "n_boxes=%d per image exceeds the shared-memory NMS capacity (%d)", n_boxes, 200 * 1024 / 33);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DC_CHECK_CUDA(cudaFuncSetAttribute(refine_generations_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_set{0};
+    DC_CHECK_CUDA(once_per_device(attr_set, [] {
+        return cudaFuncSetAttribute(refine_generations_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    }));
     refine_generations_kernel<<<n_images, kNmsThreads, smem, (cudaStream_t)stream>>>(boxes, scores, n_boxes, n_pad, nms_threshold,
                                                                                     max_keep, keep, n_keep);
     DC_CHECK_LAUNCH();

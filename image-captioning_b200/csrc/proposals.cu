@@ -547,13 +547,13 @@ extern "C" int dc_proposal_layer(const float *rpn_probs, const float *rpn_bbox, 
     const int chunk = (n_anchors + kSelCluster - 1) / kSelCluster;
     const bool cache = chunk <= kSelMaxChunk;
     const size_t smem = sizeof(SelSmem) + (cache ? (size_t)chunk * sizeof(uint32_t) : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DC_CHECK_CUDA(cudaFuncSetAttribute(proposal_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(sizeof(SelSmem) + (size_t)kSelMaxChunk * sizeof(uint32_t))));
-        DC_CHECK_CUDA(cudaFuncSetAttribute(proposal_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_set{0};
+    DC_CHECK_CUDA(once_per_device(attr_set, [] {
+        const cudaError_t e = cudaFuncSetAttribute(proposal_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(sizeof(SelSmem) + (size_t)kSelMaxChunk * sizeof(uint32_t)));
+        return e != cudaSuccess ? e : cudaFuncSetAttribute(proposal_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           (int)sizeof(SelSmem));
+    }));
     const float4 std_dev = make_float4(bbox_std_dev[0], bbox_std_dev[1], bbox_std_dev[2], bbox_std_dev[3]);
     if (cache)
         proposal_select_kernel<true><<<n_images * kSelCluster, kSelThreads, smem, s>>>(

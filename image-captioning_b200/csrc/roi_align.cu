@@ -406,11 +406,10 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
     pp.levels = levels;
     const size_t prep_smem = (size_t)n_boxes * 32;
     if (prep_smem <= 160 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(roi_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-            attr_set = true;
-        }
+        static std::atomic<unsigned long long> attr_set{0};
+        DC_CHECK_CUDA(once_per_device(attr_set, [] {
+            return cudaFuncSetAttribute(roi_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        }));
         roi_prepare_kernel<true><<<n_images, kPrepThreads, prep_smem, stream>>>(pp);
     } else {
         roi_prepare_kernel<false><<<n_images, kPrepThreads, 0, stream>>>(pp);
@@ -515,7 +514,10 @@ extern "C" int dc_pyramid_roi_align_backward_f32(const float *boxes, const float
     pp.levels = nullptr;
     const size_t prep_smem = (size_t)n_boxes * 32;
     if (prep_smem <= 160 * 1024) {
-        cudaFuncSetAttribute(roi_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        static std::atomic<unsigned long long> attr_set{0};
+        DC_CHECK_CUDA(once_per_device(attr_set, [] {
+            return cudaFuncSetAttribute(roi_prepare_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        }));
         roi_prepare_kernel<true><<<n_images, kPrepThreads, prep_smem, stream>>>(pp);
     } else {
         roi_prepare_kernel<false><<<n_images, kPrepThreads, 0, stream>>>(pp);
