@@ -96,3 +96,47 @@ def test_nms_survivors_never_overlap_more_than_the_threshold(seed, n, thr):
         better = [k for k in keep if s[k] >= s[r]]
         ov = pp.compute_overlap(b[r], b[better], area[r], area[better])
         assert (ov > F32(thr)).any()
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 60), st.floats(min_value=0.0, max_value=0.95), st.integers(1, 70))
+def test_tf_nms_invariants(seed, n, thr, max_out):
+    """tf.image.non_max_suppression restated: survivors are in score order, pairwise IoU <= thr, and every candidate that
+    was passed over before the output filled up overlaps an earlier survivor by more than thr."""
+    from oracle import proposals as pr
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(0.2, 0.8, (n, 2)); h = rng.uniform(0.0, 0.3, (n, 2))
+    b = np.concatenate([c - h, c + h], 1).astype(F32)
+    b[::6, 2:] = b[::6, :2]                                            # empty boxes: IoU 0 with everything
+    s = np.round(rng.standard_normal(n), 1).astype(F32)
+    keep = pr.tf_non_max_suppression(b, s, max_out, thr)
+    assert len(keep) <= max_out and len(set(keep.tolist())) == len(keep) and (np.diff(s[keep]) <= 0).all()
+    for i, k in enumerate(keep):
+        for j in keep[:i]:
+            assert not pr.tf_iou(b[j], b[k]) > F32(thr)
+    order = np.argsort(-s, kind="stable")
+    last = int(np.nonzero(order == keep[-1])[0][0])
+    kept = set(keep.tolist())
+    for pos in range(last):
+        r = order[pos]
+        if r not in kept:
+            earlier = [k for k in keep if int(np.nonzero(order == k)[0][0]) < pos]
+            assert any(pr.tf_iou(b[k], b[r]) > F32(thr) for k in earlier)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 40), st.integers(1, 30))
+def test_proposal_layer_outputs_are_clipped_ordered_and_padded(seed, count, limit):
+    from oracle import proposals as pr
+    rng = np.random.default_rng(seed)
+    anchors = pr.generate_pyramid_anchors((32, 64), [0.5, 1, 2], [[8, 8], [4, 4]], [16, 32], 1)
+    A = anchors.shape[0]
+    probs = rng.uniform(0, 1, (1, A, 2)).astype(F32)
+    bbox = (rng.standard_normal((1, A, 4)) * 3).astype(F32)
+    out, picked = pr.proposal_layer(probs, bbox, anchors, count, 0.7, (128, 128, 3), pre_nms_limit=limit, return_indices=True)
+    n = len(picked[0])
+    assert out.shape == (1, count, 4) and n <= min(count, limit, A)
+    assert (out >= 0).all() and (out <= 1).all() and not out[0, n:].any()
+    assert (out[0, :n, 2] >= out[0, :n, 0]).all() and (out[0, :n, 3] >= out[0, :n, 1]).all()    # exp > 0: never inverted
+    top = pr.top_k_indices(probs[0, :, 1], limit)
+    assert set(picked[0].tolist()) <= set(top.tolist()) and (np.diff(probs[0, picked[0], 1]) <= 0).all()
