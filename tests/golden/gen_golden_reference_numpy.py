@@ -248,6 +248,20 @@ ns4 = {"np": np, "self": Self, "img_boxes": np.zeros((GR, 4)), "img_features": f
 exec(compile(ast.Module(body=[loop], type_ignores=[]), "v2_greedy_loop", "exec"), ns4)
 out["v2_loop_probs"] = np.array(ns4["caps"])                   # [R, P-1, V]
 out["v2_loop_params"] = np.array([GV, GP, GR])
+# the same loop as evaluate_models/eval_text_generation_model_v2.py:176-186 runs it: started from the GT first word
+eval_src = open(os.path.join(REF, "evaluate_models", "eval_text_generation_model_v2.py")).read()
+line_no = 1 + [i for i, l in enumerate(eval_src.split("\n")) if l.strip() == "for j in range(captions.shape[0]):"][0]
+loop2 = [n for n in ast.walk(ast.parse(eval_src)) if isinstance(n, ast.For) and n.lineno == line_no][0]
+start_ids = np.array([3, 7, 1, 12])
+gt_onehot = np.zeros((GR, GP, GV))
+gt_onehot[np.arange(GR), 0, start_ids] = 1.0
+words_seen = []
+ns4b = {"np": np, "features": featg, "captions": gt_onehot, "model": V2Model(), "predictions": [],
+        "config": Self.config, "id_to_word": None, "pad_sequences": lambda seqs, maxlen: dec.pad_sequences_pre(seqs, maxlen),
+        "decode_word": lambda p, id_to_word: words_seen.append(int(np.argmax(p))) or str(int(np.argmax(p)))}
+exec(compile(ast.Module(body=[loop2], type_ignores=[]), "v2_eval_loop", "exec"), ns4b)
+out["v2_eval_start"] = start_ids
+out["v2_eval_predicted"] = np.array([[int(t) for t in d["p"].split(" ")] for d in ns4b["predictions"]])   # [R, P] ids incl. the start word
 
 # ---- the two TF layers on the path, executed over the numpy stand-in ----------------------------------------
 def _extract_defs(path, names):

@@ -173,3 +173,17 @@ def test_whole_models_equal_the_reference_builders():
     got = dec.v2_inject_predict(feat2, G["v2_model_words"], w2)
     assert got.shape == G["v2_model_probs"].shape == (R2, V2)
     np.testing.assert_allclose(got, G["v2_model_probs"], rtol=1e-5, atol=1e-8)
+
+
+def test_v2_greedy_loop_from_a_given_first_word_equals_the_reference():
+    """evaluate_models/eval_text_generation_model_v2.py:176-186 (prev = [gt[0]], then P-1 predicts) run with the stand-in
+    predict(): the decoded ids equal oracle.greedy_v2(start=...)."""
+    from image_captioning_b200 import synth
+    from oracle import decoder as dec
+    V, P, R = [int(v) for v in G["v2_loop_params"]]
+    w = synth.synth_weights_v2(np.random.default_rng(79), V=V, E=6, F=16, units=8, pool=2, C=4, trained_like=False)
+    feat = np.random.default_rng(80).standard_normal((R, 2, 2, 4)).astype(np.float32)
+    tok, _ = dec.greedy_v2(feat, w, P, start=G["v2_eval_start"])
+    want = G["v2_eval_predicted"]
+    assert want.shape == (R, P) and np.array_equal(want[:, 0], G["v2_eval_start"])
+    assert np.array_equal(tok, want[:, 1:])
