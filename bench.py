@@ -900,9 +900,11 @@ def run_ours_proposals(args):
                    "images_per_step": PROP_IMAGES * world, "sharding": "images per rank, no collective",
                    "l2": "inputs larger than L2 (%d MB of RPN outputs per step)" % (PROP_IMAGES * A * 24 // 2 ** 20),
                    "sm_count": sms, "cc": cc},
-        "clocks": clocks, "gpu_launches": K * 3,
+        # 1 select + (IoU mask + scan) per band of 1024 candidates, at most 4 bands (csrc/proposals.cu)
+        "clocks": clocks, "gpu_launches": K * (1 + 2 * min(4, (n_blk + 15) // 16)),
         "roofline": {"bound": "hbm", "kernel": "proposal_select_kernel + proposal_iou_mask_kernel + proposal_nms_scan_kernel "
-                     "(latency-bound: the NMS scan is a serial chain per image)", "achieved": round(achieved, 1), "peak": hbm_peak,
+                     "(not HBM-bound: the IoU mask kernel is issue-bound, select and scan are chains of short dependent phases; "
+                     "profiles/r1_proposals_full.txt)", "achieved": round(achieved, 1), "peak": hbm_peak,
                      "peak_source": hbm_src, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None,
                      "algorithmic_bytes_per_image": bytes_img},
     }
