@@ -26,6 +26,8 @@
 // correctly rounded fp32 exponential (fp64 exp rounded once), as in oracle/proposals.py.
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -36,6 +38,7 @@ constexpr int kSelThreads = 1024;
 constexpr int kSelCluster = 8;
 constexpr int kMaxPreNms = 8192;
 constexpr int kSelMaxChunk = 48 * 1024;          // keys cached in shared memory per CTA (192 KB) -> 393216 anchors per image
+constexpr int kPendCap = 16384;                  // keys kept for the 2nd-4th radix passes (64 KB behind the key cache)
 constexpr int kScanThreads = 1024;               // the OR phase wants many independent fetches in flight
 constexpr int kBandBlocks = 16;                  // NMS runs in bands of 16 x 64 candidates (mask launch + scan launch per band),
 constexpr int kMaxBands = 4;                     // the last band taking whatever is left
@@ -60,15 +63,16 @@ struct SelSmem {
     unsigned int hist[2][256];                // cluster-wide histogram of the current digit (CTA 0's copy), double buffered
     unsigned int lhist[kHistCopies][256];     // this CTA's histogram, one copy per warp & 7
     unsigned int n_gt[kSelCluster], n_eq[kSelCluster];   // per-CTA counts, replicated in every CTA
+    unsigned int lsum[256];                   // this CTA's histogram summed over the copies (kept until the digit is chosen)
     unsigned int warp_cnt[kSelThreads / 32];
-    unsigned int sel_bin, sel_above, ctr;
+    unsigned int sel_bin, sel_above, ctr, loc_gt, loc_eq, pend_ctr;
 };
 
 template <bool kCache>
 __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
 proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__restrict__ rpn_bbox,
                        const float4 *__restrict__ anchors, int n_anchors, int k_eff, float4 std_dev, float img_h,
-                       float img_w, float4 *__restrict__ ws_boxes, int32_t *__restrict__ ws_index) {
+                       float img_w, float4 *__restrict__ ws_boxes, int32_t *__restrict__ ws_index, int pend_cap) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     SelSmem &sm = *reinterpret_cast<SelSmem *>(sm_raw);
     uint32_t *s_key = reinterpret_cast<uint32_t *>(sm_raw + sizeof(SelSmem));
@@ -80,6 +84,11 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
 
     const int chunk = ceil_div(n_anchors, kSelCluster);
     const int lo = min(rank * chunk, n_anchors), n_local = min(lo + chunk, n_anchors) - lo;
+    // keys still in the running after the first digit (those sharing the chosen top byte), compacted so that the
+    // remaining three passes do not rescan the whole slice; behind the key cache, pend_cap entries (0 = none)
+    uint32_t *s_pend = s_key + (kCache ? ((chunk + 3) & ~3) : 0);
+    bool use_pend = false;
+    int n_scan = n_local;
     const float *score = rpn_probs + ((long long)img * n_anchors + lo) * 2 + 1;      // foreground column of [A, 2]
     auto key_at = [&](int i) -> uint32_t { return kCache ? s_key[i] : score_key(__ldg(score + 2 * (long long)i)); };
     if (kCache) {
@@ -97,11 +106,11 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
         for (int i = tid; i < kHistCopies * 256; i += kSelThreads) (&sm.lhist[0][0])[i] = 0;
         if (rank == 0 && tid < 256) sm.hist[pass & 1][tid] = 0;
         cluster.sync();                                     // zeroed before any remote add; also orders s_key writes
-        for (int base = 0; base < n_local; base += kSelThreads) {
+        for (int base = 0; base < n_scan; base += kSelThreads) {
             const int i = base + tid;
             uint32_t key = 0;
-            bool p = i < n_local;
-            if (p) { key = key_at(i); p = (key & mask) == prefix; }
+            bool p = i < n_scan;
+            if (p) { key = use_pend ? s_pend[i] : key_at(i); p = (key & mask) == prefix; }
             const unsigned int bal = __ballot_sync(0xffffffffu, p);
             if (p) {
                 const unsigned int bin = (key >> shift) & 255u;
@@ -114,6 +123,7 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
             unsigned int c = 0;
 #pragma unroll
             for (int r = 0; r < kHistCopies; ++r) c += sm.lhist[r][tid];
+            sm.lsum[tid] = c;
             if (c) atomicAdd(hist0 + tid, c);                                           // DSMEM
         }
         cluster.sync();
@@ -136,33 +146,52 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
             }
         }
         __syncthreads();
+        const unsigned int sel_bin = sm.sel_bin;
         remaining -= sm.sel_above;
-        prefix |= sm.sel_bin << shift;
+        prefix |= sel_bin << shift;
         mask |= 255u << shift;
+        if (warp == 1) {
+            // this CTA's own keys above the chosen digit are selected for good; the last pass also yields its ties
+            unsigned int above = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) above += (unsigned int)(lane * 8 + j) > sel_bin ? sm.lsum[lane * 8 + j] : 0u;
+            above = __reduce_add_sync(0xffffffffu, above);
+            if (lane == 0) {
+                sm.loc_gt = (pass == 0 ? 0u : sm.loc_gt) + above;
+                sm.loc_eq = sm.lsum[sel_bin];
+                sm.pend_ctr = 0;
+            }
+        }
         __syncthreads();
+        if (pass == 0 && (int)sm.lsum[sel_bin] <= pend_cap) {
+            // compact the keys that share the chosen top byte (order is irrelevant for the histograms)
+            for (int base = 0; base < n_local; base += kSelThreads) {
+                const int i = base + tid;
+                uint32_t key = 0;
+                if (i < n_local) key = key_at(i);
+                const bool p = i < n_local && (key & mask) == prefix;
+                const unsigned int bal = __ballot_sync(0xffffffffu, p);
+                if (p) {
+                    unsigned int pos = 0;
+                    const int leader = __ffs(bal) - 1;
+                    if (lane == leader) pos = atomicAdd(&sm.pend_ctr, (unsigned int)__popc(bal));
+                    pos = __shfl_sync(bal, pos, leader) + __popc(bal & ((1u << lane) - 1u));
+                    s_pend[pos] = key;
+                }
+            }
+            use_pend = true;
+            n_scan = (int)sm.lsum[sel_bin];
+            __syncthreads();
+        }
     }
     const uint32_t thr_key = prefix;                         // keys > thr_key are all taken; `remaining` ties are needed
 
-    // ---- counts per CTA -> every CTA knows every CTA's counts ----------------------------------------------
+    // ---- counts per CTA (accumulated from the histograms above) -> every CTA knows every CTA's counts ----------
     if (tid == 0) sm.ctr = 0;
-    if (tid < 2) sm.warp_cnt[tid] = 0;
-    __syncthreads();
-    {
-        unsigned int gt = 0, eq = 0;
-        for (int i = tid; i < n_local; i += kSelThreads) {
-            const uint32_t key = key_at(i);
-            gt += key > thr_key;
-            eq += key == thr_key;
-        }
-        gt = __reduce_add_sync(0xffffffffu, gt);
-        eq = __reduce_add_sync(0xffffffffu, eq);
-        if (lane == 0) { atomicAdd(&sm.warp_cnt[0], gt); atomicAdd(&sm.warp_cnt[1], eq); }
-    }
-    __syncthreads();
     if (tid < kSelCluster) {
         SelSmem *peer = cluster.map_shared_rank(&sm, tid);
-        peer->n_gt[rank] = sm.warp_cnt[0];
-        peer->n_eq[rank] = sm.warp_cnt[1];
+        peer->n_gt[rank] = sm.loc_gt;
+        peer->n_eq[rank] = sm.loc_eq;
     }
     cluster.sync();
     // Candidates are re-dealt evenly over the cluster before sorting (RPN scores cluster spatially, so one CTA's
@@ -205,7 +234,7 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
             pos = __shfl_sync(bal_gt, pos, leader) + __popc(bal_gt & ((1u << lane) - 1u));
             deal(base_pos + pos, comp);
         }
-        if (eq_run < quota) {                                  // uniform
+        if (eq_run < quota && __syncthreads_or(eq)) {          // uniform; ties are rare: one barrier tells that none is here
             const unsigned int bal_eq = __ballot_sync(0xffffffffu, eq);
             if (lane == 0) sm.warp_cnt[warp] = __popc(bal_eq);
             __syncthreads();
@@ -546,23 +575,26 @@ extern "C" int dc_proposal_layer(const float *rpn_probs, const float *rpn_bbox, 
 
     const int chunk = (n_anchors + kSelCluster - 1) / kSelCluster;
     const bool cache = chunk <= kSelMaxChunk;
-    const size_t smem = sizeof(SelSmem) + (cache ? (size_t)chunk * sizeof(uint32_t) : 0);
+    const size_t key_bytes = cache ? (size_t)((chunk + 3) & ~3) * sizeof(uint32_t) : 0;
+    const size_t smem_max = sizeof(SelSmem) + (size_t)kSelMaxChunk * sizeof(uint32_t);           // what the kernels are opted into
+    const int pend_cap = (int)std::min<size_t>(kPendCap, (smem_max - sizeof(SelSmem) - key_bytes) / sizeof(uint32_t));
+    const size_t smem = sizeof(SelSmem) + key_bytes + (size_t)pend_cap * sizeof(uint32_t);
     static std::atomic<unsigned long long> attr_set{0};
     DC_CHECK_CUDA(once_per_device(attr_set, [] {
         const cudaError_t e = cudaFuncSetAttribute(proposal_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    (int)(sizeof(SelSmem) + (size_t)kSelMaxChunk * sizeof(uint32_t)));
         return e != cudaSuccess ? e : cudaFuncSetAttribute(proposal_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                           (int)sizeof(SelSmem));
+                                                           (int)(sizeof(SelSmem) + (size_t)kSelMaxChunk * sizeof(uint32_t)));
     }));
     const float4 std_dev = make_float4(bbox_std_dev[0], bbox_std_dev[1], bbox_std_dev[2], bbox_std_dev[3]);
     if (cache)
         proposal_select_kernel<true><<<n_images * kSelCluster, kSelThreads, smem, s>>>(
             rpn_probs, reinterpret_cast<const float4 *>(rpn_bbox), reinterpret_cast<const float4 *>(anchors), n_anchors, k, std_dev,
-            image_h, image_w, ws_boxes, ws_index);
+            image_h, image_w, ws_boxes, ws_index, pend_cap);
     else
         proposal_select_kernel<false><<<n_images * kSelCluster, kSelThreads, smem, s>>>(
             rpn_probs, reinterpret_cast<const float4 *>(rpn_bbox), reinterpret_cast<const float4 *>(anchors), n_anchors, k, std_dev,
-            image_h, image_w, ws_boxes, ws_index);
+            image_h, image_w, ws_boxes, ws_index, pend_cap);
     DC_CHECK_LAUNCH();
     const size_t scan_smem = (size_t)n_blk * sizeof(unsigned long long) + (size_t)proposal_count * sizeof(int);
     DC_REQUIRE(scan_smem <= 48 * 1024, "proposal_count=%d too large", proposal_count);
