@@ -2,7 +2,7 @@
 """Benchmark of the per-RoI captioning hot path (contract in the task prompt, section 4).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload roi_features]
+                    [--workload captions|roi_features|train|beam|proposals]
 
 One "step" = one pass of the hot path over one batch of synthetic input.  Workloads:
 
@@ -12,6 +12,9 @@ One "step" = one pass of the hot path over one batch of synthetic input.  Worklo
                 decoder: hidden 512, vocab 10k, embedding 300, P = 15) -> [8000, 15] token ids.
                 bf16 tensor-core decoder, fp32 ROIAlign arithmetic.
   roi_features  BASELINE.json configs[1] alone: 8 images x 1000 RoIs -> [8000, 7, 7, 256] fp32.
+  train         configs[2]: one v1 decoder training step (bf16, global batch 4096 x P=16, AMSGrad), data parallel.
+  beam          configs[3]: width-3 beam decoding of 100k pre-extracted RoI feature vectors.
+  proposals     SURVEY.md 8f rank 3: ProposalLayer on 32 images x 261888 anchors per GPU (top 6000 -> NMS -> 1000).
 
 With N GPUs every rank owns its own 8 images (weak scaling, images sharded, no collective).
 
