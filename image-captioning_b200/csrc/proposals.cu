@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(64 * kMaskColBlocks) proposal_iou_mask_kernel(
     mask[((long long)img * n + i) * n_blk + cb] = bits;
 }
 
-constexpr int kScanBatch = 4;                                   // mask words in flight per thread in the OR phase
+constexpr int kScanBatch = 8;                                   // mask words in flight per thread in the OR phase
 
 // Scan state carried from one band to the next (global memory, per image).
 struct ScanState {
@@ -443,16 +443,21 @@ __global__ void __launch_bounds__(kScanThreads) proposal_nms_scan_kernel(const f
             unsigned long long r = s_removed[blk], kept = 0ull;
             int count = count0;
             const unsigned long long *diag = s_diag[blk & 1];
-            // visit only the survivors: the next one is the lowest bit that is neither removed nor already passed
-            unsigned long long todo = rows < 64 ? (1ull << rows) - 1ull : ~0ull;
-            while (count < proposal_count) {
-                const unsigned long long avail = ~r & todo;
-                if (!avail) break;
-                const int t = __ffsll((long long)avail) - 1;
-                kept |= 1ull << t;
-                ++count;
-                r |= diag[t];
-                todo &= ~((2ull << t) - 1ull);
+            // eight candidates per round: their diagonal words are fetched together (independent shared-memory loads),
+            // so the dependency chain between candidates is register arithmetic only
+            for (int t0 = 0; t0 < rows && count < proposal_count; t0 += 8) {
+                unsigned long long d[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d[q] = diag[t0 + q];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int t = t0 + q;
+                    if (t < rows && !((r >> t) & 1ull) && count < proposal_count) {
+                        kept |= 1ull << t;
+                        ++count;
+                        r |= d[q];
+                    }
+                }
             }
             s_kept_bits = kept;
             s_count = count;
