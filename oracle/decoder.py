@@ -61,14 +61,15 @@ def softmax(z):
     return e / e.sum(axis=-1, keepdims=True)
 
 
-def lstm_cell(x, h, c, kernel, recurrent, bias):
-    """Keras LSTMCell (implementation=1, tanh / hard_sigmoid, gate blocks i|f|c|o)."""
+def lstm_cell(x, h, c, kernel, recurrent, bias, recurrent_activation=hard_sigmoid):
+    """Keras LSTMCell (implementation=1, tanh / hard_sigmoid, gate blocks i|f|c|o).  ``recurrent_activation`` exists
+    for the cross-check against torch.nn.LSTMCell (logistic sigmoid) in tests/test_oracle_decoder.py."""
     z = (x @ kernel + bias) + h @ recurrent
     u = h.shape[-1]
-    i = hard_sigmoid(z[..., 0 * u:1 * u])
-    f = hard_sigmoid(z[..., 1 * u:2 * u])
+    i = recurrent_activation(z[..., 0 * u:1 * u])
+    f = recurrent_activation(z[..., 1 * u:2 * u])
     g = np.tanh(z[..., 2 * u:3 * u])
-    o = hard_sigmoid(z[..., 3 * u:4 * u])
+    o = recurrent_activation(z[..., 3 * u:4 * u])
     c_new = f * c + i * g
     h_new = o * np.tanh(c_new)
     return h_new, c_new

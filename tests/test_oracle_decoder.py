@@ -146,3 +146,64 @@ def test_oracle_reproduces_golden_decoder_vectors(golden_dir):
     assert abs(float(now["loss"]) - float(g["loss"])) < 1e-6
     np.testing.assert_allclose(now["grad_l2"], g["grad_l2"], rtol=1e-9)
     np.testing.assert_allclose(now["grad_sum"], g["grad_sum"], rtol=1e-7, atol=1e-12)
+
+
+def test_amsgrad_mechanics_agree_with_an_independent_implementation():
+    """torch.optim.Adam(amsgrad=True) is the same recurrence as Keras' up to where epsilon enters (Keras: sqrt(vhat) + eps
+    after folding both bias corrections into lr_t; torch: sqrt(vhat / (1 - b2^t)) + eps).  With a negligible epsilon
+    the two must coincide: an independent check of the moment updates, the running maximum and the bias corrections."""
+    import torch
+    rng = np.random.default_rng(17)
+    p0 = rng.standard_normal((5, 7))
+    grads = [rng.standard_normal((5, 7)) * s for s in (1.0, 0.1, 3.0, 0.01, 1.0, 0.5)]     # vhat must hold earlier maxima
+    tp = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adam([tp], lr=1e-3, betas=(0.9, 0.999), eps=1e-30, amsgrad=True)
+    p, m, v, vh = p0.copy(), np.zeros_like(p0), np.zeros_like(p0), np.zeros_like(p0)
+    for t, g in enumerate(grads, 1):
+        tp.grad = torch.from_numpy(g.copy())
+        opt.step()
+        p, m, v, vh = dec.keras_adam_amsgrad(p, g, m, v, vh, t, eps=1e-30)
+        np.testing.assert_allclose(p, tp.detach().numpy(), rtol=1e-12, atol=1e-15)
+    assert (vh >= v).all() and (vh > v).any()
+
+
+def test_lstm_cell_wiring_agrees_with_an_independent_implementation():
+    """torch.nn.LSTMCell has the same gate order (i, f, g, o) and state update as Keras' LSTMCell and differs only in the
+    recurrent activation (logistic sigmoid vs hard_sigmoid): with that swapped in, the oracle's cell must reproduce it.
+    And Keras' hard_sigmoid is the line 0.2 x + 0.5 clipped to [0, 1] (tangent-free piecewise linear, exact at 0, +-2.5)."""
+    import torch
+    rng = np.random.default_rng(18)
+    n_in, u, B = 5, 4, 3
+    cell = torch.nn.LSTMCell(n_in, u).double()
+    x, h, c = (rng.standard_normal(s) for s in ((B, n_in), (B, u), (B, u)))
+    with torch.no_grad():
+        h_t, c_t = cell(torch.from_numpy(x), (torch.from_numpy(h), torch.from_numpy(c)))
+    kernel = cell.weight_ih.detach().numpy().T                  # Keras stores [in, 4u]
+    recurrent = cell.weight_hh.detach().numpy().T
+    bias = (cell.bias_ih + cell.bias_hh).detach().numpy()
+    sigmoid = lambda z: 1.0 / (1.0 + np.exp(-z))
+    h_o, c_o = dec.lstm_cell(x, h, c, kernel, recurrent, bias, recurrent_activation=sigmoid)
+    np.testing.assert_allclose(h_o, h_t.numpy(), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(c_o, c_t.numpy(), rtol=1e-12, atol=1e-14)
+    z = np.array([-3.0, -2.5, -1.0, 0.0, 1.0, 2.5, 3.0])
+    assert dec.hard_sigmoid(z).tolist() == [0.0, 0.0, 0.3, 0.5, 0.7, 1.0, 1.0]
+
+
+def test_batchnorm_and_cross_entropy_agree_with_independent_implementations():
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(19)
+    x = rng.standard_normal((6, 9))
+    gamma, beta, mean = (rng.standard_normal(9) for _ in range(3))
+    var = rng.uniform(0.1, 2.0, 9)
+    want = F.batch_norm(torch.from_numpy(x), torch.from_numpy(mean), torch.from_numpy(var), torch.from_numpy(gamma),
+                        torch.from_numpy(beta), training=False, eps=dec.BN_EPS).numpy()
+    np.testing.assert_allclose(dec.batchnorm_inference(x, gamma, beta, mean, var), want, rtol=1e-12, atol=1e-13)
+    logits = rng.standard_normal((4, 5, 11)) * 3
+    ids = rng.integers(0, 11, (4, 5))
+    probs = dec.softmax(logits)
+    want_loss = F.cross_entropy(torch.from_numpy(logits).reshape(-1, 11), torch.from_numpy(ids).reshape(-1)).item()
+    np.testing.assert_allclose(dec.roi_caption_loss(ids, probs), want_loss, rtol=1e-10)      # no probability near the 1e-7 clip
+    valid = rng.uniform(size=(4, 5)) < 0.6
+    want_masked = F.cross_entropy(torch.from_numpy(logits)[torch.from_numpy(valid)], torch.from_numpy(ids)[torch.from_numpy(valid)]).item()
+    np.testing.assert_allclose(dec.roi_caption_loss(ids, probs, valid), want_masked, rtol=1e-10)
