@@ -54,3 +54,25 @@ def test_proposal_layer_shapes_padding_and_range():
     # fewer anchors than the pre-NMS limit and than proposal_count: everything is a candidate, rest is padding
     out = pr.proposal_layer(probs[:, :20], bbox[:, :20], anchors[:20], 50, 0.7, (128, 128, 3))
     assert out.shape == (2, 50, 4) and not out[:, 20:].any()
+
+
+def test_tf_nms_restatement_agrees_with_torchvision_nms():
+    """torchvision.ops.nms is the same greedy rule (descending score, suppress when IoU > threshold) on (x1,y1,x2,y2)
+    boxes: for well-formed boxes with distinct scores the restated tf.image.non_max_suppression must keep the same set
+    in the same order (an independent implementation of the part TensorFlow is needed for)."""
+    import torch
+    from torchvision.ops import nms
+    rng = np.random.default_rng(7)
+    for n, thr in ((50, 0.7), (300, 0.5), (300, 0.3), (800, 0.7)):
+        c = rng.uniform(0.2, 0.8, (n, 2)); h = rng.uniform(0.02, 0.25, (n, 2))
+        b = np.concatenate([c - h, c + h], 1).astype(F32)                      # (y1, x1, y2, x2), positive area
+        s = rng.permutation(n).astype(F32) / n                                  # distinct scores
+        got = pr.tf_non_max_suppression(b, s, n, thr)
+        want = nms(torch.from_numpy(b[:, [1, 0, 3, 2]].copy()), torch.from_numpy(s), thr).numpy()
+        if not np.array_equal(got, want):
+            # fp32 IoU values within an ulp of the threshold may be decided differently by the two formulas
+            diff = set(got.tolist()) ^ set(want.tolist())
+            assert len(diff) <= 2, (n, thr, sorted(diff))
+        assert len(got) > 0
+        got_cut = pr.tf_non_max_suppression(b, s, 10, thr)
+        assert np.array_equal(got_cut, got[:10])                                # max_output_size only truncates
