@@ -946,6 +946,38 @@ def run_ours_proposals(args):
         dist.destroy_process_group()
 
 
+def run_reference_proposals(args):
+    """Reference arm of the proposals workload: the numpy restatement of ProposalLayer (oracle/proposals.py) on one
+    image of the same configuration per step (the reference's own layer is a TensorFlow graph)."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import image_captioning_b200.proposals as prod
+    from oracle import proposals as opr
+    cfg = prod.ProposalConfig()
+    anchors = cfg.anchors()
+    A = anchors.shape[0]
+    rng = np.random.default_rng(1005)
+    fg = (1.0 / (1.0 + np.exp(-(rng.standard_normal((1, A)) * 2.5 - 4.0)))).astype(np.float32)
+    probs = np.stack([1 - fg, fg], -1)
+    bbox = (rng.standard_normal((1, A, 4)) * 1.5).astype(np.float32)
+    for _ in range(max(1, min(args.warmup, 2))):
+        opr.proposal_layer(probs, bbox, anchors, PROP_COUNT, PROP_NMS, cfg.IMAGE_SHAPE)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        opr.proposal_layer(probs, bbox, anchors, PROP_COUNT, PROP_NMS, cfg.IMAGE_SHAPE)
+    el = time.perf_counter() - t0
+    value = args.steps / el
+    line = {"impl": "reference", "metric": "proposal_images_per_sec", "value": round(value, 2), "unit": "images/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(el / args.steps * 1e3, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "proposals (bounded sample: 1 image x %d anchors per step)" % A},
+            "cpu_baseline": {"value": round(value, 2), "unit": "images/s", "cores": 1, "kind": "port",
+                             "sample": "1 image per step through oracle/proposals.py (numpy)"},
+            "e2e": {"value": round(value, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -958,7 +990,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
-        (run_reference if args.workload == "roi_features" else run_reference_captions)(args)
+        {"roi_features": run_reference, "proposals": run_reference_proposals}.get(args.workload, run_reference_captions)(args)
     elif args.workload == "captions":
         run_ours_captions(args)
     elif args.workload == "train":
