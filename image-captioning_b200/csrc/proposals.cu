@@ -56,11 +56,12 @@ __device__ __forceinline__ uint32_t score_key(float s) {
 __device__ __forceinline__ float std_min(float a, float b) { return b < a ? b : a; }
 __device__ __forceinline__ float std_max(float a, float b) { return a < b ? b : a; }
 
+static_assert(kSelThreads == 4 * 256, "the digit histograms are zeroed one word per thread");
 constexpr int kHistCopies = 8;                  // replicated per-CTA histograms: RPN scores share few top bytes
 
 struct SelSmem {
     unsigned long long sort[kMaxPreNms / kSelCluster];   // this CTA's share of the candidates as (key << 32) | ~anchor, sorted descending
-    unsigned int hist[2][256];                // cluster-wide histogram of the current digit (CTA 0's copy), double buffered
+    unsigned int hist[4][256];                // cluster-wide histogram of each digit (CTA 0's copy), all zeroed up front
     unsigned int lhist[kHistCopies][256];     // this CTA's histogram, one copy per warp & 7
     unsigned int n_gt[kSelCluster], n_eq[kSelCluster];   // per-CTA counts, replicated in every CTA
     unsigned int lsum[256];                   // this CTA's histogram summed over the copies (kept until the digit is chosen)
@@ -102,10 +103,14 @@ proposal_select_kernel(const float *__restrict__ rpn_probs, const float4 *__rest
     unsigned int remaining = (unsigned int)k_eff;
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
-        unsigned int *hist0 = sm0->hist[pass & 1];
+        unsigned int *hist0 = sm0->hist[pass];
         for (int i = tid; i < kHistCopies * 256; i += kSelThreads) (&sm.lhist[0][0])[i] = 0;
-        if (rank == 0 && tid < 256) sm.hist[pass & 1][tid] = 0;
-        cluster.sync();                                     // zeroed before any remote add; also orders s_key writes
+        if (pass == 0) {
+            if (rank == 0) (&sm.hist[0][0])[tid] = 0;       // 4 x 256 words, one per thread
+            cluster.sync();                                 // zeroed before any remote add; also orders s_key writes
+        } else {
+            __syncthreads();
+        }
         for (int base = 0; base < n_scan; base += kSelThreads) {
             const int i = base + tid;
             uint32_t key = 0;
