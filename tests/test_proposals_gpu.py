@@ -142,6 +142,33 @@ def test_device_tensors_stay_on_the_device_and_feed_roi_align():
     assert np.array_equal(pooled.float().cpu().numpy().reshape(ref.shape).view(np.uint32), ref.view(np.uint32))
 
 
+def test_generated_rois_through_the_caption_pipeline():
+    """use_generated_rois=True end to end on the device: RPN outputs -> ProposalLayer -> PyramidROIAlign -> head -> greedy
+    decoding (fp32 model), every stage bit-exact, so the token ids equal the oracle chain's."""
+    import image_captioning_b200 as pkg
+    from image_captioning_b200 import synth
+    from oracle import decoder as dec
+    from oracle import roi_align as ra
+    rng = np.random.default_rng(67)
+    cfg = pkg.ProposalConfig(IMAGE_MAX_DIM=256)
+    anchors = cfg.anchors()
+    probs, bbox = _rpn_like(rng, 2, anchors)
+    layer = pkg.ProposalLayer(40, 0.7, anchors, cfg)
+    rois = layer([torch.from_numpy(probs).cuda(), torch.from_numpy(bbox).cuda()])
+    C, V, P = 64, 500, 6
+    fms = [rng.standard_normal((2, 64 >> i, 64 >> i, C)).astype(F32) for i in range(4)]
+    w = synth.synth_weights_v1(np.random.default_rng(68), V=V, E=48, U=128, C=C)
+    mcfg = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], 1, P)
+    model = pkg.build_lstm_model([7, 7, C], mcfg, 128, "inference", dtype="float32")
+    model.set_weights(w)
+    tok = model.caption_rois(rois, [torch.from_numpy(f).cuda() for f in fms], tuple(cfg.IMAGE_SHAPE)).cpu().numpy()
+    rois_want = pr.proposal_layer(probs, bbox, anchors, 40, 0.7, cfg.IMAGE_SHAPE)
+    pooled, _ = ra.pyramid_roi_align(rois_want, fms, (7, 7), tuple(cfg.IMAGE_SHAPE))
+    tok_want, _ = dec.greedy_v1(dec.head(pooled[0], w), w, P)
+    assert tok.shape == tok_want.shape == (80, P)
+    assert np.array_equal(tok, tok_want)
+
+
 def test_normalize_boxes_is_an_fp32_division():
     import image_captioning_b200 as pkg
     rng = np.random.default_rng(65)
