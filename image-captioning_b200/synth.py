@@ -83,17 +83,75 @@ def _embedding(rng, V, E):
     return e
 
 
-def _vocab_bias(V, trained_like):
+# ---- "trained-like" decoders ---------------------------------------------------------------
+# Plain Glorot weights give a near-uniform soft-max whose arg-max is decided by 1e-5-sized gaps and a
+# word feedback path too weak to matter; a parity test on such a model says little.  The generators
+# below shape the random weights the way a trained captioner's are, so that free-running decoding
+#   * never emits <pad>=0 / <start>=1 (strongly negative output bias; a 0 would freeze the masked scan),
+#   * uses hundreds of distinct words (Zipf unigram prior, -log(1+rank), over a random permutation of
+#     the ids >= 3: rank and id are unrelated, as in a real vocabulary file),
+#   * depends on the consumed word (embedding -> gate and state -> dense gains), so tokens change along
+#     the caption and a wrong token changes what follows,
+#   * is as confident as the reference's own checkpoint: heavy-tailed vocabulary projection scaled to a
+#     logit spread of ~3, which puts the mean greedy -log p near the 1.69 validation loss in the
+#     reference's checkpoint name (text_generation_model.py:484) and the median top-1/top-2 gap at ~0.6,
+#   * favours <end>=2 only late: a few LSTM units are wired as step counters (input/forget/output
+#     gates saturated open, constant small candidate) that switch dedicated dense units on after ~10
+#     consumed words, which in turn feed the <end> logit.  The reference's loops never stop at <end>
+#     (text_generation_model.py:207-229), so what follows it is decoded and compared too.
+# tests/test_synth.py asserts these properties so the generator cannot slide back to degenerate captions.
+
+EMBED_GAIN = 8.0          # W[:E] of the LSTM that consumes the word
+STATE_GAIN = 5.0          # rows of the dense / image-LSTM kernel fed by the recurrent state
+LAYER2_GAIN = 4.0         # input kernel of the second LSTM of the v1 stack
+FEATURE_GAIN = 0.5        # rows of the v1 dense kernel fed by the image feature
+LOGIT_TAIL = 3.0          # vocabulary projection ~ sign(g) |g|^LOGIT_TAIL, g ~ N(0,1)
+LOGIT_SCALE = 4.0         # its column norm, in units of 1/sqrt(fan_in/2)
+SPECIAL_BIAS = -30.0      # <pad>, <start>
+COUNTER_STEP = 0.06       # tanh(candidate) of a counter unit
+V2_STATE_GAIN = 2.0       # v2: rows of the image-LSTM kernel fed by the word vector
+V2_LOGIT_SCALE = 14.0     # v2: the vocabulary projection reads 256 bounded LSTM outputs (rms ~0.2), not 1024 ReLUs
+
+
+def _vocab_kernel(rng, n_in, V, trained_like, scale=LOGIT_SCALE):
+    if not trained_like:
+        return _glorot(rng, (n_in, V), n_in, V)
+    g = rng.standard_normal((n_in, V))
+    k = np.sign(g) * np.abs(g) ** LOGIT_TAIL
+    k *= scale / np.sqrt(0.5 * n_in) / k.std()
+    return k.astype(F32)
+
+
+def _vocab_bias(rng, V, trained_like):
     if not trained_like:
         return np.zeros(V, F32)
-    # Zipfian unigram prior, as a trained captioner's output bias has (log frequency).
-    return (-np.log(1.0 + np.arange(V))).astype(F32)
+    b = np.full(V, SPECIAL_BIAS, F32)
+    if V > 3:
+        b[3 + rng.permutation(V - 3)] = -np.log(1.0 + np.arange(V - 3))
+    if V > 2:
+        b[2] = -np.log(6.0)                               # <end>: a mid-frequency word before the counters fire
+    return b
+
+
+def _n_counters(u):
+    return max(1, u // 64)
+
+
+def _wire_counters(kern, rec, bias, u):
+    """Turn the last _n_counters(u) units of a Keras LSTM (blocks i|f|c|o) into step counters:
+    c_t = COUNTER_STEP * t, h_t = tanh(c_t), independent of the input."""
+    n = _n_counters(u)
+    for g, b in ((0, 10.0), (1, 10.0), (2, float(np.arctanh(COUNTER_STEP))), (3, 10.0)):
+        cols = slice(g * u + u - n, g * u + u)
+        kern[:, cols] = 0.0
+        rec[:, cols] = 0.0
+        bias[cols] = b
+    return n
 
 
 def synth_weights_v1(rng, V=10000, E=300, F=1024, U=512, pool=7, C=256, trained_like=True):
-    """Keras-ordered weights of build_lstm_model.  ``trained_like`` sharpens the output
-    distribution (logit temperature + Zipf bias) the way a trained captioner's is; plain
-    Glorot gives a near-uniform softmax whose argmax is decided by 1e-3-sized gaps."""
+    """Keras-ordered weights of build_lstm_model; ``trained_like`` as described above, else plain
+    Glorot / orthogonal / zero-bias initialisers."""
     w = _head_weights(rng, pool, C, F)
     w["imgcap_embedding_layer/embeddings"] = _embedding(rng, V, E)
     (w["imgcap_lstm1/kernel"], w["imgcap_lstm1/recurrent_kernel"],
@@ -102,10 +160,22 @@ def synth_weights_v1(rng, V=10000, E=300, F=1024, U=512, pool=7, C=256, trained_
      w["imgcap_lstm2/bias"]) = _lstm_weights(rng, U, U)
     w["imgcap_lstm_d1/kernel"] = _glorot(rng, (U + F, 1024), U + F, 1024)
     w["imgcap_lstm_d1/bias"] = np.zeros(1024, F32)
-    w["imgcap_lstm_d2/kernel"] = _glorot(rng, (1024, V), 1024, V)
+    w["imgcap_lstm_d2/kernel"] = _vocab_kernel(rng, 1024, V, trained_like)
+    w["imgcap_lstm_d2/bias"] = _vocab_bias(rng, V, trained_like)
     if trained_like:
-        w["imgcap_lstm_d2/kernel"] *= F32(3.0)
-    w["imgcap_lstm_d2/bias"] = _vocab_bias(V, trained_like)
+        w["imgcap_lstm1/kernel"][:E] *= F32(EMBED_GAIN)
+        w["imgcap_lstm_d1/kernel"][:U] *= F32(STATE_GAIN)
+        w["imgcap_lstm_d1/kernel"][U:] *= F32(FEATURE_GAIN)
+        w["imgcap_lstm2/kernel"] *= F32(LAYER2_GAIN)
+        n = _wire_counters(w["imgcap_lstm2/kernel"], w["imgcap_lstm2/recurrent_kernel"], w["imgcap_lstm2/bias"], U)
+        # dense units 1020..1023 = relu(2*8/n * sum(counter h) - 8.5 + noise(f)); they feed only <end>
+        k1, k2 = w["imgcap_lstm_d1/kernel"], w["imgcap_lstm_d2/kernel"]
+        k1[:U, -4:] = 0.0
+        k1[U - n:U, -4:] = 16.0 / n
+        w["imgcap_lstm_d1/bias"][-4:] = -8.5
+        k2[-4:, :] = 0.0
+        if V > 2:
+            k2[-4:, 2] = 2.0
     return w
 
 
@@ -116,10 +186,24 @@ def synth_weights_v2(rng, V=10000, E=300, F=1024, units=256, pool=7, C=256, trai
     w["lstm_1/kernel"], w["lstm_1/recurrent_kernel"], w["lstm_1/bias"] = _lstm_weights(rng, E, 1024)
     (w["imgcap_lstm/kernel"], w["imgcap_lstm/recurrent_kernel"],
      w["imgcap_lstm/bias"]) = _lstm_weights(rng, F + 1024, units)
-    w["imgcap_d1/kernel"] = _glorot(rng, (units, V), units, V)
+    w["imgcap_d1/kernel"] = _vocab_kernel(rng, units, V, trained_like, V2_LOGIT_SCALE)
+    w["imgcap_d1/bias"] = _vocab_bias(rng, V, trained_like)
     if trained_like:
-        w["imgcap_d1/kernel"] *= F32(3.0)
-    w["imgcap_d1/bias"] = _vocab_bias(V, trained_like)
+        w["lstm_1/kernel"] *= F32(EMBED_GAIN)
+        w["imgcap_lstm/kernel"][F:] *= F32(V2_STATE_GAIN)
+        n = _wire_counters(w["lstm_1/kernel"], w["lstm_1/recurrent_kernel"], w["lstm_1/bias"], 1024)
+        # image-LSTM units units-2.. (single step from the zero state: h = o*tanh(i*g)) take their
+        # candidate from the word-LSTM counters only and feed only <end>
+        k, b = w["imgcap_lstm/kernel"], w["imgcap_lstm/bias"]
+        for g, bias in ((0, 10.0), (2, -8.5), (3, 10.0)):
+            cols = slice(g * units + units - 2, g * units + units)
+            k[:, cols] = 0.0
+            b[cols] = bias
+            if g == 2:
+                k[F + 1024 - n:, cols] = 16.0 / n
+        w["imgcap_d1/kernel"][-2:, :] = 0.0
+        if V > 2:
+            w["imgcap_d1/kernel"][-2:, 2] = 12.0
     return w
 
 
