@@ -299,6 +299,370 @@ roi_align_stream_kernel(const RoiStreamParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Round-2 forward path: shared-memory ring fed by bulk async copies (cp.async.bulk -> SASS UBLKCP).
+//
+// The register-gather kernel above is latency-bound (ncu: long_scoreboard 56 %, DRAM 59 % busy, 43 % of the
+// warp slots): every lane waits on its own 1 KB-granular taps.  Here the gather is decoupled from the math:
+//
+//   * roi_order_kernel (one CTA per image) only computes levels and the locality order -- 8 bytes per RoI.
+//     The sampling records of the first design (240 B per RoI, written and re-read through L2) are gone: the
+//     producer warp derives them in registers, one sample per lane.
+//   * roi_align_ring_kernel, persistent CTAs = 1 producer warp + N consumer warps around a ring of ROW SLOTS in
+//     shared memory.  For one RoI the taps live in <= 2*ph distinct map rows, and in every such row in the SAME
+//     <= 2*pw distinct pixels (NHWC: one pixel = `channels` contiguous floats).  The producer de-duplicates both
+//     (a sample row's bottom row is usually the next sample row's top row; neighbouring samples share pixels),
+//     merges adjacent pixels into runs and issues ONE bulk copy per (row, run) into the row's slot; completion
+//     is counted on the slot's mbarrier (expect_tx).  A row slot is released by the consumers as soon as the last
+//     sample row that reads it is done, so the producer runs ahead by the whole ring (K x 14 KB in flight per CTA
+//     -- far more than the 28 warps x 8 LDG.128 the gather kernel could keep outstanding) and across RoI
+//     boundaries.  Per RoI the L2 -> SM traffic drops from 196 taps to the ~144 distinct pixels.
+//   * consumers: warp = output bin column; per sample row they wait for its (top, bottom) slots, lerp out of
+//     shared memory with 128-bit LDS (lane = 4 channels, conflict-free) and write with streaming 128-bit stores.
+//     A tiny descriptor ring (slots, lerp weights, release flags) carries the producer's decisions.
+// Arithmetic is unchanged (same individually rounded ops), so results stay bit-identical to the oracle.
+// ---------------------------------------------------------------------------------------------
+struct RoiOrderParams {
+    const float *boxes;
+    int n_boxes;          // per image
+    float denom;
+    int2 *order;          // [total] sorted: {roi index, level}
+    int2 *scratch;        // [total] {key, rank} when the image does not fit the shared-memory cache
+    int32_t *levels;      // optional
+};
+
+template <bool kSmemCache>
+__global__ void __launch_bounds__(kPrepThreads) roi_order_kernel(const RoiOrderParams p) {
+    __shared__ int s_hist[kBuckets];
+    __shared__ int s_warp_sum[kPrepThreads / 32];
+    extern __shared__ int2 s_kr[];                         // [n_boxes] {key | level << 16, rank}
+    const int tid = threadIdx.x;
+    const long long img = blockIdx.x;
+    for (int i = tid; i < kBuckets; i += kPrepThreads) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < p.n_boxes; i += kPrepThreads) {
+        const long long roi = img * p.n_boxes + i;
+        const float4 box = __ldg(reinterpret_cast<const float4 *>(p.boxes) + roi);
+        const float y1 = box.x, x1 = box.y, y2 = box.z, x2 = box.w;
+        const int lv = fpn_level_dev(y1, x1, y2, x2, p.denom);
+        if (p.levels) p.levels[roi] = lv;
+        float cy = 0.5f * (y1 + y2), cx = 0.5f * (x1 + x2);
+        cy = (cy >= 0.f && cy <= 1.f) ? cy : 0.f;       // also maps NaN to 0
+        cx = (cx >= 0.f && cx <= 1.f) ? cx : 0.f;
+        const unsigned ty = min(15u, (unsigned)(cy * 16.f)), tx = min(15u, (unsigned)(cx * 16.f));
+        const int key = (lv - 2) * 256 + (int)((morton4(ty) << 1) | morton4(tx));
+        const int rank = atomicAdd(&s_hist[key], 1);
+        const int2 kr = make_int2(key | (lv << 16), rank);
+        if constexpr (kSmemCache) s_kr[i] = kr; else p.scratch[roi] = kr;
+    }
+    __syncthreads();
+    {
+        const int v = s_hist[tid];
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((tid & 31) >= d) inc += t;
+        }
+        if ((tid & 31) == 31) s_warp_sum[tid >> 5] = inc;
+        __syncthreads();
+        if (tid < 32) {
+            int w = s_warp_sum[tid];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, d);
+                if (tid >= d) w += t;
+            }
+            s_warp_sum[tid] = w;
+        }
+        __syncthreads();
+        const int warp_off = (tid >> 5) ? s_warp_sum[(tid >> 5) - 1] : 0;
+        s_hist[tid] = warp_off + inc - v;
+    }
+    __syncthreads();
+    for (int i = tid; i < p.n_boxes; i += kPrepThreads) {
+        const long long roi = img * p.n_boxes + i;
+        const int2 kr = kSmemCache ? s_kr[i] : p.scratch[roi];
+        p.order[img * p.n_boxes + s_hist[kr.x & 0xffff] + kr.y] = make_int2((int)roi, kr.x >> 16);
+    }
+    pdl_launch_dependents();
+}
+
+namespace ring {
+
+constexpr int kDescDepth = 2;
+constexpr int kMaxSamples = 16;          // per axis: one producer lane per sample
+constexpr int kMaxSlots = 16;
+
+struct Desc {                             // producer -> consumers, one per RoI in flight
+    int roi, pad0, pad1, pad2;
+    int4 y[kMaxSamples];                  // {top slot, bottom slot, bits(y lerp), flags}
+    int4 x[kMaxSamples];                  // {byte offset of the left tap inside a row slot, of the right tap, bits(x lerp), in range}
+};
+// y flags: bit0 in range, bit1 release top slot after this sample row, bit2 release bottom slot,
+//          bit3 / bit4 mbarrier phase parity of the top / bottom slot's current use
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16); completion = complete_tx on `bar`
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+}  // namespace ring
+
+struct RoiRingParams {
+    const float *boxes;
+    const int2 *order;
+    const float *fm[4];
+    int fm_h[4];
+    int fm_w[4];
+    int n_boxes;          // per image
+    int c4;               // channels / 4
+    int ph, pw;
+    void *out;
+    int total;
+    int slots;            // K row slots in the ring
+    unsigned slot_bytes;  // 2*pw pixels
+};
+
+template <bool kBf16>
+__global__ void __launch_bounds__(512) roi_align_ring_kernel(const RoiRingParams p) {
+    using namespace ring;
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+    const int K = p.slots;
+    unsigned char *slots = ring_smem;
+    Desc *desc = reinterpret_cast<Desc *>(ring_smem + (size_t)K * p.slot_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(desc + kDescDepth);
+    uint64_t *empty = full + K;
+    uint64_t *dfull = empty + K;
+    uint64_t *dempty = dfull + kDescDepth;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncons = (blockDim.x >> 5) - 1;
+    const uint32_t px_bytes = (uint32_t)p.c4 * 16u;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < K; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, ncons); }
+        for (int i = 0; i < kDescDepth; ++i) { mbar_init(dfull + i, 1); mbar_init(dempty + i, ncons); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();                                            // the order array comes from roi_order_kernel
+
+    if (warp == 0) {
+        // ------------------------------- producer -------------------------------
+        const bool is_y = lane < 16;
+        const int j = lane & 15;
+        const int n = is_y ? p.ph : p.pw;
+        unsigned head = 0;                                 // row positions issued so far (warp-uniform)
+        int it = 0;
+        int spos = blockIdx.x;
+        int2 ord = make_int2(0, 2);
+        float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (spos < p.total) {
+            ord = __ldg(p.order + spos);
+            box = __ldg(reinterpret_cast<const float4 *>(p.boxes) + ord.x);
+        }
+        for (; spos < p.total; spos += gridDim.x, ++it) {
+            const int2 cur = ord;
+            const float4 cbox = box;
+            if (spos + (long long)gridDim.x < p.total) {   // next RoI's box: in flight while this one is issued
+                ord = __ldg(p.order + spos + gridDim.x);
+                box = __ldg(reinterpret_cast<const float4 *>(p.boxes) + ord.x);
+            }
+            const int roi = cur.x;
+            int H, W;
+            const float *base;
+            switch (cur.y - 2) {
+                case 0: H = p.fm_h[0]; W = p.fm_w[0]; base = p.fm[0]; break;
+                case 1: H = p.fm_h[1]; W = p.fm_w[1]; base = p.fm[1]; break;
+                case 2: H = p.fm_h[2]; W = p.fm_w[2]; base = p.fm[2]; break;
+                default: H = p.fm_h[3]; W = p.fm_w[3]; base = p.fm[3]; break;
+            }
+            base += (long long)(roi / p.n_boxes) * H * W * p.c4 * 4;
+            // tf.image.crop_and_resize sample coordinate of this lane (one sample per bin, end points inclusive)
+            const float a1 = is_y ? cbox.x : cbox.y, a2 = is_y ? cbox.z : cbox.w;
+            const float Dm1 = (float)((is_y ? H : W) - 1);
+            float in;
+            if (n > 1) {
+                const float sc = __fdiv_rn(__fmul_rn(__fsub_rn(a2, a1), Dm1), (float)(n - 1));
+                in = __fadd_rn(__fmul_rn(a1, Dm1), __fmul_rn((float)j, sc));
+            } else {
+                in = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(a1, a2)), Dm1);
+            }
+            const bool ok = (j < n) && (in >= 0.0f) && (in <= Dm1);
+            const float fl = floorf(in);
+            const int lo = ok ? (int)fl : 0, hi = ok ? (int)ceilf(in) : 0;
+            const float frac = __fsub_rn(in, fl);
+
+            // distinct rows (y half) / pixels (x half), in sample order; a tap already loaded for the previous
+            // sample is re-used.  All lanes of a half walk the same broadcast values -> uniform results.
+            int posLo = 0, posHi = 0, cnt = 0;
+            bool newLo = false, newHi = false, runStart = false;
+            {
+                int pLo = 0, pHi = 0, pPosLo = 0, pPosHi = 0, lastNew = INT_MIN;
+                bool pOk = false;
+                const int ns = p.ph > p.pw ? p.ph : p.pw;
+                for (int s = 0; s < ns; ++s) {
+                    const int sLo = __shfl_sync(0xffffffffu, lo, s, 16), sHi = __shfl_sync(0xffffffffu, hi, s, 16);
+                    const bool sOk = __shfl_sync(0xffffffffu, (int)ok, s, 16) != 0;
+                    int qLo = 0, qHi = 0;
+                    bool nLo = false, nHi = false, rs = false;
+                    if (sOk) {
+                        if (pOk && sLo == pLo) qLo = pPosLo;
+                        else if (pOk && sLo == pHi) qLo = pPosHi;
+                        else { qLo = cnt++; nLo = true; rs = (sLo != lastNew + 1) || lastNew == INT_MIN; lastNew = sLo; }
+                        if (sHi == sLo) qHi = qLo;
+                        else if (pOk && sHi == pLo) qHi = pPosLo;
+                        else if (pOk && sHi == pHi) qHi = pPosHi;
+                        else {
+                            qHi = cnt++; nHi = true;
+                            if (!nLo) rs = (sHi != lastNew + 1) || lastNew == INT_MIN;
+                            lastNew = sHi;
+                        }
+                    }
+                    pOk = sOk; pLo = sLo; pHi = sHi; pPosLo = qLo; pPosHi = qHi;
+                    if (j == s) { posLo = qLo; posHi = qHi; newLo = nLo; newHi = nHi; runStart = rs && (nLo || nHi); }
+                }
+            }
+            const int ny = __shfl_sync(0xffffffffu, cnt, 0), nq = __shfl_sync(0xffffffffu, cnt, 16);
+            // a row / pixel position dies after the last sample that reads it: the next sample either re-uses it or
+            // nobody does (re-use only ever looks one sample back)
+            const int nxOk = __shfl_down_sync(0xffffffffu, (int)ok, 1, 16);
+            const int nxLo = __shfl_down_sync(0xffffffffu, posLo, 1, 16), nxHi = __shfl_down_sync(0xffffffffu, posHi, 1, 16);
+            const bool next_ok = (j < 15) && nxOk;
+            const bool relLo = ok && !(next_ok && (posLo == nxLo || posLo == nxHi));
+            const bool relHi = ok && posHi != posLo && !(next_ok && (posHi == nxLo || posHi == nxHi));
+            // pixel runs (x half): one bulk copy per run and row
+            const int runQ = newLo ? posLo : posHi, runPx = newLo ? lo : hi;
+            const unsigned start_mask = __reduce_or_sync(0xffffffffu, (!is_y && runStart) ? (1u << runQ) : 0u);
+            const unsigned above = (runQ + 1 < 32) ? (start_mask >> (runQ + 1)) : 0u;
+            const int runLen = above ? __ffs(above) : nq - runQ;
+
+            // publish the descriptor
+            const int di = it % kDescDepth;
+            mbar_wait(dempty + di, (((unsigned)it / kDescDepth) & 1u) ^ 1u);
+            Desc *d = desc + di;
+            {
+                const unsigned PLo = head + (unsigned)posLo, PHi = head + (unsigned)posHi;
+                if (is_y) {
+                    if (j < p.ph)
+                        d->y[j] = make_int4((int)(PLo % K), (int)(PHi % K), __float_as_int(frac),
+                                            (ok ? 1 : 0) | (relLo ? 2 : 0) | (relHi ? 4 : 0) | ((int)((PLo / K) & 1u) << 3) |
+                                                ((int)((PHi / K) & 1u) << 4));
+                } else if (j < p.pw) {
+                    d->x[j] = make_int4(posLo * (int)px_bytes, posHi * (int)px_bytes, __float_as_int(frac), ok ? 1 : 0);
+                }
+                if (lane == 0) d->roi = roi;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dfull + di);
+
+            // issue the rows in position order
+            const int yflags = (newLo ? 1 : 0) | (newHi ? 2 : 0);
+            for (int s = 0; s < p.ph; ++s) {
+                const int f = __shfl_sync(0xffffffffu, yflags, s);
+                if (!f) continue;
+                const int rLo = __shfl_sync(0xffffffffu, lo, s), rHi = __shfl_sync(0xffffffffu, hi, s);
+                const int qLo = __shfl_sync(0xffffffffu, posLo, s), qHi = __shfl_sync(0xffffffffu, posHi, s);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (!(f & (1 << e))) continue;
+                    const int row = e ? rHi : rLo;
+                    const unsigned P = head + (unsigned)(e ? qHi : qLo);
+                    const int slot = (int)(P % K);
+                    mbar_wait(empty + slot, ((P / K) & 1u) ^ 1u);
+                    if (lane == 0) mbar_expect_tx(full + slot, (uint32_t)nq * px_bytes);
+                    __syncwarp();
+                    if (!is_y && runStart)
+                        bulk_load(slots + (size_t)slot * p.slot_bytes + (size_t)runQ * px_bytes,
+                                  base + ((long long)row * W + runPx) * p.c4 * 4, (uint32_t)runLen * px_bytes, full + slot);
+                }
+            }
+            head += (unsigned)ny;
+        }
+    } else {
+        // ------------------------------- consumers -------------------------------
+        const int cw = warp - 1;
+        const int bins = p.ph * p.pw;
+        int it = 0;
+        for (int spos = blockIdx.x; spos < p.total; spos += gridDim.x, ++it) {
+            const int di = it % kDescDepth;
+            mbar_wait(dfull + di, ((unsigned)it / kDescDepth) & 1u);
+            const Desc *d = desc + di;
+            const long long out_roi = (long long)d->roi * bins * p.c4;
+            for (int by = 0; by < p.ph; ++by) {
+                const int4 ye = d->y[by];
+                const bool yok = (ye.w & 1) != 0;
+                if (yok) {
+                    mbar_wait(full + ye.x, (unsigned)(ye.w >> 3) & 1u);
+                    mbar_wait(full + ye.y, (unsigned)(ye.w >> 4) & 1u);
+                }
+                const unsigned char *top = slots + (size_t)ye.x * p.slot_bytes;
+                const unsigned char *bot = slots + (size_t)ye.y * p.slot_bytes;
+                const float ly = __int_as_float(ye.z);
+                for (int bx = cw; bx < p.pw; bx += ncons) {
+                    const int4 xe = d->x[bx];
+                    const bool ok = yok && xe.w;
+                    const float lx = __int_as_float(xe.z);
+                    const long long o = out_roi + ((long long)by * p.pw + bx) * p.c4;
+                    for (int c0 = 0; c0 < p.c4; c0 += 64) {
+                        const int ca = c0 + lane, cb = c0 + 32 + lane;
+                        const bool acta = ca < p.c4, actb = cb < p.c4;
+                        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+                        if (ok) {
+                            float4 tl, tr, bl, br, tl2, tr2, bl2, br2;
+                            if (acta) {
+                                tl = *reinterpret_cast<const float4 *>(top + xe.x + ca * 16);
+                                tr = *reinterpret_cast<const float4 *>(top + xe.y + ca * 16);
+                                bl = *reinterpret_cast<const float4 *>(bot + xe.x + ca * 16);
+                                br = *reinterpret_cast<const float4 *>(bot + xe.y + ca * 16);
+                            }
+                            if (actb) {
+                                tl2 = *reinterpret_cast<const float4 *>(top + xe.x + cb * 16);
+                                tr2 = *reinterpret_cast<const float4 *>(top + xe.y + cb * 16);
+                                bl2 = *reinterpret_cast<const float4 *>(bot + xe.x + cb * 16);
+                                br2 = *reinterpret_cast<const float4 *>(bot + xe.y + cb * 16);
+                            }
+                            if (acta) va = bilerp4(tl, tr, bl, br, lx, ly);
+                            if (actb) vb = bilerp4(tl2, tr2, bl2, br2, lx, ly);
+                        }
+                        if (acta) store_out<kBf16>(p.out, o + ca, va);
+                        if (actb) store_out<kBf16>(p.out, o + cb, vb);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0 && yok) {
+                    if (ye.w & 2) mbar_arrive(empty + ye.x);
+                    if (ye.w & 4) mbar_arrive(empty + ye.y);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dempty + di);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Backward: gradient w.r.t. the feature maps, the mirror image of the gather.
 // TF's CropAndResizeGradImage per in-range sample: dtop = (1-ly)*g, dbottom = ly*g,
 // d[top,left] += (1-lx)*dtop, d[top,right] += lx*dtop, likewise for the bottom row; boxes get no gradient
@@ -366,6 +730,8 @@ static int validate(const float *boxes, const float *const fmaps[4], const int f
         DC_REQUIRE(((uintptr_t)fmaps[l] & 15) == 0, "feature map %d not 16-byte aligned", l);
         DC_REQUIRE(fm_h[l] >= 1 && fm_w[l] >= 1, "feature map %d has empty shape", l);
         DC_REQUIRE((long long)fm_h[l] * fm_w[l] < (1ll << 30), "feature map %d too large", l);
+        DC_REQUIRE((long long)fm_h[l] * fm_w[l] * (channels / 4) < (1ll << 31),
+                   "feature map %d: H*W*C/4 must fit in int32 (record offsets)", l);
     }
     return DC_OK;
 }
@@ -388,6 +754,77 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
     DC_REQUIRE(total < (1ll << 31), "n_images*n_boxes must fit in int32");
     const int rec_len = 1 + pool_h + pool_w;
 
+    // ---- ring path (round 2): order kernel + shared-memory ring kernel ----
+    static const int path = getenv("DCAP_ROI_PATH") ? atoi(getenv("DCAP_ROI_PATH")) : 1;
+    const unsigned px_bytes = (unsigned)channels * 4u;
+    const unsigned slot_bytes = 2u * (unsigned)pool_w * px_bytes;
+    const size_t ring_fixed = ring::kDescDepth * sizeof(ring::Desc) + (2 * ring::kMaxSlots + 2 * ring::kDescDepth) * sizeof(uint64_t) + 128;
+    if (path == 1 && pool_h <= ring::kMaxSamples && pool_w <= ring::kMaxSamples && 4 * (size_t)slot_bytes + ring_fixed <= 227 * 1024) {
+        static const int env_ctas = getenv("DCAP_ROI_CTAS") ? atoi(getenv("DCAP_ROI_CTAS")) : 2;
+        static const int env_slots = getenv("DCAP_ROI_RING") ? atoi(getenv("DCAP_ROI_RING")) : 0;
+        static const int env_warps = getenv("DCAP_ROI_WARPS") ? atoi(getenv("DCAP_ROI_WARPS")) : 0;
+        int ctas = env_ctas < 1 ? 1 : env_ctas;
+        // K row slots: what fits next to `ctas` resident CTAs per SM (227 KB usable, 1 KB reserved per CTA)
+        int slots = 0;
+        for (; ctas >= 1; --ctas) {
+            const size_t per_cta = (size_t)(227 * 1024) / ctas - 1024;
+            slots = per_cta > ring_fixed ? (int)((per_cta - ring_fixed) / slot_bytes) : 0;
+            if (slots >= 4) break;
+        }
+        if (ctas < 1) ctas = 1;
+        if (env_slots >= 4 && env_slots <= slots) slots = env_slots;
+        if (slots > ring::kMaxSlots) slots = ring::kMaxSlots;
+        int ncons = env_warps > 0 ? env_warps : (pool_w < 8 ? pool_w : 8);
+        if (ncons > 15) ncons = 15;
+        const size_t smem = (size_t)slots * slot_bytes + ring_fixed;
+
+        const size_t ord_bytes = sizeof(int2) * (size_t)total;
+        char *ws = nullptr;
+        DC_CHECK_CUDA(cudaMallocAsync((void **)&ws, 2 * ord_bytes, stream));
+        RoiOrderParams op;
+        op.boxes = boxes; op.n_boxes = n_boxes; op.denom = level_denominator(img_h, img_w);
+        op.order = reinterpret_cast<int2 *>(ws);
+        op.scratch = reinterpret_cast<int2 *>(ws + ord_bytes);
+        op.levels = levels;
+        const size_t ord_smem = (size_t)n_boxes * sizeof(int2);
+        cudaError_t e;
+        if (ord_smem <= 160 * 1024) {
+            static std::atomic<unsigned long long> attr_set{0};
+            e = once_per_device(attr_set, [] {
+                return cudaFuncSetAttribute(roi_order_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+            });
+            if (e == cudaSuccess) {
+                roi_order_kernel<true><<<n_images, kPrepThreads, ord_smem, stream>>>(op);
+                e = cudaGetLastError();
+            }
+        } else {
+            roi_order_kernel<false><<<n_images, kPrepThreads, 0, stream>>>(op);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) {
+            static std::atomic<unsigned long long> attr_set2{0};
+            e = once_per_device(attr_set2, [] {
+                return cudaFuncSetAttribute(roi_align_ring_kernel<kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            });
+        }
+        if (e == cudaSuccess) {
+            PdlScope pdl;                 // the ring kernel's barrier set-up overlaps the order kernel
+            RoiRingParams rp;
+            rp.boxes = boxes; rp.order = op.order;
+            for (int l = 0; l < 4; ++l) { rp.fm[l] = fmaps[l]; rp.fm_h[l] = fm_h[l]; rp.fm_w[l] = fm_w[l]; }
+            rp.n_boxes = n_boxes; rp.c4 = channels / 4; rp.ph = pool_h; rp.pw = pool_w;
+            rp.out = out; rp.total = (int)total; rp.slots = slots; rp.slot_bytes = slot_bytes;
+            const long long mg = (long long)sm_count() * ctas;
+            e = launch_pdl(roi_align_ring_kernel<kBf16>, dim3((unsigned)(total < mg ? total : mg)), dim3((ncons + 1) * 32), smem,
+                           stream, rp);
+            if (e == cudaSuccess) e = cudaGetLastError();
+        }
+        cudaFreeAsync(ws, stream);
+        if (e != cudaSuccess) return set_error(DC_ERR_CUDA, "roi align launch failed: %s", cudaGetErrorString(e));
+        return DC_OK;
+    }
+
+    // ---- register-gather path (round 1; also the fallback for pools > 16 or very wide pixels) ----
     // stream-ordered workspace: sorted records + scratch (cached by the default pool)
     const size_t rec_bytes = sizeof(int4) * (size_t)total * rec_len;
     const size_t scr_bytes = sizeof(int4) * (size_t)total;

@@ -106,7 +106,7 @@ STATE_GAIN = 5.0          # rows of the dense / image-LSTM kernel fed by the rec
 LAYER2_GAIN = 4.0         # input kernel of the second LSTM of the v1 stack
 FEATURE_GAIN = 0.5        # rows of the v1 dense kernel fed by the image feature
 LOGIT_TAIL = 3.0          # vocabulary projection ~ sign(g) |g|^LOGIT_TAIL, g ~ N(0,1)
-LOGIT_SCALE = 4.0         # its column norm, in units of 1/sqrt(fan_in/2)
+LOGIT_SCALE = 3.0         # its column norm, in units of 1/sqrt(fan_in/2)
 SPECIAL_BIAS = -30.0      # <pad>, <start>
 COUNTER_STEP = 0.06       # tanh(candidate) of a counter unit
 V2_STATE_GAIN = 2.0       # v2: rows of the image-LSTM kernel fed by the word vector

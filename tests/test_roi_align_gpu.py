@@ -60,9 +60,12 @@ def test_layer_surface_matches_reference_contract(golden_dir):
 
 @pytest.mark.parametrize("seed,B,N,C,pool", [(1001, 1, 100, 256, (7, 7)), (5, 2, 333, 256, (7, 7)),
                                              (6, 1, 64, 256, (14, 14)), (7, 3, 50, 32, (3, 5)),
-                                             (8, 1, 10, 4, (1, 1))])
+                                             (8, 1, 10, 4, (1, 1)), (9, 2, 40, 36, (2, 16)), (10, 1, 30, 256, (17, 4)),
+                                             (11, 2, 70, 132, (16, 16)), (12, 1, 2500, 64, (7, 7))])
 def test_synthetic_vs_c_oracle(seed, B, N, C, pool):
-    """cfg1-shaped case (seed 1001: 1 image, 100 RoIs, 256 ch) and ragged variants."""
+    """cfg1-shaped case (seed 1001: 1 image, 100 RoIs, 256 ch) and ragged variants: pools up to 16x16 and any
+    channel count take the shared-memory ring kernel (C = 132: a partial second 128-channel part), pool 17x4 the
+    register-gather fallback; 2500 RoIs per image make every persistent CTA wrap its ring many times."""
     rng = np.random.default_rng(seed)
     size = 1024 if C == 256 else 256
     boxes = synth.synth_boxes(rng, B, N, 1024.0, pad_frac=0.05, straddle_frac=0.05)
