@@ -33,6 +33,13 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU reference arm (rank 0 only) must use the host's cores,
+# so the thread count is set explicitly BEFORE numpy / OpenBLAS / libgomp are loaded and recorded in the line.
+if "reference" in sys.argv[1:]:
+    _n = str(os.cpu_count() or 1)
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = _n
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -147,23 +154,66 @@ def dist_env():
             int(os.environ.get("WORLD_SIZE", 1)))
 
 
+class Ctx(object):
+    """One process per GPU: rank / device / NCCL group shared by every workload of a run."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.rank, self.local_rank, self.world = dist_env()
+        if args.gpus != self.world and self.world > 1:
+            raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, self.world))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.dist = dist
+        self.torch = torch
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def tensor_roofline(achieved_tf, timed_seconds, **extra):
+    """Fraction of the MEASURED bf16 peak.  A timed region shorter than ~2 s runs at boost clocks, so the burst
+    figure is the denominator; long regions settle at the power cap and are held against the sustained figure.
+    Both fractions are always reported."""
+    burst, src = measured_peaks("bf16_tflops")
+    sustained, _ = measured_peaks("bf16_tflops_sustained")
+    use_burst = timed_seconds < 2.0
+    peak = burst if use_burst else sustained
+    r = {"bound": "tensor", "achieved": round(achieved_tf, 1), "peak": peak,
+         "peak_source": src + (" burst (timed region %.2f s)" % timed_seconds if use_burst else
+                               " sustained (timed region %.1f s)" % timed_seconds),
+         "unit": "TFLOP/s", "frac": round(achieved_tf / peak, 4), "frac_of_burst": round(achieved_tf / burst, 4),
+         "frac_of_sustained": round(achieved_tf / sustained, 4), "traffic": None}
+    r.update(extra)
+    return r
+
+
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
 
-def run_ours_roi_features(args):
+def run_ours_roi_features(args, ctx):
     import torch
     import torch.distributed as dist
     import image_captioning_b200 as pkg
     from image_captioning_b200 import synth
 
-    rank, local_rank, world = dist_env()
-    if args.gpus != world and world > 1:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local_rank, world, dev = ctx.rank, ctx.local_rank, ctx.world, ctx.dev
     lib = pkg._lib.load()
     sms, cc = pkg._lib.device_info()
 
@@ -219,7 +269,7 @@ def run_ours_roi_features(args):
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
-    roofline = {"bound": "hbm", "kernel": "roi_align_kernel", "achieved": round(achieved, 1),
+    roofline = {"bound": "hbm", "kernel": "roi_order_kernel + roi_align_ring_kernel (fp32 output)", "achieved": round(achieved, 1),
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
                 "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
@@ -233,10 +283,8 @@ def run_ours_roi_features(args):
             pass
 
     if args.no_e2e:
-        if rank == 0:
-            print(json.dumps({"ms_per_step": round(ms_per_step, 5), "roofline_frac": roofline["frac"],
-                              "variant": os.environ.get("DCAP_ROI_VARIANT"), "ctas": os.environ.get("DCAP_ROI_CTAS")}))
-        return
+        return {"ms_per_step": round(ms_per_step, 5), "roofline_frac": roofline["frac"],
+                "path": os.environ.get("DCAP_ROI_PATH"), "ctas": os.environ.get("DCAP_ROI_CTAS")}
     # ---- e2e: host buffers through the C-ABI host entry point ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h_boxes = torch.from_numpy(boxes_np).pin_memory()
@@ -284,10 +332,7 @@ def run_ours_roi_features(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(boxes_np, [f.cpu().numpy() for f in h_fms], budget_s=12.0)
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 # --------------------------------------------------------------------------------------------
@@ -318,6 +363,18 @@ def cpu_baseline(boxes_np, fms_np, budget_s):
             "kind": "port", "sample": "%d images x %d RoIs of the same cfg2 workload, literal "
             "reference form (4x crop_and_resize + re-sort), C/OpenMP restatement" % (done, N),
             "seconds": round(el, 2)}
+
+
+def _host_threads():
+    """Threads the CPU arm really has: OpenMP (C oracle) and BLAS (numpy) pools."""
+    from tests import _c_oracle
+    info = {"omp": _c_oracle.num_threads(), "cpu_count": os.cpu_count()}
+    try:
+        from threadpoolctl import threadpool_info
+        info["blas"] = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+    except Exception:
+        info["blas"] = None
+    return info
 
 
 def run_reference(args):
@@ -355,8 +412,10 @@ def run_reference(args):
                              "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 1), "unit": "RoI/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
+            "threads": _host_threads(),
             "note": "the reference is TF-1.x/Keras Python and cannot be installed here; this arm "
-                    "times the C restatement of its CPU algorithm (oracle/c) on all host threads"}
+                    "times the C restatement of its CPU algorithm (oracle/c) on all host threads (set explicitly: "
+                    "torchrun's OMP_NUM_THREADS=1 is overridden)"}
     print(json.dumps(line), flush=True)
 
 
@@ -364,24 +423,24 @@ def run_reference(args):
 # captions workload (default): ROIAlign -> head -> greedy decode
 # --------------------------------------------------------------------------------------------
 
+def _captions_workload(B=IMAGES_PER_GPU, N=ROIS_PER_IMAGE):
+    return ("captions: per GPU %d images x %d RoIs (cfg2 RoI stage, P2-P5 of 1024x1024, 256 ch "
+            "fp32) -> PyramidROIAlign -> RoI head -> v1 inject-LSTM greedy decode (hidden %d, "
+            "vocab %d, embedding %d, P=%d)" % (B, N, UNITS, VOCAB, EMBED, PADDING))
+
+
 def _decoder_weights():
     from image_captioning_b200 import synth
     return synth.synth_weights_v1(np.random.default_rng(SEED_DECODER), V=VOCAB, E=EMBED, U=UNITS, C=CHANNELS)
 
 
-def run_ours_captions(args):
+def run_ours_captions(args, ctx):
     import torch
     import torch.distributed as dist
     import image_captioning_b200 as pkg
     from image_captioning_b200 import synth
 
-    rank, local_rank, world = dist_env()
-    if args.gpus != world and world > 1:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local_rank, world, dev = ctx.rank, ctx.local_rank, ctx.world, ctx.dev
     sms, cc = pkg._lib.device_info()
 
     B, N = IMAGES_PER_GPU, ROIS_PER_IMAGE
@@ -438,20 +497,16 @@ def run_ours_captions(args):
 
     # rooflines: decoder GEMMs (tensor, dominant share of the step) and ROIAlign (HBM)
     flops = FLOP_PER_ROI_GREEDY * R
-    tf_peak, tf_src = measured_peaks("bf16_tflops_sustained")
-    tf_burst, _ = measured_peaks("bf16_tflops")
     achieved_tf = flops / (dec_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (head + 15 decode steps: %d launches per step)"
-                % (4 + 4 * PADDING), "achieved": round(achieved_tf, 1), "peak": tf_peak, "peak_source": tf_src,
-                "unit": "TFLOP/s", "frac": round(achieved_tf / tf_peak, 4),
-                "frac_of_burst_%.0f" % tf_burst: round(achieved_tf / tf_burst, 4),
-                "traffic": None, "algorithmic_flops_per_step": flops, "decoder_ms": round(dec_ms, 4),
-                "share_of_step": round(dec_ms / (roi_ms + dec_ms), 3)}
+    roofline = tensor_roofline(achieved_tf, total_ms * 1e-3,
+                               kernel="gemm_bf16_tc2_kernel (head + 15 decode steps: %d launches per step)" % (4 + 4 * PADDING),
+                               algorithmic_flops_per_step=flops, decoder_ms=round(dec_ms, 4),
+                               share_of_step=round(dec_ms / (roi_ms + dec_ms), 3))
     t_unique = tap_unique_pixels(boxes_np, levels.cpu().numpy(), [tuple(f.shape[1:3]) for f in fms], POOL)
     alg_bytes = 4 * CHANNELS * t_unique + 2 * CHANNELS * POOL[0] * POOL[1] * R        # fp32 taps in, bf16 rows out
     hbm_peak, hbm_src = measured_peaks("hbm_gbs")
     achieved_gb = alg_bytes / (roi_ms * 1e-3) / 1e9
-    roofline_hbm = {"bound": "hbm", "kernel": "roi_prepare_kernel + roi_align_stream_kernel (bf16 output)",
+    roofline_hbm = {"bound": "hbm", "kernel": "roi_order_kernel + roi_align_ring_kernel (bf16 output)",
                     "achieved": round(achieved_gb, 1), "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
                     "frac": round(achieved_gb / hbm_peak, 4), "frac_of_nominal_8000": round(achieved_gb / 8000.0, 4),
                     "traffic": None, "algorithmic_bytes_per_step": alg_bytes, "t_unique_pixels": t_unique,
@@ -471,9 +526,7 @@ def run_ours_captions(args):
         "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "captions: per GPU %d images x %d RoIs (cfg2 RoI stage, P2-P5 of 1024x1024, 256 ch "
-                               "fp32) -> PyramidROIAlign -> RoI head -> v1 inject-LSTM greedy decode (hidden %d, "
-                               "vocab %d, embedding %d, P=%d)" % (B, N, UNITS, VOCAB, EMBED, PADDING),
+        "config": {"workload": _captions_workload(B, N),
                    "rois_per_step": R * world, "sharding": "images per rank, no collective",
                    "precision": "ROIAlign fp32 arithmetic with bf16 output; decoder bf16 operands, fp32 accumulate/state",
                    "l2": "inputs larger than L2 (pyramid %d MB per GPU; decoder weights + activations %d MB)"
@@ -510,10 +563,7 @@ def run_ours_captions(args):
                               "image-by-image upload overlapped with ROIAlign + decode)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_captions(boxes_np[:1], [f[:1].cpu().numpy() for f in fms], w, 12.0)
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def _cpu_caption_pass(boxes_np, fms_np, w, out, scratch):
@@ -574,13 +624,15 @@ def run_reference_captions(args):
             "unit": "RoI captions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(el / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "captions (bounded sample: 1 image x %d RoIs per step)" % n_rois},
+            "config": {"workload": _captions_workload(), "sample_per_step": "1 image x %d RoIs" % n_rois},
             "cpu_baseline": {"value": round(value, 1), "unit": "RoI captions/s", "cores": _c_oracle.num_threads(),
                              "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 1), "unit": "RoI captions/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
+            "threads": _host_threads(),
             "note": "the reference is TF-1.x/Keras Python and cannot be installed here (no TensorFlow); this arm "
-                    "times the CPU restatement of its algorithm (oracle/) on all host threads"}
+                    "times the CPU restatement of its algorithm (oracle/) on all host threads (set explicitly: "
+                    "torchrun's OMP_NUM_THREADS=1 is overridden)"}
     print(json.dumps(line), flush=True)
 
 
@@ -592,19 +644,13 @@ TRAIN_BATCH, TRAIN_P = 4096, 16
 FLOP_PER_ROI_FWD_TRAIN = 27787264 + 4194304 + 2097152 + TRAIN_P * (1228800 + 2097152 + 4194304 + 1048576 + 20480000)
 
 
-def run_ours_train(args):
+def run_ours_train(args, ctx):
     import torch
     import torch.distributed as dist
     import image_captioning_b200 as pkg
     from image_captioning_b200 import synth, parallel
 
-    rank, local_rank, world = dist_env()
-    if args.gpus != world and world > 1:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local_rank, world, dev = ctx.rank, ctx.local_rank, ctx.world, ctx.dev
     sms, cc = pkg._lib.device_info()
     lo, hi = parallel.shard_bounds(TRAIN_BATCH, rank, world)         # global batch split evenly: strong scaling
     Bl = hi - lo
@@ -650,7 +696,6 @@ def run_ours_train(args):
     ms_per_step = float(t.item()) / K
     value = TRAIN_BATCH / (ms_per_step * 1e-3)
     flops = 3.0 * FLOP_PER_ROI_FWD_TRAIN * Bl
-    tf_peak, tf_src = measured_peaks("bf16_tflops_sustained")
     achieved = flops / (ms_per_step * 1e-3) / 1e12
     loss_hist = [float(l.item()) for l in losses]
     line = {
@@ -666,11 +711,11 @@ def run_ours_train(args):
                    "l2": "activations larger than L2 (logits %d MB per rank)" % (Bl * TRAIN_P * VOCAB * 4 // 2 ** 20),
                    "sm_count": sms, "cc": cc, "loss_first": round(loss_hist[0], 4), "loss_last": round(loss_hist[-1], 4)},
         "clocks": clocks, "gpu_launches": K * 144,      # profiles/r1_launches_train.txt
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (forward scan + time-batched dense/vocab GEMMs + "
-                     "dgrad/wgrad GEMMs)", "achieved": round(achieved, 1), "peak": tf_peak, "peak_source": tf_src,
-                     "unit": "TFLOP/s", "frac": round(achieved / tf_peak, 4), "traffic": None,
-                     "algorithmic_flops_per_step_per_rank": flops,
-                     "note": "whole step time (GEMMs + softmax/xent + cell backward + optimiser + all-reduce) against 3x forward FLOPs"},
+        "roofline": tensor_roofline(achieved, total_ms * 1e-3,
+                                    kernel="gemm_bf16_tc2_kernel (forward scan + time-batched dense/vocab GEMMs + dgrad/wgrad GEMMs)",
+                                    algorithmic_flops_per_step_per_rank=flops,
+                                    note="whole step time (GEMMs + softmax/xent + cell backward + optimiser + all-reduce) "
+                                         "against 3x forward FLOPs"),
     }
     if not args.no_e2e:
         e2e_steps = max(1, min(K, args.e2e_steps))
@@ -696,10 +741,7 @@ def run_ours_train(args):
                        "h2d_bytes_per_step": int(h_feats.numel() * 4 + h_gt.numel() * 4), "d2h_bytes_per_step": 4,
                        "steps": e2e_steps, "api": "RoiCaptionModel.train_step_device + DataParallelTrainer (pinned host "
                        "features + captions in, scalar loss out)"}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 # --------------------------------------------------------------------------------------------
@@ -711,19 +753,13 @@ BEAM_ROIS, BEAM_K, BEAM_CHUNK = 100000, 3, int(os.environ.get("DCAP_BEAM_CHUNK",
 FLOP_PER_ROI_BEAM = 4194304 + 2097152 + (1 + (PADDING - 2) * BEAM_K) * (1228800 + 2097152 + 4194304 + 1048576 + 20480000)
 
 
-def run_ours_beam(args):
+def run_ours_beam(args, ctx):
     import torch
     import torch.distributed as dist
     import image_captioning_b200 as pkg
     from image_captioning_b200 import parallel
 
-    rank, local_rank, world = dist_env()
-    if args.gpus != world and world > 1:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local_rank, world, dev = ctx.rank, ctx.local_rank, ctx.world, ctx.dev
     sms, cc = pkg._lib.device_info()
     lo, hi = parallel.shard_bounds(BEAM_ROIS, rank, world)
     n = hi - lo
@@ -760,7 +796,6 @@ def run_ours_beam(args):
     ms_per_step = float(t.item()) / K
     value = BEAM_ROIS / (ms_per_step * 1e-3)
     flops = FLOP_PER_ROI_BEAM * n
-    tf_peak, tf_src = measured_peaks("bf16_tflops_sustained")
     achieved = flops / (ms_per_step * 1e-3) / 1e12
     chunks = (n + BEAM_CHUNK - 1) // BEAM_CHUNK
     line = {
@@ -775,10 +810,9 @@ def run_ours_beam(args):
                          % (n * 4096 // 2 ** 20, BEAM_CHUNK * BEAM_K * (832 + 1024) * 4 // 2 ** 20),
                    "sm_count": sms, "cc": cc},
         "clocks": clocks, "gpu_launches": K * chunks * (8 + 8 * (PADDING - 1)),
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tc_kernel (gate GEMMs + fused cell, dense1, vocabulary GEMM + "
-                     "fused top-k epilogue)", "achieved": round(achieved, 1), "peak": tf_peak, "peak_source": tf_src,
-                     "unit": "TFLOP/s", "frac": round(achieved / tf_peak, 4), "traffic": None,
-                     "algorithmic_flops_per_step_per_rank": flops},
+        "roofline": tensor_roofline(achieved, total_ms * 1e-3,
+                                    kernel="gemm_bf16_tc2_kernel (gate GEMMs + fused cell, dense1, vocabulary GEMM + fused top-k epilogue)",
+                                    algorithmic_flops_per_step_per_rank=flops),
     }
     if not args.no_e2e:
         h_feats = feats.cpu().pin_memory()
@@ -796,10 +830,7 @@ def run_ours_beam(args):
                        "h2d_bytes_per_step": int(h_feats.numel() * 4),
                        "d2h_bytes_per_step": int(h_tok.numel() * 4 + h_sc.numel() * 8), "steps": 1,
                        "api": "RoiCaptionModel.beam_search (host features in, [N,k,P] ids + [N,k] scores out)"}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 # --------------------------------------------------------------------------------------------
@@ -841,18 +872,12 @@ def _rpn_like(gen, n_images, anchors, dev, n_objects=40):
     return probs.contiguous(), bbox.contiguous()
 
 
-def run_ours_proposals(args):
+def run_ours_proposals(args, ctx):
     import torch
     import torch.distributed as dist
     import image_captioning_b200 as pkg
 
-    rank, local_rank, world = dist_env()
-    if args.gpus != world and world > 1:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, local_rank, world, dev = ctx.rank, ctx.local_rank, ctx.world, ctx.dev
     sms, cc = pkg._lib.device_info()
     cfg = pkg.ProposalConfig()
     anchors = cfg.anchors()
@@ -940,10 +965,7 @@ def run_ours_proposals(args):
         line["cpu_baseline"] = {"value": round(n / dt, 2), "unit": "images/s", "cores": 1, "kind": "port",
                                 "sample": "%d images of the same workload through oracle/proposals.py (numpy)" % n,
                                 "bit_exact_vs_gpu": bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def run_reference_proposals(args):
@@ -978,29 +1000,146 @@ def run_reference_proposals(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------------------------
+# dense-captioning workload shaped like BASELINE.json configs[4]: 5000 images x 300 RoIs, images dealt
+# round-robin over the ranks, FPN pyramids already on the device (the backbone's output), boxes in / ids out
+# --------------------------------------------------------------------------------------------
+VG_IMAGES, VG_ROIS, VG_BATCH, VG_POOL = 5000, 300, 8, 16
+
+
+def run_ours_captions_vg(args, ctx):
+    import torch
+    import image_captioning_b200 as pkg
+    from image_captioning_b200 import synth
+
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    my_images = list(range(rank, VG_IMAGES, world))                      # round-robin image sharding
+    n_batches = (len(my_images) + VG_BATCH - 1) // VG_BATCH
+    rng = np.random.default_rng(1004 + 7919 * rank)
+    boxes_np = synth.synth_boxes(rng, n_batches * VG_BATCH, VG_ROIS, float(IMAGE_SHAPE[0]))
+    gen = torch.Generator(device=dev).manual_seed(1004 + rank)
+    # a pool of VG_POOL distinct pyramids stands in for the backbone's per-image output (generating 5000 pyramids
+    # = 445 GB would time torch.randn, not the path); every batch reads 8 of them with its own boxes
+    pool = [torch.randn((VG_POOL, IMAGE_SHAPE[0] >> l, IMAGE_SHAPE[1] >> l, CHANNELS), device=dev, generator=gen)
+            for l in range(2, 6)]
+    w = _decoder_weights()
+    cfg = pkg.DenseCapConfig(VOCAB, w["imgcap_embedding_layer/embeddings"], 1, PADDING)
+    model = pkg.build_lstm_model([POOL[0], POOL[1], CHANNELS], cfg, UNITS, "inference", dtype="bfloat16", device=dev)
+    model.set_weights(w)
+    h_boxes = torch.from_numpy(boxes_np).pin_memory()
+    d_boxes = torch.empty((n_batches * VG_BATCH, VG_ROIS, 4), device=dev)
+    h_tok = torch.empty((n_batches * VG_BATCH * VG_ROIS, PADDING), dtype=torch.int32).pin_memory()
+    views = [[f[(i * VG_BATCH) % VG_POOL:(i * VG_BATCH) % VG_POOL + VG_BATCH] for f in pool] for i in range(VG_POOL // VG_BATCH)]
+
+    def job(host_io):
+        """boxes (pinned host) -> device, per 8-image batch ROIAlign + head + greedy decode, ids -> pinned host"""
+        if host_io:
+            d_boxes.copy_(h_boxes, non_blocking=True)
+        for i in range(n_batches):
+            n_img = min(VG_BATCH, len(my_images) - i * VG_BATCH)
+            fm = [f[:n_img] for f in views[i % len(views)]]
+            tok = model.caption_rois(d_boxes[i * VG_BATCH:i * VG_BATCH + n_img], fm, IMAGE_SHAPE)
+            if host_io:
+                h_tok[i * VG_BATCH * VG_ROIS:(i * VG_BATCH + n_img) * VG_ROIS].copy_(tok, non_blocking=True)
+
+    d_boxes.copy_(h_boxes)
+    for _ in range(max(1, min(args.warmup, 2))):
+        job(False)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    K = max(1, min(args.steps, 3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.barrier()
+    e0.record()
+    for _ in range(K):
+        job(False)
+    e1.record()
+    ctx.barrier()
+    total_ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.summary()
+    ms_per_step = total_ms / K
+    total_rois = VG_IMAGES * VG_ROIS
+    flops = FLOP_PER_ROI_GREEDY * len(my_images) * VG_ROIS
+    achieved = flops / (ms_per_step * 1e-3) / 1e12
+    ctx.barrier()
+    t0 = time.perf_counter()
+    job(True)
+    ctx.barrier()
+    e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
+    return {
+        "metric": "roi_captions_per_sec", "value": round(total_rois / (ms_per_step * 1e-3), 1), "unit": "RoI captions/s",
+        "n_gpus": world, "steps": K, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": round(ms_per_step, 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "cfg5 dense captioning: %d images x %d RoIs dealt round-robin over the ranks, batches of %d "
+                               "images; FPN pyramids resident on the device (a pool of %d distinct synthetic pyramids stands "
+                               "in for the backbone output), PyramidROIAlign -> head -> v1 greedy P=%d"
+                               % (VG_IMAGES, VG_ROIS, VG_BATCH, VG_POOL, PADDING),
+                   "rois_per_step": total_rois, "images_per_rank": len(my_images), "sharding": "round-robin images, no collective",
+                   "l2": "inputs larger than L2 (pyramid pool %d MB)" % (sum(f.numel() for f in pool) * 4 // 2 ** 20)},
+        "clocks": clocks, "gpu_launches": K * n_batches * (2 + 7 + 5 * PADDING),
+        "roofline": tensor_roofline(achieved, total_ms * 1e-3, kernel="gemm_bf16_tc2_kernel (decoder GEMMs; whole job time incl. ROIAlign)",
+                                    algorithmic_flops_per_step_per_rank=flops),
+        "e2e": {"value": round(total_rois / e2e_s, 1), "unit": "RoI captions/s", "h2d_bytes_per_step": int(h_boxes.numel() * 4) * world,
+                "d2h_bytes_per_step": int(h_tok.numel() * 4) * world, "steps": 1,
+                "api": "RoiCaptionModel.caption_rois per 8-image batch (pinned host boxes in, token ids out to pinned host)"},
+    }
+
+
+SUB_KEYS = ("metric", "value", "unit", "ms_per_step", "steps", "scaling", "dtype", "config", "clocks", "roofline",
+            "roofline_hbm", "e2e", "gpu_launches")
+
+
+def sub_records(args, ctx):
+    """Bounded runs of the other BASELINE configs appended to the default line, so that the driver's N = 1/2/4/8
+    sweep also records cfg2 (fp32 ROIAlign), cfg3 (the path's only collective: the NCCL gradient all-reduce),
+    cfg4 (beam, rows split over ranks) and cfg5 (5000 x 300 end to end)."""
+    import copy
+    out = {}
+    plan = [("roi_features", run_ours_roi_features, dict(steps=20, warmup=3, e2e_steps=2)),
+            ("train", run_ours_train, dict(steps=6, warmup=3, e2e_steps=2)),
+            ("beam", run_ours_beam, dict(steps=1, warmup=1, e2e_steps=1)),
+            ("captions_vg", run_ours_captions_vg, dict(steps=2, warmup=1, e2e_steps=1))]
+    for name, fn, over in plan:
+        a = copy.copy(args)
+        for k, v in over.items():
+            setattr(a, k, v)
+        a.no_cpu_baseline = True
+        a.no_e2e = False
+        try:
+            line = fn(a, ctx)
+            out[name] = {k: line[k] for k in SUB_KEYS if k in line}
+        except Exception as e:                                      # a sub-record must never take the headline down
+            out[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        ctx.torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="captions", choices=["captions", "roi_features", "train", "beam", "proposals"])
+    ap.add_argument("--workload", default="captions",
+                    choices=["captions", "roi_features", "train", "beam", "proposals", "captions_vg"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer leg")
+    ap.add_argument("--no-sub", action="store_true", help="captions only: skip the bounded cfg2/cfg3/cfg4/cfg5 sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         {"roi_features": run_reference, "proposals": run_reference_proposals}.get(args.workload, run_reference_captions)(args)
-    elif args.workload == "captions":
-        run_ours_captions(args)
-    elif args.workload == "train":
-        run_ours_train(args)
-    elif args.workload == "beam":
-        run_ours_beam(args)
-    elif args.workload == "proposals":
-        run_ours_proposals(args)
-    else:
-        run_ours_roi_features(args)
+        return
+    ctx = Ctx(args)
+    fn = {"captions": run_ours_captions, "roi_features": run_ours_roi_features, "train": run_ours_train, "beam": run_ours_beam,
+          "proposals": run_ours_proposals, "captions_vg": run_ours_captions_vg}[args.workload]
+    line = fn(args, ctx)
+    if args.workload == "captions" and not args.no_sub and not args.no_e2e:
+        line["workloads"] = sub_records(args, ctx)
+    if ctx.rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
 
 
 if __name__ == "__main__":

@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(kPrepThreads) roi_order_kernel(const RoiOrderP
 
 namespace ring {
 
-constexpr int kDescDepth = 2;
+constexpr int kDescDepth = 4;
 constexpr int kMaxSamples = 16;          // per axis: one producer lane per sample
 constexpr int kMaxSlots = 16;
 
@@ -410,6 +410,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -444,12 +455,15 @@ struct RoiRingParams {
     int total;
     int slots;            // K row slots in the ring
     unsigned slot_bytes;  // 2*pw pixels
+    int diag;             // DCAP_ROI_DIAG (perf triage only, wrong results): 1 = no tap reads / math, 2 = no copies, 4 = no stores
 };
 
 template <bool kBf16>
-__global__ void __launch_bounds__(512) roi_align_ring_kernel(const RoiRingParams p) {
+__global__ void __launch_bounds__(512, 1) roi_align_ring_kernel(const RoiRingParams p) {
     using namespace ring;
     extern __shared__ __align__(128) unsigned char ring_smem[];
+    __shared__ int s_row[2 * kMaxSamples];                // producer scratch: map row of every row position of the RoI
+    __shared__ int4 s_run[2 * kMaxSamples];               // producer scratch: pixel runs {byte offset in slot, first pixel, bytes}
     const int K = p.slots;
     unsigned char *slots = ring_smem;
     Desc *desc = reinterpret_cast<Desc *>(ring_smem + (size_t)K * p.slot_bytes);
@@ -577,25 +591,41 @@ __global__ void __launch_bounds__(512) roi_align_ring_kernel(const RoiRingParams
             __syncwarp();
             if (lane == 0) mbar_arrive(dfull + di);
 
-            // issue the rows in position order
-            const int yflags = (newLo ? 1 : 0) | (newHi ? 2 : 0);
-            for (int s = 0; s < p.ph; ++s) {
-                const int f = __shfl_sync(0xffffffffu, yflags, s);
-                if (!f) continue;
-                const int rLo = __shfl_sync(0xffffffffu, lo, s), rHi = __shfl_sync(0xffffffffu, hi, s);
-                const int qLo = __shfl_sync(0xffffffffu, posLo, s), qHi = __shfl_sync(0xffffffffu, posHi, s);
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    if (!(f & (1 << e))) continue;
-                    const int row = e ? rHi : rLo;
-                    const unsigned P = head + (unsigned)(e ? qHi : qLo);
-                    const int slot = (int)(P % K);
-                    mbar_wait(empty + slot, ((P / K) & 1u) ^ 1u);
-                    if (lane == 0) mbar_expect_tx(full + slot, (uint32_t)nq * px_bytes);
-                    __syncwarp();
-                    if (!is_y && runStart)
-                        bulk_load(slots + (size_t)slot * p.slot_bytes + (size_t)runQ * px_bytes,
-                                  base + ((long long)row * W + runPx) * p.c4 * 4, (uint32_t)runLen * px_bytes, full + slot);
+            // issue the rows: lane r owns row position r.  Every lane polls its own slot's empty barrier (the slot's
+            // previous use was issued K positions ago, so at most one phase is outstanding per slot as long as a batch
+            // holds <= K rows), arms the full barrier and fires one bulk copy per pixel run -- no lane waits for another.
+            __syncwarp();                                  // previous RoI's table reads are done
+            if (is_y) {
+                if (newLo) s_row[posLo] = lo;
+                if (newHi) s_row[posHi] = hi;
+            } else if (runStart) {
+                const int ri = __popc(start_mask & ((1u << runQ) - 1u));
+                s_run[ri] = make_int4(runQ * (int)px_bytes, runPx, runLen * (int)px_bytes, 0);
+            }
+            __syncwarp();
+            const int nruns = __popc(start_mask);
+            for (int b0 = 0; b0 < ny; b0 += K) {
+                const int r = b0 + lane;
+                const bool mine = lane < K && r < ny;
+                const unsigned P = head + (unsigned)r;
+                const int slot = (int)(P % K);
+                const uint32_t par = ((P / K) & 1u) ^ 1u;
+                const float *src_row = mine ? base + (long long)s_row[r] * W * p.c4 * 4 : nullptr;
+                unsigned char *dst_row = slots + (size_t)slot * p.slot_bytes;
+                unsigned pending = __ballot_sync(0xffffffffu, mine);
+                bool todo = mine;
+                while (pending) {
+                    bool fired = false;
+                    if (todo && mbar_try_wait(empty + slot, par)) {
+                        mbar_expect_tx(full + slot, (p.diag & 2) ? 0u : (uint32_t)nq * px_bytes);
+                        for (int i = 0; i < ((p.diag & 2) ? 0 : nruns); ++i) {
+                            const int4 rn = s_run[i];
+                            bulk_load(dst_row + rn.x, src_row + (long long)rn.y * p.c4 * 4, (uint32_t)rn.z, full + slot);
+                        }
+                        fired = true;
+                        todo = false;
+                    }
+                    pending &= ~__ballot_sync(0xffffffffu, fired);
                 }
             }
             head += (unsigned)ny;
@@ -622,9 +652,10 @@ __global__ void __launch_bounds__(512) roi_align_ring_kernel(const RoiRingParams
                 const float ly = __int_as_float(ye.z);
                 for (int bx = cw; bx < p.pw; bx += ncons) {
                     const int4 xe = d->x[bx];
-                    const bool ok = yok && xe.w;
+                    const bool ok = yok && xe.w && !(p.diag & 1);
                     const float lx = __int_as_float(xe.z);
                     const long long o = out_roi + ((long long)by * p.pw + bx) * p.c4;
+                    if (p.diag & 4) continue;
                     for (int c0 = 0; c0 < p.c4; c0 += 64) {
                         const int ca = c0 + lane, cb = c0 + 32 + lane;
                         const bool acta = ca < p.c4, actb = cb < p.c4;
@@ -814,6 +845,8 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
             for (int l = 0; l < 4; ++l) { rp.fm[l] = fmaps[l]; rp.fm_h[l] = fm_h[l]; rp.fm_w[l] = fm_w[l]; }
             rp.n_boxes = n_boxes; rp.c4 = channels / 4; rp.ph = pool_h; rp.pw = pool_w;
             rp.out = out; rp.total = (int)total; rp.slots = slots; rp.slot_bytes = slot_bytes;
+            static const int env_diag = getenv("DCAP_ROI_DIAG") ? atoi(getenv("DCAP_ROI_DIAG")) : 0;
+            rp.diag = env_diag;
             const long long mg = (long long)sm_count() * ctas;
             e = launch_pdl(roi_align_ring_kernel<kBf16>, dim3((unsigned)(total < mg ? total : mg)), dim3((ncons + 1) * 32), smem,
                            stream, rp);

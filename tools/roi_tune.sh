@@ -4,14 +4,14 @@ out=${1:-gpurun_out/roi_tune.log}
 : > $out
 run() { echo "== $*" >> $out; env "$@" timeout 180 python bench.py --workload roi_features --steps 30 --warmup 5 --no-e2e >> $out 2>&1; }
 run DCAP_ROI_PATH=0
-for dt in f32; do
-for ctas in 1 2 3; do
-  for warps in 7 14; do
-    run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=$ctas DCAP_ROI_WARPS=$warps
-  done
+for ctas in 1 2 3 4; do
+  run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=$ctas
 done
-done
-run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=2 DCAP_ROI_RING=4
-run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=2 DCAP_ROI_RING=5
-run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=1 DCAP_ROI_RING=8
+run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=2 DCAP_ROI_DIAG=1
+run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=2 DCAP_ROI_DIAG=2
+run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=2 DCAP_ROI_DIAG=3
+run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=2 DCAP_ROI_DIAG=4
+run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=2 DCAP_ROI_DIAG=7
+run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=1 DCAP_ROI_DIAG=7
+run DCAP_ROI_PATH=1 DCAP_ROI_CTAS=1 DCAP_ROI_DIAG=5
 cat $out
