@@ -96,6 +96,10 @@ SIGNATURES = {
     "dc_decoder_greedy_host": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void]),
     "dc_decoder_train_step": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void,
                                              ctypes.c_float, c_void, c_void]),
+    "dc_decoder_train_step_ex": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void,
+                                                ctypes.c_float, c_void, c_void, c_void]),
+    "dc_decoder_v2_train_step": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, ctypes.c_int, c_void,
+                                                ctypes.c_float, c_void, c_void]),
     "dc_decoder_teacher_forced": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void]),
     "dc_adam_step": (ctypes.c_int, [c_void, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                     ctypes.c_int, ctypes.c_int64, ctypes.c_float, c_void]),

@@ -118,8 +118,11 @@ struct Decoder {
     // training step (train.cu; bf16 v1 decoder only)
     int train_forward(const void *feats, int kind, int B, const int32_t *gt, const int32_t *targets, cudaStream_t s);
     int teacher_forced_probs(const void *feats, int kind, int B, const int32_t *gt, float *probs, cudaStream_t s);
+    const DcTrainOptions *train_opts = nullptr;        // valid during train_step only
     int train_step(const void *feats, int kind, int B, const int32_t *gt, const int32_t *targets, float inv_count,
                    float *loss, cudaStream_t s);
+    int train_step_v2(const void *feats, int kind, int B, const int32_t *words, int L, const int32_t *targets, float inv_count,
+                      float *loss, cudaStream_t s);
     int adam_step(float lr, float beta1, float beta2, float eps, int amsgrad, long long t, float grad_scale,
                   cudaStream_t s);
     int ensure_grads();

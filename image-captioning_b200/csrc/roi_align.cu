@@ -434,6 +434,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
+// mode 0: every lane polls; mode 1: lane 0 polls, the warp re-converges behind it
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, int lane, int one_lane) {
+    if (one_lane) {
+        if (lane == 0) mbar_wait(bar, parity);
+        __syncwarp();
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
 // global -> shared bulk copy (16-byte aligned, size a multiple of 16); completion = complete_tx on `bar`
 __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -456,6 +465,8 @@ struct RoiRingParams {
     int slots;            // K row slots in the ring
     unsigned slot_bytes;  // 2*pw pixels
     int diag;             // DCAP_ROI_DIAG (perf triage only, wrong results): 1 = no tap reads / math, 2 = no copies, 4 = no stores
+    int sync_mode;        // DCAP_ROI_SYNC bit0: one lane polls the mbarriers, bit1: wait only for rows that are new at this sample
+    unsigned long long *prof;   // DCAP_ROI_PROF: 8 cycle counters (producer 0..3, consumer warp 4..7), or null
 };
 
 template <bool kBf16>
@@ -496,6 +507,9 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring_kernel(const RoiRingPar
             ord = __ldg(p.order + spos);
             box = __ldg(reinterpret_cast<const float4 *>(p.boxes) + ord.x);
         }
+        unsigned long long pc[4] = {0, 0, 0, 0};
+        long long tk = clock64();
+        auto tick = [&](int i) { if (p.prof) { const long long now = clock64(); pc[i] += (unsigned long long)(now - tk); tk = now; } };
         for (; spos < p.total; spos += gridDim.x, ++it) {
             const int2 cur = ord;
             const float4 cbox = box;
@@ -574,7 +588,9 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring_kernel(const RoiRingPar
 
             // publish the descriptor
             const int di = it % kDescDepth;
-            mbar_wait(dempty + di, (((unsigned)it / kDescDepth) & 1u) ^ 1u);
+            tick(0);
+            mbar_wait_warp(dempty + di, (((unsigned)it / kDescDepth) & 1u) ^ 1u, lane, p.sync_mode & 1);
+            tick(1);
             Desc *d = desc + di;
             {
                 const unsigned PLo = head + (unsigned)posLo, PHi = head + (unsigned)posHi;
@@ -582,7 +598,7 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring_kernel(const RoiRingPar
                     if (j < p.ph)
                         d->y[j] = make_int4((int)(PLo % K), (int)(PHi % K), __float_as_int(frac),
                                             (ok ? 1 : 0) | (relLo ? 2 : 0) | (relHi ? 4 : 0) | ((int)((PLo / K) & 1u) << 3) |
-                                                ((int)((PHi / K) & 1u) << 4));
+                                                ((int)((PHi / K) & 1u) << 4) | (newLo ? 32 : 0) | (newHi ? 64 : 0));
                 } else if (j < p.pw) {
                     d->x[j] = make_int4(posLo * (int)px_bytes, posHi * (int)px_bytes, __float_as_int(frac), ok ? 1 : 0);
                 }
@@ -604,6 +620,7 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring_kernel(const RoiRingPar
             }
             __syncwarp();
             const int nruns = __popc(start_mask);
+            tick(2);
             for (int b0 = 0; b0 < ny; b0 += K) {
                 const int r = b0 + lane;
                 const bool mine = lane < K && r < ny;
@@ -629,24 +646,33 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring_kernel(const RoiRingPar
                 }
             }
             head += (unsigned)ny;
+            tick(3);
         }
+        if (p.prof && lane == 0)
+            for (int i = 0; i < 4; ++i) atomicAdd(p.prof + i, pc[i]);
     } else {
         // ------------------------------- consumers -------------------------------
         const int cw = warp - 1;
         const int bins = p.ph * p.pw;
         int it = 0;
+        unsigned long long pc[4] = {0, 0, 0, 0};
+        long long tk = clock64();
+        auto tick = [&](int i) { if (p.prof) { const long long now = clock64(); pc[i] += (unsigned long long)(now - tk); tk = now; } };
+        const int one = p.sync_mode & 1, only_new = p.sync_mode & 2;
         for (int spos = blockIdx.x; spos < p.total; spos += gridDim.x, ++it) {
             const int di = it % kDescDepth;
-            mbar_wait(dfull + di, ((unsigned)it / kDescDepth) & 1u);
+            mbar_wait_warp(dfull + di, ((unsigned)it / kDescDepth) & 1u, lane, one);
+            tick(0);
             const Desc *d = desc + di;
             const long long out_roi = (long long)d->roi * bins * p.c4;
             for (int by = 0; by < p.ph; ++by) {
                 const int4 ye = d->y[by];
                 const bool yok = (ye.w & 1) != 0;
                 if (yok) {
-                    mbar_wait(full + ye.x, (unsigned)(ye.w >> 3) & 1u);
-                    mbar_wait(full + ye.y, (unsigned)(ye.w >> 4) & 1u);
+                    if (!only_new || (ye.w & 32)) mbar_wait_warp(full + ye.x, (unsigned)(ye.w >> 3) & 1u, lane, one);
+                    if (!only_new || (ye.w & 64)) mbar_wait_warp(full + ye.y, (unsigned)(ye.w >> 4) & 1u, lane, one);
                 }
+                tick(1);
                 const unsigned char *top = slots + (size_t)ye.x * p.slot_bytes;
                 const unsigned char *bot = slots + (size_t)ye.y * p.slot_bytes;
                 const float ly = __int_as_float(ye.z);
@@ -682,6 +708,7 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring_kernel(const RoiRingPar
                     }
                 }
                 __syncwarp();
+                tick(2);
                 if (lane == 0 && yok) {
                     if (ye.w & 2) mbar_arrive(empty + ye.x);
                     if (ye.w & 4) mbar_arrive(empty + ye.y);
@@ -689,7 +716,10 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring_kernel(const RoiRingPar
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(dempty + di);
+            tick(3);
         }
+        if (p.prof && lane == 0 && cw == 0)
+            for (int i = 0; i < 4; ++i) atomicAdd(p.prof + 4 + i, pc[i]);
     }
 }
 
@@ -790,7 +820,7 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
     const unsigned px_bytes = (unsigned)channels * 4u;
     const unsigned slot_bytes = 2u * (unsigned)pool_w * px_bytes;
     const size_t ring_fixed = ring::kDescDepth * sizeof(ring::Desc) + (2 * ring::kMaxSlots + 2 * ring::kDescDepth) * sizeof(uint64_t) + 128;
-    if (path == 1 && pool_h <= ring::kMaxSamples && pool_w <= ring::kMaxSamples && 4 * (size_t)slot_bytes + ring_fixed <= 227 * 1024) {
+    if (path == 1 && pool_h <= ring::kMaxSamples && pool_w <= ring::kMaxSamples && 4 * (size_t)slot_bytes + ring_fixed <= 223 * 1024) {
         static const int env_ctas = getenv("DCAP_ROI_CTAS") ? atoi(getenv("DCAP_ROI_CTAS")) : 2;
         static const int env_slots = getenv("DCAP_ROI_RING") ? atoi(getenv("DCAP_ROI_RING")) : 0;
         static const int env_warps = getenv("DCAP_ROI_WARPS") ? atoi(getenv("DCAP_ROI_WARPS")) : 0;
@@ -798,7 +828,7 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
         // K row slots: what fits next to `ctas` resident CTAs per SM (227 KB usable, 1 KB reserved per CTA)
         int slots = 0;
         for (; ctas >= 1; --ctas) {
-            const size_t per_cta = (size_t)(227 * 1024) / ctas - 1024;
+            const size_t per_cta = (size_t)(224 * 1024) / ctas - 1024;   // static smem + the 1 KB the driver reserves per CTA
             slots = per_cta > ring_fixed ? (int)((per_cta - ring_fixed) / slot_bytes) : 0;
             if (slots >= 4) break;
         }
@@ -835,19 +865,36 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
         if (e == cudaSuccess) {
             static std::atomic<unsigned long long> attr_set2{0};
             e = once_per_device(attr_set2, [] {
-                return cudaFuncSetAttribute(roi_align_ring_kernel<kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                return cudaFuncSetAttribute(roi_align_ring_kernel<kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);   // + 640 B static
             });
         }
         if (e == cudaSuccess) {
             PdlScope pdl;                 // the ring kernel's barrier set-up overlaps the order kernel
+            const long long mg = (long long)sm_count() * ctas;
             RoiRingParams rp;
             rp.boxes = boxes; rp.order = op.order;
             for (int l = 0; l < 4; ++l) { rp.fm[l] = fmaps[l]; rp.fm_h[l] = fm_h[l]; rp.fm_w[l] = fm_w[l]; }
             rp.n_boxes = n_boxes; rp.c4 = channels / 4; rp.ph = pool_h; rp.pw = pool_w;
             rp.out = out; rp.total = (int)total; rp.slots = slots; rp.slot_bytes = slot_bytes;
             static const int env_diag = getenv("DCAP_ROI_DIAG") ? atoi(getenv("DCAP_ROI_DIAG")) : 0;
-            rp.diag = env_diag;
-            const long long mg = (long long)sm_count() * ctas;
+            static const int env_sync = getenv("DCAP_ROI_SYNC") ? atoi(getenv("DCAP_ROI_SYNC")) : 0;
+            static const bool env_prof = getenv("DCAP_ROI_PROF") != nullptr;
+            rp.diag = env_diag; rp.sync_mode = env_sync; rp.prof = nullptr;
+            static unsigned long long *prof_buf = nullptr;
+            static int prof_calls = 0;
+            if (env_prof) {
+                if (!prof_buf) { cudaMalloc((void **)&prof_buf, 64); cudaMemset(prof_buf, 0, 64); }
+                rp.prof = prof_buf;
+                if (++prof_calls % 16 == 0) {              // mean cycles per CTA role and call, over the last 16 calls
+                    unsigned long long h[8];
+                    cudaMemcpy(h, prof_buf, 64, cudaMemcpyDeviceToHost);
+                    cudaMemset(prof_buf, 0, 64);
+                    const double nc = 16.0 * (double)(total < mg ? total : mg);
+                    fprintf(stderr, "[roi ring prof] per CTA: producer compute %.0f, desc wait %.0f, publish %.0f, issue %.0f | consumer "
+                            "desc wait %.0f, row wait %.0f, compute+store %.0f, release %.0f cycles\n", h[0] / nc, h[1] / nc, h[2] / nc,
+                            h[3] / nc, h[4] / nc, h[5] / nc, h[6] / nc, h[7] / nc);
+                }
+            }
             e = launch_pdl(roi_align_ring_kernel<kBf16>, dim3((unsigned)(total < mg ? total : mg)), dim3((ncons + 1) * 32), smem,
                            stream, rp);
             if (e == cudaSuccess) e = cudaGetLastError();

@@ -59,6 +59,18 @@ struct TrainState {
     cudaStream_t side = nullptr;
     std::vector<cudaEvent_t> step_ev;                              // [T] chain A -> chain B hand-over per time step
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    // v2 inject model (train_step_v2): word LSTM over L steps, one image-LSTM step, Dense(V)
+    int v2_B = 0, v2_L = 0;
+    std::vector<void *> v2_owned;
+    int32_t *v2_tok_tm = nullptr, *v2_tgt_dummy = nullptr, *v2_ones = nullptr;   // [L, B], [L, B], [B]
+    __nv_bfloat16 *v2_X = nullptr;                                  // [(L+1), B, Epad+Wu]
+    float *v2_c = nullptr;                                          // [(L+1), B, Wu]
+    __nv_bfloat16 *v2_gates_w = nullptr, *v2_gates_i = nullptr;     // [L, B, 4Wu], [B, 4U]
+    float *v2_c_img = nullptr, *v2_logits = nullptr;                // [B, U], [B, V]
+    __nv_bfloat16 *v2_dz = nullptr, *v2_dzi = nullptr, *v2_dzw = nullptr;   // [B, V], [B, 4U], [L, B, 4Wu]
+    float *v2_dh_img = nullptr, *v2_dxin = nullptr, *v2_dh_prev = nullptr;  // [B, U], [B, F+Wu], [B, Wu]
+    float *v2_carry = nullptr, *v2_dc = nullptr, *v2_carry_i = nullptr, *v2_dc_i = nullptr;
+    float *v2_rowloss = nullptr;
 };
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -66,6 +78,7 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 void Decoder::free_train() {
     if (bf && bf->train) {
         for (void *p : bf->train->owned) cudaFree(p);
+        for (void *p : bf->train->v2_owned) cudaFree(p);
         for (cudaEvent_t e : bf->train->bucket_ev)
             if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : bf->train->step_ev)
@@ -669,6 +682,7 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[2], s));                 // bucket 2: both LSTMs
 
     if (!train_head) {
+        DC_REQUIRE(!(train_opts && train_opts->d_feats), "d_feats needs RoI-feature input (the head must be part of the graph)");
         DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[3], s));             // head gradients stay zero
         return DC_OK;
     }
@@ -698,6 +712,14 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     DC_CHECK_LAUNCH();
     if (int rc = wgrad(x0, Kin, Kin, t.dzh1, F, F, B, G("mrcnn_class_conv1/kernel"), F)) return rc;
     DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[3], s));                 // bucket 3: RoI head
+    if (train_opts && train_opts->d_feats) {
+        // joint model (dense_img_cap/dense_model.py:738-755): dL/dX = dz1 K1^T, the conv7x7(valid) read every one
+        // of the pool*pool*C inputs exactly once.  The Keras-layout kernel [Kin, F] is the K-major B operand.
+        TcEpilogue e;
+        e.out_f32 = train_opts->d_feats; e.ld_f32 = Kin;
+        const __nv_bfloat16 *k1 = b.arena_k + find("mrcnn_class_conv1/kernel")->offset;
+        if (int rc = gemm_bf16_tc(tc_op(t.dzh1, F), tc_op(k1, F), e, B, Kin, F, kEpiStore, s)) return rc;
+    }
     return DC_OK;
 }
 
@@ -758,6 +780,154 @@ int Decoder::teacher_forced_probs(const void *feats, int kind, int B, const int3
     return DC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// v2 inject model: one training step (text_generation_model_v2.py:140-166 build_model(inject=True), :263-267
+// compile(Adam(amsgrad=True), categorical_crossentropy), :312 fit_generator on batches of 1024 (prefix, next word)
+// pairs).  Trainable: lstm_1 (word LSTM 1024 over the embedded, pre-padded, masked prefix), imgcap_lstm (one
+// step from the zero state on [head feature ; word vector]) and imgcap_d1; the RoI head (trainable=False) and
+// the embedding are frozen -- their gradient slots stay zero, which Adam leaves untouched.
+// ------------------------------------------------------------------------------------------------
+static int train_reserve_v2(Decoder &D, int B, int L) {
+    Bf16State &b = *D.bf;
+    if (!b.train) b.train = new TrainState();
+    TrainState &t = *b.train;
+    if (t.v2_B >= B && t.v2_L >= L) return DC_OK;
+    for (void *p : t.v2_owned) cudaFree(p);
+    t.v2_owned.clear();
+    const DcDecoderConfig &c = D.cfg;
+    const size_t U = c.units, F = c.feat, V = c.vocab, Wu = c.word_units, Kw = b.Epad + Wu;
+    const size_t Bp = round_up(B, 128), R = (size_t)L * Bp;
+    auto A = [&](void **p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+        if (e != cudaSuccess) return set_error(DC_ERR_CUDA, "training workspace allocation failed: %s", cudaGetErrorString(e));
+        t.v2_owned.push_back(*p);
+        return DC_OK;
+    };
+    int rc = 0;
+    rc |= A((void **)&t.v2_tok_tm, 4 * R); rc |= A((void **)&t.v2_tgt_dummy, 4 * R); rc |= A((void **)&t.v2_ones, 4 * Bp);
+    rc |= A((void **)&t.v2_X, 2 * (R + Bp) * Kw); rc |= A((void **)&t.v2_c, 4 * (R + Bp) * Wu);
+    rc |= A((void **)&t.v2_gates_w, 2 * R * 4 * Wu); rc |= A((void **)&t.v2_gates_i, 2 * Bp * 4 * U);
+    rc |= A((void **)&t.v2_c_img, 4 * Bp * U); rc |= A((void **)&t.v2_logits, 4 * Bp * V);
+    rc |= A((void **)&t.v2_dz, 2 * Bp * V); rc |= A((void **)&t.v2_dzi, 2 * Bp * 4 * U); rc |= A((void **)&t.v2_dzw, 2 * R * 4 * Wu);
+    rc |= A((void **)&t.v2_dh_img, 4 * Bp * U); rc |= A((void **)&t.v2_dxin, 4 * Bp * (F + Wu)); rc |= A((void **)&t.v2_dh_prev, 4 * Bp * Wu);
+    rc |= A((void **)&t.v2_carry, 4 * Bp * Wu); rc |= A((void **)&t.v2_dc, 4 * Bp * Wu);
+    rc |= A((void **)&t.v2_carry_i, 4 * Bp * U); rc |= A((void **)&t.v2_dc_i, 4 * Bp * U);
+    rc |= A((void **)&t.v2_rowloss, 4 * Bp);
+    if (rc) { t.v2_B = t.v2_L = 0; return rc; }
+    t.v2_B = B; t.v2_L = L;
+    return DC_OK;
+}
+
+int Decoder::train_step_v2(const void *feats, int kind, int B, const int32_t *words, int L, const int32_t *targets,
+                           float inv_count, float *loss, cudaStream_t s) {
+    PdlScope pdl;
+    if (int rc = check_ready(B)) return rc;
+    DC_REQUIRE(cfg.arch == DC_ARCH_V2_INJECT && cfg.dtype == DC_DTYPE_BF16, "v2 training is served by the bf16 v2 inject decoder");
+    DC_REQUIRE(cfg.vocab % 8 == 0, "training needs VOCABULARY_SIZE %% 8 == 0 (vector gradient stores)");
+    DC_REQUIRE(B > 0 && L > 0 && feats && words && targets && loss, "null pointer argument / empty batch");
+    if (int rc = reserve(B)) return rc;
+    if (int rc = ensure_grads()) return rc;
+    Bf16State &b = *bf;
+    if (int rc = train_reserve_v2(*this, B, L)) return rc;
+    TrainState &t = *b.train;
+    const int U = cfg.units, F = cfg.feat, V = cfg.vocab, Wu = cfg.word_units, E = cfg.embed, Kw = b.Epad + Wu;
+    const long long R = (long long)L * B;
+    if (inv_count <= 0.f) inv_count = 1.0f / (float)B;
+    // bf16 mirror of the trainable arena: Keras [in, out] tensors = K-major B operands of the data-gradient GEMMs
+    if (!b.arena_k)
+        if (int rc = dev_alloc((void **)&b.arena_k, 2 * (size_t)n_train, owned)) return rc;
+    if (!b.arena_k_valid) {
+        if (int rc = f32_to_bf16(arena, b.arena_k, n_train, s)) return rc;
+        b.arena_k_valid = true;
+    }
+    auto Kk = [&](const char *name) { return b.arena_k + find(name)->offset; };
+    auto G = [&](const char *name) { return grads + find(name)->offset; };
+    auto wgrad = [&](const __nv_bfloat16 *X, long long ldx, int M, const __nv_bfloat16 *dY, long long ldy, int N, long long rows,
+                     float *out, long long ldo) {
+        TcEpilogue e;
+        e.out_f32 = out; e.ld_f32 = ldo; e.atomic = 1;
+        return gemm_bf16_tc(tc_op(X, ldx, true), tc_op(dY, ldy, true), e, M, N, (int)rows, kEpiStore, s, 0);
+    };
+
+    // ---------------- forward ----------------
+    if (int rc = v2_begin_bf16(feats, kind, B, s)) return rc;          // head -> xin[:, :F]; xin[:, F:] = 0
+    time_major_tokens_kernel<<<ceil_div((int)R, 256), 256, 0, s>>>(words, nullptr, B, L, V, t.v2_tok_tm, t.v2_tgt_dummy);
+    DC_CHECK_LAUNCH();
+    if (int rc = fill_i32(t.v2_ones, B, 1, s)) return rc;
+    DC_CHECK_CUDA(cudaMemsetAsync(t.v2_X, 0, 2 * (size_t)B * Kw, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(t.v2_c, 0, 4 * (size_t)B * Wu, s));
+    gather_embedding_rows_kernel<<<(unsigned)ceil_div<long long>(R * 32, 256), 256, 0, s>>>(
+        reinterpret_cast<const uint4 *>(b.emb), b.Epad / 8, t.v2_tok_tm, R, reinterpret_cast<uint4 *>(t.v2_X), Kw / 8);
+    DC_CHECK_LAUNCH();
+    for (int st = 0; st < L; ++st) {
+        __nv_bfloat16 *x = t.v2_X + (size_t)st * B * Kw, *xn = x + (size_t)B * Kw;
+        TcEpilogue c;
+        c.bias = b.v2_bw; c.cell_units = Wu; c.cell_tok = t.v2_tok_tm + (size_t)st * B;
+        c.cell_c = t.v2_c + (size_t)st * B * Wu; c.cell_c_out = t.v2_c + (size_t)(st + 1) * B * Wu;
+        c.cell_h_prev = x + b.Epad; c.ld_h_prev = Kw;
+        c.cell_h_a = xn + b.Epad; c.ld_h_a = Kw;
+        c.cell_h_b = b.v2_xin + F; c.ld_h_b = F + Wu;                  // the last step leaves the word vector in xin
+        c.cell_gates_out = t.v2_gates_w + (size_t)st * B * 4 * Wu; c.ld_gates_out = 4 * Wu;
+        if (int rc = gemm_bf16_tc(tc_op(x, Kw), tc_op(b.v2_w1cat, Kw), c, B, 4 * Wu, Kw, kEpiCell, s)) return rc;
+    }
+    {
+        TcEpilogue c;
+        c.bias = b.v2_bimg; c.cell_c = b.v2_czero; c.cell_c_out = t.v2_c_img; c.cell_units = U;
+        c.cell_h_a = b.v2_hb; c.ld_h_a = U;
+        c.cell_gates_out = t.v2_gates_i; c.ld_gates_out = 4 * U;
+        if (int rc = gemm_bf16_tc(tc_op(b.v2_xin, F + Wu), tc_op(b.v2_wimg, F + Wu), c, B, 4 * U, F + Wu, kEpiCell, s)) return rc;
+        TcEpilogue e;
+        e.bias = W("imgcap_d1/bias"); e.out_f32 = t.v2_logits; e.ld_f32 = V;
+        if (int rc = gemm_bf16_tc(tc_op(b.v2_hb, U), tc_op(b.v2_wd, U), e, B, V, U, kEpiStore, s)) return rc;
+    }
+    // ---------------- loss ----------------
+    DC_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n_train, s));
+    softmax_xent_kernel<<<(unsigned)B, 256, 0, s>>>(t.v2_logits, V, V, targets, inv_count, t.v2_dz, V, t.v2_rowloss);
+    DC_CHECK_LAUNCH();
+    reduce_loss_kernel<<<1, 1024, 0, s>>>(t.v2_rowloss, B, inv_count, loss);
+    DC_CHECK_LAUNCH();
+    // ---------------- backward ----------------
+    if (int rc = wgrad(b.v2_hb, U, U, t.v2_dz, V, V, B, G("imgcap_d1/kernel"), V)) return rc;
+    if (int rc = colsum(t.v2_dz, B, V, V, G("imgcap_d1/bias"), s)) return rc;
+    {
+        TcEpilogue e;
+        e.out_f32 = t.v2_dh_img; e.ld_f32 = U;
+        if (int rc = gemm_bf16_tc(tc_op(t.v2_dz, V), tc_op(Kk("imgcap_d1/kernel"), V), e, B, U, V, kEpiStore, s)) return rc;
+    }
+    for (float *p : {t.v2_carry_i, t.v2_dc_i}) DC_CHECK_CUDA(cudaMemsetAsync(p, 0, 4 * (size_t)B * U, s));
+    for (float *p : {t.v2_carry, t.v2_dc}) DC_CHECK_CUDA(cudaMemsetAsync(p, 0, 4 * (size_t)B * Wu, s));
+    DC_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3((unsigned)ceil_div<long long>((long long)B * (U / 4), 256)), dim3(256), 0, s, B, U,
+                             (const __nv_bfloat16 *)t.v2_gates_i, (const float *)b.v2_czero, (const float *)t.v2_c_img,
+                             (const int32_t *)t.v2_ones, (const float *)t.v2_dh_img, U, (const float *)nullptr, 0, t.v2_carry_i,
+                             t.v2_dc_i, t.v2_dzi, (float *)nullptr));
+    if (int rc = wgrad(b.v2_xin, F + Wu, F + Wu, t.v2_dzi, 4 * U, 4 * U, B, G("imgcap_lstm/kernel"), 4 * U)) return rc;
+    if (int rc = colsum(t.v2_dzi, B, 4 * U, 4 * U, G("imgcap_lstm/bias"), s)) return rc;
+    {   // d[head ; word vector] = dz_img K^T; the recurrent kernel saw the zero state: no gradient
+        TcEpilogue e;
+        e.out_f32 = t.v2_dxin; e.ld_f32 = F + Wu;
+        if (int rc = gemm_bf16_tc(tc_op(t.v2_dzi, 4 * U), tc_op(Kk("imgcap_lstm/kernel"), 4 * U), e, B, F + Wu, 4 * U, kEpiStore, s)) return rc;
+    }
+    const unsigned cb_grid = (unsigned)ceil_div<long long>((long long)B * (Wu / 4), 256);
+    for (int st = L - 1; st >= 0; --st) {
+        const bool last = st == L - 1;
+        __nv_bfloat16 *dzw = t.v2_dzw + (size_t)st * B * 4 * Wu;
+        DC_CHECK_CUDA(launch_pdl(lstm_cell_bwd_kernel, dim3(cb_grid), dim3(256), 0, s, B, Wu,
+                                 (const __nv_bfloat16 *)(t.v2_gates_w + (size_t)st * B * 4 * Wu), (const float *)(t.v2_c + (size_t)st * B * Wu),
+                                 (const float *)(t.v2_c + (size_t)(st + 1) * B * Wu), (const int32_t *)(t.v2_tok_tm + (size_t)st * B),
+                                 (const float *)(last ? t.v2_dxin + F : t.v2_dh_prev), last ? F + Wu : Wu, (const float *)nullptr, 0,
+                                 t.v2_carry, t.v2_dc, dzw, (float *)nullptr));
+        if (st > 0) {
+            TcEpilogue e;
+            e.out_f32 = t.v2_dh_prev; e.ld_f32 = Wu;
+            if (int rc = gemm_bf16_tc(tc_op(dzw, 4 * Wu), tc_op(Kk("lstm_1/recurrent_kernel"), 4 * Wu), e, B, Wu, 4 * Wu, kEpiStore, s)) return rc;
+        }
+    }
+    if (int rc = wgrad(t.v2_X, Kw, E, t.v2_dzw, 4 * Wu, 4 * Wu, R, G("lstm_1/kernel"), 4 * Wu)) return rc;
+    if (int rc = wgrad(t.v2_X + b.Epad, Kw, Wu, t.v2_dzw, 4 * Wu, 4 * Wu, R, G("lstm_1/recurrent_kernel"), 4 * Wu)) return rc;
+    if (int rc = colsum(t.v2_dzw, R, 4 * Wu, 4 * Wu, G("lstm_1/bias"), s)) return rc;
+    return DC_OK;
+}
+
 int Decoder::adam_step(float lr, float beta1, float beta2, float eps, int amsgrad, long long t, float grad_scale,
                        cudaStream_t s) {
     DC_REQUIRE(grads, "dc_adam_step before any dc_decoder_train_step");
@@ -785,6 +955,26 @@ extern "C" int dc_decoder_train_step(DcDecoder *dec, const void *feats, int feat
                                      const int32_t *targets, float inv_count, float *loss, void *stream) {
     DC_REQUIRE(dec, "null decoder");
     return dec->impl.train_step(feats, feats_kind, B, gt, targets, inv_count, loss, (cudaStream_t)stream);
+}
+
+extern "C" int dc_decoder_train_step_ex(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *gt,
+                                        const int32_t *targets, float inv_count, float *loss, const DcTrainOptions *opts,
+                                        void *stream) {
+    DC_REQUIRE(dec, "null decoder");
+    if (opts) {
+        DC_REQUIRE(opts->recurrent_dropout >= 0.f && opts->recurrent_dropout < 1.f, "recurrent_dropout must be in [0, 1)");
+        DC_REQUIRE(opts->recurrent_dropout == 0.f, "recurrent_dropout is not available in this build");
+    }
+    dec->impl.train_opts = opts;
+    const int rc = dec->impl.train_step(feats, feats_kind, B, gt, targets, inv_count, loss, (cudaStream_t)stream);
+    dec->impl.train_opts = nullptr;
+    return rc;
+}
+
+extern "C" int dc_decoder_v2_train_step(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *words, int L,
+                                       const int32_t *targets, float inv_count, float *loss, void *stream) {
+    DC_REQUIRE(dec, "null decoder");
+    return dec->impl.train_step_v2(feats, feats_kind, B, words, L, targets, inv_count, loss, (cudaStream_t)stream);
 }
 
 extern "C" int dc_decoder_teacher_forced(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *gt,

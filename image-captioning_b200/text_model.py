@@ -95,6 +95,12 @@ class _DeviceArray(object):
                                          "version": 2}
 
 
+class _DcTrainOptions(ctypes.Structure):
+    """include/dcap.h: DcTrainOptions"""
+    _fields_ = [("d_feats", ctypes.c_void_p), ("recurrent_dropout", ctypes.c_float), ("dropout_seed", ctypes.c_uint64),
+                ("dropout_step", ctypes.c_int64), ("row_offset", ctypes.c_int64)]
+
+
 class _DcDecoderConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in ("arch", "dtype", "vocab", "embed", "feat", "units",
                                             "word_units", "pool", "channels", "padding")]
@@ -478,9 +484,14 @@ class RoiCaptionModel(_ModelBase):
             out[n] = g
         return out
 
-    def train_step_device(self, features, gt_captions, targets=None, inv_count=0.0, loss_out=None):
+    def train_step_device(self, features, gt_captions, targets=None, inv_count=0.0, loss_out=None, d_features=None,
+                          recurrent_dropout=0.0, dropout_seed=0, dropout_step=0, row_offset=0):
         """Forward + loss + backward on device tensors; gradients stay in grad_buffer().  Returns the
-        device scalar  sum_positions(-log p_y) * inv_count  (inv_count <= 0: 1/(N*P)).  No host sync."""
+        device scalar  sum_positions(-log p_y) * inv_count  (inv_count <= 0: 1/(N*P)).  No host sync.
+        ``d_features`` (fp32 CUDA tensor shaped like the RoI features) receives dL/d(features): the gradient the
+        joint model chains into PyramidROIAlign's backward (dense_img_cap/dense_model.py:738-755).
+        ``recurrent_dropout`` > 0 applies KL.LSTM(recurrent_dropout=...) masks (text_generation_model.py:141-142),
+        drawn from (dropout_seed, dropout_step, row_offset + row): see include/dcap.h DcTrainOptions."""
         self._ready()
         t, kind, _ = self._feats_to_device(features)
         gt = self._ids_to_device(gt_captions, "gt_captions")
@@ -488,11 +499,18 @@ class RoiCaptionModel(_ModelBase):
         if gt.shape[0] != t.shape[0] or (tg is not None and tg.shape != gt.shape):
             raise ValueError("features, gt_captions and targets disagree on the batch size")
         loss = torch.empty((), dtype=torch.float32, device=self.device) if loss_out is None else loss_out
+        opts = None
+        if d_features is not None or recurrent_dropout:
+            if d_features is not None and (not d_features.is_cuda or d_features.dtype != torch.float32
+                                           or not d_features.is_contiguous() or d_features.numel() != t.numel()):
+                raise ValueError("d_features must be a contiguous fp32 CUDA tensor shaped like the RoI features")
+            opts = _DcTrainOptions(d_features.data_ptr() if d_features is not None else None, float(recurrent_dropout),
+                                   int(dropout_seed), int(dropout_step), int(row_offset))
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.dc_decoder_train_step(
+            _lib.check(self._lib.dc_decoder_train_step_ex(
                 self._h, ctypes.c_void_p(t.data_ptr()), kind, t.shape[0], ctypes.c_void_p(gt.data_ptr()),
                 ctypes.c_void_p(tg.data_ptr()) if tg is not None else None, ctypes.c_float(inv_count),
-                ctypes.c_void_p(loss.data_ptr()), self._stream()))
+                ctypes.c_void_p(loss.data_ptr()), ctypes.byref(opts) if opts is not None else None, self._stream()))
         return loss
 
     def apply_gradients(self, grad_scale=1.0):
@@ -646,6 +664,74 @@ class InjectModelV2(_ModelBase):
         if was_numpy:
             outs = [o.cpu().numpy() for o in outs]
         return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+def _v2_training_surface():
+    """compile / train_on_batch / test_on_batch / fit_generator of the v2 inject model
+    (text_generation_model_v2.py:263-267, 312-330): Adam(amsgrad=True) + keras.losses.categorical_crossentropy on
+    [N, V] next-word targets; the generator yields ([features, words], one_hot_next_word)."""
+
+    def _words_to_device(self, words, n):
+        w = torch.as_tensor(np.asarray(words) if not isinstance(words, torch.Tensor) else words)
+        if w.dim() != 2 or w.shape[0] != n:
+            raise ValueError("words must be [N, L] with the same N as the features")
+        return w.to(self.device).to(torch.int32).contiguous()
+
+    def _next_word_ids(self, y, n):
+        """one-hot [N, V] (what data_generator yields) or class ids [N]; an all-zero row = no target"""
+        t = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(y))
+        t = t.to(self.device)
+        if t.dim() == 2:
+            ids = t.argmax(-1).to(torch.int32)
+            ids = torch.where(t.sum(-1) > 0, ids, torch.full_like(ids, -1))
+        else:
+            ids = t.to(torch.int32)
+        if ids.dim() != 1 or ids.shape[0] != n:
+            raise ValueError("targets must be [N, V] one-hot rows or [N] class ids")
+        return ids.contiguous()
+
+    def train_step_device(self, features, words, targets, inv_count=0.0, loss_out=None):
+        """Forward + categorical cross-entropy + backward; gradients stay in grad_buffer().  Returns the device scalar
+        sum_rows(-log p_y) * inv_count (inv_count <= 0: 1/N).  No host sync."""
+        self._ready()
+        t, kind, _ = self._feats_to_device(features)
+        w = self._words_to_device(words, t.shape[0])
+        y = self._next_word_ids(targets, t.shape[0])
+        loss = torch.empty((), dtype=torch.float32, device=self.device) if loss_out is None else loss_out
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_v2_train_step(
+                self._h, ctypes.c_void_p(t.data_ptr()), kind, t.shape[0], ctypes.c_void_p(w.data_ptr()), w.shape[1],
+                ctypes.c_void_p(y.data_ptr()), ctypes.c_float(inv_count), ctypes.c_void_p(loss.data_ptr()), self._stream()))
+        return loss
+
+    def _inv(self, y_ids):
+        cnt = int((y_ids >= 0).sum().item())
+        return 1.0 / cnt if cnt else 0.0
+
+    def train_on_batch(self, x, y=None, sample_weight=None, class_weight=None):
+        if self.optimizer is None:
+            raise RuntimeError("compile() the model first")
+        if sample_weight is not None or class_weight is not None:
+            raise NotImplementedError("sample/class weights are not used by the reference")
+        feats, words = x
+        ids = self._next_word_ids(y, len(feats))
+        loss = self.train_step_device(feats, words, ids, self._inv(ids))
+        self.apply_gradients()
+        return float(loss.item())
+
+    def test_on_batch(self, x, y=None, sample_weight=None):
+        feats, words = x
+        ids = self._next_word_ids(y, len(feats))
+        return float(self.train_step_device(feats, words, ids, self._inv(ids)).item())
+
+    return dict(_words_to_device=_words_to_device, _next_word_ids=_next_word_ids, train_step_device=train_step_device, _inv=_inv,
+                train_on_batch=train_on_batch, test_on_batch=test_on_batch)
+
+
+for _k, _v in _v2_training_surface().items():
+    setattr(InjectModelV2, _k, _v)
+for _k in ("compile", "grad_buffer", "param_buffer", "get_gradients", "apply_gradients", "fit_generator"):
+    setattr(InjectModelV2, _k, getattr(RoiCaptionModel, _k))
 
 
 def build_lstm_model(features_input, config, units, mode, dtype="float32", device=None):

@@ -223,9 +223,42 @@ int dc_decoder_greedy_host(DcDecoder *dec, const float *feats, int feats_kind, i
  *   inv_count  1 / (number of positions the loss averages over, GLOBALLY when the batch is sharded
  *            over ranks); <= 0 means 1/(B*P)
  *   loss     device float: sum over this call's positions of -log(clip(p_y,1e-7,1-1e-7)) * inv_count
- * VOCABULARY_SIZE must be a multiple of 8.  recurrent_dropout is not applied. */
+ * VOCABULARY_SIZE must be a multiple of 8.  recurrent_dropout off (the parity mode); see dc_decoder_train_step_ex. */
 int dc_decoder_train_step(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *gt,
                           const int32_t *targets, float inv_count, float *loss, void *stream);
+
+/* Same step with the optional parts of the reference's training graph:
+ *   d_feats            NULL, or [B, pool, pool, C] fp32 (device): dL/d(RoI features), the gradient the JOINT model
+ *                      (dense_img_cap/dense_model.py:738-755: extract_roi_features -> caption head) sends back into
+ *                      PyramidROIAlign -- feed it to dc_pyramid_roi_align_backward_f32.  Needs RoI-feature input
+ *                      (DC_FEATS_ROI_F32 / DC_FEATS_ROI_BF16).
+ *   recurrent_dropout  rate of KL.LSTM(..., recurrent_dropout=0.2) (text_generation_model.py:141-142): four
+ *                      time-invariant masks per LSTM (one per gate i,f,c,o), values {0, 1/(1-rate)}, applied to
+ *                      h_{t-1} before its recurrent product.  0 = off.  Masks are counter-based (Philox-4x32-10 keyed
+ *                      by dropout_seed, counter = (global row, unit, layer, dropout_step)): no state, and a batch
+ *                      sharded over any number of ranks draws the same masks as the unsharded batch when
+ *                      row_offset = global index of this call's first row.  TF's own RNG stream cannot be matched;
+ *                      the oracle (oracle/decoder.py: philox_masks) draws the identical masks.
+ * opts == NULL behaves as dc_decoder_train_step. */
+typedef struct DcTrainOptions {
+    float *d_feats;
+    float recurrent_dropout;
+    uint64_t dropout_seed;
+    int64_t dropout_step;
+    int64_t row_offset;
+} DcTrainOptions;
+int dc_decoder_train_step_ex(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *gt,
+                             const int32_t *targets, float inv_count, float *loss, const DcTrainOptions *opts,
+                             void *stream);
+
+/* One training step of the v2 inject model (text_generation_model_v2.py:140-166 build_model(inject=True); :263-267
+ * compile(Adam(amsgrad=True), keras.losses.categorical_crossentropy); :312 fit_generator on (prefix, next word) batches).
+ *   words    [B, L] int32 pre-padded prefix ids (0 = masked)      targets  [B] int32 next-word class id (< 0: ignored)
+ *   inv_count  1 / (GLOBAL batch size); <= 0 means 1/B            loss     device float: sum_b -log(clip(p_y)) * inv_count
+ * Gradients of lstm_1, imgcap_lstm and imgcap_d1 land in the flat gradient buffer; the RoI head (trainable=False in
+ * the reference) and the embedding are frozen: their slots stay zero.  bf16 v2 handles only. */
+int dc_decoder_v2_train_step(DcDecoder *dec, const void *feats, int feats_kind, int B, const int32_t *words, int L,
+                             const int32_t *targets, float inv_count, float *loss, void *stream);
 
 /* model.predict([features, gt_captions]) of the TRAINING graph (text_generation_model.py:264-277):
  * teacher-forced word probabilities, probs [B, P, V] fp32 (device). */

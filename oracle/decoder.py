@@ -252,9 +252,11 @@ def keras_adam_amsgrad(p, g, m, v, vhat, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7)
 # fp64 reference gradients of the v1 training graph (used to check the CUDA backward)
 # ----------------------------------------------------------------------------------------
 
-def train_loss_and_grads_v1(feat, gt, w, train_head=True):
+def train_loss_and_grads_v1(feat, gt, w, train_head=True, return_dfeat=False):
     """Loss (mean CE over all B*P positions, clipping ignored -- probabilities of random models
-    stay far from 1e-7) and analytic gradients in fp64 by manual BPTT.  Returns (loss, grads)."""
+    stay far from 1e-7) and analytic gradients in fp64 by manual BPTT.  Returns (loss, grads), plus
+    dL/d(feat) [B,pool,pool,C] with ``return_dfeat`` (the gradient the joint model sends back into
+    PyramidROIAlign, dense_img_cap/dense_model.py:738-755)."""
     D = np.float64
     B, P = gt.shape
     W = {k: v.astype(D) for k, v in w.items()}
@@ -361,6 +363,8 @@ def train_loss_and_grads_v1(feat, gt, w, train_head=True):
         dz1 = dy1 * s1
         G["mrcnn_class_conv1/kernel"] = (x0.T @ dz1).reshape(W["mrcnn_class_conv1/kernel"].shape)
         G["mrcnn_class_conv1/bias"] = dz1.sum(0)
+        if return_dfeat:
+            return loss, G, (dz1 @ k1.T).reshape(feat.shape)
     return loss, G
 
 
@@ -392,6 +396,68 @@ def v2_inject_predict(feat, words, w, dtype=F32, return_logits=False):
                      w["imgcap_lstm/recurrent_kernel"].astype(dtype), w["imgcap_lstm/bias"].astype(dtype))
     z = h @ w["imgcap_d1/kernel"].astype(dtype) + w["imgcap_d1/bias"].astype(dtype)
     return z if return_logits else softmax(z)
+
+
+def train_loss_and_grads_v2(feat, words, y, w):
+    """v2 inject model training step in fp64 (text_generation_model_v2.py:140-166, 263-267): loss = mean over the
+    batch of keras.losses.categorical_crossentropy(one_hot(y), model([feat, words])) and its gradients w.r.t. the
+    TRAINABLE tensors -- lstm_1, imgcap_lstm, imgcap_d1; the RoI head (trainable=False) and the embedding are
+    frozen.  words [B,L] pre-padded ids (0 = masked), y [B] next-word ids.  Clipping ignored (see v1)."""
+    D = np.float64
+    W = {k: v.astype(D) for k, v in w.items()}
+    ids = np.asarray(words).astype(np.int32)
+    B, L = ids.shape
+    f = head(feat, w, D)
+    Wu = W["lstm_1/recurrent_kernel"].shape[0]
+    U = W["imgcap_lstm/recurrent_kernel"].shape[0]
+    Kw, Rw, bw = W["lstm_1/kernel"], W["lstm_1/recurrent_kernel"], W["lstm_1/bias"]
+    Ki, bi = W["imgcap_lstm/kernel"], W["imgcap_lstm/bias"]
+    Kd, bd = W["imgcap_d1/kernel"], W["imgcap_d1/bias"]
+    emb = W["imgcap_embedding_layer/embeddings"]
+
+    def cell_fwd(x, h, c, K, R, b, u):
+        z = x @ K + b + (h @ R if R is not None else 0.0)
+        i, fg, g, o = hard_sigmoid(z[:, :u]), hard_sigmoid(z[:, u:2 * u]), np.tanh(z[:, 2 * u:3 * u]), hard_sigmoid(z[:, 3 * u:])
+        cn = fg * c + i * g
+        tc = np.tanh(cn)
+        return o * tc, cn, (x, h, c, z, i, fg, g, o, tc)
+
+    def cell_bwd(dh, dc, kc, u):
+        x, h, c, z, i, fg, g, o, tc = kc
+        lin = lambda zz: np.where((zz > -2.5) & (zz < 2.5), 0.2, 0.0)
+        do = dh * tc
+        dcn = dc + dh * o * (1 - tc * tc)
+        dz = np.concatenate([dcn * g * lin(z[:, :u]), dcn * c * lin(z[:, u:2 * u]), dcn * i * (1 - g * g),
+                             do * lin(z[:, 3 * u:])], -1)
+        return dz, dcn * fg
+
+    h = np.zeros((B, Wu)); c = np.zeros((B, Wu))
+    cache = []
+    for t in range(L):
+        m = (ids[:, t] != 0)[:, None]
+        hn, cn, kc = cell_fwd(emb[ids[:, t]], h, c, Kw, Rw, bw, Wu)
+        cache.append((m, kc))
+        h = np.where(m, hn, h); c = np.where(m, cn, c)
+    x = np.concatenate([f, h], -1)
+    z0 = np.zeros((B, U))
+    hi, _, kci = cell_fwd(x, z0, z0, Ki, None, bi, U)              # zero state: the recurrent kernel never contributes
+    p = softmax(hi @ Kd + bd)
+    yy = np.asarray(y).astype(np.int64)
+    loss = -np.log(p[np.arange(B), yy]).mean()
+    G = {k: np.zeros_like(W[k]) for k in ("lstm_1/kernel", "lstm_1/recurrent_kernel", "lstm_1/bias", "imgcap_lstm/kernel",
+                                          "imgcap_lstm/recurrent_kernel", "imgcap_lstm/bias", "imgcap_d1/kernel", "imgcap_d1/bias")}
+    dz = p.copy(); dz[np.arange(B), yy] -= 1.0; dz /= B
+    G["imgcap_d1/kernel"] = hi.T @ dz; G["imgcap_d1/bias"] = dz.sum(0)
+    dzi, _ = cell_bwd(dz @ Kd.T, np.zeros((B, U)), kci, U)
+    G["imgcap_lstm/kernel"] = x.T @ dzi; G["imgcap_lstm/bias"] = dzi.sum(0)
+    dh = (dzi @ Ki.T)[:, f.shape[1]:]
+    dc = np.zeros((B, Wu))
+    for t in reversed(range(L)):
+        m, kc = cache[t]
+        dzw, dcp = cell_bwd(dh * m, dc * m, kc, Wu)
+        G["lstm_1/kernel"] += kc[0].T @ dzw; G["lstm_1/recurrent_kernel"] += kc[1].T @ dzw; G["lstm_1/bias"] += dzw.sum(0)
+        dh = np.where(m, dzw @ Rw.T, dh); dc = np.where(m, dcp, dc)
+    return loss, G
 
 
 def greedy_v2(feat, w, P, dtype=F32, start=None):

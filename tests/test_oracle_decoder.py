@@ -207,3 +207,36 @@ def test_batchnorm_and_cross_entropy_agree_with_independent_implementations():
     valid = rng.uniform(size=(4, 5)) < 0.6
     want_masked = F.cross_entropy(torch.from_numpy(logits)[torch.from_numpy(valid)], torch.from_numpy(ids)[torch.from_numpy(valid)]).item()
     np.testing.assert_allclose(dec.roi_caption_loss(ids, probs, valid), want_masked, rtol=1e-10)
+
+
+def test_v2_training_gradients_match_finite_differences():
+    """oracle.train_loss_and_grads_v2 (the checker of dc_decoder_v2_train_step): analytic fp64 BPTT through the masked,
+    pre-padded word LSTM, the single image-LSTM step and Dense(V) against central differences of the oracle's own
+    forward (v2_inject_predict); the image LSTM's recurrent kernel sees only the zero state -> zero gradient."""
+    rng = np.random.default_rng(3)
+    V, E, units, C, L, B = 30, 6, 5, 4, 5, 7
+    w = synth.synth_weights_v2(rng, V=V, E=E, F=1024, units=units, pool=2, C=C, trained_like=False)
+    w = {k: v.astype(np.float64) for k, v in w.items()}
+    feat = rng.standard_normal((B, 2, 2, C))
+    words = np.zeros((B, L), np.int32)
+    for i in range(B):
+        n = rng.integers(0, L + 1)
+        words[i, L - n:] = rng.integers(1, V, n)
+    words[2, L - 2] = 0
+    y = rng.integers(0, V, B)
+    loss, G = dec.train_loss_and_grads_v2(feat, words, y, w)
+
+    def f(wd):
+        p = dec.v2_inject_predict(feat, words, wd, np.float64)
+        return -np.log(p[np.arange(B), y]).mean()
+
+    assert abs(loss - f(w)) < 1e-12
+    assert not G["imgcap_lstm/recurrent_kernel"].any()
+    for name, g in G.items():
+        for _ in range(5):
+            ix = tuple(rng.integers(0, s) for s in g.shape)
+            wp, wm = dict(w), dict(w)
+            a = w[name].copy(); a[ix] += 1e-6; wp[name] = a
+            b = w[name].copy(); b[ix] -= 1e-6; wm[name] = b
+            fd = (f(wp) - f(wm)) / 2e-6
+            assert abs(fd - g[ix]) <= 1e-6 + 1e-4 * abs(fd), (name, ix, fd, g[ix])

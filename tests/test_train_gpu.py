@@ -208,3 +208,109 @@ def test_gradient_buckets_partition_the_buffer_and_signal_completion():
     final = m.grad_buffer()
     for (off, cnt), e in zip(buckets, early):
         assert torch.equal(e, final[off:off + cnt])
+
+
+def test_joint_model_gradient_chain_into_roi_align():
+    """SURVEY 8f rank 2 / dense_img_cap/dense_model.py:738-755: loss -> caption head -> PyramidROIAlign -> feature maps.
+    dc_decoder_train_step_ex's d_feats output, fed to dc_pyramid_roi_align_backward_f32, against the fp64 oracle chain
+    (oracle BPTT down to dL/dX, then the oracle's CropAndResizeGradImage)."""
+    import image_captioning_b200 as pkg
+    from oracle import roi_align as ra
+    rng = np.random.default_rng(57)
+    C, V, E, U, P, Bi, N = 64, 1000, 48, 128, 6, 2, 48
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C, trained_like=False)
+    boxes = synth.synth_boxes(rng, Bi, N, 1024.0)
+    shapes = [(64 >> i, 64 >> i) for i in range(4)]
+    fms = [rng.standard_normal((Bi, h, ww, C)).astype(np.float32) for h, ww in shapes]
+    gt = synth.synth_captions(rng, Bi * N, P, V)
+    feats_want, _ = ra.pyramid_roi_align(boxes, fms, (7, 7), (1024, 1024, 3))
+    loss_want, G, dfeat_want = dec.train_loss_and_grads_v1(feats_want[0], gt, w, return_dfeat=True)
+    dfm_want = ra.pyramid_roi_align_backward(boxes, dfeat_want, shapes, (7, 7), (1024, 1024, 3))
+
+    cfg = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], Bi * N, P)
+    m = pkg.build_lstm_model([7, 7, C], cfg, U, "training", dtype="bfloat16")
+    m.set_weights(w)
+    m.compile(optimizer=pkg.Adam(amsgrad=True), loss=pkg.roi_caption_loss)
+    tb = torch.from_numpy(boxes).cuda()
+    tf = [torch.from_numpy(f).cuda() for f in fms]
+    feats = pkg.pyramid_roi_align(tb, tf, (7, 7), (1024, 1024, 3))
+    assert np.array_equal(feats.cpu().numpy().view(np.uint32), feats_want[0].view(np.uint32))
+    d_feats = torch.full_like(feats, float("nan"))
+    loss = float(m.train_step_device(feats, gt, d_features=d_feats).item())
+    assert abs(loss - loss_want) <= 5e-3 * abs(loss_want)
+    got = d_feats.cpu().numpy()
+    assert np.isfinite(got).all()
+    rel = _rel_l2(got, dfeat_want)
+    cos = float((got.astype(np.float64) * dfeat_want).sum() / (np.linalg.norm(got) * np.linalg.norm(dfeat_want)))
+    assert rel <= 6e-2 and cos >= 0.995, (rel, cos)          # bf16 operands through head + BPTT (cf. the per-tensor bars above)
+    d_fms = pkg.pyramid_roi_align_backward(tb, d_feats, shapes, (7, 7), (1024, 1024, 3))
+    for g, want in zip(d_fms, dfm_want):
+        g = g.cpu().numpy()
+        if np.linalg.norm(want) == 0:
+            assert not g.any()
+            continue
+        assert _rel_l2(g, want) <= 6e-2, _rel_l2(g, want)
+    # the plain entry point and the _ex one with no options give the same gradients; head-feature input refuses d_feats
+    g1 = m.get_gradients()["imgcap_lstm_d2/kernel"]
+    m.train_step_device(feats, gt)
+    assert np.array_equal(g1, m.get_gradients()["imgcap_lstm_d2/kernel"]) or _rel_l2(m.get_gradients()["imgcap_lstm_d2/kernel"], g1) < 1e-3
+    with pytest.raises(RuntimeError):
+        m.train_step_device(m.head_features(feats), gt, d_features=d_feats)
+
+
+def test_v2_inject_training_step_matches_fp64_oracle():
+    """J1: the v2 inject model's training step (text_generation_model_v2.py:140-166, 263-267, 312-330): loss and the
+    gradients of lstm_1 / imgcap_lstm / imgcap_d1 against the fp64 oracle; head and embedding frozen; Keras surface
+    (compile, train_on_batch with one-hot next-word targets, fit_generator) reduces the loss."""
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(61)
+    V, E, units, C, L, B = 1000, 48, 64, 32, 6, 96
+    w = synth.synth_weights_v2(rng, V=V, E=E, units=units, C=C, trained_like=False)
+    feat = rng.standard_normal((B, 7, 7, C)).astype(np.float32)
+    words = np.zeros((B, L), np.int32)
+    for i in range(B):
+        n = int(rng.integers(0, L + 1))                       # pre-padded prefixes of every length, the empty one included
+        words[i, L - n:] = rng.integers(1, V, n)
+    words[5, L - 2] = 0                                         # a masked id inside a prefix
+    y = rng.integers(0, V, B).astype(np.int32)
+    loss_want, G = dec.train_loss_and_grads_v2(feat, words, y, w)
+    cfg = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], B, L)
+    m = pkg.build_model((7, 7, C), (L,), cfg, units, inject=True, dtype="bfloat16")
+    m.set_weights(w)
+    with pytest.raises(RuntimeError):
+        m.train_on_batch([feat, words], y)                       # not compiled
+    m.compile(optimizer=pkg.Adam(amsgrad=True), loss="categorical_crossentropy")
+    loss = float(m.train_step_device(feat, words, y).item())
+    assert abs(loss - loss_want) <= 5e-3 * abs(loss_want), (loss, loss_want)
+    got = m.get_gradients()
+    for n, want in G.items():
+        if not want.any():
+            assert not got[n].any(), n
+            continue
+        rel = _rel_l2(got[n], want)
+        cos = float((got[n].astype(np.float64) * want).sum() / (np.linalg.norm(got[n]) * np.linalg.norm(want)))
+        assert rel <= 4e-2 and cos >= 0.995, (n, rel, cos)
+    for n in got:
+        if n.startswith("mrcnn_class"):
+            assert not got[n].any(), n                           # trainable=False in the reference
+    # one-hot targets == ids; an all-zero target row is ignored and the mean runs over the others
+    onehot = np.zeros((B, V), np.float32)
+    onehot[np.arange(B), y] = 1.0
+    assert abs(m.test_on_batch([feat, words], onehot) - loss) <= 1e-6 * abs(loss) + 1e-7
+    onehot[3] = 0.0
+    keep = np.arange(B) != 3
+    lw, _ = dec.train_loss_and_grads_v2(feat[keep], words[keep], y[keep], w)
+    assert abs(m.test_on_batch([feat, words], onehot) - lw) <= 5e-3 * abs(lw)
+    # optimisation: the frozen head does not move, the loss falls
+    head_before = m.get_weights_dict()["mrcnn_class_conv1/kernel"].copy()
+    first = m.train_on_batch([feat, words], y)
+
+    def gen():
+        while True:
+            yield [feat, words], y
+    hist = m.fit_generator(gen(), steps_per_epoch=8, epochs=2, verbose=0, validation_data=([feat, words], y))
+    assert hist.history["loss"][-1] < first and hist.history["val_loss"][-1] < first
+    assert np.array_equal(m.get_weights_dict()["mrcnn_class_conv1/kernel"], head_before)
+    # inference on the same handle sees the updated weights
+    p = m.predict([feat, words])
+    assert p.shape == (B, V) and abs(float(-np.log(p[np.arange(B), y]).mean()) - hist.history["val_loss"][-1]) < 0.25
