@@ -60,7 +60,7 @@ __global__ void interleave_bias_kernel(const float *__restrict__ src, int units,
     if (n < 4 * units) dst[n] = src[(n & 3) * units + (n >> 2)];
 }
 
-static int build_kmajor(const float *src, int n_src, int row_off, int K, int N, int interleave_units,
+int build_kmajor(const float *src, int n_src, int row_off, int K, int N, int interleave_units,
                         __nv_bfloat16 *dst, long long ld_dst, int k_off, cudaStream_t s) {
     const dim3 grid(ceil_div(K, 32), ceil_div(N, 32)), block(32, 8);
     build_kmajor_kernel<<<grid, block, 0, s>>>(src, n_src, row_off, K, N, interleave_units, dst, ld_dst, k_off);

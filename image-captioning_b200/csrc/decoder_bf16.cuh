@@ -41,6 +41,10 @@ struct Bf16State {
     TrainState *train = nullptr;
 };
 
+// dst[n, k_off + k] = bf16(src[(row_off + k) * n_src + colmap(n)]): a Keras [in, out] kernel re-laid as a K-major [N, K] TMA operand
+int build_kmajor(const float *src, int n_src, int row_off, int K, int N, int interleave_units, __nv_bfloat16 *dst,
+                 long long ld_dst, int k_off, cudaStream_t s);
+
 inline TcOperand tc_op(const __nv_bfloat16 *p, long long ld, bool mn_major = false) {
     TcOperand o;
     o.ptr = p; o.ld = ld; o.mn_major = mn_major;

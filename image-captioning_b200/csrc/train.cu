@@ -18,10 +18,10 @@
 // fused softmax / cross-entropy kernel takes integer targets and overwrites the logits' role with
 // dlogits in bf16.
 //
-// Deviation: recurrent_dropout is not applied (the reference draws a fresh
-// per-gate mask per prefix position through TimeDistributed's K.rnn branch, which a single scan
-// cannot reproduce and TF's RNG stream could not be matched anyway); parity is defined with
-// dropout off.
+// recurrent_dropout=0.2 of the reference's two LSTMs (text_generation_model.py:141-142) is available through
+// dc_decoder_train_step_ex (DcTrainOptions): per-gate, time-invariant masks from a counter-based Philox generator --
+// see "recurrent dropout" below.  It is OFF by default: parity with the oracle is defined on the deterministic graph,
+// and TF's own RNG stream cannot be reproduced (the oracle draws the identical Philox masks instead).
 #include "decoder.cuh"
 #include "decoder_bf16.cuh"
 #include "gemm_tc.cuh"
@@ -59,6 +59,14 @@ struct TrainState {
     cudaStream_t side = nullptr;
     std::vector<cudaEvent_t> step_ev;                              // [T] chain A -> chain B hand-over per time step
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    // recurrent dropout (DcTrainOptions::recurrent_dropout > 0): K-stacked operands, see dropout_* below
+    int do_B = 0, do_T = 0;
+    std::vector<void *> do_owned;
+    __nv_bfloat16 *do_X1 = nullptr, *do_X2 = nullptr;               // [(T+1), B, Epad+4U], [(T+1), B, 5U]
+    __nv_bfloat16 *do_H1 = nullptr, *do_H2 = nullptr;               // [(T+1), B, U] plain h (slot 0 = zero state)
+    __nv_bfloat16 *do_w1 = nullptr, *do_w2 = nullptr;               // forward: [4U, Epad+4U], [4U, 5U] gate-interleaved rows
+    __nv_bfloat16 *do_u1k = nullptr, *do_w2k = nullptr;             // backward: [4U, 4U], [5U, 4U] block rows, Keras columns
+    float *do_dx = nullptr;                                         // [B, 5U] per-gate data gradients before the masked fold
     // v2 inject model (train_step_v2): word LSTM over L steps, one image-LSTM step, Dense(V)
     int v2_B = 0, v2_L = 0;
     std::vector<void *> v2_owned;
@@ -79,6 +87,7 @@ void Decoder::free_train() {
     if (bf && bf->train) {
         for (void *p : bf->train->owned) cudaFree(p);
         for (void *p : bf->train->v2_owned) cudaFree(p);
+        for (void *p : bf->train->do_owned) cudaFree(p);
         for (cudaEvent_t e : bf->train->bucket_ev)
             if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : bf->train->step_ev)
@@ -475,6 +484,143 @@ __global__ void adam_amsgrad_kernel(float *__restrict__ p, const float *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// recurrent dropout (KL.LSTM(..., recurrent_dropout=0.2), text_generation_model.py:141-142; a10)
+//
+// Keras draws four masks per LSTM call (one per gate, constant over time) and multiplies h_{t-1} by mask g before the
+// recurrent product of gate g.  Four differently masked copies of h would break the "one GEMM per LSTM" stacking, so the
+// masked copies are STACKED ALONG K instead: A = [x | h*m_i | h*m_f | h*m_c | h*m_o] against a weight whose recurrent
+// part is block-diagonal over the gates (row 4u+g only sees block g).  The fused cell epilogue, the gate-interleaved
+// layout and the tcgen05 kernels are untouched; the recurrent K grows 4x (only in this mode), and three small kernels
+// do the rest: expand (h -> 4 masked copies), fold (sum_g m_g * dX_g) and the block-structured weight builders.
+// Masks: Philox-4x32-10, key = seed, counter = (global row, unit, layer, step) -> four words = four gates; stateless,
+// identical for any sharding of the batch; the oracle draws the same ones (oracle/decoder.py: philox_masks).
+// ------------------------------------------------------------------------------------------------
+struct DropoutCtx {
+    float rate, scale;            // scale = 1/(1-rate)
+    unsigned k0, k1, step, thr;   // keep iff word >= thr = rate * 2^32
+    long long row_offset;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, unsigned k0, unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ void dropout_masks4(const DropoutCtx &d, int layer, long long row, int unit, float (&m)[4]) {
+    const unsigned long long gr = (unsigned long long)(row + d.row_offset);
+    const uint4 w = philox4x32_10(make_uint4((unsigned)gr, (unsigned)unit, (unsigned)(gr >> 32) | ((unsigned)layer << 16), d.step), d.k0, d.k1);
+    m[0] = w.x >= d.thr ? d.scale : 0.f; m[1] = w.y >= d.thr ? d.scale : 0.f;
+    m[2] = w.z >= d.thr ? d.scale : 0.f; m[3] = w.w >= d.thr ? d.scale : 0.f;
+}
+
+// out[b, g*U + u] = bf16(h[b, u] * m_g(b, u))
+__global__ void dropout_expand_kernel(const __nv_bfloat16 *__restrict__ h, long long ld_h, int B, int U, int layer, DropoutCtx d,
+                                      __nv_bfloat16 *__restrict__ out, long long ld_out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * U) return;
+    const int b = (int)(idx / U), u = (int)(idx - (long long)b * U);
+    float m[4];
+    dropout_masks4(d, layer, b, u, m);
+    const float v = __bfloat162float(h[(long long)b * ld_h + u]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) out[(long long)b * ld_out + (long long)g * U + u] = __float2bfloat16_rn(v * m[g]);
+}
+
+// out[b, u] = sum_g m_g(b, u) * dx[b, g*U + u]; optional straight copy of `ncopy` leading columns of src_copy
+__global__ void dropout_fold_kernel(const float *__restrict__ dx, long long ld_dx, int B, int U, int layer, DropoutCtx d,
+                                    float *__restrict__ out, long long ld_out, const float *__restrict__ src_copy, int ncopy,
+                                    float *__restrict__ dst_copy) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * U) return;
+    const int b = (int)(idx / U), u = (int)(idx - (long long)b * U);
+    float m[4];
+    dropout_masks4(d, layer, b, u, m);
+    float acc = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) acc += m[g] * dx[(long long)b * ld_dx + (long long)g * U + u];
+    out[(long long)b * ld_out + u] = acc;
+    if (src_copy && u < ncopy) dst_copy[(long long)b * ld_out + u] = src_copy[(long long)b * ld_dx + u];
+}
+
+// forward operand: dst[(4u+g), k_off + g*U + k] = bf16(R[k, g*U + u])   (R = Keras recurrent kernel [U, 4U]; rest pre-zeroed)
+__global__ void dropout_build_fwd_kernel(const float *__restrict__ R, int U, __nv_bfloat16 *__restrict__ dst, long long ld, int k_off) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)U * 4 * U) return;
+    const int k = (int)(idx / (4 * U)), col = (int)(idx - (long long)k * 4 * U), g = col / U, u = col - g * U;
+    dst[(long long)(4 * u + g) * ld + k_off + (long long)g * U + k] = __float2bfloat16_rn(R[idx]);
+}
+
+// backward operand (B of dX = dz * W^T, [N = in, K = out] K-major): dst[(row_off + g*U + k), g*U + u] = bf16(R[k, g*U + u])
+__global__ void dropout_build_bwd_kernel(const float *__restrict__ R, int U, __nv_bfloat16 *__restrict__ dst, int row_off) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)U * 4 * U) return;
+    const int k = (int)(idx / (4 * U)), col = (int)(idx - (long long)k * 4 * U), g = col / U;
+    dst[(long long)(row_off + g * U + k) * 4 * U + col] = __float2bfloat16_rn(R[idx]);
+}
+
+static DropoutCtx dropout_ctx(const DcTrainOptions *o) {
+    DropoutCtx d;
+    d.rate = o->recurrent_dropout; d.scale = 1.0f / (1.0f - d.rate);
+    d.k0 = (unsigned)(o->dropout_seed & 0xffffffffull); d.k1 = (unsigned)(o->dropout_seed >> 32);
+    d.step = (unsigned)((unsigned long long)o->dropout_step & 0xffffffffull);
+    d.thr = (unsigned)((double)d.rate * 4294967296.0);
+    d.row_offset = o->row_offset;
+    return d;
+}
+
+static int dropout_reserve(Decoder &D, int B, int T) {
+    Bf16State &b = *D.bf;
+    TrainState &t = *b.train;
+    if (t.do_B >= B && t.do_T >= T) return DC_OK;
+    for (void *p : t.do_owned) cudaFree(p);
+    t.do_owned.clear();
+    const size_t U = D.cfg.units, K1d = b.Epad + 4 * U, Bp = round_up(B, 128), R = (size_t)(T + 1) * Bp;
+    auto A = [&](void **p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess) return set_error(DC_ERR_CUDA, "dropout workspace allocation failed: %s", cudaGetErrorString(e));
+        t.do_owned.push_back(*p);
+        return DC_OK;
+    };
+    int rc = 0;
+    rc |= A((void **)&t.do_X1, 2 * R * K1d); rc |= A((void **)&t.do_X2, 2 * R * 5 * U);
+    rc |= A((void **)&t.do_H1, 2 * R * U); rc |= A((void **)&t.do_H2, 2 * R * U);
+    rc |= A((void **)&t.do_w1, 2 * 4 * U * K1d); rc |= A((void **)&t.do_w2, 2 * 4 * U * 5 * U);
+    rc |= A((void **)&t.do_u1k, 2 * 4 * U * 4 * U); rc |= A((void **)&t.do_w2k, 2 * 5 * U * 4 * U);
+    rc |= A((void **)&t.do_dx, 4 * Bp * 5 * U);
+    if (rc) { t.do_B = t.do_T = 0; return rc; }
+    t.do_B = B; t.do_T = T;
+    return DC_OK;
+}
+
+// the block-structured weights follow the master weights: rebuilt at every step of this mode (16 MB of writes)
+static int dropout_build_weights(Decoder &D, cudaStream_t s) {
+    Bf16State &b = *D.bf;
+    TrainState &t = *b.train;
+    const int U = D.cfg.units, E = D.cfg.embed, K1d = b.Epad + 4 * U;
+    DC_CHECK_CUDA(cudaMemsetAsync(t.do_w1, 0, 2 * (size_t)4 * U * K1d, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(t.do_w2, 0, 2 * (size_t)4 * U * 5 * U, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(t.do_u1k, 0, 2 * (size_t)4 * U * 4 * U, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(t.do_w2k, 0, 2 * (size_t)5 * U * 4 * U, s));
+    if (int rc = build_kmajor(D.W("imgcap_lstm1/kernel"), 4 * U, 0, E, 4 * U, U, t.do_w1, K1d, 0, s)) return rc;
+    if (int rc = build_kmajor(D.W("imgcap_lstm2/kernel"), 4 * U, 0, U, 4 * U, U, t.do_w2, 5 * U, 0, s)) return rc;
+    const unsigned grid = (unsigned)ceil_div<long long>((long long)U * 4 * U, 256);
+    dropout_build_fwd_kernel<<<grid, 256, 0, s>>>(D.W("imgcap_lstm1/recurrent_kernel"), U, t.do_w1, K1d, b.Epad);
+    dropout_build_fwd_kernel<<<grid, 256, 0, s>>>(D.W("imgcap_lstm2/recurrent_kernel"), U, t.do_w2, 5 * U, U);
+    dropout_build_bwd_kernel<<<grid, 256, 0, s>>>(D.W("imgcap_lstm1/recurrent_kernel"), U, t.do_u1k, 0);
+    dropout_build_bwd_kernel<<<grid, 256, 0, s>>>(D.W("imgcap_lstm2/recurrent_kernel"), U, t.do_w2k, U);
+    DC_CHECK_LAUNCH();
+    // rows [0, U) of the layer-2 backward operand = the input kernel W2 [U, 4U] as it lies in the bf16 arena mirror
+    DC_CHECK_CUDA(cudaMemcpyAsync(t.do_w2k, b.w2cat_k, 2 * (size_t)U * 4 * U, cudaMemcpyDeviceToDevice, s));
+    return DC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // the step
 // ------------------------------------------------------------------------------------------------
 // Teacher-forced forward up to the logits [T*B, V] (time-major) with every activation the backward needs.
@@ -506,32 +652,57 @@ int Decoder::train_forward(const void *feats, int kind, int B, const int32_t *gt
     if (int rc = head(train_head ? (const void *)x0 : feats, train_head ? DC_FEATS_ROI_BF16 : kind, B, ws.F, s)) return rc;
     if (int rc = v1_hoist_bf16(B, s)) return rc;                       // ws.g1f (gate-interleaved, + b1), ws.d1f (+ bd1)
 
+    // recurrent dropout: K-stacked operands (see dropout_* above); off in parity mode and for predict()
+    const bool dropout = train_opts && train_opts->recurrent_dropout > 0.f;
+    DropoutCtx dctx{};
+    if (dropout) {
+        if (int rc = dropout_reserve(*this, B, T)) return rc;
+        if (int rc = refresh_train_weights(s)) return rc;                 // w2cat_k feeds the layer-2 backward operand
+        if (int rc = dropout_build_weights(*this, s)) return rc;
+        dctx = dropout_ctx(train_opts);
+    }
+    const int K1x = dropout ? b.Epad + 4 * U : K1, K2x = dropout ? 5 * U : 2 * U;
+    __nv_bfloat16 *X1b = dropout ? t.do_X1 : t.X1, *X2b = dropout ? t.do_X2 : t.X2;
+    const __nv_bfloat16 *W1op = dropout ? t.do_w1 : b.w1cat, *W2op = dropout ? t.do_w2 : b.w2cat;
     // slot 0 of the state buffers = zero state; embedding rows of every (t, b) gathered at once
-    DC_CHECK_CUDA(cudaMemsetAsync(t.X1, 0, 2 * (size_t)B * K1, s));
-    DC_CHECK_CUDA(cudaMemsetAsync(t.X2, 0, 2 * (size_t)B * 2 * U, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(X1b, 0, 2 * (size_t)B * K1x, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(X2b, 0, 2 * (size_t)B * K2x, s));
+    if (dropout) {
+        DC_CHECK_CUDA(cudaMemsetAsync(t.do_H1, 0, 2 * (size_t)B * U, s));
+        DC_CHECK_CUDA(cudaMemsetAsync(t.do_H2, 0, 2 * (size_t)B * U, s));
+    }
     DC_CHECK_CUDA(cudaMemsetAsync(t.c1, 0, 4 * (size_t)B * U, s));
     DC_CHECK_CUDA(cudaMemsetAsync(t.c2, 0, 4 * (size_t)B * U, s));
     gather_embedding_rows_kernel<<<(unsigned)ceil_div<long long>(R * 32, 256), 256, 0, s>>>(
-        reinterpret_cast<const uint4 *>(b.emb), b.Epad / 8, t.tok_tm, R, reinterpret_cast<uint4 *>(t.X1), K1 / 8);
+        reinterpret_cast<const uint4 *>(b.emb), b.Epad / 8, t.tok_tm, R, reinterpret_cast<uint4 *>(X1b), K1x / 8);
     DC_CHECK_LAUNCH();
     // Wavefront: LSTM1 of step t+1 needs only LSTM1 of step t (the tokens are given), LSTM2 of step t needs LSTM1 of
     // step t and LSTM2 of step t-1.  Chain A (LSTM1) runs on `s`, chain B (LSTM2) on the side stream one step behind;
     // their persistent GEMMs interleave at CTA granularity and fill each other's tails (a single chain of these
     // 1.7-wave launches leaves most SMs idle most of the time).
-    static const bool no_wave = getenv("DCAP_NO_WAVEFRONT") != nullptr;
+    static const bool env_no_wave = getenv("DCAP_NO_WAVEFRONT") != nullptr;
+    const bool no_wave = env_no_wave || dropout;
     cudaStream_t s2 = no_wave ? s : t.side;
+    const unsigned ex_grid = (unsigned)ceil_div<long long>((long long)B * U, 256);
     for (int st = 0; st < T; ++st) {
-        __nv_bfloat16 *x1 = t.X1 + (size_t)st * B * K1, *x1n = x1 + (size_t)B * K1;
-        __nv_bfloat16 *x2 = t.X2 + (size_t)st * B * 2 * U, *x2n = x2 + (size_t)B * 2 * U;
+        __nv_bfloat16 *x1 = X1b + (size_t)st * B * K1x, *x1n = x1 + (size_t)B * K1x;
+        __nv_bfloat16 *x2 = X2b + (size_t)st * B * K2x, *x2n = x2 + (size_t)B * K2x;
+        __nv_bfloat16 *h1p = dropout ? t.do_H1 + (size_t)st * B * U : x1 + b.Epad, *h1n = dropout ? h1p + (size_t)B * U : x1n + b.Epad;
+        __nv_bfloat16 *h2p = dropout ? t.do_H2 + (size_t)st * B * U : x2 + U, *h2n = dropout ? h2p + (size_t)B * U : x2n + U;
+        const int ldh1 = dropout ? U : K1, ldh2 = dropout ? U : 2 * U;
         const int32_t *tok = t.tok_tm + (size_t)st * B;
         TcEpilogue c1;
         c1.addend = ws.g1f; c1.ld_addend = 4 * U; c1.cell_units = U; c1.cell_tok = tok;
         c1.cell_c = t.c1 + (size_t)st * B * U; c1.cell_c_out = t.c1 + (size_t)(st + 1) * B * U;
-        c1.cell_h_prev = x1 + b.Epad; c1.ld_h_prev = K1;
-        c1.cell_h_a = x1n + b.Epad; c1.ld_h_a = K1;
-        c1.cell_h_b = x2; c1.ld_h_b = 2 * U;
+        c1.cell_h_prev = h1p; c1.ld_h_prev = ldh1;
+        c1.cell_h_a = h1n; c1.ld_h_a = ldh1;
+        c1.cell_h_b = x2; c1.ld_h_b = K2x;
         c1.cell_gates_out = t.gates1 + (size_t)st * B * 4 * U; c1.ld_gates_out = 4 * U;
-        if (int rc = gemm_bf16_tc(tc_op(x1, K1), tc_op(b.w1cat, K1), c1, B, 4 * U, K1, kEpiCell, s)) return rc;
+        if (int rc = gemm_bf16_tc(tc_op(x1, K1x), tc_op(W1op, K1x), c1, B, 4 * U, K1x, kEpiCell, s)) return rc;
+        if (dropout) {
+            dropout_expand_kernel<<<ex_grid, 256, 0, s>>>(h1n, U, B, U, 1, dctx, x1n + b.Epad, K1x);
+            DC_CHECK_LAUNCH();
+        }
         if (!no_wave) {
             DC_CHECK_CUDA(cudaEventRecord(t.step_ev[st], s));
             DC_CHECK_CUDA(cudaStreamWaitEvent(s2, t.step_ev[st], 0));
@@ -539,21 +710,26 @@ int Decoder::train_forward(const void *feats, int kind, int B, const int32_t *gt
         TcEpilogue c2;
         c2.bias = b.b2_i; c2.cell_units = U; c2.cell_tok = tok;
         c2.cell_c = t.c2 + (size_t)st * B * U; c2.cell_c_out = t.c2 + (size_t)(st + 1) * B * U;
-        c2.cell_h_prev = x2 + U; c2.ld_h_prev = 2 * U;
-        c2.cell_h_a = x2n + U; c2.ld_h_a = 2 * U;
+        c2.cell_h_prev = h2p; c2.ld_h_prev = ldh2;
+        c2.cell_h_a = h2n; c2.ld_h_a = ldh2;
         c2.cell_gates_out = t.gates2 + (size_t)st * B * 4 * U; c2.ld_gates_out = 4 * U;
-        if (int rc = gemm_bf16_tc(tc_op(x2, 2 * U), tc_op(b.w2cat, 2 * U), c2, B, 4 * U, 2 * U, kEpiCell, s2)) return rc;
+        if (int rc = gemm_bf16_tc(tc_op(x2, K2x), tc_op(W2op, K2x), c2, B, 4 * U, K2x, kEpiCell, s2)) return rc;
+        if (dropout) {
+            dropout_expand_kernel<<<ex_grid, 256, 0, s2>>>(h2n, U, B, U, 2, dctx, x2n + U, K2x);
+            DC_CHECK_LAUNCH();
+        }
     }
     if (!no_wave) {
         DC_CHECK_CUDA(cudaEventRecord(t.join_ev, s2));
         DC_CHECK_CUDA(cudaStreamWaitEvent(s, t.join_ev, 0));
     }
-    // h2_t of row (t, b) lives in X2 slot t+1, columns U..2U: one strided view over all T*B rows
-    const __nv_bfloat16 *h2_all = t.X2 + (size_t)B * 2 * U + U;
+    // h2_t of row (t, b): slot t+1 of the state buffer -- one strided view over all T*B rows
+    const __nv_bfloat16 *h2_all = dropout ? t.do_H2 + (size_t)B * U : t.X2 + (size_t)B * 2 * U + U;
+    const int ld_h2 = dropout ? U : 2 * U;
     {
         TcEpilogue e;
         e.addend = ws.d1f; e.ld_addend = kDense; e.addend_mod = B; e.relu = 1; e.out_bf16 = t.d_all; e.ld_bf16 = kDense;
-        if (int rc = gemm_bf16_tc(tc_op(h2_all, 2 * U), tc_op(b.wd1h, U), e, (int)R, kDense, U, kEpiStore, s)) return rc;
+        if (int rc = gemm_bf16_tc(tc_op(h2_all, ld_h2), tc_op(b.wd1h, U), e, (int)R, kDense, U, kEpiStore, s)) return rc;
         TcEpilogue v;
         v.bias = W("imgcap_lstm_d2/bias"); v.out_f32 = t.logits; v.ld_f32 = V;
         if (int rc = gemm_bf16_tc(tc_op(t.d_all, kDense), tc_op(b.wd2, kDense), v, (int)R, V, kDense, kEpiStore, s)) return rc;
@@ -577,7 +753,12 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     if (inv_count <= 0.f) inv_count = 1.0f / (float)R;
     const bool train_head = kind != DC_FEATS_HEAD_F32;
     const __nv_bfloat16 *x0 = t.x0_used;
-    const __nv_bfloat16 *h2_all = t.X2 + (size_t)B * 2 * U + U;
+    const bool dropout = train_opts && train_opts->recurrent_dropout > 0.f;
+    const DropoutCtx dctx = dropout ? dropout_ctx(train_opts) : DropoutCtx{};
+    const __nv_bfloat16 *h2_all = dropout ? t.do_H2 + (size_t)B * U : t.X2 + (size_t)B * 2 * U + U;
+    const int ld_h2 = dropout ? U : 2 * U;
+    const int K1x = dropout ? b.Epad + 4 * U : K1, K2x = dropout ? 5 * U : 2 * U;
+    const __nv_bfloat16 *X1b = dropout ? t.do_X1 : t.X1, *X2b = dropout ? t.do_X2 : t.X2;
     auto G = [&](const char *name) { return grads + find(name)->offset; };
     DC_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n_train, s));
 
@@ -609,7 +790,7 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
                                                                                              t.ddsum_b);
     DC_CHECK_LAUNCH();
     // dense1: rows [0,U) of the kernel see h2_t, rows [U, U+F) the (time-constant) RoI feature
-    if (int rc = wgrad(h2_all, 2 * U, U, t.dd, kDense, kDense, R, G("imgcap_lstm_d1/kernel"), kDense)) return rc;
+    if (int rc = wgrad(h2_all, ld_h2, U, t.dd, kDense, kDense, R, G("imgcap_lstm_d1/kernel"), kDense)) return rc;
     if (int rc = wgrad(b.Fb, F, F, t.ddsum_b, kDense, kDense, B, G("imgcap_lstm_d1/kernel") + (size_t)U * kDense, kDense)) return rc;
     if (int rc = colsum(t.ddsum, B, kDense, kDense, G("imgcap_lstm_d1/bias"), s)) return rc;
     DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[1], s));                 // bucket 1: dense1
@@ -626,8 +807,10 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     for (float *p : {t.carry1, t.carry2, t.dc1, t.dc2})
         DC_CHECK_CUDA(cudaMemsetAsync(p, 0, 4 * (size_t)B * U, s));
     DC_CHECK_CUDA(cudaMemsetAsync(t.dz1sum, 0, 4 * (size_t)B * 4 * U, s));
-    static const bool no_wave = getenv("DCAP_NO_WAVEFRONT") != nullptr;
+    static const bool env_no_wave = getenv("DCAP_NO_WAVEFRONT") != nullptr;
+    const bool no_wave = env_no_wave || dropout;
     cudaStream_t s2 = no_wave ? s : t.side;
+    const unsigned fold_grid = (unsigned)ceil_div<long long>((long long)B * U, 256);
     if (!no_wave) {
         DC_CHECK_CUDA(cudaEventRecord(t.fork_ev, s));                  // dh2d, zeroed carries are ready
         DC_CHECK_CUDA(cudaStreamWaitEvent(s2, t.fork_ev, 0));
@@ -643,10 +826,16 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
                                  (const float *)(t.c2 + (size_t)(st + 1) * B * U), tok, (const float *)(t.dh2d + (size_t)st * B * U), U,
                                  (const float *)(last ? nullptr : dx + (size_t)B * 2 * U + U), 2 * U, t.carry2, t.dc2, dz2,
                                  (float *)nullptr));
-        {   // [dh1_t | dh2_{t-1}] = dz2 [W2 ; U2]^T
+        if (!dropout) {   // [dh1_t | dh2_{t-1}] = dz2 [W2 ; U2]^T
             TcEpilogue e;
             e.out_f32 = dx; e.ld_f32 = 2 * U;
             if (int rc = gemm_bf16_tc(tc_op(dz2, 4 * U), tc_op(b.w2cat_k, 4 * U), e, B, 2 * U, 4 * U, kEpiStore, s2)) return rc;
+        } else {          // [dh1_t | d(h2*m_i) | d(h2*m_f) | d(h2*m_c) | d(h2*m_o)], then dh2_{t-1} = sum_g m_g * d(h2*m_g)
+            TcEpilogue e;
+            e.out_f32 = t.do_dx; e.ld_f32 = 5 * U;
+            if (int rc = gemm_bf16_tc(tc_op(dz2, 4 * U), tc_op(t.do_w2k, 4 * U), e, B, 5 * U, 4 * U, kEpiStore, s2)) return rc;
+            dropout_fold_kernel<<<fold_grid, 256, 0, s2>>>(t.do_dx + U, 5 * U, B, U, 2, dctx, dx + U, 2 * U, t.do_dx, U, dx);
+            DC_CHECK_LAUNCH();
         }
         if (!no_wave) DC_CHECK_CUDA(cudaEventRecord(t.step_ev[st], s2));
     }
@@ -660,10 +849,16 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
                                  (const __nv_bfloat16 *)(t.gates1 + (size_t)st * B * 4 * U), (const float *)(t.c1 + (size_t)st * B * U),
                                  (const float *)(t.c1 + (size_t)(st + 1) * B * U), tok, dx, 2 * U,
                                  (const float *)(last ? nullptr : t.dh1p), U, t.carry1, t.dc1, dz1, t.dz1sum));
-        if (st > 0) {   // dh1_{t-1} = dz1 U1^T
+        if (st > 0 && !dropout) {   // dh1_{t-1} = dz1 U1^T
             TcEpilogue e;
             e.out_f32 = t.dh1p; e.ld_f32 = U;
             if (int rc = gemm_bf16_tc(tc_op(dz1, 4 * U), tc_op(b.u1_k, 4 * U), e, B, U, 4 * U, kEpiStore, s)) return rc;
+        } else if (st > 0) {
+            TcEpilogue e;
+            e.out_f32 = t.do_dx; e.ld_f32 = 4 * U;
+            if (int rc = gemm_bf16_tc(tc_op(dz1, 4 * U), tc_op(t.do_u1k, 4 * U), e, B, 4 * U, 4 * U, kEpiStore, s)) return rc;
+            dropout_fold_kernel<<<fold_grid, 256, 0, s>>>(t.do_dx, 4 * U, B, U, 1, dctx, t.dh1p, U, nullptr, 0, nullptr);
+            DC_CHECK_LAUNCH();
         }
     }
     f32_to_bf16_rows_kernel<<<(unsigned)ceil_div<long long>((long long)B * 4 * U, 256), 256, 0, s>>>(t.dz1sum, (long long)B * 4 * U,
@@ -672,11 +867,24 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
 
     // ---------------- backward: LSTM weight gradients (one GEMM over all T*B rows each) ----------------
     // [dW2 ; dU2] = [h1_t | h2_{t-1}]^T dz2  (kernel and recurrent_kernel gradients are adjacent)
-    if (int rc = wgrad(t.X2, 2 * U, 2 * U, t.dz2_all, 4 * U, 4 * U, R, G("imgcap_lstm2/kernel"), 4 * U)) return rc;
+    if (!dropout) {
+        if (int rc = wgrad(t.X2, 2 * U, 2 * U, t.dz2_all, 4 * U, 4 * U, R, G("imgcap_lstm2/kernel"), 4 * U)) return rc;
+    } else {              // dW2 = h1^T dz2; dU2[:, gate g] = (h2*m_g)^T dz2[:, gate g]
+        if (int rc = wgrad(X2b, K2x, U, t.dz2_all, 4 * U, 4 * U, R, G("imgcap_lstm2/kernel"), 4 * U)) return rc;
+        for (int g = 0; g < 4; ++g)
+            if (int rc = wgrad(X2b + U + (size_t)g * U, K2x, U, t.dz2_all + (size_t)g * U, 4 * U, U, R,
+                               G("imgcap_lstm2/recurrent_kernel") + (size_t)g * U, 4 * U)) return rc;
+    }
     if (int rc = colsum(t.dz2_all, R, 4 * U, 4 * U, G("imgcap_lstm2/bias"), s)) return rc;
     // dW1[:E] = emb_t^T dz1 ; dU1 = h1_{t-1}^T dz1 ; dW1[E:] = f^T sum_t dz1
-    if (int rc = wgrad(t.X1, K1, E, t.dz1_all, 4 * U, 4 * U, R, G("imgcap_lstm1/kernel"), 4 * U)) return rc;
-    if (int rc = wgrad(t.X1 + b.Epad, K1, U, t.dz1_all, 4 * U, 4 * U, R, G("imgcap_lstm1/recurrent_kernel"), 4 * U)) return rc;
+    if (int rc = wgrad(X1b, K1x, E, t.dz1_all, 4 * U, 4 * U, R, G("imgcap_lstm1/kernel"), 4 * U)) return rc;
+    if (!dropout) {
+        if (int rc = wgrad(t.X1 + b.Epad, K1, U, t.dz1_all, 4 * U, 4 * U, R, G("imgcap_lstm1/recurrent_kernel"), 4 * U)) return rc;
+    } else {
+        for (int g = 0; g < 4; ++g)
+            if (int rc = wgrad(X1b + b.Epad + (size_t)g * U, K1x, U, t.dz1_all + (size_t)g * U, 4 * U, U, R,
+                               G("imgcap_lstm1/recurrent_kernel") + (size_t)g * U, 4 * U)) return rc;
+    }
     if (int rc = wgrad(b.Fb, F, F, t.dz1sum_b, 4 * U, 4 * U, B, G("imgcap_lstm1/kernel") + (size_t)E * 4 * U, 4 * U)) return rc;
     if (int rc = colsum(t.dz1sum, B, 4 * U, 4 * U, G("imgcap_lstm1/bias"), s)) return rc;
     DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[2], s));                 // bucket 2: both LSTMs
@@ -963,7 +1171,6 @@ extern "C" int dc_decoder_train_step_ex(DcDecoder *dec, const void *feats, int f
     DC_REQUIRE(dec, "null decoder");
     if (opts) {
         DC_REQUIRE(opts->recurrent_dropout >= 0.f && opts->recurrent_dropout < 1.f, "recurrent_dropout must be in [0, 1)");
-        DC_REQUIRE(opts->recurrent_dropout == 0.f, "recurrent_dropout is not available in this build");
     }
     dec->impl.train_opts = opts;
     const int rc = dec->impl.train_step(feats, feats_kind, B, gt, targets, inv_count, loss, (cudaStream_t)stream);

@@ -83,10 +83,12 @@ class DataParallelTrainer(object):
             n = float((t.sum(-1) > 0).sum()) if t.dim() == 3 else float((t >= 0).sum())
         return torch.tensor([n], dtype=torch.float64)
 
-    def train_step(self, features, gt, targets=None, global_positions=None):
+    def train_step(self, features, gt, targets=None, global_positions=None, **step_options):
         """Local forward/backward + gradient all-reduce + update.  Returns the GLOBAL mean loss as a
         device scalar (no host sync).  ``global_positions``: number of loss positions over all
-        ranks; derived with one tiny all-reduce if not given."""
+        ranks; derived with one tiny all-reduce if not given.  ``step_options`` go to
+        ``model.train_step_device`` (recurrent_dropout / dropout_seed / dropout_step / row_offset: pass this rank's
+        first global row as row_offset and the masks equal those of the unsharded batch)."""
         if global_positions is None:
             cnt = self._count_positions(gt, targets)
             if self.world > 1:
@@ -96,7 +98,7 @@ class DataParallelTrainer(object):
             global_positions = float(cnt.item())
         if global_positions <= 0:
             return torch.zeros(())
-        loss = self.model.train_step_device(features, gt, targets, 1.0 / global_positions)
+        loss = self.model.train_step_device(features, gt, targets, 1.0 / global_positions, **step_options)
         if self.world > 1:
             g = self.model.grad_buffer()
             if self.overlap and hasattr(self.model, "wait_grad_bucket"):

@@ -249,14 +249,58 @@ def keras_adam_amsgrad(p, g, m, v, vhat, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7)
 
 
 # ----------------------------------------------------------------------------------------
+# recurrent dropout masks (a10): KL.LSTM(..., recurrent_dropout=0.2), text_generation_model.py:141-142
+# ----------------------------------------------------------------------------------------
+# Keras 2.1 LSTMCell (implementation=1) draws FOUR masks per call, K.dropout(ones([B, units]), rate) -- one per gate
+# i, f, c, o, values {0, 1/(1-rate)}, constant over the time steps of the call -- and multiplies h_{t-1} by mask g
+# before the recurrent product of gate g.  TF's RNG stream cannot be reproduced, so the product and this oracle
+# agree on a counter-based generator instead: Philox-4x32-10 (Salmon et al., SC'11; Random123 known-answer vectors in
+# tests/test_oracle_decoder.py), key = the 64-bit seed, counter = (global row, unit, layer, step); the four output
+# words decide the four gates: keep iff word >= rate * 2^32.
+
+PHILOX_M0, PHILOX_M1 = 0xD2511F53, 0xCD9E8D57
+PHILOX_W0, PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(counter, key):
+    """counter [..., 4] uint32, key (k0, k1) -> [..., 4] uint32."""
+    c = [np.asarray(counter[..., i], np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(PHILOX_M0) * c[0]
+        p1 = np.uint64(PHILOX_M1) * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c = [(hi1 ^ c[1] ^ k0) & mask, lo1, (hi0 ^ c[3] ^ k1) & mask, lo0]
+        k0 = (k0 + np.uint64(PHILOX_W0)) & mask
+        k1 = (k1 + np.uint64(PHILOX_W1)) & mask
+    return np.stack(c, -1).astype(np.uint32)
+
+
+def philox_masks(rate, seed, step, layer, rows, units, row_offset=0, dtype=np.float64):
+    """[rows, 4, units] recurrent-dropout masks of one LSTM (gate order i, f, c, o) for global rows
+    row_offset .. row_offset + rows - 1."""
+    r = (np.arange(rows, dtype=np.uint64) + np.uint64(row_offset))[:, None]
+    u = np.arange(units, dtype=np.uint64)[None, :]
+    ctr = np.stack(np.broadcast_arrays(r & np.uint64(0xFFFFFFFF), u, (r >> np.uint64(32)) | (np.uint64(layer) << np.uint64(16)),
+                                       np.uint64(step & 0xFFFFFFFF) + 0 * r), -1)
+    w = philox4x32_10(ctr, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))            # [rows, units, 4]
+    thr = np.uint64(int(rate * 4294967296.0))
+    keep = w.astype(np.uint64) >= thr
+    return np.where(keep, 1.0 / (1.0 - rate), 0.0).astype(dtype).transpose(0, 2, 1)
+
+
+# ----------------------------------------------------------------------------------------
 # fp64 reference gradients of the v1 training graph (used to check the CUDA backward)
 # ----------------------------------------------------------------------------------------
 
-def train_loss_and_grads_v1(feat, gt, w, train_head=True, return_dfeat=False):
+def train_loss_and_grads_v1(feat, gt, w, train_head=True, return_dfeat=False, rec_masks=None):
     """Loss (mean CE over all B*P positions, clipping ignored -- probabilities of random models
     stay far from 1e-7) and analytic gradients in fp64 by manual BPTT.  Returns (loss, grads), plus
     dL/d(feat) [B,pool,pool,C] with ``return_dfeat`` (the gradient the joint model sends back into
-    PyramidROIAlign, dense_img_cap/dense_model.py:738-755)."""
+    PyramidROIAlign, dense_img_cap/dense_model.py:738-755).  ``rec_masks`` = (m1, m2), each [B, 4, U]: the recurrent
+    dropout masks of the two LSTMs (philox_masks); None = dropout off."""
     D = np.float64
     B, P = gt.shape
     W = {k: v.astype(D) for k, v in w.items()}
@@ -282,8 +326,11 @@ def train_loss_and_grads_v1(feat, gt, w, train_head=True, return_dfeat=False):
     Kd2, bd2 = W["imgcap_lstm_d2/kernel"], W["imgcap_lstm_d2/bias"]
     emb = W["imgcap_embedding_layer/embeddings"]
 
-    def cell_fwd(x, h, c, K, R, b):
-        z = x @ K + b + h @ R
+    def cell_fwd(x, h, c, K, R, b, msk=None):
+        if msk is None:
+            z = x @ K + b + h @ R
+        else:
+            z = x @ K + b + np.concatenate([(h * msk[:, g]) @ R[:, g * U:(g + 1) * U] for g in range(4)], -1)
         zi, zf, zg, zo = z[:, :U], z[:, U:2 * U], z[:, 2 * U:3 * U], z[:, 3 * U:]
         i, fg, g, o = hard_sigmoid(zi), hard_sigmoid(zf), np.tanh(zg), hard_sigmoid(zo)
         cn = fg * c + i * g
@@ -296,9 +343,9 @@ def train_loss_and_grads_v1(feat, gt, w, train_head=True, return_dfeat=False):
     for t in range(P):
         m = (ids[:, t] != 0)[:, None]
         x1 = np.concatenate([emb[ids[:, t]], f], -1)
-        h1n, c1n, k1c = cell_fwd(x1, h1, c1, K1, R1, b1)
+        h1n, c1n, k1c = cell_fwd(x1, h1, c1, K1, R1, b1, rec_masks[0] if rec_masks else None)
         h1 = np.where(m, h1n, h1); c1 = np.where(m, c1n, c1)
-        h2n, c2n, k2c = cell_fwd(h1, h2, c2, K2, R2, b2)
+        h2n, c2n, k2c = cell_fwd(h1, h2, c2, K2, R2, b2, rec_masks[1] if rec_masks else None)
         h2 = np.where(m, h2n, h2); c2 = np.where(m, c2n, c2)
         din = np.concatenate([h2, f], -1)
         zd = din @ Kd1 + bd1
@@ -316,7 +363,7 @@ def train_loss_and_grads_v1(feat, gt, w, train_head=True, return_dfeat=False):
     def hs_grad(z):
         return np.where((z > -2.5) & (z < 2.5), 0.2, 0.0)
 
-    def cell_bwd(dh, dc, kc, K, R):
+    def cell_bwd(dh, dc, kc, K, R, msk=None):
         x, h, c, z, i, fg, g, o, tc = kc
         do = dh * tc
         dcn = dc + dh * o * (1 - tc * tc)
@@ -324,7 +371,11 @@ def train_loss_and_grads_v1(feat, gt, w, train_head=True, return_dfeat=False):
         dc_prev = dcn * fg
         dz = np.concatenate([di * hs_grad(z[:, :U]), dfg * hs_grad(z[:, U:2 * U]),
                              dg * (1 - g * g), do * hs_grad(z[:, 3 * U:])], -1)
-        return dz, dz @ K.T, dz @ R.T, dc_prev, x, h
+        if msk is None:
+            return dz, dz @ K.T, dz @ R.T, dc_prev, x, h, h.T @ dz
+        dhp = sum(msk[:, q] * (dz[:, q * U:(q + 1) * U] @ R[:, q * U:(q + 1) * U].T) for q in range(4))
+        dR = np.concatenate([(h * msk[:, q]).T @ dz[:, q * U:(q + 1) * U] for q in range(4)], -1)
+        return dz, dz @ K.T, dhp, dc_prev, x, h, dR
 
     for t in reversed(range(P)):
         m, k1c, k2c, din, zd, d, p = cache[t]
@@ -335,13 +386,13 @@ def train_loss_and_grads_v1(feat, gt, w, train_head=True, return_dfeat=False):
         ddin = dd @ Kd1.T
         dh2 = dh2 + ddin[:, :U]; df += ddin[:, U:]
         # layer 2 (masked rows carry their state gradient through untouched)
-        dzz, dx, dhp, dcp, x, h = cell_bwd(dh2 * m, dc2 * m, k2c, K2, R2)
-        G["imgcap_lstm2/kernel"] += x.T @ dzz; G["imgcap_lstm2/recurrent_kernel"] += h.T @ dzz
+        dzz, dx, dhp, dcp, x, h, dR = cell_bwd(dh2 * m, dc2 * m, k2c, K2, R2, rec_masks[1] if rec_masks else None)
+        G["imgcap_lstm2/kernel"] += x.T @ dzz; G["imgcap_lstm2/recurrent_kernel"] += dR
         G["imgcap_lstm2/bias"] += dzz.sum(0)
         dh1 = dh1 + dx
         dh2 = np.where(m, dhp, dh2); dc2 = np.where(m, dcp, dc2)
-        dzz, dx, dhp, dcp, x, h = cell_bwd(dh1 * m, dc1 * m, k1c, K1, R1)
-        G["imgcap_lstm1/kernel"] += x.T @ dzz; G["imgcap_lstm1/recurrent_kernel"] += h.T @ dzz
+        dzz, dx, dhp, dcp, x, h, dR = cell_bwd(dh1 * m, dc1 * m, k1c, K1, R1, rec_masks[0] if rec_masks else None)
+        G["imgcap_lstm1/kernel"] += x.T @ dzz; G["imgcap_lstm1/recurrent_kernel"] += dR
         G["imgcap_lstm1/bias"] += dzz.sum(0)
         df += dx[:, E:]
         dh1 = np.where(m, dhp, dh1); dc1 = np.where(m, dcp, dc1)

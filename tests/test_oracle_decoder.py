@@ -240,3 +240,44 @@ def test_v2_training_gradients_match_finite_differences():
             b = w[name].copy(); b[ix] -= 1e-6; wm[name] = b
             fd = (f(wp) - f(wm)) / 2e-6
             assert abs(fd - g[ix]) <= 1e-6 + 1e-4 * abs(fd), (name, ix, fd, g[ix])
+
+
+def test_philox_known_answers_and_mask_statistics():
+    """Random123 known-answer vectors for Philox-4x32-10 (kat_vectors: zero / all-ones / pi-digits inputs), then the
+    recurrent-dropout masks drawn from it: values {0, 1/(1-rate)}, keep rate ~ 1-rate, four different masks per LSTM,
+    independent of how the batch is cut into shards (row_offset)."""
+    z = np.zeros((1, 4), np.uint32)
+    assert [hex(v) for v in dec.philox4x32_10(z, (0, 0))[0]] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    f = np.full((1, 4), 0xFFFFFFFF, np.uint32)
+    assert [hex(v) for v in dec.philox4x32_10(f, (0xFFFFFFFF, 0xFFFFFFFF))[0]] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    pi = np.array([[0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344]], np.uint32)
+    assert [hex(v) for v in dec.philox4x32_10(pi, (0xA4093822, 0x299F31D0))[0]] == ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+    m = dec.philox_masks(0.2, seed=1234, step=7, layer=1, rows=512, units=64)
+    assert m.shape == (512, 4, 64) and set(np.unique(m)) == {0.0, 1.25}
+    assert abs((m > 0).mean() - 0.8) < 0.01
+    assert not np.array_equal(m[:, 0], m[:, 1]) and not np.array_equal(m, dec.philox_masks(0.2, 1234, 8, 1, 512, 64))
+    assert not np.array_equal(m, dec.philox_masks(0.2, 1234, 7, 2, 512, 64))
+    assert np.array_equal(m[100:], dec.philox_masks(0.2, 1234, 7, 1, 412, 64, row_offset=100))
+
+
+def test_dropout_gradients_match_finite_differences():
+    """fp64 BPTT with recurrent-dropout masks (per gate, time-invariant) against central differences."""
+    rng = np.random.default_rng(8)
+    shp = dict(V=20, E=5, F=1024, U=6, pool=2, C=3)
+    w = {k: v.astype(np.float64) for k, v in synth.synth_weights_v1(rng, trained_like=False, **shp).items()}
+    B, P = 5, 4
+    feat = rng.standard_normal((B, 2, 2, 3))
+    gt = synth.synth_captions(rng, B, P, shp["V"]); gt[1, 2] = 0
+    masks = (dec.philox_masks(0.3, 5, 1, 1, B, 6), dec.philox_masks(0.3, 5, 1, 2, B, 6))
+    loss, G = dec.train_loss_and_grads_v1(feat, gt, w, rec_masks=masks)
+    loss0, _ = dec.train_loss_and_grads_v1(feat, gt, w)
+    assert abs(loss - loss0) > 1e-6
+    for name in ("imgcap_lstm1/recurrent_kernel", "imgcap_lstm2/recurrent_kernel", "imgcap_lstm1/kernel", "imgcap_lstm_d1/kernel",
+                 "mrcnn_class_conv2/kernel"):
+        for _ in range(4):
+            ix = tuple(rng.integers(0, s) for s in G[name].shape)
+            wp, wm = dict(w), dict(w)
+            a = w[name].copy(); a[ix] += 1e-6; wp[name] = a
+            b = w[name].copy(); b[ix] -= 1e-6; wm[name] = b
+            fd = (dec.train_loss_and_grads_v1(feat, gt, wp, rec_masks=masks)[0] - dec.train_loss_and_grads_v1(feat, gt, wm, rec_masks=masks)[0]) / 2e-6
+            assert abs(fd - G[name][ix]) <= 1e-7 + 1e-4 * abs(fd), (name, ix, fd, G[name][ix])

@@ -314,3 +314,97 @@ def test_v2_inject_training_step_matches_fp64_oracle():
     # inference on the same handle sees the updated weights
     p = m.predict([feat, words])
     assert p.shape == (B, V) and abs(float(-np.log(p[np.arange(B), y]).mean()) - hist.history["val_loss"][-1]) < 0.25
+
+
+def test_recurrent_dropout_matches_oracle_with_the_same_masks():
+    """a10: KL.LSTM(..., recurrent_dropout=0.2) (text_generation_model.py:141-142).  Per-gate, time-invariant masks from
+    Philox-4x32-10 keyed by (seed, step, global row): the fp64 oracle draws the identical masks, so loss and gradients
+    are held to the same bars as the deterministic step; rate 0 equals the plain entry point; a batch cut into two
+    shards (row_offset) sums to the unsharded gradients."""
+    pkg, rng, w, feat, gt, m = _setup(33, 96)
+    B, U = 96, SHAPE["U"]
+    rate, seed, step = 0.2, 0x1234567890ABCDEF, 11
+    masks = (dec.philox_masks(rate, seed, step, 1, B, U), dec.philox_masks(rate, seed, step, 2, B, U))
+    loss_want, G = dec.train_loss_and_grads_v1(feat, gt, w, rec_masks=masks)
+    loss_plain, G0 = dec.train_loss_and_grads_v1(feat, gt, w)
+    assert abs(loss_want - loss_plain) > 1e-4                      # the masks matter
+    loss = float(m.train_step_device(feat, gt, recurrent_dropout=rate, dropout_seed=seed, dropout_step=step).item())
+    assert abs(loss - loss_want) <= 5e-3 * abs(loss_want), (loss, loss_want, loss_plain)
+    got = m.get_gradients()
+    for n in ("imgcap_lstm1/recurrent_kernel", "imgcap_lstm2/recurrent_kernel", "imgcap_lstm1/kernel", "imgcap_lstm2/kernel",
+              "imgcap_lstm1/bias", "imgcap_lstm2/bias", "imgcap_lstm_d1/kernel", "imgcap_lstm_d2/kernel", "mrcnn_class_conv2/kernel"):
+        rel = _rel_l2(got[n], G[n])
+        cos = float((got[n].astype(np.float64) * G[n]).sum() / (np.linalg.norm(got[n]) * np.linalg.norm(G[n])))
+        assert rel <= 6e-2 and cos >= 0.995, (n, rel, cos)
+        # ... and they are the DROPOUT gradients, not the plain ones
+        if n.endswith("recurrent_kernel"):
+            assert _rel_l2(got[n], G0[n]) > 2 * rel, n
+    # a different step draws different masks
+    l2 = float(m.train_step_device(feat, gt, recurrent_dropout=rate, dropout_seed=seed, dropout_step=step + 1).item())
+    assert abs(l2 - loss) > 1e-5
+    # sharding invariance: two half batches with their global row offsets == the full batch
+    gfull = m.grad_buffer().clone()
+    m.train_step_device(feat, gt, recurrent_dropout=rate, dropout_seed=seed, dropout_step=step)
+    gfull = m.grad_buffer().clone()
+    inv = 1.0 / (B * gt.shape[1])
+    m.train_step_device(feat[:40], gt[:40], inv_count=inv, recurrent_dropout=rate, dropout_seed=seed, dropout_step=step, row_offset=0)
+    ga = m.grad_buffer().clone()
+    m.train_step_device(feat[40:], gt[40:], inv_count=inv, recurrent_dropout=rate, dropout_seed=seed, dropout_step=step, row_offset=40)
+    gb = m.grad_buffer().clone()
+    rel = float(((ga + gb - gfull).norm() / gfull.norm()).item())
+    assert rel <= 2e-3, rel
+    # rate 0 through the _ex entry point is the deterministic step
+    la = float(m.train_step_device(feat, gt).item())
+    lb = float(m.train_step_device(feat, gt, recurrent_dropout=0.0, dropout_seed=seed, dropout_step=step,
+                                   d_features=torch.empty((B, 7, 7, SHAPE["C"]), device="cuda")).item())
+    assert la == lb
+    with pytest.raises(RuntimeError):
+        m.train_step_device(feat, gt, recurrent_dropout=1.5)
+
+
+def test_gradients_at_baseline_shapes_match_fp64_oracle():
+    """BASELINE configs[2] shapes (V = 10 000, E = 300, U = 512, C = 256, P = 16) at B = 256 RoIs: loss and EVERY gradient
+    tensor against the fp64 oracle -- the toy-shape test above never ran the split-K weight gradients over thousands
+    of rows, the 10 000-column soft-max / cross-entropy, or the 12 544-deep head GEMMs.  Same bar: per tensor
+    max(2e-2, 1.5 x the model's own bf16 quantisation sensitivity) relative L2, cosine >= 0.995.  A second batch of
+    4096 RoIs (the cfg3 per-step size) checks what the oracle cannot afford through linearity: the gradient of the
+    concatenation of 16 copies of the batch equals the gradient of one copy (mean loss), K = 65 536 rows per
+    weight-gradient GEMM."""
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(1003)
+    V, E, U, C, Pn, B = 10000, 300, 512, 256, 16, 256
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C, trained_like=False)
+    feat = rng.standard_normal((B, 7, 7, C)).astype(np.float32)
+    gt = synth.synth_captions(rng, B, Pn, V)
+    gt[1, 2] = 0
+    loss_want, G = dec.train_loss_and_grads_v1(feat, gt, w)
+    r16 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).float().numpy()
+    wq = {k: (r16(v) if ("kernel" in k or "embeddings" in k) else v) for k, v in w.items()}
+    _, Gq = dec.train_loss_and_grads_v1(r16(feat), gt, wq)
+    cfg = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], B, Pn)
+    m = pkg.build_lstm_model([7, 7, C], cfg, U, "training", dtype="bfloat16")
+    m.set_weights(w)
+    m.compile(optimizer=pkg.Adam(amsgrad=True), loss=pkg.roi_caption_loss)
+    loss = float(m.train_step_device(feat, gt).item())
+    assert abs(loss - loss_want) <= 5e-3 * abs(loss_want), (loss, loss_want)
+    got = m.get_gradients()
+    worst, bad = {}, {}
+    for n, g in got.items():
+        worst[n] = _rel_l2(g, G[n])
+        tol = max(GRAD_REL_L2, 1.5 * _rel_l2(Gq[n], G[n]))
+        cos = float(np.dot(g.ravel().astype(np.float64), G[n].ravel()) / (np.linalg.norm(g.astype(np.float64)) * np.linalg.norm(G[n])))
+        if not (worst[n] <= tol and cos >= 0.995):
+            bad[n] = (worst[n], tol, cos)
+    assert not bad, "gradient tensors outside the bar (rel L2, tol, cos): %s (all: %s)" % (bad, worst)
+    g256 = m.grad_buffer().clone()
+    # cfg3 size by linearity: 16 copies of the batch, mean over 16x the positions -> the same gradient
+    cfg2 = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], 16 * B, Pn)
+    m2 = pkg.build_lstm_model([7, 7, C], cfg2, U, "training", dtype="bfloat16")
+    m2.set_weights(w)
+    m2.compile(optimizer=pkg.Adam(amsgrad=True), loss=pkg.roi_caption_loss)
+    tf = torch.from_numpy(feat).cuda().repeat(16, 1, 1, 1)
+    tg = torch.from_numpy(gt).cuda().repeat(16, 1)
+    loss16 = float(m2.train_step_device(tf, tg).item())
+    assert abs(loss16 - loss) <= 1e-4 * abs(loss)
+    rel = float(((m2.grad_buffer() - g256).norm() / g256.norm()).item())
+    assert rel <= 2e-3, rel
