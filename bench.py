@@ -154,6 +154,32 @@ def dist_env():
             int(os.environ.get("WORLD_SIZE", 1)))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs of its GPU's NUMA node BEFORE any pinned host memory is allocated (first touch
+    then places the staging buffers next to the PCIe root the GPU hangs off).  Returns what was done, for the line."""
+    try:
+        bdf = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]                                            # 00000000:1b:00.0 -> 0000:1b:00.0
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) < 2:
+            return {"numa_node": node, "numa_nodes": len(nodes), "bound": False}
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "numa_nodes": len(nodes), "bound": bool(allowed), "cpus": len(allowed)}
+    except Exception as e:
+        return {"bound": False, "error": "%s: %s" % (type(e).__name__, e)}
+
+
 class Ctx(object):
     """One process per GPU: rank / device / NCCL group shared by every workload of a run."""
 
@@ -161,6 +187,7 @@ class Ctx(object):
         import torch
         import torch.distributed as dist
         self.rank, self.local_rank, self.world = dist_env()
+        self.numa = bind_to_gpu_numa_node(self.local_rank)
         if args.gpus != self.world and self.world > 1:
             raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, self.world))
         torch.cuda.set_device(self.local_rank)
@@ -539,28 +566,47 @@ def run_ours_captions(args, ctx):
         "roofline_hbm": roofline_hbm,
     }
     if not args.no_e2e:
-        e2e_steps = max(1, min(K, args.e2e_steps))
+        e2e_steps = max(3, min(K, args.e2e_steps))
         h_boxes = torch.from_numpy(boxes_np).pin_memory()
         h_fms = [f.cpu().pin_memory() for f in fms]
         h_np = [f.numpy() for f in h_fms]
         model.caption_rois(h_boxes.numpy(), h_np, IMAGE_SHAPE)          # warm-up (allocations)
+        model.caption_rois(h_boxes.numpy(), h_np, IMAGE_SHAPE)
+        # the host-side ceiling: every rank uploads its pinned pyramid at the same time, nothing else running
+        h2d_bytes = int(sum(f.numel() * 4 for f in h_fms) + h_boxes.numel() * 4)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        c0.record()
+        for _ in range(3):
+            for f, hf in zip(fms, h_fms):
+                f.copy_(hf, non_blocking=True)
+        c1.record()
+        barrier()
+        copy_s = ctx.max_over_ranks(c0.elapsed_time(c1) * 1e-3 / 3)
+        barrier()
+        # pipelined public API: two calls in flight, the upload of call k+1 under the decode tail of call k
+        outs = []
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            h_tok = model.caption_rois(h_boxes.numpy(), h_np, IMAGE_SHAPE)
+        for i in range(e2e_steps):
+            outs.append(model.caption_rois(h_boxes.numpy(), h_np, IMAGE_SHAPE, wait=False))
+            if i >= 1:
+                model.caption_rois_wait()
+        model.caption_rois_wait()
         barrier()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        e2e_s = ctx.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        h_tok = outs[-1]
         agree = float((torch.from_numpy(h_tok).to(dev) == tokens).float().mean().item())
+        same_all = all(np.array_equal(o, outs[0]) for o in outs)
         line["e2e"] = {"value": round(R * world / e2e_s, 1), "unit": "RoI captions/s",
-                       "h2d_bytes_per_step": int(sum(f.numel() * 4 for f in h_fms) + h_boxes.numel() * 4),
-                       "d2h_bytes_per_step": int(R * PADDING * 4), "steps": e2e_steps,
-                       "token_agreement_with_device_run": round(agree, 5),
-                       "api": "dc_caption_rois_host (pinned host pyramid + boxes in, token ids out; "
-                              "image-by-image upload overlapped with ROIAlign + decode)"}
+                       "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(R * PADDING * 4), "steps": e2e_steps,
+                       "token_agreement_with_device_run": round(agree, 5), "all_steps_identical": same_all,
+                       "h2d_gbs_per_rank_all_ranks_copying": round(h2d_bytes / copy_s / 1e9, 2),
+                       "host_copy_ceiling": round(R * world / copy_s, 1),
+                       "frac_of_host_copy_ceiling": round(copy_s / e2e_s, 4), "numa": ctx.numa,
+                       "api": "dc_caption_rois_host_submit / _wait (pinned host pyramid + boxes in, token ids out; images "
+                              "uploaded one by one under ROIAlign + decode of the previous one, two calls in flight); "
+                              "host_copy_ceiling = the same metric if the pinned H2D copy of the pyramids were the only cost, "
+                              "measured with all ranks copying at once"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_captions(boxes_np[:1], [f[:1].cpu().numpy() for f in fms], w, 12.0)
     return line

@@ -93,6 +93,9 @@ SIGNATURES = {
                         [ctypes.c_int] * 4 + [c_void, c_void]),
     "dc_caption_rois_host": (ctypes.c_int, [c_void, c_void, c_void * 4, ctypes.c_int * 4, ctypes.c_int * 4] +
                              [ctypes.c_int] * 4 + [c_void]),
+    "dc_caption_rois_host_submit": (ctypes.c_int, [c_void, c_void, c_void * 4, ctypes.c_int * 4, ctypes.c_int * 4] +
+                                    [ctypes.c_int] * 4 + [c_void]),
+    "dc_caption_rois_host_wait": (ctypes.c_int, [c_void]),
     "dc_decoder_greedy_host": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void]),
     "dc_decoder_train_step": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void,
                                              ctypes.c_float, c_void, c_void]),

@@ -99,6 +99,7 @@ int Decoder::layout_arena() {
 }
 
 Decoder::~Decoder() {
+    if (host_pipe) free_host_pipe(host_pipe);
     drop_graphs();
     free_train();
     if (graph_stream) cudaStreamDestroy(graph_stream);

@@ -34,6 +34,8 @@ struct Workspace {
 };
 
 struct Bf16State;                 // decoder_bf16.cu
+struct HostPipe;                  // pipeline.cu: streams / events / staging of dc_caption_rois_host_*
+void free_host_pipe(HostPipe *p);
 int accumulate_log(float *scores, const float *maxprob, int rows, bool first, cudaStream_t s);   // decoder.cu
 
 struct Decoder {
@@ -49,6 +51,7 @@ struct Decoder {
     float *w1cat = nullptr, *w2cat = nullptr;
     float *rep_g1f = nullptr, *rep_d1f = nullptr;
     Bf16State *bf = nullptr;
+    HostPipe *host_pipe = nullptr;
     void *roi_buf = nullptr;
     // CUDA graphs of the bf16 greedy loop, keyed by (feats, kind, B, tokens); captured on the second
     // call with the same key and replayed afterwards (removes ~100 launches of host overhead per call)

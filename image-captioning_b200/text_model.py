@@ -369,10 +369,13 @@ class RoiCaptionModel(_ModelBase):
             return tokens.cpu().numpy(), scores.cpu().numpy()
         return tokens, scores
 
-    def caption_rois(self, boxes, feature_maps, image_shape):
+    def caption_rois(self, boxes, feature_maps, image_shape, wait=True):
         """generate_features + predict in one call: ROIAlign -> head -> greedy ids [B*N, P].
         torch CUDA inputs run on the device (dc_caption_rois); numpy inputs go through the
-        host-buffer pipeline (dc_caption_rois_host)."""
+        host-buffer pipeline (dc_caption_rois_host).  ``wait=False`` (host inputs): only enqueue the call
+        (dc_caption_rois_host_submit) and return the token array it WILL fill; ``caption_rois_wait()`` blocks until the
+        oldest outstanding call is complete.  Up to two calls may be outstanding: the upload of the second overlaps the
+        decode tail of the first.  Keep the (pinned) inputs alive and unmodified until the wait."""
         self._ready()
         P = self.config.PADDING_SIZE
         on_dev = all(isinstance(t, torch.Tensor) and t.is_cuda for t in [boxes] + list(feature_maps))
@@ -401,11 +404,20 @@ class RoiCaptionModel(_ModelBase):
             return tokens
         tokens = np.empty((B * N, P), np.int32)
         ptrs = (ctypes.c_void_p * 4)(*[f.ctypes.data for f in fms])
+        fn = self._lib.dc_caption_rois_host if wait else self._lib.dc_caption_rois_host_submit
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.dc_caption_rois_host(self._h, ctypes.c_void_p(b.ctypes.data), ptrs, hs, ws, B, N,
-                                                      int(image_shape[0]), int(image_shape[1]),
-                                                      ctypes.c_void_p(tokens.ctypes.data)))
+            _lib.check(fn(self._h, ctypes.c_void_p(b.ctypes.data), ptrs, hs, ws, B, N, int(image_shape[0]),
+                          int(image_shape[1]), ctypes.c_void_p(tokens.ctypes.data)))
+        if not wait:
+            self._inflight = getattr(self, "_inflight", []) + [(b, fms, tokens)]      # keep the host buffers alive
         return tokens
+
+    def caption_rois_wait(self):
+        """Block until the oldest caption_rois(..., wait=False) call has delivered its tokens."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_caption_rois_host_wait(self._h))
+        if getattr(self, "_inflight", None):
+            self._inflight.pop(0)
 
     # ---- training surface (text_generation_model.py:424-426, 470-472) ----
     def compile(self, optimizer="adam", loss=None, metrics=None, **kwargs):

@@ -304,10 +304,21 @@ int dc_caption_rois(DcDecoder *dec, const float *boxes, const float *const fmaps
 
 /* Host-buffer form: HOST pointers (pinned memory makes the copies asynchronous); the pyramid is
  * uploaded image by image while the previous image is aligned and decoded; returns when `tokens`
- * is complete. */
+ * is complete.  Streams, events and device staging are kept in the handle and reused by every call.  No caller
+ * stream: work enqueued on the handle from another stream (dc_adam_step ...) must have completed. */
 int dc_caption_rois_host(DcDecoder *dec, const float *boxes, const float *const fmaps[4],
                          const int fm_h[4], const int fm_w[4], int n_images, int n_boxes, int img_h,
                          int img_w, int32_t *tokens);
+/* The same pipeline split in two so that consecutive calls overlap: submit() enqueues the uploads, kernels and the
+ * token download of one call and returns; wait() blocks until the OLDEST outstanding call's tokens are on the
+ * host.  At most two calls are outstanding (a third submit first retires the oldest); host buffers of a submitted
+ * call must stay valid and unmodified until its wait() returns.  With two in flight, call k+1's upload runs under
+ * call k's last-image decode. */
+int dc_caption_rois_host_submit(DcDecoder *dec, const float *boxes, const float *const fmaps[4],
+                         const int fm_h[4], const int fm_w[4], int n_images, int n_boxes, int img_h,
+                         int img_w, int32_t *tokens);
+int dc_caption_rois_host_wait(DcDecoder *dec);
+
 
 /* ------------------------------------------------------------------------------------------
  * Caption post-processing (the step after the decoder in the dense-captioning evaluation path)
