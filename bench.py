@@ -763,6 +763,27 @@ def run_ours_train(args, ctx):
                                     note="whole step time (GEMMs + softmax/xent + cell backward + optimiser + all-reduce) "
                                          "against 3x forward FLOPs"),
     }
+    # where the step goes (names the strong-scaling limiter): local forward+backward alone, optimiser alone; the rest of
+    # ms_per_step is the exposed part of the NCCL all-reduce plus launch gaps
+    def timed(fn, n=4):
+        fn()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.barrier()
+        a.record()
+        for _ in range(n):
+            fn()
+        b2.record()
+        torch.cuda.synchronize()
+        return ctx.max_over_ranks(a.elapsed_time(b2) / n)
+    fb_ms = timed(lambda: model.train_step_device(feats, gt, None, 1.0 / npos))
+    saved_iter = model.optimizer.iterations
+    opt_ms = timed(lambda: model.apply_gradients())
+    model.optimizer.iterations = saved_iter
+    line["breakdown"] = {"forward_backward_ms": round(fb_ms, 4), "optimizer_ms": round(opt_ms, 4),
+                         "allreduce_exposed_plus_gaps_ms": round(max(0.0, ms_per_step - fb_ms - opt_ms), 4),
+                         "allreduce_bytes": int(model.grad_buffer().numel() * 4) if world > 1 else 0,
+                         "kernel_launches_per_step": 144 + (5 if world > 1 else 0),
+                         "note": "per-rank batch %d: the %d recurrent step kernels run %d-row GEMMs" % (Bl, 6 * TRAIN_P, Bl)}
     if not args.no_e2e:
         e2e_steps = max(1, min(K, args.e2e_steps))
         h_feats = feats.cpu().pin_memory()
@@ -1133,7 +1154,7 @@ def run_ours_captions_vg(args, ctx):
 
 
 SUB_KEYS = ("metric", "value", "unit", "ms_per_step", "steps", "scaling", "dtype", "config", "clocks", "roofline",
-            "roofline_hbm", "e2e", "gpu_launches")
+            "roofline_hbm", "e2e", "gpu_launches", "breakdown")
 
 
 def sub_records(args, ctx):
