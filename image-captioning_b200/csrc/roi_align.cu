@@ -724,6 +724,355 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring_kernel(const RoiRingPar
 }
 
 // ---------------------------------------------------------------------------------------------
+// Ring kernel, second form.  Profiling the first one with clock64 marks (DCAP_ROI_PROF) showed its single producer
+// warp as the bottleneck: ~4000 dependent-instruction cycles per RoI for the sample arithmetic and the serial
+// de-duplication, ~800 to publish the descriptor, ~3400 in the issue loop -- 7700 cycles per RoI against a budget of
+// ~4500, while the consumers sat in their row waits.  Here everything that depends only on the BOX moves into a
+// massively parallel pre-pass (one warp per RoI, latency irrelevant) that writes a 1 KB "ring record" per RoI:
+// sample weights, row / pixel positions, release flags, pixel runs, map rows.  The producer warp only loads the
+// record (prefetched one RoI ahead) and issues the bulk copies; the consumer warps read the record themselves
+// (L2 / L1 resident) and track the ring head on their own, so the shared-memory descriptor ring and its two
+// barrier sets are gone.  Slot arithmetic is division free (the head is kept as slot + phase).
+// ---------------------------------------------------------------------------------------------
+namespace ring2 {
+constexpr int kRec = 64;                                   // int4 entries per RoI record (1 KB)
+constexpr int kHdr = 0, kHdr2 = 1, kY = 2, kX = 18, kRun = 34, kRow = 50;   // rows: 32 ints = 8 entries
+}  // namespace ring2
+
+struct RoiRecParams {
+    const float *boxes;
+    const int2 *order;
+    const float *fm[4];
+    int fm_h[4];
+    int fm_w[4];
+    int n_boxes, c4, ph, pw, total;
+    int4 *records;
+};
+
+__global__ void __launch_bounds__(256) roi_ring_records_kernel(const RoiRecParams p) {
+    using namespace ring2;
+    const int lane = threadIdx.x & 31;
+    const long long spos = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    pdl_wait();                                            // the order array comes from roi_order_kernel
+    pdl_launch_dependents();
+    if (spos >= p.total) return;
+    const int2 cur = __ldg(p.order + spos);
+    const float4 cbox = __ldg(reinterpret_cast<const float4 *>(p.boxes) + cur.x);
+    const int roi = cur.x;
+    int H, W;
+    const float *base;
+    switch (cur.y - 2) {
+        case 0: H = p.fm_h[0]; W = p.fm_w[0]; base = p.fm[0]; break;
+        case 1: H = p.fm_h[1]; W = p.fm_w[1]; base = p.fm[1]; break;
+        case 2: H = p.fm_h[2]; W = p.fm_w[2]; base = p.fm[2]; break;
+        default: H = p.fm_h[3]; W = p.fm_w[3]; base = p.fm[3]; break;
+    }
+    base += (long long)(roi / p.n_boxes) * H * W * p.c4 * 4;
+    const bool is_y = lane < 16;
+    const int j = lane & 15;
+    const int n = is_y ? p.ph : p.pw;
+    const unsigned px_bytes = (unsigned)p.c4 * 16u;
+    // tf.image.crop_and_resize sample coordinate of this lane (one sample per bin, end points inclusive)
+    const float a1 = is_y ? cbox.x : cbox.y, a2 = is_y ? cbox.z : cbox.w;
+    const float Dm1 = (float)((is_y ? H : W) - 1);
+    float in;
+    if (n > 1) {
+        const float sc = __fdiv_rn(__fmul_rn(__fsub_rn(a2, a1), Dm1), (float)(n - 1));
+        in = __fadd_rn(__fmul_rn(a1, Dm1), __fmul_rn((float)j, sc));
+    } else {
+        in = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(a1, a2)), Dm1);
+    }
+    const bool ok = (j < n) && (in >= 0.0f) && (in <= Dm1);
+    const float fl = floorf(in);
+    const int lo = ok ? (int)fl : 0, hi = ok ? (int)ceilf(in) : 0;
+    const float frac = __fsub_rn(in, fl);
+    // distinct rows (y half) / pixels (x half) in sample order; a tap already loaded for the previous sample is re-used
+    int posLo = 0, posHi = 0, cnt = 0;
+    bool newLo = false, newHi = false, runStart = false;
+    {
+        int pLo = 0, pHi = 0, pPosLo = 0, pPosHi = 0, lastNew = INT_MIN;
+        bool pOk = false;
+        const int ns = p.ph > p.pw ? p.ph : p.pw;
+        for (int s = 0; s < ns; ++s) {
+            const int sLo = __shfl_sync(0xffffffffu, lo, s, 16), sHi = __shfl_sync(0xffffffffu, hi, s, 16);
+            const bool sOk = __shfl_sync(0xffffffffu, (int)ok, s, 16) != 0;
+            int qLo = 0, qHi = 0;
+            bool nLo = false, nHi = false, rs = false;
+            if (sOk) {
+                if (pOk && sLo == pLo) qLo = pPosLo;
+                else if (pOk && sLo == pHi) qLo = pPosHi;
+                else { qLo = cnt++; nLo = true; rs = (sLo != lastNew + 1) || lastNew == INT_MIN; lastNew = sLo; }
+                if (sHi == sLo) qHi = qLo;
+                else if (pOk && sHi == pLo) qHi = pPosLo;
+                else if (pOk && sHi == pHi) qHi = pPosHi;
+                else {
+                    qHi = cnt++; nHi = true;
+                    if (!nLo) rs = (sHi != lastNew + 1) || lastNew == INT_MIN;
+                    lastNew = sHi;
+                }
+            }
+            pOk = sOk; pLo = sLo; pHi = sHi; pPosLo = qLo; pPosHi = qHi;
+            if (j == s) { posLo = qLo; posHi = qHi; newLo = nLo; newHi = nHi; runStart = rs && (nLo || nHi); }
+        }
+    }
+    const int ny = __shfl_sync(0xffffffffu, cnt, 0), nq = __shfl_sync(0xffffffffu, cnt, 16);
+    // a row / pixel position dies after the last sample that reads it (re-use only ever looks one sample back)
+    const int nxOk = __shfl_down_sync(0xffffffffu, (int)ok, 1, 16);
+    const int nxLo = __shfl_down_sync(0xffffffffu, posLo, 1, 16), nxHi = __shfl_down_sync(0xffffffffu, posHi, 1, 16);
+    const bool next_ok = (j < 15) && nxOk;
+    const bool relLo = ok && !(next_ok && (posLo == nxLo || posLo == nxHi));
+    const bool relHi = ok && posHi != posLo && !(next_ok && (posHi == nxLo || posHi == nxHi));
+    const int runQ = newLo ? posLo : posHi, runPx = newLo ? lo : hi;
+    const unsigned start_mask = __reduce_or_sync(0xffffffffu, (!is_y && runStart) ? (1u << runQ) : 0u);
+    const unsigned above = (runQ + 1 < 32) ? (start_mask >> (runQ + 1)) : 0u;
+    const int runLen = above ? __ffs(above) : nq - runQ;
+    const int nruns = __popc(start_mask);
+
+    int4 *rec = p.records + spos * kRec;
+    if (lane == 0) {
+        const unsigned long long bp = (unsigned long long)base;
+        rec[kHdr] = make_int4((int)(bp & 0xffffffffull), (int)(bp >> 32), roi, ny | (nq << 8) | (nruns << 16));
+        rec[kHdr2] = make_int4(W * p.c4, 0, 0, 0);
+    }
+    if (is_y) {
+        rec[kY + j] = make_int4(posLo, posHi, __float_as_int(frac),
+                                (ok ? 1 : 0) | (relLo ? 2 : 0) | (relHi ? 4 : 0) | (newLo ? 32 : 0) | (newHi ? 64 : 0));
+        int *rows = reinterpret_cast<int *>(rec + kRow);
+        if (newLo) rows[posLo] = lo;
+        if (newHi) rows[posHi] = hi;
+    } else {
+        rec[kX + j] = make_int4(posLo * (int)px_bytes, posHi * (int)px_bytes, __float_as_int(frac), ok ? 1 : 0);
+        if (runStart) rec[kRun + __popc(start_mask & ((1u << runQ) - 1u))] = make_int4(runQ * (int)px_bytes, runPx * p.c4, runLen * (int)px_bytes, 0);
+    }
+}
+
+struct RoiRing2Params {
+    const int4 *records;
+    int c4, ph, pw, total;
+    void *out;
+    int slots;            // K row slots in the ring
+    unsigned slot_bytes;  // 2*pw pixels
+    int diag;
+    unsigned long long *prof;
+};
+
+template <bool kBf16>
+__global__ void __launch_bounds__(512, 1) roi_align_ring2_kernel(const RoiRing2Params p) {
+    using namespace ring;
+    using namespace ring2;
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+    __shared__ int4 s_run[2 * kMaxSamples];                // producer scratch: this RoI's pixel runs
+    const int K = p.slots;
+    unsigned char *slots = ring_smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring_smem + (size_t)K * p.slot_bytes);
+    uint64_t *empty = full + K;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncons = (blockDim.x >> 5) - 1;
+    const uint32_t px_bytes = (uint32_t)p.c4 * 16u;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < K; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, ncons); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();                                            // the records come from roi_ring_records_kernel
+    int headSlot = 0, headPhase = 0;                       // ring position of the current RoI's first row (all warps track it)
+    unsigned long long pc[4] = {0, 0, 0, 0};
+    long long tk = clock64();
+    auto tick = [&](int i) { if (p.prof) { const long long now = clock64(); pc[i] += (unsigned long long)(now - tk); tk = now; } };
+
+    if (warp == 0) {
+        // ------------------------------- producer -------------------------------
+        int spos = blockIdx.x;
+        int4 hdr = make_int4(0, 0, 0, 0), hdr2 = hdr, myrun = hdr;
+        int myrow = 0;
+        if (spos < p.total) {
+            const int4 *rec = p.records + (long long)spos * kRec;
+            hdr = __ldg(rec + kHdr); hdr2 = __ldg(rec + kHdr2);
+            myrun = __ldg(rec + kRun + (lane & 15));
+            myrow = __ldg(reinterpret_cast<const int *>(rec + kRow) + lane);
+        }
+        for (; spos < p.total; spos += gridDim.x) {
+            const int4 chdr = hdr, chdr2 = hdr2, crun = myrun;
+            const int crow = myrow;
+            if (spos + (long long)gridDim.x < p.total) {   // next RoI's record: in flight while this one is issued
+                const int4 *rec = p.records + ((long long)spos + gridDim.x) * kRec;
+                hdr = __ldg(rec + kHdr); hdr2 = __ldg(rec + kHdr2);
+                myrun = __ldg(rec + kRun + (lane & 15));
+                myrow = __ldg(reinterpret_cast<const int *>(rec + kRow) + lane);
+            }
+            const int ny = chdr.w & 255, nq = (chdr.w >> 8) & 255, nruns = (chdr.w >> 16) & 255;
+            const float4 *base = reinterpret_cast<const float4 *>(((unsigned long long)(unsigned)chdr.x) | ((unsigned long long)(unsigned)chdr.y << 32));
+            __syncwarp();                                  // the previous RoI's run table is no longer read
+            if (lane < 16) s_run[lane] = crun;
+            __syncwarp();
+            tick(0);
+            for (int b0 = 0; b0 < ny; b0 += K) {
+                const int r = b0 + lane;
+                const bool mine = lane < K && r < ny;
+                int slot = headSlot + r, wraps = 0;
+                while (slot >= K) { slot -= K; ++wraps; }
+                const uint32_t par = (uint32_t)((headPhase + wraps) & 1) ^ 1u;
+                const int rowidx = __shfl_sync(0xffffffffu, crow, r & 31);
+                const float4 *src_row = base + (long long)rowidx * chdr2.x;
+                unsigned char *dst_row = slots + (size_t)slot * p.slot_bytes;
+                unsigned pending = __ballot_sync(0xffffffffu, mine);
+                bool todo = mine;
+                while (pending) {
+                    bool fired = false;
+                    if (todo && mbar_try_wait(empty + slot, par)) {
+                        mbar_expect_tx(full + slot, (p.diag & 2) ? 0u : (uint32_t)nq * px_bytes);
+                        for (int i = 0; i < ((p.diag & 2) ? 0 : nruns); ++i) {
+                            const int4 rn = s_run[i];
+                            bulk_load(dst_row + rn.x, src_row + rn.y, (uint32_t)rn.z, full + slot);
+                        }
+                        fired = true;
+                        todo = false;
+                    }
+                    pending &= ~__ballot_sync(0xffffffffu, fired);
+                }
+            }
+            headSlot += ny;
+            while (headSlot >= K) { headSlot -= K; headPhase ^= 1; }
+            tick(1);
+        }
+        if (p.prof && lane == 0)
+            for (int i = 0; i < 2; ++i) atomicAdd(p.prof + i, pc[i]);
+    } else {
+        // ------------------------------- consumers -------------------------------
+        const int cw = warp - 1;
+        const int bins = p.ph * p.pw;
+        int spos = blockIdx.x;
+        int4 hdr = make_int4(0, 0, 0, 0), ylane = hdr;
+        if (spos < p.total) {
+            const int4 *rec = p.records + (long long)spos * kRec;
+            hdr = __ldg(rec + kHdr);
+            ylane = __ldg(rec + kY + (lane & 15));
+        }
+        for (; spos < p.total; spos += gridDim.x) {
+            const int4 chdr = hdr, cy = ylane;
+            const int4 *rec = p.records + (long long)spos * kRec;
+            if (spos + (long long)gridDim.x < p.total) {
+                const int4 *nrec = p.records + ((long long)spos + gridDim.x) * kRec;
+                hdr = __ldg(nrec + kHdr);
+                ylane = __ldg(nrec + kY + (lane & 15));
+            }
+            const int ny = chdr.w & 255;
+            const long long out_roi = (long long)chdr.z * bins * p.c4;
+            // ring slot / phase of row position `lane` of this RoI
+            int slotOf = headSlot + lane, wraps = 0;
+            while (slotOf >= K) { slotOf -= K; ++wraps; }
+            const int parOf = (headPhase + wraps) & 1;
+            const bool single = p.pw <= ncons;                 // one bin column per warp: its x entry is loaded once per RoI
+            const int4 xe0 = (single && cw < p.pw) ? __ldg(rec + kX + cw) : make_int4(0, 0, 0, 0);
+            tick(0);
+            for (int by = 0; by < p.ph; ++by) {
+                const int yPosLo = __shfl_sync(0xffffffffu, cy.x, by), yPosHi = __shfl_sync(0xffffffffu, cy.y, by);
+                const float ly = __int_as_float(__shfl_sync(0xffffffffu, cy.z, by));
+                const int yflags = __shfl_sync(0xffffffffu, cy.w, by);
+                const bool yok = (yflags & 1) != 0;
+                const int sTop = __shfl_sync(0xffffffffu, slotOf, yPosLo), sBot = __shfl_sync(0xffffffffu, slotOf, yPosHi);
+                const int pTop = __shfl_sync(0xffffffffu, parOf, yPosLo), pBot = __shfl_sync(0xffffffffu, parOf, yPosHi);
+                if (yok) {
+                    mbar_wait(full + sTop, (uint32_t)pTop);
+                    mbar_wait(full + sBot, (uint32_t)pBot);
+                }
+                tick(1);
+                const unsigned char *top = slots + (size_t)sTop * p.slot_bytes;
+                const unsigned char *bot = slots + (size_t)sBot * p.slot_bytes;
+                for (int bx = cw; bx < p.pw; bx += ncons) {
+                    const int4 xe = single ? xe0 : __ldg(rec + kX + bx);
+                    const bool ok = yok && xe.w && !(p.diag & 1);
+                    const float lx = __int_as_float(xe.z);
+                    const long long o = out_roi + ((long long)by * p.pw + bx) * p.c4;
+                    if (p.diag & 4) continue;
+                    for (int c0 = 0; c0 < p.c4; c0 += 64) {
+                        const int ca = c0 + lane, cb = c0 + 32 + lane;
+                        const bool acta = ca < p.c4, actb = cb < p.c4;
+                        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+                        if (ok) {
+                            float4 tl, tr, bl, br, tl2, tr2, bl2, br2;
+                            if (acta) {
+                                tl = *reinterpret_cast<const float4 *>(top + xe.x + ca * 16);
+                                tr = *reinterpret_cast<const float4 *>(top + xe.y + ca * 16);
+                                bl = *reinterpret_cast<const float4 *>(bot + xe.x + ca * 16);
+                                br = *reinterpret_cast<const float4 *>(bot + xe.y + ca * 16);
+                            }
+                            if (actb) {
+                                tl2 = *reinterpret_cast<const float4 *>(top + xe.x + cb * 16);
+                                tr2 = *reinterpret_cast<const float4 *>(top + xe.y + cb * 16);
+                                bl2 = *reinterpret_cast<const float4 *>(bot + xe.x + cb * 16);
+                                br2 = *reinterpret_cast<const float4 *>(bot + xe.y + cb * 16);
+                            }
+                            if (acta) va = bilerp4(tl, tr, bl, br, lx, ly);
+                            if (actb) vb = bilerp4(tl2, tr2, bl2, br2, lx, ly);
+                        }
+                        if (acta) store_out<kBf16>(p.out, o + ca, va);
+                        if (actb) store_out<kBf16>(p.out, o + cb, vb);
+                    }
+                }
+                __syncwarp();
+                tick(2);
+                if (lane == 0 && yok) {
+                    if (yflags & 2) mbar_arrive(empty + sTop);
+                    if (yflags & 4) mbar_arrive(empty + sBot);
+                }
+            }
+            headSlot += ny;
+            while (headSlot >= K) { headSlot -= K; headPhase ^= 1; }
+            tick(3);
+        }
+        if (p.prof && lane == 0 && cw == 0)
+            for (int i = 0; i < 4; ++i) atomicAdd(p.prof + 4 + i, pc[i]);
+    }
+}
+
+// Sampling records of the register-gather kernel in sorted order, one thread per record ENTRY over the whole grid
+// (round 1 built them with one CTA per image: 8 of 148 SMs busy for ~30 us at the benchmark shape).
+__global__ void __launch_bounds__(256) roi_gather_records_kernel(const RoiRecParams p) {
+    const int rec_len = 1 + p.ph + p.pw;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
+    pdl_launch_dependents();
+    if (idx >= (long long)p.total * rec_len) return;
+    const long long spos = idx / rec_len;
+    const int e = (int)(idx - spos * rec_len);
+    const int2 cur = __ldg(p.order + spos);
+    const float4 box = __ldg(reinterpret_cast<const float4 *>(p.boxes) + cur.x);
+    int H, W;
+    const float *base;
+    switch (cur.y - 2) {
+        case 0: H = p.fm_h[0]; W = p.fm_w[0]; base = p.fm[0]; break;
+        case 1: H = p.fm_h[1]; W = p.fm_w[1]; base = p.fm[1]; break;
+        case 2: H = p.fm_h[2]; W = p.fm_w[2]; base = p.fm[2]; break;
+        default: H = p.fm_h[3]; W = p.fm_w[3]; base = p.fm[3]; break;
+    }
+    int4 v;
+    if (e == 0) {
+        base += (long long)(cur.x / p.n_boxes) * H * W * p.c4 * 4;
+        const unsigned long long bp = (unsigned long long)base;
+        v = make_int4((int)(bp & 0xffffffffull), (int)(bp >> 32), cur.x, cur.y);
+    } else {
+        const bool is_y = e <= p.ph;
+        const int j = is_y ? e - 1 : e - 1 - p.ph;
+        const int n = is_y ? p.ph : p.pw;
+        const float a1 = is_y ? box.x : box.y, a2 = is_y ? box.z : box.w;
+        const float Dm1 = (float)((is_y ? H : W) - 1);
+        const int stride = is_y ? W * p.c4 : p.c4;
+        float in;
+        if (n > 1) {
+            const float sc = __fdiv_rn(__fmul_rn(__fsub_rn(a2, a1), Dm1), (float)(n - 1));
+            in = __fadd_rn(__fmul_rn(a1, Dm1), __fmul_rn((float)j, sc));
+        } else {
+            in = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(a1, a2)), Dm1);
+        }
+        const bool ok = (in >= 0.0f) && (in <= Dm1);
+        const float fl = floorf(in);
+        v = make_int4(ok ? (int)fl * stride : 0, ok ? (int)ceilf(in) * stride : 0, __float_as_int(__fsub_rn(in, fl)), ok ? 1 : 0);
+    }
+    p.records[idx] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Backward: gradient w.r.t. the feature maps, the mirror image of the gather.
 // TF's CropAndResizeGradImage per in-range sample: dtop = (1-ly)*g, dbottom = ly*g,
 // d[top,left] += (1-lx)*dtop, d[top,right] += lx*dtop, likewise for the bottom row; boxes get no gradient
@@ -815,8 +1164,106 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
     DC_REQUIRE(total < (1ll << 31), "n_images*n_boxes must fit in int32");
     const int rec_len = 1 + pool_h + pool_w;
 
-    // ---- ring path (round 2): order kernel + shared-memory ring kernel ----
-    static const int path = getenv("DCAP_ROI_PATH") ? atoi(getenv("DCAP_ROI_PATH")) : 1;
+    static const int path = getenv("DCAP_ROI_PATH") ? atoi(getenv("DCAP_ROI_PATH")) : 3;
+    // ---- paths 2 / 3 (round 2): locality order (one small CTA per image) -> wide record pre-pass -> gather or ring ----
+    {
+        const unsigned px_b = (unsigned)channels * 4u, slot_b = 2u * (unsigned)pool_w * px_b;
+        const size_t fixed = 2 * ring::kMaxSlots * sizeof(uint64_t) + 128;
+        const bool ring_ok = pool_h <= ring::kMaxSamples && pool_w <= ring::kMaxSamples && 4 * (size_t)slot_b + fixed <= 222 * 1024;
+        if (path == 2 || (path == 3 && ring_ok)) {
+            const bool use_ring = path == 3;
+            const size_t ord_bytes = sizeof(int2) * (size_t)total;
+            const size_t rec_bytes2 = use_ring ? sizeof(int4) * (size_t)total * ring2::kRec : sizeof(int4) * (size_t)total * rec_len;
+            char *ws = nullptr;
+            DC_CHECK_CUDA(cudaMallocAsync((void **)&ws, 2 * ord_bytes + rec_bytes2, stream));
+            RoiOrderParams op;
+            op.boxes = boxes; op.n_boxes = n_boxes; op.denom = level_denominator(img_h, img_w);
+            op.order = reinterpret_cast<int2 *>(ws);
+            op.scratch = reinterpret_cast<int2 *>(ws + ord_bytes);
+            op.levels = levels;
+            const size_t ord_smem = (size_t)n_boxes * sizeof(int2);
+            cudaError_t e;
+            if (ord_smem <= 160 * 1024) {
+                static std::atomic<unsigned long long> attr_set{0};
+                e = once_per_device(attr_set, [] {
+                    return cudaFuncSetAttribute(roi_order_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+                });
+                if (e == cudaSuccess) {
+                    roi_order_kernel<true><<<n_images, kPrepThreads, ord_smem, stream>>>(op);
+                    e = cudaGetLastError();
+                }
+            } else {
+                roi_order_kernel<false><<<n_images, kPrepThreads, 0, stream>>>(op);
+                e = cudaGetLastError();
+            }
+            PdlScope pdl;                 // each kernel's set-up overlaps its predecessor's tail
+            RoiRecParams rp;
+            rp.boxes = boxes; rp.order = op.order;
+            for (int l = 0; l < 4; ++l) { rp.fm[l] = fmaps[l]; rp.fm_h[l] = fm_h[l]; rp.fm_w[l] = fm_w[l]; }
+            rp.n_boxes = n_boxes; rp.c4 = channels / 4; rp.ph = pool_h; rp.pw = pool_w; rp.total = (int)total;
+            rp.records = reinterpret_cast<int4 *>(ws + 2 * ord_bytes);
+            if (e == cudaSuccess && use_ring) {
+                e = launch_pdl(roi_ring_records_kernel, dim3((unsigned)ceil_div<long long>(total * 32, 256)), dim3(256), 0, stream, rp);
+            } else if (e == cudaSuccess) {
+                e = launch_pdl(roi_gather_records_kernel, dim3((unsigned)ceil_div<long long>(total * rec_len, 256)), dim3(256), 0, stream, rp);
+            }
+            if (e == cudaSuccess && use_ring) {
+                static const int env_ctas = getenv("DCAP_ROI_CTAS") ? atoi(getenv("DCAP_ROI_CTAS")) : 2;
+                static const int env_slots = getenv("DCAP_ROI_RING") ? atoi(getenv("DCAP_ROI_RING")) : 0;
+                static const int env_warps = getenv("DCAP_ROI_WARPS") ? atoi(getenv("DCAP_ROI_WARPS")) : 0;
+                static const int env_diag = getenv("DCAP_ROI_DIAG") ? atoi(getenv("DCAP_ROI_DIAG")) : 0;
+                static const bool env_prof = getenv("DCAP_ROI_PROF") != nullptr;
+                int ctas = env_ctas < 1 ? 1 : env_ctas, slots = 0;
+                for (; ctas >= 1; --ctas) {     // K row slots: what fits next to `ctas` resident CTAs per SM
+                    const size_t per_cta = (size_t)(224 * 1024) / ctas - 1024 - 512;
+                    slots = per_cta > fixed ? (int)((per_cta - fixed) / slot_b) : 0;
+                    if (slots >= 4) break;
+                }
+                if (ctas < 1) ctas = 1;
+                if (env_slots >= 4 && env_slots <= slots) slots = env_slots;
+                if (slots > ring::kMaxSlots) slots = ring::kMaxSlots;
+                int ncons = env_warps > 0 ? env_warps : (pool_w < 8 ? pool_w : 8);
+                if (ncons > 15) ncons = 15;
+                const size_t smem = (size_t)slots * slot_b + fixed;
+                static std::atomic<unsigned long long> attr_set2{0};
+                e = once_per_device(attr_set2, [] {
+                    return cudaFuncSetAttribute(roi_align_ring2_kernel<kBf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+                });
+                RoiRing2Params kp;
+                kp.records = rp.records; kp.c4 = channels / 4; kp.ph = pool_h; kp.pw = pool_w; kp.total = (int)total;
+                kp.out = out; kp.slots = slots; kp.slot_bytes = slot_b; kp.diag = env_diag; kp.prof = nullptr;
+                const long long mg = (long long)sm_count() * ctas;
+                static unsigned long long *prof_buf = nullptr;
+                static int prof_calls = 0;
+                if (env_prof) {
+                    if (!prof_buf) { cudaMalloc((void **)&prof_buf, 64); cudaMemset(prof_buf, 0, 64); }
+                    kp.prof = prof_buf;
+                    if (++prof_calls % 16 == 0) {
+                        unsigned long long h[8];
+                        cudaMemcpy(h, prof_buf, 64, cudaMemcpyDeviceToHost);
+                        cudaMemset(prof_buf, 0, 64);
+                        const double nc = 16.0 * (double)(total < mg ? total : mg);
+                        fprintf(stderr, "[roi ring2 prof] per CTA: producer load+table %.0f, issue %.0f | consumer record %.0f, row wait %.0f, "
+                                "compute+store %.0f, release %.0f cycles\n", h[0] / nc, h[1] / nc, h[4] / nc, h[5] / nc, h[6] / nc, h[7] / nc);
+                    }
+                }
+                if (e == cudaSuccess)
+                    e = launch_pdl(roi_align_ring2_kernel<kBf16>, dim3((unsigned)(total < mg ? total : mg)), dim3((ncons + 1) * 32), smem, stream, kp);
+            } else if (e == cudaSuccess) {
+                RoiStreamParams sp;
+                sp.records = rp.records; sp.c4 = channels / 4; sp.parts = (sp.c4 + 31) / 32; sp.ph = pool_h; sp.pw = pool_w;
+                sp.out = out; sp.total = (int)total;
+                const int warps = pool_h < 7 ? pool_h : 7;
+                const long long mg = (long long)sm_count() * 4;
+                e = launch_pdl(roi_align_stream_kernel<2, 72, kBf16>, dim3((unsigned)(total < mg ? total : mg)), dim3(warps * 32), 0, stream, sp);
+            }
+            if (e == cudaSuccess) e = cudaGetLastError();
+            cudaFreeAsync(ws, stream);
+            if (e != cudaSuccess) return set_error(DC_ERR_CUDA, "roi align launch failed: %s", cudaGetErrorString(e));
+            return DC_OK;
+        }
+    }
+    // ---- ring path, first form (kept for A/B: DCAP_ROI_PATH=1) ----
     const unsigned px_bytes = (unsigned)channels * 4u;
     const unsigned slot_bytes = 2u * (unsigned)pool_w * px_bytes;
     const size_t ring_fixed = ring::kDescDepth * sizeof(ring::Desc) + (2 * ring::kMaxSlots + 2 * ring::kDescDepth) * sizeof(uint64_t) + 128;
