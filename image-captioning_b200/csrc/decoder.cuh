@@ -124,6 +124,7 @@ struct Decoder {
     int train_forward(const void *feats, int kind, int B, const int32_t *gt, const int32_t *targets, cudaStream_t s);
     int teacher_forced_probs(const void *feats, int kind, int B, const int32_t *gt, float *probs, cudaStream_t s);
     const DcTrainOptions *train_opts = nullptr;        // valid during train_step only
+    bool train_logits_bf16 = false;                    // train_step: the vocabulary GEMM stores bf16 logits into the dlogits buffer
     int train_step(const void *feats, int kind, int B, const int32_t *gt, const int32_t *targets, float inv_count,
                    float *loss, cudaStream_t s);
     int train_step_v2(const void *feats, int kind, int B, const int32_t *words, int L, const int32_t *targets, float inv_count,

@@ -39,7 +39,8 @@ struct TrainState {
     float *c1 = nullptr, *c2 = nullptr;                            // [(T+1), B, U]
     __nv_bfloat16 *gates1 = nullptr, *gates2 = nullptr;            // [T, B, 4U] bf16 post-activation (i,f,g,o), gate-interleaved
     __nv_bfloat16 *d_all = nullptr;                                // [T*B, 1024] relu(dense1)
-    float *logits = nullptr;                                       // [T*B, V]
+    float *logits = nullptr;                                       // [T*B, V] fp32, allocated on first use by teacher_forced_probs
+    bool logits_in_dz = false;                                     // the last forward stored bf16 logits in dz
     __nv_bfloat16 *dz = nullptr;                                   // [T*B, V]   dlogits
     __nv_bfloat16 *dd = nullptr;                                   // [T*B, 1024]
     float *dh2d = nullptr;                                         // [T*B, U]   dense-path gradient of h2_t
@@ -159,7 +160,7 @@ static int train_reserve(Decoder &D, int B, int T) {
     rc |= A((void **)&t.c1, 4 * (R + Bp) * U); rc |= A((void **)&t.c2, 4 * (R + Bp) * U);
     rc |= A((void **)&t.gates1, 2 * R * 4 * U); rc |= A((void **)&t.gates2, 2 * R * 4 * U);
     rc |= A((void **)&t.d_all, 2 * R * kDense);
-    rc |= A((void **)&t.logits, 4 * R * V); rc |= A((void **)&t.dz, 2 * R * V);
+    rc |= A((void **)&t.dz, 2 * R * V);                               // fp32 logits: only the predict surface needs them (lazy)
     rc |= A((void **)&t.dd, 2 * R * kDense); rc |= A((void **)&t.dh2d, 4 * R * U);
     rc |= A((void **)&t.dz1_all, 2 * R * 4 * U); rc |= A((void **)&t.dz2_all, 2 * R * 4 * U);
     rc |= A((void **)&t.ddsum, 4 * Bp * kDense); rc |= A((void **)&t.dz1sum, 4 * Bp * 4 * U);
@@ -219,32 +220,51 @@ __global__ void gather_embedding_rows_kernel(const uint4 *__restrict__ emb, int 
 // integer targets; one CTA per (time, RoI) row.
 //   p = softmax(z); loss_row = -log(clip(p_y, 1e-7, 1-1e-7)); dz = (p - onehot(y)) * inv_count, and
 //   zero when the clip is active (the clip has zero gradient) or the position is ignored (y < 0).
-__global__ void __launch_bounds__(256) softmax_xent_kernel(const float *__restrict__ logits, long long ld, int V,
+template <typename TIn>
+__device__ __forceinline__ void load8(const TIn *p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float *p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16 *p, float (&v)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4 *>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+
+// TIn = float: logits as the vocabulary GEMM accumulated them (predict surface, v2).  TIn = bf16: the training step's
+// vocabulary GEMM stores its logits ONCE, as bf16, straight into the dlogits buffer, and this kernel turns them into
+// dlogits IN PLACE (dz == logits): the fp32 [T*B, V] logits (2.6 GB written + read per cfg3 step) never exist.
+// V % 8 == 0.  In place is safe: every thread re-reads exactly the elements it then overwrites, after the row
+// statistics (first pass) are complete.
+template <typename TIn>
+__global__ void __launch_bounds__(256) softmax_xent_kernel(const TIn *logits, long long ld, int V,
                                                            const int32_t *__restrict__ tgt, float inv_count,
-                                                           __nv_bfloat16 *__restrict__ dz, long long ld_dz,
+                                                           __nv_bfloat16 *dz, long long ld_dz,
                                                            float *__restrict__ rowloss) {
     const long long r = blockIdx.x;
-    const float *z = logits + r * ld;
+    const TIn *z = logits + r * ld;
     __nv_bfloat16 *g = dz + r * ld_dz;
     const int y = tgt[r];
     __shared__ float red[2][8];
     float mx = -INFINITY, sum = 0.f;
-    for (int j = threadIdx.x * 4; j < V; j += 256 * 4) {
-        float v[4];
-        if (j + 4 <= V) {
-            const float4 q = *reinterpret_cast<const float4 *>(z + j);
-            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        } else {
-            for (int i = 0; i < 4; ++i) v[i] = (j + i < V) ? z[j + i] : -INFINITY;
-        }
-        const float m4 = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
-        if (m4 > mx) { sum *= __expf(mx - m4); mx = m4; }
-        for (int i = 0; i < 4; ++i) sum += __expf(v[i] - mx);
+    for (int j = threadIdx.x * 8; j < V; j += 256 * 8) {
+        float v[8];
+        load8<TIn>(z + j, v);
+        float m8 = v[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) m8 = fmaxf(m8, v[i]);
+        if (m8 > mx) { sum *= __expf(mx - m8); mx = m8; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum += __expf(v[i] - mx);
     }
     for (int o = 16; o > 0; o >>= 1) {
         const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
         const float nm = fmaxf(mx, om);
-        sum = sum * __expf(mx - nm) + os * __expf(om - nm);
+        sum = (mx > -INFINITY ? sum * __expf(mx - nm) : 0.f) + (om > -INFINITY ? os * __expf(om - nm) : 0.f);
         mx = nm;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -253,32 +273,32 @@ __global__ void __launch_bounds__(256) softmax_xent_kernel(const float *__restri
     float gm = red[0][0];
     for (int i = 1; i < 8; ++i) gm = fmaxf(gm, red[0][i]);
     float gs = 0.f;
-    for (int i = 0; i < 8; ++i) gs += red[1][i] * __expf(red[0][i] - gm);
+    for (int i = 0; i < 8; ++i) gs += red[0][i] > -INFINITY ? red[1][i] * __expf(red[0][i] - gm) : 0.f;
     const float inv = 1.0f / gs;
     bool live = y >= 0;
+    float py = 0.f;
+    if (live) py = __expf((float)z[y] - gm) * inv;
+    __syncthreads();                                       // z[y] is read by every thread before anyone overwrites it (in place)
     if (live) {
-        const float py = __expf(z[y] - gm) * inv;
         if (threadIdx.x == 0) rowloss[r] = -logf(fminf(fmaxf(py, 1e-7f), 1.0f - 1e-7f));
         live = py > 1e-7f && py < 1.0f - 1e-7f;
     } else if (threadIdx.x == 0) {
         rowloss[r] = 0.f;
     }
     const float sc = live ? inv_count : 0.f;
-    for (int j = threadIdx.x * 4; j < V; j += 256 * 4) {
-        if (j + 4 <= V) {
-            const float4 q = *reinterpret_cast<const float4 *>(z + j);
-            float p[4] = {__expf(q.x - gm) * inv, __expf(q.y - gm) * inv, __expf(q.z - gm) * inv, __expf(q.w - gm) * inv};
-            if (y >= j && y < j + 4) p[y - j] -= 1.0f;
-            __nv_bfloat162 lo = __floats2bfloat162_rn(p[0] * sc, p[1] * sc), hi = __floats2bfloat162_rn(p[2] * sc, p[3] * sc);
-            uint2 pk = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
-            *reinterpret_cast<uint2 *>(g + j) = pk;
-        } else {
-            for (int i = 0; j + i < V; ++i) {
-                float p = __expf(z[j + i] - gm) * inv;
-                if (y == j + i) p -= 1.0f;
-                g[j + i] = __float2bfloat16_rn(p * sc);
-            }
+    for (int j = threadIdx.x * 8; j < V; j += 256 * 8) {
+        float v[8];
+        load8<TIn>(z + j, v);
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float p0 = __expf(v[2 * i] - gm) * inv, p1 = __expf(v[2 * i + 1] - gm) * inv;
+            if (y == j + 2 * i) p0 -= 1.0f;
+            if (y == j + 2 * i + 1) p1 -= 1.0f;
+            __nv_bfloat162 pk = __floats2bfloat162_rn(p0 * sc, p1 * sc);
+            w[i] = *reinterpret_cast<uint32_t *>(&pk);
         }
+        *reinterpret_cast<uint4 *>(g + j) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -625,6 +645,7 @@ static int dropout_build_weights(Decoder &D, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // Teacher-forced forward up to the logits [T*B, V] (time-major) with every activation the backward needs.
 int Decoder::train_forward(const void *feats, int kind, int B, const int32_t *gt, const int32_t *targets, cudaStream_t s) {
+    const bool want_bf16_logits = train_logits_bf16;                   // set by train_step only: predict() keeps fp32 logits
     PdlScope pdl;                                          // chained GEMMs overlap their prologues with the predecessor's tail
     if (int rc = check_ready(B)) return rc;
     DC_REQUIRE(cfg.arch == DC_ARCH_V1 && cfg.dtype == DC_DTYPE_BF16, "the training graph is served by the bf16 v1 decoder");
@@ -731,7 +752,20 @@ int Decoder::train_forward(const void *feats, int kind, int B, const int32_t *gt
         e.addend = ws.d1f; e.ld_addend = kDense; e.addend_mod = B; e.relu = 1; e.out_bf16 = t.d_all; e.ld_bf16 = kDense;
         if (int rc = gemm_bf16_tc(tc_op(h2_all, ld_h2), tc_op(b.wd1h, U), e, (int)R, kDense, U, kEpiStore, s)) return rc;
         TcEpilogue v;
-        v.bias = W("imgcap_lstm_d2/bias"); v.out_f32 = t.logits; v.ld_f32 = V;
+        v.bias = W("imgcap_lstm_d2/bias");
+        static const bool f32_logits_env = getenv("DCAP_TRAIN_F32_LOGITS") != nullptr;
+        t.logits_in_dz = want_bf16_logits && !f32_logits_env;
+        if (t.logits_in_dz) {
+            v.out_bf16 = t.dz; v.ld_bf16 = V;                              // turned into dlogits in place by softmax_xent_kernel
+        } else {
+            if (!t.logits) {
+                const size_t Bp = round_up(t.B, 128);
+                const cudaError_t e = cudaMalloc((void **)&t.logits, 4 * (size_t)t.T * Bp * V);
+                if (e != cudaSuccess) return set_error(DC_ERR_CUDA, "fp32 logits allocation failed: %s", cudaGetErrorString(e));
+                t.owned.push_back(t.logits);
+            }
+            v.out_f32 = t.logits; v.ld_f32 = V;
+        }
         if (int rc = gemm_bf16_tc(tc_op(t.d_all, kDense), tc_op(b.wd2, kDense), v, (int)R, V, kDense, kEpiStore, s)) return rc;
     }
     t.x0_used = x0;
@@ -742,7 +776,10 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
                         float *loss, cudaStream_t s) {
     DC_REQUIRE(loss, "null loss pointer");
     PdlScope pdl;
-    if (int rc = train_forward(feats, kind, B, gt, targets, s)) return rc;
+    train_logits_bf16 = true;
+    const int frc = train_forward(feats, kind, B, gt, targets, s);
+    train_logits_bf16 = false;
+    if (frc) return frc;
     if (int rc = ensure_grads()) return rc;
     Bf16State &b = *bf;
     if (int rc = refresh_train_weights(s)) return rc;
@@ -765,7 +802,10 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     // softmax + cross-entropy + dlogits: one CTA per row keeps ~10 rows in flight per SM, which is what makes
     // this kernel run at HBM speed (a variant that kept rows in registers and accumulated the vocabulary-bias
     // gradient in place was latency-bound on its per-row barrier and measured 0.7 ms SLOWER per step)
-    softmax_xent_kernel<<<(unsigned)R, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
+    if (t.logits_in_dz)
+        softmax_xent_kernel<__nv_bfloat16><<<(unsigned)R, 256, 0, s>>>(t.dz, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
+    else
+        softmax_xent_kernel<float><<<(unsigned)R, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
     DC_CHECK_LAUNCH();
     reduce_loss_kernel<<<1, 1024, 0, s>>>(t.rowloss, R, inv_count, loss);
     DC_CHECK_LAUNCH();
@@ -1090,7 +1130,7 @@ int Decoder::train_step_v2(const void *feats, int kind, int B, const int32_t *wo
     }
     // ---------------- loss ----------------
     DC_CHECK_CUDA(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)n_train, s));
-    softmax_xent_kernel<<<(unsigned)B, 256, 0, s>>>(t.v2_logits, V, V, targets, inv_count, t.v2_dz, V, t.v2_rowloss);
+    softmax_xent_kernel<float><<<(unsigned)B, 256, 0, s>>>(t.v2_logits, V, V, targets, inv_count, t.v2_dz, V, t.v2_rowloss);
     DC_CHECK_LAUNCH();
     reduce_loss_kernel<<<1, 1024, 0, s>>>(t.v2_rowloss, B, inv_count, loss);
     DC_CHECK_LAUNCH();
