@@ -102,9 +102,6 @@ Decoder::~Decoder() {
     if (host_pipe) free_host_pipe(host_pipe);
     drop_graphs();
     free_train();
-    if (lane_stream) cudaStreamDestroy(lane_stream);
-    if (lane_fork) cudaEventDestroy(lane_fork);
-    if (lane_join) cudaEventDestroy(lane_join);
     if (graph_stream) cudaStreamDestroy(graph_stream);
     if (graph_ev_in) cudaEventDestroy(graph_ev_in);
     if (graph_ev_out) cudaEventDestroy(graph_ev_out);

@@ -61,8 +61,6 @@ struct Decoder {
     cudaStream_t graph_stream = nullptr;
     cudaEvent_t graph_ev_in = nullptr, graph_ev_out = nullptr;
     bool use_graphs = true;
-    cudaStream_t lane_stream = nullptr;               // second lane of the two-lane greedy decode (decoder_bf16.cu)
-    cudaEvent_t lane_fork = nullptr, lane_join = nullptr;
     size_t roi_buf_bytes = 0;
     // One flat fp32 arena for all weights: trainable tensors first (declaration order), frozen ones
     // after, so that gradients / optimiser state / the NCCL all-reduce are single contiguous ranges.

@@ -225,37 +225,27 @@ int Decoder::reset_state_bf16(int R, cudaStream_t s) {
 
 // the three GEMMs up to the Dense(1024) activations; leaves d (bf16) ready for the vocab GEMM
 // addend_div > 0: rows are (RoI, beam) pairs and the per-RoI terms g1f / d1f are indexed by row / addend_div
-// rows [row0, row0 + R) of the batch, operand parity p (the caller toggles it once per step)
-static int step_core_rows(Decoder &D, int row0, int R, int p, const float *g1f, const float *d1f, bool gather, cudaStream_t s,
-                          int addend_div = 0) {
-    Bf16State &b = *D.bf;
-    const DcDecoderConfig &cfg = D.cfg;
-    const int E = cfg.embed, U = cfg.units, V = cfg.vocab, K1 = b.Epad + U;
-    const size_t r0 = (size_t)row0;
-    int32_t *tok = D.ws.tok + r0;
-    __nv_bfloat16 *x1 = b.X1[p] + r0 * K1, *x1n = b.X1[p ^ 1] + r0 * K1, *x2 = b.X2[p] + r0 * 2 * U, *x2n = b.X2[p ^ 1] + r0 * 2 * U;
-    // gather == false: the embedding rows were already placed in X1[p] by the previous step's merge kernel
-    if (gather)
-        if (int rc = embed_gather(D.W("imgcap_embedding_layer/embeddings"), tok, R, E, V, x1, K1, true, s)) return rc;
-    TcEpilogue c1;
-    c1.addend = g1f; c1.ld_addend = 4 * U; c1.addend_div = addend_div; c1.cell_c = D.ws.c1 + r0 * U; c1.cell_units = U; c1.cell_tok = tok;
-    c1.cell_h_prev = x1 + b.Epad; c1.ld_h_prev = K1;
-    c1.cell_h_a = x1n + b.Epad; c1.ld_h_a = K1;
-    c1.cell_h_b = x2; c1.ld_h_b = 2 * U;
-    if (int rc = gemm_bf16_tc(op(x1, K1), op(b.w1cat, K1), c1, R, 4 * U, K1, kEpiCell, s)) return rc;
-    TcEpilogue c2;
-    c2.bias = b.b2_i; c2.cell_c = D.ws.c2 + r0 * U; c2.cell_units = U; c2.cell_tok = tok;
-    c2.cell_h_prev = x2 + U; c2.ld_h_prev = 2 * U;
-    c2.cell_h_a = x2n + U; c2.ld_h_a = 2 * U;
-    if (int rc = gemm_bf16_tc(op(x2, 2 * U), op(b.w2cat, 2 * U), c2, R, 4 * U, 2 * U, kEpiCell, s)) return rc;
-    TcEpilogue d1;
-    d1.addend = d1f; d1.ld_addend = kDense; d1.addend_div = addend_div; d1.relu = 1; d1.out_bf16 = b.d + r0 * kDense; d1.ld_bf16 = kDense;
-    return gemm_bf16_tc(op(x2n + U, 2 * U), op(b.wd1h, U), d1, R, kDense, U, kEpiStore, s);
-}
-
 static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, bool gather, cudaStream_t s, int addend_div = 0) {
     Bf16State &b = *D.bf;
-    if (int rc = step_core_rows(D, 0, R, b.parity, g1f, d1f, gather, s, addend_div)) return rc;
+    const DcDecoderConfig &cfg = D.cfg;
+    const int E = cfg.embed, U = cfg.units, V = cfg.vocab, K1 = b.Epad + U, p = b.parity;
+    // gather == false: the embedding rows were already placed in X1[p] by the previous step's merge kernel
+    if (gather)
+        if (int rc = embed_gather(D.W("imgcap_embedding_layer/embeddings"), D.ws.tok, R, E, V, b.X1[p], K1, true, s)) return rc;
+    TcEpilogue c1;
+    c1.addend = g1f; c1.ld_addend = 4 * U; c1.addend_div = addend_div; c1.cell_c = D.ws.c1; c1.cell_units = U; c1.cell_tok = D.ws.tok;
+    c1.cell_h_prev = b.X1[p] + b.Epad; c1.ld_h_prev = K1;
+    c1.cell_h_a = b.X1[p ^ 1] + b.Epad; c1.ld_h_a = K1;
+    c1.cell_h_b = b.X2[p]; c1.ld_h_b = 2 * U;
+    if (int rc = gemm_bf16_tc(op(b.X1[p], K1), op(b.w1cat, K1), c1, R, 4 * U, K1, kEpiCell, s)) return rc;
+    TcEpilogue c2;
+    c2.bias = b.b2_i; c2.cell_c = D.ws.c2; c2.cell_units = U; c2.cell_tok = D.ws.tok;
+    c2.cell_h_prev = b.X2[p] + U; c2.ld_h_prev = 2 * U;
+    c2.cell_h_a = b.X2[p ^ 1] + U; c2.ld_h_a = 2 * U;
+    if (int rc = gemm_bf16_tc(op(b.X2[p], 2 * U), op(b.w2cat, 2 * U), c2, R, 4 * U, 2 * U, kEpiCell, s)) return rc;
+    TcEpilogue d1;
+    d1.addend = d1f; d1.ld_addend = kDense; d1.addend_div = addend_div; d1.relu = 1; d1.out_bf16 = b.d; d1.ld_bf16 = kDense;
+    if (int rc = gemm_bf16_tc(op(b.X2[p ^ 1] + U, 2 * U), op(b.wd1h, U), d1, R, kDense, U, kEpiStore, s)) return rc;
     b.parity ^= 1;
     return DC_OK;
 }
@@ -268,67 +258,33 @@ int Decoder::v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_
     return gemm_bf16_tc(op(bf->d, kDense), op(bf->wd2, kDense), e, R, cfg.vocab, kDense, kEpiStore, s);
 }
 
-// greedy fast path: tokens only, the [B,V] logits never exist.
-// Rows are independent, so a large batch is decoded as TWO LANES: rows [0, B0) on `s`, rows [B0, B) on the handle's
-// lane stream, every GEMM limited to half of the SMs.  The two chains of persistent kernels run side by side and fill
-// each other's launch gaps, pipeline fills and last-wave tails (each of the 4 GEMMs of a step leaves ~8 us of those
-// exposed when it runs alone); the fork / join events are captured into the CUDA graph with everything else.
+// greedy fast path: tokens only, the [B,V] logits never exist
+// (Round 2 tried decoding the batch as two lanes -- half-batches on two streams, every GEMM limited to half of the
+// SMs so that the two chains run side by side -- to hide launch gaps and tile-wave tails: 4.09 ms against 4.04 ms per
+// 8000 RoIs, no gain; inside the CUDA graph the kernels already run back to back, and their inefficiency is in the
+// main loop / epilogue, not between launches.  Removed.)
 int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s, float *scores) {
-    const int P = cfg.padding, V = cfg.vocab, K1 = bf->Epad + cfg.units;
+    const int P = cfg.padding, V = cfg.vocab;
     if (int rc = head(feats, kind, B, ws.F, s)) return rc;
     if (int rc = v1_hoist(B, s)) return rc;
     if (int rc = v1_reset_state(B, s)) return rc;
     if (int rc = fill_i32(ws.tok, B, 1, s)) return rc;
     const int slots = gemm_tc_argmax_tiles(V);
-    static const int env_lanes = getenv("DCAP_LANES") ? atoi(getenv("DCAP_LANES")) : 2;
-    static const int env_lane_min = getenv("DCAP_LANE_MIN_ROWS") ? atoi(getenv("DCAP_LANE_MIN_ROWS")) : 4096;
-    const bool two = env_lanes >= 2 && B >= env_lane_min;
-    const int B0 = two ? ((B / 2 + 255) / 256) * 256 : B;              // lane boundary on a 256-row tile edge
-    const int row0[2] = {0, B0}, rows[2] = {B0, B - B0};
-    cudaStream_t ls[2] = {s, s};
-    if (two) {
-        if (!lane_stream) {
-            DC_CHECK_CUDA(cudaStreamCreateWithFlags(&lane_stream, cudaStreamNonBlocking));
-            DC_CHECK_CUDA(cudaEventCreateWithFlags(&lane_fork, cudaEventDisableTiming));
-            DC_CHECK_CUDA(cudaEventCreateWithFlags(&lane_join, cudaEventDisableTiming));
-        }
-        ls[1] = lane_stream;
-        DC_CHECK_CUDA(cudaEventRecord(lane_fork, s));
-        DC_CHECK_CUDA(cudaStreamWaitEvent(lane_stream, lane_fork, 0));
-        gemm_tc_set_sm_limit(sm_count() / 2);
-    }
-    int rc = DC_OK;
-    int p = bf->parity;
-    for (int t = 0; t < P && rc == DC_OK; ++t) {
+    for (int t = 0; t < P; ++t) {
+        if (int rc = step_core(*this, B, ws.g1f, ws.d1f, t == 0, s)) return rc;
+        TcEpilogue e;
+        e.bias = W("imgcap_lstm_d2/bias"); e.partial = bf->partial;
+        // caption scores need the softmax probability of the arg-max: the epilogue also sums exp(v - max)
+        if (int rc = gemm_bf16_tc(op(bf->d, kDense), op(bf->wd2, kDense), e, B, V, kDense, scores ? kEpiArgmaxSum : kEpiArgmax, s)) return rc;
+        // token of this step + its embedding row, written into the operand buffer of step t+1
         const bool more = t + 1 < P;
-        for (int l = 0; l < (two ? 2 : 1) && rc == DC_OK; ++l) {
-            const size_t r0 = (size_t)row0[l];
-            rc = step_core_rows(*this, row0[l], rows[l], p, ws.g1f + r0 * 4 * cfg.units, ws.d1f + r0 * kDense, t == 0, ls[l]);
-            if (rc) break;
-            TcEpilogue e;
-            e.bias = W("imgcap_lstm_d2/bias"); e.partial = bf->partial + r0 * slots * 4;
-            // caption scores need the softmax probability of the arg-max: the epilogue also sums exp(v - max)
-            rc = gemm_bf16_tc(op(bf->d + r0 * kDense, kDense), op(bf->wd2, kDense), e, rows[l], V, kDense,
-                              scores ? kEpiArgmaxSum : kEpiArgmax, ls[l]);
-            if (rc) break;
-            // token of this step + its embedding row, written into the operand buffer of step t+1
-            rc = argmax_merge(bf->partial + r0 * slots * 4, rows[l], slots, tokens + r0 * P + t, P, ws.tok + r0,
-                              scores ? ws.cand_p + r0 : nullptr, ls[l], more ? bf->emb : nullptr, bf->Epad,
-                              more ? bf->X1[p ^ 1] + r0 * K1 : nullptr, K1);
-            if (rc) break;
-            if (scores) rc = accumulate_log(scores + r0, ws.cand_p + r0, rows[l], t == 0, ls[l]);
-        }
-        p ^= 1;
+        if (int rc = argmax_merge(bf->partial, B, slots, tokens + t, P, ws.tok, scores ? ws.cand_p : nullptr, s,
+                                  more ? bf->emb : nullptr, bf->Epad, more ? bf->X1[bf->parity] : nullptr,
+                                  bf->Epad + cfg.units)) return rc;
+        if (scores)
+            if (int rc = accumulate_log(scores, ws.cand_p, B, t == 0, s)) return rc;
     }
-    bf->parity = p;
-    if (two) {
-        gemm_tc_set_sm_limit(0);
-        const cudaError_t e1 = cudaEventRecord(lane_join, lane_stream);       // always re-join (stream capture needs it)
-        const cudaError_t e2 = cudaStreamWaitEvent(s, lane_join, 0);
-        if (rc == DC_OK && (e1 != cudaSuccess || e2 != cudaSuccess))
-            rc = set_error(DC_ERR_CUDA, "lane join failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    }
-    return rc;
+    return DC_OK;
 }
 
 void Decoder::drop_graphs() {

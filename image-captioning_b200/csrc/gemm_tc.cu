@@ -23,15 +23,6 @@
 
 namespace dcap {
 
-// Launches of this host thread use at most this many SMs (0 = all): two independent chains of persistent GEMMs on two
-// streams, each limited to half of the SMs, run side by side and hide each other's launch gaps, pipeline fills and
-// tails (decoder_bf16.cu: two-lane greedy decoding).
-static thread_local int tl_sm_limit = 0;
-static inline int eff_sms() {
-    const int n = sm_count();
-    return tl_sm_limit > 0 && tl_sm_limit < n ? tl_sm_limit : n;
-}
-
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
@@ -971,7 +962,7 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const CUtenso
     auto kern = gemm_bf16_tc_kernel<kBlockN, kEpi>;
     DC_CHECK_CUDA(once_per_device(attr_set, [&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes); }));
     const int units = ceil_div(g.M, kBlockM) * ceil_div(g.N, kBlockN) * g.splits;
-    const int grid = units < eff_sms() ? units : eff_sms();
+    const int grid = units < sm_count() ? units : sm_count();
     DC_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreads), (size_t)(g.tma_out ? S::kBytes : S::kBaseBytes), stream, ma, mb, mo,
                              mc ? *mc : ma, ep, g));
     return DC_OK;
@@ -1202,7 +1193,7 @@ static int launch_tc2(const CUtensorMap &ma, const CUtensorMap &mb, const CUtens
         return e != cudaSuccess ? e : cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
     }));
     const int tiles = ceil_div(g.M, 2 * kBlockM) * ceil_div(g.N, 256) * g.splits;
-    const int pairs = tiles < eff_sms() / 2 ? tiles : eff_sms() / 2;
+    const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = g.tma_out ? S::kBytes : S::kBaseBytes; cfg.stream = stream;
@@ -1216,13 +1207,11 @@ static int launch_tc2(const CUtensorMap &ma, const CUtensorMap &mb, const CUtens
     return DC_OK;
 }
 
-void gemm_tc_set_sm_limit(int sms) { tl_sm_limit = sms; }
-
 int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, int M, int N, int K, int epi,
                  cudaStream_t stream, int split_k) {
     if (M <= 0 || N <= 0) return DC_OK;
     DC_REQUIRE(K > 0 && A.ptr && B.ptr, "gemm_bf16_tc: bad arguments");
-    const int sms = eff_sms();
+    const int sms = sm_count();
     const int num_kb = ceil_div(K, kBlockK);
     const int tiles_m = ceil_div(M, kBlockM);
     // tile width: 256 columns unless that leaves most SMs without a tile and 128 fills more of them

@@ -60,7 +60,6 @@ struct TcEpilogue {
 int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, int M, int N, int K, int epi,
                  cudaStream_t stream, int split_k = 1);
 int gemm_tc_argmax_tiles(int N);
-void gemm_tc_set_sm_limit(int sms);   // this host thread's GEMM launches use at most `sms` SMs (0 = all)
 // merges the kEpiTopK partials: per row the k largest softmax probabilities in ASCENDING order (ties: the larger
 // index ranks higher, as a stable ascending argsort followed by [-k:]) -> idx_out / p_out [rows, k]
 int topk_merge(const float *partial, int rows, int slots, int k, int32_t *idx_out, float *p_out, cudaStream_t s);

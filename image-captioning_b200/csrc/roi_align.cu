@@ -1164,7 +1164,7 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
     DC_REQUIRE(total < (1ll << 31), "n_images*n_boxes must fit in int32");
     const int rec_len = 1 + pool_h + pool_w;
 
-    static const int path = getenv("DCAP_ROI_PATH") ? atoi(getenv("DCAP_ROI_PATH")) : 3;
+    static const int path = getenv("DCAP_ROI_PATH") ? atoi(getenv("DCAP_ROI_PATH")) : 2;
     // ---- paths 2 / 3 (round 2): locality order (one small CTA per image) -> wide record pre-pass -> gather or ring ----
     {
         const unsigned px_b = (unsigned)channels * 4u, slot_b = 2u * (unsigned)pool_w * px_b;
