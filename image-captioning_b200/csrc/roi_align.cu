@@ -240,7 +240,7 @@ __device__ __forceinline__ void store_out(void *out, long long idx4, const float
     }
 }
 
-template <int kUnroll, int kMaxReg, bool kBf16>
+template <int kUnroll, int kMaxReg, bool kBf16, bool kDedupe = false>
 __global__ void __maxnreg__(kMaxReg)
 roi_align_stream_kernel(const RoiStreamParams p) {
     const int lane = threadIdx.x & 31;
@@ -269,6 +269,7 @@ roi_align_stream_kernel(const RoiStreamParams p) {
                     float4 tl[kUnroll], tr[kUnroll], bl[kUnroll], br[kUnroll];
                     float lx[kUnroll];
                     bool ok[kUnroll];
+                    int pl = -1, pr = -1;                    // tap offsets of the previous bin of this group (warp-uniform)
 #pragma unroll
                     for (int k = 0; k < kUnroll; ++k) {
                         ok[k] = false;
@@ -277,10 +278,15 @@ roi_align_stream_kernel(const RoiStreamParams p) {
                             ok[k] = act && ye.w && xe.w;
                             lx[k] = __int_as_float(xe.z);
                             if (ok[k]) {
-                                tl[k] = __ldg(row_t + xe.x + c);
-                                tr[k] = __ldg(row_t + xe.y + c);
-                                bl[k] = __ldg(row_b + xe.x + c);
-                                br[k] = __ldg(row_b + xe.y + c);
+                                // neighbouring samples less than two pixels apart share a tap column: re-use the registers
+                                // (kDedupe: the L2 -> SM tap traffic, not DRAM, is what bounds this kernel)
+                                if (kDedupe && k > 0 && ok[k - 1] && xe.x == pr) { tl[k] = tr[k - 1]; bl[k] = br[k - 1]; }
+                                else if (kDedupe && k > 0 && ok[k - 1] && xe.x == pl) { tl[k] = tl[k - 1]; bl[k] = bl[k - 1]; }
+                                else { tl[k] = __ldg(row_t + xe.x + c); bl[k] = __ldg(row_b + xe.x + c); }
+                                if (kDedupe && xe.y == xe.x) { tr[k] = tl[k]; br[k] = bl[k]; }
+                                else if (kDedupe && k > 0 && ok[k - 1] && xe.y == pr) { tr[k] = tr[k - 1]; br[k] = br[k - 1]; }
+                                else { tr[k] = __ldg(row_t + xe.y + c); br[k] = __ldg(row_b + xe.y + c); }
+                                pl = xe.x; pr = xe.y;
                             }
                         }
                     }
@@ -853,6 +859,9 @@ struct RoiRing2Params {
     int slots;            // K row slots in the ring
     unsigned slot_bytes;  // 2*pw pixels
     int diag;
+    int nprod;            // producer warps (1 or 2): warp q issues the row positions r with r % nprod == q
+    int groups;           // consumer warp groups: group g computes the sample rows by with by % groups == g
+    int only_new;         // wait only for the rows that are new at this sample (the others were waited for one sample earlier)
     unsigned long long *prof;
 };
 
@@ -861,13 +870,14 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring2_kernel(const RoiRing2P
     using namespace ring;
     using namespace ring2;
     extern __shared__ __align__(128) unsigned char ring_smem[];
-    __shared__ int4 s_run[2 * kMaxSamples];                // producer scratch: this RoI's pixel runs
+    __shared__ int4 s_run[2][2 * kMaxSamples];             // producer scratch (per producer warp): this RoI's pixel runs
     const int K = p.slots;
     unsigned char *slots = ring_smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring_smem + (size_t)K * p.slot_bytes);
     uint64_t *empty = full + K;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ncons = (blockDim.x >> 5) - 1;
+    const int nprod = p.nprod;
+    const int ncons = (blockDim.x >> 5) - nprod;
     const uint32_t px_bytes = (uint32_t)p.c4 * 16u;
     if (threadIdx.x == 0) {
         for (int i = 0; i < K; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, ncons); }
@@ -880,8 +890,9 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring2_kernel(const RoiRing2P
     long long tk = clock64();
     auto tick = [&](int i) { if (p.prof) { const long long now = clock64(); pc[i] += (unsigned long long)(now - tk); tk = now; } };
 
-    if (warp == 0) {
-        // ------------------------------- producer -------------------------------
+    if (warp < nprod) {
+        // ------------------------------- producers -------------------------------
+        int4 *my_runs = s_run[warp];
         int spos = blockIdx.x;
         int4 hdr = make_int4(0, 0, 0, 0), hdr2 = hdr, myrun = hdr;
         int myrow = 0;
@@ -903,12 +914,12 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring2_kernel(const RoiRing2P
             const int ny = chdr.w & 255, nq = (chdr.w >> 8) & 255, nruns = (chdr.w >> 16) & 255;
             const float4 *base = reinterpret_cast<const float4 *>(((unsigned long long)(unsigned)chdr.x) | ((unsigned long long)(unsigned)chdr.y << 32));
             __syncwarp();                                  // the previous RoI's run table is no longer read
-            if (lane < 16) s_run[lane] = crun;
+            if (lane < 16) my_runs[lane] = crun;
             __syncwarp();
             tick(0);
             for (int b0 = 0; b0 < ny; b0 += K) {
-                const int r = b0 + lane;
-                const bool mine = lane < K && r < ny;
+                const int r = b0 + lane * nprod + warp;            // this warp's positions: r % nprod == warp
+                const bool mine = lane * nprod + warp < K && r < ny;
                 int slot = headSlot + r, wraps = 0;
                 while (slot >= K) { slot -= K; ++wraps; }
                 const uint32_t par = (uint32_t)((headPhase + wraps) & 1) ^ 1u;
@@ -922,7 +933,7 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring2_kernel(const RoiRing2P
                     if (todo && mbar_try_wait(empty + slot, par)) {
                         mbar_expect_tx(full + slot, (p.diag & 2) ? 0u : (uint32_t)nq * px_bytes);
                         for (int i = 0; i < ((p.diag & 2) ? 0 : nruns); ++i) {
-                            const int4 rn = s_run[i];
+                            const int4 rn = my_runs[i];
                             bulk_load(dst_row + rn.x, src_row + rn.y, (uint32_t)rn.z, full + slot);
                         }
                         fired = true;
@@ -935,11 +946,13 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring2_kernel(const RoiRing2P
             while (headSlot >= K) { headSlot -= K; headPhase ^= 1; }
             tick(1);
         }
-        if (p.prof && lane == 0)
+        if (p.prof && lane == 0 && warp == 0)
             for (int i = 0; i < 2; ++i) atomicAdd(p.prof + i, pc[i]);
     } else {
         // ------------------------------- consumers -------------------------------
-        const int cw = warp - 1;
+        const int cw_all = warp - nprod;
+        const int per_group = ncons / p.groups;                // warps per group
+        const int grp = cw_all / per_group, cw = cw_all - grp * per_group;
         const int bins = p.ph * p.pw;
         int spos = blockIdx.x;
         int4 hdr = make_int4(0, 0, 0, 0), ylane = hdr;
@@ -962,7 +975,7 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring2_kernel(const RoiRing2P
             int slotOf = headSlot + lane, wraps = 0;
             while (slotOf >= K) { slotOf -= K; ++wraps; }
             const int parOf = (headPhase + wraps) & 1;
-            const bool single = p.pw <= ncons;                 // one bin column per warp: its x entry is loaded once per RoI
+            const bool single = p.pw <= per_group;             // one bin column per warp: its x entry is loaded once per RoI
             const int4 xe0 = (single && cw < p.pw) ? __ldg(rec + kX + cw) : make_int4(0, 0, 0, 0);
             tick(0);
             for (int by = 0; by < p.ph; ++by) {
@@ -973,13 +986,14 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring2_kernel(const RoiRing2P
                 const int sTop = __shfl_sync(0xffffffffu, slotOf, yPosLo), sBot = __shfl_sync(0xffffffffu, slotOf, yPosHi);
                 const int pTop = __shfl_sync(0xffffffffu, parOf, yPosLo), pBot = __shfl_sync(0xffffffffu, parOf, yPosHi);
                 if (yok) {
-                    mbar_wait(full + sTop, (uint32_t)pTop);
-                    mbar_wait(full + sBot, (uint32_t)pBot);
+                    if (!p.only_new || (yflags & 32)) mbar_wait(full + sTop, (uint32_t)pTop);
+                    if (!p.only_new || (yflags & 64)) mbar_wait(full + sBot, (uint32_t)pBot);
                 }
                 tick(1);
+                const bool mine_row = (by % p.groups) == grp;      // the other group(s) compute this sample row
                 const unsigned char *top = slots + (size_t)sTop * p.slot_bytes;
                 const unsigned char *bot = slots + (size_t)sBot * p.slot_bytes;
-                for (int bx = cw; bx < p.pw; bx += ncons) {
+                for (int bx = mine_row ? cw : p.pw; bx < p.pw; bx += per_group) {
                     const int4 xe = single ? xe0 : __ldg(rec + kX + bx);
                     const bool ok = yok && xe.w && !(p.diag & 1);
                     const float lx = __int_as_float(xe.z);
@@ -1021,7 +1035,7 @@ __global__ void __launch_bounds__(512, 1) roi_align_ring2_kernel(const RoiRing2P
             while (headSlot >= K) { headSlot -= K; headPhase ^= 1; }
             tick(3);
         }
-        if (p.prof && lane == 0 && cw == 0)
+        if (p.prof && lane == 0 && cw_all == 0)
             for (int i = 0; i < 4; ++i) atomicAdd(p.prof + 4 + i, pc[i]);
     }
 }
@@ -1222,8 +1236,14 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
                 if (ctas < 1) ctas = 1;
                 if (env_slots >= 4 && env_slots <= slots) slots = env_slots;
                 if (slots > ring::kMaxSlots) slots = ring::kMaxSlots;
-                int ncons = env_warps > 0 ? env_warps : (pool_w < 8 ? pool_w : 8);
-                if (ncons > 15) ncons = 15;
+                static const int env_prod = getenv("DCAP_ROI_PROD") ? atoi(getenv("DCAP_ROI_PROD")) : 1;
+                static const int env_groups = getenv("DCAP_ROI_GROUPS") ? atoi(getenv("DCAP_ROI_GROUPS")) : 1;
+                static const int env_only_new = getenv("DCAP_ROI_ONLY_NEW") ? atoi(getenv("DCAP_ROI_ONLY_NEW")) : 0;
+                const int nprod = env_prod >= 2 ? 2 : 1;
+                int groups = env_groups >= 1 && env_groups <= 4 ? env_groups : 1;
+                int ncons = env_warps > 0 ? env_warps : (pool_w < 8 ? pool_w : 8) * groups;
+                if (ncons > 16 - nprod) ncons = 16 - nprod;
+                if (ncons % groups) groups = 1;
                 const size_t smem = (size_t)slots * slot_b + fixed;
                 static std::atomic<unsigned long long> attr_set2{0};
                 e = once_per_device(attr_set2, [] {
@@ -1232,6 +1252,7 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
                 RoiRing2Params kp;
                 kp.records = rp.records; kp.c4 = channels / 4; kp.ph = pool_h; kp.pw = pool_w; kp.total = (int)total;
                 kp.out = out; kp.slots = slots; kp.slot_bytes = slot_b; kp.diag = env_diag; kp.prof = nullptr;
+                kp.nprod = nprod; kp.groups = groups; kp.only_new = env_only_new;
                 const long long mg = (long long)sm_count() * ctas;
                 static unsigned long long *prof_buf = nullptr;
                 static int prof_calls = 0;
@@ -1248,14 +1269,23 @@ static int launch(const float *boxes, const float *const fmaps[4], const int fm_
                     }
                 }
                 if (e == cudaSuccess)
-                    e = launch_pdl(roi_align_ring2_kernel<kBf16>, dim3((unsigned)(total < mg ? total : mg)), dim3((ncons + 1) * 32), smem, stream, kp);
+                    e = launch_pdl(roi_align_ring2_kernel<kBf16>, dim3((unsigned)(total < mg ? total : mg)), dim3((ncons + nprod) * 32), smem, stream, kp);
             } else if (e == cudaSuccess) {
                 RoiStreamParams sp;
                 sp.records = rp.records; sp.c4 = channels / 4; sp.parts = (sp.c4 + 31) / 32; sp.ph = pool_h; sp.pw = pool_w;
                 sp.out = out; sp.total = (int)total;
                 const int warps = pool_h < 7 ? pool_h : 7;
-                const long long mg = (long long)sm_count() * 4;
-                e = launch_pdl(roi_align_stream_kernel<2, 72, kBf16>, dim3((unsigned)(total < mg ? total : mg)), dim3(warps * 32), 0, stream, sp);
+                static const int g_ctas = getenv("DCAP_ROI_CTAS") ? atoi(getenv("DCAP_ROI_CTAS")) : 4;
+                static const int g_var = getenv("DCAP_ROI_VARIANT") ? atoi(getenv("DCAP_ROI_VARIANT")) : 0;
+                const long long mg = (long long)sm_count() * g_ctas;
+                const dim3 grid((unsigned)(total < mg ? total : mg)), block(warps * 32);
+                switch (g_var) {
+                    case 1: e = launch_pdl(roi_align_stream_kernel<2, 72, kBf16, true>, grid, block, 0, stream, sp); break;
+                    case 2: e = launch_pdl(roi_align_stream_kernel<4, 128, kBf16, true>, grid, block, 0, stream, sp); break;
+                    case 3: e = launch_pdl(roi_align_stream_kernel<4, 128, kBf16, false>, grid, block, 0, stream, sp); break;
+                    case 4: e = launch_pdl(roi_align_stream_kernel<7, 168, kBf16, true>, grid, block, 0, stream, sp); break;
+                    default: e = launch_pdl(roi_align_stream_kernel<2, 72, kBf16>, grid, block, 0, stream, sp); break;
+                }
             }
             if (e == cudaSuccess) e = cudaGetLastError();
             cudaFreeAsync(ws, stream);
