@@ -296,7 +296,7 @@ def run_ours_roi_features(args, ctx):
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
-    roofline = {"bound": "hbm", "kernel": "roi_order_kernel + roi_align_ring_kernel (fp32 output)", "achieved": round(achieved, 1),
+    roofline = {"bound": "hbm", "kernel": "roi_order_kernel + roi_gather_records_kernel + roi_align_stream_kernel (fp32 output)", "achieved": round(achieved, 1),
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
                 "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
@@ -310,8 +310,7 @@ def run_ours_roi_features(args, ctx):
             pass
 
     if args.no_e2e:
-        return {"ms_per_step": round(ms_per_step, 5), "roofline_frac": roofline["frac"],
-                "path": os.environ.get("DCAP_ROI_PATH"), "ctas": os.environ.get("DCAP_ROI_CTAS")}
+        return {"ms_per_step": round(ms_per_step, 5), "roofline_frac": roofline["frac"]}
     # ---- e2e: host buffers through the C-ABI host entry point ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h_boxes = torch.from_numpy(boxes_np).pin_memory()
@@ -533,7 +532,7 @@ def run_ours_captions(args, ctx):
     alg_bytes = 4 * CHANNELS * t_unique + 2 * CHANNELS * POOL[0] * POOL[1] * R        # fp32 taps in, bf16 rows out
     hbm_peak, hbm_src = measured_peaks("hbm_gbs")
     achieved_gb = alg_bytes / (roi_ms * 1e-3) / 1e9
-    roofline_hbm = {"bound": "hbm", "kernel": "roi_order_kernel + roi_align_ring_kernel (bf16 output)",
+    roofline_hbm = {"bound": "hbm", "kernel": "roi_order_kernel + roi_gather_records_kernel + roi_align_stream_kernel (bf16 output)",
                     "achieved": round(achieved_gb, 1), "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
                     "frac": round(achieved_gb / hbm_peak, 4), "frac_of_nominal_8000": round(achieved_gb / 8000.0, 4),
                     "traffic": None, "algorithmic_bytes_per_step": alg_bytes, "t_unique_pixels": t_unique,

@@ -421,6 +421,15 @@ int Decoder::roi_feature_buffer(int R, void **out) {
 int Decoder::ensure_rep(int R) {
     if (R <= rep_cap) return DC_OK;
     const size_t U = cfg.units;
+    // growth: the previous (smaller) buffers are released here, not kept on the workspace list until the next reserve()
+    for (float **p : {&rep_g1f, &rep_d1f}) {
+        if (!*p) continue;
+        for (auto it = ws_owned.begin(); it != ws_owned.end(); ++it)
+            if (*it == *p) { ws_owned.erase(it); break; }
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    rep_cap = 0;
     if (int rc = dev_alloc((void **)&rep_g1f, sizeof(float) * (size_t)R * 4 * U, ws_owned)) return rc;
     if (int rc = dev_alloc((void **)&rep_d1f, sizeof(float) * (size_t)R * kDense, ws_owned)) return rc;
     rep_cap = R;

@@ -306,6 +306,7 @@ int Decoder::greedy_bf16_graphed(const void *feats, int kind, int B, int32_t *to
     const GraphKey key(feats, kind, B, (void *)internal);
     auto it = graphs.find(key);
     if (it == graphs.end()) {
+        if (graph_calls.size() >= 64) graph_calls.clear();          // callers that pass a fresh feats pointer every call never capture: bound the map
         if (++graph_calls[key] < 2) return greedy_bf16(feats, kind, B, tokens, s);   // first call: eager
         if (!graph_stream) {
             DC_CHECK_CUDA(cudaStreamCreateWithFlags(&graph_stream, cudaStreamNonBlocking));

@@ -255,7 +255,7 @@ def test_joint_model_gradient_chain_into_roi_align():
     g1 = m.get_gradients()["imgcap_lstm_d2/kernel"]
     m.train_step_device(feats, gt)
     assert np.array_equal(g1, m.get_gradients()["imgcap_lstm_d2/kernel"]) or _rel_l2(m.get_gradients()["imgcap_lstm_d2/kernel"], g1) < 1e-3
-    with pytest.raises(RuntimeError):
+    with pytest.raises((RuntimeError, ValueError)):            # the shim checks the shape, the C ABI the feature kind
         m.train_step_device(m.head_features(feats), gt, d_features=d_feats)
 
 
