@@ -301,11 +301,11 @@ def run_ours_roi_features(args, ctx):
                 "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
                 "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
                 "t_unique_pixels": t_unique, "kernel_ms": round(k_ms, 5)}
-    prof = os.path.join(ROOT, "profiles", "roi_align_traffic.json")
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
             with open(prof) as f:
-                roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
+                roofline["traffic"] = json.load(f).get("roi_align_f32_dram_bytes_per_launch")
         except Exception:
             pass
 
