@@ -199,7 +199,9 @@ roi_align_stream_kernel(const RoiStreamParams p) {
 //     RoIs: the ring has to be row-granular, and at ~12 rows x 8000 RoIs the per-row handshakes cost more than the
 //     ~25 % of L2 -> SM tap traffic the de-duplication saves;
 //   * re-using tap registers between neighbouring bins inside the gather kernel (the branch-free loads become
-//     conditional): 0.287 ms.
+//     conditional): 0.287 ms;
+//   * prefetch.global.L2 of the taps of the CTA's next RoI from inside the gather kernel: 0.221-0.228 ms (more requests,
+//     not fewer stalls: the memory system's request throughput on 1 KB granules is the bound, not latency).
 // What bounds the gather kernel is the L2 -> SM path: ~1.6 GB of taps per launch in ~0.14 ms = 11-12 TB/s, with DRAM at
 // the compulsory bytes (profiles/): close to what the part's L2 delivers to tcgen05 operand loads as well (section 9).
 // ---------------------------------------------------------------------------------------------
