@@ -323,6 +323,41 @@ def test_caption_rois_end_to_end_matches_two_stage_path():
     assert np.array_equal(got_dev.cpu().numpy(), want)
 
 
+def test_caption_rois_host_pipeline_submit_wait():
+    """dc_caption_rois_host_submit / _wait: several calls in flight (different boxes, different batch shapes, a larger
+    later call that forces the staging to grow) deliver exactly what the blocking call delivers, in order; the handle's
+    streams / staging are reused; wait() with nothing outstanding is a no-op."""
+    from oracle import roi_align as ra
+    rng = np.random.default_rng(43)
+    V, E, U, C, P = 300, 24, 64, 16, 6
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    m = _model_v1(w, P, V, E, U, C)
+    m.caption_rois_wait()                                          # nothing outstanding
+    calls = []
+    for B, N in ((2, 30), (3, 30), (1, 17), (4, 64), (2, 30)):
+        boxes = synth.synth_boxes(rng, B, N, 1024.0)
+        fms = [rng.standard_normal((B, 64 >> i, 64 >> i, C)).astype(np.float32) for i in range(4)]
+        feats, _ = ra.pyramid_roi_align(boxes, fms, (7, 7), (1024, 1024, 3))
+        want, _ = dec.greedy_v1(dec.head(feats[0], w), w, P)
+        calls.append((boxes, fms, want))
+    outs = []
+    for i, (boxes, fms, _) in enumerate(calls):
+        outs.append(m.caption_rois(boxes, fms, (1024, 1024, 3), wait=False))
+        if i >= 1:
+            m.caption_rois_wait()                                  # retires call i-1: at most two in flight
+            assert np.array_equal(outs[i - 1], calls[i - 1][2]), i - 1
+    m.caption_rois_wait()
+    assert np.array_equal(outs[-1], calls[-1][2])
+    m.caption_rois_wait()
+    # three submits without an explicit wait: the third retires the first by itself
+    o3 = [m.caption_rois(b, f, (1024, 1024, 3), wait=False) for b, f, _ in calls[:3]]
+    m.caption_rois_wait(); m.caption_rois_wait(); m.caption_rois_wait()
+    for o, (_, _, want) in zip(o3, calls[:3]):
+        assert np.array_equal(o, want)
+    # and the blocking form still works on the same handle
+    assert np.array_equal(m.caption_rois(calls[0][0], calls[0][1], (1024, 1024, 3)), calls[0][2])
+
+
 def test_fp32_path_matches_golden_decoder_vectors(golden_dir):
     """CUDA fp32 path against the committed golden vectors (tests/golden/decoder_small.npz)."""
     import os
