@@ -73,45 +73,70 @@ def measured_peaks(key="hbm_gbs"):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML in-process every 5 ms (the timed regions
+    are 0.1-1 s long; spawning nvidia-smi takes ~50 ms per sample), nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []            # (sm MHz, max MHz, set of reasons)
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and all(x.strip().isdigit() for x in visible.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                         "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                         "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                         "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.samples.append((mhz, self.max_mhz, {k for k, b in self.bits.items() if mask & b}))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            f = [x.strip() for x in out.split(",")]
+            self.samples.append((float(f[0]), float(f[1]), {n for n, v in zip(self.NAMES, f[2:6]) if v.lower().startswith("active")}))
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            self.stop_flag.wait(0.1)
+                if self.nvml is not None:
+                    self.nvml = None                     # fall back to nvidia-smi
+            self.stop_flag.wait(0.005 if self.nvml is not None else 0.1)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples]
+        reasons = set()
         for s in self.samples:
-            try:
-                sm.append(float(s[0])); mx.append(float(s[1]))
-            except Exception:
-                continue
-            for n, v in zip(names, s[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+            reasons |= s[2]
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def tap_unique_pixels(boxes, levels, fm_shapes, pool):
