@@ -107,6 +107,8 @@ struct Decoder {
     int reset_state_bf16(int R, cudaStream_t s);
     int v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_t s);
     int greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s, float *scores = nullptr);
+    bool greedy_loop_ok() const;                       // greedy_loop.cu: the whole loop as one persistent kernel
+    int greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_t s);
     int greedy_bf16_graphed(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s);
     void drop_graphs();
     int v2_begin_bf16(const void *feats, int kind, int B, cudaStream_t s);

@@ -168,6 +168,8 @@ int Decoder::reserve_bf16(size_t R) {
     rc |= A16(&b.roi, R * Kin); rc |= A16(&b.a1, R * F); rc |= A16(&b.Fb, R * F); rc |= A16(&b.d, R * kDense);
     for (int i = 0; i < 2; ++i) { rc |= A16(&b.X1[i], R * K1); rc |= A16(&b.X2[i], R * 2 * U); }
     rc |= dev_alloc((void **)&b.partial, sizeof(float) * 4 * R * gemm_tc_argmax_tiles(cfg.vocab), ws_owned);
+    b.loop_cnt_bytes = sizeof(unsigned) * (16 * ((R + 255) / 256) + 4);     // greedy_loop.cu: 8 counters per 128 rows + error word
+    rc |= dev_alloc((void **)&b.loop_cnt, b.loop_cnt_bytes, ws_owned);
     return rc;
 }
 
@@ -269,6 +271,8 @@ int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cu
     if (int rc = v1_hoist(B, s)) return rc;
     if (int rc = v1_reset_state(B, s)) return rc;
     if (int rc = fill_i32(ws.tok, B, 1, s)) return rc;
+    // the whole loop as one persistent kernel (greedy_loop.cu); DCAP_GREEDY_LOOP=0 keeps the launch-per-GEMM form below
+    if (greedy_loop_ok()) return greedy_loop_bf16(B, tokens, scores, s);
     const int slots = gemm_tc_argmax_tiles(V);
     for (int t = 0; t < P; ++t) {
         if (int rc = step_core(*this, B, ws.g1f, ws.d1f, t == 0, s)) return rc;

@@ -21,6 +21,8 @@ struct Bf16State {
     float *topk_partial = nullptr;                   // beam search: [rows, slots, 2 + 2k]
     size_t topk_cap = 0;
     int parity = 0;
+    unsigned int *loop_cnt = nullptr;                // greedy_loop.cu: dependency counters of the persistent decoding kernel
+    size_t loop_cnt_bytes = 0;
     // backward-pass operand copies: a bf16 mirror of the whole trainable arena (same offsets; written by the
     // optimiser kernel itself, or by one cast after set_weights); the Keras [in, out] tensors inside it are
     // the K-major B operands of dX = dY * W^T (N = in, K = out).  Pointers set by refresh_train_weights().

@@ -15,6 +15,7 @@
 //               -> partial[m, n_tile]; the [M,V] logits are never written (greedy decoding)
 //   kEpiTopK  : like kEpiArgmax but keeps the k best (value, index) pairs per row and tile
 #include "gemm_tc.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda.h>
 #include <stdlib.h>
@@ -23,153 +24,10 @@
 
 namespace dcap {
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
-}
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-// smem tile -> global through the tensor map (clipped at the tensor bounds); bulk_group completion
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-}
-// same, but global += smem (fp32): the split-K / accumulating weight-gradient path
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
-    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulation
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// mbarrier arrives when every tcgen05.mma issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives TMEM lane (base+i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// ------------------------------------------------------------------------------------------------
-// descriptors
-// ------------------------------------------------------------------------------------------------
-// Shared-memory matrix descriptors (fields in 16-byte units; version 1 = sm_100; layout type 2 =
-// SWIZZLE_128B).  Both operand forms are staged by TMA with CU_TENSOR_MAP_SWIZZLE_128B as 8 KB
-// slabs of 64 rows x 128 bytes:
-//   K-major  operand tile [rows][64 k]   : a slab row is one operand row (64 k values); 8-row groups
-//                                          are 1024 B apart (SBO = 1024); LBO unused (1); a k-step of
-//                                          16 elements advances the start address by 32 B.
-//   MN-major operand tile [64 k][64 mn]  : a slab row is one k (64 consecutive operand rows);
-//                                          8-k groups are 1024 B apart (SBO = 1024); the next 64
-//                                          operand rows live in the next slab (LBO = 8192); a k-step
-//                                          of 16 advances the start address by 16 rows = 2048 B.
-// (canonical layouts: Swizzle<3,4,3> o ((8,n),2):((8,SBO),1) and ((8,n),(8,k)):((1,LBO),(8,SBO)).)
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address      bits [0,14)
-    d |= (uint64_t)(lbo_bytes >> 4) << 16;                // leading byte off.  bits [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte off.   bits [32,46)
-    d |= (uint64_t)1 << 46;                               // descriptor version bits [46,48)
-    d |= (uint64_t)2 << 61;                               // SWIZZLE_128B       bits [61,64)
-    return d;
-}
-
-// Instruction descriptor for kind::f16: D fp32, A/B bf16, M x N tile; bit 15 / 16 = A / B MN-major.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
-    return (1u << 4)                        // c_format  = F32
-           | (1u << 7)                      // a_format  = BF16
-           | (1u << 10)                     // b_format  = BF16
-           | ((uint32_t)(a_mn & 1) << 15)
-           | ((uint32_t)(b_mn & 1) << 16)
-           | ((uint32_t)(N >> 3) << 17)     // n_dim
-           | ((uint32_t)(M >> 4) << 24);    // m_dim
-}
 
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;                 // 64 bf16 = 128 B = one swizzle row
-constexpr int kUmmaK = 16;
-constexpr int kSlab = 64 * 128;             // 8 KB: 64 rows x 128 B
-constexpr int kEpiWarps = 8;                // 2 per TMEM lane quarter: each owns half of the tile's columns
-constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 struct TcGeom {
     int M, N, K;
@@ -178,8 +36,6 @@ struct TcGeom {
     int split_major;         // work-unit order: 1 = unit -> (split, tile) with CTAs that run together sharing a K range
     int tma_out;             // store epilogue output path: 0 = per-thread stores, 1 = fp32 via TMA, 2 = bf16 via TMA
 };
-
-constexpr int kOutStage = 4096;             // per epilogue warp: 32 rows x 128 B, SWIZZLE_128B
 
 constexpr int kCellAddBytes = 128 * 128 * 4;      // fp32 addend of a 128 x 128 tile: 4 boxes of [128 rows x 32 cols]
 constexpr int kCellCBytes = 128 * 32 * 4;         // fp32 cell state of the tile's 32 units
@@ -196,16 +52,6 @@ struct TcSmem {
     static constexpr int kBytes = kBaseBytes + (kCellTma ? 0 : kEpiWarps * kOutStage);   // + output staging (TMA stores)
 };
 
-// MUFU.TANH: max relative error 2^-11, well inside the bf16 operand rounding (2^-9) of this path
-__device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-__device__ __forceinline__ float hard_sigmoid_tc(float x) {
-    return fminf(fmaxf(__fadd_rn(__fmul_rn(0.2f, x), 0.5f), 0.f), 1.f);
-}
 
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -983,63 +829,6 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const CUtenso
 // epilogue warps of both CTAs arrive on the leader's tmem-empty barrier.  K-major or MN-major operands, split-K
 // with reduce-add epilogues as in the single-CTA kernel.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `p` (an address in this CTA's shared memory) inside CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_u32(const void *p, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load whose completion bytes are signalled on a barrier that may live in the peer CTA
-__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap *map, uint32_t bar_cluster_addr, void *dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t *dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                              uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrives (once every MMA issued so far has completed) on the barrier at this shared-memory offset in BOTH CTAs
-__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-
-struct TcSmem2 {
-    static constexpr int kStageA = kBlockM * kBlockK * 2;            // this CTA's 128 rows of A
-    static constexpr int kStageB = 128 * kBlockK * 2;                // this CTA's 128 of the tile's 256 B rows
-    static constexpr int kStages = 6;
-    static constexpr int kBarOff = kStages * (kStageA + kStageB);    // 192 KB
-    static constexpr int kOutOff = kBarOff + 1024;
-    static constexpr int kBaseBytes = kOutOff + 1024;
-    static constexpr int kBytes = kBaseBytes + kEpiWarps * kOutStage;
-};
 
 template <int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)

@@ -1,0 +1,594 @@
+// The whole greedy decoding loop of the v1 word model (text_generation_model.py:130-156, 192-232) as ONE
+// persistent tcgen05 kernel.
+//
+// Per decoding step the bf16 path runs four dependent GEMMs (decoder_bf16.cu): LSTM1 gates + cell, LSTM2 gates +
+// cell, Dense(1024)+ReLU, vocabulary projection + arg-max, and a merge that picks the token and fetches its
+// embedding row.  As separate launches the three small GEMMs (26 % of the FLOPs) take half of the step: each has
+// <= 4 tile waves, so its ~4 us prologue, its last epilogue and its partial last wave are not amortised.  Every one
+// of these dependencies is PER ROW BLOCK, though: rows [256 rb, 256 rb + 256) of step t need nothing from any other
+// row block.  This kernel therefore walks ONE global list of work items
+//
+//     item = (step t, stage s, row block rb, column block cb)     ordered by t, then s, then rb, then cb
+//
+// dealt round-robin over the CTA pairs (cluster of 2, tcgen05 cta_group::2, 256 x 256 tiles, the main loop of
+// gemm_bf16_tc2_kernel).  An item waits for the items it depends on through monotone counters in global memory
+// (one per stage and 128-row block, bumped by every epilogue warp that has finished that block of a tile); since
+// every dependency points to an EARLIER item of the list and every pair works through its items in list order, the
+// earliest unfinished item can always run: no deadlock as long as all pairs are resident (one CTA per SM; the
+// host asks the occupancy API how many clusters fit).  The tail of one stage overlaps the head of the next, tile
+// waves never drain, and the 75 launches of a 15-step loop become one.
+//
+//   stage 0  z1 = [emb | h1] . [W1e ; U1]^T + (f . W1f + b1)      -> Keras LSTM cell -> h1 (bf16, into X1' and X2), c1
+//   stage 1  z2 = [h1 | h2] . [W2 ; U2]^T + b2                    -> Keras LSTM cell -> h2 (bf16, into X2'), c2
+//   stage 2  d  = relu(h2 . Wd1h^T + (f . Wd1f + bd1))            -> bf16
+//   stage 3  per row and 128-column region: max / first arg-max (/ sum exp) of d . Wd2^T + bd2   -> partial[slot][row]
+//            the LAST of the 2 x 40 epilogue warps to finish a 32-row group merges its partials: token id, optional
+//            caption score, and the token's embedding row copied into the next step's [emb | h1] operand.
+//
+// Operands written by other SMs' epilogues (generic proxy) are read by TMA (async proxy): writers fence
+// (fence.proxy.async + __threadfence) before they bump a counter, the TMA producer acquires the counter and
+// fences before it issues the loads.  Mutable data read by epilogue threads (c, tokens, previous h, partials)
+// is loaded with ld.global.cg (L2, the coherence point).  Every wait carries a watchdog (trap after ~2 s) so
+// that a protocol bug or a second spinning kernel on the same GPU ends in an error, not in a hung device.
+#include "decoder.cuh"
+#include "decoder_bf16.cuh"
+#include "tc_ptx.cuh"
+
+#include <stdlib.h>
+
+namespace dcap {
+
+enum { kMapX1a = 0, kMapX1b, kMapX2a, kMapX2b, kMapH2a, kMapH2b, kMapD, kMapW1, kMapW2, kMapWd1, kMapWd2, kLoopMaps };
+struct LoopMaps { CUtensorMap m[kLoopMaps]; };
+
+struct LoopParams {
+    int R, P, V, U, Epad, K1;
+    int tiles_m;                       // row blocks of 256
+    int tiles_n[4], num_kb[4], first[5];   // per stage: column tiles, k-blocks, first item of the stage inside a step ([4] = items per step)
+    int map_a[4][2], map_b[4];         // tensor-map index of the A operand by step parity, and of B
+    const float *g1f, *d1f, *b2, *bias_v;
+    float *c1, *c2;
+    __nv_bfloat16 *X1[2], *X2[2], *d;
+    float4 *partial;                   // [slots][R] {max, arg-max bits, sum exp, -}
+    int slots;
+    const __nv_bfloat16 *emb;
+    int32_t *tok, *tokens;
+    float *scores;                     // kSum only
+    unsigned int *cnt;                 // [0,n128) stage 0 | [n128,2n128) stage 1 | [2n128,3n128) stage 2 | [3n128,4n128) merges | [4n128,8n128) stage 3 per 32 rows | error word
+    int n128;
+    int l2_prefetch;
+};
+
+constexpr long long kWatchdogCycles = 4000000000ll;      // ~2 s
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// Watchdog: a wait that lasts ~2 s records its code in the error word; every wait polls that word and gives up once
+// it is set, so the whole grid drains (with garbage results) instead of hanging the device.  The host checks the
+// word after the call when DCAP_LOOP_DEBUG is set (tools/loop_check.py) -- in production it never fires.
+__device__ __forceinline__ bool loop_aborted(const unsigned *err) { return *reinterpret_cast<const volatile unsigned *>(err) != 0; }
+// counter >= target (acquire)
+__device__ __forceinline__ void wait_count(const unsigned *p, unsigned target, unsigned *err, unsigned code) {
+    if (ld_acquire_u32(p) >= target) return;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (ld_acquire_u32(p) < target) {
+        __nanosleep(40);
+        if ((spins++ & 63u) == 0) {
+            if (loop_aborted(err)) return;
+            if (clock64() - t0 > kWatchdogCycles) { atomicCAS(err, 0u, code | (target << 8)); return; }
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, unsigned *err, unsigned code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((spins++ & 255u) == 0) {
+            if (loop_aborted(err)) return;
+            if (clock64() - t0 > kWatchdogCycles) { atomicCAS(err, 0u, code); return; }
+        }
+    }
+}
+
+struct LoopItem { int t, s, rb, cb; };
+__device__ __forceinline__ LoopItem decode_item(const LoopParams &p, int item) {
+    LoopItem it;
+    const int ips = p.first[4];
+    it.t = item / ips;
+    int j = item - it.t * ips;
+    it.s = (j >= p.first[1]) + (j >= p.first[2]) + (j >= p.first[3]);
+    j -= p.first[it.s];
+    it.rb = j / p.tiles_n[it.s];
+    it.cb = j - it.rb * p.tiles_n[it.s];
+    return it;
+}
+
+// ---- epilogue bodies: one warp = 32 rows (lane = row) x 128 columns of the CTA's 128 x 256 accumulator half ----
+
+// Keras LSTM cell on gate-interleaved columns (column 4u+g): z = acc + addend / bias; hard-sigmoid gates, tanh
+// candidate, masked rows (consumed token 0) carry (h, c).  c fp32 in place, h bf16 into one or two operand buffers.
+template <bool kAdd>
+__device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, const float *add_row, const float *bias,
+                                          float *c_row, bool masked, const __nv_bfloat16 *h_prev_row,
+                                          __nv_bfloat16 *h_a_row, __nv_bfloat16 *h_b_row, uint64_t *full_bar,
+                                          uint32_t full_phase, unsigned *err) {
+    float4 a_nxt[8], c_nxt[2];
+    uint4 h_nxt = make_uint4(0, 0, 0, 0);
+    auto load_operands = [&](int nb) {
+        if constexpr (kAdd) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a_nxt[j] = __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a_nxt[j] = __ldg(reinterpret_cast<const float4 *>(bias + nb + 4 * j));
+        }
+        c_nxt[0] = __ldcg(reinterpret_cast<const float4 *>(c_row + (nb >> 2)));
+        c_nxt[1] = __ldcg(reinterpret_cast<const float4 *>(c_row + (nb >> 2) + 4));
+        if (masked) h_nxt = __ldcg(reinterpret_cast<const uint4 *>(h_prev_row + (nb >> 2)));
+    };
+    load_operands(n0);
+    mbar_wait_wd(full_bar, full_phase, err, 0x30u);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+        const int nb = n0 + c0;
+        float4 a_cur[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a_cur[j] = a_nxt[j];
+        const float c_old[8] = {c_nxt[0].x, c_nxt[0].y, c_nxt[0].z, c_nxt[0].w, c_nxt[1].x, c_nxt[1].y, c_nxt[1].z, c_nxt[1].w};
+        const uint32_t hw[4] = {h_nxt.x, h_nxt.y, h_nxt.z, h_nxt.w};
+        if (c0 + 32 < 128) load_operands(nb + 32);
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        float c_new[8], h_new[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float zi = v[4 * j] + a_cur[j].x, zf = v[4 * j + 1] + a_cur[j].y;
+            const float zg = v[4 * j + 2] + a_cur[j].z, zo = v[4 * j + 3] + a_cur[j].w;
+            const float ig = hard_sigmoid_tc(zi), fg = hard_sigmoid_tc(zf);
+            const float gg = tanh_fast(zg), og = hard_sigmoid_tc(zo);
+            c_new[j] = __fadd_rn(__fmul_rn(fg, c_old[j]), __fmul_rn(ig, gg));
+            h_new[j] = __fmul_rn(og, tanh_fast(c_new[j]));
+            if (masked) {                                            // K.rnn mask: carry (h, c)
+                c_new[j] = c_old[j];
+                h_new[j] = __uint_as_float((j & 1) ? (hw[j >> 1] & 0xffff0000u) : (hw[j >> 1] << 16));
+            }
+        }
+        if (valid) {
+            const int u0 = nb >> 2;
+            reinterpret_cast<float4 *>(c_row + u0)[0] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
+            reinterpret_cast<float4 *>(c_row + u0)[1] = make_float4(c_new[4], c_new[5], c_new[6], c_new[7]);
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(h_new[2 * j], h_new[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t *>(&t2);
+            }
+            const uint4 hv = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4 *>(h_a_row + u0) = hv;
+            if (h_b_row) *reinterpret_cast<uint4 *>(h_b_row + u0) = hv;
+        }
+    }
+}
+
+// d = relu(acc + addend) -> bf16
+__device__ __forceinline__ void loop_dense(uint32_t taddr, int n0, bool valid, const float *add_row, __nv_bfloat16 *out_row,
+                                           uint64_t *full_bar, uint32_t full_phase, unsigned *err) {
+    float4 a_nxt[8];
+    auto load_operands = [&](int nb) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a_nxt[j] = __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j));
+    };
+    load_operands(n0);
+    mbar_wait_wd(full_bar, full_phase, err, 0x31u);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+        const int nb = n0 + c0;
+        float4 a_cur[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a_cur[j] = a_nxt[j];
+        if (c0 + 32 < 128) load_operands(nb + 32);
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float x0 = fmaxf(v[4 * j] + a_cur[j].x, 0.f), x1 = fmaxf(v[4 * j + 1] + a_cur[j].y, 0.f);
+            const float x2 = fmaxf(v[4 * j + 2] + a_cur[j].z, 0.f), x3 = fmaxf(v[4 * j + 3] + a_cur[j].w, 0.f);
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(x0, x1), t1 = __floats2bfloat162_rn(x2, x3);
+            pk[2 * j] = *reinterpret_cast<uint32_t *>(&t0);
+            pk[2 * j + 1] = *reinterpret_cast<uint32_t *>(&t1);
+        }
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                reinterpret_cast<uint4 *>(out_row + nb)[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+    }
+}
+
+// per row: max, first arg-max (, sum exp(v - max)) of acc + bias over this warp's 128 columns
+template <bool kSum>
+__device__ __forceinline__ float4 loop_argmax(uint32_t taddr, int n0, int N, const float *bias, uint64_t *full_bar,
+                                              uint32_t full_phase, unsigned *err) {
+    mbar_wait_wd(full_bar, full_phase, err, 0x32u);
+    tc_fence_after();
+    float best = -INFINITY, sum = 0.f;
+    int best_i = 0x7fffffff;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+        const int nb = n0 + c0;
+        if (nb >= N) break;                                          // warp-uniform
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        float cmax = -INFINITY;
+        int ci = 0x7fffffff;
+        if (nb + 32 <= N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + nb + 4 * j));
+                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (v[j] > cmax) { cmax = v[j]; ci = nb + j; }       // strict > keeps the first index
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = nb + j;
+                const float x = (n < N) ? v[j] + __ldg(bias + n) : -INFINITY;
+                v[j] = x;
+                if (x > cmax) { cmax = x; ci = n; }
+            }
+        }
+        if constexpr (kSum) {
+            if (cmax > best) sum *= __expf(best - cmax);
+        }
+        if (cmax > best) { best = cmax; best_i = ci; }
+        if constexpr (kSum) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += __expf(v[j] - best);
+        }
+    }
+    return make_float4(best, __int_as_float(best_i), sum, 0.f);
+}
+
+template <bool kSum>
+__global__ void __launch_bounds__(kThreads, 1)
+greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
+    using S = TcSmem2;
+    constexpr int kStages = S::kStages;
+    constexpr int kBlockN = 256;
+    constexpr uint32_t kTmemCols = 2 * kBlockN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem + kStages * S::kStageA;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + S::kBarOff);
+    uint64_t *empty_bar = full_bar + kStages;
+    uint64_t *tmem_full = empty_bar + kStages;
+    uint64_t *tmem_empty = tmem_full + 2;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int total = p.P * p.first[4];
+    const int n128 = p.n128;
+    unsigned *err = p.cnt + 8 * n128;
+    unsigned *cnt_stage = p.cnt;                    // + s * n128 + rb128, s = 0..2
+    unsigned *cnt_merge = p.cnt + 3 * n128;         // + rb128
+    unsigned *cnt_vocab = p.cnt + 4 * n128;         // + rb128 * 4 + quarter
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < kLoopMaps; ++i) tma_prefetch_desc(&maps.m[i]);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_ptr, kTmemCols);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = pair; item < total; item += num_pairs) {
+            const LoopItem it = decode_item(p, item);
+            const int m0 = it.rb * 256 + (int)rank * 128;
+            const int rb128 = it.rb * 2 + (int)rank;
+            // the fp32 per-RoI terms of this tile (constant over the loop) on their way into L2 while the operands load
+            if (p.l2_prefetch && (it.s == 0 || it.s == 2)) {
+                const float *base = it.s == 0 ? p.g1f : p.d1f;
+                const long long ld = it.s == 0 ? 4ll * p.U : (long long)kDense;
+                for (int r = lane; r < 128; r += 32)
+                    if (m0 + r < p.R) prefetch_l2_bulk(base + (long long)(m0 + r) * ld + it.cb * 256, 1024);
+            }
+            if (lane == 0) {
+                // operands of this CTA's 128 rows written by earlier items
+                if (it.s == 0) {
+                    if (it.t > 0) wait_count(cnt_merge + rb128, 4u * it.t, err, 0x10u);
+                } else {
+                    wait_count(cnt_stage + (it.s - 1) * n128 + rb128, (unsigned)(kEpiWarps * p.tiles_n[it.s - 1]) * (it.t + 1), err, 0x10u + it.s);
+                }
+                fence_proxy_async_all();
+                const CUtensorMap *ma = &maps.m[p.map_a[it.s][it.t & 1]], *mb = &maps.m[p.map_b[it.s]];
+                const int nb0 = it.cb * kBlockN + (int)rank * 128;       // this CTA's half of the B tile
+                const int num_kb = p.num_kb[it.s];
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_wd(&empty_bar[stage], phase ^ 1, err, 0x20u);
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (S::kStageA + S::kStageB));
+                    const uint32_t bar = mapa_u32(&full_bar[stage], 0);
+                    tma_load_2d_2sm(ma, bar, smem_a + stage * S::kStageA, kb * kBlockK, m0);
+                    tma_load_2d_2sm(mb, bar, smem_b + stage * S::kStageB, kb * kBlockK, nb0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = make_idesc_bf16(2 * kBlockM, kBlockN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int item = pair; item < total; item += num_pairs) {
+                const LoopItem it = decode_item(p, item);
+                const int num_kb = p.num_kb[it.s];
+                mbar_wait_wd(&tmem_empty[acc], acc_phase ^ 1, err, 0x21u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kBlockN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_wd(&full_bar[stage], phase, err, 0x22u);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * S::kStageA), 16);
+                    const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * S::kStageB), 16);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, kb > 0 || k != 0);
+                    umma_commit_2sm(&empty_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..9, both CTAs: own 128 x 256 accumulator half) =====================
+        const int quarter = warp & 3;                                  // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                              // which 128 of the tile's 256 columns
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int item = pair; item < total; item += num_pairs) {
+            const LoopItem it = decode_item(p, item);
+            const int rb128 = it.rb * 2 + (int)rank;
+            const int m_base = it.rb * 256 + (int)rank * 128 + quarter * 32;
+            const int m = m_base + lane;
+            const bool valid = m < p.R;
+            const long long mr = valid ? m : (long long)(p.R - 1);
+            const int n0 = it.cb * kBlockN + half * 128;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * 128;
+            const int par = it.t & 1;
+            if (it.s <= 1) {
+                // this warp reads state written by other SMs (c, consumed token, previous h): acquire the same
+                // counter the producer waited for (already satisfied)
+                if (lane == 0) {
+                    if (it.s == 0) { if (it.t > 0) wait_count(cnt_merge + rb128, 4u * it.t, err, 0x40u); }
+                    else wait_count(cnt_stage + rb128, (unsigned)(kEpiWarps * p.tiles_n[0]) * (it.t + 1), err, 0x41u);
+                }
+                __syncwarp();
+                const bool masked = __ldcg(p.tok + mr) == 0;
+                if (it.s == 0)
+                    loop_cell<true>(taddr, n0, valid, p.g1f + mr * (4ll * p.U), nullptr, p.c1 + mr * p.U, masked,
+                                    p.X1[par] + mr * p.K1 + p.Epad, p.X1[par ^ 1] + mr * p.K1 + p.Epad,
+                                    p.X2[par] + mr * (2ll * p.U), &tmem_full[acc], acc_phase, err);
+                else
+                    loop_cell<false>(taddr, n0, valid, nullptr, p.b2, p.c2 + mr * p.U, masked,
+                                     p.X2[par] + mr * (2ll * p.U) + p.U, p.X2[par ^ 1] + mr * (2ll * p.U) + p.U,
+                                     nullptr, &tmem_full[acc], acc_phase, err);
+            } else if (it.s == 2) {
+                loop_dense(taddr, n0, valid, p.d1f + mr * kDense, p.d + mr * kDense, &tmem_full[acc], acc_phase, err);
+            } else {
+                const float4 r4 = loop_argmax<kSum>(taddr, n0, p.V, p.bias_v, &tmem_full[acc], acc_phase, err);
+                if (valid) p.partial[(long long)(it.cb * 2 + half) * p.R + m] = r4;
+            }
+            // accumulator buffer drained: hand it back to the MMA issuer (the leader's barrier)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            // publish this warp's rows of the tile
+            fence_proxy_async_all();
+            __syncwarp();
+            if (it.s < 3) {
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(cnt_stage + it.s * n128 + rb128, 1u);
+                }
+            } else {
+                unsigned old = 0;
+                if (lane == 0) {
+                    __threadfence();
+                    old = atomicAdd(cnt_vocab + rb128 * 4 + quarter, 1u);
+                }
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if (old + 1 == (unsigned)(2 * p.tiles_n[3]) * (it.t + 1)) {
+                    // last of the 2 x tiles_n warps of this 32-row group and step: merge the partials
+                    __threadfence();
+                    float best = -INFINITY, sum = 0.f;
+                    int bi = 0x7fffffff;
+                    const float4 *pp = p.partial + mr;
+#pragma unroll 8
+                    for (int sl = 0; sl < p.slots; ++sl) {
+                        const float4 q = __ldcg(pp + (long long)sl * p.R);
+                        const int idx = __float_as_int(q.y);
+                        if constexpr (kSum) {
+                            if (q.x > best) { sum = sum * __expf(best - q.x) + q.z; best = q.x; bi = idx; }
+                            else if (q.x == best) { sum += q.z; bi = min(bi, idx); }
+                            else sum += q.z * __expf(q.x - best);
+                        } else {
+                            if (q.x > best) { best = q.x; bi = idx; }     // slots ascend in column order: strict > keeps the first index
+                        }
+                    }
+                    if ((unsigned)bi >= (unsigned)p.V) bi = 0;            // all-NaN row
+                    if (valid) {
+                        p.tokens[(long long)m * p.P + it.t] = bi;
+                        p.tok[m] = bi;
+                        if constexpr (kSum) p.scores[m] = (it.t ? __ldcg(p.scores + m) : 0.f) + logf(1.0f / sum);
+                    }
+                    if (it.t + 1 < p.P) {
+                        // Embedding lookup of the greedy feedback: the token's row into the next step's [emb | h1] operand
+                        __nv_bfloat16 *xn = p.X1[par ^ 1];
+                        const int e8 = p.Epad >> 3;
+#pragma unroll 4
+                        for (int i = 0; i < 32; ++i) {
+                            const int ti = __shfl_sync(0xffffffffu, bi, i);
+                            const int row = m_base + i;
+                            if (row < p.R) {
+                                const uint4 *src = reinterpret_cast<const uint4 *>(p.emb + (long long)ti * p.Epad);
+                                uint4 *dst = reinterpret_cast<uint4 *>(xn + (long long)row * p.K1);
+                                for (int j = lane; j < e8; j += 32) dst[j] = __ldg(src + j);
+                            }
+                        }
+                    }
+                    fence_proxy_async_all();
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence();
+                        atomicAdd(cnt_merge + rb128, 1u);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, kTmemCols);
+    }
+}
+
+// read at every call (not cached): tools/loop_check.py flips it inside one process for the A/B
+static bool loop_env_on() {
+    const char *e = getenv("DCAP_GREEDY_LOOP");
+    return !(e && atoi(e) == 0);
+}
+
+bool Decoder::greedy_loop_ok() const {
+    if (!loop_env_on() || !bf || cfg.arch != DC_ARCH_V1) return false;
+    const int U = cfg.units;
+    return U % 64 == 0 && (4 * U) % 256 == 0 && bf->Epad % 64 == 0 && cfg.vocab >= 256 && cfg.padding >= 1;
+}
+
+// Steps 0..P-1 of the greedy loop after head / hoisted terms / state reset; ws.tok holds <start>.
+int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_t s) {
+    Bf16State &b = *bf;
+    const int U = cfg.units, V = cfg.vocab, P = cfg.padding, K1 = b.Epad + U;
+    LoopParams p = {};
+    p.R = B; p.P = P; p.V = V; p.U = U; p.Epad = b.Epad; p.K1 = K1;
+    p.tiles_m = ceil_div(B, 256);
+    p.n128 = 2 * p.tiles_m;
+    const int Ns[4] = {4 * U, 4 * U, kDense, V}, Ks[4] = {K1, 2 * U, U, kDense};
+    int first = 0;
+    for (int i = 0; i < 4; ++i) {
+        p.tiles_n[i] = ceil_div(Ns[i], 256);
+        p.num_kb[i] = ceil_div(Ks[i], kBlockK);
+        p.first[i] = first;
+        first += p.tiles_m * p.tiles_n[i];
+    }
+    p.first[4] = first;
+    DC_REQUIRE((long long)first * P < (1ll << 31), "greedy loop: too many work items");
+    p.slots = 2 * p.tiles_n[3];
+    // counters (+ error word), zeroed before every launch
+    const size_t cnt_bytes = sizeof(unsigned) * (8 * (size_t)p.n128 + 4);
+    DC_REQUIRE(b.loop_cnt && cnt_bytes <= b.loop_cnt_bytes, "greedy loop: counter buffer not reserved");
+    DC_CHECK_CUDA(cudaMemsetAsync(b.loop_cnt, 0, cnt_bytes, s));
+    p.cnt = b.loop_cnt;
+    LoopMaps maps;
+    int rc = 0;
+    rc |= make_tmap_bf16(&maps.m[kMapX1a], b.X1[0], B, K1, K1, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapX1b], b.X1[1], B, K1, K1, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapX2a], b.X2[0], B, 2 * U, 2 * U, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapX2b], b.X2[1], B, 2 * U, 2 * U, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapH2a], b.X2[0] + U, B, U, 2 * U, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapH2b], b.X2[1] + U, B, U, 2 * U, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapD], b.d, B, kDense, kDense, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapW1], b.w1cat, 4 * U, K1, K1, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapW2], b.w2cat, 4 * U, 2 * U, 2 * U, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapWd1], b.wd1h, kDense, U, U, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapWd2], b.wd2, V, kDense, kDense, 128);
+    if (rc) return rc;
+    // step t (parity t & 1): LSTM1 reads X1[par]; LSTM2 reads X2[par]; Dense(1024) reads the h2 half of X2[par ^ 1]
+    p.map_a[0][0] = kMapX1a; p.map_a[0][1] = kMapX1b; p.map_b[0] = kMapW1;
+    p.map_a[1][0] = kMapX2a; p.map_a[1][1] = kMapX2b; p.map_b[1] = kMapW2;
+    p.map_a[2][0] = kMapH2b; p.map_a[2][1] = kMapH2a; p.map_b[2] = kMapWd1;
+    p.map_a[3][0] = kMapD;   p.map_a[3][1] = kMapD;   p.map_b[3] = kMapWd2;
+    p.g1f = ws.g1f; p.d1f = ws.d1f; p.b2 = b.b2_i; p.bias_v = W("imgcap_lstm_d2/bias");
+    p.c1 = ws.c1; p.c2 = ws.c2;
+    p.X1[0] = b.X1[0]; p.X1[1] = b.X1[1]; p.X2[0] = b.X2[0]; p.X2[1] = b.X2[1]; p.d = b.d;
+    p.partial = reinterpret_cast<float4 *>(b.partial);
+    p.emb = b.emb; p.tok = ws.tok; p.tokens = tokens; p.scores = scores;
+    static const int l2pf = getenv("DCAP_LOOP_L2PF") ? atoi(getenv("DCAP_LOOP_L2PF")) : 1;
+    p.l2_prefetch = l2pf;
+    // <start> embedding rows of step 0
+    if (int rc2 = embed_gather(W("imgcap_embedding_layer/embeddings"), ws.tok, B, cfg.embed, V, b.X1[0], K1, true, s)) return rc2;
+
+    using S = TcSmem2;
+    auto kern = scores ? greedy_loop_kernel<true> : greedy_loop_kernel<false>;
+    static std::atomic<unsigned long long> attr_set[2];
+    DC_CHECK_CUDA(once_per_device(attr_set[scores ? 1 : 0], [&] {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBaseBytes);
+        return e != cudaSuccess ? e : cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+    }));
+    cudaLaunchConfig_t cfgl = {};
+    cfgl.blockDim = dim3(kThreads);
+    cfgl.dynamicSmemBytes = S::kBaseBytes; cfgl.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfgl.attrs = attr; cfgl.numAttrs = 1;
+    // every pair must be resident at once (the items wait for each other): ask how many clusters fit
+    int pairs = sm_count() / 2;
+    cfgl.gridDim = dim3(2 * pairs);
+    int fit = 0;
+    if (cudaOccupancyMaxActiveClusters(&fit, kern, &cfgl) == cudaSuccess && fit > 0 && fit < pairs) pairs = fit;
+    else cudaGetLastError();
+    static const int pairs_env = getenv("DCAP_LOOP_PAIRS") ? atoi(getenv("DCAP_LOOP_PAIRS")) : 0;
+    if (pairs_env > 0 && pairs_env < pairs) pairs = pairs_env;
+    const int total = P * first;
+    if (pairs > total) pairs = total;
+    cfgl.gridDim = dim3(2 * pairs);
+    DC_CHECK_CUDA(cudaLaunchKernelEx(&cfgl, kern, maps, p));
+    b.parity = P & 1;
+    if (getenv("DCAP_LOOP_DEBUG")) {
+        // debugging aid (never inside graph capture): drain the stream and report the watchdog word
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusNone) {
+            unsigned word = 0;
+            DC_CHECK_CUDA(cudaStreamSynchronize(s));
+            DC_CHECK_CUDA(cudaMemcpy(&word, b.loop_cnt + 8 * p.n128, sizeof(word), cudaMemcpyDeviceToHost));
+            if (word) return set_error(DC_ERR_CUDA, "greedy loop kernel: watchdog code 0x%x (pairs %d, items %d)", word, pairs, total);
+        }
+    }
+    return DC_OK;
+}
+
+}  // namespace dcap
