@@ -44,7 +44,8 @@ struct LoopMaps { CUtensorMap m[kLoopMaps]; };
 struct LoopParams {
     int R, P, V, U, Epad, K1;
     int tiles_m;                       // row blocks of 256
-    int tiles_n[4], num_kb[4], first[5];   // per stage: column tiles, k-blocks, first item of the stage inside a step ([4] = items per step)
+    int tiles_n[4], num_kb[4], first[5];   // per stage: column tiles, k-blocks, first item of the stage inside a slot ([4] = items per slot)
+    int skew[4], total;                // item order: slot v holds stage s of virtual row block v - skew[s]; total = number of items
     int map_a[4][2], map_b[4];         // tensor-map index of the A operand by step parity, and of B
     const float *g1f, *d1f, *b2, *bias_v;
     float *c1, *c2;
@@ -57,6 +58,9 @@ struct LoopParams {
     unsigned int *cnt;                 // [0,n128) stage 0 | [n128,2n128) stage 1 | [2n128,3n128) stage 2 | [3n128,4n128) merges | [4n128,8n128) stage 3 per 32 rows | error word
     int n128;
     int l2_prefetch;
+    int writer_proxy_fence;            // 1: epilogue warps also run fence.proxy.async before they publish (belt and braces; measured)
+    unsigned long long *trace;         // debugging: [pairs][trace_items][8] globaltimer marks of the leader CTA (DCAP_LOOP_TRACE)
+    int trace_items;
 };
 
 constexpr long long kWatchdogCycles = 4000000000ll;      // ~2 s
@@ -99,16 +103,38 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, uns
     }
 }
 
-struct LoopItem { int t, s, rb, cb; };
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+#define LOOP_TRACE(slot)                                                                                      \
+    do {                                                                                                      \
+        if (p.trace && rank == 0) {                                                                           \
+            const int n_ = (item - pair) / num_pairs;                                                         \
+            if (n_ < p.trace_items) p.trace[((long long)pair * p.trace_items + n_) * 8 + (slot)] = globaltimer_ns(); \
+        }                                                                                                     \
+    } while (0)
+
+// Item order: a diagonal wavefront over (step, row block).  Slot v of the list holds, one after the other, the column
+// tiles of stage 0 for virtual row block u = v, of stage 1 for u = v - skew[1], of stage 2 for u = v - skew[2] and of
+// the vocabulary stage for u = v - skew[3]; u = t * tiles_m + rb.  So at any moment different row blocks are in
+// different stages: every pair sees a fine mixture of long-epilogue (LSTM cells) and long-main-loop (vocabulary) tiles
+// -- the epilogues hide under the next tile's MMAs --, and every dependency was listed skew slots (several tile times)
+// earlier, so it is normally met when its consumer comes up.  skew[3] < tiles_m keeps "dependencies point backwards":
+// stage 0 of (t + 1, rb) sits tiles_m - skew[3] slots after the vocabulary stage of (t, rb).
+struct LoopItem { int t, s, rb, cb; bool live; };
 __device__ __forceinline__ LoopItem decode_item(const LoopParams &p, int item) {
     LoopItem it;
     const int ips = p.first[4];
-    it.t = item / ips;
-    int j = item - it.t * ips;
+    const int v = item / ips;
+    const int j = item - v * ips;
     it.s = (j >= p.first[1]) + (j >= p.first[2]) + (j >= p.first[3]);
-    j -= p.first[it.s];
-    it.rb = j / p.tiles_n[it.s];
-    it.cb = j - it.rb * p.tiles_n[it.s];
+    it.cb = j - p.first[it.s];
+    const int u = v - p.skew[it.s];
+    it.live = u >= 0 && u < p.P * p.tiles_m;
+    it.t = u / p.tiles_m;
+    it.rb = u - it.t * p.tiles_m;
     return it;
 }
 
@@ -283,7 +309,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-    const int total = p.P * p.first[4];
+    const int total = p.total;
     const int n128 = p.n128;
     unsigned *err = p.cnt + 8 * n128;
     unsigned *cnt_stage = p.cnt;                    // + s * n128 + rb128, s = 0..2
@@ -309,6 +335,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
         uint32_t phase = 0;
         for (int item = pair; item < total; item += num_pairs) {
             const LoopItem it = decode_item(p, item);
+            if (!it.live) continue;                                    // warp-uniform: pipeline fill / drain slots
             const int m0 = it.rb * 256 + (int)rank * 128;
             const int rb128 = it.rb * 2 + (int)rank;
             // the fp32 per-RoI terms of this tile (constant over the loop) on their way into L2 while the operands load
@@ -319,6 +346,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                     if (m0 + r < p.R) prefetch_l2_bulk(base + (long long)(m0 + r) * ld + it.cb * 256, 1024);
             }
             if (lane == 0) {
+                LOOP_TRACE(0);
                 // operands of this CTA's 128 rows written by earlier items
                 if (it.s == 0) {
                     if (it.t > 0) wait_count(cnt_merge + rb128, 4u * it.t, err, 0x10u);
@@ -326,6 +354,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                     wait_count(cnt_stage + (it.s - 1) * n128 + rb128, (unsigned)(kEpiWarps * p.tiles_n[it.s - 1]) * (it.t + 1), err, 0x10u + it.s);
                 }
                 fence_proxy_async_all();
+                LOOP_TRACE(1);
                 const CUtensorMap *ma = &maps.m[p.map_a[it.s][it.t & 1]], *mb = &maps.m[p.map_b[it.s]];
                 const int nb0 = it.cb * kBlockN + (int)rank * 128;       // this CTA's half of the B tile
                 const int num_kb = p.num_kb[it.s];
@@ -337,6 +366,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                     tma_load_2d_2sm(mb, bar, smem_b + stage * S::kStageB, kb * kBlockK, nb0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                LOOP_TRACE(2);
             }
             __syncwarp();
         }
@@ -350,13 +380,16 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             uint32_t acc_phase = 0;
             for (int item = pair; item < total; item += num_pairs) {
                 const LoopItem it = decode_item(p, item);
+                if (!it.live) continue;
                 const int num_kb = p.num_kb[it.s];
                 mbar_wait_wd(&tmem_empty[acc], acc_phase ^ 1, err, 0x21u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kBlockN;
+                LOOP_TRACE(3);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait_wd(&full_bar[stage], phase, err, 0x22u);
                     tc_fence_after();
+                    if (kb == 0) LOOP_TRACE(4);
                     const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem_a + stage * S::kStageA), 16);
                     const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem_b + stage * S::kStageB), 16);
 #pragma unroll
@@ -366,6 +399,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit_2sm(&tmem_full[acc]);
+                LOOP_TRACE(5);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -378,6 +412,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
         uint32_t acc_phase = 0;
         for (int item = pair; item < total; item += num_pairs) {
             const LoopItem it = decode_item(p, item);
+            if (!it.live) continue;
             const int rb128 = it.rb * 2 + (int)rank;
             const int m_base = it.rb * 256 + (int)rank * 128 + quarter * 32;
             const int m = m_base + lane;
@@ -414,8 +449,9 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (warp == 2 && lane == 0) LOOP_TRACE(6);
             // publish this warp's rows of the tile
-            fence_proxy_async_all();
+            if (p.writer_proxy_fence) fence_proxy_async_all();
             __syncwarp();
             if (it.s < 3) {
                 if (lane == 0) {
@@ -435,16 +471,21 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                     float best = -INFINITY, sum = 0.f;
                     int bi = 0x7fffffff;
                     const float4 *pp = p.partial + mr;
-#pragma unroll 8
-                    for (int sl = 0; sl < p.slots; ++sl) {
-                        const float4 q = __ldcg(pp + (long long)sl * p.R);
-                        const int idx = __float_as_int(q.y);
-                        if constexpr (kSum) {
-                            if (q.x > best) { sum = sum * __expf(best - q.x) + q.z; best = q.x; bi = idx; }
-                            else if (q.x == best) { sum += q.z; bi = min(bi, idx); }
-                            else sum += q.z * __expf(q.x - best);
-                        } else {
-                            if (q.x > best) { best = q.x; bi = idx; }     // slots ascend in column order: strict > keeps the first index
+                    for (int s0 = 0; s0 < p.slots; s0 += 8) {            // 8 loads in flight per lane
+                        float4 q[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) q[i] = __ldcg(pp + (long long)min(s0 + i, p.slots - 1) * p.R);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (s0 + i >= p.slots) break;
+                            const int idx = __float_as_int(q[i].y);
+                            if constexpr (kSum) {
+                                if (q[i].x > best) { sum = sum * __expf(best - q[i].x) + q[i].z; best = q[i].x; bi = idx; }
+                                else if (q[i].x == best) { sum += q[i].z; bi = min(bi, idx); }
+                                else sum += q[i].z * __expf(q[i].x - best);
+                            } else {
+                                if (q[i].x > best) { best = q[i].x; bi = idx; }   // slots ascend in column order: strict > keeps the first index
+                            }
                         }
                     }
                     if ((unsigned)bi >= (unsigned)p.V) bi = 0;            // all-NaN row
@@ -454,18 +495,26 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                         if constexpr (kSum) p.scores[m] = (it.t ? __ldcg(p.scores + m) : 0.f) + logf(1.0f / sum);
                     }
                     if (it.t + 1 < p.P) {
-                        // Embedding lookup of the greedy feedback: the token's row into the next step's [emb | h1] operand
-                        __nv_bfloat16 *xn = p.X1[par ^ 1];
-                        const int e8 = p.Epad >> 3;
-#pragma unroll 4
-                        for (int i = 0; i < 32; ++i) {
-                            const int ti = __shfl_sync(0xffffffffu, bi, i);
-                            const int row = m_base + i;
-                            if (row < p.R) {
-                                const uint4 *src = reinterpret_cast<const uint4 *>(p.emb + (long long)ti * p.Epad);
-                                uint4 *dst = reinterpret_cast<uint4 *>(xn + (long long)row * p.K1);
-                                for (int j = lane; j < e8; j += 32) dst[j] = __ldg(src + j);
+                        // Embedding lookup of the greedy feedback: the tokens' rows into the next step's [emb | h1] operand.
+                        // The group's 32 x e8 16-byte pieces are dealt over the lanes, 8 loads in flight each (a row-by-row
+                        // copy serialises load -> store -> load on possible aliasing: measured ~100 us per group).
+                        const uint4 *__restrict__ emb4 = reinterpret_cast<const uint4 *>(p.emb);
+                        uint4 *__restrict__ xn4 = reinterpret_cast<uint4 *>(p.X1[par ^ 1]);
+                        const int e8 = p.Epad >> 3, k8 = p.K1 >> 3;
+                        for (int k0 = 0; k0 < e8; k0 += 8) {
+                            uint4 v8[8];
+                            long long dsti[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int q = lane + 32 * min(k0 + i, e8 - 1);
+                                const int r = q / e8, j = q - r * e8;
+                                const int ti = __shfl_sync(0xffffffffu, bi, r);
+                                v8[i] = __ldg(emb4 + (long long)ti * e8 + j);
+                                dsti[i] = (m_base + r < p.R && k0 + i < e8) ? (long long)(m_base + r) * k8 + j : -1;
                             }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (dsti[i] >= 0) xn4[dsti[i]] = v8[i];
                         }
                     }
                     fence_proxy_async_all();
@@ -476,6 +525,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                     }
                 }
             }
+            if (warp == 2 && lane == 0) LOOP_TRACE(7);
         }
     }
     tc_fence_before();
@@ -512,10 +562,18 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
         p.tiles_n[i] = ceil_div(Ns[i], 256);
         p.num_kb[i] = ceil_div(Ks[i], kBlockK);
         p.first[i] = first;
-        first += p.tiles_m * p.tiles_n[i];
+        first += p.tiles_n[i];
     }
-    p.first[4] = first;
-    DC_REQUIRE((long long)first * P < (1ll << 31), "greedy loop: too many work items");
+    p.first[4] = first;                                    // items per slot
+    // wavefront skews (slots): each must cover its producer stage's latency (tile + epilogue + publish, 11-15 us;
+    // a slot of ~60 items is ~4.5 us on 74 pairs), and skew[3] < tiles_m (see decode_item)
+    static const int skew_env = getenv("DCAP_LOOP_SKEW") ? atoi(getenv("DCAP_LOOP_SKEW")) : 14;
+    int sk3 = p.tiles_m - 6 < skew_env ? p.tiles_m - 6 : skew_env;
+    if (sk3 < 0) sk3 = 0;
+    p.skew[0] = 0; p.skew[1] = sk3 * 5 / 14; p.skew[2] = sk3 * 10 / 14; p.skew[3] = sk3;
+    const long long total_ll = ((long long)P * p.tiles_m + sk3) * first;
+    DC_REQUIRE(total_ll < (1ll << 31), "greedy loop: too many work items");
+    p.total = (int)total_ll;
     p.slots = 2 * p.tiles_n[3];
     // counters (+ error word), zeroed before every launch
     const size_t cnt_bytes = sizeof(unsigned) * (8 * (size_t)p.n128 + 4);
@@ -548,6 +606,8 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     p.emb = b.emb; p.tok = ws.tok; p.tokens = tokens; p.scores = scores;
     static const int l2pf = getenv("DCAP_LOOP_L2PF") ? atoi(getenv("DCAP_LOOP_L2PF")) : 1;
     p.l2_prefetch = l2pf;
+    static const int wpf = getenv("DCAP_LOOP_WPF") ? atoi(getenv("DCAP_LOOP_WPF")) : 0;
+    p.writer_proxy_fence = wpf;
     // <start> embedding rows of step 0
     if (int rc2 = embed_gather(W("imgcap_embedding_layer/embeddings"), ws.tok, B, cfg.embed, V, b.X1[0], K1, true, s)) return rc2;
 
@@ -573,11 +633,37 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     else cudaGetLastError();
     static const int pairs_env = getenv("DCAP_LOOP_PAIRS") ? atoi(getenv("DCAP_LOOP_PAIRS")) : 0;
     if (pairs_env > 0 && pairs_env < pairs) pairs = pairs_env;
-    const int total = P * first;
+    const int total = p.total;
     if (pairs > total) pairs = total;
     cfgl.gridDim = dim3(2 * pairs);
+    const char *trace_path = getenv("DCAP_LOOP_TRACE");
+    static unsigned long long *trace_buf = nullptr;
+    const int trace_items = ceil_div(total, pairs);
+    const size_t trace_bytes = sizeof(unsigned long long) * 8 * (size_t)trace_items * pairs;
+    if (trace_path) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusNone) {
+            if (trace_buf) cudaFree(trace_buf);
+            DC_CHECK_CUDA(cudaMalloc((void **)&trace_buf, trace_bytes));
+            DC_CHECK_CUDA(cudaMemsetAsync(trace_buf, 0, trace_bytes, s));
+            p.trace = trace_buf; p.trace_items = trace_items;
+        }
+    }
     DC_CHECK_CUDA(cudaLaunchKernelEx(&cfgl, kern, maps, p));
     b.parity = P & 1;
+    if (p.trace) {
+        // debugging aid: dump the marks as int32 header {pairs, items per pair, steps, items per slot, first[0..3], tiles_n[0..3], tiles_m, skew[1..3]} + uint64 data
+        std::vector<unsigned long long> host(trace_bytes / sizeof(unsigned long long));
+        DC_CHECK_CUDA(cudaStreamSynchronize(s));
+        DC_CHECK_CUDA(cudaMemcpy(host.data(), trace_buf, trace_bytes, cudaMemcpyDeviceToHost));
+        if (FILE *fp = fopen(trace_path, "wb")) {
+            const int hdr[16] = {pairs, trace_items, P, first, p.first[0], p.first[1], p.first[2], p.first[3],
+                                 p.tiles_n[0], p.tiles_n[1], p.tiles_n[2], p.tiles_n[3], p.tiles_m, p.skew[1], p.skew[2], p.skew[3]};
+            fwrite(hdr, sizeof(int), 16, fp);
+            fwrite(host.data(), 1, trace_bytes, fp);
+            fclose(fp);
+        }
+    }
     if (getenv("DCAP_LOOP_DEBUG")) {
         // debugging aid (never inside graph capture): drain the stream and report the watchdog word
         cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
