@@ -44,8 +44,8 @@ struct LoopMaps { CUtensorMap m[kLoopMaps]; };
 struct LoopParams {
     int R, P, V, U, Epad, K1;
     int tiles_m;                       // row blocks of 256
-    int tiles_n[4], num_kb[4], first[5];   // per stage: column tiles, k-blocks, first item of the stage inside a slot ([4] = items per slot)
-    int skew[4], total;                // item order: slot v holds stage s of virtual row block v - skew[s]; total = number of items
+    int tiles_n[5], num_kb[5], first[6];   // per stage (4 = merge, one item, no GEMM): column tiles, k-blocks, first item of the stage inside a slot ([5] = items per slot)
+    int skew[5], total;                // item order: slot v holds stage s of virtual row block v - skew[s]; total = number of items
     int map_a[4][2], map_b[4];         // tensor-map index of the A operand by step parity, and of B
     const float *g1f, *d1f, *b2, *bias_v;
     float *c1, *c2;
@@ -55,7 +55,7 @@ struct LoopParams {
     const __nv_bfloat16 *emb;
     int32_t *tok, *tokens;
     float *scores;                     // kSum only
-    unsigned int *cnt;                 // [0,n128) stage 0 | [n128,2n128) stage 1 | [2n128,3n128) stage 2 | [3n128,4n128) merges | [4n128,8n128) stage 3 per 32 rows | error word
+    unsigned int *cnt;                 // [s * n128 + 128-row block], s = 0..4: epilogue warps that have finished that block of a stage-s item; then the error word at 8 * n128
     int n128;
     int l2_prefetch;
     int writer_proxy_fence;            // 1: epilogue warps also run fence.proxy.async before they publish (belt and braces; measured)
@@ -117,19 +117,19 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     } while (0)
 
 // Item order: a diagonal wavefront over (step, row block).  Slot v of the list holds, one after the other, the column
-// tiles of stage 0 for virtual row block u = v, of stage 1 for u = v - skew[1], of stage 2 for u = v - skew[2] and of
-// the vocabulary stage for u = v - skew[3]; u = t * tiles_m + rb.  So at any moment different row blocks are in
+// tiles of stage 0 for virtual row block u = v, of stage 1 for u = v - skew[1], of stage 2 for u = v - skew[2], of
+// the vocabulary stage for u = v - skew[3] and the merge item for u = v - skew[4]; u = t * tiles_m + rb.  So at any moment different row blocks are in
 // different stages: every pair sees a fine mixture of long-epilogue (LSTM cells) and long-main-loop (vocabulary) tiles
 // -- the epilogues hide under the next tile's MMAs --, and every dependency was listed skew slots (several tile times)
-// earlier, so it is normally met when its consumer comes up.  skew[3] < tiles_m keeps "dependencies point backwards":
-// stage 0 of (t + 1, rb) sits tiles_m - skew[3] slots after the vocabulary stage of (t, rb).
+// earlier, so it is normally met when its consumer comes up.  skew[4] < tiles_m keeps "dependencies point backwards":
+// stage 0 of (t + 1, rb) sits tiles_m - skew[4] slots after the merge of (t, rb).
 struct LoopItem { int t, s, rb, cb; bool live; };
 __device__ __forceinline__ LoopItem decode_item(const LoopParams &p, int item) {
     LoopItem it;
-    const int ips = p.first[4];
+    const int ips = p.first[5];
     const int v = item / ips;
     const int j = item - v * ips;
-    it.s = (j >= p.first[1]) + (j >= p.first[2]) + (j >= p.first[3]);
+    it.s = (j >= p.first[1]) + (j >= p.first[2]) + (j >= p.first[3]) + (j >= p.first[4]);
     it.cb = j - p.first[it.s];
     const int u = v - p.skew[it.s];
     it.live = u >= 0 && u < p.P * p.tiles_m;
@@ -289,6 +289,81 @@ __device__ __forceinline__ float4 loop_argmax(uint32_t taddr, int n0, int N, con
     return make_float4(best, __int_as_float(best_i), sum, 0.f);
 }
 
+// Merge of the vocabulary stage's partials for 16 rows (one warp): lanes 2r / 2r+1 scan the lower / upper half of
+// row r's column regions (8 loads in flight each) and combine; ties keep the smaller column index, as np.argmax.
+// Then the token ids, the caption score (kSum) and the tokens' embedding rows, copied as bf16 into the next step's
+// [emb | h1] operand (Embedding lookup of the greedy feedback, text_generation_model.py:147,222-225).
+template <bool kSum>
+__device__ __forceinline__ void loop_merge(const LoopParams &p, int m_base, int t, int lane) {
+    const int r = lane >> 1, h = lane & 1;
+    const int m = m_base + r;
+    const bool valid = m < p.R;
+    const long long mr = valid ? m : (long long)(p.R - 1);
+    const int half_slots = (p.slots + 1) >> 1;
+    const int s_lo = h * half_slots, s_hi = min(p.slots, s_lo + half_slots);
+    float best = -INFINITY, sum = 0.f;
+    int bi = 0x7fffffff;
+    const float4 *pp = p.partial + mr;
+    for (int s0 = s_lo; s0 < s_hi; s0 += 8) {
+        float4 q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __ldcg(pp + (long long)min(s0 + i, s_hi - 1) * p.R);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (s0 + i >= s_hi) break;
+            const int idx = __float_as_int(q[i].y);
+            if constexpr (kSum) {
+                if (q[i].x > best) { sum = sum * __expf(best - q[i].x) + q[i].z; best = q[i].x; bi = idx; }
+                else if (q[i].x == best) { sum += q[i].z; bi = min(bi, idx); }
+                else sum += q[i].z * __expf(q[i].x - best);
+            } else {
+                if (q[i].x > best) { best = q[i].x; bi = idx; }       // regions ascend in column order: strict > keeps the first index
+            }
+        }
+    }
+    {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, 1);
+        const float os = __shfl_xor_sync(0xffffffffu, sum, 1);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, 1);
+        // a = lower half (smaller indices), b = upper half
+        const float ab = h ? ob : best, bb = h ? best : ob, as = h ? os : sum, bs = h ? sum : os;
+        const int ai = h ? oi : bi, bi2 = h ? bi : oi;
+        if (bb > ab) { best = bb; bi = bi2; if constexpr (kSum) sum = bs + as * __expf(ab - bb); }
+        else { best = ab; bi = ai; if constexpr (kSum) sum = as + (bb > -INFINITY ? bs * __expf(bb - ab) : 0.f); }
+    }
+    if ((unsigned)bi >= (unsigned)p.V) bi = 0;                        // all-NaN row
+    if (valid && h == 0) {
+        p.tokens[(long long)m * p.P + t] = bi;
+        p.tok[m] = bi;
+        if constexpr (kSum) p.scores[m] = (t ? __ldcg(p.scores + m) : 0.f) + logf(1.0f / sum);
+    }
+    if (t + 1 < p.P) {
+        // the 16 x e8 16-byte pieces are dealt over the lanes, 8 loads in flight each (a row-by-row copy serialises
+        // load -> store -> load on possible aliasing: measured ~100 us per 32 rows)
+        const uint4 *__restrict__ emb4 = reinterpret_cast<const uint4 *>(p.emb);
+        uint4 *__restrict__ xn4 = reinterpret_cast<uint4 *>(p.X1[(t + 1) & 1]);
+        const int e8 = p.Epad >> 3, k8 = p.K1 >> 3;
+        const int iters = e8 >> 1;                                    // 16 * e8 pieces / 32 lanes
+        for (int k0 = 0; k0 < iters; k0 += 8) {
+            uint4 v8[8];
+            long long dsti[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = lane + 32 * min(k0 + i, iters - 1);
+                const int rr = q / e8, j = q - rr * e8;
+                const int ti = __shfl_sync(0xffffffffu, bi, 2 * rr);
+                v8[i] = __ldg(emb4 + (long long)ti * e8 + j);
+                dsti[i] = (m_base + rr < p.R && k0 + i < iters) ? (long long)(m_base + rr) * k8 + j : -1;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (dsti[i] >= 0) xn4[dsti[i]] = v8[i];
+        }
+    }
+    // the embedding rows are read by TMA (async proxy) in the next step
+    if (p.writer_proxy_fence) fence_proxy_async_all();
+}
+
 template <bool kSum>
 __global__ void __launch_bounds__(kThreads, 1)
 greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
@@ -312,9 +387,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
     const int total = p.total;
     const int n128 = p.n128;
     unsigned *err = p.cnt + 8 * n128;
-    unsigned *cnt_stage = p.cnt;                    // + s * n128 + rb128, s = 0..2
-    unsigned *cnt_merge = p.cnt + 3 * n128;         // + rb128
-    unsigned *cnt_vocab = p.cnt + 4 * n128;         // + rb128 * 4 + quarter
+    unsigned *cnt_stage = p.cnt;                    // + s * n128 + rb128
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < kLoopMaps; ++i) tma_prefetch_desc(&maps.m[i]);
@@ -335,7 +408,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
         uint32_t phase = 0;
         for (int item = pair; item < total; item += num_pairs) {
             const LoopItem it = decode_item(p, item);
-            if (!it.live) continue;                                    // warp-uniform: pipeline fill / drain slots
+            if (!it.live || it.s == 4) continue;                       // warp-uniform: pipeline fill / drain slots; merge items have no operands
             const int m0 = it.rb * 256 + (int)rank * 128;
             const int rb128 = it.rb * 2 + (int)rank;
             // the fp32 per-RoI terms of this tile (constant over the loop) on their way into L2 while the operands load
@@ -349,7 +422,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                 LOOP_TRACE(0);
                 // operands of this CTA's 128 rows written by earlier items
                 if (it.s == 0) {
-                    if (it.t > 0) wait_count(cnt_merge + rb128, 4u * it.t, err, 0x10u);
+                    if (it.t > 0) wait_count(cnt_stage + 4 * n128 + rb128, (unsigned)kEpiWarps * it.t, err, 0x10u);
                 } else {
                     wait_count(cnt_stage + (it.s - 1) * n128 + rb128, (unsigned)(kEpiWarps * p.tiles_n[it.s - 1]) * (it.t + 1), err, 0x10u + it.s);
                 }
@@ -380,7 +453,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             uint32_t acc_phase = 0;
             for (int item = pair; item < total; item += num_pairs) {
                 const LoopItem it = decode_item(p, item);
-                if (!it.live) continue;
+                if (!it.live || it.s == 4) continue;
                 const int num_kb = p.num_kb[it.s];
                 mbar_wait_wd(&tmem_empty[acc], acc_phase ^ 1, err, 0x21u);
                 tc_fence_after();
@@ -414,18 +487,31 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             const LoopItem it = decode_item(p, item);
             if (!it.live) continue;
             const int rb128 = it.rb * 2 + (int)rank;
+            const int par = it.t & 1;
+            if (it.s == 4) {
+                // ---- merge item: token, caption score and next embedding row of this CTA's 128 rows; 16 rows per warp ----
+                if (lane == 0) wait_count(cnt_stage + 3 * n128 + rb128, (unsigned)(kEpiWarps * p.tiles_n[3]) * (it.t + 1), err, 0x44u);
+                __syncwarp();
+                loop_merge<kSum>(p, it.rb * 256 + (int)rank * 128 + (warp - 2) * 16, it.t, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(cnt_stage + 4 * n128 + rb128, 1u);
+                }
+                if (warp == 2 && lane == 0) { LOOP_TRACE(6); LOOP_TRACE(7); }
+                continue;
+            }
             const int m_base = it.rb * 256 + (int)rank * 128 + quarter * 32;
             const int m = m_base + lane;
             const bool valid = m < p.R;
             const long long mr = valid ? m : (long long)(p.R - 1);
             const int n0 = it.cb * kBlockN + half * 128;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * 128;
-            const int par = it.t & 1;
             if (it.s <= 1) {
                 // this warp reads state written by other SMs (c, consumed token, previous h): acquire the same
                 // counter the producer waited for (already satisfied)
                 if (lane == 0) {
-                    if (it.s == 0) { if (it.t > 0) wait_count(cnt_merge + rb128, 4u * it.t, err, 0x40u); }
+                    if (it.s == 0) { if (it.t > 0) wait_count(cnt_stage + 4 * n128 + rb128, (unsigned)kEpiWarps * it.t, err, 0x40u); }
                     else wait_count(cnt_stage + rb128, (unsigned)(kEpiWarps * p.tiles_n[0]) * (it.t + 1), err, 0x41u);
                 }
                 __syncwarp();
@@ -453,77 +539,9 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             // publish this warp's rows of the tile
             if (p.writer_proxy_fence) fence_proxy_async_all();
             __syncwarp();
-            if (it.s < 3) {
-                if (lane == 0) {
-                    __threadfence();
-                    atomicAdd(cnt_stage + it.s * n128 + rb128, 1u);
-                }
-            } else {
-                unsigned old = 0;
-                if (lane == 0) {
-                    __threadfence();
-                    old = atomicAdd(cnt_vocab + rb128 * 4 + quarter, 1u);
-                }
-                old = __shfl_sync(0xffffffffu, old, 0);
-                if (old + 1 == (unsigned)(2 * p.tiles_n[3]) * (it.t + 1)) {
-                    // last of the 2 x tiles_n warps of this 32-row group and step: merge the partials
-                    __threadfence();
-                    float best = -INFINITY, sum = 0.f;
-                    int bi = 0x7fffffff;
-                    const float4 *pp = p.partial + mr;
-                    for (int s0 = 0; s0 < p.slots; s0 += 8) {            // 8 loads in flight per lane
-                        float4 q[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) q[i] = __ldcg(pp + (long long)min(s0 + i, p.slots - 1) * p.R);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (s0 + i >= p.slots) break;
-                            const int idx = __float_as_int(q[i].y);
-                            if constexpr (kSum) {
-                                if (q[i].x > best) { sum = sum * __expf(best - q[i].x) + q[i].z; best = q[i].x; bi = idx; }
-                                else if (q[i].x == best) { sum += q[i].z; bi = min(bi, idx); }
-                                else sum += q[i].z * __expf(q[i].x - best);
-                            } else {
-                                if (q[i].x > best) { best = q[i].x; bi = idx; }   // slots ascend in column order: strict > keeps the first index
-                            }
-                        }
-                    }
-                    if ((unsigned)bi >= (unsigned)p.V) bi = 0;            // all-NaN row
-                    if (valid) {
-                        p.tokens[(long long)m * p.P + it.t] = bi;
-                        p.tok[m] = bi;
-                        if constexpr (kSum) p.scores[m] = (it.t ? __ldcg(p.scores + m) : 0.f) + logf(1.0f / sum);
-                    }
-                    if (it.t + 1 < p.P) {
-                        // Embedding lookup of the greedy feedback: the tokens' rows into the next step's [emb | h1] operand.
-                        // The group's 32 x e8 16-byte pieces are dealt over the lanes, 8 loads in flight each (a row-by-row
-                        // copy serialises load -> store -> load on possible aliasing: measured ~100 us per group).
-                        const uint4 *__restrict__ emb4 = reinterpret_cast<const uint4 *>(p.emb);
-                        uint4 *__restrict__ xn4 = reinterpret_cast<uint4 *>(p.X1[par ^ 1]);
-                        const int e8 = p.Epad >> 3, k8 = p.K1 >> 3;
-                        for (int k0 = 0; k0 < e8; k0 += 8) {
-                            uint4 v8[8];
-                            long long dsti[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int q = lane + 32 * min(k0 + i, e8 - 1);
-                                const int r = q / e8, j = q - r * e8;
-                                const int ti = __shfl_sync(0xffffffffu, bi, r);
-                                v8[i] = __ldg(emb4 + (long long)ti * e8 + j);
-                                dsti[i] = (m_base + r < p.R && k0 + i < e8) ? (long long)(m_base + r) * k8 + j : -1;
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (dsti[i] >= 0) xn4[dsti[i]] = v8[i];
-                        }
-                    }
-                    fence_proxy_async_all();
-                    __syncwarp();
-                    if (lane == 0) {
-                        __threadfence();
-                        atomicAdd(cnt_merge + rb128, 1u);
-                    }
-                }
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(cnt_stage + it.s * n128 + rb128, 1u);
             }
             if (warp == 2 && lane == 0) LOOP_TRACE(7);
         }
@@ -564,14 +582,15 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
         p.first[i] = first;
         first += p.tiles_n[i];
     }
-    p.first[4] = first;                                    // items per slot
+    p.tiles_n[4] = 1; p.num_kb[4] = 0; p.first[4] = first; first += 1;   // the merge item
+    p.first[5] = first;                                    // items per slot
     // wavefront skews (slots): each must cover its producer stage's latency (tile + epilogue + publish, 11-15 us;
-    // a slot of ~60 items is ~4.5 us on 74 pairs), and skew[3] < tiles_m (see decode_item)
-    static const int skew_env = getenv("DCAP_LOOP_SKEW") ? atoi(getenv("DCAP_LOOP_SKEW")) : 14;
-    int sk3 = p.tiles_m - 6 < skew_env ? p.tiles_m - 6 : skew_env;
-    if (sk3 < 0) sk3 = 0;
-    p.skew[0] = 0; p.skew[1] = sk3 * 5 / 14; p.skew[2] = sk3 * 10 / 14; p.skew[3] = sk3;
-    const long long total_ll = ((long long)P * p.tiles_m + sk3) * first;
+    // a slot of ~60 items is ~4.5 us on 74 pairs), and skew[4] < tiles_m (see decode_item)
+    static const int skew_env = getenv("DCAP_LOOP_SKEW") ? atoi(getenv("DCAP_LOOP_SKEW")) : 19;
+    int sk4 = p.tiles_m - 6 < skew_env ? p.tiles_m - 6 : skew_env;
+    if (sk4 < 0) sk4 = 0;
+    p.skew[0] = 0; p.skew[1] = sk4 * 5 / 19; p.skew[2] = sk4 * 10 / 19; p.skew[3] = sk4 * 14 / 19; p.skew[4] = sk4;
+    const long long total_ll = ((long long)P * p.tiles_m + sk4) * first;
     DC_REQUIRE(total_ll < (1ll << 31), "greedy loop: too many work items");
     p.total = (int)total_ll;
     p.slots = 2 * p.tiles_n[3];
@@ -652,13 +671,13 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     DC_CHECK_CUDA(cudaLaunchKernelEx(&cfgl, kern, maps, p));
     b.parity = P & 1;
     if (p.trace) {
-        // debugging aid: dump the marks as int32 header {pairs, items per pair, steps, items per slot, first[0..3], tiles_n[0..3], tiles_m, skew[1..3]} + uint64 data
+        // debugging aid: dump the marks as int32 header {pairs, items per pair, steps, items per slot, first[1..4], tiles_m, skew[1..4], 0, 0, 0} + uint64 data
         std::vector<unsigned long long> host(trace_bytes / sizeof(unsigned long long));
         DC_CHECK_CUDA(cudaStreamSynchronize(s));
         DC_CHECK_CUDA(cudaMemcpy(host.data(), trace_buf, trace_bytes, cudaMemcpyDeviceToHost));
         if (FILE *fp = fopen(trace_path, "wb")) {
-            const int hdr[16] = {pairs, trace_items, P, first, p.first[0], p.first[1], p.first[2], p.first[3],
-                                 p.tiles_n[0], p.tiles_n[1], p.tiles_n[2], p.tiles_n[3], p.tiles_m, p.skew[1], p.skew[2], p.skew[3]};
+            const int hdr[16] = {pairs, trace_items, P, first, p.first[1], p.first[2], p.first[3], p.first[4],
+                                 p.tiles_m, p.skew[1], p.skew[2], p.skew[3], p.skew[4], 0, 0, 0};
             fwrite(hdr, sizeof(int), 16, fp);
             fwrite(host.data(), 1, trace_bytes, fp);
             fclose(fp);

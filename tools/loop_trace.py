@@ -12,24 +12,24 @@ def main():
     raw = open(path, "rb").read()
     hdr = np.frombuffer(raw[:64], dtype=np.int32)
     pairs, items, P, ips = (int(x) for x in hdr[:4])
-    first = [int(x) for x in hdr[4:8]] + [ips]
-    tiles_m = int(hdr[12])
-    skew = np.array([0] + [int(x) for x in hdr[13:16]])
+    first = [0] + [int(x) for x in hdr[4:8]]
+    tiles_m = int(hdr[8])
+    skew = np.array([0] + [int(x) for x in hdr[9:13]])
     d = np.frombuffer(raw[64:], dtype=np.uint64).reshape(pairs, items, 8).astype(np.float64)
     t0 = d[d > 0].min()
     d = np.where(d > 0, (d - t0) / 1e3, np.nan)         # us
-    total = (P * tiles_m + int(skew[3])) * ips
+    total = (P * tiles_m + int(skew[4])) * ips
     print("pairs %d, items/pair %d, steps %d, items/slot %d, tiles_m %d, skews %s, kernel span %.1f us" % (pairs, items, P, ips, tiles_m, skew.tolist(), np.nanmax(d)))
     idx = np.arange(items)[None, :] * pairs + np.arange(pairs)[:, None]
     j = idx % ips
-    stage = (j >= first[1]).astype(int) + (j >= first[2]) + (j >= first[3])
+    stage = (j >= first[1]).astype(int) + (j >= first[2]) + (j >= first[3]) + (j >= first[4])
     u = idx // ips - skew[stage]
-    valid = (idx < total) & (u >= 0) & (u < P * tiles_m) & ~np.isnan(d[..., 5])
+    valid = (idx < total) & (u >= 0) & (u < P * tiles_m) & ~np.isnan(d[..., 7])
     step = u // tiles_m
     sel_step = int(sys.argv[2]) if len(sys.argv) > 2 else None
     names = ["dep wait (1-0)", "issue loads (2-1)", "acc buffer->first operands (4-3)", "mma issue (5-4)",
              "mma end->tmem released (6-5)", "publish (+merge) (7-6)", "item period (5 - prev 5)"]
-    for s in range(4):
+    for s in range(5):
         m = valid & (stage == s)
         if sel_step is not None:
             m &= step == sel_step
