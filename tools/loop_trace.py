@@ -1,5 +1,5 @@
 """Summary of a DCAP_LOOP_TRACE dump (csrc/greedy_loop.cu): per stage, how long the leader CTA of a pair spends in
-each phase of an item.  Marks: 0 producer reaches the item, 1 dependency met, 2 loads issued, 3 MMA issuer has the
+each phase of an item.  Marks: 0 producer reaches the item, 1 dependency met, 2 proxy fence done, 3 MMA issuer has the
 accumulator buffer, 4 first operands landed, 5 last MMA issued, 6 epilogue warp 2 released TMEM, 7 published.
 Usage: python tools/loop_trace.py gpurun_out/trace.bin [step]"""
 import sys
@@ -27,7 +27,7 @@ def main():
     valid = (idx < total) & (u >= 0) & (u < P * tiles_m) & ~np.isnan(d[..., 7])
     step = u // tiles_m
     sel_step = int(sys.argv[2]) if len(sys.argv) > 2 else None
-    names = ["dep wait (1-0)", "issue loads (2-1)", "acc buffer->first operands (4-3)", "mma issue (5-4)",
+    names = ["dep wait (1-0)", "proxy fence (2-1)", "acc buffer->first operands (4-3)", "mma issue (5-4)",
              "mma end->tmem released (6-5)", "publish (+merge) (7-6)", "item period (5 - prev 5)"]
     for s in range(5):
         m = valid & (stage == s)
