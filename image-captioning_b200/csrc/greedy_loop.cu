@@ -49,7 +49,7 @@ struct LoopParams {
     int map_a[4][2], map_b[4];         // tensor-map index of the A operand by step parity, and of B
     int kb_main[4], map_b2[4];         // folded feature term: k-blocks >= kb_main[s] come from (Fb, map_b2[s]) -- [x | f] . [W ; Wf]^T in one accumulator
     const float *b1, *bd1;             // fold: biases of LSTM1 (gate-interleaved) and Dense(1024) (without fold they sit inside g1f / d1f)
-    int fold, pfence, epi_acquire;     // knobs (see greedy_loop_bf16)
+    int fold, pfence, next_prefetch;   // knobs (see greedy_loop_bf16)
     const float *g1f, *d1f, *b2, *bias_v;
     float *c1, *c2;
     __nv_bfloat16 *X1[2], *X2[2], *d;
@@ -75,6 +75,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -151,7 +152,9 @@ __device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, co
                                           float *c_row, bool masked, const __nv_bfloat16 *h_prev_row,
                                           __nv_bfloat16 *h_a_row, __nv_bfloat16 *h_b_row, uint64_t *full_bar,
                                           uint32_t full_phase, unsigned *err) {
-    float4 a_nxt[8], c_nxt[2];
+    // The cell state of all four chunks is requested before the accumulator is waited for (it does not depend on
+    // it): inside the TMEM-holding part only the addend / bias rows are still fetched, one chunk ahead.
+    float4 a_nxt[8], c_all[8];
     uint4 h_nxt = make_uint4(0, 0, 0, 0);
     auto load_operands = [&](int nb) {
         if constexpr (kAdd) {
@@ -161,20 +164,21 @@ __device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, co
 #pragma unroll
             for (int j = 0; j < 8; ++j) a_nxt[j] = __ldg(reinterpret_cast<const float4 *>(bias + nb + 4 * j));
         }
-        c_nxt[0] = __ldcg(reinterpret_cast<const float4 *>(c_row + (nb >> 2)));
-        c_nxt[1] = __ldcg(reinterpret_cast<const float4 *>(c_row + (nb >> 2) + 4));
         if (masked) h_nxt = __ldcg(reinterpret_cast<const uint4 *>(h_prev_row + (nb >> 2)));
     };
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c_all[j] = __ldcg(reinterpret_cast<const float4 *>(c_row + (n0 >> 2)) + j);
     load_operands(n0);
     mbar_wait_wd(full_bar, full_phase, err, 0x30u);
     tc_fence_after();
-#pragma unroll 1
+#pragma unroll
     for (int c0 = 0; c0 < 128; c0 += 32) {
         const int nb = n0 + c0;
         float4 a_cur[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) a_cur[j] = a_nxt[j];
-        const float c_old[8] = {c_nxt[0].x, c_nxt[0].y, c_nxt[0].z, c_nxt[0].w, c_nxt[1].x, c_nxt[1].y, c_nxt[1].z, c_nxt[1].w};
+        const float4 c_lo = c_all[c0 >> 4], c_hi = c_all[(c0 >> 4) + 1];
+        const float c_old[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
         const uint32_t hw[4] = {h_nxt.x, h_nxt.y, h_nxt.z, h_nxt.w};
         if (c0 + 32 < 128) load_operands(nb + 32);
         float v[32];
@@ -494,6 +498,21 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
         for (int item = pair; item < total; item += num_pairs) {
             const LoopItem it = decode_item(p, item);
             if (!it.live) continue;
+            if (p.next_prefetch && item + num_pairs < total) {
+                // the fp32 rows this warp will read in its NEXT item (per-RoI terms, cell state) start their way from
+                // DRAM into L2 now: a whole item period ahead, from threads that are otherwise waiting
+                const LoopItem nx = decode_item(p, item + num_pairs);
+                const int nm = nx.rb * 256 + (int)rank * 128 + quarter * 32 + lane;
+                if (nx.live && nx.s <= 2 && nm < p.R) {
+                    const int nn0 = nx.cb * kBlockN + half * 128;
+                    if (nx.s != 1) {
+                        const float *row = nx.s == 0 ? p.g1f + (long long)nm * (4ll * p.U) + nn0 : p.d1f + (long long)nm * kDense + nn0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) prefetch_l2(row + 32 * j);
+                    }
+                    if (nx.s <= 1) prefetch_l2((nx.s == 0 ? p.c1 : p.c2) + (long long)nm * p.U + (nn0 >> 2));
+                }
+            }
             const int rb128 = it.rb * 2 + (int)rank;
             const int par = it.t & 1;
             if (it.s == 4) {
@@ -516,16 +535,15 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             const int n0 = it.cb * kBlockN + half * 128;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * 128;
             if (it.s <= 1) {
-                // This warp reads state written by other SMs (c, consumed token, previous h) with ld.global.cg, after the
-                // tile's MMAs, whose operands this CTA's producer only loaded once the counter it acquired said that state
-                // was published.  epi_acquire = 1 re-acquires that counter here as well (measured: ~1 us per item and warp).
-                if (p.epi_acquire) {
-                    if (lane == 0) {
-                        if (it.s == 0) { if (it.t > 0) wait_count(cnt_stage + 4 * n128 + rb128, (unsigned)kEpiWarps * it.t, err, 0x40u); }
-                        else wait_count(cnt_stage + rb128, (unsigned)(kEpiWarps * p.tiles_n[0]) * (it.t + 1), err, 0x41u);
-                    }
-                    __syncwarp();
+                // This warp reads state written by other SMs (c, consumed token, previous h), and it requests that state
+                // BEFORE it waits for the accumulator -- i.e. possibly before this CTA's producer has seen the dependency:
+                // it has to wait for the counter itself (without this wait small batches, whose dependencies are only just
+                // met, decode wrong tokens: measured).
+                if (lane == 0) {
+                    if (it.s == 0) { if (it.t > 0) wait_count(cnt_stage + 4 * n128 + rb128, (unsigned)kEpiWarps * it.t, err, 0x40u); }
+                    else wait_count(cnt_stage + rb128, (unsigned)(kEpiWarps * p.tiles_n[0]) * (it.t + 1), err, 0x41u);
                 }
+                __syncwarp();
                 const bool masked = __ldcg(p.tok + mr) == 0;
                 if (it.s == 0 && p.fold)
                     loop_cell<false>(taddr, n0, valid, nullptr, p.b1, p.c1 + mr * p.U, masked,
@@ -576,9 +594,11 @@ static bool loop_env_on() {
     return !(e && atoi(e) == 0);
 }
 
+// Measured at F = 1024 (8000 RoIs): folding costs 16 more k-blocks in two stages (+36 % tensor work per step) and is
+// slower than re-reading the hoisted fp32 terms (3.56 vs 3.38 ms); off unless DCAP_LOOP_FOLD=1.
 bool Decoder::greedy_loop_folds() const {
     const char *e = getenv("DCAP_LOOP_FOLD");
-    return !(e && atoi(e) == 0) && cfg.feat % kBlockK == 0;
+    return e && atoi(e) != 0 && cfg.feat % kBlockK == 0;
 }
 
 bool Decoder::greedy_loop_ok() const {
@@ -607,10 +627,10 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     p.first[5] = first;                                    // items per slot
     // wavefront skews (slots): each must cover its producer stage's latency (tile + epilogue + publish, 11-15 us;
     // a slot of ~60 items is ~4.5 us on 74 pairs), and skew[4] < tiles_m (see decode_item)
-    static const int skew_env = getenv("DCAP_LOOP_SKEW") ? atoi(getenv("DCAP_LOOP_SKEW")) : 19;
+    static const int skew_env = getenv("DCAP_LOOP_SKEW") ? atoi(getenv("DCAP_LOOP_SKEW")) : 21;
     int sk4 = p.tiles_m - 6 < skew_env ? p.tiles_m - 6 : skew_env;
     if (sk4 < 0) sk4 = 0;
-    p.skew[0] = 0; p.skew[1] = sk4 * 5 / 19; p.skew[2] = sk4 * 10 / 19; p.skew[3] = sk4 * 14 / 19; p.skew[4] = sk4;
+    p.skew[0] = 0; p.skew[1] = sk4 * 5 / 21; p.skew[2] = sk4 * 12 / 21; p.skew[3] = sk4 * 16 / 21; p.skew[4] = sk4;
     const long long total_ll = ((long long)P * p.tiles_m + sk4) * first;
     DC_REQUIRE(total_ll < (1ll << 31), "greedy loop: too many work items");
     p.total = (int)total_ll;
@@ -638,9 +658,9 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     rc |= make_tmap_bf16(&maps.m[kMapW1f], b.w1f, 4 * U, F, F, 128);
     rc |= make_tmap_bf16(&maps.m[kMapWd1f], b.wd1f, kDense, F, F, 128);
     if (rc) return rc;
-    // Feature terms folded into the contraction (default): [emb | h1 | f] . [W1e ; U1 ; W1f]^T and [h2 | f] . [Wd1h ; Wd1f]^T
-    // in ONE accumulator, the feature k-blocks coming from the bf16 head output -- instead of re-reading the hoisted
-    // fp32 terms (97 MB per step at 8000 RoIs, which no longer fit L2 next to the rest of a step) in the epilogues.
+    // Optional (DCAP_LOOP_FOLD=1): feature terms folded into the contraction, [emb | h1 | f] . [W1e ; U1 ; W1f]^T and
+    // [h2 | f] . [Wd1h ; Wd1f]^T in ONE accumulator, the feature k-blocks coming from the bf16 head output -- instead of
+    // re-reading the hoisted fp32 terms (97 MB per step at 8000 RoIs) in the epilogues.
     p.fold = greedy_loop_folds() ? 1 : 0;
     for (int i = 0; i < 4; ++i) { p.kb_main[i] = p.num_kb[i]; p.map_b2[i] = kMapW1f; }
     if (p.fold) {
@@ -650,8 +670,8 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     p.b1 = b.b1_i; p.bd1 = W("imgcap_lstm_d1/bias");
     static const int pfence_env = getenv("DCAP_LOOP_PFENCE") ? atoi(getenv("DCAP_LOOP_PFENCE")) : 2;
     p.pfence = pfence_env;
-    static const int epiacq_env = getenv("DCAP_LOOP_EPIACQ") ? atoi(getenv("DCAP_LOOP_EPIACQ")) : 0;
-    p.epi_acquire = epiacq_env;
+    static const int npf_env = getenv("DCAP_LOOP_NPF") ? atoi(getenv("DCAP_LOOP_NPF")) : 1;
+    p.next_prefetch = npf_env;
     // step t (parity t & 1): LSTM1 reads X1[par]; LSTM2 reads X2[par]; Dense(1024) reads the h2 half of X2[par ^ 1]
     p.map_a[0][0] = kMapX1a; p.map_a[0][1] = kMapX1b; p.map_b[0] = kMapW1;
     p.map_a[1][0] = kMapX2a; p.map_a[1][1] = kMapX2b; p.map_b[1] = kMapW2;
