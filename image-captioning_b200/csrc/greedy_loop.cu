@@ -66,12 +66,30 @@ struct LoopParams {
     int trace_items;
 };
 
+constexpr int kLoopThreads = kThreads;
+constexpr int kRing = 8;                                 // item-done / dependency-seen barrier rings
 constexpr long long kWatchdogCycles = 4000000000ll;      // ~2 s
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
@@ -93,6 +111,17 @@ __device__ __forceinline__ void wait_count(const unsigned *p, unsigned target, u
         if ((spins++ & 63u) == 0) {
             if (loop_aborted(err)) return;
             if (clock64() - t0 > kWatchdogCycles) { atomicCAS(err, 0u, code | (target << 8)); return; }
+        }
+    }
+}
+__device__ __forceinline__ void mbar_wait_acq_cluster_wd(uint64_t *bar, uint32_t parity, unsigned *err, unsigned code) {
+    if (mbar_try_wait_acq_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (!mbar_try_wait_acq_cluster(bar, parity)) {
+        if ((spins++ & 255u) == 0) {
+            if (loop_aborted(err)) return;
+            if (clock64() - t0 > kWatchdogCycles) { atomicCAS(err, 0u, code); return; }
         }
     }
 }
@@ -147,28 +176,29 @@ __device__ __forceinline__ LoopItem decode_item(const LoopParams &p, int item) {
 
 // Keras LSTM cell on gate-interleaved columns (column 4u+g): z = acc + addend / bias; hard-sigmoid gates, tanh
 // candidate, masked rows (consumed token 0) carry (h, c).  c fp32 in place, h bf16 into one or two operand buffers.
-template <bool kAdd>
+template <bool kAdd, int kAhead>
 __device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, const float *add_row, const float *bias,
                                           float *c_row, bool masked, const __nv_bfloat16 *h_prev_row,
                                           __nv_bfloat16 *h_a_row, __nv_bfloat16 *h_b_row, uint64_t *full_bar,
                                           uint32_t full_phase, unsigned *err) {
     // The cell state of all four chunks is requested before the accumulator is waited for (it does not depend on
     // it): inside the TMEM-holding part only the addend / bias rows are still fetched, one chunk ahead.
-    float4 a_nxt[8], c_all[8];
-    uint4 h_nxt = make_uint4(0, 0, 0, 0);
-    auto load_operands = [&](int nb) {
+    float4 a_buf[2][8], c_all[8];
+    uint4 h_buf[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    auto load_operands = [&](float4 (&a)[8], uint4 &hp, int nb) {
         if constexpr (kAdd) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a_nxt[j] = __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j));
+            for (int j = 0; j < 8; ++j) a[j] = __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j));
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a_nxt[j] = __ldg(reinterpret_cast<const float4 *>(bias + nb + 4 * j));
+            for (int j = 0; j < 8; ++j) a[j] = __ldg(reinterpret_cast<const float4 *>(bias + nb + 4 * j));
         }
-        if (masked) h_nxt = __ldcg(reinterpret_cast<const uint4 *>(h_prev_row + (nb >> 2)));
+        if (masked) hp = __ldcg(reinterpret_cast<const uint4 *>(h_prev_row + (nb >> 2)));
     };
 #pragma unroll
     for (int j = 0; j < 8; ++j) c_all[j] = __ldcg(reinterpret_cast<const float4 *>(c_row + (n0 >> 2)) + j);
-    load_operands(n0);
+    load_operands(a_buf[0], h_buf[0], n0);
+    if constexpr (kAdd && kAhead == 2) load_operands(a_buf[1], h_buf[1], n0 + 32);  // addend rows come from DRAM: two chunks in flight
     mbar_wait_wd(full_bar, full_phase, err, 0x30u);
     tc_fence_after();
 #pragma unroll
@@ -176,11 +206,16 @@ __device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, co
         const int nb = n0 + c0;
         float4 a_cur[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a_cur[j] = a_nxt[j];
+        for (int j = 0; j < 8; ++j) a_cur[j] = a_buf[(c0 >> 5) & 1][j];
         const float4 c_lo = c_all[c0 >> 4], c_hi = c_all[(c0 >> 4) + 1];
         const float c_old[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
-        const uint32_t hw[4] = {h_nxt.x, h_nxt.y, h_nxt.z, h_nxt.w};
-        if (c0 + 32 < 128) load_operands(nb + 32);
+        const uint4 hq = h_buf[(c0 >> 5) & 1];
+        const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+        if constexpr (kAdd && kAhead == 2) {
+            if (c0 + 64 < 128) load_operands(a_buf[(c0 >> 5) & 1], h_buf[(c0 >> 5) & 1], nb + 64);
+        } else {
+            if (c0 + 32 < 128) load_operands(a_buf[((c0 >> 5) & 1) ^ 1], h_buf[((c0 >> 5) & 1) ^ 1], nb + 32);
+        }
         float v[32];
         tmem_ld32(taddr + c0, v);
         float c_new[8], h_new[8];
@@ -217,21 +252,22 @@ __device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, co
 // d = relu(acc + addend) -> bf16
 __device__ __forceinline__ void loop_dense(uint32_t taddr, int n0, bool valid, const float *add_row, __nv_bfloat16 *out_row,
                                            uint64_t *full_bar, uint32_t full_phase, unsigned *err) {
-    float4 a_nxt[8];
-    auto load_operands = [&](int nb) {
+    float4 a_buf[2][8];
+    auto load_operands = [&](float4 (&a)[8], int nb) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a_nxt[j] = __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j));
+        for (int j = 0; j < 8; ++j) a[j] = __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j));
     };
-    load_operands(n0);
+    load_operands(a_buf[0], n0);
+    load_operands(a_buf[1], n0 + 32);
     mbar_wait_wd(full_bar, full_phase, err, 0x31u);
     tc_fence_after();
-#pragma unroll 1
+#pragma unroll
     for (int c0 = 0; c0 < 128; c0 += 32) {
         const int nb = n0 + c0;
         float4 a_cur[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a_cur[j] = a_nxt[j];
-        if (c0 + 32 < 128) load_operands(nb + 32);
+        for (int j = 0; j < 8; ++j) a_cur[j] = a_buf[(c0 >> 5) & 1][j];
+        if (c0 + 64 < 128) load_operands(a_buf[(c0 >> 5) & 1], nb + 64);
         float v[32];
         tmem_ld32(taddr + c0, v);
         uint32_t pk[16];
@@ -372,8 +408,8 @@ __device__ __forceinline__ void loop_merge(const LoopParams &p, int m_base, int 
     if (p.writer_proxy_fence) fence_proxy_async_all();
 }
 
-template <bool kSum>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kSum, int kAhead>
+__global__ void __launch_bounds__(kLoopThreads, 1)
 greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
     using S = TcSmem2;
     constexpr int kStages = S::kStages;
@@ -387,7 +423,9 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
     uint64_t *empty_bar = full_bar + kStages;
     uint64_t *tmem_full = empty_bar + kStages;
     uint64_t *tmem_empty = tmem_full + 2;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    uint64_t *done_bar = tmem_empty + 2;                           // [kRing] (CTA 1's copy is used) the 16 epilogue warps of the pair have finished an item -> publisher
+    uint64_t *dep_bar = done_bar + kRing;                          // [kRing] the producer has seen a stage-0/1 item's dependency -> epilogue warps
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(dep_bar + kRing);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -401,6 +439,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
         for (int i = 0; i < kLoopMaps; ++i) tma_prefetch_desc(&maps.m[i]);
         for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * kEpiWarps); }
+        for (int i = 0; i < kRing; ++i) { mbar_init(&done_bar[i], 2 * kEpiWarps); mbar_init(&dep_bar[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -414,6 +453,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
         // ===================== TMA producer (both CTAs) =====================
         int stage = 0;
         uint32_t phase = 0;
+        int n_dep = 0;                                                 // stage-0/1 items so far (dep_bar ring position)
         for (int item = pair; item < total; item += num_pairs) {
             const LoopItem it = decode_item(p, item);
             if (!it.live || it.s == 4) continue;                       // warp-uniform: pipeline fill / drain slots; merge items have no operands
@@ -430,10 +470,13 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                 LOOP_TRACE(0);
                 // operands of this CTA's 128 rows written by earlier items
                 if (it.s == 0) {
-                    if (it.t > 0) wait_count(cnt_stage + 4 * n128 + rb128, (unsigned)kEpiWarps * it.t, err, 0x10u);
+                    if (it.t > 0) wait_count(cnt_stage + 4 * n128 + rb128, (unsigned)it.t, err, 0x10u);
                 } else {
-                    wait_count(cnt_stage + (it.s - 1) * n128 + rb128, (unsigned)(kEpiWarps * p.tiles_n[it.s - 1]) * (it.t + 1), err, 0x10u + it.s);
+                    wait_count(cnt_stage + (it.s - 1) * n128 + rb128, (unsigned)p.tiles_n[it.s - 1] * (it.t + 1), err, 0x10u + it.s);
                 }
+                // the epilogue warps of stage-0/1 items read state published by the same items: tell them it is there
+                // (cta-scope release on top of the gpu-scope acquire above)
+                if (it.s <= 1) { mbar_arrive(&dep_bar[n_dep & (kRing - 1)]); ++n_dep; }
                 LOOP_TRACE(1);
                 if (p.pfence == 1) fence_proxy_async_all();
                 else if (p.pfence == 2) fence_proxy_async_global();
@@ -455,6 +498,25 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             }
             __syncwarp();
         }
+    } else if (warp == 1 && rank == 1) {
+        // ===================== publisher (this warp is idle in CTA 1: the leader issues the MMAs) =====================
+        // An item's results become visible to the other SMs here: once the pair's 16 epilogue warps have arrived on the
+        // item's barrier (cluster-scope release / acquire), ONE gpu-scope fence and one counter increment per 128-row
+        // block publish them all (cumulativity: the pattern of a grid barrier).  The epilogue warps never wait for a
+        // fence themselves.
+        if (lane == 0) {
+            int n_done = 0;
+            for (int item = pair; item < total; item += num_pairs) {
+                const LoopItem it = decode_item(p, item);
+                if (!it.live) continue;
+                mbar_wait_acq_cluster_wd(&done_bar[n_done & (kRing - 1)], (n_done / kRing) & 1, err, 0x50u);
+                ++n_done;
+                __threadfence();
+                atomicAdd(cnt_stage + it.s * n128 + it.rb * 2, 1u);
+                atomicAdd(cnt_stage + it.s * n128 + it.rb * 2 + 1, 1u);
+            }
+        }
+        __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (lane == 0 && rank == 0) {
@@ -495,6 +557,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
         const int half = (warp - 2) >> 2;                              // which 128 of the tile's 256 columns
         int acc = 0;
         uint32_t acc_phase = 0;
+        int n_done = 0, n_dep = 0;                                     // ring positions: items finished, stage-0/1 items seen
         for (int item = pair; item < total; item += num_pairs) {
             const LoopItem it = decode_item(p, item);
             if (!it.live) continue;
@@ -517,14 +580,12 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             const int par = it.t & 1;
             if (it.s == 4) {
                 // ---- merge item: token, caption score and next embedding row of this CTA's 128 rows; 16 rows per warp ----
-                if (lane == 0) wait_count(cnt_stage + 3 * n128 + rb128, (unsigned)(kEpiWarps * p.tiles_n[3]) * (it.t + 1), err, 0x44u);
+                if (lane == 0) wait_count(cnt_stage + 3 * n128 + rb128, (unsigned)p.tiles_n[3] * (it.t + 1), err, 0x44u);
                 __syncwarp();
                 loop_merge<kSum>(p, it.rb * 256 + (int)rank * 128 + (warp - 2) * 16, it.t, lane);
                 __syncwarp();
-                if (lane == 0) {
-                    __threadfence();
-                    atomicAdd(cnt_stage + 4 * n128 + rb128, 1u);
-                }
+                if (lane == 0) mbar_arrive_release_cluster(mapa_u32(&done_bar[n_done & (kRing - 1)], 1));
+                ++n_done;
                 if (warp == 2 && lane == 0) { LOOP_TRACE(6); LOOP_TRACE(7); }
                 continue;
             }
@@ -537,24 +598,21 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             if (it.s <= 1) {
                 // This warp reads state written by other SMs (c, consumed token, previous h), and it requests that state
                 // BEFORE it waits for the accumulator -- i.e. possibly before this CTA's producer has seen the dependency:
-                // it has to wait for the counter itself (without this wait small batches, whose dependencies are only just
-                // met, decode wrong tokens: measured).
-                if (lane == 0) {
-                    if (it.s == 0) { if (it.t > 0) wait_count(cnt_stage + 4 * n128 + rb128, (unsigned)kEpiWarps * it.t, err, 0x40u); }
-                    else wait_count(cnt_stage + rb128, (unsigned)(kEpiWarps * p.tiles_n[0]) * (it.t + 1), err, 0x41u);
-                }
-                __syncwarp();
+                // it waits until the producer, which acquired the dependency counter, says so (without a wait small batches,
+                // whose dependencies are only just met, decode wrong tokens: measured).
+                mbar_wait_wd(&dep_bar[n_dep & (kRing - 1)], (n_dep / kRing) & 1, err, 0x40u);
+                ++n_dep;
                 const bool masked = __ldcg(p.tok + mr) == 0;
                 if (it.s == 0 && p.fold)
-                    loop_cell<false>(taddr, n0, valid, nullptr, p.b1, p.c1 + mr * p.U, masked,
+                    loop_cell<false, kAhead>(taddr, n0, valid, nullptr, p.b1, p.c1 + mr * p.U, masked,
                                      p.X1[par] + mr * p.K1 + p.Epad, p.X1[par ^ 1] + mr * p.K1 + p.Epad,
                                      p.X2[par] + mr * (2ll * p.U), &tmem_full[acc], acc_phase, err);
                 else if (it.s == 0)
-                    loop_cell<true>(taddr, n0, valid, p.g1f + mr * (4ll * p.U), nullptr, p.c1 + mr * p.U, masked,
+                    loop_cell<true, kAhead>(taddr, n0, valid, p.g1f + mr * (4ll * p.U), nullptr, p.c1 + mr * p.U, masked,
                                     p.X1[par] + mr * p.K1 + p.Epad, p.X1[par ^ 1] + mr * p.K1 + p.Epad,
                                     p.X2[par] + mr * (2ll * p.U), &tmem_full[acc], acc_phase, err);
                 else
-                    loop_cell<false>(taddr, n0, valid, nullptr, p.b2, p.c2 + mr * p.U, masked,
+                    loop_cell<false, kAhead>(taddr, n0, valid, nullptr, p.b2, p.c2 + mr * p.U, masked,
                                      p.X2[par] + mr * (2ll * p.U) + p.U, p.X2[par ^ 1] + mr * (2ll * p.U) + p.U,
                                      nullptr, &tmem_full[acc], acc_phase, err);
             } else if (it.s == 2) {
@@ -570,13 +628,11 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             if (warp == 2 && lane == 0) LOOP_TRACE(6);
-            // publish this warp's rows of the tile
+            // this warp's rows of the tile are written: hand them to the publisher
             if (p.writer_proxy_fence) fence_proxy_async_all();
             __syncwarp();
-            if (lane == 0) {
-                __threadfence();
-                atomicAdd(cnt_stage + it.s * n128 + rb128, 1u);
-            }
+            if (lane == 0) mbar_arrive_release_cluster(mapa_u32(&done_bar[n_done & (kRing - 1)], 1));
+            ++n_done;
             if (warp == 2 && lane == 0) LOOP_TRACE(7);
         }
     }
@@ -670,7 +726,7 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     p.b1 = b.b1_i; p.bd1 = W("imgcap_lstm_d1/bias");
     static const int pfence_env = getenv("DCAP_LOOP_PFENCE") ? atoi(getenv("DCAP_LOOP_PFENCE")) : 2;
     p.pfence = pfence_env;
-    static const int npf_env = getenv("DCAP_LOOP_NPF") ? atoi(getenv("DCAP_LOOP_NPF")) : 1;
+    static const int npf_env = getenv("DCAP_LOOP_NPF") ? atoi(getenv("DCAP_LOOP_NPF")) : 0;     // measured: no gain (3.36 vs 3.26 ms)
     p.next_prefetch = npf_env;
     // step t (parity t & 1): LSTM1 reads X1[par]; LSTM2 reads X2[par]; Dense(1024) reads the h2 half of X2[par ^ 1]
     p.map_a[0][0] = kMapX1a; p.map_a[0][1] = kMapX1b; p.map_b[0] = kMapW1;
@@ -690,14 +746,17 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     if (int rc2 = embed_gather(W("imgcap_embedding_layer/embeddings"), ws.tok, B, cfg.embed, V, b.X1[0], K1, true, s)) return rc2;
 
     using S = TcSmem2;
-    auto kern = scores ? greedy_loop_kernel<true> : greedy_loop_kernel<false>;
-    static std::atomic<unsigned long long> attr_set[2];
-    DC_CHECK_CUDA(once_per_device(attr_set[scores ? 1 : 0], [&] {
+    // addend rows of the LSTM1 cell one or two chunks ahead (two: a few registers spilled, measured)
+    static const int ahead_env = getenv("DCAP_LOOP_AHEAD") ? atoi(getenv("DCAP_LOOP_AHEAD")) : 1;
+    auto kern = ahead_env == 2 ? (scores ? greedy_loop_kernel<true, 2> : greedy_loop_kernel<false, 2>)
+                               : (scores ? greedy_loop_kernel<true, 1> : greedy_loop_kernel<false, 1>);
+    static std::atomic<unsigned long long> attr_set[4];
+    DC_CHECK_CUDA(once_per_device(attr_set[(scores ? 1 : 0) + (ahead_env == 2 ? 2 : 0)], [&] {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBaseBytes);
         return e != cudaSuccess ? e : cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
     }));
     cudaLaunchConfig_t cfgl = {};
-    cfgl.blockDim = dim3(kThreads);
+    cfgl.blockDim = dim3(kLoopThreads);
     cfgl.dynamicSmemBytes = S::kBaseBytes; cfgl.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
