@@ -62,7 +62,7 @@ struct LoopParams {
     int n128;
     int l2_prefetch;
     int writer_proxy_fence;            // 1: epilogue warps also run fence.proxy.async before they publish (belt and braces; measured)
-    unsigned long long *trace;         // debugging: [pairs][trace_items][8] globaltimer marks of the leader CTA (DCAP_LOOP_TRACE)
+    unsigned long long *trace;         // debugging: [pairs][trace_items][12] globaltimer marks of the leader CTA (DCAP_LOOP_TRACE)
     int trace_items;
 };
 
@@ -146,7 +146,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     do {                                                                                                      \
         if (p.trace && rank == 0) {                                                                           \
             const int n_ = (item - pair) / num_pairs;                                                         \
-            if (n_ < p.trace_items) p.trace[((long long)pair * p.trace_items + n_) * 8 + (slot)] = globaltimer_ns(); \
+            if (n_ < p.trace_items) p.trace[((long long)pair * p.trace_items + n_) * 12 + (slot)] = globaltimer_ns(); \
         }                                                                                                     \
     } while (0)
 
@@ -578,6 +578,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             }
             const int rb128 = it.rb * 2 + (int)rank;
             const int par = it.t & 1;
+            if (warp == 2 && lane == 0) LOOP_TRACE(8);
             if (it.s == 4) {
                 // ---- merge item: token, caption score and next embedding row of this CTA's 128 rows; 16 rows per warp ----
                 if (lane == 0) wait_count(cnt_stage + 3 * n128 + rb128, (unsigned)p.tiles_n[3] * (it.t + 1), err, 0x44u);
@@ -622,6 +623,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                 const float4 r4 = loop_argmax<kSum>(taddr, n0, p.V, p.bias_v, &tmem_full[acc], acc_phase, err);
                 if (valid) p.partial[(long long)(it.cb * 2 + half) * p.R + m] = r4;
             }
+            if (warp == 2 && lane == 0) LOOP_TRACE(9);
             // accumulator buffer drained: hand it back to the MMA issuer (the leader's barrier)
             tc_fence_before();
             __syncwarp();
@@ -776,7 +778,7 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     const char *trace_path = getenv("DCAP_LOOP_TRACE");
     static unsigned long long *trace_buf = nullptr;
     const int trace_items = ceil_div(total, pairs);
-    const size_t trace_bytes = sizeof(unsigned long long) * 8 * (size_t)trace_items * pairs;
+    const size_t trace_bytes = sizeof(unsigned long long) * 12 * (size_t)trace_items * pairs;
     if (trace_path) {
         cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st == cudaStreamCaptureStatusNone) {

@@ -1,6 +1,6 @@
 """Summary of a DCAP_LOOP_TRACE dump (csrc/greedy_loop.cu): per stage, how long the leader CTA of a pair spends in
 each phase of an item.  Marks: 0 producer reaches the item, 1 dependency met, 2 proxy fence done, 3 MMA issuer has the
-accumulator buffer, 4 first operands landed, 5 last MMA issued, 6 epilogue warp 2 released TMEM, 7 published.
+accumulator buffer, 4 first operands landed, 5 last MMA issued, 6 epilogue warp 2 released TMEM, 7 published, 8 epilogue warp 2 starts the item, 9 its body is done (before the TMEM release).
 Usage: python tools/loop_trace.py gpurun_out/trace.bin [step]"""
 import sys
 
@@ -15,7 +15,7 @@ def main():
     first = [0] + [int(x) for x in hdr[4:8]]
     tiles_m = int(hdr[8])
     skew = np.array([0] + [int(x) for x in hdr[9:13]])
-    d = np.frombuffer(raw[64:], dtype=np.uint64).reshape(pairs, items, 8).astype(np.float64)
+    d = np.frombuffer(raw[64:], dtype=np.uint64).reshape(pairs, items, 12).astype(np.float64)
     t0 = d[d > 0].min()
     d = np.where(d > 0, (d - t0) / 1e3, np.nan)         # us
     total = (P * tiles_m + int(skew[4])) * ips
@@ -28,7 +28,8 @@ def main():
     step = u // tiles_m
     sel_step = int(sys.argv[2]) if len(sys.argv) > 2 else None
     names = ["dep wait (1-0)", "proxy fence (2-1)", "acc buffer->first operands (4-3)", "mma issue (5-4)",
-             "mma end->tmem released (6-5)", "publish (+merge) (7-6)", "item period (5 - prev 5)"]
+             "mma end->tmem released (6-5)", "publish (+merge) (7-6)", "item period (5 - prev 5)",
+             "epilogue: start->body done (9-8)", "epilogue: own period (8 - prev 8)", "epilogue: start lag behind mma end (8-5)"]
     for s in range(5):
         m = valid & (stage == s)
         if sel_step is not None:
@@ -38,6 +39,11 @@ def main():
         period = np.full_like(d[..., 5], np.nan)
         period[:, 1:] = d[:, 1:, 5] - d[:, :-1, 5]
         rows.append(period)
+        rows.append(d[..., 9] - d[..., 8])
+        ep = np.full_like(d[..., 8], np.nan)
+        ep[:, 1:] = d[:, 1:, 8] - d[:, :-1, 8]
+        rows.append(ep)
+        rows.append(d[..., 8] - d[..., 5])
         print("stage %d: %d items" % (s, int(m.sum())))
         for name, r in zip(names, rows):
             v = r[m]
