@@ -285,8 +285,11 @@ int Decoder::v1_reset_state(int R, cudaStream_t s) {
     const size_t E = cfg.embed, U = cfg.units;
     DC_CHECK_CUDA(cudaMemsetAsync(ws.xh1, 0, sizeof(float) * R * (E + U), s));
     DC_CHECK_CUDA(cudaMemsetAsync(ws.xh2, 0, sizeof(float) * R * 2 * U, s));
-    DC_CHECK_CUDA(cudaMemsetAsync(ws.c1, 0, sizeof(float) * R * U, s));
-    DC_CHECK_CUDA(cudaMemsetAsync(ws.c2, 0, sizeof(float) * R * U, s));
+    // whole 32-row blocks: the persistent greedy loop keeps c in a blocked-32 layout (greedy_loop.cu), where row m's state is
+    // spread over its block; the workspace is reserved in multiples of 128 rows
+    const size_t Rc = ((size_t)R + 31) / 32 * 32;
+    DC_CHECK_CUDA(cudaMemsetAsync(ws.c1, 0, sizeof(float) * Rc * U, s));
+    DC_CHECK_CUDA(cudaMemsetAsync(ws.c2, 0, sizeof(float) * Rc * U, s));
     if (cfg.dtype == DC_DTYPE_BF16) return reset_state_bf16(R, s);
     return DC_OK;
 }

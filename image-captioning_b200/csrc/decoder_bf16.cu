@@ -201,16 +201,18 @@ int Decoder::head_bf16(const void *feats, int kind, int B, float *out, cudaStrea
     return gemm_bf16_tc(op(b.a1, F), op(b.w_head2, F), e2, B, F, F, kEpiStore, s);
 }
 
-int Decoder::v1_hoist_bf16(int B, cudaStream_t s) {
+int Decoder::v1_hoist_bf16(int B, cudaStream_t s, bool blocked32) {
     Bf16State &b = *bf;
     const int F = cfg.feat, U = cfg.units;
     // ws.F (fp32) may have come from the caller (DC_FEATS_HEAD_F32): refresh the bf16 operand copy
     if (int rc = f32_to_bf16(ws.F, b.Fb, (long long)B * F, s)) return rc;
     TcEpilogue e1;
     e1.bias = b.b1_i; e1.out_f32 = ws.g1f; e1.ld_f32 = 4 * U;                  // gate-interleaved columns
+    e1.blocked32 = blocked32 ? 1 : 0;
     if (int rc = gemm_bf16_tc(op(b.Fb, F), op(b.w1f, F), e1, B, 4 * U, F, kEpiStore, s)) return rc;
     TcEpilogue e2;
     e2.bias = W("imgcap_lstm_d1/bias"); e2.out_f32 = ws.d1f; e2.ld_f32 = kDense;
+    e2.blocked32 = blocked32 ? 1 : 0;
     return gemm_bf16_tc(op(b.Fb, F), op(b.wd1f, F), e2, B, kDense, F, kEpiStore, s);
 }
 
@@ -272,6 +274,9 @@ int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cu
         // the loop kernel contracts over the head features itself: only their bf16 copy is needed (ws.F may have come
         // from the caller: DC_FEATS_HEAD_F32), not the hoisted fp32 terms
         if (int rc = f32_to_bf16(ws.F, bf->Fb, (long long)B * cfg.feat, s)) return rc;
+    } else if (greedy_loop_ok()) {
+        // hoisted per-RoI terms in the blocked-32 layout the loop kernel's epilogues read with coalesced accesses
+        if (int rc = v1_hoist_bf16(B, s, true)) return rc;
     } else if (int rc = v1_hoist(B, s)) return rc;
     if (int rc = v1_reset_state(B, s)) return rc;
     if (int rc = fill_i32(ws.tok, B, 1, s)) return rc;

@@ -323,6 +323,11 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
                             reinterpret_cast<float4 *>(dst)[1] = make_float4(v[16 + g], v[20 + g], v[24 + g], v[28 + g]);
                         }
                     }
+                } else if (ep.blocked32) {
+                    // 32 consecutive rows x one column quad are 512 contiguous bytes: the lanes' stores coalesce
+                    float4 *dst = reinterpret_cast<float4 *>(ep.out_f32) + ((long long)(m >> 5) * (ep.ld_f32 >> 2) + (nb >> 2)) * 32 + (m & 31);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j * 32] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 } else {
                     float *dst = ep.out_f32 + (long long)m * ep.ld_f32 + nb;
 #pragma unroll
@@ -1062,7 +1067,9 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
         CUtensorMap mo = ma;
         const bool row_ops = ep.addend || ep.mask_src;
         const bool accum = ep.atomic || g.splits > 1;
-        bool want = ep.deint_units == 0 && (!row_ops || (tma_mask & 4)) && (!accum || (tma_mask & 8));
+        DC_REQUIRE(!ep.blocked32 || (ep.out_f32 && !ep.out_bf16 && !accum && N % 32 == 0 && ep.ld_f32 == N && ep.deint_units == 0),
+                   "blocked-32 output needs a plain fp32 output with N %% 32 == 0, ld == N");
+        bool want = ep.deint_units == 0 && !ep.blocked32 && (!row_ops || (tma_mask & 4)) && (!accum || (tma_mask & 8));
         if (want && ep.out_f32 && (accum || (tma_mask & 1))) {
             if (int rc = make_tmap(&mo, ep.out_f32, M, N, ep.ld_f32, 32, 32, 4)) return rc;
             g.tma_out = 1;

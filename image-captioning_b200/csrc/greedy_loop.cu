@@ -49,7 +49,7 @@ struct LoopParams {
     int map_a[4][2], map_b[4];         // tensor-map index of the A operand by step parity, and of B
     int kb_main[4], map_b2[4];         // folded feature term: k-blocks >= kb_main[s] come from (Fb, map_b2[s]) -- [x | f] . [W ; Wf]^T in one accumulator
     const float *b1, *bd1;             // fold: biases of LSTM1 (gate-interleaved) and Dense(1024) (without fold they sit inside g1f / d1f)
-    int fold, pfence, next_prefetch;   // knobs (see greedy_loop_bf16)
+    int fold, pfence, lookahead, defer;  // knobs (see greedy_loop_bf16)
     const float *g1f, *d1f, *b2, *bias_v;
     float *c1, *c2;
     __nv_bfloat16 *X1[2], *X2[2], *d;
@@ -60,7 +60,6 @@ struct LoopParams {
     float *scores;                     // kSum only
     unsigned int *cnt;                 // [s * n128 + 128-row block], s = 0..4: epilogue warps that have finished that block of a stage-s item; then the error word at 8 * n128
     int n128;
-    int l2_prefetch;
     int writer_proxy_fence;            // 1: epilogue warps also run fence.proxy.async before they publish (belt and braces; measured)
     unsigned long long *trace;         // debugging: [pairs][trace_items][12] globaltimer marks of the leader CTA (DCAP_LOOP_TRACE)
     int trace_items;
@@ -174,13 +173,36 @@ __device__ __forceinline__ LoopItem decode_item(const LoopParams &p, int item) {
 
 // ---- epilogue bodies: one warp = 32 rows (lane = row) x 128 columns of the CTA's 128 x 256 accumulator half ----
 
+// "Blocked-32" layout of the fp32 arrays that the epilogues touch with lane = row (hoisted per-RoI terms, cell state):
+// [row / 32][column / 4][row % 32][4 floats], so that the 32 lanes of a warp (32 consecutive rows, same column
+// quad) read or write 512 CONTIGUOUS bytes.  Row-major, a lane = row access touches 32 different lines per
+// instruction and the load/store unit serialises them: 16 bytes per cycle and SM, which made the LSTM1 tile's
+// epilogue LSU-bound (16 k LSU cycles = 8.6 us of its 11.4 us, measured).  ld4 = row length in float4.
+__device__ __forceinline__ const float4 *blk32(const float *base, long long m, int ld4) {
+    return reinterpret_cast<const float4 *>(base) + ((m >> 5) * ld4) * 32 + (m & 31);
+}
+__device__ __forceinline__ float4 *blk32(float *base, long long m, int ld4) {
+    return reinterpret_cast<float4 *>(base) + ((m >> 5) * ld4) * 32 + (m & 31);
+}
+
+// Deferred publication (big batches): a warp hands its PREVIOUS item to the publisher here, right after the wait for
+// the current item's accumulator and before the current item's first store -- the previous item's stores have
+// drained by then, so the release does not stall the warp (~1.4 us per item when it directly follows the stores).
+__device__ __forceinline__ void publish_pending(uint32_t pend) {
+    if (pend) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive_release_cluster(pend);
+    }
+}
+
 // Keras LSTM cell on gate-interleaved columns (column 4u+g): z = acc + addend / bias; hard-sigmoid gates, tanh
-// candidate, masked rows (consumed token 0) carry (h, c).  c fp32 in place, h bf16 into one or two operand buffers.
-template <bool kAdd, int kAhead>
-__device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, const float *add_row, const float *bias,
-                                          float *c_row, bool masked, const __nv_bfloat16 *h_prev_row,
+// candidate, masked rows (consumed token 0) carry (h, c).  c fp32 in place (blocked-32), h bf16 into one or two
+// operand buffers (row-major: they are TMA operands).  add_blk / c_blk = blk32(...) of this lane's row.
+template <bool kAdd>
+__device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, const float4 *add_blk, const float *bias,
+                                          float4 *c_blk, bool masked, const __nv_bfloat16 *h_prev_row,
                                           __nv_bfloat16 *h_a_row, __nv_bfloat16 *h_b_row, uint64_t *full_bar,
-                                          uint32_t full_phase, unsigned *err) {
+                                          uint32_t full_phase, unsigned *err, uint32_t pend) {
     // The cell state of all four chunks is requested before the accumulator is waited for (it does not depend on
     // it): inside the TMEM-holding part only the addend / bias rows are still fetched, one chunk ahead.
     float4 a_buf[2][8], c_all[8];
@@ -188,7 +210,7 @@ __device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, co
     auto load_operands = [&](float4 (&a)[8], uint4 &hp, int nb) {
         if constexpr (kAdd) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j));
+            for (int j = 0; j < 8; ++j) a[j] = __ldg(add_blk + ((nb >> 2) + j) * 32);
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] = __ldg(reinterpret_cast<const float4 *>(bias + nb + 4 * j));
@@ -196,26 +218,21 @@ __device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, co
         if (masked) hp = __ldcg(reinterpret_cast<const uint4 *>(h_prev_row + (nb >> 2)));
     };
 #pragma unroll
-    for (int j = 0; j < 8; ++j) c_all[j] = __ldcg(reinterpret_cast<const float4 *>(c_row + (n0 >> 2)) + j);
+    for (int j = 0; j < 8; ++j) c_all[j] = __ldcg(c_blk + ((n0 >> 4) + j) * 32);
     load_operands(a_buf[0], h_buf[0], n0);
-    if constexpr (kAdd && kAhead == 2) load_operands(a_buf[1], h_buf[1], n0 + 32);  // addend rows come from DRAM: two chunks in flight
     mbar_wait_wd(full_bar, full_phase, err, 0x30u);
     tc_fence_after();
+    publish_pending(pend);
 #pragma unroll
     for (int c0 = 0; c0 < 128; c0 += 32) {
-        const int nb = n0 + c0;
+        const int nb = n0 + c0, b = (c0 >> 5) & 1;
         float4 a_cur[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a_cur[j] = a_buf[(c0 >> 5) & 1][j];
+        for (int j = 0; j < 8; ++j) a_cur[j] = a_buf[b][j];
         const float4 c_lo = c_all[c0 >> 4], c_hi = c_all[(c0 >> 4) + 1];
         const float c_old[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
-        const uint4 hq = h_buf[(c0 >> 5) & 1];
-        const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
-        if constexpr (kAdd && kAhead == 2) {
-            if (c0 + 64 < 128) load_operands(a_buf[(c0 >> 5) & 1], h_buf[(c0 >> 5) & 1], nb + 64);
-        } else {
-            if (c0 + 32 < 128) load_operands(a_buf[((c0 >> 5) & 1) ^ 1], h_buf[((c0 >> 5) & 1) ^ 1], nb + 32);
-        }
+        const uint32_t hw[4] = {h_buf[b].x, h_buf[b].y, h_buf[b].z, h_buf[b].w};
+        if (c0 + 32 < 128) load_operands(a_buf[b ^ 1], h_buf[b ^ 1], nb + 32);
         float v[32];
         tmem_ld32(taddr + c0, v);
         float c_new[8], h_new[8];
@@ -234,8 +251,8 @@ __device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, co
         }
         if (valid) {
             const int u0 = nb >> 2;
-            reinterpret_cast<float4 *>(c_row + u0)[0] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
-            reinterpret_cast<float4 *>(c_row + u0)[1] = make_float4(c_new[4], c_new[5], c_new[6], c_new[7]);
+            c_blk[(u0 >> 2) * 32] = make_float4(c_new[0], c_new[1], c_new[2], c_new[3]);
+            c_blk[((u0 >> 2) + 1) * 32] = make_float4(c_new[4], c_new[5], c_new[6], c_new[7]);
             uint32_t pk[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -249,18 +266,21 @@ __device__ __forceinline__ void loop_cell(uint32_t taddr, int n0, bool valid, co
     }
 }
 
-// d = relu(acc + addend) -> bf16
-__device__ __forceinline__ void loop_dense(uint32_t taddr, int n0, bool valid, const float *add_row, __nv_bfloat16 *out_row,
-                                           uint64_t *full_bar, uint32_t full_phase, unsigned *err) {
+// d = relu(acc + addend) -> bf16.  blocked: the addend is blk32(...) of this lane's row; else a row-major row
+// (the bias vector in fold mode)
+template <bool kBlocked>
+__device__ __forceinline__ void loop_dense(uint32_t taddr, int n0, bool valid, const float4 *add4, __nv_bfloat16 *out_row,
+                                           uint64_t *full_bar, uint32_t full_phase, unsigned *err, uint32_t pend) {
     float4 a_buf[2][8];
     auto load_operands = [&](float4 (&a)[8], int nb) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j));
+        for (int j = 0; j < 8; ++j) a[j] = __ldg(add4 + ((nb >> 2) + j) * (kBlocked ? 32 : 1));
     };
     load_operands(a_buf[0], n0);
     load_operands(a_buf[1], n0 + 32);
     mbar_wait_wd(full_bar, full_phase, err, 0x31u);
     tc_fence_after();
+    publish_pending(pend);
 #pragma unroll
     for (int c0 = 0; c0 < 128; c0 += 32) {
         const int nb = n0 + c0;
@@ -287,47 +307,82 @@ __device__ __forceinline__ void loop_dense(uint32_t taddr, int n0, bool valid, c
     }
 }
 
-// per row: max, first arg-max (, sum exp(v - max)) of acc + bias over this warp's 128 columns
+// 32 lanes x 64 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+          "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+          "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+          "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// per row: max, first arg-max (, sum exp(v - max)) of acc + bias over this warp's 128 columns.  64 columns per TMEM
+// load; the arg-max is a TREE of (value, index) pairs -- a serial "if (x > best)" scan is a 32-long dependent chain
+// per chunk that two warps per scheduler cannot hide.  In a pair the higher index wins only on strict >, so the
+// first index of the maximum survives every level, as np.argmax.
 template <bool kSum>
 __device__ __forceinline__ float4 loop_argmax(uint32_t taddr, int n0, int N, const float *bias, uint64_t *full_bar,
-                                              uint32_t full_phase, unsigned *err) {
+                                              uint32_t full_phase, unsigned *err, uint32_t pend) {
     mbar_wait_wd(full_bar, full_phase, err, 0x32u);
     tc_fence_after();
+    publish_pending(pend);
     float best = -INFINITY, sum = 0.f;
     int best_i = 0x7fffffff;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
+    for (int c0 = 0; c0 < 128; c0 += 64) {
         const int nb = n0 + c0;
         if (nb >= N) break;                                          // warp-uniform
-        float v[32];
-        tmem_ld32(taddr + c0, v);
-        float cmax = -INFINITY;
-        int ci = 0x7fffffff;
-        if (nb + 32 <= N) {
+        float v[64];
+        tmem_ld64(taddr + c0, v);
+        if (nb + 64 <= N) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + nb + 4 * j));
                 v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
             }
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (v[j] > cmax) { cmax = v[j]; ci = nb + j; }       // strict > keeps the first index
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = nb + j;
-                const float x = (n < N) ? v[j] + __ldg(bias + n) : -INFINITY;
-                v[j] = x;
-                if (x > cmax) { cmax = x; ci = n; }
+            for (int j = 0; j < 64; ++j) v[j] = (nb + j < N) ? v[j] + __ldg(bias + min(nb + j, N - 1)) : -INFINITY;
+        }
+        float m[32];
+        int ix[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const bool hi = v[2 * j + 1] > v[2 * j];
+            m[j] = hi ? v[2 * j + 1] : v[2 * j];
+            ix[j] = hi ? 2 * j + 1 : 2 * j;
+        }
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) {
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+                const bool hi = m[2 * j + 1] > m[2 * j];
+                m[j] = hi ? m[2 * j + 1] : m[2 * j];
+                ix[j] = hi ? ix[2 * j + 1] : ix[2 * j];
             }
         }
+        const float cmax = m[0];
         if constexpr (kSum) {
             if (cmax > best) sum *= __expf(best - cmax);
         }
-        if (cmax > best) { best = cmax; best_i = ci; }
+        if (cmax > best) { best = cmax; best_i = nb + ix[0]; }
         if constexpr (kSum) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum += __expf(v[j] - best);
+            for (int j = 0; j < 64; ++j) sum += __expf(v[j] - best);
         }
     }
     return make_float4(best, __int_as_float(best_i), sum, 0.f);
@@ -408,7 +463,7 @@ __device__ __forceinline__ void loop_merge(const LoopParams &p, int m_base, int 
     if (p.writer_proxy_fence) fence_proxy_async_all();
 }
 
-template <bool kSum, int kAhead>
+template <bool kSum>
 __global__ void __launch_bounds__(kLoopThreads, 1)
 greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
     using S = TcSmem2;
@@ -451,42 +506,65 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
-        int stage = 0;
-        uint32_t phase = 0;
-        int n_dep = 0;                                                 // stage-0/1 items so far (dep_bar ring position)
-        for (int item = pair; item < total; item += num_pairs) {
-            const LoopItem it = decode_item(p, item);
-            if (!it.live || it.s == 4) continue;                       // warp-uniform: pipeline fill / drain slots; merge items have no operands
-            const int m0 = it.rb * 256 + (int)rank * 128;
-            const int rb128 = it.rb * 2 + (int)rank;
-            // the fp32 per-RoI terms of this tile (constant over the loop) on their way into L2 while the operands load
-            if (p.l2_prefetch && !p.fold && (it.s == 0 || it.s == 2)) {
-                const float *base = it.s == 0 ? p.g1f : p.d1f;
-                const long long ld = it.s == 0 ? 4ll * p.U : (long long)kDense;
-                for (int r = lane; r < 128; r += 32)
-                    if (m0 + r < p.R) prefetch_l2_bulk(base + (long long)(m0 + r) * ld + it.cb * 256, 1024);
-            }
-            if (lane == 0) {
+        // The dependency of the NEXT item is polled (acquire loads) in the producer's idle time -- the spins on a full
+        // operand ring -- so that an item whose dependency is met (the normal case) starts loading with no L2 round trip
+        // in front of it: with six ring slots the producer is only ~2 us ahead of the MMAs, and ~0.5 us per item spent
+        // on the counter showed up as MMA stalls (28 us per step, measured).
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int n_dep = 0;                                             // stage-0/1 items so far (dep_bar ring position)
+            auto next_gemm = [&](int item) {                           // next live GEMM item of this pair (>= item), or total
+                for (; item < total; item += num_pairs) {
+                    const LoopItem it = decode_item(p, item);
+                    if (it.live && it.s != 4) break;
+                }
+                return item;
+            };
+            auto dependency = [&](const LoopItem &it, const unsigned *&cnt, unsigned &target) {
+                const int rb128 = it.rb * 2 + (int)rank;
+                if (it.s == 0) { cnt = cnt_stage + 4 * n128 + rb128; target = (unsigned)it.t; }
+                else { cnt = cnt_stage + (it.s - 1) * n128 + rb128; target = (unsigned)p.tiles_n[it.s - 1] * (it.t + 1); }
+            };
+            int item = next_gemm(pair);
+            bool ready = false;
+            while (item < total) {
+                const LoopItem it = decode_item(p, item);
+                const int m0 = it.rb * 256 + (int)rank * 128;
                 LOOP_TRACE(0);
                 // operands of this CTA's 128 rows written by earlier items
-                if (it.s == 0) {
-                    if (it.t > 0) wait_count(cnt_stage + 4 * n128 + rb128, (unsigned)it.t, err, 0x10u);
-                } else {
-                    wait_count(cnt_stage + (it.s - 1) * n128 + rb128, (unsigned)p.tiles_n[it.s - 1] * (it.t + 1), err, 0x10u + it.s);
+                if (!ready) {
+                    const unsigned *cnt; unsigned target;
+                    dependency(it, cnt, target);
+                    if (target) wait_count(cnt, target, err, 0x10u + it.s);
                 }
                 // the epilogue warps of stage-0/1 items read state published by the same items: tell them it is there
-                // (cta-scope release on top of the gpu-scope acquire above)
+                // (cta-scope release on top of the gpu-scope acquire)
                 if (it.s <= 1) { mbar_arrive(&dep_bar[n_dep & (kRing - 1)]); ++n_dep; }
                 LOOP_TRACE(1);
                 if (p.pfence == 1) fence_proxy_async_all();
                 else if (p.pfence == 2) fence_proxy_async_global();
                 LOOP_TRACE(2);
+                const int nxt = next_gemm(item + num_pairs);
+                const unsigned *ncnt = nullptr; unsigned ntarget = 0;
+                if (nxt < total) { const LoopItem ni = decode_item(p, nxt); dependency(ni, ncnt, ntarget); }
+                bool nready = ntarget == 0;
                 const CUtensorMap *ma = &maps.m[p.map_a[it.s][it.t & 1]], *mb = &maps.m[p.map_b[it.s]];
                 const CUtensorMap *ma2 = &maps.m[kMapF], *mb2 = &maps.m[p.map_b2[it.s]];
                 const int nb0 = it.cb * kBlockN + (int)rank * 128;       // this CTA's half of the B tile
                 const int num_kb = p.num_kb[it.s], kb_main = p.kb_main[it.s];
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait_wd(&empty_bar[stage], phase ^ 1, err, 0x20u);
+                    if (!mbar_try_wait(&empty_bar[stage], phase ^ 1)) {
+                        const long long t0 = clock64();
+                        unsigned spins = 0;
+                        do {
+                            if (!nready && p.lookahead) nready = ld_acquire_u32(ncnt) >= ntarget;
+                            if ((spins++ & 255u) == 0) {
+                                if (loop_aborted(err)) break;
+                                if (clock64() - t0 > kWatchdogCycles) { atomicCAS(err, 0u, 0x20u); break; }
+                            }
+                        } while (!mbar_try_wait(&empty_bar[stage], phase ^ 1));
+                    }
                     if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (S::kStageA + S::kStageB));
                     const uint32_t bar = mapa_u32(&full_bar[stage], 0);
                     const bool main = kb < kb_main;
@@ -495,9 +573,11 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                     tma_load_2d_2sm(main ? mb : mb2, bar, smem_b + stage * S::kStageB, kc, nb0);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                ready = nready;
+                item = nxt;
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp == 1 && rank == 1) {
         // ===================== publisher (this warp is idle in CTA 1: the leader issues the MMAs) =====================
         // An item's results become visible to the other SMs here: once the pair's 16 epilogue warps have arrived on the
@@ -558,29 +638,17 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
         int acc = 0;
         uint32_t acc_phase = 0;
         int n_done = 0, n_dep = 0;                                     // ring positions: items finished, stage-0/1 items seen
+        uint32_t pend = 0;                                             // deferred publication: the previous item's done barrier (cluster address) or 0
         for (int item = pair; item < total; item += num_pairs) {
             const LoopItem it = decode_item(p, item);
             if (!it.live) continue;
-            if (p.next_prefetch && item + num_pairs < total) {
-                // the fp32 rows this warp will read in its NEXT item (per-RoI terms, cell state) start their way from
-                // DRAM into L2 now: a whole item period ahead, from threads that are otherwise waiting
-                const LoopItem nx = decode_item(p, item + num_pairs);
-                const int nm = nx.rb * 256 + (int)rank * 128 + quarter * 32 + lane;
-                if (nx.live && nx.s <= 2 && nm < p.R) {
-                    const int nn0 = nx.cb * kBlockN + half * 128;
-                    if (nx.s != 1) {
-                        const float *row = nx.s == 0 ? p.g1f + (long long)nm * (4ll * p.U) + nn0 : p.d1f + (long long)nm * kDense + nn0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) prefetch_l2(row + 32 * j);
-                    }
-                    if (nx.s <= 1) prefetch_l2((nx.s == 0 ? p.c1 : p.c2) + (long long)nm * p.U + (nn0 >> 2));
-                }
-            }
             const int rb128 = it.rb * 2 + (int)rank;
             const int par = it.t & 1;
             if (warp == 2 && lane == 0) LOOP_TRACE(8);
             if (it.s == 4) {
                 // ---- merge item: token, caption score and next embedding row of this CTA's 128 rows; 16 rows per warp ----
+                publish_pending(pend);                                 // never block on a counter with an item unpublished
+                pend = 0;
                 if (lane == 0) wait_count(cnt_stage + 3 * n128 + rb128, (unsigned)p.tiles_n[3] * (it.t + 1), err, 0x44u);
                 __syncwarp();
                 loop_merge<kSum>(p, it.rb * 256 + (int)rank * 128 + (warp - 2) * 16, it.t, lane);
@@ -604,25 +672,28 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                 mbar_wait_wd(&dep_bar[n_dep & (kRing - 1)], (n_dep / kRing) & 1, err, 0x40u);
                 ++n_dep;
                 const bool masked = __ldcg(p.tok + mr) == 0;
+                const int u4 = p.U >> 2;
                 if (it.s == 0 && p.fold)
-                    loop_cell<false, kAhead>(taddr, n0, valid, nullptr, p.b1, p.c1 + mr * p.U, masked,
+                    loop_cell<false>(taddr, n0, valid, nullptr, p.b1, blk32(p.c1, mr, u4), masked,
                                      p.X1[par] + mr * p.K1 + p.Epad, p.X1[par ^ 1] + mr * p.K1 + p.Epad,
-                                     p.X2[par] + mr * (2ll * p.U), &tmem_full[acc], acc_phase, err);
+                                     p.X2[par] + mr * (2ll * p.U), &tmem_full[acc], acc_phase, err, pend);
                 else if (it.s == 0)
-                    loop_cell<true, kAhead>(taddr, n0, valid, p.g1f + mr * (4ll * p.U), nullptr, p.c1 + mr * p.U, masked,
+                    loop_cell<true>(taddr, n0, valid, blk32(p.g1f, mr, p.U), nullptr, blk32(p.c1, mr, u4), masked,
                                     p.X1[par] + mr * p.K1 + p.Epad, p.X1[par ^ 1] + mr * p.K1 + p.Epad,
-                                    p.X2[par] + mr * (2ll * p.U), &tmem_full[acc], acc_phase, err);
+                                    p.X2[par] + mr * (2ll * p.U), &tmem_full[acc], acc_phase, err, pend);
                 else
-                    loop_cell<false, kAhead>(taddr, n0, valid, nullptr, p.b2, p.c2 + mr * p.U, masked,
+                    loop_cell<false>(taddr, n0, valid, nullptr, p.b2, blk32(p.c2, mr, u4), masked,
                                      p.X2[par] + mr * (2ll * p.U) + p.U, p.X2[par ^ 1] + mr * (2ll * p.U) + p.U,
-                                     nullptr, &tmem_full[acc], acc_phase, err);
+                                     nullptr, &tmem_full[acc], acc_phase, err, pend);
             } else if (it.s == 2) {
                 // fold: the addend is the bias row (same for every lane: broadcast loads)
-                loop_dense(taddr, n0, valid, p.fold ? p.bd1 : p.d1f + mr * kDense, p.d + mr * kDense, &tmem_full[acc], acc_phase, err);
+                if (p.fold) loop_dense<false>(taddr, n0, valid, reinterpret_cast<const float4 *>(p.bd1), p.d + mr * kDense, &tmem_full[acc], acc_phase, err, pend);
+                else loop_dense<true>(taddr, n0, valid, blk32(p.d1f, mr, kDense / 4), p.d + mr * kDense, &tmem_full[acc], acc_phase, err, pend);
             } else {
-                const float4 r4 = loop_argmax<kSum>(taddr, n0, p.V, p.bias_v, &tmem_full[acc], acc_phase, err);
+                const float4 r4 = loop_argmax<kSum>(taddr, n0, p.V, p.bias_v, &tmem_full[acc], acc_phase, err, pend);
                 if (valid) p.partial[(long long)(it.cb * 2 + half) * p.R + m] = r4;
             }
+            pend = 0;                                                  // published inside the body
             if (warp == 2 && lane == 0) LOOP_TRACE(9);
             // accumulator buffer drained: hand it back to the MMA issuer (the leader's barrier)
             tc_fence_before();
@@ -630,13 +701,24 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             if (lane == 0) mbar_arrive_cluster(mapa_u32(&tmem_empty[acc], 0));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             if (warp == 2 && lane == 0) LOOP_TRACE(6);
-            // this warp's rows of the tile are written: hand them to the publisher
+            // this warp's rows of the tile are written: hand them to the publisher -- now, or (big batches) after the wait
+            // for the next item's accumulator
             if (p.writer_proxy_fence) fence_proxy_async_all();
             __syncwarp();
-            if (lane == 0) mbar_arrive_release_cluster(mapa_u32(&done_bar[n_done & (kRing - 1)], 1));
+            pend = mapa_u32(&done_bar[n_done & (kRing - 1)], 1);
+            // deferral is safe only if this pair's NEXT list item is live: then the item that waits is one stride
+            // (num_pairs items) behind the unpublished one, closer than any dependency reaches (host: p.defer), so no
+            // chain of dependencies can lead from the unpublished item to an item some pair is blocked on
+            bool defer = p.defer && item + num_pairs < total;
+            if (defer) defer = decode_item(p, item + num_pairs).live;
+            if (!defer) {
+                if (lane == 0) mbar_arrive_release_cluster(pend);
+                pend = 0;
+            }
             ++n_done;
             if (warp == 2 && lane == 0) LOOP_TRACE(7);
         }
+        publish_pending(pend);
     }
     tc_fence_before();
     cluster_sync_all();
@@ -726,10 +808,11 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
         p.num_kb[2] += F / kBlockK; p.map_b2[2] = kMapWd1f;
     }
     p.b1 = b.b1_i; p.bd1 = W("imgcap_lstm_d1/bias");
+    static const int look_env = getenv("DCAP_LOOP_LOOKAHEAD") ? atoi(getenv("DCAP_LOOP_LOOKAHEAD")) : 1;
+    p.lookahead = look_env;
     static const int pfence_env = getenv("DCAP_LOOP_PFENCE") ? atoi(getenv("DCAP_LOOP_PFENCE")) : 2;
     p.pfence = pfence_env;
-    static const int npf_env = getenv("DCAP_LOOP_NPF") ? atoi(getenv("DCAP_LOOP_NPF")) : 0;     // measured: no gain (3.36 vs 3.26 ms)
-    p.next_prefetch = npf_env;
+
     // step t (parity t & 1): LSTM1 reads X1[par]; LSTM2 reads X2[par]; Dense(1024) reads the h2 half of X2[par ^ 1]
     p.map_a[0][0] = kMapX1a; p.map_a[0][1] = kMapX1b; p.map_b[0] = kMapW1;
     p.map_a[1][0] = kMapX2a; p.map_a[1][1] = kMapX2b; p.map_b[1] = kMapW2;
@@ -740,20 +823,15 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     p.X1[0] = b.X1[0]; p.X1[1] = b.X1[1]; p.X2[0] = b.X2[0]; p.X2[1] = b.X2[1]; p.d = b.d;
     p.partial = reinterpret_cast<float4 *>(b.partial);
     p.emb = b.emb; p.tok = ws.tok; p.tokens = tokens; p.scores = scores;
-    static const int l2pf = getenv("DCAP_LOOP_L2PF") ? atoi(getenv("DCAP_LOOP_L2PF")) : 0;       // measured: slower (3.47 vs 3.31 ms)
-    p.l2_prefetch = l2pf;
     static const int wpf = getenv("DCAP_LOOP_WPF") ? atoi(getenv("DCAP_LOOP_WPF")) : 0;
     p.writer_proxy_fence = wpf;
     // <start> embedding rows of step 0
     if (int rc2 = embed_gather(W("imgcap_embedding_layer/embeddings"), ws.tok, B, cfg.embed, V, b.X1[0], K1, true, s)) return rc2;
 
     using S = TcSmem2;
-    // addend rows of the LSTM1 cell one or two chunks ahead (two: a few registers spilled, measured)
-    static const int ahead_env = getenv("DCAP_LOOP_AHEAD") ? atoi(getenv("DCAP_LOOP_AHEAD")) : 1;
-    auto kern = ahead_env == 2 ? (scores ? greedy_loop_kernel<true, 2> : greedy_loop_kernel<false, 2>)
-                               : (scores ? greedy_loop_kernel<true, 1> : greedy_loop_kernel<false, 1>);
-    static std::atomic<unsigned long long> attr_set[4];
-    DC_CHECK_CUDA(once_per_device(attr_set[(scores ? 1 : 0) + (ahead_env == 2 ? 2 : 0)], [&] {
+    auto kern = scores ? greedy_loop_kernel<true> : greedy_loop_kernel<false>;
+    static std::atomic<unsigned long long> attr_set[2];
+    DC_CHECK_CUDA(once_per_device(attr_set[scores ? 1 : 0], [&] {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBaseBytes);
         return e != cudaSuccess ? e : cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
     }));
@@ -774,6 +852,15 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     if (pairs_env > 0 && pairs_env < pairs) pairs = pairs_env;
     const int total = p.total;
     if (pairs > total) pairs = total;
+    {
+        // deferred publication (see publish_pending) needs every dependency to reach further back than one stride of a
+        // pair through the item list: (smallest stage gap - 1) slots + 1 item > pairs
+        int gap = p.skew[1];
+        for (int i = 2; i <= 4; ++i) gap = gap < p.skew[i] - p.skew[i - 1] ? gap : p.skew[i] - p.skew[i - 1];
+        gap = gap < p.tiles_m - p.skew[4] ? gap : p.tiles_m - p.skew[4];
+        static const int defer_env = getenv("DCAP_LOOP_DEFER") ? atoi(getenv("DCAP_LOOP_DEFER")) : 1;
+        p.defer = (defer_env && (gap - 1) * first + 1 > pairs) ? 1 : 0;
+    }
     cfgl.gridDim = dim3(2 * pairs);
     const char *trace_path = getenv("DCAP_LOOP_TRACE");
     static unsigned long long *trace_buf = nullptr;
