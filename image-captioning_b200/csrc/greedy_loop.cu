@@ -77,6 +77,9 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
 __device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_relaxed_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -336,7 +339,7 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 // first index of the maximum survives every level, as np.argmax.
 template <bool kSum>
 __device__ __forceinline__ float4 loop_argmax(uint32_t taddr, int n0, int N, const float *bias, uint64_t *full_bar,
-                                              uint32_t full_phase, unsigned *err, uint32_t pend) {
+                                              uint32_t full_phase, unsigned *err, uint32_t pend, int tag) {
     mbar_wait_wd(full_bar, full_phase, err, 0x32u);
     tc_fence_after();
     publish_pending(pend);
@@ -385,7 +388,7 @@ __device__ __forceinline__ float4 loop_argmax(uint32_t taddr, int n0, int N, con
             for (int j = 0; j < 64; ++j) sum += __expf(v[j] - best);
         }
     }
-    return make_float4(best, __int_as_float(best_i), sum, 0.f);
+    return make_float4(best, __int_as_float(best_i), sum, __int_as_float(tag));
 }
 
 // Merge of the vocabulary stage's partials for 16 rows (one warp): lanes 2r / 2r+1 scan the lower / upper half of
@@ -393,7 +396,7 @@ __device__ __forceinline__ float4 loop_argmax(uint32_t taddr, int n0, int N, con
 // Then the token ids, the caption score (kSum) and the tokens' embedding rows, copied as bf16 into the next step's
 // [emb | h1] operand (Embedding lookup of the greedy feedback, text_generation_model.py:147,222-225).
 template <bool kSum>
-__device__ __forceinline__ void loop_merge(const LoopParams &p, int m_base, int t, int lane) {
+__device__ __forceinline__ void loop_merge(const LoopParams &p, int m_base, int t, int lane, unsigned *err) {
     const int r = lane >> 1, h = lane & 1;
     const int m = m_base + r;
     const bool valid = m < p.R;
@@ -403,10 +406,27 @@ __device__ __forceinline__ void loop_merge(const LoopParams &p, int m_base, int 
     float best = -INFINITY, sum = 0.f;
     int bi = 0x7fffffff;
     const float4 *pp = p.partial + mr;
+    const int tag = t + 1;
     for (int s0 = s_lo; s0 < s_hi; s0 += 8) {
         float4 q[8];
+        // Flag in data: a partial is ONE 16-byte store {max, arg-max, sum exp, step tag}, so the entry itself says whether
+        // this step's value has arrived (the buffer is zeroed before every launch) -- the vocabulary tiles, two thirds
+        // of all items, publish nothing through a fence.
+        const long long t0 = clock64();
+        for (unsigned spins = 0;; ++spins) {
+            bool ok = true;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) q[i] = __ldcg(pp + (long long)min(s0 + i, s_hi - 1) * p.R);
+            for (int i = 0; i < 8; ++i) {
+                q[i] = __ldcg(pp + (long long)min(s0 + i, s_hi - 1) * p.R);
+                ok = ok && __float_as_int(q[i].w) == tag;
+            }
+            if (ok) break;
+            __nanosleep(100);
+            if ((spins & 63u) == 63u) {
+                if (loop_aborted(err)) break;
+                if (clock64() - t0 > kWatchdogCycles) { atomicCAS(err, 0u, 0x45u); break; }
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             if (s0 + i >= s_hi) break;
@@ -649,9 +669,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                 // ---- merge item: token, caption score and next embedding row of this CTA's 128 rows; 16 rows per warp ----
                 publish_pending(pend);                                 // never block on a counter with an item unpublished
                 pend = 0;
-                if (lane == 0) wait_count(cnt_stage + 3 * n128 + rb128, (unsigned)p.tiles_n[3] * (it.t + 1), err, 0x44u);
-                __syncwarp();
-                loop_merge<kSum>(p, it.rb * 256 + (int)rank * 128 + (warp - 2) * 16, it.t, lane);
+                loop_merge<kSum>(p, it.rb * 256 + (int)rank * 128 + (warp - 2) * 16, it.t, lane, err);
                 __syncwarp();
                 if (lane == 0) mbar_arrive_release_cluster(mapa_u32(&done_bar[n_done & (kRing - 1)], 1));
                 ++n_done;
@@ -690,7 +708,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                 if (p.fold) loop_dense<false>(taddr, n0, valid, reinterpret_cast<const float4 *>(p.bd1), p.d + mr * kDense, &tmem_full[acc], acc_phase, err, pend);
                 else loop_dense<true>(taddr, n0, valid, blk32(p.d1f, mr, kDense / 4), p.d + mr * kDense, &tmem_full[acc], acc_phase, err, pend);
             } else {
-                const float4 r4 = loop_argmax<kSum>(taddr, n0, p.V, p.bias_v, &tmem_full[acc], acc_phase, err, pend);
+                const float4 r4 = loop_argmax<kSum>(taddr, n0, p.V, p.bias_v, &tmem_full[acc], acc_phase, err, pend, it.t + 1);
                 if (valid) p.partial[(long long)(it.cb * 2 + half) * p.R + m] = r4;
             }
             pend = 0;                                                  // published inside the body
@@ -709,9 +727,14 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             // deferral is safe only if this pair's NEXT list item is live: then the item that waits is one stride
             // (num_pairs items) behind the unpublished one, closer than any dependency reaches (host: p.defer), so no
             // chain of dependencies can lead from the unpublished item to an item some pair is blocked on
-            bool defer = p.defer && item + num_pairs < total;
+            bool defer = p.defer && it.s != 3 && item + num_pairs < total;
             if (defer) defer = decode_item(p, item + num_pairs).live;
-            if (!defer) {
+            if (it.s == 3) {
+                // nothing to release: the partials carry their own flags (loop_merge); the arrival only keeps the
+                // publisher's ring in step
+                if (lane == 0) mbar_arrive_relaxed_cluster(pend);
+                pend = 0;
+            } else if (!defer) {
                 if (lane == 0) mbar_arrive_release_cluster(pend);
                 pend = 0;
             }
@@ -767,10 +790,10 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     p.first[5] = first;                                    // items per slot
     // wavefront skews (slots): each must cover its producer stage's latency (tile + epilogue + publish, 11-15 us;
     // a slot of ~60 items is ~4.5 us on 74 pairs), and skew[4] < tiles_m (see decode_item)
-    static const int skew_env = getenv("DCAP_LOOP_SKEW") ? atoi(getenv("DCAP_LOOP_SKEW")) : 21;
+    static const int skew_env = getenv("DCAP_LOOP_SKEW") ? atoi(getenv("DCAP_LOOP_SKEW")) : 23;
     int sk4 = p.tiles_m - 6 < skew_env ? p.tiles_m - 6 : skew_env;
     if (sk4 < 0) sk4 = 0;
-    p.skew[0] = 0; p.skew[1] = sk4 * 5 / 21; p.skew[2] = sk4 * 12 / 21; p.skew[3] = sk4 * 16 / 21; p.skew[4] = sk4;
+    p.skew[0] = 0; p.skew[1] = sk4 * 5 / 23; p.skew[2] = sk4 * 12 / 23; p.skew[3] = sk4 * 18 / 23; p.skew[4] = sk4;
     const long long total_ll = ((long long)P * p.tiles_m + sk4) * first;
     DC_REQUIRE(total_ll < (1ll << 31), "greedy loop: too many work items");
     p.total = (int)total_ll;
@@ -779,6 +802,8 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     const size_t cnt_bytes = sizeof(unsigned) * (8 * (size_t)p.n128 + 4);
     DC_REQUIRE(b.loop_cnt && cnt_bytes <= b.loop_cnt_bytes, "greedy loop: counter buffer not reserved");
     DC_CHECK_CUDA(cudaMemsetAsync(b.loop_cnt, 0, cnt_bytes, s));
+    // the partials carry step tags (flag in data, see loop_merge): no stale tag of an earlier launch may survive
+    DC_CHECK_CUDA(cudaMemsetAsync(b.partial, 0, sizeof(float4) * (size_t)p.slots * B, s));
     p.cnt = b.loop_cnt;
     LoopMaps maps;
     int rc = 0;
