@@ -549,8 +549,11 @@ def run_ours_captions(args, ctx):
     # rooflines: decoder GEMMs (tensor, dominant share of the step) and ROIAlign (HBM)
     flops = FLOP_PER_ROI_GREEDY * R
     achieved_tf = flops / (dec_ms * 1e-3) / 1e12
+    loop_kernel = os.environ.get("DCAP_GREEDY_LOOP", "1") != "0"          # csrc/greedy_loop.cu: the 15 steps as ONE persistent kernel
     roofline = tensor_roofline(achieved_tf, total_ms * 1e-3,
-                               kernel="gemm_bf16_tc2_kernel (head + 15 decode steps: %d launches per step)" % (4 + 4 * PADDING),
+                               kernel=("greedy_loop_kernel (all %d decode steps in one persistent launch) + gemm_bf16_tc2_kernel (head, hoisted terms)" % PADDING)
+                               if loop_kernel else
+                               "gemm_bf16_tc2_kernel (head + 15 decode steps: %d launches per step)" % (4 + 4 * PADDING),
                                algorithmic_flops_per_step=flops, decoder_ms=round(dec_ms, 4),
                                share_of_step=round(dec_ms / (roi_ms + dec_ms), 3))
     t_unique = tap_unique_pixels(boxes_np, levels.cpu().numpy(), [tuple(f.shape[1:3]) for f in fms], POOL)
@@ -584,9 +587,10 @@ def run_ours_captions(args, ctx):
                          % (sum(f.numel() for f in fms) * 4 // 2 ** 20, (63 + R * (12544 * 2 + 4 * 2048 * 2) // 2 ** 20)),
                    "sm_count": sms, "cc": cc, "public_api_matches": same_as_fused},
         "clocks": clocks,
-        # per step: roi_prepare + roi_align_stream, head (2 GEMMs), bf16 cast, 2 hoisted-term GEMMs, token fill,
-        # first embedding gather, then P x (2 gate GEMMs + dense1 + vocabulary GEMM + merge) -- profiles/r1_launches_captions.txt
-        "gpu_launches": K * (2 + 7 + 5 * PADDING), "roofline": roofline,
+        # per step: ROIAlign (order + records + stream), head (2 GEMMs), bf16 cast, 2 hoisted-term GEMMs, token fill,
+        # first embedding gather, then ONE greedy_loop_kernel launch -- or, with DCAP_GREEDY_LOOP=0, P x (2 gate GEMMs +
+        # dense1 + vocabulary GEMM + merge); profiles/r2_launches_captions*.txt
+        "gpu_launches": K * (3 + 7 + (1 if loop_kernel else 5 * PADDING)), "roofline": roofline,
         "roofline_hbm": roofline_hbm,
     }
     if not args.no_e2e:
@@ -1168,7 +1172,8 @@ def run_ours_captions_vg(args, ctx):
                                % (VG_IMAGES, VG_ROIS, VG_BATCH, VG_POOL, PADDING),
                    "rois_per_step": total_rois, "images_per_rank": len(my_images), "sharding": "round-robin images, no collective",
                    "l2": "inputs larger than L2 (pyramid pool %d MB)" % (sum(f.numel() for f in pool) * 4 // 2 ** 20)},
-        "clocks": clocks, "gpu_launches": K * n_batches * (2 + 7 + 5 * PADDING),
+        "clocks": clocks,
+        "gpu_launches": K * n_batches * (3 + 7 + (1 if os.environ.get("DCAP_GREEDY_LOOP", "1") != "0" else 5 * PADDING)),
         "roofline": tensor_roofline(achieved, total_ms * 1e-3, kernel="gemm_bf16_tc2_kernel (decoder GEMMs; whole job time incl. ROIAlign)",
                                     algorithmic_flops_per_step_per_rank=flops),
         "e2e": {"value": round(total_rois / e2e_s, 1), "unit": "RoI captions/s", "h2d_bytes_per_step": int(h_boxes.numel() * 4) * world,
