@@ -108,7 +108,7 @@ struct Decoder {
     int v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_t s);
     int greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s, float *scores = nullptr);
     bool greedy_loop_folds() const;                    // ... with the head-feature terms folded into its contractions (no hoisted fp32 terms)
-    bool greedy_loop_ok() const;                       // greedy_loop.cu: the whole loop as one persistent kernel
+    bool greedy_loop_ok(int B) const;                      // greedy_loop.cu: the whole loop as one persistent kernel
     int greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_t s);
     int greedy_bf16_graphed(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s);
     void drop_graphs();

@@ -270,18 +270,19 @@ int Decoder::v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_
 int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s, float *scores) {
     const int P = cfg.padding, V = cfg.vocab;
     if (int rc = head(feats, kind, B, ws.F, s)) return rc;
-    if (greedy_loop_ok() && greedy_loop_folds()) {
+    const bool loop = greedy_loop_ok(B);
+    if (loop && greedy_loop_folds()) {
         // the loop kernel contracts over the head features itself: only their bf16 copy is needed (ws.F may have come
         // from the caller: DC_FEATS_HEAD_F32), not the hoisted fp32 terms
         if (int rc = f32_to_bf16(ws.F, bf->Fb, (long long)B * cfg.feat, s)) return rc;
-    } else if (greedy_loop_ok()) {
+    } else if (loop) {
         // hoisted per-RoI terms in the blocked-32 layout the loop kernel's epilogues read with coalesced accesses
         if (int rc = v1_hoist_bf16(B, s, true)) return rc;
     } else if (int rc = v1_hoist(B, s)) return rc;
     if (int rc = v1_reset_state(B, s)) return rc;
     if (int rc = fill_i32(ws.tok, B, 1, s)) return rc;
     // the whole loop as one persistent kernel (greedy_loop.cu); DCAP_GREEDY_LOOP=0 keeps the launch-per-GEMM form below
-    if (greedy_loop_ok()) return greedy_loop_bf16(B, tokens, scores, s);
+    if (loop) return greedy_loop_bf16(B, tokens, scores, s);
     const int slots = gemm_tc_argmax_tiles(V);
     for (int t = 0; t < P; ++t) {
         if (int rc = step_core(*this, B, ws.g1f, ws.d1f, t == 0, s)) return rc;

@@ -339,10 +339,12 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 // first index of the maximum survives every level, as np.argmax.
 template <bool kSum>
 __device__ __forceinline__ float4 loop_argmax(uint32_t taddr, int n0, int N, const float *bias, uint64_t *full_bar,
-                                              uint32_t full_phase, unsigned *err, uint32_t pend, int tag) {
+                                              uint32_t full_phase, unsigned *err, uint32_t pend, int tag,
+                                              unsigned long long *tr) {
     mbar_wait_wd(full_bar, full_phase, err, 0x32u);
     tc_fence_after();
     publish_pending(pend);
+    if (tr) tr[10] = globaltimer_ns();
     float best = -INFINITY, sum = 0.f;
     int best_i = 0x7fffffff;
 #pragma unroll 1
@@ -351,6 +353,7 @@ __device__ __forceinline__ float4 loop_argmax(uint32_t taddr, int n0, int N, con
         if (nb >= N) break;                                          // warp-uniform
         float v[64];
         tmem_ld64(taddr + c0, v);
+        if (tr && c0 == 0) tr[11] = globaltimer_ns();
         if (nb + 64 <= N) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -708,7 +711,9 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                 if (p.fold) loop_dense<false>(taddr, n0, valid, reinterpret_cast<const float4 *>(p.bd1), p.d + mr * kDense, &tmem_full[acc], acc_phase, err, pend);
                 else loop_dense<true>(taddr, n0, valid, blk32(p.d1f, mr, kDense / 4), p.d + mr * kDense, &tmem_full[acc], acc_phase, err, pend);
             } else {
-                const float4 r4 = loop_argmax<kSum>(taddr, n0, p.V, p.bias_v, &tmem_full[acc], acc_phase, err, pend, it.t + 1);
+                const float4 r4 = loop_argmax<kSum>(taddr, n0, p.V, p.bias_v, &tmem_full[acc], acc_phase, err, pend, it.t + 1,
+                                                    (p.trace && rank == 0 && warp == 2 && lane == 0 && (item - pair) / num_pairs < p.trace_items)
+                                                        ? p.trace + ((long long)pair * p.trace_items + (item - pair) / num_pairs) * 12 : nullptr);
                 if (valid) p.partial[(long long)(it.cb * 2 + half) * p.R + m] = r4;
             }
             pend = 0;                                                  // published inside the body
@@ -764,10 +769,17 @@ bool Decoder::greedy_loop_folds() const {
     return e && atoi(e) != 0 && cfg.feat % kBlockK == 0;
 }
 
-bool Decoder::greedy_loop_ok() const {
+// Batches of 3-5 row blocks (513 .. 1280 RoIs) keep the launch-per-GEMM form: too few row blocks for the wavefront
+// (all of them sit in the same stage at the same time and the 40 vocabulary tiles of each queue up behind one another),
+// too many rows for the saved launches to pay -- measured 1.26 vs 1.10 ms at 1000 RoIs, against 0.69 vs 0.77 (37),
+// 0.80 vs 0.95 (300), 1.38 vs 1.71 (2500), 3.06 vs 3.60-3.86 ms (8000).  DCAP_GREEDY_LOOP=2 forces the loop kernel.
+bool Decoder::greedy_loop_ok(int B) const {
     if (!loop_env_on() || !bf || cfg.arch != DC_ARCH_V1) return false;
     const int U = cfg.units;
-    return U % 64 == 0 && (4 * U) % 256 == 0 && bf->Epad % 64 == 0 && cfg.vocab >= 256 && cfg.padding >= 1;
+    if (!(U % 64 == 0 && (4 * U) % 256 == 0 && bf->Epad % 64 == 0 && cfg.vocab >= 256 && cfg.padding >= 1)) return false;
+    const char *e = getenv("DCAP_GREEDY_LOOP");
+    const int tiles_m = (B + 255) / 256;
+    return (e && atoi(e) == 2) || tiles_m <= 2 || tiles_m >= 6;
 }
 
 // Steps 0..P-1 of the greedy loop after head / hoisted terms / state reset; ws.tok holds <start>.

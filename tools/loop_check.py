@@ -45,7 +45,7 @@ def main():
     for B in [int(x) for x in a.sizes.split(",")]:
         feats = torch.randn((B, 1024), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)).relu()
         out = {}
-        for mode in ("0", "1"):
+        for mode in ("0", "2"):
             os.environ["DCAP_GREEDY_LOOP"] = mode
             m = model(w, P, V, U, C)
             t0 = time.time()
@@ -57,7 +57,7 @@ def main():
             out[mode] = (tok.cpu().numpy(), tok2.cpu().numpy(), tok3.cpu().numpy(), ts.cpu().numpy(), sc.cpu().numpy())
             ms = timed(lambda: m.generate(feats)) if a.time else float("nan")
             print("B=%d loop=%s first-call wall %.2fs, ms per call %.3f" % (B, mode, time.time() - t0, ms), flush=True)
-        o, n = out["0"], out["1"]
+        o, n = out["0"], out["2"]
         agree = float((o[0] == n[0]).mean())
         rep = all(np.array_equal(n[0], n[i]) for i in (1, 2, 3))
         ds = float(np.abs(o[4] - n[4])[(o[3] == n[3]).all(1)].max()) if (o[3] == n[3]).all(1).any() else float("nan")

@@ -29,7 +29,9 @@ def main():
     sel_step = int(sys.argv[2]) if len(sys.argv) > 2 else None
     names = ["dep wait (1-0)", "proxy fence (2-1)", "acc buffer->first operands (4-3)", "mma issue (5-4)",
              "mma end->tmem released (6-5)", "publish (+merge) (7-6)", "item period (5 - prev 5)",
-             "epilogue: start->body done (9-8)", "epilogue: own period (8 - prev 8)", "epilogue: start lag behind mma end (8-5)"]
+             "epilogue: start->body done (9-8)", "epilogue: own period (8 - prev 8)", "epilogue: start lag behind mma end (8-5)",
+             "vocab epilogue: accumulator ready -> first TMEM load back (11-10)", "vocab epilogue: accumulator ready -> body done (9-10)",
+             "vocab epilogue: mma end -> accumulator seen (10-5)"]
     for s in range(5):
         m = valid & (stage == s)
         if sel_step is not None:
@@ -44,6 +46,9 @@ def main():
         ep[:, 1:] = d[:, 1:, 8] - d[:, :-1, 8]
         rows.append(ep)
         rows.append(d[..., 8] - d[..., 5])
+        rows.append(d[..., 11] - d[..., 10])
+        rows.append(d[..., 9] - d[..., 10])
+        rows.append(d[..., 10] - d[..., 5])
         print("stage %d: %d items" % (s, int(m.sum())))
         for name, r in zip(names, rows):
             v = r[m]
