@@ -769,17 +769,13 @@ bool Decoder::greedy_loop_folds() const {
     return e && atoi(e) != 0 && cfg.feat % kBlockK == 0;
 }
 
-// Batches of 3-5 row blocks (513 .. 1280 RoIs) keep the launch-per-GEMM form: too few row blocks for the wavefront
-// (all of them sit in the same stage at the same time and the 40 vocabulary tiles of each queue up behind one another),
-// too many rows for the saved launches to pay -- measured 1.26 vs 1.10 ms at 1000 RoIs, against 0.69 vs 0.77 (37),
-// 0.80 vs 0.95 (300), 1.38 vs 1.71 (2500), 3.06 vs 3.60-3.86 ms (8000).  DCAP_GREEDY_LOOP=2 forces the loop kernel.
+// Used at every batch size: measured (ms per call, loop vs launch per GEMM) 0.71 vs 0.75 (1 RoI), 0.69 vs 0.76 (37),
+// 0.79 vs 0.94 (300), 0.95 vs 1.09 (1000), 0.89 vs 1.26 (1300), 1.11 vs 1.70 (2500), 1.56 vs 2.10 (4000), 2.93 vs 3.73 (8000).
 bool Decoder::greedy_loop_ok(int B) const {
+    (void)B;
     if (!loop_env_on() || !bf || cfg.arch != DC_ARCH_V1) return false;
     const int U = cfg.units;
-    if (!(U % 64 == 0 && (4 * U) % 256 == 0 && bf->Epad % 64 == 0 && cfg.vocab >= 256 && cfg.padding >= 1)) return false;
-    const char *e = getenv("DCAP_GREEDY_LOOP");
-    const int tiles_m = (B + 255) / 256;
-    return (e && atoi(e) == 2) || tiles_m <= 2 || tiles_m >= 6;
+    return U % 64 == 0 && (4 * U) % 256 == 0 && bf->Epad % 64 == 0 && cfg.vocab >= 256 && cfg.padding >= 1;
 }
 
 // Steps 0..P-1 of the greedy loop after head / hoisted terms / state reset; ws.tok holds <start>.
@@ -802,10 +798,17 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     p.first[5] = first;                                    // items per slot
     // wavefront skews (slots): each must cover its producer stage's latency (tile + epilogue + publish, 11-15 us;
     // a slot of ~60 items is ~4.5 us on 74 pairs), and skew[4] < tiles_m (see decode_item)
+    // Stage gaps: 5 / 7 / 6 / 5 slots when there are enough row blocks (>= 29), else the row blocks of a step are spread
+    // evenly over the five stages (gap = tiles_m / 5), so that even a few row blocks sit in DIFFERENT stages at any time
+    // instead of queueing up behind one another in the same one.  DCAP_LOOP_SKEW=n caps the last skew.
     static const int skew_env = getenv("DCAP_LOOP_SKEW") ? atoi(getenv("DCAP_LOOP_SKEW")) : 23;
-    int sk4 = p.tiles_m - 6 < skew_env ? p.tiles_m - 6 : skew_env;
-    if (sk4 < 0) sk4 = 0;
-    p.skew[0] = 0; p.skew[1] = sk4 * 5 / 23; p.skew[2] = sk4 * 12 / 23; p.skew[3] = sk4 * 18 / 23; p.skew[4] = sk4;
+    static const int full[5] = {0, 5, 12, 18, 23};
+    for (int i = 0; i < 5; ++i) {
+        int sk = i * p.tiles_m / 5;
+        const int cap = skew_env >= 23 ? full[i] + (i == 4 ? skew_env - 23 : 0) : full[i] * skew_env / 23;
+        p.skew[i] = sk < cap ? sk : cap;
+    }
+    const int sk4 = p.skew[4];
     const long long total_ll = ((long long)P * p.tiles_m + sk4) * first;
     DC_REQUIRE(total_ll < (1ll << 31), "greedy loop: too many work items");
     p.total = (int)total_ll;
