@@ -201,7 +201,10 @@ roi_align_stream_kernel(const RoiStreamParams p) {
 //   * re-using tap registers between neighbouring bins inside the gather kernel (the branch-free loads become
 //     conditional): 0.287 ms;
 //   * prefetch.global.L2 of the taps of the CTA's next RoI from inside the gather kernel: 0.221-0.228 ms (more requests,
-//     not fewer stalls: the memory system's request throughput on 1 KB granules is the bound, not latency).
+//     not fewer stalls: the memory system's request throughput on 1 KB granules is the bound, not latency);
+//   * the 4 (or 2, or 8) CTAs resident on one SM working on ADJACENT positions of the locality order at the same time, so
+//     that overlapping boxes meet in that SM's L1: 0.177 / 0.170 ms (4 / 2 adjacent, 4 CTAs per SM) and 0.193 ms (8 per
+//     SM) against 0.169 ms -- neighbours in the order then no longer spread over many SMs' request queues.
 // What bounds the gather kernel is the L2 -> SM path: ~1.6 GB of taps per launch in ~0.14 ms = 11-12 TB/s, with DRAM at
 // the compulsory bytes (profiles/): close to what the part's L2 delivers to tcgen05 operand loads as well (section 9).
 // ---------------------------------------------------------------------------------------------
