@@ -769,13 +769,43 @@ bool Decoder::greedy_loop_folds() const {
     return e && atoi(e) != 0 && cfg.feat % kBlockK == 0;
 }
 
+// Can the kernel run here at all?  One probe per device: shared memory opt-in + at least one resident cluster of 2.
+static bool loop_launchable() {
+    static std::atomic<unsigned long long> probed{0}, usable{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(probed.load(std::memory_order_acquire) & bit)) {
+        bool ok = true;
+        for (int v = 0; v < 2 && ok; ++v) {
+            auto kern = v ? greedy_loop_kernel<true> : greedy_loop_kernel<false>;
+            ok = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem2::kBaseBytes) == cudaSuccess &&
+                 cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0) == cudaSuccess;
+            if (!ok) break;
+            cudaLaunchConfig_t c = {};
+            c.blockDim = dim3(kLoopThreads); c.gridDim = dim3(2 * (sm_count() / 2 > 0 ? sm_count() / 2 : 1));
+            c.dynamicSmemBytes = TcSmem2::kBaseBytes;
+            cudaLaunchAttribute a[1];
+            a[0].id = cudaLaunchAttributeClusterDimension;
+            a[0].val.clusterDim.x = 2; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+            c.attrs = a; c.numAttrs = 1;
+            int fit = 0;
+            ok = cudaOccupancyMaxActiveClusters(&fit, kern, &c) == cudaSuccess && fit >= 1;
+        }
+        if (!ok) cudaGetLastError();
+        if (ok) usable.fetch_or(bit, std::memory_order_release);
+        probed.fetch_or(bit, std::memory_order_release);
+    }
+    return (usable.load(std::memory_order_acquire) & bit) != 0;
+}
+
 // Used at every batch size: measured (ms per call, loop vs launch per GEMM) 0.71 vs 0.75 (1 RoI), 0.69 vs 0.76 (37),
 // 0.79 vs 0.94 (300), 0.95 vs 1.09 (1000), 0.89 vs 1.26 (1300), 1.11 vs 1.70 (2500), 1.56 vs 2.10 (4000), 2.93 vs 3.73 (8000).
 bool Decoder::greedy_loop_ok(int B) const {
     (void)B;
     if (!loop_env_on() || !bf || cfg.arch != DC_ARCH_V1) return false;
     const int U = cfg.units;
-    return U % 64 == 0 && (4 * U) % 256 == 0 && bf->Epad % 64 == 0 && cfg.vocab >= 256 && cfg.padding >= 1;
+    return U % 64 == 0 && (4 * U) % 256 == 0 && bf->Epad % 64 == 0 && cfg.vocab >= 256 && cfg.padding >= 1 && loop_launchable();
 }
 
 // Steps 0..P-1 of the greedy loop after head / hoisted terms / state reset; ws.tok holds <start>.
