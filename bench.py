@@ -519,6 +519,21 @@ def run_ours_captions(args, ctx):
     tokens_fused = model.caption_rois(boxes, fms, IMAGE_SHAPE)          # the single-call public API
     torch.cuda.synchronize()
     same_as_fused = bool(torch.equal(tokens, tokens_fused))
+    # the persistent greedy-loop kernel against the launch-per-GEMM form of the same decoder (a fresh feature buffer: the
+    # handle's CUDA graphs are keyed by the input pointer, so this call runs eagerly with the other path)
+    loop_vs_launches = None
+    if os.environ.get("DCAP_GREEDY_LOOP", "1") != "0":
+        prev = os.environ.get("DCAP_GREEDY_LOOP")
+        os.environ["DCAP_GREEDY_LOOP"] = "0"
+        try:
+            tokens_launches = model.generate(feats.clone())
+            torch.cuda.synchronize()
+            loop_vs_launches = float((tokens_launches == tokens).float().mean().item())
+        finally:
+            if prev is None:
+                os.environ.pop("DCAP_GREEDY_LOOP", None)
+            else:
+                os.environ["DCAP_GREEDY_LOOP"] = prev
     for _ in range(max(args.warmup, 3)):
         pkg.pyramid_roi_align(boxes, fms, POOL, IMAGE_SHAPE, out_dtype=torch.bfloat16, out=feats)
         model.generate(feats)
@@ -585,12 +600,13 @@ def run_ours_captions(args, ctx):
                    "precision": "ROIAlign fp32 arithmetic with bf16 output; decoder bf16 operands, fp32 accumulate/state",
                    "l2": "inputs larger than L2 (pyramid %d MB per GPU; decoder weights + activations %d MB)"
                          % (sum(f.numel() for f in fms) * 4 // 2 ** 20, (63 + R * (12544 * 2 + 4 * 2048 * 2) // 2 ** 20)),
-                   "sm_count": sms, "cc": cc, "public_api_matches": same_as_fused},
+                   "sm_count": sms, "cc": cc, "public_api_matches": same_as_fused,
+                   "token_agreement_with_launch_per_gemm_path": loop_vs_launches},
         "clocks": clocks,
-        # per step: ROIAlign (order + records + stream), head (2 GEMMs), bf16 cast, 2 hoisted-term GEMMs, token fill,
-        # first embedding gather, then ONE greedy_loop_kernel launch -- or, with DCAP_GREEDY_LOOP=0, P x (2 gate GEMMs +
-        # dense1 + vocabulary GEMM + merge); profiles/r2_launches_captions*.txt
-        "gpu_launches": K * (3 + 7 + (1 if loop_kernel else 5 * PADDING)), "roofline": roofline,
+        # per step: ROIAlign (order + records + stream), head (2 GEMMs), ONE merged hoisted-term GEMM, token fill, first
+        # embedding gather, ONE greedy_loop_kernel launch = 9 -- or, with DCAP_GREEDY_LOOP=0: head 2, bf16 cast, 2 hoisted-term
+        # GEMMs, fill, gather, then P x (2 gate GEMMs + dense1 + vocabulary GEMM + merge); profiles/r2_launches_captions*.txt
+        "gpu_launches": K * ((3 + 2 + 1 + 1 + 1 + 1) if loop_kernel else (3 + 7 + 5 * PADDING)), "roofline": roofline,
         "roofline_hbm": roofline_hbm,
     }
     if not args.no_e2e:
@@ -1173,7 +1189,7 @@ def run_ours_captions_vg(args, ctx):
                    "rois_per_step": total_rois, "images_per_rank": len(my_images), "sharding": "round-robin images, no collective",
                    "l2": "inputs larger than L2 (pyramid pool %d MB)" % (sum(f.numel() for f in pool) * 4 // 2 ** 20)},
         "clocks": clocks,
-        "gpu_launches": K * n_batches * (3 + 7 + (1 if os.environ.get("DCAP_GREEDY_LOOP", "1") != "0" else 5 * PADDING)),
+        "gpu_launches": K * n_batches * (9 if os.environ.get("DCAP_GREEDY_LOOP", "1") != "0" else 3 + 7 + 5 * PADDING),
         "roofline": tensor_roofline(achieved, total_ms * 1e-3, kernel="gemm_bf16_tc2_kernel (decoder GEMMs; whole job time incl. ROIAlign)",
                                     algorithmic_flops_per_step_per_rank=flops),
         "e2e": {"value": round(total_rois / e2e_s, 1), "unit": "RoI captions/s", "h2d_bytes_per_step": int(h_boxes.numel() * 4) * world,

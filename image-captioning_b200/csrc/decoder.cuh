@@ -104,6 +104,8 @@ struct Decoder {
     int reserve_bf16(size_t R);
     int head_bf16(const void *feats, int kind, int B, float *out, cudaStream_t s);
     int v1_hoist_bf16(int B, cudaStream_t s, bool blocked32 = false);   // blocked32: the layout greedy_loop.cu reads
+    int v1_hoist_merged_bf16(int B, bool fresh_fb, cudaStream_t s);
+    static bool hoist_merged();
     int reset_state_bf16(int R, cudaStream_t s);
     int v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_t s);
     int greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s, float *scores = nullptr);

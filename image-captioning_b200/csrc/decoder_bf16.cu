@@ -111,12 +111,15 @@ int Decoder::refresh_bf16(bool fresh, cudaStream_t s) {
     const int K1 = b.Epad + U;
     if (fresh) {
         rc |= A16(&b.w_head1, (size_t)F * Kin); rc |= A16(&b.w_head2, (size_t)F * F);
-        rc |= A16(&b.w1cat, (size_t)4 * U * K1); rc |= A16(&b.w1f, (size_t)4 * U * F);
+        rc |= A16(&b.w1cat, (size_t)4 * U * K1);
+        rc |= A16(&b.w1f, ((size_t)4 * U + kDense) * F);      // [W1f ; Wd1f] adjacent: one merged hoist GEMM (v1_hoist_merged_bf16)
+        b.wd1f = rc ? nullptr : b.w1f + (size_t)4 * U * F;
         rc |= A16(&b.w2cat, (size_t)4 * U * 2 * U);
-        rc |= A16(&b.wd1h, (size_t)kDense * U); rc |= A16(&b.wd1f, (size_t)kDense * F);
+        rc |= A16(&b.wd1h, (size_t)kDense * U);
         rc |= A16(&b.wd2, (size_t)V * kDense);
         rc |= A16(&b.emb, (size_t)V * b.Epad);
-        rc |= dev_alloc((void **)&b.b1_i, sizeof(float) * 4 * U, owned);
+        rc |= dev_alloc((void **)&b.bias_hoist, sizeof(float) * (4 * U + kDense), owned);
+        b.b1_i = b.bias_hoist;                                  // [b1 (gate-interleaved) | bd1]
         rc |= dev_alloc((void **)&b.b2_i, sizeof(float) * 4 * U, owned);
         if (rc) return rc;
         DC_CHECK_CUDA(cudaMemsetAsync(b.w1cat, 0, 2 * (size_t)4 * U * K1, s));      // zero the E..Epad padding
@@ -141,6 +144,7 @@ int Decoder::refresh_bf16(bool fresh, cudaStream_t s) {
     rc |= build_kmajor(W("imgcap_lstm_d2/kernel"), V, 0, kDense, V, 0, b.wd2, kDense, 0, s);
     if (rc) return rc;
     interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm1/bias"), U, b.b1_i);
+    DC_CHECK_CUDA(cudaMemcpyAsync(b.bias_hoist + 4 * U, W("imgcap_lstm_d1/bias"), sizeof(float) * kDense, cudaMemcpyDeviceToDevice, s));
     interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm2/bias"), U, b.b2_i);
     DC_CHECK_LAUNCH();
     return DC_OK;
@@ -168,6 +172,7 @@ int Decoder::reserve_bf16(size_t R) {
     rc |= A16(&b.roi, R * Kin); rc |= A16(&b.a1, R * F); rc |= A16(&b.Fb, R * F); rc |= A16(&b.d, R * kDense);
     for (int i = 0; i < 2; ++i) { rc |= A16(&b.X1[i], R * K1); rc |= A16(&b.X2[i], R * 2 * U); }
     rc |= dev_alloc((void **)&b.partial, sizeof(float) * 4 * R * gemm_tc_argmax_tiles(cfg.vocab), ws_owned);
+    rc |= dev_alloc((void **)&b.hoist_all, sizeof(float) * R * (4 * U + kDense), ws_owned);
     b.loop_cnt_bytes = sizeof(unsigned) * (16 * ((R + 255) / 256) + 4);     // greedy_loop.cu: 8 counters per 128 rows + error word
     rc |= dev_alloc((void **)&b.loop_cnt, b.loop_cnt_bytes, ws_owned);
     return rc;
@@ -197,7 +202,7 @@ int Decoder::head_bf16(const void *feats, int kind, int B, float *out, cudaStrea
     TcEpilogue e2;
     e2.bias = W("mrcnn_class_conv2/bias"); e2.scale = bn_scale[1]; e2.shift = bn_shift[1]; e2.relu = 1;
     e2.out_bf16 = b.Fb; e2.ld_bf16 = F;
-    e2.out_f32 = out; e2.ld_f32 = F;
+    e2.out_f32 = out; e2.ld_f32 = F;                               // out == nullptr: only the bf16 copy (one bulk tensor store)
     return gemm_bf16_tc(op(b.a1, F), op(b.w_head2, F), e2, B, F, F, kEpiStore, s);
 }
 
@@ -214,6 +219,18 @@ int Decoder::v1_hoist_bf16(int B, cudaStream_t s, bool blocked32) {
     e2.bias = W("imgcap_lstm_d1/bias"); e2.out_f32 = ws.d1f; e2.ld_f32 = kDense;
     e2.blocked32 = blocked32 ? 1 : 0;
     return gemm_bf16_tc(op(b.Fb, F), op(b.wd1f, F), e2, B, kDense, F, kEpiStore, s);
+}
+
+// [f W1f + b1 | f Wd1f + bd1] in ONE GEMM (N = 4U + 1024; the two weight blocks are adjacent), written in the blocked-32
+// layout of greedy_loop.cu.  fresh_fb: bf->Fb already holds bf16(ws.F) (head_bf16 ran in this call).
+int Decoder::v1_hoist_merged_bf16(int B, bool fresh_fb, cudaStream_t s) {
+    Bf16State &b = *bf;
+    const int F = cfg.feat, U = cfg.units, N = 4 * U + kDense;
+    if (!fresh_fb)
+        if (int rc = f32_to_bf16(ws.F, b.Fb, (long long)B * F, s)) return rc;
+    TcEpilogue e;
+    e.bias = b.bias_hoist; e.out_f32 = b.hoist_all; e.ld_f32 = N; e.blocked32 = 1;
+    return gemm_bf16_tc(op(b.Fb, F), op(b.w1f, F), e, B, N, F, kEpiStore, s);
 }
 
 int Decoder::reset_state_bf16(int R, cudaStream_t s) {
@@ -269,15 +286,19 @@ int Decoder::v1_step_bf16(int R, const float *g1f, const float *d1f, cudaStream_
 // main loop / epilogue, not between launches.  Removed.)
 int Decoder::greedy_bf16(const void *feats, int kind, int B, int32_t *tokens, cudaStream_t s, float *scores) {
     const int P = cfg.padding, V = cfg.vocab;
-    if (int rc = head(feats, kind, B, ws.F, s)) return rc;
     const bool loop = greedy_loop_ok(B);
+    // the loop kernel's hoist GEMM reads the bf16 head output only: the fp32 copy is not produced at all then
+    const bool head_bf16_only = loop && !greedy_loop_folds() && hoist_merged() && kind != DC_FEATS_HEAD_F32;
+    if (head_bf16_only) { if (int rc = head_bf16(feats, kind, B, nullptr, s)) return rc; }
+    else if (int rc = head(feats, kind, B, ws.F, s)) return rc;
     if (loop && greedy_loop_folds()) {
         // the loop kernel contracts over the head features itself: only their bf16 copy is needed (ws.F may have come
         // from the caller: DC_FEATS_HEAD_F32), not the hoisted fp32 terms
         if (int rc = f32_to_bf16(ws.F, bf->Fb, (long long)B * cfg.feat, s)) return rc;
     } else if (loop) {
-        // hoisted per-RoI terms in the blocked-32 layout the loop kernel's epilogues read with coalesced accesses
-        if (int rc = v1_hoist_bf16(B, s, true)) return rc;
+        // hoisted per-RoI terms, one GEMM, in the blocked-32 layout the loop kernel's epilogues read with coalesced accesses
+        if (hoist_merged()) { if (int rc = v1_hoist_merged_bf16(B, head_bf16_only, s)) return rc; }
+        else if (int rc = v1_hoist_bf16(B, s, true)) return rc;
     } else if (int rc = v1_hoist(B, s)) return rc;
     if (int rc = v1_reset_state(B, s)) return rc;
     if (int rc = fill_i32(ws.tok, B, 1, s)) return rc;

@@ -12,6 +12,8 @@ struct Bf16State {
     __nv_bfloat16 *w_head1 = nullptr, *w_head2 = nullptr;
     __nv_bfloat16 *w1cat = nullptr, *w1f = nullptr, *w2cat = nullptr, *wd1h = nullptr, *wd1f = nullptr, *wd2 = nullptr;
     float *b1_i = nullptr, *b2_i = nullptr;          // gate-interleaved LSTM biases
+    float *bias_hoist = nullptr;                     // [4U + 1024] = [b1 (gate-interleaved) | bd1]: bias of the merged hoist GEMM (w1f and wd1f are adjacent)
+    float *hoist_all = nullptr;                      // [R, 4U + 1024] fp32, blocked-32: [f W1f + b1 | f Wd1f + bd1] for greedy_loop.cu
     __nv_bfloat16 *emb = nullptr;                    // [V, Epad] bf16 embedding table (zero padded)
     int Epad = 0;
     // activations

@@ -1069,7 +1069,8 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
         const bool accum = ep.atomic || g.splits > 1;
         DC_REQUIRE(!ep.blocked32 || (ep.out_f32 && !ep.out_bf16 && !accum && N % 32 == 0 && ep.ld_f32 == N && ep.deint_units == 0),
                    "blocked-32 output needs a plain fp32 output with N %% 32 == 0, ld == N");
-        bool want = ep.deint_units == 0 && !ep.blocked32 && (!row_ops || (tma_mask & 4)) && (!accum || (tma_mask & 8));
+        // (with BOTH outputs requested the bulk-store variants would write only the fp32 one: they keep the per-thread stores)
+        bool want = ep.deint_units == 0 && !ep.blocked32 && !(ep.out_f32 && ep.out_bf16) && (!row_ops || (tma_mask & 4)) && (!accum || (tma_mask & 8));
         if (want && ep.out_f32 && (accum || (tma_mask & 1))) {
             if (int rc = make_tmap(&mo, ep.out_f32, M, N, ep.ld_f32, 32, 32, 4)) return rc;
             g.tma_out = 1;

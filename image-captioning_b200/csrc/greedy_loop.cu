@@ -50,7 +50,8 @@ struct LoopParams {
     int kb_main[4], map_b2[4];         // folded feature term: k-blocks >= kb_main[s] come from (Fb, map_b2[s]) -- [x | f] . [W ; Wf]^T in one accumulator
     const float *b1, *bd1;             // fold: biases of LSTM1 (gate-interleaved) and Dense(1024) (without fold they sit inside g1f / d1f)
     int fold, pfence, lookahead, defer;  // knobs (see greedy_loop_bf16)
-    const float *g1f, *d1f, *b2, *bias_v;
+    const float *g1f, *d1f, *b2, *bias_v;   // g1f / d1f: column blocks of ONE blocked-32 array of row length hoist_ld4 float4
+    int g1f_ld4, d1f_ld4;
     float *c1, *c2;
     __nv_bfloat16 *X1[2], *X2[2], *d;
     float4 *partial;                   // [slots][R] {max, arg-max bits, sum exp, -}
@@ -699,7 +700,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
                                      p.X1[par] + mr * p.K1 + p.Epad, p.X1[par ^ 1] + mr * p.K1 + p.Epad,
                                      p.X2[par] + mr * (2ll * p.U), &tmem_full[acc], acc_phase, err, pend);
                 else if (it.s == 0)
-                    loop_cell<true>(taddr, n0, valid, blk32(p.g1f, mr, p.U), nullptr, blk32(p.c1, mr, u4), masked,
+                    loop_cell<true>(taddr, n0, valid, blk32(p.g1f, mr, p.g1f_ld4), nullptr, blk32(p.c1, mr, u4), masked,
                                     p.X1[par] + mr * p.K1 + p.Epad, p.X1[par ^ 1] + mr * p.K1 + p.Epad,
                                     p.X2[par] + mr * (2ll * p.U), &tmem_full[acc], acc_phase, err, pend);
                 else
@@ -709,7 +710,7 @@ greedy_loop_kernel(const __grid_constant__ LoopMaps maps, const LoopParams p) {
             } else if (it.s == 2) {
                 // fold: the addend is the bias row (same for every lane: broadcast loads)
                 if (p.fold) loop_dense<false>(taddr, n0, valid, reinterpret_cast<const float4 *>(p.bd1), p.d + mr * kDense, &tmem_full[acc], acc_phase, err, pend);
-                else loop_dense<true>(taddr, n0, valid, blk32(p.d1f, mr, kDense / 4), p.d + mr * kDense, &tmem_full[acc], acc_phase, err, pend);
+                else loop_dense<true>(taddr, n0, valid, blk32(p.d1f, mr, p.d1f_ld4), p.d + mr * kDense, &tmem_full[acc], acc_phase, err, pend);
             } else {
                 const float4 r4 = loop_argmax<kSum>(taddr, n0, p.V, p.bias_v, &tmem_full[acc], acc_phase, err, pend, it.t + 1,
                                                     (p.trace && rank == 0 && warp == 2 && lane == 0 && (item - pair) / num_pairs < p.trace_items)
@@ -767,6 +768,12 @@ static bool loop_env_on() {
 bool Decoder::greedy_loop_folds() const {
     const char *e = getenv("DCAP_LOOP_FOLD");
     return e && atoi(e) != 0 && cfg.feat % kBlockK == 0;
+}
+
+// DCAP_HOIST_MERGED=0: the two hoisted terms from two GEMMs into two blocked-32 arrays (debugging aid)
+bool Decoder::hoist_merged() {
+    const char *e = getenv("DCAP_HOIST_MERGED");
+    return !(e && atoi(e) == 0);
 }
 
 // Can the kernel run here at all?  One probe per device: shared memory opt-in + at least one resident cluster of 2.
@@ -888,7 +895,15 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     p.map_a[1][0] = kMapX2a; p.map_a[1][1] = kMapX2b; p.map_b[1] = kMapW2;
     p.map_a[2][0] = kMapH2b; p.map_a[2][1] = kMapH2a; p.map_b[2] = kMapWd1;
     p.map_a[3][0] = kMapD;   p.map_a[3][1] = kMapD;   p.map_b[3] = kMapWd2;
-    p.g1f = ws.g1f; p.d1f = ws.d1f; p.b2 = b.b2_i; p.bias_v = W("imgcap_lstm_d2/bias");
+    // [g1f | d1f] = the merged hoist GEMM's output (v1_hoist_merged_bf16): d1f starts at column 4U = float4 column U
+    if (hoist_merged()) {
+        p.g1f_ld4 = p.d1f_ld4 = (4 * U + kDense) / 4;
+        p.g1f = b.hoist_all; p.d1f = b.hoist_all + (size_t)U * 32 * 4;
+    } else {
+        p.g1f_ld4 = U; p.d1f_ld4 = kDense / 4;
+        p.g1f = ws.g1f; p.d1f = ws.d1f;
+    }
+    p.b2 = b.b2_i; p.bias_v = W("imgcap_lstm_d2/bias");
     p.c1 = ws.c1; p.c2 = ws.c2;
     p.X1[0] = b.X1[0]; p.X1[1] = b.X1[1]; p.X2[0] = b.X2[0]; p.X2[1] = b.X2[1]; p.d = b.d;
     p.partial = reinterpret_cast<float4 *>(b.partial);

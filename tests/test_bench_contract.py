@@ -42,6 +42,8 @@ def test_default_arm_line():
     assert 0.2 < r["frac"] < 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
     assert d["e2e"]["h2d_bytes_per_step"] > 7e8 and d["e2e"]["d2h_bytes_per_step"] == 8000 * 15 * 4
     assert d["e2e"]["token_agreement_with_device_run"] == 1.0
-    # per step: ROIAlign 3 + head 2 + cast 1 + hoisted terms 2 + token fill 1 + embedding gather 1 + the persistent greedy loop 1
-    assert d["gpu_launches"] == 3 * 11 and d["config"]["public_api_matches"] is True
+    # per step: ROIAlign 3 + head 2 + merged hoisted-term GEMM 1 + token fill 1 + embedding gather 1 + the persistent greedy loop 1
+    # (profiles/r2_launches_captions_loop.txt)
+    assert d["gpu_launches"] == 3 * 9 and d["config"]["public_api_matches"] is True
+    assert d["config"]["token_agreement_with_launch_per_gemm_path"] == 1.0
     assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1

@@ -69,3 +69,22 @@ def test_loop_kernel_full_size_and_back_to_back_calls():
     d = m.generate(feats[:333].contiguous()).cpu().numpy()
     assert np.array_equal(a, want[0]) and np.array_equal(c, a)
     assert np.array_equal(b, a[:333]) and np.array_equal(d, b)
+
+
+@pytest.mark.parametrize("B", [16, 700])
+def test_loop_kernel_from_roi_features(B):
+    """RoI features in (the head runs inside the call, its bf16 output feeds the merged hoist GEMM directly): same ids
+    as the launch-per-GEMM path, and close to the fp32 oracle."""
+    from oracle import decoder as dec
+    rng = np.random.default_rng(77)
+    w = synth.synth_weights_v1(rng, V=V, E=E, U=U, C=C)
+    roi = torch.from_numpy(rng.standard_normal((B, 7, 7, C)).astype(np.float32)).cuda()
+    want_calls, want_tok, want_sc = _run(w, roi, loop=False)
+    got_calls, got_tok, got_sc = _run(w, roi, loop=True)
+    for c in got_calls:
+        assert np.array_equal(c, want_calls[0])
+    assert np.array_equal(got_tok, want_tok)
+    np.testing.assert_allclose(got_sc, want_sc, rtol=0, atol=2e-5)
+    if B <= 64:
+        tok32, _ = dec.greedy_v1(dec.head(roi.cpu().numpy(), w), w, P)
+        assert (got_calls[0] == tok32).mean() >= 0.9
