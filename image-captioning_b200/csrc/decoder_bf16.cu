@@ -246,7 +246,9 @@ int Decoder::reset_state_bf16(int R, cudaStream_t s) {
 
 // the three GEMMs up to the Dense(1024) activations; leaves d (bf16) ready for the vocab GEMM
 // addend_div > 0: rows are (RoI, beam) pairs and the per-RoI terms g1f / d1f are indexed by row / addend_div
-static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, bool gather, cudaStream_t s, int addend_div = 0) {
+// blocked_ld > 0: g1f / d1f are column blocks of one blocked-32 array of that row length (v1_hoist_merged_bf16)
+static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, bool gather, cudaStream_t s, int addend_div = 0,
+                     int blocked_ld = 0) {
     Bf16State &b = *D.bf;
     const DcDecoderConfig &cfg = D.cfg;
     const int E = cfg.embed, U = cfg.units, V = cfg.vocab, K1 = b.Epad + U, p = b.parity;
@@ -254,7 +256,7 @@ static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, bool
     if (gather)
         if (int rc = embed_gather(D.W("imgcap_embedding_layer/embeddings"), D.ws.tok, R, E, V, b.X1[p], K1, true, s)) return rc;
     TcEpilogue c1;
-    c1.addend = g1f; c1.ld_addend = 4 * U; c1.addend_div = addend_div; c1.cell_c = D.ws.c1; c1.cell_units = U; c1.cell_tok = D.ws.tok;
+    c1.addend = g1f; c1.ld_addend = blocked_ld > 0 ? blocked_ld : 4 * U; c1.addend_blocked32 = blocked_ld > 0; c1.addend_div = addend_div; c1.cell_c = D.ws.c1; c1.cell_units = U; c1.cell_tok = D.ws.tok;
     c1.cell_h_prev = b.X1[p] + b.Epad; c1.ld_h_prev = K1;
     c1.cell_h_a = b.X1[p ^ 1] + b.Epad; c1.ld_h_a = K1;
     c1.cell_h_b = b.X2[p]; c1.ld_h_b = 2 * U;
@@ -265,7 +267,7 @@ static int step_core(Decoder &D, int R, const float *g1f, const float *d1f, bool
     c2.cell_h_a = b.X2[p ^ 1] + U; c2.ld_h_a = 2 * U;
     if (int rc = gemm_bf16_tc(op(b.X2[p], 2 * U), op(b.w2cat, 2 * U), c2, R, 4 * U, 2 * U, kEpiCell, s)) return rc;
     TcEpilogue d1;
-    d1.addend = d1f; d1.ld_addend = kDense; d1.addend_div = addend_div; d1.relu = 1; d1.out_bf16 = b.d; d1.ld_bf16 = kDense;
+    d1.addend = d1f; d1.ld_addend = blocked_ld > 0 ? blocked_ld : kDense; d1.addend_blocked32 = blocked_ld > 0; d1.addend_div = addend_div; d1.relu = 1; d1.out_bf16 = b.d; d1.ld_bf16 = kDense;
     if (int rc = gemm_bf16_tc(op(b.X2[p ^ 1] + U, 2 * U), op(b.wd1h, U), d1, R, kDense, U, kEpiStore, s)) return rc;
     b.parity ^= 1;
     return DC_OK;
@@ -393,6 +395,8 @@ struct BeamPermute {
     const int32_t *hist_src; int32_t *hist_dst, *tok;
     int k, U, P, col;
     int compact;          // first step: the state rows are per RoI (row b), not per beam (row b*k + parent)
+    const uint4 *emb; int e8;     // bf16 embedding table [V, 8 * e8]: the new token's row goes into the next step's [emb | h1] operand
+    uint4 *x1_dst;                // row base of that operand (ld1 elements per row); null: the next step gathers itself
 };
 
 __global__ void __launch_bounds__(128) beam_permute_kernel(const BeamPermute a, int rows) {
@@ -411,6 +415,9 @@ __global__ void __launch_bounds__(128) beam_permute_kernel(const BeamPermute a, 
     for (int i = threadIdx.x; i < a.P; i += blockDim.x)
         a.hist_dst[(long long)r * a.P + i] = (i == a.col) ? nt : a.hist_src[hr * a.P + i];
     if (threadIdx.x == 0) a.tok[r] = nt;
+    if (a.x1_dst)
+        for (int i = threadIdx.x; i < a.e8; i += blockDim.x)
+            a.x1_dst[(long long)r * (a.ld1 >> 3) + i] = __ldg(a.emb + (long long)nt * a.e8 + i);
 }
 
 int Decoder::beam_bf16(const void *feats, int kind, int B, int k, int32_t *tokens, double *scores, cudaStream_t s) {
@@ -426,7 +433,17 @@ int Decoder::beam_bf16(const void *feats, int kind, int B, int k, int32_t *token
     }
     // head + hoisted per-RoI terms on B rows; the step GEMMs read them with addend row = beam row / k
     if (int rc = head(feats, kind, B, ws.F, s)) return rc;
-    if (int rc = v1_hoist(B, s)) return rc;
+    // per-RoI terms: one GEMM into the blocked-32 layout (the beams of a RoI read row m / k: neighbouring lanes then hit
+    // the same 512-byte line instead of 11 different ones); DCAP_BEAM_BLOCKED=0 keeps the row-major pair.  Measured on
+    // cfg4 (100 k RoIs, width 3): 147-150 ms either way -- at 100 k rows per chunk the step is bound by the main loops of
+    // its GEMMs under the power cap, not by these epilogues; kept because it saves a launch and 1.2 GB of strided reads
+    static const bool blocked_env = !(getenv("DCAP_BEAM_BLOCKED") && atoi(getenv("DCAP_BEAM_BLOCKED")) == 0);
+    const int blocked_ld = blocked_env ? 4 * U + kDense : 0;
+    const float *g1f = ws.g1f, *d1f = ws.d1f;
+    if (blocked_ld) {
+        if (int rc = v1_hoist_merged_bf16(B, kind != DC_FEATS_HEAD_F32, s)) return rc;
+        g1f = b.hoist_all; d1f = b.hoist_all + (size_t)U * 32 * 4;
+    } else if (int rc = v1_hoist(B, s)) return rc;
     if (int rc = v1_reset_state(R, s)) return rc;
     if (int rc = fill_i32(ws.tok, R, 1, s)) return rc;                  // <start> = 1
     DC_CHECK_CUDA(cudaMemsetAsync(ws.score_a, 0, sizeof(double) * R, s));
@@ -439,7 +456,8 @@ int Decoder::beam_bf16(const void *feats, int kind, int B, int k, int32_t *token
         // addends read directly) and the permutation below fans the state out to the k beams
         const bool first = t == 0;
         const int rows = first ? B : R;
-        if (int rc = step_core(*this, rows, ws.g1f, ws.d1f, true, s, first ? 0 : k)) return rc;
+        // from the second step on the permutation kernel has already placed the new tokens' embedding rows
+        if (int rc = step_core(*this, rows, g1f, d1f, first, s, first ? 0 : k, blocked_ld)) return rc;
         TcEpilogue e;
         e.bias = W("imgcap_lstm_d2/bias"); e.partial = b.topk_partial; e.topk = k;
         if (int rc = gemm_bf16_tc(op(b.d, kDense), op(b.wd2, kDense), e, rows, V, kDense, kEpiTopK, s)) return rc;
@@ -455,6 +473,8 @@ int Decoder::beam_bf16(const void *feats, int kind, int B, int k, int32_t *token
         a.c1_src = ws.c1; a.c1_dst = ws.c1b; a.c2_src = ws.c2; a.c2_dst = ws.c2b;
         a.hist_src = hist; a.hist_dst = hist_n; a.tok = ws.tok;
         a.k = k; a.U = U; a.P = P; a.col = t + 1; a.compact = first ? 1 : 0;
+        a.emb = reinterpret_cast<const uint4 *>(b.emb); a.e8 = b.Epad / 8;
+        a.x1_dst = t + 2 < P ? reinterpret_cast<uint4 *>(b.X1[p ^ 1]) : nullptr;
         beam_permute_kernel<<<R, 128, 0, s>>>(a, R);
         DC_CHECK_LAUNCH();
         b.parity ^= 1;

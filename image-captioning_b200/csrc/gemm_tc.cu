@@ -57,6 +57,28 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Addend of epilogue row `ri`: a float4 pointer and the stride (in float4) between consecutive column quads --
+// row-major (stride 1) or blocked-32 (stride 32, see TcEpilogue::addend_blocked32).
+struct AddendRow {
+    const float4 *p;
+    int stride;
+    __device__ __forceinline__ float4 quad(int n) const { return __ldg(p + (long long)(n >> 2) * stride); }
+    __device__ __forceinline__ float at(int n) const { return __ldg(reinterpret_cast<const float *>(p + (long long)(n >> 2) * stride) + (n & 3)); }
+};
+__device__ __forceinline__ AddendRow addend_row(const TcEpilogue &ep, long long mr) {
+    AddendRow a;
+    a.p = nullptr; a.stride = 1;
+    if (!ep.addend) return a;
+    const long long ri = ep.addend_mod > 0 ? mr % ep.addend_mod : (ep.addend_div > 0 ? mr / ep.addend_div : mr);
+    if (ep.addend_blocked32) {
+        a.p = reinterpret_cast<const float4 *>(ep.addend) + ((ri >> 5) * (ep.ld_addend >> 2)) * 32 + (ri & 31);
+        a.stride = 32;
+    } else {
+        a.p = reinterpret_cast<const float4 *>(ep.addend + ri * ep.ld_addend);
+    }
+    return a;
+}
+
 // Top-k epilogue body for one (warp, column region): per row (lane) the running max / sum exp and the K best
 // (value, index) pairs in descending lexicographic order (value, then index: among equal values the LARGER
 // index ranks higher, as np.argsort(p)[-k:] of a stable sort does).  Lane = row, so a data-dependent
@@ -193,7 +215,7 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
         const int m = m_base + lane;
         const bool valid = m < M;
         const long long mr = valid ? m : (long long)(M - 1);
-        const float *add_row = ep.addend ? ep.addend + (ep.addend_mod > 0 ? mr % ep.addend_mod : (ep.addend_div > 0 ? mr / ep.addend_div : mr)) * ep.ld_addend : nullptr;
+        const AddendRow add_row = addend_row(ep, mr);
         const __nv_bfloat16 *mask_row = ep.mask_src ? ep.mask_src + mr * ep.ld_mask : nullptr;
         const bool bf16_vec8 = ep.out_bf16 && ((ep.ld_bf16 & 7) == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0);
         // Output path.  tma_out != 0: the warp's 32 x 32 fp32 (or 32 x 64 bf16) sub-tile is staged in a
@@ -208,8 +230,8 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 a_nxt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (add_row && nb + 4 * j + 4 <= N)
-                    a_nxt[j] = __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j));
+                if (add_row.p && nb + 4 * j + 4 <= N)
+                    a_nxt[j] = add_row.quad(nb + 4 * j);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -276,7 +298,7 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
                     float x = 0.f;
                     if (n < N) {
                         x = v[j];
-                        if (add_row) x += __ldg(add_row + n);
+                        if (add_row.p) x += add_row.at(n);
                         if (ep.bias) x += __ldg(ep.bias + n);
                         if (ep.scale) x = x * __ldg(ep.scale + n) + __ldg(ep.shift + n);
                         if (ep.relu) x = fmaxf(x, 0.f);
@@ -389,7 +411,7 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
         const int m = m_base + lane;
         const bool valid = m < M;
         const long long mr = valid ? m : (long long)(M - 1);
-        const float *add_row = ep.addend ? ep.addend + (ep.addend_mod > 0 ? mr % ep.addend_mod : (ep.addend_div > 0 ? mr / ep.addend_div : mr)) * ep.ld_addend : nullptr;
+        const AddendRow add_row = addend_row(ep, mr);
         const float *c_row = ep.cell_c + mr * ep.cell_units;
         float *c_dst = (ep.cell_c_out ? ep.cell_c_out : ep.cell_c) + mr * ep.cell_units;
         const bool masked = ep.cell_tok && __ldg(ep.cell_tok + mr) == 0;
@@ -398,8 +420,7 @@ __device__ __forceinline__ void epilogue_region(const TcEpilogue &ep, uint32_t t
         auto load_operands = [&](int nb) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                a_nxt[j] = add_row ? __ldg(reinterpret_cast<const float4 *>(add_row + nb + 4 * j))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                a_nxt[j] = add_row.p ? add_row.quad(nb + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
             c_nxt[0] = *reinterpret_cast<const float4 *>(c_row + (nb >> 2));
             c_nxt[1] = *reinterpret_cast<const float4 *>(c_row + (nb >> 2) + 4);
             if (masked) h_nxt = *reinterpret_cast<const uint4 *>(ep.cell_h_prev + mr * ep.ld_h_prev + (nb >> 2));
@@ -1103,7 +1124,7 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
         static const bool cell_tma_off = getenv("DCAP_CELL_TMA") && atoi(getenv("DCAP_CELL_TMA")) == 0;
         // (measured: pays when there is an fp32 addend to stage -- 44 -> 39 us at 8000 x 2048 x 832; without one the
         // 128 x 256 tiles win because they read the B operand from shared memory half as often)
-        const bool cell_tma = !cell_tma_off && ep.addend && !g.a_mn && !g.b_mn && N % 128 == 0 && ep.addend_mod == 0 && ep.addend_div == 0 &&
+        const bool cell_tma = !cell_tma_off && ep.addend && !ep.addend_blocked32 && !g.a_mn && !g.b_mn && N % 128 == 0 && ep.addend_mod == 0 && ep.addend_div == 0 &&
                               ((uintptr_t)ep.cell_c & 15) == 0 && ep.cell_units % 4 == 0;
         if (two_cta && !cell_tma) return launch_tc2<kEpiCell>(ma, mb2, ma, ep, g, stream);
         if (cell_tma) {

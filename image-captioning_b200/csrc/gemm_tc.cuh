@@ -39,6 +39,8 @@ struct TcEpilogue {
     int addend_mod = 0;                   // > 0: addend row = m % addend_mod (per-RoI term broadcast over time)
     int addend_div = 0;                   // > 0: addend row = m / addend_div (per-RoI term shared by the beams of a RoI)
     int deint_units = 0;                  // > 0: fp32 output column 4u+g is written to column g*units+u
+    int addend_blocked32 = 0;             // the addend lies in the blocked-32 layout [row / 32][col / 4][row % 32][4] (row = m, m % mod or m / div;
+                                          // ld_addend = its row length): lane = row loads of neighbouring rows coalesce
     int blocked32 = 0;                    // fp32 output in the blocked-32 layout [m / 32][n / 4][m % 32][4] (greedy_loop.cu; rows padded to 32)
     const __nv_bfloat16 *mask_src = nullptr; long long ld_mask = 0;   // v = mask_src[m,n] > 0 ? v : 0 (ReLU backward)
     int atomic = 0;                       // fp32 output is accumulated with red.global.add (implied by split-K)
