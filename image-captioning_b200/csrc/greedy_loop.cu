@@ -8,31 +8,39 @@
 // of these dependencies is PER ROW BLOCK, though: rows [256 rb, 256 rb + 256) of step t need nothing from any other
 // row block.  This kernel therefore walks ONE global list of work items
 //
-//     item = (step t, stage s, row block rb, column block cb)     ordered by t, then s, then rb, then cb
+//     item = (step t, stage s, row block rb, column block cb)
 //
-// dealt round-robin over the CTA pairs (cluster of 2, tcgen05 cta_group::2, 256 x 256 tiles, the main loop of
-// gemm_bf16_tc2_kernel).  An item waits for the items it depends on through monotone counters in global memory
-// (one per stage and 128-row block, bumped by every epilogue warp that has finished that block of a tile); since
-// every dependency points to an EARLIER item of the list and every pair works through its items in list order, the
-// earliest unfinished item can always run: no deadlock as long as all pairs are resident (one CTA per SM; the
-// host asks the occupancy API how many clusters fit).  The tail of one stage overlaps the head of the next, tile
-// waves never drain, and the 75 launches of a 15-step loop become one.
-//
-// (Also measured without gain: an L2 prefetch of the next item's hoisted-term / cell-state lines from the epilogue warps,
-// row-major and blocked-32 alike: 2.95-3.05 ms either way.)
+// ordered as a diagonal wavefront over (step, row block) (decode_item) and dealt round-robin over the CTA pairs
+// (cluster of 2, tcgen05 cta_group::2, 256 x 256 tiles, the main loop of gemm_bf16_tc2_kernel).  An item waits for
+// the items it depends on through monotone counters in global memory (one per stage and 128-row block); since every
+// dependency points to an EARLIER item of the list and every pair works through its items in list order, the earliest
+// unfinished item can always run: no deadlock as long as all pairs are resident (one CTA per SM; the host asks the
+// occupancy API how many clusters fit).  The tail of one stage overlaps the head of the next, tile waves never drain,
+// and the 75 launches of a 15-step loop become one.
 //
 //   stage 0  z1 = [emb | h1] . [W1e ; U1]^T + (f . W1f + b1)      -> Keras LSTM cell -> h1 (bf16, into X1' and X2), c1
 //   stage 1  z2 = [h1 | h2] . [W2 ; U2]^T + b2                    -> Keras LSTM cell -> h2 (bf16, into X2'), c2
 //   stage 2  d  = relu(h2 . Wd1h^T + (f . Wd1f + bd1))            -> bf16
-//   stage 3  per row and 128-column region: max / first arg-max (/ sum exp) of d . Wd2^T + bd2   -> partial[slot][row]
-//            the LAST of the 2 x 40 epilogue warps to finish a 32-row group merges its partials: token id, optional
-//            caption score, and the token's embedding row copied into the next step's [emb | h1] operand.
+//   stage 3  per row and 128-column region: {max, first arg-max, sum exp, step tag} of d . Wd2^T + bd2 -> partial[region][row]
+//   stage 4  merge item (no GEMM): per row the token id, optional caption score, and the token's embedding row copied
+//            into the next step's [emb | h1] operand; it polls the step tags of the partials (flag in data).
 //
-// Operands written by other SMs' epilogues (generic proxy) are read by TMA (async proxy): writers fence
-// (fence.proxy.async + __threadfence) before they bump a counter, the TMA producer acquires the counter and
-// fences before it issues the loads.  Mutable data read by epilogue threads (c, tokens, previous h, partials)
-// is loaded with ld.global.cg (L2, the coherence point).  Every wait carries a watchdog (trap after ~2 s) so
-// that a protocol bug or a second spinning kernel on the same GPU ends in an error, not in a hung device.
+// Warp roles per CTA (10 warps): warp 0 = TMA producer (dependency wait + operand loads), warp 1 = MMA issuer in the
+// leader CTA / PUBLISHER in CTA 1 (one gpu-scope fence + counter increments per item once the pair's 16 epilogue warps
+// have arrived on a cluster-scope mbarrier), warps 2..9 = epilogue (TMEM lane quarter x column half).
+//
+// Memory-model notes.  Operands written by other SMs' epilogues (generic proxy) are read by TMA (async proxy): the
+// publisher fences at gpu scope before it bumps a counter, the TMA producer acquires the counter and issues
+// fence.proxy.async.global before its loads.  Mutable data read by epilogue threads (c, tokens, previous h, partials)
+// is loaded with ld.global.cg (L2, the coherence point), and only after the producer has seen the dependency (a
+// shared-memory barrier ring from the producer to the epilogue warps).  Every wait carries a watchdog: after ~2 s it
+// records a code in an error word that all waits poll, so a protocol bug or a second spinning kernel on the same GPU
+// drains the grid (with garbage results, reported under DCAP_LOOP_DEBUG) instead of hanging the device.
+//
+// Measured without gain and not kept: L2 prefetch of the next item's hoisted-term / cell-state lines (bulk prefetch from
+// the producer warp: slower; prefetch.global.L2 from the epilogue warps, row-major and blocked-32: 2.95-3.05 ms either
+// way), 16 epilogue warps of 64 columns (96 registers: spills, 3.83 vs 3.30 ms), two chunks of addend look-ahead
+// (spills).  DESIGN.md section 4 has the numbers.
 #include "decoder.cuh"
 #include "decoder_bf16.cuh"
 #include "tc_ptx.cuh"
@@ -99,10 +107,6 @@ __device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint64_t *bar, uint32_
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 // Watchdog: a wait that lasts ~2 s records its code in the error word; every wait polls that word and gives up once
 // it is set, so the whole grid drains (with garbage results) instead of hanging the device.  The host checks the
 // word after the call when DCAP_LOOP_DEBUG is set (tools/loop_check.py) -- in production it never fires.
