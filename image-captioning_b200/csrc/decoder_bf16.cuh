@@ -25,6 +25,8 @@ struct Bf16State {
     int parity = 0;
     unsigned int *loop_cnt = nullptr;                // greedy_loop.cu: dependency counters of the persistent decoding kernel
     size_t loop_cnt_bytes = 0;
+    unsigned int *loop_err_host = nullptr;           // pinned: the kernel's watchdog word of the latest finished launch (checked at the next call)
+    ~Bf16State() { if (loop_err_host) cudaFreeHost(loop_err_host); }
     // backward-pass operand copies: a bf16 mirror of the whole trainable arena (same offsets; written by the
     // optimiser kernel itself, or by one cast after set_weights); the Keras [in, out] tensors inside it are
     // the K-major B operands of dX = dY * W^T (N = in, K = out).  Pointers set by refresh_train_weights().

@@ -860,6 +860,17 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
     // counters (+ error word), zeroed before every launch
     const size_t cnt_bytes = sizeof(unsigned) * (8 * (size_t)p.n128 + 4);
     DC_REQUIRE(b.loop_cnt && cnt_bytes <= b.loop_cnt_bytes, "greedy loop: counter buffer not reserved");
+    // A watchdog hit of an EARLIER launch on this handle (its error word is copied to pinned memory behind every launch)
+    // is reported now: that call returned garbage tokens.
+    if (!b.loop_err_host) {
+        DC_CHECK_CUDA(cudaHostAlloc((void **)&b.loop_err_host, sizeof(unsigned), cudaHostAllocDefault));
+        *b.loop_err_host = 0;
+    }
+    if (const unsigned word = *reinterpret_cast<volatile unsigned *>(b.loop_err_host)) {
+        *b.loop_err_host = 0;
+        return set_error(DC_ERR_CUDA, "an earlier greedy-loop launch on this decoder hit its watchdog (code 0x%x): its tokens are invalid "
+                                      "(another persistent kernel on the same GPU, or a protocol fault)", word);
+    }
     DC_CHECK_CUDA(cudaMemsetAsync(b.loop_cnt, 0, cnt_bytes, s));
     // the partials carry step tags (flag in data, see loop_merge): no stale tag of an earlier launch may survive
     DC_CHECK_CUDA(cudaMemsetAsync(b.partial, 0, sizeof(float4) * (size_t)p.slots * B, s));
@@ -968,6 +979,7 @@ int Decoder::greedy_loop_bf16(int B, int32_t *tokens, float *scores, cudaStream_
         }
     }
     DC_CHECK_CUDA(cudaLaunchKernelEx(&cfgl, kern, maps, p));
+    DC_CHECK_CUDA(cudaMemcpyAsync(b.loop_err_host, b.loop_cnt + 8 * p.n128, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     b.parity = P & 1;
     if (p.trace) {
         // debugging aid: dump the marks as int32 header {pairs, items per pair, steps, items per slot, first[1..4], tiles_m, skew[1..4], 0, 0, 0} + uint64 data
