@@ -30,8 +30,8 @@ def main():
     names = ["dep wait (1-0)", "proxy fence (2-1)", "acc buffer->first operands (4-3)", "mma issue (5-4)",
              "mma end->tmem released (6-5)", "publish (+merge) (7-6)", "item period (5 - prev 5)",
              "epilogue: start->body done (9-8)", "epilogue: own period (8 - prev 8)", "epilogue: start lag behind mma end (8-5)",
-             "vocab epilogue: accumulator ready -> first TMEM load back (11-10)", "vocab epilogue: accumulator ready -> body done (9-10)",
-             "vocab epilogue: mma end -> accumulator seen (10-5)"]
+             "epilogue: accumulator ready -> first chunk done / first TMEM load back (11-10)", "epilogue: accumulator ready -> body done (9-10)",
+             "epilogue: mma end -> accumulator seen (10-5)"]
     for s in range(5):
         m = valid & (stage == s)
         if sel_step is not None:
