@@ -41,12 +41,10 @@
 // the producer warp: slower; prefetch.global.L2 from the epilogue warps, row-major and blocked-32: 2.95-3.05 ms either
 // way), 16 epilogue warps of 64 columns (96 registers: spills, 3.83 vs 3.30 ms), two chunks of addend look-ahead
 // (spills), bias values of the vocabulary / LSTM2 epilogues staged in shared memory before the accumulator wait (the
-// vocabulary tile's hold time 2.2 -> 1.85 us, the kernel 2.94 ms either way).  DESIGN.md section 4 has the numbers.
-//
-// What bounds the main loop (in-kernel timeline, profiles/r2_greedy_loop_trace.txt): ~0.39 us per k-block of a pair against
-// 0.27 us at the tensor peak -- Little's law on the operand ring: 6 slots x 32 KB per CTA in flight against a loaded
-// L2 -> shared-memory latency of ~2 us is ~96 GB/s per SM, the 'crossbar ceiling' of ~10-14 TB/s seen by every
-// tcgen05 kernel of this repo; shared memory is full, so only fewer operand bytes per FLOP would lift it.
+// vocabulary tile's hold time 2.2 -> 1.85 us, the kernel 2.94 ms either way), a SEVENTH operand-ring slot in the
+// shared memory the missing output staging leaves free (2.96 vs 2.93 ms at 8000 RoIs, 1.155 vs 1.105 at 2500: the main
+// loop's ~0.39 us per k-block -- 0.27 at the tensor peak -- is not a bytes-in-flight x latency limit, and the L1 the
+// epilogues' global loads live in shrinks).  DESIGN.md section 4 has the numbers.
 #include "decoder.cuh"
 #include "decoder_bf16.cuh"
 #include "tc_ptx.cuh"
