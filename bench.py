@@ -751,7 +751,10 @@ def run_ours_train(args, ctx):
     model = pkg.build_lstm_model([POOL[0], POOL[1], CHANNELS], cfg, UNITS, "training", dtype="bfloat16", device=dev)
     model.set_weights(w)
     model.compile(optimizer=pkg.Adam(amsgrad=True), loss=pkg.roi_caption_loss)
-    trainer = parallel.DataParallelTrainer(model, overlap=os.environ.get("DCAP_NO_OVERLAP") is None)
+    # DCAP_SHARD_OPT=0: replicated optimiser behind an all-reduce; default: sharded (reduce-scatter, update of the rank's
+    # own ranges, all-gather of the updated parameters)
+    trainer = parallel.DataParallelTrainer(model, overlap=os.environ.get("DCAP_NO_OVERLAP") is None,
+                                           shard_optimizer=os.environ.get("DCAP_SHARD_OPT", "1") != "0")
     rng = np.random.default_rng(1003)
     gt_np = synth.synth_captions(rng, TRAIN_BATCH, TRAIN_P, VOCAB)[lo:hi]
     gen = torch.Generator(device=dev).manual_seed(1003 + rank)
@@ -798,6 +801,8 @@ def run_ours_train(args, ctx):
                                % (TRAIN_BATCH, TRAIN_P, UNITS, VOCAB, EMBED),
                    "rois_per_step": TRAIN_BATCH, "rois_per_rank": Bl, "sharding": "global batch split over ranks; "
                    "one all-reduce(sum) of %d fp32 gradients per step" % model.grad_buffer().numel(),
+                   "optimizer": "sharded over the ranks (reduce-scatter, range update, all-gather)" if trainer.shard_optimizer
+                                else "replicated on every rank",
                    "l2": "activations larger than L2 (logits %d MB per rank)" % (Bl * TRAIN_P * VOCAB * 4 // 2 ** 20),
                    "sm_count": sms, "cc": cc, "loss_first": round(loss_hist[0], 4), "loss_last": round(loss_hist[-1], 4)},
         "clocks": clocks, "gpu_launches": K * 144,      # profiles/r1_launches_train.txt

@@ -106,6 +106,9 @@ SIGNATURES = {
     "dc_decoder_teacher_forced": (ctypes.c_int, [c_void, c_void, ctypes.c_int, ctypes.c_int, c_void, c_void, c_void]),
     "dc_adam_step": (ctypes.c_int, [c_void, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                     ctypes.c_int, ctypes.c_int64, ctypes.c_float, c_void]),
+    "dc_adam_step_range": (ctypes.c_int, [c_void, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                          ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_int64, ctypes.c_int64, c_void]),
+    "dc_decoder_params_updated": (ctypes.c_int, [c_void, c_void]),
     "dc_decoder_grad_buffer": (ctypes.c_int, [c_void, ctypes.POINTER(c_void), ctypes.POINTER(ctypes.c_int64)]),
     "dc_decoder_param_buffer": (ctypes.c_int, [c_void, ctypes.POINTER(c_void), ctypes.POINTER(ctypes.c_int64)]),
     "dc_decoder_grad_bucket": (ctypes.c_int, [c_void, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),

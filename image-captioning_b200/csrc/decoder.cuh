@@ -134,6 +134,9 @@ struct Decoder {
                       float *loss, cudaStream_t s);
     int adam_step(float lr, float beta1, float beta2, float eps, int amsgrad, long long t, float grad_scale,
                   cudaStream_t s);
+    int adam_step_range(float lr, float beta1, float beta2, float eps, int amsgrad, long long t, float grad_scale,
+                        long long offset, long long numel, bool refresh, cudaStream_t s);
+    int params_updated(cudaStream_t s);
     int ensure_grads();
     int refresh_train_weights(cudaStream_t s);
     void invalidate_train_copy();

@@ -1176,19 +1176,46 @@ int Decoder::train_step_v2(const void *feats, int kind, int B, const int32_t *wo
     return DC_OK;
 }
 
-int Decoder::adam_step(float lr, float beta1, float beta2, float eps, int amsgrad, long long t, float grad_scale,
-                       cudaStream_t s) {
+// The update on [offset, offset + numel) of the flat buffers; refresh: re-derive the operand copies afterwards (the
+// whole-buffer step); a sharded optimiser (parallel.py, ZeRO-1 style) steps its own range without it, exchanges the
+// updated ranges and calls params_updated().
+int Decoder::adam_step_range(float lr, float beta1, float beta2, float eps, int amsgrad, long long t, float grad_scale,
+                             long long offset, long long numel, bool refresh, cudaStream_t s) {
     DC_REQUIRE(grads, "dc_adam_step before any dc_decoder_train_step");
     DC_REQUIRE(t >= 1, "iteration count starts at 1");
+    DC_REQUIRE(offset >= 0 && numel >= 0 && offset + numel <= n_train && offset % 4 == 0 && numel % 4 == 0,
+               "optimiser range [%lld, %lld) outside the %lld trainable parameters or not a multiple of 4", offset, offset + numel,
+               (long long)n_train);
     const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t));
-    const long long n = n_train;
-    adam_amsgrad_kernel<<<(unsigned)ceil_div<long long>(n / 4, 256), 256, 0, s>>>(arena, grads, adam_m, adam_v, adam_vhat, n,
-                                                                                 (float)lr_t, beta1, beta2, eps, amsgrad,
-                                                                                 grad_scale, bf ? bf->arena_k : nullptr);
-    DC_CHECK_LAUNCH();
+    if (numel > 0) {
+        adam_amsgrad_kernel<<<(unsigned)ceil_div<long long>(numel / 4, 256), 256, 0, s>>>(
+            arena + offset, grads + offset, adam_m + offset, adam_v + offset, adam_vhat + offset, numel, (float)lr_t, beta1, beta2,
+            eps, amsgrad, grad_scale, (bf && bf->arena_k) ? bf->arena_k + offset : nullptr);
+        DC_CHECK_LAUNCH();
+    }
+    if (!refresh) {
+        if (bf) bf->arena_k_valid = false;                 // only this range of the bf16 mirror is current
+        return DC_OK;
+    }
     if (bf && bf->arena_k) bf->arena_k_valid = true;
     // folded BN + bf16 operand copies (forward and backward layouts) are rebuilt IN PLACE, so captured
     // inference graphs stay valid
+    return refresh_derived(s);
+}
+
+int Decoder::adam_step(float lr, float beta1, float beta2, float eps, int amsgrad, long long t, float grad_scale,
+                       cudaStream_t s) {
+    return adam_step_range(lr, beta1, beta2, eps, amsgrad, t, grad_scale, 0, n_train, true, s);
+}
+
+// The flat parameter buffer was written from outside (all-gather of the ranks' updated ranges): bf16 mirror of the arena
+// and every derived operand copy again.
+int Decoder::params_updated(cudaStream_t s) {
+    if (bf) {
+        bf->arena_k_valid = false;
+        if (bf->arena_k)
+            if (int rc = refresh_train_weights(s)) return rc;
+    }
     return refresh_derived(s);
 }
 
@@ -1235,6 +1262,20 @@ extern "C" int dc_adam_step(DcDecoder *dec, float lr, float beta1, float beta2, 
     DC_REQUIRE(dec, "null decoder");
     if (int rc = dec->impl.check_ready(0)) return rc;
     return dec->impl.adam_step(lr, beta1, beta2, epsilon, amsgrad, iteration, grad_scale, (cudaStream_t)stream);
+}
+
+extern "C" int dc_adam_step_range(DcDecoder *dec, float lr, float beta1, float beta2, float epsilon, int amsgrad,
+                                  int64_t iteration, float grad_scale, int64_t offset, int64_t numel, void *stream) {
+    DC_REQUIRE(dec, "null decoder");
+    if (int rc = dec->impl.check_ready(0)) return rc;
+    return dec->impl.adam_step_range(lr, beta1, beta2, epsilon, amsgrad, iteration, grad_scale, offset, numel, false,
+                                     (cudaStream_t)stream);
+}
+
+extern "C" int dc_decoder_params_updated(DcDecoder *dec, void *stream) {
+    DC_REQUIRE(dec, "null decoder");
+    if (int rc = dec->impl.check_ready(0)) return rc;
+    return dec->impl.params_updated((cudaStream_t)stream);
 }
 
 extern "C" int dc_decoder_grad_buffer(DcDecoder *dec, float **ptr, int64_t *numel) {

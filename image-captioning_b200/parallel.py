@@ -63,11 +63,48 @@ class DataParallelTrainer(object):
     ``apply_gradients(grad_scale)``.  Semantics equal ONE process training on the concatenated
     global batch: loss = mean over all positions of all ranks."""
 
-    def __init__(self, model, group=None, bucket_mb=0, overlap=True):
+    def __init__(self, model, group=None, bucket_mb=0, overlap=True, shard_optimizer=False):
         self.model, self.group = model, group
         self.overlap, self._comm, self._buckets = overlap, None, None
         self.rank, self.world = _world(group)
         self.bucket_elems = int(bucket_mb * (1 << 20) // 4)
+        # Sharded optimiser (ZeRO-1 style): every gradient bucket is reduce-SCATTERED, each rank applies the update to
+        # the slice it received, and the updated parameter slices are all-gathered -- the same bytes on the wire as the
+        # all-reduce, but the optimiser pass (31.6 M parameters, 0.33 ms on a B200) shrinks by the world size instead of
+        # being repeated on every rank.  Replicas stay bit-identical: every rank ends with the same gathered buffer.
+        self.shard_optimizer = bool(shard_optimizer) and self.world > 1 and hasattr(model, "apply_gradients_ranges")
+
+    def _slices(self, off, n):
+        """Split [off, off + n) into world equal chunks (multiples of 4 floats) + a replicated remainder."""
+        chunk = (n // (self.world * 4)) * 4
+        return chunk, off + chunk * self.world, n - chunk * self.world
+
+    def _reduce_scatter(self, g, off, n):
+        """Sum over ranks of g[off:off+n]; afterwards this rank's chunk (and the replicated remainder) hold the totals."""
+        chunk, rem_off, rem = self._slices(off, n)
+        nccl = dist.get_backend(self.group) == "nccl"
+        if chunk > 0:
+            whole = g[off:off + chunk * self.world]
+            if nccl:                                        # in place: the output is this rank's chunk of the input
+                dist.reduce_scatter_tensor(whole[self.rank * chunk:(self.rank + 1) * chunk], whole, group=self.group)
+            else:                                           # gloo has no reduce-scatter: same result through an all-reduce
+                dist.all_reduce(whole, group=self.group)
+        if rem > 0:
+            dist.all_reduce(g[rem_off:rem_off + rem], group=self.group)
+
+    def _all_gather(self, p, off, n):
+        chunk, _, _ = self._slices(off, n)
+        if chunk <= 0:
+            return
+        whole = p[off:off + chunk * self.world]
+        mine = whole[self.rank * chunk:(self.rank + 1) * chunk]
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_gather_into_tensor(whole, mine, group=self.group)       # in place
+        else:
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine.clone(), group=self.group)
+            for r, part in enumerate(parts):
+                whole[r * chunk:(r + 1) * chunk].copy_(part)
 
     def broadcast_parameters(self, src=0):
         """Make every replica start from rank ``src``'s trainable weights (Keras towers share variables)."""
@@ -99,6 +136,33 @@ class DataParallelTrainer(object):
         if global_positions <= 0:
             return torch.zeros(())
         loss = self.model.train_step_device(features, gt, targets, 1.0 / global_positions, **step_options)
+        if self.shard_optimizer:
+            g, p = self.model.grad_buffer(), self.model.param_buffer()
+            buckets = self.model.grad_buckets() if hasattr(self.model, "grad_buckets") else [(0, g.numel())]
+            overlap = self.overlap and hasattr(self.model, "wait_grad_bucket") and g.is_cuda
+            if overlap:
+                cur = torch.cuda.current_stream(g.device)
+                if self._comm is None:
+                    self._comm = torch.cuda.Stream(device=g.device)
+                for i, (off, n) in enumerate(buckets):
+                    self.model.wait_grad_bucket(i, self._comm)
+                    with torch.cuda.stream(self._comm):
+                        self._reduce_scatter(g, off, n)
+                cur.wait_stream(self._comm)
+            else:
+                for off, n in buckets:
+                    self._reduce_scatter(g, off, n)
+            dist.all_reduce(loss, group=self.group)
+            ranges = []
+            for off, n in buckets:
+                chunk, rem_off, rem = self._slices(off, n)
+                ranges.append((off + self.rank * chunk, chunk))
+                ranges.append((rem_off, rem))              # the remainder (< 4 * world floats) is updated on every rank
+            self.model.apply_gradients_ranges(ranges, 1.0)
+            for off, n in buckets:
+                self._all_gather(p, off, n)
+            self.model.params_updated()
+            return loss
         if self.world > 1:
             g = self.model.grad_buffer()
             if self.overlap and hasattr(self.model, "wait_grad_bucket"):

@@ -537,6 +537,29 @@ class RoiCaptionModel(_ModelBase):
                                               ctypes.c_float(o.beta_2), ctypes.c_float(o.epsilon), int(o.amsgrad),
                                               ctypes.c_int64(o.iterations), ctypes.c_float(grad_scale), self._stream()))
 
+    def apply_gradients_ranges(self, ranges, grad_scale=1.0):
+        """ONE optimiser update restricted to the ``(offset, numel)`` ranges of the flat buffers (sharded optimiser:
+        this rank's ranges after the gradient reduce-scatter).  Advances the iteration count once; call
+        ``params_updated()`` when the ranks have exchanged their ranges."""
+        if self.optimizer is None:
+            raise RuntimeError("compile() the model first")
+        o = self.optimizer
+        lr = o.current_lr()
+        o.iterations += 1
+        with torch.cuda.device(self.device):
+            for offset, numel in ranges:
+                if numel <= 0:
+                    continue
+                _lib.check(self._lib.dc_adam_step_range(self._h, ctypes.c_float(lr), ctypes.c_float(o.beta_1),
+                                                        ctypes.c_float(o.beta_2), ctypes.c_float(o.epsilon), int(o.amsgrad),
+                                                        ctypes.c_int64(o.iterations), ctypes.c_float(grad_scale),
+                                                        ctypes.c_int64(int(offset)), ctypes.c_int64(int(numel)), self._stream()))
+
+    def params_updated(self):
+        """The flat parameter buffer was written from outside (all-gather): refresh every derived copy."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.dc_decoder_params_updated(self._h, self._stream()))
+
     def train_on_batch(self, x, y=None, sample_weight=None, class_weight=None):
         """Keras train_on_batch([features, gt_captions], one_hot_targets) -> scalar loss."""
         if self.optimizer is None:

@@ -272,6 +272,15 @@ int dc_decoder_teacher_forced(DcDecoder *dec, const void *feats, int feats_kind,
 int dc_adam_step(DcDecoder *dec, float lr, float beta1, float beta2, float epsilon, int amsgrad,
                  int64_t iteration, float grad_scale, void *stream);
 
+/* Sharded optimiser (one process per GPU, parallel.DataParallelTrainer(shard_optimizer=True); replaces the replicated
+ * update behind parallel_model.py:22-102): the same update on the range [offset, offset + numel) of the flat buffers
+ * only (both multiples of 4 floats) -- each rank steps the range whose summed gradient it received from the
+ * reduce-scatter; the operand copies are NOT re-derived.  After the ranks have all-gathered their updated ranges into
+ * dc_decoder_param_buffer, dc_decoder_params_updated refreshes the bf16 mirror and every derived operand copy. */
+int dc_adam_step_range(DcDecoder *dec, float lr, float beta1, float beta2, float epsilon, int amsgrad,
+                       int64_t iteration, float grad_scale, int64_t offset, int64_t numel, void *stream);
+int dc_decoder_params_updated(DcDecoder *dec, void *stream);
+
 /* Flat fp32 device buffers over all TRAINABLE tensors (BatchNorm moving statistics and the frozen
  * embedding excluded): the gradient buffer is what a data-parallel host all-reduces (NCCL) between
  * dc_decoder_train_step and dc_adam_step; dc_decoder_weight_offset gives each tensor's offset

@@ -55,6 +55,20 @@ class _StubModel(object):
         self.steps += 1
         self.w -= 0.05 * grad_scale * self.g.view_as(self.w)
 
+    # sharded-optimiser surface: the update on ranges of the flat buffers, then a refresh hook
+    def apply_gradients_ranges(self, ranges, grad_scale=1.0):
+        self.steps += 1
+        flat = self.w.view(-1)
+        for off, n in ranges:
+            flat[off:off + n] -= 0.05 * grad_scale * self.g[off:off + n]
+
+    def params_updated(self):
+        self.refreshed = getattr(self, "refreshed", 0) + 1
+
+    def grad_buckets(self):
+        n = self.g.numel()
+        return [(n // 2, n - n // 2), (0, n // 2)]          # two buckets in backward-completion order
+
 
 def _free_port():
     with socket.socket() as s:
@@ -62,7 +76,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, feats, gt, bucket_mb, out):
+def _worker(rank, world, port, feats, gt, bucket_mb, out, shard_optimizer=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -70,7 +84,8 @@ def _worker(rank, world, port, feats, gt, bucket_mb, out):
         model = _StubModel(feats.shape[1], gt.shape[1])
         if rank == 1:
             model.w += 1.0                                   # replicas start apart: broadcast must fix it
-        tr = parallel.DataParallelTrainer(model, bucket_mb=bucket_mb)
+        tr = parallel.DataParallelTrainer(model, bucket_mb=bucket_mb, shard_optimizer=shard_optimizer)
+        assert tr.shard_optimizer == bool(shard_optimizer)
         tr.broadcast_parameters(0)
         lo, hi = parallel.shard_bounds(feats.shape[0], rank, world)
         losses = [tr.train_on_batch([feats[lo:hi], gt[lo:hi]]) for _ in range(3)]
@@ -99,3 +114,25 @@ def test_data_parallel_training_equals_single_process(bucket_mb):
         torch.testing.assert_close(w, ref.w, rtol=1e-12, atol=1e-12)
         assert rows[:, 0].tolist() == list(range(11))
     torch.testing.assert_close(out[0][1], out[1][1], rtol=0, atol=0)     # replicas stay identical
+
+
+def test_sharded_optimizer_equals_single_process():
+    """ZeRO-1 style: reduce-scatter of every gradient bucket (emulated under gloo), range update on the owning rank,
+    all-gather of the updated parameter slices == single-process training; replicas stay bit-identical; the remainder
+    that does not divide by 4 * world floats is updated redundantly on every rank."""
+    torch.manual_seed(4)
+    feats = torch.randn(11, 7, dtype=torch.float64)          # 7 x 5 = 35 parameters: chunks of 4 per rank + remainders
+    gt = torch.randn(11, 5, dtype=torch.float64)
+    ref = _StubModel(7, 5)
+    ref_tr = parallel.DataParallelTrainer(ref)
+    ref_losses = [ref_tr.train_on_batch([feats, gt]) for _ in range(3)]
+
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, feats, gt, 0, out, True), nprocs=world, join=True)
+    for r in range(world):
+        losses, w, rows = out[r]
+        np.testing.assert_allclose(losses, ref_losses, rtol=1e-12)
+        torch.testing.assert_close(w, ref.w, rtol=1e-12, atol=1e-12)
+    torch.testing.assert_close(out[0][1], out[1][1], rtol=0, atol=0)

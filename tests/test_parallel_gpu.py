@@ -33,7 +33,7 @@ def _model(w, batch, device):
     return m
 
 
-def _worker(rank, world, port, dropout, out_path):
+def _worker(rank, world, port, dropout, out_path, shard_optimizer=False):
     import torch.distributed as dist
     from image_captioning_b200 import parallel
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -43,7 +43,8 @@ def _worker(rank, world, port, dropout, out_path):
     w, feat, gt = _data()
     lo, hi = parallel.shard_bounds(B, rank, world)
     m = _model(w, hi - lo, dev)
-    tr = parallel.DataParallelTrainer(m, overlap=True)
+    tr = parallel.DataParallelTrainer(m, overlap=True, shard_optimizer=shard_optimizer)
+    assert tr.shard_optimizer == bool(shard_optimizer)
     tr.broadcast_parameters()
     losses = []
     for it in range(STEPS):
@@ -58,8 +59,10 @@ def _worker(rank, world, port, dropout, out_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dropout", [0.0, 0.2])
-def test_two_rank_nccl_training_equals_single_process(tmp_path, dropout):
+@pytest.mark.parametrize("dropout,shard_optimizer", [(0.0, False), (0.2, False), (0.0, True)])
+def test_two_rank_nccl_training_equals_single_process(tmp_path, dropout, shard_optimizer):
+    """shard_optimizer: ZeRO-1 style -- NCCL reduce-scatter of every gradient bucket (in place), the AMSGrad update on the
+    rank's own ranges (dc_adam_step_range), NCCL all-gather of the updated parameter ranges, dc_decoder_params_updated."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -67,7 +70,7 @@ def test_two_rank_nccl_training_equals_single_process(tmp_path, dropout):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     out = str(tmp_path / "dp.npz")
-    mp.spawn(_worker, args=(2, port, dropout, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, dropout, out, shard_optimizer), nprocs=2, join=True)
     got = np.load(out)
     assert got["replicas_identical"].all()
     # single process, whole batch, same steps
