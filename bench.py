@@ -751,10 +751,11 @@ def run_ours_train(args, ctx):
     model = pkg.build_lstm_model([POOL[0], POOL[1], CHANNELS], cfg, UNITS, "training", dtype="bfloat16", device=dev)
     model.set_weights(w)
     model.compile(optimizer=pkg.Adam(amsgrad=True), loss=pkg.roi_caption_loss)
-    # DCAP_SHARD_OPT=0: replicated optimiser behind an all-reduce; default: sharded (reduce-scatter, update of the rank's
-    # own ranges, all-gather of the updated parameters)
+    # optimiser: replicated behind an all-reduce, or sharded (reduce-scatter, update of the rank's own ranges, all-gather of
+    # the updated parameters) -- "auto" shards from 4 ranks on (measured crossover); DCAP_SHARD_OPT=0/1 forces one
+    so = os.environ.get("DCAP_SHARD_OPT")
     trainer = parallel.DataParallelTrainer(model, overlap=os.environ.get("DCAP_NO_OVERLAP") is None,
-                                           shard_optimizer=os.environ.get("DCAP_SHARD_OPT", "1") != "0")
+                                           shard_optimizer="auto" if so is None else so != "0")
     rng = np.random.default_rng(1003)
     gt_np = synth.synth_captions(rng, TRAIN_BATCH, TRAIN_P, VOCAB)[lo:hi]
     gen = torch.Generator(device=dev).manual_seed(1003 + rank)

@@ -72,6 +72,11 @@ class DataParallelTrainer(object):
         # the slice it received, and the updated parameter slices are all-gathered -- the same bytes on the wire as the
         # all-reduce, but the optimiser pass (31.6 M parameters, 0.33 ms on a B200) shrinks by the world size instead of
         # being repeated on every rank.  Replicas stay bit-identical: every rank ends with the same gathered buffer.
+        # Measured on B200s (cfg3, global batch 4096 x 16): 2 ranks 4.96-5.02 ms sharded vs 4.80 replicated (the all-gather of
+        # the updated parameters is not overlapped with anything, the all-reduce was hidden under the backward pass), 8 ranks
+        # 2.755 vs 2.81 ms -- "auto" shards from 4 ranks on.
+        if shard_optimizer == "auto":
+            shard_optimizer = self.world >= 4
         self.shard_optimizer = bool(shard_optimizer) and self.world > 1 and hasattr(model, "apply_gradients_ranges")
 
     def _slices(self, off, n):
