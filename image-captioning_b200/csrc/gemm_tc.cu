@@ -1044,9 +1044,17 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
     g.split_major = split_major_env;
     // CTA-pair variant (cta_group::2, 256 x 256 tiles).  Measured (same box, A/B): greedy decoder 3.92 -> 3.70 ms
     // per 8000 RoIs, training step 9.15 -> 8.85 ms, beam search 229 -> 215 ms.
-    static const int two_cta_env = getenv("DCAP_2CTA") ? atoi(getenv("DCAP_2CTA")) : 1;     // 0 = off, n = minimum number of pair tiles
+    // Launches of fewer than ~sms/8 pair tiles (the 512- / 1024-row step and data-gradient GEMMs of a training step
+    // split over 8 / 4 ranks, the launch-per-GEMM decoder on a few hundred RoIs) run faster as 128 x 128 single-CTA
+    // tiles: four times as many SMs get a tile and the launch is latency-, not throughput-bound.  Measured on one
+    // GPU (gpurun_out/r2f_smallm*.log, forward+backward of the cfg3 step): 512 rows 1.96 -> 1.78 ms, 1024 rows
+    // 2.70 -> 2.62 ms, 2048 / 4096 rows unchanged (a threshold of 33 and more is SLOWER there: 4.28 -> 4.38 ms).
+    // (read per call so that the tests can hold both kernel families to the same small and ragged shapes)
+    const char *two_cta_str = getenv("DCAP_2CTA");
+    const int two_cta_env = two_cta_str ? atoi(two_cta_str) : -1;                            // 0 = off, n = minimum number of pair tiles
+    const int two_cta_min = two_cta_env >= 0 ? two_cta_env : (sms + 7) / 8;
     const int tiles2 = ceil_div(M, 256) * ceil_div(N, 256);
-    const bool two_cta = two_cta_env != 0 && N >= 256 && tiles2 >= two_cta_env;
+    const bool two_cta = two_cta_min != 0 && N >= 256 && tiles2 >= two_cta_min;
     if (epi == kEpiStore && ep.atomic && ep.out_f32 && !ep.out_bf16) {
         int want = split_k;
         if (want <= 0) {                      // fill ~2 waves of CTAs (CTA pairs), keep >= 8 k-blocks per unit

@@ -8,6 +8,20 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["default", "pair", "single"])
+def kernel_family(request, monkeypatch):
+    """Every tcgen05 test runs three times: with the dispatcher's own choice (launches of fewer than ~sms/8 pair tiles
+    take the single-CTA kernels), with the CTA-pair kernels forced wherever N >= 256 (DCAP_2CTA=1) and with them off
+    (DCAP_2CTA=0) -- csrc/gemm_tc.cu reads the variable per call."""
+    if request.param == "pair":
+        monkeypatch.setenv("DCAP_2CTA", "1")
+    elif request.param == "single":
+        monkeypatch.setenv("DCAP_2CTA", "0")
+    else:
+        monkeypatch.delenv("DCAP_2CTA", raising=False)
+    return request.param
+
+
 def _rand(shape, seed, dtype=torch.float32):
     g = torch.Generator(device="cuda").manual_seed(seed)
     return torch.randn(shape, device="cuda", generator=g).to(dtype)
