@@ -25,8 +25,10 @@
 #include "decoder.cuh"
 #include "decoder_bf16.cuh"
 #include "gemm_tc.cuh"
+#include "tc_ptx.cuh"
 
 #include <math.h>
+#include <type_traits>
 #include <stdlib.h>
 
 namespace dcap {
@@ -300,6 +302,246 @@ __global__ void __launch_bounds__(256) softmax_xent_kernel(const TIn *logits, lo
         }
         *reinterpret_cast<uint4 *>(g + j) = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+
+// ---- fused form for the training step: softmax + cross-entropy + dlogits IN PLACE + vocabulary-bias gradient ----
+// The one-CTA-per-row kernel above reads every row twice through L1/L2 with ~32 KB of loads in flight per SM and two
+// exponentials per element (3.9 TB/s), and the bias gradient then re-reads all 1.3 GB of dlogits (colsum_kernel:
+// 0.28 ms per cfg3 step).  Here two persistent CTAs per SM stream blocks of G rows through two-slot shared-memory rings
+// filled by 1-D bulk copies (cp.async.bulk, one mbarrier per slot: no register stands behind a byte in flight);
+// thread t owns the same 8-column vectors (t + 512 k) of EVERY row, so the column sums of dlogits stay in its registers
+// across all the rows the CTA sees and leave with V atomics per CTA at the end.  Three passes over a slot, one
+// exponential per element: (A) row maxima; (B) e = exp(z - max), row sums, e written back into the slot as bf16;
+// (C) dlogits = (e / sum - onehot) * scale to global memory, column sums.  The target's own probability (loss, clip
+// decision) is taken from the fp32 e of the thread that owns its column, not from the bf16 copy.
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kXentThreads = 512, kXentWarps = kXentThreads / 32;
+
+// one MUFU.EX2 (exp2f() without fast-math brackets it with a range test and two scalings; flushing the results that
+// would be denormal is exactly right for a softmax numerator)
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int NV, int G>      // NV 8-column vectors per thread (V <= NV * 4096), G rows per ring slot
+__global__ void __launch_bounds__(kXentThreads, 2) softmax_xent_colsum_kernel(__nv_bfloat16 *z, long long ld, int V, long long R,
+                                                                               const int32_t *__restrict__ tgt, float inv_count,
+                                                                               float *__restrict__ rowloss,
+                                                                               float *__restrict__ bias_grad) {
+    extern __shared__ __align__(128) unsigned char xent_smem[];
+    __shared__ uint64_t full[2];
+    __shared__ float red_m[kXentWarps][G], red_s[kXentWarps][G];
+    __shared__ float st_ey[G];
+    __shared__ int st_y[G];
+    constexpr float kLog2e = 1.4426950408889634f;
+    const uint32_t rowbytes = (uint32_t)V * 2;
+    const long long nblk = (R + G - 1) / G;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long blk, int b) {
+        const long long r0 = blk * G;
+        const int rows = (int)(R - r0 < G ? R - r0 : G);
+        mbar_expect_tx(&full[b], (uint32_t)rows * rowbytes);
+        for (int g = 0; g < rows; ++g)
+            bulk_load_1d(xent_smem + ((size_t)b * G + g) * rowbytes, z + (r0 + g) * ld, rowbytes, &full[b]);
+    };
+    float acc[NV][8];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+    long long blk = blockIdx.x;
+    if (tid == 0 && blk < nblk) issue(blk, 0);
+    for (int it = 0; blk < nblk; blk += gridDim.x, ++it) {
+        const int b = it & 1;
+        // slot b^1 was released by the barrier that closed the previous iteration
+        if (tid == 0 && blk + gridDim.x < nblk) issue(blk + gridDim.x, b ^ 1);
+        const long long r0 = blk * G;
+        const int rows = (int)(R - r0 < G ? R - r0 : G);
+        if (tid < rows) st_y[tid] = tgt[r0 + tid];
+        mbar_wait(&full[b], (uint32_t)(it >> 1) & 1u);
+        unsigned char *buf = xent_smem + (size_t)b * G * rowbytes;
+        // FULL = all G rows of the slot are live (every block but a ragged last one): no per-row predicates
+        auto passes = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        // ---- (A) row maxima
+        float m[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) m[g] = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int j = (tid + k * kXentThreads) * 8;
+            if (j < V) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    if (FULL || g < rows) {
+                        float v[8];
+                        load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16 *>(buf + (size_t)g * rowbytes) + j, v);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) m[g] = fmaxf(m[g], v[i]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            for (int o = 16; o > 0; o >>= 1) m[g] = fmaxf(m[g], __shfl_xor_sync(0xffffffffu, m[g], o));
+            if (lane == 0) red_m[warp][g] = m[g];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float gm = red_m[0][g];
+#pragma unroll
+            for (int w = 1; w < kXentWarps; ++w) gm = fmaxf(gm, red_m[w][g]);
+            m[g] = gm * kLog2e;
+        }
+        // ---- (B) e = exp(z - max) once per element, row sums; e goes back into the slot as bf16
+        float sum[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) sum[g] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int j = (tid + k * kXentThreads) * 8;
+            if (j < V) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    if (FULL || g < rows) {
+                        __nv_bfloat16 *row = reinterpret_cast<__nv_bfloat16 *>(buf + (size_t)g * rowbytes) + j;
+                        float v[8];
+                        load8<__nv_bfloat16>(row, v);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { v[i] = ex2_ftz(fmaf(v[i], kLog2e, -m[g])); sum[g] += v[i]; }
+                        const int yo = st_y[g] - j;
+                        if (yo >= 0 && yo < 8) {
+                            float ey = v[0];
+#pragma unroll
+                            for (int i = 1; i < 8; ++i) ey = yo == i ? v[i] : ey;
+                            st_ey[g] = ey;
+                        }
+                        uint32_t w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                            w[i] = *reinterpret_cast<uint32_t *>(&pk);
+                        }
+                        *reinterpret_cast<uint4 *>(row) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            for (int o = 16; o > 0; o >>= 1) sum[g] += __shfl_xor_sync(0xffffffffu, sum[g], o);
+            if (lane == 0) red_s[warp][g] = sum[g];
+        }
+        __syncthreads();
+        // ---- (C) dlogits to global memory, column sums in registers
+        float scale[G];                                    // inv * (gradient scale, or 0 when the clip is active / no target)
+        float sub[G];                                      // what the target's column loses: that scale without the 1 / sum
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float gs = 0.f;
+#pragma unroll
+            for (int w = 0; w < kXentWarps; ++w) gs += red_s[w][g];
+            const float inv = 1.0f / gs;
+            bool live = (FULL || g < rows) && st_y[g] >= 0;
+            float loss = 0.f;
+            if (live) {
+                const float py = st_ey[g] * inv;
+                loss = -logf(fminf(fmaxf(py, 1e-7f), 1.0f - 1e-7f));
+                live = py > 1e-7f && py < 1.0f - 1e-7f;
+            }
+            if (tid == g && (FULL || g < rows)) rowloss[r0 + g] = loss;
+            sub[g] = live ? inv_count : 0.f;
+            scale[g] = inv * sub[g];
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int j = (tid + k * kXentThreads) * 8;
+            if (j < V) {
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    if (FULL || g < rows) {
+                        float v[8];
+                        load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16 *>(buf + (size_t)g * rowbytes) + j, v);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] *= scale[g];
+                        const int yo = st_y[g] - j;
+                        if (yo >= 0 && yo < 8) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] -= yo == i ? sub[g] : 0.f;
+                        }
+                        uint32_t w[4];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[k][i] += v[i];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                            w[i] = *reinterpret_cast<uint32_t *>(&pk);
+                        }
+                        *reinterpret_cast<uint4 *>(z + (r0 + g) * ld + j) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+        };
+        if (rows == G) passes(std::true_type{});
+        else passes(std::false_type{});
+        __syncthreads();                                   // every read of slot b (and of st_*) is done: it may be refilled
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int j = (tid + k * kXentThreads) * 8;
+        if (j < V) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(bias_grad + j + i, acc[k][i]);
+        }
+    }
+}
+
+template <int NV, int G>
+static int launch_xent_colsum(__nv_bfloat16 *z, long long ld, int V, long long R, const int32_t *tgt, float inv_count,
+                              float *rowloss, float *bias_grad, cudaStream_t s) {
+    const size_t smem = 2 * (size_t)G * V * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DC_CHECK_CUDA(cudaFuncSetAttribute(softmax_xent_colsum_kernel<NV, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    const long long nblk = (R + G - 1) / G, slots = 2ll * sm_count();
+    const unsigned grid = (unsigned)(nblk < slots ? nblk : slots);
+    softmax_xent_colsum_kernel<NV, G><<<grid, kXentThreads, smem, s>>>(z, ld, V, R, tgt, inv_count, rowloss, bias_grad);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
+// returns false when the shape is outside the fused kernel's range (V > 24576, unaligned rows): the caller then runs
+// softmax_xent_kernel + colsum
+static bool xent_colsum_supported(const void *z, long long ld, int V) {
+    return V % 8 == 0 && V <= 24576 && (ld * 2) % 16 == 0 && ((uintptr_t)z & 15) == 0;
+}
+
+// ring slots of at most 48 KB so that two CTAs fit on an SM
+static int softmax_xent_colsum(__nv_bfloat16 *z, long long ld, int V, long long R, const int32_t *tgt, float inv_count,
+                               float *rowloss, float *bias_grad, cudaStream_t s) {
+    if (R <= 0) return DC_OK;
+    if (V <= 4096) return launch_xent_colsum<1, 2>(z, ld, V, R, tgt, inv_count, rowloss, bias_grad, s);
+    if (V <= 8192) return launch_xent_colsum<2, 2>(z, ld, V, R, tgt, inv_count, rowloss, bias_grad, s);
+    if (V <= 12288) return launch_xent_colsum<3, 2>(z, ld, V, R, tgt, inv_count, rowloss, bias_grad, s);
+    if (V <= 16384) return launch_xent_colsum<4, 1>(z, ld, V, R, tgt, inv_count, rowloss, bias_grad, s);
+    return launch_xent_colsum<6, 1>(z, ld, V, R, tgt, inv_count, rowloss, bias_grad, s);
 }
 
 // loss = sum(rowloss) * inv_count, deterministic (one CTA, fixed order)
@@ -802,11 +1044,20 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     // softmax + cross-entropy + dlogits: one CTA per row keeps ~10 rows in flight per SM, which is what makes
     // this kernel run at HBM speed (a variant that kept rows in registers and accumulated the vocabulary-bias
     // gradient in place was latency-bound on its per-row barrier and measured 0.7 ms SLOWER per step)
-    if (t.logits_in_dz)
-        softmax_xent_kernel<__nv_bfloat16><<<(unsigned)R, 256, 0, s>>>(t.dz, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
-    else
-        softmax_xent_kernel<float><<<(unsigned)R, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
-    DC_CHECK_LAUNCH();
+    // The fused form (softmax_xent_colsum_kernel: shared-memory ring fed by bulk copies, persistent CTAs, the
+    // vocabulary-bias gradient accumulated in registers on the way) replaces this kernel AND colsum(dz) below whenever
+    // the logits sit in dz; DCAP_XENT_FUSED=0 keeps the two-kernel form (A/B, tests).
+    const char *xf = getenv("DCAP_XENT_FUSED");
+    const bool fused_xent = t.logits_in_dz && !(xf && atoi(xf) == 0) && xent_colsum_supported(t.dz, V, V);
+    if (fused_xent) {
+        if (int rc = softmax_xent_colsum(t.dz, V, V, R, t.tgt_tm, inv_count, t.rowloss, G("imgcap_lstm_d2/bias"), s)) return rc;
+    } else {
+        if (t.logits_in_dz)
+            softmax_xent_kernel<__nv_bfloat16><<<(unsigned)R, 256, 0, s>>>(t.dz, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
+        else
+            softmax_xent_kernel<float><<<(unsigned)R, 256, 0, s>>>(t.logits, V, V, t.tgt_tm, inv_count, t.dz, V, t.rowloss);
+        DC_CHECK_LAUNCH();
+    }
     reduce_loss_kernel<<<1, 1024, 0, s>>>(t.rowloss, R, inv_count, loss);
     DC_CHECK_LAUNCH();
 
@@ -819,7 +1070,8 @@ int Decoder::train_step(const void *feats, int kind, int B, const int32_t *gt, c
     };
     // dense2: dWd2 = d^T dz, dbd2 = colsum(dz), dd = (dz Wd2^T) * [d > 0]
     if (int rc = wgrad(t.d_all, kDense, kDense, t.dz, V, V, R, G("imgcap_lstm_d2/kernel"), V)) return rc;
-    if (int rc = colsum(t.dz, R, V, V, G("imgcap_lstm_d2/bias"), s)) return rc;
+    if (!fused_xent)
+        if (int rc = colsum(t.dz, R, V, V, G("imgcap_lstm_d2/bias"), s)) return rc;
     DC_CHECK_CUDA(cudaEventRecord(t.bucket_ev[0], s));                 // bucket 0: vocabulary projection
     {
         TcEpilogue e;

@@ -409,3 +409,34 @@ def test_gradients_at_baseline_shapes_match_fp64_oracle():
     assert abs(loss16 - loss) <= 1e-4 * abs(loss)
     rel = float(((m2.grad_buffer() - g256).norm() / g256.norm()).item())
     assert rel <= 2e-3, rel
+
+
+@pytest.mark.parametrize("B,V", [(96, 1000), (37, 4104), (21, 10000), (5, 12296), (3, 16384), (2, 20000)])
+def test_fused_softmax_xent_bias_gradient_equals_the_two_kernel_form(B, V, monkeypatch):
+    """softmax_xent_colsum_kernel (shared-memory ring, column sums in registers) against softmax_xent_kernel + colsum
+    (DCAP_XENT_FUSED=0) on the same step: same loss, same dlogits (through the gradients they feed), and a vocabulary-bias
+    gradient that is at least as close to the two-kernel one as bf16 rounding of dlogits allows.  The shapes cover every
+    (vectors per thread, rows per slot) instantiation, ragged last row blocks and rows without a target."""
+    import image_captioning_b200 as pkg
+    rng = np.random.default_rng(77 + V)
+    shape = dict(V=V, E=48, U=128, C=64)
+    w = synth.synth_weights_v1(rng, trained_like=False, **shape)
+    feat = rng.standard_normal((B, 7, 7, shape["C"])).astype(np.float32)
+    gt = synth.synth_captions(rng, B, P, V)
+    gt[0, 3:] = 0                                       # a caption that ends early: positions without a target
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DCAP_XENT_FUSED", mode)
+        cfg = pkg.DenseCapConfig(V, w["imgcap_embedding_layer/embeddings"], B, P)
+        m = pkg.build_lstm_model([7, 7, shape["C"]], cfg, shape["U"], "training", dtype="bfloat16")
+        m.set_weights(w)
+        m.compile(optimizer=pkg.Adam(amsgrad=True), loss=pkg.roi_caption_loss)
+        loss = float(m.train_step_device(feat, gt).item())
+        res[mode] = (loss, m.get_gradients())
+    (l1, g1), (l0, g0) = res["1"], res["0"]
+    assert abs(l1 - l0) <= 1e-5 * abs(l0), (l1, l0)
+    # the fused kernel rounds exp(z - max) to bf16 before the division by the row sum and the final bf16 rounding of
+    # dlogits (one exponential per element): its dlogits differ from the two-kernel form's by bf16 rounding noise
+    # (2^-9 relative per element), and so does every gradient computed from them
+    for name in g0:
+        assert np.isfinite(g1[name]).all() and _rel_l2(g1[name], g0[name]) <= 6e-3, (name, _rel_l2(g1[name], g0[name]))
