@@ -340,6 +340,8 @@ __global__ void __launch_bounds__(kXentThreads, 2) softmax_xent_colsum_kernel(__
     __shared__ float st_ey[G];
     __shared__ int st_y[G];
     constexpr float kLog2e = 1.4426950408889634f;
+    // the dispatcher picks NV from V's range, so only the last vector(s) of a thread can lie beyond V
+    constexpr int kNoCheck = NV == 6 ? 4 : NV - 1;
     const uint32_t rowbytes = (uint32_t)V * 2;
     const long long nblk = (R + G - 1) / G;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -375,37 +377,44 @@ __global__ void __launch_bounds__(kXentThreads, 2) softmax_xent_colsum_kernel(__
         // FULL = all G rows of the slot are live (every block but a ragged last one): no per-row predicates
         auto passes = [&](auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
-        // ---- (A) row maxima
-        float m[G];
+        // ---- (A) row maxima, on the packed bf16 pairs as they lie in the slot (max is exact in any format)
+        __nv_bfloat162 mx2[G];
 #pragma unroll
-        for (int g = 0; g < G; ++g) m[g] = -INFINITY;
+        for (int g = 0; g < G; ++g) mx2[g] = __float2bfloat162_rn(-INFINITY);
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const int j = (tid + k * kXentThreads) * 8;
-            if (j < V) {
+            if (k < kNoCheck || j < V) {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     if (FULL || g < rows) {
-                        float v[8];
-                        load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16 *>(buf + (size_t)g * rowbytes) + j, v);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) m[g] = fmaxf(m[g], v[i]);
+                        const uint4 q = *reinterpret_cast<const uint4 *>(buf + (size_t)g * rowbytes + (size_t)j * 2);
+                        const __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&q.x), *reinterpret_cast<const __nv_bfloat162 *>(&q.y));
+                        const __nv_bfloat162 c = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(&q.z), *reinterpret_cast<const __nv_bfloat162 *>(&q.w));
+                        mx2[g] = __hmax2(mx2[g], __hmax2(a, c));
                     }
                 }
             }
         }
+        float m[G];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
+            m[g] = fmaxf(__low2float(mx2[g]), __high2float(mx2[g]));
             for (int o = 16; o > 0; o >>= 1) m[g] = fmaxf(m[g], __shfl_xor_sync(0xffffffffu, m[g], o));
             if (lane == 0) red_m[warp][g] = m[g];
         }
         __syncthreads();
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            float gm = red_m[0][g];
+        for (int g = 0; g < G; ++g) {                       // 16 warp partials: one load per lane and a 4-step shuffle tree
+            float gm = red_m[lane & (kXentWarps - 1)][g];
 #pragma unroll
-            for (int w = 1; w < kXentWarps; ++w) gm = fmaxf(gm, red_m[w][g]);
+            for (int o = kXentWarps / 2; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
             m[g] = gm * kLog2e;
+            // the thread that owns the target's column keeps its fp32 exponential: loss and clip decision do not see the
+            // bf16 copy (it reads the logit before its own pass-B store overwrites it)
+            const int y = st_y[g];
+            if ((FULL || g < rows) && y >= 0 && ((y >> 3) & (kXentThreads - 1)) == tid)
+                st_ey[g] = ex2_ftz(fmaf(__bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(buf + (size_t)g * rowbytes)[y]), kLog2e, -m[g]));
         }
         // ---- (B) e = exp(z - max) once per element, row sums; e goes back into the slot as bf16
         float sum[G];
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(kXentThreads, 2) softmax_xent_colsum_kernel(__
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const int j = (tid + k * kXentThreads) * 8;
-            if (j < V) {
+            if (k < kNoCheck || j < V) {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     if (FULL || g < rows) {
@@ -423,13 +432,6 @@ __global__ void __launch_bounds__(kXentThreads, 2) softmax_xent_colsum_kernel(__
                         load8<__nv_bfloat16>(row, v);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) { v[i] = ex2_ftz(fmaf(v[i], kLog2e, -m[g])); sum[g] += v[i]; }
-                        const int yo = st_y[g] - j;
-                        if (yo >= 0 && yo < 8) {
-                            float ey = v[0];
-#pragma unroll
-                            for (int i = 1; i < 8; ++i) ey = yo == i ? v[i] : ey;
-                            st_ey[g] = ey;
-                        }
                         uint32_t w[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -452,9 +454,9 @@ __global__ void __launch_bounds__(kXentThreads, 2) softmax_xent_colsum_kernel(__
         float sub[G];                                      // what the target's column loses: that scale without the 1 / sum
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            float gs = 0.f;
+            float gs = red_s[lane & (kXentWarps - 1)][g];
 #pragma unroll
-            for (int w = 0; w < kXentWarps; ++w) gs += red_s[w][g];
+            for (int o = kXentWarps / 2; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
             const float inv = 1.0f / gs;
             bool live = (FULL || g < rows) && st_y[g] >= 0;
             float loss = 0.f;
@@ -470,22 +472,15 @@ __global__ void __launch_bounds__(kXentThreads, 2) softmax_xent_colsum_kernel(__
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const int j = (tid + k * kXentThreads) * 8;
-            if (j < V) {
+            if (k < kNoCheck || j < V) {
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     if (FULL || g < rows) {
                         float v[8];
                         load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16 *>(buf + (size_t)g * rowbytes) + j, v);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] *= scale[g];
-                        const int yo = st_y[g] - j;
-                        if (yo >= 0 && yo < 8) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] -= yo == i ? sub[g] : 0.f;
-                        }
                         uint32_t w[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[k][i] += v[i];
+                        for (int i = 0; i < 8; ++i) { v[i] *= scale[g]; acc[k][i] += v[i]; }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             __nv_bfloat162 pk = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
@@ -494,6 +489,17 @@ __global__ void __launch_bounds__(kXentThreads, 2) softmax_xent_colsum_kernel(__
                         *reinterpret_cast<uint4 *>(z + (r0 + g) * ld + j) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
+            }
+        }
+        // the "- onehot" term: the owner of the target's column rewrites that one element behind its own vector store
+        // (program order within the thread) and takes it out of the column sum
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int y = st_y[g];
+            if ((FULL || g < rows) && y >= 0 && ((y >> 3) & (kXentThreads - 1)) == tid && sub[g] != 0.f) {
+                const float e = __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(buf + (size_t)g * rowbytes)[y]);
+                z[(r0 + g) * ld + y] = __float2bfloat16_rn(e * scale[g] - sub[g]);
+                atomicAdd(bias_grad + y, -sub[g]);
             }
         }
         };
