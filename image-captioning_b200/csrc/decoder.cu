@@ -123,14 +123,17 @@ int Decoder::dev_alloc(void **p, size_t bytes, std::vector<void *> &list) {
 // ------------------------------------------------------------------------------------------
 // finalize: derived buffers
 // ------------------------------------------------------------------------------------------
-__global__ void bn_fold_kernel(const float *gamma, const float *beta, const float *mean,
-                               const float *var, float eps, int n, float *scale, float *shift) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+struct BnFoldArgs {
+    const float *gamma[2], *beta[2], *mean[2], *var[2];
+    float *scale[2], *shift[2];
+};
+__global__ void bn_fold_kernel(BnFoldArgs a, float eps, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y;
     if (i >= n) return;
     // tf.nn.batch_normalization: inv = rsqrt(var + eps) * gamma; x*inv + (beta - mean*inv)
-    const float inv = (1.0f / sqrtf(var[i] + eps)) * gamma[i];
-    scale[i] = inv;
-    shift[i] = beta[i] - mean[i] * inv;
+    const float inv = (1.0f / sqrtf(a.var[l][i] + eps)) * a.gamma[l][i];
+    a.scale[l][i] = inv;
+    a.shift[l][i] = a.beta[l][i] - a.mean[l][i] * inv;
 }
 
 int Decoder::finalize(cudaStream_t s) {
@@ -156,12 +159,16 @@ int Decoder::refresh_derived(cudaStream_t s) {
             if (int rc = dev_alloc((void **)&bn_scale[i], sizeof(float) * F, owned)) return rc;
             if (int rc = dev_alloc((void **)&bn_shift[i], sizeof(float) * F, owned)) return rc;
         }
-        const std::string bn = i == 0 ? "mrcnn_class_bn1" : "mrcnn_class_bn2";
-        bn_fold_kernel<<<ceil_div(F, 256), 256, 0, s>>>(
-            W((bn + "/gamma").c_str()), W((bn + "/beta").c_str()), W((bn + "/moving_mean").c_str()),
-            W((bn + "/moving_variance").c_str()), kBnEps, F, bn_scale[i], bn_shift[i]);
-        DC_CHECK_LAUNCH();
     }
+    BnFoldArgs bn;                                          // both BatchNorm layers of the head in one launch (blockIdx.y)
+    for (int i = 0; i < 2; ++i) {
+        const std::string name = i == 0 ? "mrcnn_class_bn1" : "mrcnn_class_bn2";
+        bn.gamma[i] = W((name + "/gamma").c_str()); bn.beta[i] = W((name + "/beta").c_str());
+        bn.mean[i] = W((name + "/moving_mean").c_str()); bn.var[i] = W((name + "/moving_variance").c_str());
+        bn.scale[i] = bn_scale[i]; bn.shift[i] = bn_shift[i];
+    }
+    bn_fold_kernel<<<dim3(ceil_div(F, 256), 2), 256, 0, s>>>(bn, kBnEps, F);
+    DC_CHECK_LAUNCH();
     if (cfg.dtype == DC_DTYPE_BF16) return refresh_bf16(fresh, s);
     if (cfg.arch == DC_ARCH_V1) {
         // stacked operands: [W1[:E] ; U1]  and  [W2 ; U2]

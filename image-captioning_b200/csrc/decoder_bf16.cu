@@ -60,6 +60,67 @@ __global__ void interleave_bias_kernel(const float *__restrict__ src, int units,
     if (n < 4 * units) dst[n] = src[(n & 3) * units + (n >> 2)];
 }
 
+// The same re-layout for up to kMaxKmajorJobs tensors in ONE launch (the optimiser re-derives every operand copy after
+// each step: ten launches of 3 - 20 us each were a chain of launch gaps, 0.12 ms of a 2.6 ms step at 8 ranks).
+// Blocks are numbered job after job; a block finds its job by walking the (short) table of first-block indices.
+constexpr int kMaxKmajorJobs = 12;
+struct KmajorJob {
+    const float *src; __nv_bfloat16 *dst; long long ld_dst;
+    int n_src, row_off, K, N, interleave_units, k_off, tiles_k, first_block;
+};
+struct KmajorBatch {
+    KmajorJob job[kMaxKmajorJobs];
+    int n = 0, blocks = 0;
+    void add(const float *src, int n_src, int row_off, int K, int N, int interleave_units, __nv_bfloat16 *dst, long long ld_dst,
+             int k_off) {
+        KmajorJob &j = job[n++];
+        j.src = src; j.dst = dst; j.ld_dst = ld_dst; j.n_src = n_src; j.row_off = row_off; j.K = K; j.N = N;
+        j.interleave_units = interleave_units; j.k_off = k_off; j.tiles_k = ceil_div(K, 32); j.first_block = blocks;
+        blocks += j.tiles_k * ceil_div(N, 32);
+    }
+};
+
+__global__ void __launch_bounds__(256) build_kmajor_batch_kernel(const __grid_constant__ KmajorBatch batch) {
+    __shared__ float tile[32][33];
+    int ji = 0;
+    while (ji + 1 < batch.n && (int)blockIdx.x >= batch.job[ji + 1].first_block) ++ji;
+    const KmajorJob &j = batch.job[ji];
+    const int local = blockIdx.x - j.first_block;
+    const int k0 = (local % j.tiles_k) * 32, n0 = (local / j.tiles_k) * 32;
+    const int n = n0 + threadIdx.x;
+    const int col = j.interleave_units ? (n & 3) * j.interleave_units + (n >> 2) : n;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int k = k0 + i;
+        tile[i][threadIdx.x] = (k < j.K && n < j.N) ? j.src[(long long)(j.row_off + k) * j.n_src + col] : 0.f;
+    }
+    __syncthreads();
+    const int k = k0 + threadIdx.x;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int nn = n0 + i;
+        if (k < j.K && nn < j.N) j.dst[(long long)nn * j.ld_dst + j.k_off + k] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+}
+
+static int launch_kmajor_batch(const KmajorBatch &batch, cudaStream_t s) {
+    if (batch.blocks == 0) return DC_OK;
+    build_kmajor_batch_kernel<<<batch.blocks, dim3(32, 8), 0, s>>>(batch);
+    DC_CHECK_LAUNCH();
+    return DC_OK;
+}
+
+// gate-interleaved LSTM biases and the dense1 bias of the merged hoist GEMM, one launch
+__global__ void derive_biases_kernel(const float *__restrict__ b1, const float *__restrict__ b2, const float *__restrict__ bd1,
+                                     int units, int dense, float *__restrict__ b1_i, float *__restrict__ b2_i,
+                                     float *__restrict__ bd1_dst) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < 4 * units) {
+        const int src = (n & 3) * units + (n >> 2);
+        b1_i[n] = b1[src];
+        b2_i[n] = b2[src];
+    }
+    if (n < dense) bd1_dst[n] = bd1[n];
+}
+
 int build_kmajor(const float *src, int n_src, int row_off, int K, int N, int interleave_units,
                         __nv_bfloat16 *dst, long long ld_dst, int k_off, cudaStream_t s) {
     const dim3 grid(ceil_div(K, 32), ceil_div(N, 32)), block(32, 8);
@@ -132,20 +193,21 @@ int Decoder::refresh_bf16(bool fresh, cudaStream_t s) {
             W("imgcap_embedding_layer/embeddings"), V, E, b.emb, b.Epad);
         DC_CHECK_LAUNCH();
     }
-    rc |= build_kmajor(W("mrcnn_class_conv1/kernel"), F, 0, Kin, F, 0, b.w_head1, Kin, 0, s);
-    rc |= build_kmajor(W("mrcnn_class_conv2/kernel"), F, 0, F, F, 0, b.w_head2, F, 0, s);
-    rc |= build_kmajor(W("imgcap_lstm1/kernel"), 4 * U, 0, E, 4 * U, U, b.w1cat, K1, 0, s);
-    rc |= build_kmajor(W("imgcap_lstm1/recurrent_kernel"), 4 * U, 0, U, 4 * U, U, b.w1cat, K1, b.Epad, s);
-    rc |= build_kmajor(W("imgcap_lstm1/kernel"), 4 * U, E, F, 4 * U, U, b.w1f, F, 0, s);
-    rc |= build_kmajor(W("imgcap_lstm2/kernel"), 4 * U, 0, U, 4 * U, U, b.w2cat, 2 * U, 0, s);
-    rc |= build_kmajor(W("imgcap_lstm2/recurrent_kernel"), 4 * U, 0, U, 4 * U, U, b.w2cat, 2 * U, U, s);
-    rc |= build_kmajor(W("imgcap_lstm_d1/kernel"), kDense, 0, U, kDense, 0, b.wd1h, U, 0, s);
-    rc |= build_kmajor(W("imgcap_lstm_d1/kernel"), kDense, U, F, kDense, 0, b.wd1f, F, 0, s);
-    rc |= build_kmajor(W("imgcap_lstm_d2/kernel"), V, 0, kDense, V, 0, b.wd2, kDense, 0, s);
-    if (rc) return rc;
-    interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm1/bias"), U, b.b1_i);
-    DC_CHECK_CUDA(cudaMemcpyAsync(b.bias_hoist + 4 * U, W("imgcap_lstm_d1/bias"), sizeof(float) * kDense, cudaMemcpyDeviceToDevice, s));
-    interleave_bias_kernel<<<ceil_div(4 * U, 256), 256, 0, s>>>(W("imgcap_lstm2/bias"), U, b.b2_i);
+    KmajorBatch kb;
+    kb.add(W("mrcnn_class_conv1/kernel"), F, 0, Kin, F, 0, b.w_head1, Kin, 0);
+    kb.add(W("mrcnn_class_conv2/kernel"), F, 0, F, F, 0, b.w_head2, F, 0);
+    kb.add(W("imgcap_lstm1/kernel"), 4 * U, 0, E, 4 * U, U, b.w1cat, K1, 0);
+    kb.add(W("imgcap_lstm1/recurrent_kernel"), 4 * U, 0, U, 4 * U, U, b.w1cat, K1, b.Epad);
+    kb.add(W("imgcap_lstm1/kernel"), 4 * U, E, F, 4 * U, U, b.w1f, F, 0);
+    kb.add(W("imgcap_lstm2/kernel"), 4 * U, 0, U, 4 * U, U, b.w2cat, 2 * U, 0);
+    kb.add(W("imgcap_lstm2/recurrent_kernel"), 4 * U, 0, U, 4 * U, U, b.w2cat, 2 * U, U);
+    kb.add(W("imgcap_lstm_d1/kernel"), kDense, 0, U, kDense, 0, b.wd1h, U, 0);
+    kb.add(W("imgcap_lstm_d1/kernel"), kDense, U, F, kDense, 0, b.wd1f, F, 0);
+    kb.add(W("imgcap_lstm_d2/kernel"), V, 0, kDense, V, 0, b.wd2, kDense, 0);
+    if (int rc2 = launch_kmajor_batch(kb, s)) return rc2;
+    const int nb = 4 * U > kDense ? 4 * U : kDense;
+    derive_biases_kernel<<<ceil_div(nb, 256), 256, 0, s>>>(W("imgcap_lstm1/bias"), W("imgcap_lstm2/bias"), W("imgcap_lstm_d1/bias"), U,
+                                                           kDense, b.b1_i, b.b2_i, b.bias_hoist + 4 * U);
     DC_CHECK_LAUNCH();
     return DC_OK;
 }

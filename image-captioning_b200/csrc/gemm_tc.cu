@@ -1052,7 +1052,10 @@ int gemm_bf16_tc(const TcOperand &A, const TcOperand &B, const TcEpilogue &ep, i
     // (read per call so that the tests can hold both kernel families to the same small and ragged shapes)
     const char *two_cta_str = getenv("DCAP_2CTA");
     const int two_cta_env = two_cta_str ? atoi(two_cta_str) : -1;                            // 0 = off, n = minimum number of pair tiles
-    const int two_cta_min = two_cta_env >= 0 ? two_cta_env : (sms + 7) / 8;
+    // (accumulating weight-gradient GEMMs are split along K into ~2 waves of work units whatever their tile count: they
+    // keep the pair kernel -- with the rule applied to them the 4096-row step measured 0.1 ms slower)
+    const bool splittable = epi == kEpiStore && ep.atomic && ep.out_f32 && !ep.out_bf16;
+    const int two_cta_min = two_cta_env >= 0 ? two_cta_env : (splittable ? 1 : (sms + 7) / 8);
     const int tiles2 = ceil_div(M, 256) * ceil_div(N, 256);
     const bool two_cta = two_cta_min != 0 && N >= 256 && tiles2 >= two_cta_min;
     if (epi == kEpiStore && ep.atomic && ep.out_f32 && !ep.out_bf16) {
