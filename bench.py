@@ -174,6 +174,20 @@ def tap_unique_pixels(boxes, levels, fm_shapes, pool):
     return int(total)
 
 
+
+def l2_path(tap_pixels, out_bytes, ms, sm_mhz):
+    """Why ROIAlign stops short of the HBM roofline: every bilinear tap (4 per sample, 196 per RoI) crosses the L2 -> SM
+    fabric even when DRAM serves each distinct pixel once (overlapping RoIs share taps 3.5x at cfg2), and the stores cross
+    it too.  The fabric's measured ceiling is ~6300 B per clock for the whole chip whatever the access path
+    (/opt/skills/guides/B300_MICROARCH.md, "LTS throughput cap"; measured there on B300 -- the same L2 slice count).
+    Returns that traffic (before the ~13 % the L1 filters, profiles/r2_roi_align_full.txt) against the cap at the SM clock
+    sampled during the run."""
+    tap_bytes = int(tap_pixels) * 4 * CHANNELS
+    cap_tbs = 6300.0 * (sm_mhz or 1965.0) * 1e6 / 1e12
+    tbs = (tap_bytes + out_bytes) / (ms * 1e-3) / 1e12
+    return {"tap_bytes": tap_bytes, "out_bytes": int(out_bytes), "achieved_tbs": round(tbs, 2), "cap_tbs": round(cap_tbs, 2),
+            "frac": round(tbs / cap_tbs, 3), "note": "taps + stores through the L2 -> SM fabric against its ~6300 B/clk ceiling"}
+
 def dist_env():
     return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
             int(os.environ.get("WORLD_SIZE", 1)))
@@ -325,7 +339,8 @@ def run_ours_roi_features(args, ctx):
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
                 "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
-                "t_unique_pixels": t_unique, "kernel_ms": round(k_ms, 5)}
+                "t_unique_pixels": t_unique, "kernel_ms": round(k_ms, 5),
+                "l2_path": l2_path(4 * POOL[0] * POOL[1] * B * N, 4 * CHANNELS * POOL[0] * POOL[1] * B * N, k_ms, (clocks or {}).get("sm_mhz"))}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
@@ -579,7 +594,8 @@ def run_ours_captions(args, ctx):
                     "achieved": round(achieved_gb, 1), "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
                     "frac": round(achieved_gb / hbm_peak, 4), "frac_of_nominal_8000": round(achieved_gb / 8000.0, 4),
                     "traffic": None, "algorithmic_bytes_per_step": alg_bytes, "t_unique_pixels": t_unique,
-                    "roi_align_ms": round(roi_ms, 4), "share_of_step": round(roi_ms / (roi_ms + dec_ms), 3)}
+                    "roi_align_ms": round(roi_ms, 4), "share_of_step": round(roi_ms / (roi_ms + dec_ms), 3),
+                    "l2_path": l2_path(4 * POOL[0] * POOL[1] * R, 2 * CHANNELS * POOL[0] * POOL[1] * R, roi_ms, (clocks or {}).get("sm_mhz"))}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
