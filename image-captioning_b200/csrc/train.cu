@@ -505,6 +505,9 @@ __global__ void __launch_bounds__(kXentThreads, 2) softmax_xent_colsum_kernel(__
         };
         if (rows == G) passes(std::true_type{});
         else passes(std::false_type{});
+        // pass B wrote into the slot through the generic proxy and the next bulk copy into it goes through the async proxy:
+        // order the two before the barrier that releases the slot
+        fence_async_smem();
         __syncthreads();                                   // every read of slot b (and of st_*) is done: it may be refilled
     }
 #pragma unroll
