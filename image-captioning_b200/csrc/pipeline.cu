@@ -5,6 +5,8 @@
 // the bf16 decoder consumes the ROIAlign output directly in bf16 (half the feature traffic).
 #include "decoder.cuh"
 
+#include <string.h>
+
 using namespace dcap;
 
 extern "C" int dc_caption_rois(DcDecoder *dec, const float *boxes, const float *const fmaps[4],
@@ -38,7 +40,7 @@ extern "C" int dc_caption_rois(DcDecoder *dec, const float *boxes, const float *
 //
 // The pipeline state (two streams, events, two pyramid slots, per-call box / token staging) lives in the decoder
 // handle and is reused by every call.  submit() only enqueues; wait() blocks until the OLDEST outstanding call's
-// tokens are on the host.  With two calls outstanding the upload of call k+1 runs under the decode tail of call k
+// tokens are on the host (they land in pinned staging memory and wait() copies them into the caller's array).  With two calls outstanding the upload of call k+1 runs under the decode tail of call k
 // (the last image of a call cannot be decoded before its pyramid has landed, so a single blocking call always
 // exposes one image's decode: 14.6 ms against the 12.9 ms copy floor at 8 x 1000 RoIs).
 // These entry points take no caller stream: they order against their own streams only.  Work the caller has
@@ -53,6 +55,12 @@ struct HostPipe {
     size_t fm_cap[4] = {0, 0, 0, 0};
     float *boxes[2] = {nullptr, nullptr};
     int32_t *tok[2] = {nullptr, nullptr};
+    // pinned staging of a call's token ids: a device -> host copy straight into the caller's (usually pageable) array
+    // would make cudaMemcpyAsync block until the whole call has run, and the "two calls in flight" would never overlap
+    float *box_host[2] = {nullptr, nullptr};              // the (small) box array is staged too: callers pass pageable numpy arrays
+    int32_t *tok_host[2] = {nullptr, nullptr};
+    int32_t *tok_user[2] = {nullptr, nullptr};
+    size_t tok_bytes[2] = {0, 0};
     size_t box_cap[2] = {0, 0}, tok_cap[2] = {0, 0};
     long long images = 0;        // pyramid-slot uses so far (slot = images & 1)
     long long submitted = 0, waited = 0;
@@ -64,6 +72,8 @@ struct HostPipe {
             for (int l = 0; l < 4; ++l) if (fm[i][l]) cudaFree(fm[i][l]);
             if (boxes[i]) cudaFree(boxes[i]);
             if (tok[i]) cudaFree(tok[i]);
+            if (tok_host[i]) cudaFreeHost(tok_host[i]);
+            if (box_host[i]) cudaFreeHost(box_host[i]);
             for (cudaEvent_t e : {up[i], done[i], finished[i]}) if (e) cudaEventDestroy(e);
         }
         if (copy) cudaStreamDestroy(copy);
@@ -92,6 +102,8 @@ extern "C" int dc_caption_rois_host_wait(DcDecoder *dec) {
     hp->waited++;
     const cudaError_t e = cudaEventSynchronize(hp->finished[slot]);
     if (e != cudaSuccess) return set_error(DC_ERR_CUDA, "caption pipeline failed: %s", cudaGetErrorString(e));
+    if (hp->tok_user[slot] && hp->tok_bytes[slot]) memcpy(hp->tok_user[slot], hp->tok_host[slot], hp->tok_bytes[slot]);
+    hp->tok_user[slot] = nullptr;
     return DC_OK;
 }
 
@@ -145,13 +157,24 @@ extern "C" int dc_caption_rois_host_submit(DcDecoder *dec, const float *boxes, c
                 }
                 hp.fm_cap[l] = cap;
             }
+        if (hp.box_cap[cs] < sizeof(float) * 4 * (size_t)R) {
+            if (hp.box_host[cs]) cudaFreeHost(hp.box_host[cs]);
+            hp.box_host[cs] = nullptr;
+            DC_CHECK_CUDA(cudaHostAlloc((void **)&hp.box_host[cs], sizeof(float) * 4 * (size_t)R, cudaHostAllocDefault));
+        }
         if (int rc = pipe_grow((void **)&hp.boxes[cs], &hp.box_cap[cs], sizeof(float) * 4 * (size_t)R)) return rc;
+        if (hp.tok_cap[cs] < sizeof(int32_t) * (size_t)R * P) {
+            if (hp.tok_host[cs]) cudaFreeHost(hp.tok_host[cs]);
+            hp.tok_host[cs] = nullptr;
+            DC_CHECK_CUDA(cudaHostAlloc((void **)&hp.tok_host[cs], sizeof(int32_t) * (size_t)R * P, cudaHostAllocDefault));
+        }
         if (int rc = pipe_grow((void **)&hp.tok[cs], &hp.tok_cap[cs], sizeof(int32_t) * (size_t)R * P)) return rc;
         if (int rc = D.reserve(n_boxes)) return rc;
         void *unused = nullptr;
         if (int rc = D.roi_feature_buffer(n_boxes, &unused)) return rc;
     }
-    DC_CHECK_CUDA(cudaMemcpyAsync(hp.boxes[cs], boxes, sizeof(float) * 4 * (size_t)R, cudaMemcpyHostToDevice, hp.copy));
+    memcpy(hp.box_host[cs], boxes, sizeof(float) * 4 * (size_t)R);       // slot cs is free: its previous call has been waited for
+    DC_CHECK_CUDA(cudaMemcpyAsync(hp.boxes[cs], hp.box_host[cs], sizeof(float) * 4 * (size_t)R, cudaMemcpyHostToDevice, hp.copy));
     for (int img = 0; img < n_images; ++img) {
         const int s = (int)(hp.images & 1);
         if (hp.used[s]) DC_CHECK_CUDA(cudaStreamWaitEvent(hp.copy, hp.done[s], 0));   // the slot's previous image is decoded
@@ -167,7 +190,9 @@ extern "C" int dc_caption_rois_host_submit(DcDecoder *dec, const float *boxes, c
         hp.used[s] = true;
         hp.images++;
     }
-    DC_CHECK_CUDA(cudaMemcpyAsync(tokens, hp.tok[cs], sizeof(int32_t) * (size_t)R * P, cudaMemcpyDeviceToHost, hp.compute));
+    hp.tok_user[cs] = tokens;
+    hp.tok_bytes[cs] = sizeof(int32_t) * (size_t)R * P;
+    DC_CHECK_CUDA(cudaMemcpyAsync(hp.tok_host[cs], hp.tok[cs], hp.tok_bytes[cs], cudaMemcpyDeviceToHost, hp.compute));
     DC_CHECK_CUDA(cudaEventRecord(hp.finished[cs], hp.compute));
     hp.submitted++;
     return DC_OK;

@@ -322,7 +322,10 @@ int dc_caption_rois_host(DcDecoder *dec, const float *boxes, const float *const 
  * token download of one call and returns; wait() blocks until the OLDEST outstanding call's tokens are on the
  * host.  At most two calls are outstanding (a third submit first retires the oldest); host buffers of a submitted
  * call must stay valid and unmodified until its wait() returns.  With two in flight, call k+1's upload runs under
- * call k's last-image decode. */
+ * call k's last-image decode.  `boxes` and `tokens` may be pageable (numpy arrays): boxes are copied into pinned
+ * staging inside submit(), token ids land in pinned staging and wait() copies them into `tokens` -- a device -> host
+ * copy straight into pageable memory would block submit() until the whole call had run.  The feature maps are not
+ * staged (89 MB per image): pin them, or the uploads serialise with the host. */
 int dc_caption_rois_host_submit(DcDecoder *dec, const float *boxes, const float *const fmaps[4],
                          const int fm_h[4], const int fm_w[4], int n_images, int n_boxes, int img_h,
                          int img_w, int32_t *tokens);
