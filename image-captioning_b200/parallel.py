@@ -55,6 +55,88 @@ def gather_rows(local, total_rows, group=None):
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], 0)
 
 
+class HostBatchPrefetcher(object):
+    """Uploads training batches from host memory one step ahead of the step that consumes them -- the device-side half of
+    what ``fit_generator(..., max_queue_size=, workers=)`` does for the reference (text_generation_model.py:470-472: Keras
+    keeps a queue of generator batches filled while the previous batch trains).
+
+    ``put(*host_tensors)`` copies a batch into one of ``depth`` device slots on a private copy stream (pinned host tensors
+    make the copies asynchronous; the host tensors must stay unmodified until the matching ``get``); ``get()`` makes the
+    CURRENT stream wait for the oldest uploaded batch and returns its device tensors; ``done()`` marks them consumed by
+    everything enqueued on the current stream so far, which is what lets ``put`` reuse the slot.  Loop::
+
+        pf.put(feats0, gt0)
+        for k in range(steps):
+            if k + 1 < steps: pf.put(*batch(k + 1))     # rides under step k's kernels
+            d_feats, d_gt = pf.get()
+            loss = trainer.train_step(d_feats, d_gt, None, npos); pf.done()
+
+    Measured on cfg3 (205 MB of fp32 RoI features per 4096-RoI step, 3.7 ms over PCIe against a 7.7 ms step): see
+    bench.py --workload train, ``e2e``.  On a CPU device the copies are plain synchronous copies (gloo tests)."""
+
+    def __init__(self, device, depth=2):
+        self.device = torch.device(device)
+        self.depth = int(depth)
+        if self.depth < 1:
+            raise ValueError("depth must be >= 1")
+        self._cuda = self.device.type == "cuda"
+        self._copy = torch.cuda.Stream(device=self.device) if self._cuda else None
+        self._bufs = [None] * self.depth
+        self._ready = [None] * self.depth
+        self._consumed = [None] * self.depth
+        self._n_put = self._n_get = 0
+        self._last = None
+
+    def pending(self):
+        """Batches uploaded (or uploading) and not yet handed out."""
+        return self._n_put - self._n_get
+
+    def put(self, *host_tensors):
+        if self.pending() >= self.depth:
+            raise RuntimeError("all %d slots hold batches that were not fetched yet: call get() first" % self.depth)
+        slot = self._n_put % self.depth
+        hts = [torch.as_tensor(h) for h in host_tensors]
+        bufs = self._bufs[slot]
+        if bufs is None or len(bufs) != len(hts) or any(b.shape != h.shape or b.dtype != h.dtype for b, h in zip(bufs, hts)):
+            if self._cuda and self._consumed[slot] is not None:
+                self._consumed[slot].synchronize()          # the old buffers may still be read: do not free them under it
+            bufs = [torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in hts]
+            self._bufs[slot] = bufs
+            if self._cuda:                                  # the allocator may hand out memory the current stream still uses
+                self._copy.wait_stream(torch.cuda.current_stream(self.device))
+        if self._cuda:
+            with torch.cuda.stream(self._copy):
+                if self._consumed[slot] is not None:
+                    self._copy.wait_event(self._consumed[slot])
+                for b, h in zip(bufs, hts):
+                    b.copy_(h, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy)
+            self._ready[slot] = ev
+        else:
+            for b, h in zip(bufs, hts):
+                b.copy_(h)
+        self._n_put += 1
+
+    def get(self):
+        if self.pending() <= 0:
+            raise RuntimeError("get() without a batch in flight: call put() first")
+        slot = self._n_get % self.depth
+        if self._cuda:
+            torch.cuda.current_stream(self.device).wait_event(self._ready[slot])
+        self._n_get += 1
+        self._last = slot
+        return tuple(self._bufs[slot])
+
+    def done(self):
+        if self._last is None:
+            raise RuntimeError("done() before get()")
+        if self._cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._consumed[self._last] = ev
+
+
 class DataParallelTrainer(object):
     """Data-parallel ``train_on_batch`` over the ranks of ``group``.
 

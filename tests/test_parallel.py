@@ -136,3 +136,29 @@ def test_sharded_optimizer_equals_single_process():
         np.testing.assert_allclose(losses, ref_losses, rtol=1e-12)
         torch.testing.assert_close(w, ref.w, rtol=1e-12, atol=1e-12)
     torch.testing.assert_close(out[0][1], out[1][1], rtol=0, atol=0)
+
+
+def test_host_batch_prefetcher_order_and_slot_reuse():
+    """put / get / done bookkeeping on a CPU device (synchronous copies): batches come back in the order they were put,
+    a slot is reused only after its batch was fetched, shapes may change between batches."""
+    from image_captioning_b200.parallel import HostBatchPrefetcher
+    pf = HostBatchPrefetcher("cpu", depth=2)
+    with pytest.raises(RuntimeError):
+        pf.get()
+    with pytest.raises(RuntimeError):
+        pf.done()
+    batches = [(torch.full((3, 4), float(i)), torch.arange(5, dtype=torch.int32) + i) for i in range(5)]
+    batches.append((torch.full((2, 7), 9.0), torch.arange(3, dtype=torch.int32)))         # a last, smaller batch
+    pf.put(*batches[0])
+    for k in range(len(batches)):
+        if k + 1 < len(batches):
+            pf.put(*batches[k + 1])
+            assert pf.pending() == 2
+            with pytest.raises(RuntimeError):
+                pf.put(*batches[k + 1])                     # both slots hold unfetched batches
+        a, b = pf.get()
+        assert torch.equal(a, batches[k][0]) and torch.equal(b, batches[k][1])
+        pf.done()
+    assert pf.pending() == 0
+    with pytest.raises(ValueError):
+        HostBatchPrefetcher("cpu", depth=0)

@@ -440,3 +440,40 @@ def test_fused_softmax_xent_bias_gradient_equals_the_two_kernel_form(B, V, monke
     # (2^-9 relative per element), and so does every gradient computed from them
     for name in g0:
         assert np.isfinite(g1[name]).all() and _rel_l2(g1[name], g0[name]) <= 6e-3, (name, _rel_l2(g1[name], g0[name]))
+
+
+def test_prefetched_batches_train_like_directly_fed_ones():
+    """parallel.HostBatchPrefetcher: batches uploaded one step ahead on the copy stream (different data every step, the
+    two slots reused three times) give the same losses and the same final weights as the same batches fed directly."""
+    import image_captioning_b200 as pkg
+    from image_captioning_b200.parallel import DataParallelTrainer, HostBatchPrefetcher
+    B, steps = 64, 6
+    rng = np.random.default_rng(5)
+    w = synth.synth_weights_v1(rng, trained_like=False, **SHAPE)
+    feats = [torch.from_numpy(rng.standard_normal((B, 7, 7, SHAPE["C"])).astype(np.float32)).pin_memory() for _ in range(steps)]
+    gts = [torch.from_numpy(synth.synth_captions(rng, B, P, SHAPE["V"]).astype(np.int32)).pin_memory() for _ in range(steps)]
+    npos = float(B * P)
+    res = {}
+    for mode in ("direct", "prefetch"):
+        cfg = pkg.DenseCapConfig(SHAPE["V"], w["imgcap_embedding_layer/embeddings"], B, P)
+        m = pkg.build_lstm_model([7, 7, SHAPE["C"]], cfg, SHAPE["U"], "training", dtype="bfloat16")
+        m.set_weights(w)
+        m.compile(optimizer=pkg.Adam(amsgrad=True), loss=pkg.roi_caption_loss)
+        tr = DataParallelTrainer(m)
+        losses = []
+        if mode == "direct":
+            for k in range(steps):
+                losses.append(tr.train_step(feats[k].cuda(), gts[k].cuda(), None, npos))
+        else:
+            pf = HostBatchPrefetcher(torch.device("cuda"))
+            pf.put(feats[0], gts[0])
+            for k in range(steps):
+                if k + 1 < steps:
+                    pf.put(feats[k + 1], gts[k + 1])
+                d_f, d_g = pf.get()
+                losses.append(tr.train_step(d_f, d_g, None, npos))
+                pf.done()
+        res[mode] = ([float(l.item()) for l in losses], m.get_weights_dict())
+    assert res["direct"][0] == res["prefetch"][0], (res["direct"][0], res["prefetch"][0])
+    for name, v in res["direct"][1].items():
+        assert np.array_equal(v, res["prefetch"][1][name]), name
