@@ -822,7 +822,7 @@ def run_ours_train(args, ctx):
                                 else "replicated on every rank",
                    "l2": "activations larger than L2 (logits %d MB per rank)" % (Bl * TRAIN_P * VOCAB * 4 // 2 ** 20),
                    "sm_count": sms, "cc": cc, "loss_first": round(loss_hist[0], 4), "loss_last": round(loss_hist[-1], 4)},
-        "clocks": clocks, "gpu_launches": K * 144,      # profiles/r1_launches_train.txt
+        "clocks": clocks, "gpu_launches": K * 132,      # profiles/r2_launches_train_final.txt
         "roofline": tensor_roofline(achieved, total_ms * 1e-3,
                                     kernel="gemm_bf16_tc2_kernel (forward scan + time-batched dense/vocab GEMMs + dgrad/wgrad GEMMs)",
                                     algorithmic_flops_per_step_per_rank=flops,
@@ -857,7 +857,7 @@ def run_ours_train(args, ctx):
                          "optimizer_ms": round(opt_ms, 4),
                          "allreduce_exposed_plus_gaps_ms": round(max(0.0, ms_per_step - fb_ms - opt_ms), 4),
                          "allreduce_bytes": int(model.grad_buffer().numel() * 4) if world > 1 else 0,
-                         "kernel_launches_per_step": 144 + (5 if world > 1 else 0),
+                         "kernel_launches_per_step": 132 + (5 if world > 1 else 0),
                          "note": "per-rank batch %d: the %d recurrent step kernels run %d-row GEMMs" % (Bl, 6 * TRAIN_P, Bl)}
     if not args.no_e2e:
         e2e_steps = max(1, min(K, args.e2e_steps))

@@ -444,7 +444,7 @@ def test_fused_softmax_xent_bias_gradient_equals_the_two_kernel_form(B, V, monke
 
 def test_prefetched_batches_train_like_directly_fed_ones():
     """parallel.HostBatchPrefetcher: batches uploaded one step ahead on the copy stream (different data every step, the
-    two slots reused three times) give the same losses and the same final weights as the same batches fed directly."""
+    two slots reused three times) give the losses and final weights of the same batches fed directly."""
     import image_captioning_b200 as pkg
     from image_captioning_b200.parallel import DataParallelTrainer, HostBatchPrefetcher
     B, steps = 64, 6
@@ -474,6 +474,7 @@ def test_prefetched_batches_train_like_directly_fed_ones():
                 losses.append(tr.train_step(d_f, d_g, None, npos))
                 pf.done()
         res[mode] = ([float(l.item()) for l in losses], m.get_weights_dict())
-    assert res["direct"][0] == res["prefetch"][0], (res["direct"][0], res["prefetch"][0])
+    # (not bit for bit: split-K and bias-gradient atomics sum in a different order from run to run)
+    np.testing.assert_allclose(res["prefetch"][0], res["direct"][0], rtol=1e-5)
     for name, v in res["direct"][1].items():
-        assert np.array_equal(v, res["prefetch"][1][name]), name
+        np.testing.assert_allclose(res["prefetch"][1][name], v, rtol=2e-3, atol=2e-6, err_msg=name)
