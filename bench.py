@@ -1250,8 +1250,8 @@ def sub_records(args, ctx):
     cfg4 (beam, rows split over ranks) and cfg5 (5000 x 300 end to end)."""
     import copy
     out = {}
-    plan = [("roi_features", run_ours_roi_features, dict(steps=20, warmup=3, e2e_steps=2)),
-            ("train", run_ours_train, dict(steps=6, warmup=3, e2e_steps=2)),
+    plan = [("roi_features", run_ours_roi_features, dict(steps=20, warmup=3, e2e_steps=4)),
+            ("train", run_ours_train, dict(steps=10, warmup=3, e2e_steps=8)),       # 8 steps: the un-overlapped first upload is 1/8 of the leg
             ("beam", run_ours_beam, dict(steps=1, warmup=1, e2e_steps=1)),
             ("captions_vg", run_ours_captions_vg, dict(steps=2, warmup=1, e2e_steps=1))]
     for name, fn, over in plan:
