@@ -9,6 +9,8 @@ callers use -- ``predict``, ``get_weights`` / ``set_weights`` / ``load_weights``
 kernels behind the C ABI (include/dcap.h).  No TensorFlow, no CPU fallback.
 """
 import ctypes
+import queue
+import threading
 
 import numpy as np
 import torch
@@ -77,6 +79,72 @@ def roi_caption_loss(y_true=None, y_pred=None):
     """Marker for compile(loss=roi_caption_loss) (text_generation_model.py:286-294).  The loss is
     evaluated inside the fused training step (dc_decoder_train_step); it is not a host function."""
     raise NotImplementedError("roi_caption_loss is fused into the training step; use train_on_batch / evaluate")
+
+
+class GeneratorQueue(object):
+    """What Keras puts behind ``fit_generator(generator, max_queue_size=, workers=)`` (GeneratorEnqueuer; the reference
+    trains with max_queue_size=100 and the default single worker, text_generation_model.py:470-472): a background thread
+    that keeps up to ``max_queue_size`` batches of the generator ready while the previous batch trains.  One worker thread,
+    so batches arrive in generator order; ``workers=0`` pulls from the generator on the calling thread, as Keras does.
+    The generator's numpy work overlaps the training step because the step's host side is mostly a wait on the device
+    (which releases the GIL).  Exceptions raised by the generator -- StopIteration included -- surface from ``get()``."""
+
+    _END = object()
+
+    def __init__(self, generator, max_queue_size=10, workers=1):
+        self._gen = generator
+        self._thread = None
+        if workers and workers > 0:
+            self._q = queue.Queue(maxsize=max(1, int(max_queue_size)))
+            self._stop = threading.Event()
+            self._thread = threading.Thread(target=self._fill, name="dcap-generator-queue", daemon=True)
+            self._thread.start()
+
+    def _fill(self):
+        try:
+            while not self._stop.is_set():
+                try:
+                    item = (True, next(self._gen))
+                except BaseException as e:                  # StopIteration too: hand it to the consumer and end
+                    item = (False, e)
+                while not self._stop.is_set():
+                    try:
+                        self._q.put(item, timeout=0.05)
+                        break
+                    except queue.Full:
+                        continue
+                if not item[0]:
+                    return
+        finally:
+            pass
+
+    def get(self):
+        if self._thread is None:
+            return next(self._gen)
+        ok, item = self._q.get()
+        if not ok:
+            self._q.put((False, item))                      # every later get() raises again
+            raise item
+        return item
+
+    def close(self):
+        """Stop the worker (the batches it had queued are dropped -- Keras' enqueuer.stop())."""
+        if self._thread is not None:
+            self._stop.set()
+            try:
+                while True:
+                    self._q.get_nowait()
+            except queue.Empty:
+                pass
+            self._thread.join(timeout=5.0)
+            self._thread = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
 
 class History(object):
@@ -616,26 +684,29 @@ class RoiCaptionModel(_ModelBase):
         for cb in callbacks or []:
             if hasattr(cb, "set_model"):
                 cb.set_model(self)
-        for epoch in range(initial_epoch, epochs):
-            losses = []
-            for _ in range(steps_per_epoch):
-                x, y = next(generator)[:2]
-                losses.append(self.train_on_batch(x, y))
-            logs = {"loss": float(np.mean(losses))}
-            if validation_data is not None:
-                if isinstance(validation_data, (tuple, list)):
-                    logs["val_loss"] = self.test_on_batch(validation_data[0], validation_data[1])
-                else:
-                    vs = [self.test_on_batch(*next(validation_data)[:2]) for _ in range(validation_steps or 1)]
-                    logs["val_loss"] = float(np.mean(vs))
-            hist.epoch.append(epoch)
-            for k, v in logs.items():
-                hist.history.setdefault(k, []).append(v)
-            if verbose:
-                print("Epoch %d/%d - " % (epoch + 1, epochs) + " - ".join("%s: %.4f" % kv for kv in logs.items()))
-            for cb in callbacks or []:
-                if hasattr(cb, "on_epoch_end"):
-                    cb.on_epoch_end(epoch, logs)
+        # max_queue_size / workers as in Keras: a worker thread keeps the next batches of the generator ready while the
+        # current one trains (workers=0: the generator runs on this thread); use_multiprocessing is accepted and ignored
+        with GeneratorQueue(generator, max_queue_size, workers) as batches:
+            for epoch in range(initial_epoch, epochs):
+                losses = []
+                for _ in range(steps_per_epoch):
+                    x, y = batches.get()[:2]
+                    losses.append(self.train_on_batch(x, y))
+                logs = {"loss": float(np.mean(losses))}
+                if validation_data is not None:
+                    if isinstance(validation_data, (tuple, list)):
+                        logs["val_loss"] = self.test_on_batch(validation_data[0], validation_data[1])
+                    else:
+                        vs = [self.test_on_batch(*next(validation_data)[:2]) for _ in range(validation_steps or 1)]
+                        logs["val_loss"] = float(np.mean(vs))
+                hist.epoch.append(epoch)
+                for k, v in logs.items():
+                    hist.history.setdefault(k, []).append(v)
+                if verbose:
+                    print("Epoch %d/%d - " % (epoch + 1, epochs) + " - ".join("%s: %.4f" % kv for kv in logs.items()))
+                for cb in callbacks or []:
+                    if hasattr(cb, "on_epoch_end"):
+                        cb.on_epoch_end(epoch, logs)
         return hist
 
     def head_features(self, features):
