@@ -67,6 +67,7 @@ constexpr int kMaxKmajorJobs = 12;
 struct KmajorJob {
     const float *src; __nv_bfloat16 *dst; long long ld_dst;
     int n_src, row_off, K, N, interleave_units, k_off, tiles_k, first_block;
+    int pair_ok;                 // destination rows start on 4-byte boundaries: bf16 pairs can be stored as one word
 };
 struct KmajorBatch {
     KmajorJob job[kMaxKmajorJobs];
@@ -75,29 +76,41 @@ struct KmajorBatch {
              int k_off) {
         KmajorJob &j = job[n++];
         j.src = src; j.dst = dst; j.ld_dst = ld_dst; j.n_src = n_src; j.row_off = row_off; j.K = K; j.N = N;
-        j.interleave_units = interleave_units; j.k_off = k_off; j.tiles_k = ceil_div(K, 32); j.first_block = blocks;
+        j.interleave_units = interleave_units; j.k_off = k_off; j.tiles_k = ceil_div(K, 64); j.first_block = blocks;
+        j.pair_ok = (ld_dst % 2 == 0 && k_off % 2 == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) ? 1 : 0;
         blocks += j.tiles_k * ceil_div(N, 32);
     }
 };
 
+// 64 (k) x 32 (n) tiles: reads run along n (whole 32-byte sectors, also through the gate interleave), writes along k as
+// bf16 pairs (128 bytes per warp instruction; the 32 x 32 tiles of build_kmajor_kernel write 64)
 __global__ void __launch_bounds__(256) build_kmajor_batch_kernel(const __grid_constant__ KmajorBatch batch) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[64][33];
     int ji = 0;
     while (ji + 1 < batch.n && (int)blockIdx.x >= batch.job[ji + 1].first_block) ++ji;
     const KmajorJob &j = batch.job[ji];
     const int local = blockIdx.x - j.first_block;
-    const int k0 = (local % j.tiles_k) * 32, n0 = (local / j.tiles_k) * 32;
+    const int k0 = (local % j.tiles_k) * 64, n0 = (local / j.tiles_k) * 32;
     const int n = n0 + threadIdx.x;
     const int col = j.interleave_units ? (n & 3) * j.interleave_units + (n >> 2) : n;
-    for (int i = threadIdx.y; i < 32; i += 8) {
+#pragma unroll
+    for (int i = threadIdx.y; i < 64; i += 8) {
         const int k = k0 + i;
         tile[i][threadIdx.x] = (k < j.K && n < j.N) ? j.src[(long long)(j.row_off + k) * j.n_src + col] : 0.f;
     }
     __syncthreads();
-    const int k = k0 + threadIdx.x;
+    const int k = k0 + 2 * threadIdx.x;
+#pragma unroll
     for (int i = threadIdx.y; i < 32; i += 8) {
         const int nn = n0 + i;
-        if (k < j.K && nn < j.N) j.dst[(long long)nn * j.ld_dst + j.k_off + k] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+        if (nn >= j.N || k >= j.K) continue;
+        __nv_bfloat16 *d = j.dst + (long long)nn * j.ld_dst + j.k_off + k;
+        if (k + 1 < j.K && j.pair_ok)
+            *reinterpret_cast<__nv_bfloat162 *>(d) = __floats2bfloat162_rn(tile[2 * threadIdx.x][i], tile[2 * threadIdx.x + 1][i]);
+        else {
+            d[0] = __float2bfloat16_rn(tile[2 * threadIdx.x][i]);
+            if (k + 1 < j.K) d[1] = __float2bfloat16_rn(tile[2 * threadIdx.x + 1][i]);
+        }
     }
 }
 
