@@ -47,3 +47,15 @@ def test_default_arm_line():
     assert d["gpu_launches"] == 3 * 9 and d["config"]["public_api_matches"] is True
     assert d["config"]["token_agreement_with_launch_per_gemm_path"] == 1.0
     assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_l2_path_helper():
+    """roofline_hbm.l2_path: taps + stores against the L2 -> SM fabric ceiling (6300 B per clock at the sampled SM clock)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.l2_path(tap_pixels=4 * 49 * 8000, out_bytes=2 * 256 * 49 * 8000, ms=0.16, sm_mhz=1965.0)
+    assert r["tap_bytes"] == 4 * 49 * 8000 * 4 * 256 and r["out_bytes"] == 2 * 256 * 49 * 8000
+    assert abs(r["cap_tbs"] - 6300 * 1965e6 / 1e12) < 0.01
+    assert abs(r["achieved_tbs"] - (r["tap_bytes"] + r["out_bytes"]) / 0.16e-3 / 1e12) < 0.01
+    assert abs(r["frac"] - r["achieved_tbs"] / r["cap_tbs"]) < 2e-3
+    assert bench.l2_path(1, 1, 1.0, None)["cap_tbs"] == round(6300 * 1965e6 / 1e12, 2)      # no clock sample: the part's maximum
