@@ -281,3 +281,44 @@ class DataParallelTrainer(object):
     def train_on_batch(self, x, y=None):
         feats, gt = x
         return float(self.train_step(feats, gt, y).item())
+
+    def fit_generator(self, generator, steps_per_epoch=None, epochs=1, verbose=1, callbacks=None, max_queue_size=10,
+                      workers=1, initial_epoch=0, global_batches=True, **kwargs):
+        """``ParallelModel(model, gpu_count).fit_generator(...)`` of the reference (parallel_model.py:22-102 wraps the
+        Keras model, so the training script's fit_generator call -- text_generation_model.py:470-472 -- feeds ONE
+        generator whose batches tf.split deals over the towers).  Here every rank runs the same generator (same seed)
+        and, with ``global_batches=True``, takes its ``shard_bounds`` rows of every batch -- features, captions and
+        targets alike; ``global_batches=False`` means the generator already yields this rank's shard.  The loss reported
+        per epoch is the global mean (identical on all ranks); callbacks run on rank 0 only (checkpoint / CSV writers).
+        Batches are pulled through the same worker-thread queue as the single-GPU fit_generator."""
+        from .text_model import GeneratorQueue, History
+        if steps_per_epoch is None:
+            raise ValueError("steps_per_epoch is required for a generator")
+        hist = History()
+        cbs = (callbacks or []) if self.rank == 0 else []
+        for cb in cbs:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self.model)
+
+        def mine(a):
+            if a is None or not global_batches:
+                return a
+            lo, hi = shard_bounds(len(a), self.rank, self.world)
+            return a[lo:hi]
+        with GeneratorQueue(generator, max_queue_size, workers) as batches:
+            for epoch in range(initial_epoch, epochs):
+                losses = []
+                for _ in range(steps_per_epoch):
+                    x, y = batches.get()[:2]
+                    feats, gt = x
+                    losses.append(float(self.train_step(mine(feats), mine(gt), mine(y)).item()))
+                logs = {"loss": float(sum(losses) / max(1, len(losses)))}
+                hist.epoch.append(epoch)
+                for k, v in logs.items():
+                    hist.history.setdefault(k, []).append(v)
+                if verbose and self.rank == 0:
+                    print("Epoch %d/%d - " % (epoch + 1, epochs) + " - ".join("%s: %.4f" % kv for kv in logs.items()))
+                for cb in cbs:
+                    if hasattr(cb, "on_epoch_end"):
+                        cb.on_epoch_end(epoch, logs)
+        return hist

@@ -162,3 +162,47 @@ def test_host_batch_prefetcher_order_and_slot_reuse():
     assert pf.pending() == 0
     with pytest.raises(ValueError):
         HostBatchPrefetcher("cpu", depth=0)
+
+
+def _global_batches(n_batches, rows, dim, P, seed=11):
+    g = torch.Generator().manual_seed(seed)
+    for _ in range(n_batches):
+        yield ([torch.randn(rows, dim, generator=g, dtype=torch.float64), torch.randn(rows, P, generator=g, dtype=torch.float64)], None)
+
+
+def _fit_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = _StubModel(6, 4)
+        tr = parallel.DataParallelTrainer(model)
+        seen = []
+
+        class Cb(object):
+            def on_epoch_end(self, epoch, logs):
+                seen.append((epoch, logs["loss"]))
+        hist = tr.fit_generator(_global_batches(6, 9, 6, 4), steps_per_epoch=3, epochs=2, verbose=0, callbacks=[Cb()],
+                                max_queue_size=2, workers=1)
+        out[rank] = (hist.history["loss"], model.w.clone(), seen)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fit_generator_deals_global_batches_over_the_ranks():
+    """DataParallelTrainer.fit_generator: every rank runs the same generator of GLOBAL batches (9 rows: shards of 5 + 4) and
+    trains on its rows; losses and weights equal single-process training on the whole batches; callbacks on rank 0 only."""
+    ref = _StubModel(6, 4)
+    ref_hist = parallel.DataParallelTrainer(ref).fit_generator(_global_batches(6, 9, 6, 4), steps_per_epoch=3, epochs=2,
+                                                                verbose=0, workers=0)
+    assert len(ref_hist.history["loss"]) == 2 and ref.steps == 6
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_fit_worker, args=(world, port, out), nprocs=world, join=True)
+    for r in range(world):
+        losses, w, seen = out[r]
+        np.testing.assert_allclose(losses, ref_hist.history["loss"], rtol=1e-12)
+        torch.testing.assert_close(w, ref.w, rtol=1e-12, atol=1e-12)
+        assert len(seen) == (2 if r == 0 else 0)
+    with pytest.raises(ValueError):
+        parallel.DataParallelTrainer(_StubModel(6, 4)).fit_generator(_global_batches(1, 9, 6, 4))
