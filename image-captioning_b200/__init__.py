@@ -14,3 +14,4 @@ from .postprocess import refine_generations, caption_text    # noqa: F401
 from .proposals import ProposalLayer, ProposalConfig, generate_pyramid_anchors, normalize_boxes   # noqa: F401
 from . import parallel    # noqa: F401
 from . import data    # noqa: F401
+from . import callbacks    # noqa: F401

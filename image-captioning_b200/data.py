@@ -262,6 +262,27 @@ def load_keras_h5_weights(path):
         return weights_from_h5_group(f)
 
 
+def write_weight_file(path, weights):
+    """{'layer/weight': array} -> an .npz archive keyed by Keras weight name, written EXACTLY at ``path`` whatever its
+    extension: the reference's scripts name their checkpoints ``*.h5`` (ModelCheckpoint(model_filepath, ...),
+    text_generation_model.py:461) and read them back under the same name (:484)."""
+    with open(path, "wb") as f:
+        np.savez(f, **{k.replace("/", "__"): np.asarray(v) for k, v in weights.items()})
+
+
+def read_weight_file(path):
+    """{'layer/weight': array} from a weight file, the format decided by the file's first bytes and not by its name:
+    an .npz archive as written by ``write_weight_file`` / ``save_weights`` (zip magic), or Keras HDF5 (needs h5py)."""
+    with open(path, "rb") as f:
+        magic = f.read(8)
+    if magic == b"\x89HDF\r\n\x1a\n":
+        return load_keras_h5_weights(path)
+    if magic[:2] == b"PK":
+        with np.load(path) as z:
+            return {k.replace("__", "/"): z[k] for k in z.files}
+    raise ValueError("%s is neither an .npz archive nor an HDF5 file" % path)
+
+
 def convert_keras_h5_to_npz(h5_path, npz_path):
     """Offline converter: Keras .h5 weights -> the .npz (keyed by Keras weight name) that load_weights reads."""
     np.savez(npz_path, **{k.replace("/", "__"): v for k, v in load_keras_h5_weights(h5_path).items()})

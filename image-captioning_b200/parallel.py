@@ -299,6 +299,9 @@ class DataParallelTrainer(object):
         for cb in cbs:
             if hasattr(cb, "set_model"):
                 cb.set_model(self.model)
+        for cb in cbs:
+            if hasattr(cb, "on_train_begin"):
+                cb.on_train_begin()
 
         def mine(a):
             if a is None or not global_batches:
@@ -321,4 +324,7 @@ class DataParallelTrainer(object):
                 for cb in cbs:
                     if hasattr(cb, "on_epoch_end"):
                         cb.on_epoch_end(epoch, logs)
+        for cb in cbs:
+            if hasattr(cb, "on_train_end"):
+                cb.on_train_end()
         return hist

@@ -290,20 +290,22 @@ class _ModelBase(object):
     def get_weights_dict(self):
         return {n: self._get_one(n) for n in self.weight_names}
 
-    def save_weights(self, path):
-        """Weights as an .npz keyed by Keras weight name (h5py is not available; the converter
-        from Keras HDF5 is an offline tool)."""
-        np.savez(path, **{n.replace("/", "__"): v for n, v in self.get_weights_dict().items()})
+    def save_weights(self, path, overwrite=True):
+        """Weights as an .npz archive keyed by Keras weight name, written exactly at ``path`` (the reference names its
+        checkpoints *.h5; h5py is not available here, and load_weights tells the formats apart by content)."""
+        from . import data
+        data.write_weight_file(path, self.get_weights_dict())
+
+    def save(self, path, overwrite=True, include_optimizer=False):
+        """keras Model.save as ModelCheckpoint(save_weights_only=False) calls it: these models have no state besides
+        their weights (the optimiser slots are not written), so this is save_weights."""
+        self.save_weights(path)
 
     def load_weights(self, path, by_name=False, skip_mismatch=False):
         """by_name=True loads only the tensors present in the file (as the reference does with
         mask_rcnn_coco.h5 to fill the head, text_generation_model.py:468)."""
-        if str(path).endswith((".h5", ".hdf5")):
-            from . import data                               # Keras HDF5 (needs h5py; raises ImportError without it)
-            found = data.load_keras_h5_weights(path)
-        else:
-            with np.load(path) as z:
-                found = {k.replace("__", "/"): z[k] for k in z.files}
+        from . import data
+        found = data.read_weight_file(path)                  # .npz archive, or Keras HDF5 (needs h5py) -- by content
         for n, v in found.items():
             if n not in self._shapes:
                 if by_name:
@@ -684,6 +686,9 @@ class RoiCaptionModel(_ModelBase):
         for cb in callbacks or []:
             if hasattr(cb, "set_model"):
                 cb.set_model(self)
+        for cb in callbacks or []:
+            if hasattr(cb, "on_train_begin"):
+                cb.on_train_begin()
         # max_queue_size / workers as in Keras: a worker thread keeps the next batches of the generator ready while the
         # current one trains (workers=0: the generator runs on this thread); use_multiprocessing is accepted and ignored
         with GeneratorQueue(generator, max_queue_size, workers) as batches:
@@ -707,6 +712,9 @@ class RoiCaptionModel(_ModelBase):
                 for cb in callbacks or []:
                     if hasattr(cb, "on_epoch_end"):
                         cb.on_epoch_end(epoch, logs)
+        for cb in callbacks or []:
+            if hasattr(cb, "on_train_end"):
+                cb.on_train_end()
         return hist
 
     def head_features(self, features):

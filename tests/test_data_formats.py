@@ -7,6 +7,7 @@ import os
 import pickle
 
 import numpy as np
+import pytest
 
 from image_captioning_b200 import data
 
@@ -140,3 +141,26 @@ def test_keras_h5_group_walker_on_a_stand_in():
             assert "h5py" in str(e)
         else:
             raise AssertionError("expected ImportError without h5py")
+
+
+def test_weight_files_are_told_apart_by_content_not_by_name(tmp_path):
+    """A checkpoint the reference's script names *.h5 (ModelCheckpoint(model_filepath), text_generation_model.py:461) is
+    written as an .npz archive at exactly that path and read back under the same name."""
+    from image_captioning_b200 import data
+    w = {"imgcap_lstm1/kernel": np.arange(12, dtype=np.float32).reshape(3, 4), "mrcnn_class_bn1/gamma": np.ones(5, np.float32)}
+    path = str(tmp_path / "weights-01.h5")
+    data.write_weight_file(path, w)
+    import os
+    assert os.path.exists(path) and not os.path.exists(path + ".npz")
+    back = data.read_weight_file(path)
+    assert set(back) == set(w) and all(np.array_equal(back[k], w[k]) for k in w)
+    junk = str(tmp_path / "junk.h5")
+    with open(junk, "wb") as f:
+        f.write(b"not a weight file")
+    with pytest.raises(ValueError):
+        data.read_weight_file(junk)
+    hdf = str(tmp_path / "real.h5")
+    with open(hdf, "wb") as f:
+        f.write(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(ImportError):                        # HDF5 by content: needs h5py, which this image lacks
+        data.read_weight_file(hdf)
