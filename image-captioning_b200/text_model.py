@@ -47,6 +47,8 @@ class DenseCapConfig(object):
     GPU_COUNT = 1
     IMAGES_PER_GPU = 1
     BATCH_SIZE = 10
+    STEPS_PER_EPOCH = 500
+    VALIDATION_STEPS = 50
     PADDING_SIZE = 10
     POOL_SIZE = 7
 
@@ -58,6 +60,16 @@ class DenseCapConfig(object):
             self.BATCH_SIZE = int(batch_size)
         if padding_size is not None:
             self.PADDING_SIZE = int(padding_size)
+
+    def display(self):
+        """Config.display() as the training scripts call it (config.py:166-172): one line per public attribute.  The
+        embedding matrix is shown by shape, not dumped."""
+        print("\nConfigurations:")
+        for a in dir(self):
+            if not a.startswith("__") and not callable(getattr(self, a)):
+                v = getattr(self, a)
+                print("{:30} {}".format(a, "array%s" % (tuple(v.shape),) if isinstance(v, np.ndarray) else v))
+        print("\n")
 
 
 class Adam(object):

@@ -125,3 +125,14 @@ def test_fit_generator_drives_the_callbacks(tmp_path):
     assert rows[0] == "epoch,loss" and len(rows) == 4
     np.testing.assert_allclose([float(r.split(",")[1]) for r in rows[1:]], hist.history["loss"])
     assert hist.history["loss"][-1] < hist.history["loss"][0]
+
+
+def test_dense_cap_config_surface(capsys):
+    """DenseCapConfig as the scripts use it (text_generation_model.py:23-49, config.display() at :475)."""
+    import image_captioning_b200 as pkg
+    c = pkg.DenseCapConfig(100, np.zeros((100, 8), np.float32), 4)
+    assert (c.VOCABULARY_SIZE, c.EMBEDDING_SIZE, c.BATCH_SIZE, c.PADDING_SIZE) == (100, 8, 4, 10)
+    assert (c.STEPS_PER_EPOCH, c.VALIDATION_STEPS, c.GPU_COUNT, c.IMAGES_PER_GPU) == (500, 50, 1, 1)
+    c.display()
+    out = capsys.readouterr().out
+    assert "Configurations:" in out and "VOCABULARY_SIZE" in out and "array(100, 8)" in out
