@@ -40,6 +40,16 @@ V2_WEIGHT_ORDER = _HEAD + [
     "imgcap_d1/kernel", "imgcap_d1/bias"]
 
 
+def trainable_weight_names(arch):
+    """Names behind Keras' ``model.trainable_weights`` (the training scripts print it: text_generation_model.py:465,
+    text_generation_model_v2.py:305).  v1: everything but the BatchNorm moving statistics and the frozen embedding
+    (text_generation_model.py:130-139, trainable=False).  v2 inject: the RoI head is frozen as well
+    (text_generation_model_v2.py:141-152), so only the two LSTMs and the output layer train."""
+    if arch == ARCH_V1:
+        return [n for n in V1_WEIGHT_ORDER if "/moving_" not in n and not n.endswith("/embeddings")]
+    return [n for n in V2_WEIGHT_ORDER if n not in _HEAD and not n.endswith("/embeddings")]
+
+
 class DenseCapConfig(object):
     """The fields of the reference's DenseCapConfig that the text models read
     (text_generation_model.py:23-49)."""
@@ -345,14 +355,34 @@ class _ModelBase(object):
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    @property
+    def trainable_weights(self):
+        """Keras attribute; here the NAMES of the trainable tensors (get_weights_dict()[name] is the value)."""
+        return trainable_weight_names(self.arch)
+
+    @property
+    def non_trainable_weights(self):
+        t = set(self.trainable_weights)
+        return [n for n in self.weight_names if n not in t]
+
+    @property
+    def weights(self):
+        return self.weight_names
+
+    def count_params(self):
+        return int(sum(int(np.prod(self._shapes[n])) for n in self.weight_names))
+
     def summary(self):
-        total = 0
+        total, trainable = 0, set(self.trainable_weights)
         print("%-40s %-24s %12s" % ("weight", "shape", "params"))
         for n in self.weight_names:
             k = int(np.prod(self._shapes[n]))
             total += k
             print("%-40s %-24s %12d" % (n, self._shapes[n], k))
+        n_train = int(sum(int(np.prod(self._shapes[n])) for n in trainable))
         print("Total params: %d" % total)
+        print("Trainable params: %d" % n_train)
+        print("Non-trainable params: %d" % (total - n_train))
 
     # ---- feature plumbing ----
     def _feats_to_device(self, x):

@@ -136,3 +136,13 @@ def test_dense_cap_config_surface(capsys):
     c.display()
     out = capsys.readouterr().out
     assert "Configurations:" in out and "VOCABULARY_SIZE" in out and "array(100, 8)" in out
+
+
+def test_trainable_weight_names_follow_the_reference_graphs():
+    from image_captioning_b200 import text_model as tm
+    v1 = tm.trainable_weight_names(tm.ARCH_V1)
+    assert len(v1) == 18 and "imgcap_embedding_layer/embeddings" not in v1 and not any("/moving_" in n for n in v1)
+    assert "mrcnn_class_conv1/kernel" in v1 and "mrcnn_class_bn2/gamma" in v1          # the head trains in the v1 graph
+    v2 = tm.trainable_weight_names(tm.ARCH_V2_INJECT)
+    assert v2 == ["lstm_1/kernel", "lstm_1/recurrent_kernel", "lstm_1/bias", "imgcap_lstm/kernel",
+                  "imgcap_lstm/recurrent_kernel", "imgcap_lstm/bias", "imgcap_d1/kernel", "imgcap_d1/bias"]
