@@ -142,6 +142,10 @@ class RegionCaptionDataset(object):
     def add_rois(self, rois):
         self.rois = rois
 
+    def add_sequences(self, sequences):
+        """v2 training sequences (load_sequences) -- text_generation_model_v2.py:95-96."""
+        self.sequences = sequences
+
     def encode_region_caption(self, caption):
         return encode_caption(caption, self.word_to_id, self.tokenizer)
 
@@ -222,6 +226,56 @@ def load_sequences(dataset):
             out.append((image_id, i, [0], cap[0]))
             out.extend((image_id, i, cap[:j], cap[j]) for j in range(1, len(cap)))
     return out
+
+
+def pad_sequences(sequences, maxlen, dtype="int32", value=0):
+    """keras.preprocessing.sequence.pad_sequences with its defaults, as the v2 scripts call it
+    (text_generation_model_v2.py:183, evaluate_models/test_score_dense_captions.py:219): padding='pre',
+    truncating='pre' -- shorter sequences get ``value`` in FRONT, longer ones keep their LAST ``maxlen`` entries."""
+    out = np.full((len(sequences), int(maxlen)), value, dtype=dtype)
+    for i, s in enumerate(sequences):
+        s = list(s)[-int(maxlen):] if maxlen > 0 else []
+        if s:
+            out[i, -len(s):] = s
+    return out
+
+
+def sequence_generator(dataset, features_fn, config, batch_size, shuffle=False, one_hot=True, shuffle_fn=None):
+    """Batches of the v2 (next-word) model, the reference's second ``data_generator``
+    (text_generation_model_v2.py:169-205): endless, one training sequence (image_id, roi index, previous words, next word)
+    of ``dataset.sequences`` after the other, yields ``([features [B, p, p, C], previous words [B, PADDING_SIZE] int32,
+    pre-padded], next word)`` where the next word is the reference's one-hot float64 ``[B, VOCABULARY_SIZE]`` row
+    (``one_hot=True``) or the class id ``[B]`` int32 (InjectModelV2.train_on_batch takes either).  ``features_fn(image_id)``
+    returns the RoI features of ALL RoIs of an image and is called once per run of sequences of the same image, as the
+    reference caches ``generate_features``.  ``shuffle`` re-shuffles the sequence order at every wrap-around
+    (``shuffle_fn`` defaults to ``np.random.shuffle``, the reference's)."""
+    order = np.arange(len(dataset.sequences))
+    shuffle_fn = shuffle_fn or np.random.shuffle
+    b, idx, prev_image, prev_feats = 0, -1, None, None
+    V, P = int(config.VOCABULARY_SIZE), int(config.PADDING_SIZE)
+    while True:
+        idx = (idx + 1) % len(order)
+        if shuffle and idx == 0:
+            shuffle_fn(order)
+        image_id, roi_id, prev_words, next_word = dataset.sequences[order[idx]][:4]
+        if prev_image != image_id:
+            prev_feats = features_fn(image_id)
+        prev_image = image_id
+        roi_features = prev_feats[roi_id]
+        if b == 0:
+            batch_f = np.zeros((batch_size,) + roi_features.shape, dtype=roi_features.dtype)
+            batch_w = np.zeros((batch_size, P), dtype=np.int32)
+            batch_y = np.zeros((batch_size, V)) if one_hot else np.zeros((batch_size,), np.int32)
+        batch_f[b] = roi_features
+        batch_w[b] = pad_sequences([prev_words], P)[0]
+        if one_hot:
+            batch_y[b, int(next_word)] = 1
+        else:
+            batch_y[b] = int(next_word)
+        b += 1
+        if b >= batch_size:
+            yield [batch_f, batch_w], batch_y
+            b = 0
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -180,6 +180,30 @@ exec(compile(ast.Module(body=[_extract(os.path.join(REF, "dense_img_cap_separate
 seqs = ns2["load_sequences"](FakeDataset())
 out["v2_sequences"] = np.array(["%d|%d|%s|%d" % (a, b, ",".join(str(int(t)) for t in c), int(d)) for a, b, c, d in seqs])
 
+# the v2 script's own data_generator (text_generation_model_v2.py:169-205) on those sequences: 18 sequences, batches of 4,
+# five batches = one wrap-around; keras' pad_sequences is the oracle's restatement of its defaults (pre-padding)
+from oracle import decoder as _dec_pad
+
+
+class FakeSeqDataset(FakeDataset):
+    sequences = seqs
+
+
+class Cfg3:
+    VOCABULARY_SIZE = V
+    PADDING_SIZE = 4                                           # shorter than the longest prefix (5): pre-truncation too
+
+
+ns2b = {"np": np, "generate_features": lambda dataset, image_id, model: feats_by_image[image_id],
+        "pad_sequences": lambda sequences, maxlen: _dec_pad.pad_sequences_pre(sequences, maxlen)}
+exec(compile(ast.Module(body=[_extract(os.path.join(REF, "dense_img_cap_separate_models", "text_generation_model_v2.py"), "data_generator")],
+                        type_ignores=[]), "data_generator_v2", "exec"), ns2b)
+gen2 = ns2b["data_generator"](FakeSeqDataset(), None, Cfg3, 4, shuffle=False)
+batches2 = [next(gen2) for _ in range(5)]
+out["v2gen_features"] = np.stack([b[0][0] for b in batches2])
+out["v2gen_words"] = np.stack([b[0][1] for b in batches2])
+out["v2gen_next"] = np.stack([b[1] for b in batches2])
+
 # ---- beam search control flow -----------------------------------------------------------------------
 # gen_captions ("image captioning/test.py":23-64) is plain Python around model.predict: run it with a stand-in model
 # whose predict() is the oracle's v1 word model (float64 copy of the fp32 probabilities, so that the score sums are

@@ -164,3 +164,46 @@ def test_weight_files_are_told_apart_by_content_not_by_name(tmp_path):
         f.write(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
     with pytest.raises(ImportError):                        # HDF5 by content: needs h5py, which this image lacks
         data.read_weight_file(hdf)
+
+
+def test_v2_sequence_generator_equals_the_reference():
+    """data.sequence_generator against the v2 script's own data_generator (text_generation_model_v2.py:169-205), run on
+    the same fake dataset by tests/golden/gen_golden_reference_numpy.py: 18 sequences in batches of 4 (one wrap-around),
+    PADDING_SIZE 4 < longest prefix (pre-truncation), features fetched once per run of sequences of an image."""
+    caps = {7: G["gen_caps_7"], 9: G["gen_caps_9"]}
+    feats = {7: G["gen_feats_7"], 9: G["gen_feats_9"]}
+
+    class DS:
+        image_ids = [7, 9]
+
+        def load_captions_and_rois(self, image_id):
+            return None, caps[image_id]
+    ds = DS()
+    ds.sequences = data.load_sequences(ds)
+    assert len(ds.sequences) == 18
+
+    class Cfg:
+        VOCABULARY_SIZE = G["v2gen_next"].shape[-1]
+        PADDING_SIZE = G["v2gen_words"].shape[-1]
+    calls = []
+
+    def fetch(image_id):
+        calls.append(image_id)
+        return feats[image_id]
+    gen = data.sequence_generator(ds, fetch, Cfg, 4)
+    ids = data.sequence_generator(ds, lambda i: feats[i], Cfg, 4, one_hot=False)
+    for b in range(5):
+        (f, w), y = next(gen)
+        assert np.array_equal(f, G["v2gen_features"][b]) and f.dtype == G["v2gen_features"].dtype
+        assert np.array_equal(w, G["v2gen_words"][b]) and w.dtype == G["v2gen_words"].dtype
+        assert np.array_equal(y, G["v2gen_next"][b]) and y.dtype == G["v2gen_next"].dtype
+        yi = next(ids)[1]
+        assert yi.dtype == np.int32 and np.array_equal(yi, y.argmax(-1))
+    assert calls == [7, 9, 7]                                # 12 sequences of image 7, 6 of image 9, then the wrap-around
+    # keras pad_sequences defaults: pre-padding, pre-truncation
+    assert data.pad_sequences([[0], [3, 7], [1, 2, 3, 4, 5, 6]], 4).tolist() == [[0, 0, 0, 0], [0, 0, 3, 7], [3, 4, 5, 6]]
+    # shuffling happens at every wrap-around, with the reference's np.random.shuffle by default
+    order = []
+    sh = data.sequence_generator(ds, lambda i: feats[i], Cfg, 18, shuffle=True, shuffle_fn=lambda a: (order.append(1), a.__setitem__(slice(None), a[::-1].copy())))
+    (f1, w1), y1 = next(sh)
+    assert len(order) == 1 and np.array_equal(y1[0], G["v2gen_next"].reshape(-1, y1.shape[-1])[17])
