@@ -104,6 +104,35 @@ def decode_caption(ids, id_to_word, stop=None):
     return " ".join(words)
 
 
+def generate_predictions(model, dataset, features_fn, config, id_to_word, separator=" <end>", cache_path=None, progress=None):
+    """The evaluation loop around the path (evaluate_models/eval_text_generation_model.py:129-153): for every image of
+    ``dataset`` the RoI features (``features_fn(image_id)`` -- ROIAlign of the image's RoIs), ``model.predict(features,
+    batch_size=config.BATCH_SIZE)``, each caption decoded to words and cut at the first ``separator``, paired with the
+    lower-cased ground-truth phrase: ``[{'p': predicted, 'r': real}, ...]``.  ``predict`` may return token ids [N, P] or
+    per-word distributions [N, P, V] (arg-max taken, as decode_word does).  ``cache_path``: the reference's pickle cache
+    (protocol 2) -- read when it exists, written otherwise.  ``progress`` wraps the image loop (tqdm in the reference)."""
+    import os
+    import pickle
+    if cache_path and os.path.exists(cache_path):
+        with open(cache_path, "rb") as f:
+            return pickle.load(f)
+    predictions = []
+    ids = dataset.image_ids
+    for image_id in (progress(ids) if progress else ids):
+        features = features_fn(image_id)
+        _, captions = dataset.load_original_captions_and_rois(image_id)
+        result = np.asarray(model.predict(features, batch_size=config.BATCH_SIZE))
+        if result.ndim == 3:
+            result = result.argmax(-1)
+        for i in range(result.shape[0]):
+            text = "".join(id_to_word[int(t)] + " " for t in result[i])        # decode_caption: every word followed by ' '
+            predictions.append({"p": text.split(separator, 1)[0], "r": captions[i][0].lower()})
+    if cache_path:
+        with open(cache_path, "wb") as f:
+            pickle.dump(predictions, f, protocol=2)
+    return predictions
+
+
 def read_region_descriptions(data_file, image_ids=None):
     """Visual Genome region_descriptions.json -> {image_id: [(roi [y1,x1,y2,x2] px, phrase), ...]}
     (text_generation_model.py:57-80)."""

@@ -207,3 +207,35 @@ def test_v2_sequence_generator_equals_the_reference():
     sh = data.sequence_generator(ds, lambda i: feats[i], Cfg, 18, shuffle=True, shuffle_fn=lambda a: (order.append(1), a.__setitem__(slice(None), a[::-1].copy())))
     (f1, w1), y1 = next(sh)
     assert len(order) == 1 and np.array_equal(y1[0], G["v2gen_next"].reshape(-1, y1.shape[-1])[17])
+
+
+def test_generate_predictions_is_the_reference_evaluation_loop(tmp_path):
+    """data.generate_predictions (evaluate_models/eval_text_generation_model.py:129-153) with a stand-in model: captions
+    decoded word by word, cut at ' <end>', paired with the lower-cased ground truth; pickle cache read back."""
+    id_to_word = {0: "<pad>", 1: "<start>", 2: "<end>", 3: "a", 4: "red", 5: "dog"}
+
+    class DS:
+        image_ids = [7, 9]
+
+        def load_original_captions_and_rois(self, image_id):
+            return None, {7: [["A Red Dog"], ["Dog"]], 9: [["a DOG"]]}[image_id]
+
+    class Model:
+        calls = []
+
+        def predict(self, features, batch_size=None):
+            self.calls.append((features.shape[0], batch_size))
+            ids = {2: [[3, 4, 5, 2, 0], [5, 2, 2, 0, 0]], 1: [[3, 5, 4, 3, 5]]}[features.shape[0]]
+            ids = np.array(ids)
+            return np.eye(6)[ids] if features.shape[0] == 1 else ids          # distributions [N,P,V] or ids [N,P]
+
+    class Cfg:
+        BATCH_SIZE = 4
+    feats = {7: np.zeros((2, 7, 7, 4), np.float32), 9: np.zeros((1, 7, 7, 4), np.float32)}
+    cache = str(tmp_path / "m_predictions.pickle")
+    m = Model()
+    got = data.generate_predictions(m, DS(), lambda i: feats[i], Cfg, id_to_word, cache_path=cache)
+    assert got == [{"p": "a red dog", "r": "a red dog"}, {"p": "dog", "r": "dog"}, {"p": "a dog red a dog ", "r": "a dog"}]
+    assert m.calls == [(2, 4), (1, 4)]
+    again = data.generate_predictions(None, None, None, None, None, cache_path=cache)      # served from the cache
+    assert again == got
