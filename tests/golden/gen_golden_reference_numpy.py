@@ -19,8 +19,9 @@ and records their outputs on seeded inputs:
                                                            -> pins oracle.pyramid_roi_align_literal / proposal_layer
   * dense_img_cap_separate_models/preprocess.py: load_corpus, encode_caption (nltk stubbed with the product's
     regular-expression tokenizer: the token FILTERING is what is pinned), and, extracted with ast from
-    text_generation_model.py / text_generation_model_v2.py, data_generator (:330-372) and load_sequences
-    (:128-137) run on a small fake dataset                  -> pins image_captioning_b200/data.py
+    text_generation_model.py / text_generation_model_v2.py, data_generator (:330-372), load_sequences
+    (:128-137) and the v2 script's own data_generator (:169-205) run on a small fake dataset
+                                                           -> pins image_captioning_b200/data.py
 
 Scores are made distinct: numpy's default argsort is not stable, so tie order is not a property of the
 reference.  Run from the repo root (only where /root/reference exists):
